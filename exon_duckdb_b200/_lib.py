@@ -1,0 +1,152 @@
+"""ctypes binding of libexon_b200.so (C ABI: include/exon_b200.h).
+
+The CUDA library IS the product: if it is missing or cannot be loaded this
+module raises -- there is no Python or CPU fallback for any operation.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libexon_b200.so")
+
+# flags / enums (mirror include/exon_b200.h)
+F_LINES, F_SEQ, F_QUAL = 1, 2, 4
+P_MEAN_QUALITY, P_GC_CONTENT, P_SEQ_LEN, P_QUAL_LEN = 0, 1, 2, 3
+OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "=": 4, "==": 4, "!=": 5, "<>": 5}
+MAP_REVERSE_COMPLEMENT, MAP_COMPLEMENT = 0, 1
+GEN_FASTA, GEN_ILLUMINA, GEN_ONT = 1, 2, 4
+ERR_CUDA, ERR_ARG, ERR_FORMAT, ERR_CAPACITY, ERR_IO, ERR_INVALID_CHAR = -1, -2, -3, -4, -5, -6
+NO_POS = 0xFFFFFFFFFFFFFFFF
+
+
+class ScanResult(C.Structure):
+    _fields_ = [
+        ("total_lines", C.c_uint64),
+        ("open_line_start", C.c_int64),
+        ("err_pos", C.c_uint64),
+        ("overflow", C.c_uint32),
+        ("pad", C.c_uint32),
+        ("n_records", C.c_uint64),
+        ("seq_bytes", C.c_uint64),
+        ("gc_total", C.c_uint64),
+        ("tail_s", C.c_int64),
+        ("tail_g", C.c_int64),
+        ("tail_hdr", C.c_uint64),
+    ]
+
+
+class Predicate(C.Structure):
+    _fields_ = [("field", C.c_int32), ("op", C.c_int32), ("value", C.c_double)]
+
+
+class GenParams(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("seed", C.c_uint64),
+        ("n_records", C.c_int64),
+        ("first_record", C.c_int64),
+        ("len_min", C.c_int32),
+        ("len_max", C.c_int32),
+        ("wrap", C.c_int32),
+        ("crlf", C.c_int32),
+    ]
+
+
+class ReaderResult(C.Structure):
+    _fields_ = [("error", C.c_void_p)]
+
+
+class ReplacementScanResult(C.Structure):
+    _fields_ = [("file_type", C.c_void_p)]
+
+
+class ExonError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("exon_b200 error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+# every symbol include/exon_b200.h declares: (restype, argtypes)
+_vp, _i64, _u64, _i32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int
+SIGNATURES = {
+    "exb_last_error": (C.c_char_p, []),
+    "exb_version": (C.c_char_p, []),
+    "exb_device_available": (_i32, []),
+    "new_reader": (ReaderResult, [_vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "replacement_scan": (ReplacementScanResult, [C.c_char_p]),
+    "exb_free_string": (None, [_vp]),
+    "exb_scan_workspace_bytes": (_i64, [_i64]),
+    "exb_fastq_scan": (_i32, [_vp, _i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "exb_scan_result_fetch": (_i32, [_vp, C.POINTER(ScanResult), _vp]),
+    "exb_fastq_filter": (_i32, [_vp, _vp, _vp, _vp, _i64, C.POINTER(Predicate), _i32, _vp, _vp, _vp]),
+    "exb_fastq_fields": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "exb_exclusive_scan_u32": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp]),
+    "exb_select_rows": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "exb_fastq_gather": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "exb_fasta_scan": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "exb_fasta_headers": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "exb_gather_ranges": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "exb_gc_from_prefix": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "exb_gc_from_counts": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "exb_gc_content": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "exb_seq_map": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "exb_quality_decode": (_i32, [_vp, _i64, _vp, _vp]),
+    "exb_gen_size": (_i64, [C.POINTER(GenParams)]),
+    "exb_gen_device": (_i32, [C.POINTER(GenParams), _vp, _i64, _vp]),
+    "exb_gen_host": (_i32, [C.POINTER(GenParams), _vp, _i64]),
+    "exb_fastq_count_host": (_i32, [_vp, _i64, C.POINTER(Predicate), _i32, _i64, _i32, C.POINTER(_i64), C.POINTER(ScanResult)]),
+    "exb_engine_create": (_i32, [_i32, _i64, C.POINTER(_vp)]),
+    "exb_engine_destroy": (None, [_vp]),
+    "exb_engine_fastq_count": (_i32, [_vp, _vp, _i64, C.POINTER(Predicate), _i32, C.POINTER(_i64), C.POINTER(ScanResult)]),
+    "exb_host_alloc": (_vp, [_i64]),
+    "exb_host_free": (None, [_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises ImportError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "exon_duckdb_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here = ABI drift between header and library
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise ExonError(rc, lib().exb_last_error().decode("utf-8", "replace"))
+
+
+def predicates(preds):
+    """[(field, op, value)] with field one of 'mean_quality', 'gc_content', 'seq_len', 'qual_len' -> ctypes array."""
+    names = {"mean_quality": P_MEAN_QUALITY, "gc_content": P_GC_CONTENT, "seq_len": P_SEQ_LEN, "qual_len": P_QUAL_LEN}
+    arr = (Predicate * max(1, len(preds)))()
+    for i, (f, op, v) in enumerate(preds):
+        arr[i].field = names[f] if isinstance(f, str) else int(f)
+        arr[i].op = OPS[op] if isinstance(op, str) else int(op)
+        arr[i].value = float(v)
+    return arr, len(preds)
+
+
+def gen_params(kind, n_records, seed=1, first_record=0, len_min=150, len_max=150, wrap=60, crlf=False):
+    p = GenParams()
+    p.kind = {"fasta": GEN_FASTA, "illumina": GEN_ILLUMINA, "ont": GEN_ONT}[kind] if isinstance(kind, str) else kind
+    p.seed = seed
+    p.n_records = n_records
+    p.first_record = first_record
+    p.len_min = len_min
+    p.len_max = len_max
+    p.wrap = wrap
+    p.crlf = 1 if crlf else 0
+    return p

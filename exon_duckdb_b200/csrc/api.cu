@@ -1,0 +1,353 @@
+// api.cu -- the device layer of the C ABI (include/exon_b200.h): argument checks,
+// workspace carving, kernel launches, synthetic-input generators.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "exon_b200_internal.h"
+#include "gen_common.h"
+
+namespace exb {
+// record_ops.cu
+cudaError_t exclusive_scan_launch_u32(const uint32_t*, int64_t, int64_t*, TileSlot*, unsigned long long*, cudaStream_t);
+cudaError_t exclusive_scan_launch_u8(const uint8_t*, int64_t, int64_t*, TileSlot*, unsigned long long*, cudaStream_t);
+int64_t scan_tiles(int64_t n);
+cudaError_t select_rows_launch(const uint8_t*, const int64_t*, int64_t, int64_t*, cudaStream_t);
+cudaError_t fastq_fields_launch(const uint8_t*, int64_t, int64_t, const void*, bool, const int64_t*, int64_t, uint32_t*, uint8_t*,
+                                int64_t*, cudaStream_t);
+cudaError_t fastq_gather_launch(const uint8_t*, int64_t, int64_t, const void*, bool, const int64_t*, int64_t, int, const uint32_t*,
+                                const int64_t*, uint8_t*, cudaStream_t);
+cudaError_t gather_ranges_launch(const uint8_t*, const int64_t*, const uint32_t*, const int64_t*, int64_t, uint8_t*, cudaStream_t);
+cudaError_t fastq_filter_launch(const uint32_t*, const uint32_t*, const uint32_t*, const int32_t*, int64_t, const exb_predicate*, int,
+                                uint8_t*, int64_t*, cudaStream_t);
+cudaError_t fasta_headers_launch(const uint8_t*, const int64_t*, const int64_t*, int64_t, int64_t, uint32_t*, int64_t*, uint8_t*,
+                                 unsigned long long*, cudaStream_t);
+cudaError_t gc_from_prefix_launch(const int64_t*, const int64_t*, int64_t, float*, cudaStream_t);
+cudaError_t gc_from_counts_launch(const uint32_t*, const uint32_t*, int64_t, float*, cudaStream_t);
+cudaError_t gc_content_launch(const int64_t*, const uint8_t*, int64_t, float*, cudaStream_t);
+cudaError_t seq_map_launch(const uint8_t*, int64_t, int, uint8_t*, unsigned long long*, cudaStream_t);
+cudaError_t quality_decode_launch(const uint8_t*, int64_t, int32_t*, cudaStream_t);
+
+static thread_local char g_err[512] = "";
+int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return set_err(EXB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// workspace: [0,128) ScanResult | [128,136) ticket | [256, ...) TileSlot[n_tiles]
+constexpr int64_t WS_HEADER = 256;
+static_assert(sizeof(ScanResult) <= 128, "ScanResult must fit the header");
+static_assert(sizeof(ScanResult) == sizeof(exb_scan_result), "ABI mirror");
+
+int64_t tiles_for(int64_t begin, int64_t n, int is_final) {
+    int64_t origin = begin & ~(int64_t)15;
+    // final chunk: +1 byte of room for the virtual terminator at n
+    int64_t t = (n + (is_final ? 1 : 0) - origin + TILE_BYTES - 1) / TILE_BYTES;
+    return t > 0 ? t : 1;
+}
+
+struct Workspace {
+    ScanResult* result;
+    unsigned long long* ticket;
+    TileSlot* slots;
+};
+int carve(void* ws, int64_t ws_bytes, int64_t n_tiles, cudaStream_t st, Workspace* out) {
+    int64_t need = WS_HEADER + n_tiles * (int64_t)sizeof(TileSlot);
+    if (!ws || ws_bytes < need) return set_err(EXB_ERR_ARG, "workspace too small: need %lld bytes, have %lld", (long long)need, (long long)ws_bytes);
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+    out->result = reinterpret_cast<ScanResult*>(ws);
+    out->ticket = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 128);
+    out->slots = reinterpret_cast<TileSlot*>(reinterpret_cast<uint8_t*>(ws) + WS_HEADER);
+    return 0;
+}
+
+__global__ void init_result_kernel(ScanResult* r) { r->err_pos = ~0ull; }
+
+// ---------------------------------------------------------------- generators
+__global__ void gen_sizes_kernel(exb_gen_params p, uint32_t* sizes) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_records; i += (int64_t)gridDim.x * blockDim.x)
+        sizes[i] = (uint32_t)exb_gen_record(&p, (uint64_t)(p.first_record + i), nullptr);
+}
+__global__ void gen_fill_kernel(exb_gen_params p, const int64_t* off, uint8_t* out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_records; i += (int64_t)gridDim.x * blockDim.x)
+        exb_gen_record(&p, (uint64_t)(p.first_record + i), out + off[i]);
+}
+}  // namespace exb
+
+using namespace exb;
+
+extern "C" {
+
+const char* exb_last_error(void) { return g_err; }
+const char* exb_version(void) { return "exon-b200 0.1.0 (sm_100a)"; }
+
+int exb_device_available(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n > 0;
+}
+
+int64_t exb_scan_workspace_bytes(int64_t n) {
+    if (n < 0) n = 0;
+    return WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);
+}
+
+int exb_fastq_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, uint64_t max_lines,
+                   int flags, void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len, uint32_t* d_gc,
+                   uint32_t* d_qual_len, int32_t* d_qsum, int64_t rec_cap, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_buf || begin < 0 || n < begin) return set_err(EXB_ERR_ARG, "exb_fastq_scan: bad buffer range");
+    if (((uintptr_t)d_buf & 15) != 0) return set_err(EXB_ERR_ARG, "exb_fastq_scan: d_buf must be 16-byte aligned");
+    if ((flags & EXB_F_LINES) && !d_line_end) return set_err(EXB_ERR_ARG, "exb_fastq_scan: EXB_F_LINES without d_line_end");
+    if ((flags & EXB_F_LINES) && !wide_offsets && n >= (int64_t)0xFFFFFFFFll)
+        return set_err(EXB_ERR_ARG, "exb_fastq_scan: 32-bit line offsets need n < 4 GiB");
+    if ((flags & EXB_F_SEQ) && (!d_seq_len || !d_gc)) return set_err(EXB_ERR_ARG, "exb_fastq_scan: EXB_F_SEQ without outputs");
+    if ((flags & EXB_F_QUAL) && (!d_qual_len || !d_qsum)) return set_err(EXB_ERR_ARG, "exb_fastq_scan: EXB_F_QUAL without outputs");
+    FastqScanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.buf = reinterpret_cast<const uint8_t*>(d_buf);
+    a.begin = begin;
+    a.n = n;
+    a.prev = reinterpret_cast<const ScanResult*>(d_prev_workspace);
+    a.is_final = is_final ? 1 : 0;
+    a.max_lines = max_lines;
+    a.n_tiles = tiles_for(begin, n, a.is_final);
+    if (d_prev_workspace == d_workspace) return set_err(EXB_ERR_ARG, "exb_fastq_scan: d_prev_workspace must differ from d_workspace");
+    Workspace w;
+    int rc = carve(d_workspace, workspace_bytes, a.n_tiles, st, &w);
+    if (rc) return rc;
+    init_result_kernel<<<1, 1, 0, st>>>(w.result);
+    a.slots = w.slots;
+    a.ticket = w.ticket;
+    a.result = w.result;
+    a.line_end = d_line_end;
+    a.line_cap = line_cap;
+    a.seq_len = d_seq_len;
+    a.gc = d_gc;
+    a.qual_len = d_qual_len;
+    a.qsum = d_qsum;
+    a.rec_cap = rec_cap;
+    cudaError_t e = fastq_scan_launch(a, flags, wide_offsets != 0, st);
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_scan launch");
+    return 0;
+}
+
+int exb_scan_result_fetch(const void* d_workspace, exb_scan_result* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(out, d_workspace, sizeof(exb_scan_result), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(result)");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    return 0;
+}
+
+int exb_fastq_filter(const uint32_t* d_seq_len, const uint32_t* d_gc, const uint32_t* d_qual_len, const int32_t* d_qsum,
+                     int64_t n_records, const exb_predicate* preds, int n_preds, uint8_t* d_pass, int64_t* d_agg, void* stream) {
+    if (n_preds < 0 || n_preds > EXB_MAX_PREDICATES) return set_err(EXB_ERR_ARG, "exb_fastq_filter: at most %d predicates", EXB_MAX_PREDICATES);
+    for (int i = 0; i < n_preds; i++) {
+        int f = preds[i].field;
+        if (f < 0 || f > 3 || preds[i].op < 0 || preds[i].op > 5) return set_err(EXB_ERR_ARG, "exb_fastq_filter: bad predicate %d", i);
+        if (f == EXB_P_MEAN_QUALITY && (!d_qual_len || !d_qsum)) return set_err(EXB_ERR_ARG, "mean_quality predicate needs qual_len/qsum");
+        if (f == EXB_P_GC_CONTENT && (!d_seq_len || !d_gc)) return set_err(EXB_ERR_ARG, "gc_content predicate needs seq_len/gc");
+        if (f == EXB_P_SEQ_LEN && !d_seq_len) return set_err(EXB_ERR_ARG, "length(sequence) predicate needs seq_len");
+        if (f == EXB_P_QUAL_LEN && !d_qual_len) return set_err(EXB_ERR_ARG, "length(quality_scores) predicate needs qual_len");
+    }
+    if (!d_agg) return set_err(EXB_ERR_ARG, "exb_fastq_filter: d_agg is required");
+    cudaError_t e = fastq_filter_launch(d_seq_len, d_gc, d_qual_len, d_qsum, n_records, preds, n_preds, d_pass, d_agg, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_filter launch");
+    return 0;
+}
+
+int exb_fastq_fields(const void* d_buf, int64_t begin, int64_t n, const void* d_line_end, int wide_offsets, const int64_t* d_sel,
+                     int64_t n_rows, uint32_t* d_lens, uint8_t* d_desc_valid, int64_t* d_starts, void* stream) {
+    cudaError_t e = fastq_fields_launch(reinterpret_cast<const uint8_t*>(d_buf), begin, n, d_line_end, wide_offsets != 0, d_sel, n_rows,
+                                        d_lens, d_desc_valid, d_starts, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_fields launch");
+    return 0;
+}
+
+int exb_exclusive_scan_u32(const uint32_t* d_in, int64_t n, int64_t* d_out, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace w;
+    int rc = carve(d_workspace, workspace_bytes, scan_tiles(n), st, &w);
+    if (rc) return rc;
+    cudaError_t e = exclusive_scan_launch_u32(d_in, n, d_out, w.slots, w.ticket, st);
+    if (e != cudaSuccess) return cuda_fail(e, "exclusive_scan launch");
+    return 0;
+}
+
+int exb_select_rows(const uint8_t* d_pass, int64_t n, int64_t* d_offsets, int64_t* d_sel, void* d_workspace, int64_t workspace_bytes,
+                    void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace w;
+    int rc = carve(d_workspace, workspace_bytes, scan_tiles(n), st, &w);
+    if (rc) return rc;
+    cudaError_t e = exclusive_scan_launch_u8(d_pass, n, d_offsets, w.slots, w.ticket, st);
+    if (e != cudaSuccess) return cuda_fail(e, "exclusive_scan launch");
+    e = select_rows_launch(d_pass, d_offsets, n, d_sel, st);
+    if (e != cudaSuccess) return cuda_fail(e, "select_rows launch");
+    return 0;
+}
+
+int exb_fastq_gather(const void* d_buf, int64_t begin, int64_t n, const void* d_line_end, int wide_offsets, const int64_t* d_sel,
+                     int64_t n_rows, int col, const uint32_t* d_lens, const int64_t* d_off, uint8_t* d_out, void* stream) {
+    if (col < 0 || col > 3) return set_err(EXB_ERR_ARG, "exb_fastq_gather: col must be 0..3");
+    cudaError_t e = fastq_gather_launch(reinterpret_cast<const uint8_t*>(d_buf), begin, n, d_line_end, wide_offsets != 0, d_sel, n_rows,
+                                        col, d_lens, d_off, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_gather launch");
+    return 0;
+}
+
+int exb_fasta_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, int64_t halo_n, const void* d_prev_workspace,
+                   int64_t* d_hdr_start, int64_t* d_hdr_end, int64_t* d_seq_off, int64_t* d_gc_prefix, int64_t rec_cap,
+                   uint8_t* d_seq_out, int64_t seq_cap, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_buf || begin < 0 || n < begin) return set_err(EXB_ERR_ARG, "exb_fasta_scan: bad buffer range");
+    if (((uintptr_t)d_buf & 15) != 0) return set_err(EXB_ERR_ARG, "exb_fasta_scan: d_buf must be 16-byte aligned");
+    if (d_seq_out && ((uintptr_t)d_seq_out & 15) != 0) return set_err(EXB_ERR_ARG, "exb_fasta_scan: d_seq_out must be 16-byte aligned");
+    if (!d_hdr_start || !d_hdr_end || !d_seq_off || !d_gc_prefix) return set_err(EXB_ERR_ARG, "exb_fasta_scan: per-record outputs are required");
+    FastaScanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.buf = reinterpret_cast<const uint8_t*>(d_buf);
+    a.begin = begin;
+    a.n = n;
+    a.prev = reinterpret_cast<const ScanResult*>(d_prev_workspace);
+    a.is_final = is_final ? 1 : 0;
+    a.halo_n = halo_n > n ? halo_n : n;
+    a.n_tiles = tiles_for(begin, n, a.is_final);
+    if (d_prev_workspace == d_workspace) return set_err(EXB_ERR_ARG, "exb_fasta_scan: d_prev_workspace must differ from d_workspace");
+    Workspace w;
+    int rc = carve(d_workspace, workspace_bytes, a.n_tiles, st, &w);
+    if (rc) return rc;
+    init_result_kernel<<<1, 1, 0, st>>>(w.result);
+    a.slots = w.slots;
+    a.ticket = w.ticket;
+    a.result = w.result;
+    a.hdr_start = d_hdr_start;
+    a.hdr_end = d_hdr_end;
+    a.seq_off = d_seq_off;
+    a.gc_prefix = d_gc_prefix;
+    a.rec_cap = rec_cap;
+    a.seq_out = d_seq_out;
+    a.seq_cap = seq_cap;
+    cudaError_t e = fasta_scan_launch(a, 0, st);
+    if (e != cudaSuccess) return cuda_fail(e, "fasta_scan launch");
+    return 0;
+}
+
+int exb_fasta_headers(const void* d_buf, int64_t n, const int64_t* d_hdr_start, const int64_t* d_hdr_end, int64_t n_rows,
+                      uint32_t* d_lens, int64_t* d_desc_start, uint8_t* d_desc_valid, uint64_t* d_err_pos, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_err_pos, 0xFF, 8, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    e = fasta_headers_launch(reinterpret_cast<const uint8_t*>(d_buf), d_hdr_start, d_hdr_end, n_rows, n, d_lens, d_desc_start,
+                             d_desc_valid, reinterpret_cast<unsigned long long*>(d_err_pos), st);
+    if (e != cudaSuccess) return cuda_fail(e, "fasta_headers launch");
+    return 0;
+}
+
+int exb_gather_ranges(const void* d_buf, const int64_t* d_start, const uint32_t* d_len, const int64_t* d_off, int64_t n_rows,
+                      uint8_t* d_out, void* stream) {
+    cudaError_t e = gather_ranges_launch(reinterpret_cast<const uint8_t*>(d_buf), d_start, d_len, d_off, n_rows, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gather_ranges launch");
+    return 0;
+}
+
+int exb_gc_from_prefix(const int64_t* d_seq_off, const int64_t* d_gc_prefix, int64_t n_rows, float* d_out, void* stream) {
+    cudaError_t e = gc_from_prefix_launch(d_seq_off, d_gc_prefix, n_rows, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gc_from_prefix launch");
+    return 0;
+}
+int exb_gc_from_counts(const uint32_t* d_seq_len, const uint32_t* d_gc, int64_t n_rows, float* d_out, void* stream) {
+    cudaError_t e = gc_from_counts_launch(d_seq_len, d_gc, n_rows, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gc_from_counts launch");
+    return 0;
+}
+int exb_gc_content(const int64_t* d_off, const uint8_t* d_data, int64_t n_rows, float* d_out, void* stream) {
+    cudaError_t e = gc_content_launch(d_off, d_data, n_rows, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gc_content launch");
+    return 0;
+}
+int exb_seq_map(const uint8_t* d_in, int64_t n_bytes, int mode, uint8_t* d_out, uint64_t* d_bad_pos, void* stream) {
+    if (mode != EXB_MAP_REVERSE_COMPLEMENT && mode != EXB_MAP_COMPLEMENT) return set_err(EXB_ERR_ARG, "exb_seq_map: bad mode");
+    cudaError_t e = seq_map_launch(d_in, n_bytes, mode, d_out, reinterpret_cast<unsigned long long*>(d_bad_pos), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "seq_map launch");
+    return 0;
+}
+int exb_quality_decode(const uint8_t* d_in, int64_t n_bytes, int32_t* d_out, void* stream) {
+    cudaError_t e = quality_decode_launch(d_in, n_bytes, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "quality_decode launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------- generators
+int64_t exb_gen_size(const exb_gen_params* p) {
+    int64_t tot = 0;
+    for (int64_t i = 0; i < p->n_records; i++) tot += exb_gen_record(p, (uint64_t)(p->first_record + i), nullptr);
+    return tot;
+}
+int exb_gen_host(const exb_gen_params* p, void* out, int64_t cap) {
+    uint8_t* o = reinterpret_cast<uint8_t*>(out);
+    int64_t at = 0;
+    for (int64_t i = 0; i < p->n_records; i++) {
+        int64_t sz = exb_gen_record(p, (uint64_t)(p->first_record + i), nullptr);
+        if (at + sz > cap) return set_err(EXB_ERR_CAPACITY, "exb_gen_host: buffer too small");
+        exb_gen_record(p, (uint64_t)(p->first_record + i), o + at);
+        at += sz;
+    }
+    return 0;
+}
+int exb_gen_device(const exb_gen_params* p, void* d_out, int64_t cap, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = p->n_records;
+    if (n == 0) return 0;
+    uint32_t* sizes = nullptr;
+    int64_t* off = nullptr;
+    void* ws = nullptr;
+    const int64_t ws_bytes = exb_scan_workspace_bytes(4 * n);
+    cudaError_t e = cudaMalloc(&sizes, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&off, (size_t)(n + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&ws, (size_t)ws_bytes);
+    int rc = 0;
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(gen scratch)");
+    if (!rc) {
+        int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
+        gen_sizes_kernel<<<blocks, 256, 0, st>>>(*p, sizes);
+        rc = exb_exclusive_scan_u32(sizes, n, off, ws, ws_bytes, st);
+        if (!rc) {
+            int64_t total = 0;
+            e = cudaMemcpyAsync(&total, off + n, 8, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = cuda_fail(e, "gen sizes");
+            else if (total > cap) rc = set_err(EXB_ERR_CAPACITY, "exb_gen_device: need %lld bytes, have %lld", (long long)total, (long long)cap);
+            else {
+                // few long records (genomes): one thread each is still the simplest correct mapping
+                int fblocks = (int)((n + 63) / 64 < 148 * 64 ? (n + 63) / 64 : 148 * 64);
+                gen_fill_kernel<<<fblocks, 64, 0, st>>>(*p, off, reinterpret_cast<uint8_t*>(d_out));
+                e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) rc = cuda_fail(e, "gen fill");
+            }
+        }
+    }
+    cudaFree(sizes);
+    cudaFree(off);
+    cudaFree(ws);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// exon_b200_internal.h -- kernel argument blocks shared between the .cu files.
+// Nothing in here crosses the C ABI (see include/exon_b200.h for that).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/exon_b200.h"
+
+namespace exb {
+
+struct TileSlot;
+
+// Device-resident scalar results of one scan launch.  Layout is mirrored by
+// exb_scan_result in include/exon_b200.h (copied back verbatim).
+struct ScanResult {
+    uint64_t total_lines;       // FASTQ: newlines seen (incl. the virtual one at EOF)
+    int64_t open_line_start;    // first byte after the last newline
+    unsigned long long err_pos; // smallest offset of a malformed line start; ~0 = none
+    uint32_t overflow;          // an output capacity was too small
+    uint32_t pad;
+    uint64_t n_records;         // FASTA: header lines seen
+    uint64_t seq_bytes;         // FASTA: sequence bytes kept (newlines / CR stripped)
+    uint64_t gc_total;          // FASTA: G/C among them
+    int64_t tail_s, tail_g;     // FASTQ: byte sum / G,C count of the open line (chunk chaining)
+    uint64_t tail_hdr;          // FASTA: the open line is a header line (chunk chaining)
+};
+
+struct FastqScanArgs {
+    const uint8_t* buf;
+    int64_t begin, n;           // parse bytes [begin, n)
+    const ScanResult* prev;     // null: `begin` starts line 0; else continue from that scan's final state
+    int is_final;               // 1: n is the end of the input (an unterminated last line gets a virtual '\n')
+    uint64_t max_lines;         // lines with index >= max_lines are ignored
+    int64_t n_tiles;
+    TileSlot* slots;            // n_tiles zeroed slots
+    unsigned long long* ticket; // zeroed
+    ScanResult* result;
+    void* line_end;             // OffT[line_cap]
+    int64_t line_cap;
+    uint32_t *seq_len, *gc, *qual_len;
+    int32_t* qsum;
+    int64_t rec_cap;
+};
+
+cudaError_t fastq_scan_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st);
+
+struct FastaScanArgs {
+    const uint8_t* buf;
+    int64_t begin, n;
+    const ScanResult* prev;
+    int is_final;
+    int64_t halo_n;             // bytes of buf that are readable (>= n): the CRLF test looks one byte ahead
+    int64_t n_tiles;
+    TileSlot* slots;
+    unsigned long long* ticket;
+    ScanResult* result;
+    // per record r (single writer = the thread that owns the '>' / the header's newline)
+    int64_t* hdr_start;         // offset of '>'
+    int64_t* hdr_end;           // offset of the header line's '\n' (or n at EOF)
+    int64_t* seq_off;           // rec_cap + 1: sequence bytes kept before record r
+    int64_t* gc_prefix;         // rec_cap + 1: G/C among them
+    int64_t rec_cap;
+    uint8_t* seq_out;           // compacted sequence column (may be null)
+    int64_t seq_cap;
+};
+
+cudaError_t fasta_scan_launch(const FastaScanArgs& a, int flags, cudaStream_t st);
+
+}  // namespace exb

@@ -1,0 +1,501 @@
+// record_ops.cu -- per-record kernels that consume the scan outputs:
+// predicate / aggregate evaluation, field extents, offset scans, gathers into
+// Arrow-style column buffers, and the sequence scalar functions.
+//
+// Reference semantics restated here:
+//   gc_content                 exon/src/exon/sequence_functions/module.cpp:131-158
+//   reverse_complement         module.cpp:30-69   (A->C T->G C->A G->T, no reversal)
+//   complement                 module.cpp:81-121
+//   quality_score_string_to_list   exon/src/exon/fastq_functions/module.cpp:32-50
+//   name/description split     noodles-fastq 0.8 read_record / noodles-fasta 0.27
+//                              Definition::from_str (not in the reference tree)
+#include "common.cuh"
+#include "exon_b200_internal.h"
+#include "x87div.h"
+
+namespace exb {
+
+// ================================================================= filter
+struct FilterArgs {
+    const uint32_t *seq_len, *gc, *qual_len;
+    const int32_t* qsum;
+    int64_t n;
+    exb_predicate preds[EXB_MAX_PREDICATES];
+    int n_preds;
+    uint8_t* pass;
+    long long* agg;
+};
+
+__device__ __forceinline__ float gc_fraction(uint32_t gc, uint32_t len) {
+    // (float)gc_count / (float)size with both operands C ints; '' -> 0 (module.cpp:142-156)
+    return len == 0 ? 0.0f : __fdiv_rn(__uint2float_rn(gc), __uint2float_rn(len));
+}
+
+__global__ void __launch_bounds__(256) fastq_filter_kernel(FilterArgs a) {
+    long long v[5] = {0, 0, 0, 0, 0};
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t sl = a.seq_len ? a.seq_len[r] : 0, g = a.gc ? a.gc[r] : 0;
+        const uint32_t ql = a.qual_len ? a.qual_len[r] : 0;
+        const int32_t qs = a.qsum ? a.qsum[r] : 0;
+        bool ok = true;
+        for (int i = 0; i < a.n_preds; i++) {
+            const exb_predicate p = a.preds[i];
+            bool c;
+            switch (p.field) {
+            case EXB_P_MEAN_QUALITY: c = exb_mean_cmp((int64_t)qs, ql, p.op, p.value); break;
+            case EXB_P_GC_CONTENT: c = exb_cmp((double)gc_fraction(g, sl), p.op, p.value); break;
+            case EXB_P_SEQ_LEN: c = exb_cmp((double)sl, p.op, p.value); break;
+            default: c = exb_cmp((double)ql, p.op, p.value); break;
+            }
+            ok = ok && c;
+        }
+        if (a.pass) a.pass[r] = ok ? 1 : 0;
+        if (ok) {
+            v[0] += 1;
+            v[1] += sl;
+            v[2] += g;
+            v[3] += qs;
+            v[4] += ql;
+        }
+    }
+    __shared__ long long s_acc[5];
+    if (threadIdx.x < 5) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        long long x = v[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if ((threadIdx.x & 31) == 0 && x != 0) atomicAdd((unsigned long long*)&s_acc[i], (unsigned long long)x);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && s_acc[threadIdx.x] != 0)
+        atomicAdd((unsigned long long*)&a.agg[threadIdx.x], (unsigned long long)s_acc[threadIdx.x]);
+}
+
+// ================================================================= exclusive scan (u32 / u8 -> i64)
+struct alignas(16) SumState {
+    int64_t sum;
+    int64_t pad;
+    __device__ static SumState combine(const SumState& p, const SumState& t) { return SumState{p.sum + t.sum, 0}; }
+};
+
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = BLOCK_THREADS * SCAN_ITEMS;
+
+template <typename T>
+__global__ void __launch_bounds__(BLOCK_THREADS) exclusive_scan_kernel(const T* __restrict__ in, int64_t n, int64_t* __restrict__ out,
+                                                                      TileSlot* slots, unsigned long long* ticket, int64_t n_tiles) {
+    __shared__ int64_t s_tile_id;
+    __shared__ uint64_t s_warp[WARPS];
+    __shared__ int64_t s_excl;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_tile_id = (int64_t)atomicAdd(ticket, 1ull);
+    __syncthreads();
+    const int64_t tile = s_tile_id;
+    const int64_t base = tile * SCAN_TILE + (int64_t)t * SCAN_ITEMS;
+    uint32_t x[SCAN_ITEMS];
+    uint64_t loc = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        x[i] = (base + i < n) ? (uint32_t)in[base + i] : 0u;
+        loc += x[i];
+    }
+    uint64_t incl = warp_incl_scan_u64(loc);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint64_t woff = 0, tot = 0;
+    for (int w = 0; w < WARPS; w++) {
+        if (w < warp) woff += s_warp[w];
+        tot += s_warp[w];
+    }
+    if (t == 0) {
+        SumState excl = lookback<SumState>(slots, tile, SumState{(int64_t)tot, 0}, SumState{0, 0});
+        s_excl = excl.sum;
+        if (tile == n_tiles - 1) out[n] = excl.sum + (int64_t)tot;
+    }
+    __syncthreads();
+    int64_t run = s_excl + (int64_t)(woff + incl - loc);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < n) out[base + i] = run;
+        run += x[i];
+    }
+}
+
+cudaError_t exclusive_scan_launch_u32(const uint32_t* in, int64_t n, int64_t* out, TileSlot* slots, unsigned long long* ticket,
+                                      cudaStream_t st) {
+    int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (n_tiles == 0) n_tiles = 1;
+    exclusive_scan_kernel<uint32_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles);
+    return cudaGetLastError();
+}
+cudaError_t exclusive_scan_launch_u8(const uint8_t* in, int64_t n, int64_t* out, TileSlot* slots, unsigned long long* ticket,
+                                     cudaStream_t st) {
+    int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (n_tiles == 0) n_tiles = 1;
+    exclusive_scan_kernel<uint8_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles);
+    return cudaGetLastError();
+}
+int64_t scan_tiles(int64_t n) {
+    int64_t t = (n + SCAN_TILE - 1) / SCAN_TILE;
+    return t ? t : 1;
+}
+
+__global__ void select_rows_kernel(const uint8_t* __restrict__ pass, const int64_t* __restrict__ off, int64_t n,
+                                   int64_t* __restrict__ sel) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        if (pass[r]) sel[off[r]] = r;
+}
+cudaError_t select_rows_launch(const uint8_t* pass, const int64_t* off, int64_t n, int64_t* sel, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    select_rows_kernel<<<blocks, 256, 0, st>>>(pass, off, n, sel);
+    return cudaGetLastError();
+}
+
+// ================================================================= FASTQ field extents
+template <typename OffT>
+struct FqLines {
+    const uint8_t* buf;
+    const OffT* line_end;
+    int64_t begin, n;
+    // start of line g and its end with a trailing CR removed
+    __device__ __forceinline__ int64_t start(int64_t g) const { return g == 0 ? begin : (int64_t)line_end[g - 1] + 1; }
+    __device__ __forceinline__ int64_t end(int64_t g, int64_t s) const {
+        int64_t e = (int64_t)line_end[g];
+        // e == n is the virtual terminator of an unterminated last line: it strips no CR
+        if (e > s && e < n && buf[e - 1] == '\r') e--;
+        return e;
+    }
+};
+
+template <typename OffT>
+__global__ void __launch_bounds__(256) fastq_fields_kernel(FqLines<OffT> L, const int64_t* __restrict__ sel, int64_t n_rows,
+                                                           uint32_t* __restrict__ lens, uint8_t* __restrict__ desc_valid,
+                                                           int64_t* __restrict__ starts) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = sel ? sel[i] : i;
+        const int64_t g = 4 * r;
+        int64_t s0 = L.start(g), e0 = L.end(g, s0);
+        int64_t hs = s0 + 1;  // skip '@'
+        int64_t sp = hs;
+        while (sp < e0 && L.buf[sp] != ' ') sp++;  // first SPACE splits name / description
+        uint32_t name_len = (uint32_t)(sp - hs);
+        uint32_t desc_len = sp < e0 ? (uint32_t)(e0 - sp - 1) : 0u;
+        int64_t s1 = (int64_t)L.line_end[g] + 1, e1 = L.end(g + 1, s1);
+        int64_t s3 = (int64_t)L.line_end[g + 2] + 1, e3 = L.end(g + 3, s3);
+        lens[0 * n_rows + i] = name_len;
+        lens[1 * n_rows + i] = desc_len;
+        lens[2 * n_rows + i] = (uint32_t)(e1 - s1);
+        lens[3 * n_rows + i] = (uint32_t)(e3 - s3);
+        desc_valid[i] = desc_len > 0;  // exon's builder maps an empty description to NULL
+        if (starts) {
+            starts[0 * n_rows + i] = hs;
+            starts[1 * n_rows + i] = sp < e0 ? sp + 1 : e0;
+            starts[2 * n_rows + i] = s1;
+            starts[3 * n_rows + i] = s3;
+        }
+    }
+}
+
+// ================================================================= gathers
+// One warp per row: copies len bytes from src to dst.  dst-aligned 4-byte words
+// in the body (two aligned source loads + funnel shift), bytes at the edges.
+__device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t len, int lane) {
+    if (len <= 0) return;
+    int head = (int)((4 - ((uintptr_t)dst & 3)) & 3);
+    if (head > len) head = (int)len;
+    if (lane < head) dst[lane] = src[lane];
+    dst += head;
+    src += head;
+    len -= head;
+    const int64_t nwords = len >> 2;
+    const int sh = (int)((uintptr_t)src & 3);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(src - sh);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst);
+    if (sh == 0) {
+        for (int64_t w = lane; w < nwords; w += 32) dw[w] = sw[w];
+    } else {
+        for (int64_t w = lane; w < nwords; w += 32) dw[w] = __funnelshift_r(sw[w], sw[w + 1], sh * 8);
+    }
+    const int tail = (int)(len & 3);
+    if (lane < tail) dst[nwords * 4 + lane] = src[nwords * 4 + lane];
+}
+
+template <typename OffT>
+__global__ void __launch_bounds__(256) fastq_gather_kernel(FqLines<OffT> L, const int64_t* __restrict__ sel, int64_t n_rows, int col,
+                                                           const uint32_t* __restrict__ lens, const int64_t* __restrict__ off,
+                                                           uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = wid; i < n_rows; i += nw) {
+        const int64_t r = sel ? sel[i] : i;
+        const int64_t g = 4 * r;
+        int64_t src;
+        if (col == 0) src = L.start(g) + 1;
+        else if (col == 1) src = L.start(g) + 1 + lens[i] + 1;  // lens[0][i] = name length
+        else if (col == 2) src = (int64_t)L.line_end[g] + 1;
+        else src = (int64_t)L.line_end[g + 2] + 1;
+        warp_copy(out + off[i], L.buf + src, lens[(int64_t)col * n_rows + i], lane);
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_ranges_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ start,
+                                                            const uint32_t* __restrict__ len, const int64_t* __restrict__ off,
+                                                            int64_t n_rows, uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = wid; i < n_rows; i += nw) warp_copy(out + off[i], buf + start[i], len[i], lane);
+}
+
+static int row_blocks(int64_t n_rows, int rows_per_block) {
+    int64_t b = (n_rows + rows_per_block - 1) / rows_per_block;
+    const int64_t cap = 148 * 32;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <typename OffT>
+static cudaError_t fields_launch_t(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, const int64_t* sel, int64_t n_rows,
+                                   uint32_t* lens, uint8_t* desc_valid, int64_t* starts, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    FqLines<OffT> L{buf, reinterpret_cast<const OffT*>(line_end), begin, n};
+    fastq_fields_kernel<OffT><<<row_blocks(n_rows, 256), 256, 0, st>>>(L, sel, n_rows, lens, desc_valid, starts);
+    return cudaGetLastError();
+}
+cudaError_t fastq_fields_launch(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, bool wide, const int64_t* sel,
+                                int64_t n_rows, uint32_t* lens, uint8_t* desc_valid, int64_t* starts, cudaStream_t st) {
+    return wide ? fields_launch_t<uint64_t>(buf, begin, n, line_end, sel, n_rows, lens, desc_valid, starts, st)
+                : fields_launch_t<uint32_t>(buf, begin, n, line_end, sel, n_rows, lens, desc_valid, starts, st);
+}
+template <typename OffT>
+static cudaError_t gather_launch_t(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, const int64_t* sel, int64_t n_rows,
+                                   int col, const uint32_t* lens, const int64_t* off, uint8_t* out, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    FqLines<OffT> L{buf, reinterpret_cast<const OffT*>(line_end), begin, n};
+    fastq_gather_kernel<OffT><<<row_blocks(n_rows, 8), 256, 0, st>>>(L, sel, n_rows, col, lens, off, out);
+    return cudaGetLastError();
+}
+cudaError_t fastq_gather_launch(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, bool wide, const int64_t* sel,
+                                int64_t n_rows, int col, const uint32_t* lens, const int64_t* off, uint8_t* out, cudaStream_t st) {
+    return wide ? gather_launch_t<uint64_t>(buf, begin, n, line_end, sel, n_rows, col, lens, off, out, st)
+                : gather_launch_t<uint32_t>(buf, begin, n, line_end, sel, n_rows, col, lens, off, out, st);
+}
+cudaError_t gather_ranges_launch(const uint8_t* buf, const int64_t* start, const uint32_t* len, const int64_t* off, int64_t n_rows,
+                                 uint8_t* out, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    gather_ranges_kernel<<<row_blocks(n_rows, 8), 256, 0, st>>>(buf, start, len, off, n_rows, out);
+    return cudaGetLastError();
+}
+
+cudaError_t fastq_filter_launch(const uint32_t* seq_len, const uint32_t* gc, const uint32_t* qual_len, const int32_t* qsum, int64_t n,
+                                const exb_predicate* preds, int n_preds, uint8_t* pass, int64_t* agg, cudaStream_t st) {
+    FilterArgs a;
+    a.seq_len = seq_len;
+    a.gc = gc;
+    a.qual_len = qual_len;
+    a.qsum = qsum;
+    a.n = n;
+    a.n_preds = n_preds;
+    for (int i = 0; i < n_preds; i++) a.preds[i] = preds[i];
+    a.pass = pass;
+    a.agg = reinterpret_cast<long long*>(agg);
+    cudaError_t e = cudaMemsetAsync(agg, 0, 8 * sizeof(int64_t), st);
+    if (e != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    fastq_filter_kernel<<<row_blocks(n, 256 * 4), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ================================================================= FASTA headers
+__device__ __forceinline__ bool is_ascii_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\f' || c == '\r'; }
+__device__ __forceinline__ bool is_trim_ws(uint8_t c) { return c == ' ' || (c >= 0x09 && c <= 0x0D); }
+
+// Definition::from_str (noodles-fasta 0.27): name = up to the first ASCII
+// whitespace; description = remainder trimmed; absent remainder = NULL.
+__global__ void __launch_bounds__(256) fasta_headers_kernel(const uint8_t* __restrict__ buf, const int64_t* __restrict__ hdr_start,
+                                                            const int64_t* __restrict__ hdr_end, int64_t n_rows, int64_t n_total,
+                                                            uint32_t* __restrict__ lens, int64_t* __restrict__ desc_start,
+                                                            uint8_t* __restrict__ desc_valid, unsigned long long* err_pos) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = hdr_start[i] + 1, e = hdr_end[i];
+        if (e > s && e < n_total && buf[e - 1] == '\r') e--;  // CRLF; an unterminated last line keeps its CR
+        int64_t p = s;
+        while (p < e && !is_ascii_ws(buf[p])) p++;
+        if (p == s) atomicMin(err_pos, (unsigned long long)hdr_start[i]);  // MissingName
+        lens[i] = (uint32_t)(p - s);
+        desc_start[i] = s;  // starts[0][i]: the id
+        desc_start += n_rows;
+        if (p < e) {
+            int64_t ds = p + 1, de = e;
+            while (ds < de && is_trim_ws(buf[ds])) ds++;
+            while (de > ds && is_trim_ws(buf[de - 1])) de--;
+            lens[n_rows + i] = (uint32_t)(de - ds);
+            desc_start[i] = ds;
+            desc_valid[i] = 1;
+        } else {
+            lens[n_rows + i] = 0;
+            desc_start[i] = e;
+            desc_valid[i] = 0;
+        }
+        desc_start -= n_rows;
+    }
+}
+cudaError_t fasta_headers_launch(const uint8_t* buf, const int64_t* hdr_start, const int64_t* hdr_end, int64_t n_rows, int64_t n_total,
+                                 uint32_t* lens, int64_t* desc_start, uint8_t* desc_valid, unsigned long long* err_pos,
+                                 cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    fasta_headers_kernel<<<row_blocks(n_rows, 256), 256, 0, st>>>(buf, hdr_start, hdr_end, n_rows, n_total, lens, desc_start,
+                                                                  desc_valid, err_pos);
+    return cudaGetLastError();
+}
+
+// ================================================================= gc_content
+__global__ void gc_from_prefix_kernel(const int64_t* __restrict__ seq_off, const int64_t* __restrict__ gc_prefix, int64_t n,
+                                      float* __restrict__ out) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        // the reference counts in C ints; lengths beyond INT_MAX are outside what it can represent,
+        // so the int64 -> float conversions below are the natural extension (round to nearest)
+        long long len = seq_off[r + 1] - seq_off[r], gc = gc_prefix[r + 1] - gc_prefix[r];
+        out[r] = len == 0 ? 0.0f : __fdiv_rn(__ll2float_rn(gc), __ll2float_rn(len));
+    }
+}
+__global__ void gc_from_counts_kernel(const uint32_t* __restrict__ seq_len, const uint32_t* __restrict__ gc, int64_t n,
+                                      float* __restrict__ out) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        out[r] = gc_fraction(gc[r], seq_len[r]);
+}
+cudaError_t gc_from_prefix_launch(const int64_t* seq_off, const int64_t* gc_prefix, int64_t n, float* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    gc_from_prefix_kernel<<<row_blocks(n, 256), 256, 0, st>>>(seq_off, gc_prefix, n, out);
+    return cudaGetLastError();
+}
+cudaError_t gc_from_counts_launch(const uint32_t* seq_len, const uint32_t* gc, int64_t n, float* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    gc_from_counts_kernel<<<row_blocks(n, 256), 256, 0, st>>>(seq_len, gc, n, out);
+    return cudaGetLastError();
+}
+
+// gc_content over a string column: one warp per row, 16-byte loads in the body.
+__device__ __forceinline__ int gc_count_word(uint32_t x) { return __popc(gc_bytes(x)); }
+
+__global__ void __launch_bounds__(256) gc_content_kernel(const int64_t* __restrict__ off, const uint8_t* __restrict__ data, int64_t n_rows,
+                                                         float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = wid; r < n_rows; r += nw) {
+        const int64_t s = off[r], e = off[r + 1];
+        const uint8_t* p = data + s;
+        const int64_t len = e - s;
+        long long cnt = 0;
+        // head up to 16-byte alignment, body in uint4, tail
+        int64_t head = (int64_t)((16 - ((uintptr_t)p & 15)) & 15);
+        if (head > len) head = len;
+        if (lane < head) cnt += (p[lane] == 'G' || p[lane] == 'C');
+        const int64_t nvec = (len - head) >> 4;
+        const uint4* v = reinterpret_cast<const uint4*>(p + head);
+        for (int64_t i = lane; i < nvec; i += 32) {
+            uint4 x = v[i];
+            cnt += gc_count_word(x.x) + gc_count_word(x.y) + gc_count_word(x.z) + gc_count_word(x.w);
+        }
+        const int64_t tail0 = head + nvec * 16;
+        if (tail0 + lane < len) cnt += (p[tail0 + lane] == 'G' || p[tail0 + lane] == 'C');
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (lane == 0) out[r] = len == 0 ? 0.0f : __fdiv_rn(__ll2float_rn(cnt), __ll2float_rn((long long)len));
+    }
+}
+cudaError_t gc_content_launch(const int64_t* off, const uint8_t* data, int64_t n_rows, float* out, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    gc_content_kernel<<<row_blocks(n_rows, 8), 256, 0, st>>>(off, data, n_rows, out);
+    return cudaGetLastError();
+}
+
+// ================================================================= LUT map / Phred decode
+// 256-entry table in shared memory; entry 0 = invalid.  16 bytes per thread per step.
+__global__ void __launch_bounds__(256) seq_map_kernel(const uint8_t* __restrict__ in, int64_t n, int mode, uint8_t* __restrict__ out,
+                                                      unsigned long long* bad_pos) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (mode == EXB_MAP_REVERSE_COMPLEMENT) {
+            lut['A'] = 'C'; lut['T'] = 'G'; lut['C'] = 'A'; lut['G'] = 'T';
+        } else {
+            lut['A'] = 'T'; lut['T'] = 'A'; lut['C'] = 'G'; lut['G'] = 'C';
+        }
+    }
+    __syncthreads();
+    const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+    const int64_t nvec = aligned ? (n >> 4) : 0;
+    const uint4* vin = reinterpret_cast<const uint4*>(in);
+    uint4* vout = reinterpret_cast<uint4*>(out);
+    unsigned long long bad = ~0ull;
+    auto map4 = [&](uint32_t x, int64_t pos) -> uint32_t {
+        uint32_t b0 = lut[x & 0xFF], b1 = lut[(x >> 8) & 0xFF], b2 = lut[(x >> 16) & 0xFF], b3 = lut[x >> 24];
+        if (b0 == 0 || b1 == 0 || b2 == 0 || b3 == 0) {
+            int k = b0 == 0 ? 0 : (b1 == 0 ? 1 : (b2 == 0 ? 2 : 3));
+            unsigned long long p = (unsigned long long)(pos + k);
+            bad = p < bad ? p : bad;
+        }
+        return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 x = vin[i], y;
+        y.x = map4(x.x, i * 16);
+        y.y = map4(x.y, i * 16 + 4);
+        y.z = map4(x.z, i * 16 + 8);
+        y.w = map4(x.w, i * 16 + 12);
+        vout[i] = y;
+    }
+    for (int64_t i = nvec * 16 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint8_t b = lut[in[i]];
+        if (b == 0) bad = (unsigned long long)i < bad ? (unsigned long long)i : bad;
+        out[i] = b;
+    }
+    if (bad != ~0ull) atomicMin(bad_pos, bad);
+}
+cudaError_t seq_map_launch(const uint8_t* in, int64_t n, int mode, uint8_t* out, unsigned long long* bad_pos, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(bad_pos, 0xFF, 8, st);
+    if (e != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    int64_t b = ((n >> 4) + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    seq_map_kernel<<<(int)b, 256, 0, st>>>(in, n, mode, out, bad_pos);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) quality_decode_kernel(const uint8_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+    // 4 input bytes -> one 16-byte store per thread per step
+    const bool aligned = ((((uintptr_t)in) & 3) | (((uintptr_t)out) & 15)) == 0;
+    const int64_t nq = aligned ? (n >> 2) : 0;
+    const uint32_t* win = reinterpret_cast<const uint32_t*>(in);
+    int4* vout = reinterpret_cast<int4*>(out);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t x = win[i];
+        int4 y;
+        y.x = (int)(signed char)(x & 0xFF) - 33;
+        y.y = (int)(signed char)((x >> 8) & 0xFF) - 33;
+        y.z = (int)(signed char)((x >> 16) & 0xFF) - 33;
+        y.w = (int)(signed char)(x >> 24) - 33;
+        vout[i] = y;
+    }
+    for (int64_t i = nq * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int)(signed char)in[i] - 33;
+}
+cudaError_t quality_decode_launch(const uint8_t* in, int64_t n, int32_t* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    int64_t b = ((n >> 2) + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    if (b < 1) b = 1;
+    quality_decode_kernel<<<(int)b, 256, 0, st>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace exb

@@ -1,0 +1,366 @@
+"""Device-resident pipeline: torch tensors own the HBM, the kernels come from
+libexon_b200.so through the C ABI.  torch is plumbing here (allocation, streams,
+events); nothing in this module computes on tensors with torch ops.
+
+All functions take/return CUDA tensors; `buf` is a uint8 tensor holding the file
+image (allocate with `alloc_input` or any 16-byte aligned CUDA tensor).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import F_LINES, F_QUAL, F_SEQ, NO_POS, ExonError, check, lib
+
+UINT64_MAX = 0xFFFFFFFFFFFFFFFF
+
+
+class FormatError(ValueError):
+    """Malformed FASTA/FASTQ input (the reference aborts the query)."""
+
+    def __init__(self, msg, pos=-1):
+        super().__init__(msg)
+        self.pos = pos
+
+
+class InvalidInput(ValueError):
+    """duckdb::InvalidInputException of reverse_complement / complement."""
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _empty(n, dtype, device):
+    return torch.empty(max(int(n), 1), dtype=dtype, device=device)[: int(n)]
+
+
+def alloc_input(n, device="cuda"):
+    """uint8 buffer with slack so the kernels' 16-byte staging never leaves the allocation."""
+    return torch.empty(int(n) + 64, dtype=torch.uint8, device=device)[: int(n)]
+
+
+def to_device(data, device="cuda"):
+    """bytes / numpy uint8 -> CUDA uint8 tensor (test and tooling helper)."""
+    import numpy as np
+
+    arr = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    buf = alloc_input(arr.size, device)
+    if arr.size:
+        buf.copy_(torch.from_numpy(arr.copy()))
+    return buf
+
+
+def workspace(n_bytes, device):
+    return torch.empty(lib().exb_scan_workspace_bytes(int(n_bytes)), dtype=torch.uint8, device=device)
+
+
+def fetch_result(ws):
+    res = _lib.ScanResult()
+    check(lib().exb_scan_result_fetch(_ptr(ws), C.byref(res), _stream()))
+    return res
+
+
+class FastqScan:
+    """Outputs of one exb_fastq_scan launch (device tensors; scalars after `.result`)."""
+
+    def __init__(self):
+        self.buf = None
+        self.n = 0
+        self.begin = 0
+        self.flags = 0
+        self.wide = False
+        self.line_end = None
+        self.seq_len = self.gc = self.qual_len = self.qsum = None
+        self.ws = None
+        self._res = None
+
+    @property
+    def result(self):
+        if self._res is None:
+            self._res = fetch_result(self.ws)
+        return self._res
+
+    def validate(self):
+        r = self.result
+        if r.err_pos != NO_POS:
+            raise FormatError("malformed FASTQ record at byte %d" % r.err_pos, r.err_pos)
+        if r.total_lines % 4 != 0:
+            raise FormatError("truncated FASTQ record: %d lines" % r.total_lines)
+        if r.overflow:
+            raise ExonError(_lib.ERR_CAPACITY, "output capacity exceeded")
+        return int(r.total_lines // 4)
+
+
+def fastq_scan(buf, flags=F_SEQ | F_QUAL, rec_cap=None, begin=0, n=None, max_lines=UINT64_MAX, out=None):
+    """Launch the single-pass FASTQ scan (asynchronous).  `out` reuses a previous FastqScan's buffers."""
+    n = buf.numel() if n is None else int(n)
+    dev = buf.device
+    s = out if out is not None else FastqScan()
+    span = n - begin
+    if rec_cap is None:
+        rec_cap = span // 32 + 4096
+    if out is None:
+        s.wide = n >= 0xFFFFFFFF
+        if flags & F_LINES:
+            s.line_end = _empty(4 * rec_cap, torch.int64 if s.wide else torch.int32, dev)
+        if flags & F_SEQ:
+            s.seq_len = _empty(rec_cap, torch.int32, dev)
+            s.gc = _empty(rec_cap, torch.int32, dev)
+        if flags & F_QUAL:
+            s.qual_len = _empty(rec_cap, torch.int32, dev)
+            s.qsum = _empty(rec_cap, torch.int32, dev)
+        s.ws = workspace(span + 16, dev)
+        s.rec_cap = rec_cap
+    s.buf, s.n, s.begin, s.flags, s._res = buf, n, begin, flags, None
+    check(lib().exb_fastq_scan(_ptr(buf), begin, n, 1, None, max_lines, flags, _ptr(s.line_end),
+                               s.line_end.numel() if s.line_end is not None else 0, 1 if s.wide else 0,
+                               _ptr(s.seq_len), _ptr(s.gc), _ptr(s.qual_len), _ptr(s.qsum), s.rec_cap,
+                               _ptr(s.ws), s.ws.numel(), _stream()))
+    return s
+
+
+def fastq_scan_sync(buf, flags=F_SEQ | F_QUAL, **kw):
+    """Scan, growing the per-record capacity to the hard bound if the estimate was too small."""
+    s = fastq_scan(buf, flags, **kw)
+    if s.result.overflow:
+        kw.pop("rec_cap", None)
+        span = (kw.get("n") or buf.numel()) - kw.get("begin", 0)
+        s = fastq_scan(buf, flags, rec_cap=span // 4 + 16, **kw)
+    return s
+
+
+def fastq_filter(scan, n_records, preds, want_pass=False, agg=None):
+    """Per-record predicates (ANDed) + aggregates over the passing records (asynchronous).
+
+    Returns (agg int64[8] tensor: count, sum seq_len, sum gc, sum qsum, sum qual_len; pass uint8 tensor or None)."""
+    dev = scan.buf.device
+    arr, k = _lib.predicates(preds)
+    if agg is None:
+        agg = torch.empty(8, dtype=torch.int64, device=dev)
+    pas = _empty(n_records, torch.uint8, dev) if want_pass else None
+    check(lib().exb_fastq_filter(_ptr(scan.seq_len), _ptr(scan.gc), _ptr(scan.qual_len), _ptr(scan.qsum), n_records,
+                                 arr, k, _ptr(pas), _ptr(agg), _stream()))
+    return agg, pas
+
+
+def exclusive_scan_u32(x, n=None):
+    n = x.numel() if n is None else n
+    out = torch.empty(n + 1, dtype=torch.int64, device=x.device)
+    ws = workspace(4 * n + 16, x.device)
+    check(lib().exb_exclusive_scan_u32(_ptr(x), n, _ptr(out), _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def select_rows(pas):
+    n = pas.numel()
+    off = torch.empty(n + 1, dtype=torch.int64, device=pas.device)
+    sel = _empty(n, torch.int64, pas.device)
+    ws = workspace(4 * n + 16, pas.device)
+    check(lib().exb_select_rows(_ptr(pas), n, _ptr(off), _ptr(sel), _ptr(ws), ws.numel(), _stream()))
+    cnt = int(off[n].item())
+    return sel[:cnt]
+
+
+class Column:
+    """Arrow-style string column on the device: int64 offsets (n+1), uint8 data, optional validity bytes."""
+
+    def __init__(self, offsets, data, valid=None):
+        self.offsets, self.data, self.valid = offsets, data, valid
+
+    def __len__(self):
+        return self.offsets.numel() - 1
+
+    def to_pylist(self):
+        off = self.offsets.cpu().numpy()
+        dat = self.data.cpu().numpy().tobytes()
+        val = self.valid.cpu().numpy() if self.valid is not None else None
+        return [dat[off[i]:off[i + 1]] if (val is None or val[i]) else None for i in range(len(off) - 1)]
+
+
+FASTQ_COLUMNS = ["name", "description", "sequence", "quality_scores"]
+FASTA_COLUMNS = ["id", "description", "sequence"]
+
+
+def fastq_table(buf, columns=None, preds=(), n=None):
+    """read_fastq on a device buffer: {column: Column}, projected to `columns`, filtered by `preds`."""
+    columns = list(columns) if columns is not None else list(FASTQ_COLUMNS)
+    dev = buf.device
+    n = buf.numel() if n is None else int(n)
+    flags = F_LINES | ((F_SEQ | F_QUAL) if preds else 0)
+    scan = fastq_scan_sync(buf, flags, n=n)
+    n_rec = scan.validate()
+    sel = None
+    n_rows = n_rec
+    if preds:
+        _, pas = fastq_filter(scan, n_rec, preds, want_pass=True)
+        sel = select_rows(pas)
+        n_rows = sel.numel()
+    lens = _empty(4 * n_rows, torch.int32, dev)
+    valid = _empty(n_rows, torch.uint8, dev)
+    wide = 1 if scan.wide else 0
+    check(lib().exb_fastq_fields(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, _ptr(lens), _ptr(valid), None, _stream()))
+    out = {}
+    for name in columns:
+        c = FASTQ_COLUMNS.index(name)
+        off = exclusive_scan_u32(lens[c * n_rows:(c + 1) * n_rows] if n_rows else lens, n_rows)
+        total = int(off[n_rows].item())
+        data = _empty(total, torch.uint8, dev)
+        check(lib().exb_fastq_gather(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, c, _ptr(lens), _ptr(off),
+                                     _ptr(data), _stream()))
+        out[name] = Column(off, data, valid if name == "description" else None)
+    out["__n_rows__"] = n_rows
+    return out
+
+
+class FastaScan:
+    def __init__(self):
+        self.hdr_start = self.hdr_end = self.seq_off = self.gc_prefix = self.seq = None
+        self.ws = None
+        self._res = None
+
+    @property
+    def result(self):
+        if self._res is None:
+            self._res = fetch_result(self.ws)
+        return self._res
+
+
+def fasta_scan(buf, rec_cap=None, compact=True, n=None, seq_cap=None, out=None):
+    """Launch the single-pass FASTA scan (+ sequence compaction) (asynchronous)."""
+    n = buf.numel() if n is None else int(n)
+    dev = buf.device
+    s = out if out is not None else FastaScan()
+    if out is None:
+        if rec_cap is None:
+            rec_cap = n // 64 + 4096
+        s.rec_cap = rec_cap
+        s.hdr_start = _empty(rec_cap, torch.int64, dev)
+        s.hdr_end = _empty(rec_cap, torch.int64, dev)
+        s.seq_off = _empty(rec_cap + 1, torch.int64, dev)
+        s.gc_prefix = _empty(rec_cap + 1, torch.int64, dev)
+        s.seq = alloc_input(n if seq_cap is None else seq_cap, dev) if compact else None
+        s.ws = workspace(n + 16, dev)
+    s.buf, s.n, s._res = buf, n, None
+    check(lib().exb_fasta_scan(_ptr(buf), 0, n, 1, n, None, _ptr(s.hdr_start), _ptr(s.hdr_end), _ptr(s.seq_off), _ptr(s.gc_prefix),
+                               s.rec_cap, _ptr(s.seq), s.seq.numel() if s.seq is not None else 0, _ptr(s.ws), s.ws.numel(),
+                               _stream()))
+    return s
+
+
+def fasta_scan_sync(buf, **kw):
+    s = fasta_scan(buf, **kw)
+    if s.result.overflow:
+        kw.pop("rec_cap", None)
+        n = kw.get("n") or buf.numel()
+        s = fasta_scan(buf, rec_cap=n // 2 + 16, **kw)
+    r = s.result
+    if r.err_pos != NO_POS:
+        raise FormatError("malformed FASTA input at byte %d" % r.err_pos, r.err_pos)
+    if r.overflow:
+        raise ExonError(_lib.ERR_CAPACITY, "output capacity exceeded")
+    return s
+
+
+def fasta_table(buf, columns=None, n=None):
+    """read_fasta on a device buffer: {column: Column} (+ '__gc__': per-record gc_content from the scan's prefixes)."""
+    columns = list(columns) if columns is not None else list(FASTA_COLUMNS)
+    dev = buf.device
+    n = buf.numel() if n is None else int(n)
+    s = fasta_scan_sync(buf, n=n, compact="sequence" in columns)
+    n_rows = int(s.result.n_records)
+    out = {"__n_rows__": n_rows, "__scan__": s}
+    if "id" in columns or "description" in columns:
+        lens = _empty(2 * n_rows, torch.int32, dev)
+        starts = _empty(2 * n_rows, torch.int64, dev)
+        valid = _empty(n_rows, torch.uint8, dev)
+        err = torch.empty(1, dtype=torch.int64, device=dev)
+        check(lib().exb_fasta_headers(_ptr(buf), n, _ptr(s.hdr_start), _ptr(s.hdr_end), n_rows, _ptr(lens), _ptr(starts), _ptr(valid),
+                                      _ptr(err), _stream()))
+        bad = int(err.item())
+        if bad != -1:
+            raise FormatError("FASTA definition without a name at byte %d" % bad, bad)
+        for c, name in enumerate(["id", "description"]):
+            if name not in columns:
+                continue
+            ln = lens[c * n_rows:(c + 1) * n_rows] if n_rows else lens
+            off = exclusive_scan_u32(ln, n_rows)
+            total = int(off[n_rows].item())
+            data = _empty(total, torch.uint8, dev)
+            start = starts[c * n_rows:(c + 1) * n_rows] if n_rows else starts
+            check(lib().exb_gather_ranges(_ptr(buf), _ptr(start), _ptr(ln), _ptr(off), n_rows, _ptr(data), _stream()))
+            out[name] = Column(off, data, valid if c == 1 else None)
+    if "sequence" in columns:
+        out["sequence"] = Column(s.seq_off[:n_rows + 1], s.seq[:int(s.result.seq_bytes)])
+    return out
+
+
+def gc_from_prefix(seq_off, gc_prefix, n_rows):
+    out = _empty(n_rows, torch.float32, seq_off.device)
+    check(lib().exb_gc_from_prefix(_ptr(seq_off), _ptr(gc_prefix), n_rows, _ptr(out), _stream()))
+    return out
+
+
+def gc_from_counts(seq_len, gc, n_rows):
+    out = _empty(n_rows, torch.float32, seq_len.device)
+    check(lib().exb_gc_from_counts(_ptr(seq_len), _ptr(gc), n_rows, _ptr(out), _stream()))
+    return out
+
+
+def gc_content(col):
+    """gc_content(VARCHAR) -> FLOAT over a device Column (sequence_functions/module.cpp:131-158, per-row formula)."""
+    n = len(col)
+    out = _empty(n, torch.float32, col.offsets.device)
+    check(lib().exb_gc_content(_ptr(col.offsets), _ptr(col.data), n, _ptr(out), _stream()))
+    return out
+
+
+def _seq_map(col, mode):
+    dev = col.offsets.device
+    nb = col.data.numel()
+    out = alloc_input(nb, dev)
+    bad = torch.empty(1, dtype=torch.int64, device=dev)
+    check(lib().exb_seq_map(_ptr(col.data), nb, mode, _ptr(out), _ptr(bad), _stream()))
+    b = int(bad.item())
+    if b != -1:
+        ch = int(col.data[b].item())
+        raise InvalidInput("Invalid character in sequence: %s" % chr(ch))
+    return Column(col.offsets, out, col.valid)
+
+
+def reverse_complement(col):
+    """reverse_complement(VARCHAR) with the reference's semantics (module.cpp:30-69): A->C T->G C->A G->T, no reversal."""
+    return _seq_map(col, _lib.MAP_REVERSE_COMPLEMENT)
+
+
+def complement(col):
+    return _seq_map(col, _lib.MAP_COMPLEMENT)
+
+
+def quality_score_string_to_list(col):
+    """LIST(INTEGER) child vector: int32 tensor of byte - 33; list offsets are col.offsets (fastq_functions/module.cpp:32-50)."""
+    nb = col.data.numel()
+    out = _empty(nb, torch.int32, col.offsets.device)
+    check(lib().exb_quality_decode(_ptr(col.data), nb, _ptr(out), _stream()))
+    return out
+
+
+def gen_device(params, device="cuda"):
+    """Synthetic FASTA/FASTQ text generated on the device."""
+    size = lib().exb_gen_size(C.byref(params))
+    buf = alloc_input(size, device)
+    check(lib().exb_gen_device(C.byref(params), _ptr(buf), size, _stream()))
+    return buf
+
+
+def gen_host(params):
+    import numpy as np
+
+    size = lib().exb_gen_size(C.byref(params))
+    out = np.empty(size, dtype=np.uint8)
+    check(lib().exb_gen_host(C.byref(params), C.c_void_p(out.ctypes.data), size))
+    return out

@@ -1,0 +1,322 @@
+/*
+ * exon_b200.h -- C ABI of the B200-native FASTA/FASTQ scan engine.
+ *
+ * Plain C: pointers, sizes, PODs.  No C++ or torch types cross this boundary.
+ * Every function returns 0 on success or a negative exb_status; the message for
+ * the calling thread's last failure is exb_last_error().
+ *
+ * Two layers:
+ *
+ *  (1) Reference-FFI layer -- the two symbols the reference's C++ glue binds for
+ *      the read_fasta / read_fastq path, same names and signatures, so the
+ *      unmodified glue links against this library instead of the Rust staticlib:
+ *        new_reader        <- exon/include/rust.hpp:41-46, rust/src/arrow_reader.rs:38-166
+ *                             callers: arrow_table_function/module.cpp:95-103 (bind),
+ *                             :235-244 (init_global)
+ *        replacement_scan  <- exon/include/rust.hpp:48, rust/src/arrow_reader.rs:173-197
+ *                             caller: arrow_table_function/module.cpp:324
+ *      The Arrow C data / stream structs are the public Arrow ABI.
+ *
+ *  (2) Device layer (exb_*) -- the kernels behind it, callable on buffers that
+ *      are already resident in HBM (bench.py `value`, parity tests, and hosts
+ *      that keep data on the GPU).  All d_* pointers are device pointers; `stream`
+ *      is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *      asynchronous on `stream` unless stated otherwise.
+ */
+#ifndef EXON_B200_H
+#define EXON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EXB_API __attribute__((visibility("default")))
+#else
+#define EXB_API
+#endif
+
+typedef enum exb_status {
+    EXB_OK = 0,
+    EXB_ERR_CUDA = -1,      /* a CUDA call failed (no device, launch error, ...) */
+    EXB_ERR_ARG = -2,       /* bad argument */
+    EXB_ERR_FORMAT = -3,    /* malformed FASTA/FASTQ input (see err_pos) */
+    EXB_ERR_CAPACITY = -4,  /* an output buffer was too small */
+    EXB_ERR_IO = -5,        /* file could not be opened / read */
+    EXB_ERR_INVALID_CHAR = -6 /* reverse_complement/complement met a byte outside ACGT */
+} exb_status;
+
+EXB_API const char *exb_last_error(void);
+EXB_API const char *exb_version(void);
+/* 1 if a CUDA device is usable from this process, else 0 (never fails). */
+EXB_API int exb_device_available(void);
+
+/* ---------------------------------------------------------------------------
+ * (1) Reference-FFI layer
+ * ------------------------------------------------------------------------- */
+
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowSchema {
+    const char *format;
+    const char *name;
+    const char *metadata;
+    int64_t flags;
+    int64_t n_children;
+    struct ArrowSchema **children;
+    struct ArrowSchema *dictionary;
+    void (*release)(struct ArrowSchema *);
+    void *private_data;
+};
+struct ArrowArray {
+    int64_t length;
+    int64_t null_count;
+    int64_t offset;
+    int64_t n_buffers;
+    int64_t n_children;
+    const void **buffers;
+    struct ArrowArray **children;
+    struct ArrowArray *dictionary;
+    void (*release)(struct ArrowArray *);
+    void *private_data;
+};
+#endif
+#ifndef ARROW_C_STREAM_INTERFACE
+#define ARROW_C_STREAM_INTERFACE
+struct ArrowArrayStream {
+    int (*get_schema)(struct ArrowArrayStream *, struct ArrowSchema *out);
+    int (*get_next)(struct ArrowArrayStream *, struct ArrowArray *out);
+    const char *(*get_last_error)(struct ArrowArrayStream *);
+    void (*release)(struct ArrowArrayStream *);
+    void *private_data;
+};
+#endif
+
+/* rust.hpp:7-9.  error == NULL on success; otherwise a NUL-terminated message
+ * the caller may release with exb_free_string (the reference leaks it). */
+typedef struct ReaderResult {
+    const char *error;
+} ReaderResult;
+/* rust.hpp:11-13.  "FASTA" / "FASTQ" or NULL. */
+typedef struct ReplacementScanResult {
+    const char *file_type;
+} ReplacementScanResult;
+
+/*
+ * Open `uri` (a local file or a directory of files) as an Arrow stream of
+ * record batches of at most `batch_size` rows (the reference passes 2048).
+ *   compression: NULL = infer from the last '.'-suffix ("gz" / "zst"), else
+ *                "gzip" / "zstd" / anything else = uncompressed
+ *                (arrow_reader.rs:60-91).
+ *   file_format: "fasta" or "fastq" (case-insensitive).
+ *   filters:     NULL / "" or the predicate text produced by the reference's
+ *                FilterToString (module.cpp:158-214): `col<op>'const'` terms
+ *                joined by AND / OR, `col IS [NOT] NULL`.  This build also
+ *                accepts the function predicates it can push down:
+ *                  mean_quality(quality_scores) <op> number
+ *                  gc_content(sequence) <op> number
+ *                  length(sequence) <op> integer
+ * Schema: FASTA (id, description, sequence); FASTQ (name, description,
+ * sequence, quality_scores); all utf8, description nullable.
+ */
+EXB_API ReaderResult new_reader(struct ArrowArrayStream *stream_ptr, const char *uri, uintptr_t batch_size,
+                                const char *compression, const char *file_format, const char *filters);
+EXB_API ReplacementScanResult replacement_scan(const char *uri);
+EXB_API void exb_free_string(const char *s);
+
+/* ---------------------------------------------------------------------------
+ * (2) Device layer
+ * ------------------------------------------------------------------------- */
+
+/* what a FASTQ scan writes */
+#define EXB_F_LINES 1 /* line_end[g]: offset of the '\n' that ends line g       */
+#define EXB_F_SEQ 2   /* seq_len[r], gc[r]                                       */
+#define EXB_F_QUAL 4  /* qual_len[r], qsum[r] = sum((signed char)c - 33)         */
+
+typedef struct exb_scan_result {
+    uint64_t total_lines;     /* FASTQ: lines seen, the unterminated last line included  */
+    int64_t open_line_start;  /* offset of the first byte after the last newline         */
+    uint64_t err_pos;         /* smallest offset of a malformed line start; ~0 = none    */
+    uint32_t overflow;        /* 1 = an output capacity was too small                    */
+    uint32_t pad;
+    uint64_t n_records;       /* FASTA: number of '>' header lines                       */
+    uint64_t seq_bytes;       /* FASTA: sequence bytes kept (line terminators stripped)  */
+    uint64_t gc_total;        /* FASTA: G/C among them                                   */
+    int64_t tail_s, tail_g;   /* FASTQ: state of the open line (used when chaining chunks) */
+    uint64_t tail_hdr;        /* FASTA: the open line is a header line (chaining)          */
+} exb_scan_result;
+
+/* Bytes of zero-initialised scratch a scan over n input bytes needs. */
+EXB_API int64_t exb_scan_workspace_bytes(int64_t n);
+
+/*
+ * FASTQ scan of d_buf[begin, n) (noodles-fastq read_record semantics):
+ * strict 4-line records, LF or CRLF, last line may be unterminated.
+ * Chunked input: scan consecutive ranges of ONE device buffer in stream order,
+ * passing the previous call's workspace as d_prev_workspace (NULL for the first
+ * range, whose `begin` must be a record start) and is_final = 1 only for the
+ * range that ends the input; line / record indices and the outputs they address
+ * continue across the calls.  Lines with index >= max_lines are ignored
+ * (UINT64_MAX = all).  d_buf must be 16-byte aligned and `begin` of a chained
+ * range a multiple of 16.  d_workspace: exb_scan_workspace_bytes(n)
+ * bytes; it is cleared on `stream` by this call.  The scalar results land in
+ * the first sizeof(exb_scan_result) bytes of the workspace; fetch them with
+ * exb_scan_result_fetch.
+ *   d_line_end : uint32_t[line_cap] (wide_offsets = 0, n < 4 GiB) or uint64_t[line_cap]
+ *   d_seq_len, d_gc, d_qual_len : uint32_t[rec_cap];  d_qsum : int32_t[rec_cap]
+ */
+EXB_API int exb_fastq_scan(const void *d_buf, int64_t begin, int64_t n, int is_final,
+                           const void *d_prev_workspace, uint64_t max_lines, int flags, void *d_line_end, int64_t line_cap, int wide_offsets, uint32_t *d_seq_len,
+                           uint32_t *d_gc, uint32_t *d_qual_len, int32_t *d_qsum, int64_t rec_cap,
+                           void *d_workspace, int64_t workspace_bytes, void *stream);
+
+/* Synchronises `stream`, copies the result block out of the workspace. */
+EXB_API int exb_scan_result_fetch(const void *d_workspace, exb_scan_result *out, void *stream);
+
+/* Predicates evaluated per record on the scan's outputs, ANDed together. */
+#define EXB_P_MEAN_QUALITY 0 /* list_avg(quality_score_string_to_list(q)) : DOUBLE, NULL when empty */
+#define EXB_P_GC_CONTENT 1   /* gc_content(sequence) : FLOAT widened to DOUBLE                      */
+#define EXB_P_SEQ_LEN 2      /* length(sequence)                                                     */
+#define EXB_P_QUAL_LEN 3     /* length(quality_scores)                                               */
+#define EXB_OP_GT 0
+#define EXB_OP_GE 1
+#define EXB_OP_LT 2
+#define EXB_OP_LE 3
+#define EXB_OP_EQ 4
+#define EXB_OP_NE 5
+typedef struct exb_predicate {
+    int32_t field;
+    int32_t op;
+    double value;
+} exb_predicate;
+#define EXB_MAX_PREDICATES 8
+
+/* d_agg (int64_t[8], zeroed by the call): over the PASSING records
+ *   [0] count  [1] sum seq_len  [2] sum gc  [3] sum qsum  [4] sum qual_len
+ * d_pass (optional): uint8_t[n_records] 1 = passes.  Arrays a predicate or an
+ * aggregate does not need may be NULL. */
+EXB_API int exb_fastq_filter(const uint32_t *d_seq_len, const uint32_t *d_gc, const uint32_t *d_qual_len,
+                             const int32_t *d_qsum, int64_t n_records, const exb_predicate *preds, int n_preds,
+                             uint8_t *d_pass, int64_t *d_agg, void *stream);
+
+/* Field extents of FASTQ records from the line index: d_lens is uint32_t[4][n_records]
+ * (name, description, sequence, quality_scores); d_desc_valid uint8_t[n_records]
+ * (0 = NULL description).  d_sel (optional) lists the records to take; d_starts (optional)
+ * int64_t[4][n_rows] receives the field offsets in d_buf (input of exb_gather_ranges). */
+EXB_API int exb_fastq_fields(const void *d_buf, int64_t begin, int64_t n, const void *d_line_end, int wide_offsets,
+                             const int64_t *d_sel, int64_t n_rows, uint32_t *d_lens, uint8_t *d_desc_valid,
+                             int64_t *d_starts, void *stream);
+
+/* Exclusive prefix sum uint32 -> int64 with the total in d_out[n] (n + 1 outputs).
+ * d_workspace: exb_scan_workspace_bytes(4 * n) zero-initialised by the call. */
+EXB_API int exb_exclusive_scan_u32(const uint32_t *d_in, int64_t n, int64_t *d_out, void *d_workspace,
+                                   int64_t workspace_bytes, void *stream);
+
+/* Row ids of the records whose d_pass byte is set: d_sel[0..count), count -> d_offsets[n]
+ * where d_offsets (int64[n+1]) is scratch. */
+EXB_API int exb_select_rows(const uint8_t *d_pass, int64_t n, int64_t *d_offsets, int64_t *d_sel, void *d_workspace,
+                            int64_t workspace_bytes, void *stream);
+
+/* Copy column `col` (0..3) of the selected FASTQ records into d_out at d_off[row]. */
+EXB_API int exb_fastq_gather(const void *d_buf, int64_t begin, int64_t n, const void *d_line_end, int wide_offsets,
+                             const int64_t *d_sel, int64_t n_rows, int col, const uint32_t *d_lens,
+                             const int64_t *d_off, uint8_t *d_out, void *stream);
+
+/*
+ * FASTA scan of d_buf[begin, n) (noodles-fasta read_definition / read_sequence
+ * semantics): records start at a line whose first byte is '>'; the sequence is
+ * the concatenation of the following lines with LF / CRLF removed.  Per record
+ * r: d_hdr_start[r] = offset of '>', d_hdr_end[r] = offset of the header
+ * line's terminator; d_seq_off / d_gc_prefix (rec_cap + 1 entries) = sequence
+ * bytes / G,C bytes before record r, closed with the totals.  d_seq_out
+ * (optional, seq_cap bytes) receives the compacted sequence column.
+ * Chunk chaining as for exb_fastq_scan; halo_n (>= n) = how many bytes of d_buf
+ * are already valid: a CR in the last byte of a non-final range needs one byte
+ * of look-ahead to know whether an LF follows.
+ */
+EXB_API int exb_fasta_scan(const void *d_buf, int64_t begin, int64_t n, int is_final, int64_t halo_n,
+                           const void *d_prev_workspace, int64_t *d_hdr_start, int64_t *d_hdr_end,
+                           int64_t *d_seq_off, int64_t *d_gc_prefix, int64_t rec_cap, uint8_t *d_seq_out,
+                           int64_t seq_cap, void *d_workspace, int64_t workspace_bytes, void *stream);
+
+/* id / description extents of FASTA header lines (Definition::from_str):
+ * d_lens uint32_t[2][n_rows], d_starts int64_t[2][n_rows] (offsets of id / description in
+ * d_buf, ready for exb_gather_ranges), d_desc_valid uint8_t[n_rows];
+ * *d_err_pos (set to ~0 first) = smallest offset of a header with an empty name. */
+EXB_API int exb_fasta_headers(const void *d_buf, int64_t n, const int64_t *d_hdr_start, const int64_t *d_hdr_end,
+                              int64_t n_rows, uint32_t *d_lens, int64_t *d_starts, uint8_t *d_desc_valid,
+                              uint64_t *d_err_pos, void *stream);
+
+/* Generic gather of byte ranges: d_out[d_off[i] .. +d_len[i]) = d_buf[d_start[i] ..). */
+EXB_API int exb_gather_ranges(const void *d_buf, const int64_t *d_start, const uint32_t *d_len,
+                              const int64_t *d_off, int64_t n_rows, uint8_t *d_out, void *stream);
+
+/* gc_content per record from FASTA scan prefixes: out[r] = (float)gc / (float)len, '' -> 0. */
+EXB_API int exb_gc_from_prefix(const int64_t *d_seq_off, const int64_t *d_gc_prefix, int64_t n_rows, float *d_out,
+                               void *stream);
+/* same from FASTQ per-record counts */
+EXB_API int exb_gc_from_counts(const uint32_t *d_seq_len, const uint32_t *d_gc, int64_t n_rows, float *d_out,
+                               void *stream);
+
+/* ---- scalar functions over an Arrow-style string column (int64 offsets + bytes) ----
+ * sequence_functions/module.cpp:131-158 (per-row formula; d_valid NULL = all valid;
+ * invalid rows produce 0 and stay invalid in the caller's mask). */
+EXB_API int exb_gc_content(const int64_t *d_off, const uint8_t *d_data, int64_t n_rows, float *d_out, void *stream);
+
+#define EXB_MAP_REVERSE_COMPLEMENT 0 /* module.cpp:30-69  A->C T->G C->A G->T (reference semantics) */
+#define EXB_MAP_COMPLEMENT 1         /* module.cpp:81-121 A<->T C<->G                                 */
+/* Maps n_bytes bytes through the table; *d_bad_pos (uint64, set to ~0 first)
+ * receives the smallest index of a byte outside ACGT (the reference throws
+ * InvalidInputException for it). */
+EXB_API int exb_seq_map(const uint8_t *d_in, int64_t n_bytes, int mode, uint8_t *d_out, uint64_t *d_bad_pos,
+                        void *stream);
+
+/* fastq_functions/module.cpp:32-50: out[i] = (signed char)in[i] - 33 (list child vector;
+ * the list offsets are the string offsets). */
+EXB_API int exb_quality_decode(const uint8_t *d_in, int64_t n_bytes, int32_t *d_out, void *stream);
+
+/* ---- deterministic synthetic inputs, counter-based RNG ---- */
+#define EXB_GEN_ILLUMINA 2 /* C2/C5: 150 bp reads, '@SIM:1:FC1:lane:tile:x:y 1:N:0:ACGTACGT' */
+#define EXB_GEN_ONT 4      /* C4: 10-50 kb reads                                               */
+#define EXB_GEN_FASTA 1    /* C1/C3: wrapped FASTA                                              */
+typedef struct exb_gen_params {
+    int32_t kind;
+    uint64_t seed;
+    int64_t n_records;
+    int64_t first_record; /* global index of record 0 of this call (sharded generation) */
+    int32_t len_min, len_max; /* read / contig length range (inclusive) */
+    int32_t wrap;         /* FASTA line width */
+    int32_t crlf;         /* 1 = CRLF line ends */
+} exb_gen_params;
+/* Size in bytes of the text the parameters describe (host computation, exact). */
+EXB_API int64_t exb_gen_size(const exb_gen_params *p);
+/* Generate on the device: d_out must hold exb_gen_size(p) bytes (+16 slack). Synchronous. */
+EXB_API int exb_gen_device(const exb_gen_params *p, void *d_out, int64_t cap, void *stream);
+/* Generate on the host (same bytes), no GPU needed. */
+EXB_API int exb_gen_host(const exb_gen_params *p, void *out, int64_t cap);
+
+/* ---- host-buffer engine (end-to-end path): parse a FASTQ held in host memory ----
+ * Streams `n` host bytes through pinned staging buffers with double-buffered
+ * cudaMemcpyAsync, runs scan + filter per chunk, returns the aggregates
+ * (same layout as exb_fastq_filter's d_agg, plus [5] = records seen).
+ * Synchronous.  device = CUDA device ordinal. */
+EXB_API int exb_fastq_count_host(const void *host_buf, int64_t n, const exb_predicate *preds, int n_preds,
+                                 int64_t chunk_bytes, int device, int64_t *agg_out, exb_scan_result *res_out);
+
+/* The same with the device buffers, streams and events kept across calls. */
+typedef struct exb_engine exb_engine;
+EXB_API int exb_engine_create(int device, int64_t chunk_bytes, exb_engine **out);
+EXB_API void exb_engine_destroy(exb_engine *engine);
+EXB_API int exb_engine_fastq_count(exb_engine *engine, const void *host_buf, int64_t n, const exb_predicate *preds,
+                                   int n_preds, int64_t *agg_out, exb_scan_result *res_out);
+/* Page-locked host memory (cudaHostAlloc): the source layout the engine copies from at full PCIe rate. */
+EXB_API void *exb_host_alloc(int64_t bytes);
+EXB_API void exb_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXON_B200_H */

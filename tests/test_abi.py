@@ -1,0 +1,138 @@
+"""CPU-side checks of the C ABI: the library loads without a GPU, exports every
+symbol include/exon_b200.h declares, and the host-side logic (file-type sniffing,
+filter parsing, error reporting, generators, x87 emulation) behaves."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from exon_duckdb_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cstr(p):
+    return C.cast(p, C.c_char_p).value if p else None
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "exon_b200.h")).read()
+    declared = set(re.findall(r"^EXB_API [^;(]*?\b(\w+)\s*\(", hdr, re.M))
+    assert {"new_reader", "replacement_scan", "exb_fastq_scan", "exb_fasta_scan", "exb_gc_content", "exb_seq_map",
+            "exb_quality_decode"} <= declared
+    for name in declared:
+        assert hasattr(L, name), "library does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), "python binding and header disagree: %s" % (declared ^ set(_lib.SIGNATURES))
+    assert b"sm_100a" in L.exb_version()
+
+
+@pytest.mark.parametrize("uri,want", [
+    # test_fasta_scan.test:28-49 / test_fastq_scan.test:43-59: the suffixes the reference pins
+    ("./x/test.fasta", b"FASTA"), ("./x/test.fasta.gz", b"FASTA"), ("./x/test.fastq", b"FASTQ"),
+    ("./x/test.fastq.gz", b"FASTQ"), ("./x/test.fastq.zst", b"FASTQ"),
+    ("a.fa", b"FASTA"), ("a.fna", b"FASTA"), ("a.fq.gz", b"FASTQ"),
+    ("a.txt", None), ("a.gff", None), ("noext", None), ("a.gz", None),
+])
+def test_replacement_scan(uri, want):
+    r = _lib.lib().replacement_scan(uri.encode())
+    assert _cstr(r.file_type) == want
+
+
+class _Stream(C.Structure):
+    _fields_ = [("get_schema", C.c_void_p), ("get_next", C.c_void_p), ("get_last_error", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+def _new_reader(uri, fmt, filters=None, compression=None):
+    s = _Stream()
+    r = _lib.lib().new_reader(C.byref(s), uri.encode(), 2048, compression, fmt.encode(), filters)
+    return s, _cstr(r.error)
+
+
+def test_new_reader_errors_without_touching_the_gpu(golden_dir):
+    # test_fasta_scan.test:51-53, test_fastq_scan.test:61-62: '' is an error at bind time
+    for fmt in ("fasta", "fastq"):
+        _, err = _new_reader("", fmt)
+        assert err and b"could not register table" in err
+    _, err = _new_reader(os.path.join(golden_dir, "test.fastq"), "gff")
+    assert err and b"could not parse file_format" in err
+    _, err = _new_reader(os.path.join(golden_dir, "test.fastq"), "fastq", b"nosuchcol='a'")
+    assert err and b"unknown column" in err
+    _, err = _new_reader(os.path.join(golden_dir, "test.fastq"), "fastq", b"name='a")
+    assert err and b"unterminated" in err
+
+
+def test_new_reader_schema_matches_reference_columns(golden_dir):
+    pa = pytest.importorskip("pyarrow")
+    for fmt, f, cols in (("fastq", "test.fastq", ["name", "description", "sequence", "quality_scores"]),
+                         ("fasta", "test.fasta", ["id", "description", "sequence"])):
+        s, err = _new_reader(os.path.join(golden_dir, f), fmt, b"description IS NOT NULL AND (%s='a' OR %s>='b')" % ((cols[0].encode(),) * 2))
+        assert err is None
+        rd = pa.RecordBatchReader._import_from_c(C.addressof(s))
+        assert rd.schema.names == cols
+        assert all(str(t) == "string" for t in rd.schema.types)  # VARCHAR, as GetArrowLogicalType maps "u"
+
+
+def test_generators_are_deterministic_and_sized():
+    L = _lib.lib()
+    for kind, kw in (("illumina", {}), ("ont", dict(len_min=1000, len_max=3000)), ("fasta", dict(len_min=0, len_max=500)),
+                     ("illumina", dict(crlf=True)), ("fasta", dict(len_min=10, len_max=200, crlf=True, wrap=7))):
+        p = _lib.gen_params(kind, 50, seed=7, **kw)
+        n = L.exb_gen_size(C.byref(p))
+        a = np.zeros(n, np.uint8)
+        b = np.zeros(n, np.uint8)
+        assert L.exb_gen_host(C.byref(p), a.ctypes.data, n) == 0
+        assert L.exb_gen_host(C.byref(p), b.ctypes.data, n) == 0
+        assert (a == b).all() and a[-1] == 10
+        # record i of a shard equals record first_record + i of the whole
+        q = _lib.gen_params(kind, 10, seed=7, first_record=40, **kw)
+        m = L.exb_gen_size(C.byref(q))
+        c = np.zeros(m, np.uint8)
+        assert L.exb_gen_host(C.byref(q), c.ctypes.data, m) == 0
+        assert a[n - m:].tobytes() == c.tobytes()
+        assert L.exb_gen_host(C.byref(p), a.ctypes.data, n - 1) == _lib.ERR_CAPACITY
+
+
+def test_generated_inputs_parse_with_the_oracle():
+    from oracle import oracle as O
+    L = _lib.lib()
+    p = _lib.gen_params("illumina", 200, seed=20)
+    n = L.exb_gen_size(C.byref(p))
+    a = np.zeros(n, np.uint8)
+    L.exb_gen_host(C.byref(p), a.ctypes.data, n)
+    t = O.parse_fastq(a.tobytes())
+    assert t.n == 200
+    assert all(len(s) == 150 for s in t.strings("sequence"))
+    assert all(d in (b"1:N:0:ACGTACGT", b"2:N:0:ACGTACGT") for d in t.strings("description"))
+    means = [O.mean_quality(q) for q in t.strings("quality_scores")]
+    assert 20 < sum(means) / len(means) < 40 and any(m > 30 for m in means) and any(m <= 30 for m in means)
+    p = _lib.gen_params("fasta", 20, seed=3, len_min=100, len_max=5000)
+    n = L.exb_gen_size(C.byref(p))
+    a = np.zeros(n, np.uint8)
+    L.exb_gen_host(C.byref(p), a.ctypes.data, n)
+    t = O.parse_fasta(a.tobytes())
+    assert t.n == 20 and t.strings("id")[3] == b"contig3"
+
+
+def test_x87_division_emulation_matches_long_double(tmp_path):
+    """exb_x87_div (the device's stand-in for DuckDB's long double average) vs native x87 on this host."""
+    src = tmp_path / "x87t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "%s/exon_duckdb_b200/csrc/x87div.h"
+int main(void){ unsigned long long s=88172645463325252ULL; long bad=0,dr=0;
+ for(long i=0;i<3000000;i++){ s^=s<<13; s^=s>>7; s^=s<<17; unsigned n=(unsigned)(s>>40)%%300+1; if(i%%3==0) n=(unsigned)(s>>33)|1;
+  long long sum=(long long)((s>>8)%%(41ull*n+1)); if(i%%5==0) sum=-(long long)(s%%100000); if(i%%7==0) sum=(long long)(s>>12);
+  double ref=(double)((long double)sum/(long double)n), got=exb_x87_div(sum,n); if(ref!=got) bad++; if(ref!=(double)sum/(double)n) dr++;
+  if(exb_mean_cmp(sum,n,0,ref)!=0 || exb_mean_cmp(sum,n,1,ref)!=1) bad++; }
+ printf("%%ld %%ld\n",bad,dr); return 0; }
+''' % ROOT)
+    exe = tmp_path / "x87t"
+    subprocess.check_call(["gcc", "-O2", "-o", str(exe), str(src), "-lm"])
+    bad, dr = subprocess.check_output([str(exe)]).split()
+    assert int(bad) == 0
+    assert int(dr) > 0  # the sample does contain double-rounding cases, so the emulation is exercised

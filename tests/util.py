@@ -1,0 +1,91 @@
+"""Seeded builders of FASTA/FASTQ test inputs (shared by CPU and GPU tests)."""
+import random
+
+BASES = b"ACGT"
+
+
+def rand_seq(rng, n, alphabet=BASES):
+    return bytes(rng.choice(alphabet) for _ in range(n))
+
+
+def rand_qual(rng, n, lo=33, hi=126):
+    return bytes(rng.randint(lo, hi) for _ in range(n))
+
+
+def fastq_text(records, eol=b"\n", final_eol=True, plus_repeat=False):
+    """records: list of (name, desc or None, seq, qual) byte tuples."""
+    out = bytearray()
+    for i, (name, desc, seq, qual) in enumerate(records):
+        out += b"@" + name
+        if desc is not None:
+            out += b" " + desc
+        out += eol + seq + eol + b"+"
+        if plus_repeat:
+            out += name
+        out += eol + qual
+        if i + 1 < len(records) or final_eol:
+            out += eol
+    return bytes(out)
+
+
+def random_fastq(seed, n_records, min_len=0, max_len=300, crlf=False, final_eol=True, tricky=True):
+    """Random records inside the pinned domain, with the nasty-but-legal cases switched on:
+    '@' / '+' as first quality character, spaces in descriptions, empty sequences, tabs in names."""
+    rng = random.Random(seed)
+    recs = []
+    for i in range(n_records):
+        L = rng.randint(min_len, max_len)
+        name = b"r%d" % i + (b"\tx" if tricky and rng.random() < 0.1 else b"") + rand_seq(rng, rng.randint(0, 12), b"abcXYZ:/_-0123456789")
+        r = rng.random()
+        if r < 0.3:
+            desc = None
+        elif r < 0.4:
+            desc = b""  # "@name " : empty description
+        else:
+            desc = rand_seq(rng, rng.randint(1, 30), b"abc  :=/ GC@+>")
+        seq = rand_seq(rng, L, b"ACGTNacgtn" if tricky else BASES)
+        qual = bytearray(rand_qual(rng, L))
+        if tricky and L > 0 and rng.random() < 0.3:
+            qual[0] = rng.choice(b"@+>")
+        recs.append((name, desc, seq, bytes(qual)))
+    return fastq_text(recs, b"\r\n" if crlf else b"\n", final_eol, plus_repeat=rng.random() < 0.3), recs
+
+
+def fasta_text(records, wrap=60, eol=b"\n", final_eol=True, blank_lines=False, rng=None):
+    """records: list of (header line without '>', seq)."""
+    out = bytearray()
+    for i, (hdr, seq) in enumerate(records):
+        out += b">" + hdr + eol
+        lines = [seq[k:k + wrap] for k in range(0, len(seq), wrap)] if wrap else [seq]
+        for j, ln in enumerate(lines):
+            out += ln
+            last = i + 1 == len(records) and j + 1 == len(lines)
+            if not last or final_eol:
+                out += eol
+            if blank_lines and rng is not None and rng.random() < 0.1 and not last:
+                out += eol
+    return bytes(out)
+
+
+def random_fasta(seed, n_records, min_len=0, max_len=500, wrap=60, crlf=False, final_eol=True, tricky=True):
+    rng = random.Random(seed)
+    recs = []
+    for i in range(n_records):
+        L = rng.randint(min_len, max_len)
+        name = b"s%d" % i + rand_seq(rng, rng.randint(0, 8), b"abc.|_-")
+        r = rng.random()
+        if r < 0.3:
+            hdr = name
+        elif r < 0.4:
+            hdr = name + b" "
+        elif r < 0.5:
+            hdr = name + b"\t  padded description \t"
+        else:
+            hdr = name + b" " + rand_seq(rng, rng.randint(1, 40), b"abc =:>GC  ")
+        seq = bytearray(rand_seq(rng, L, b"ACGTNacgtn" if tricky else BASES))
+        if tricky and L > 3 and rng.random() < 0.3:
+            seq[rng.randint(1, L - 1)] = ord(">")  # '>' that is not at a line start... unless wrap puts it there
+        recs.append((hdr, bytes(seq)))
+    eol = b"\r\n" if crlf else b"\n"
+    text = fasta_text(recs, wrap, eol, final_eol, blank_lines=tricky, rng=rng)
+    return text, recs
