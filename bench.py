@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- read_fastq + mean-quality filter throughput on B200 (BASELINE.json configs[1]).
+
+Workload (per GPU): synthetic Illumina FASTQ, 20 M reads x 150 bp (~7 GB), query
+    SELECT COUNT(*) FROM read_fastq(f) WHERE list_avg(quality_score_string_to_list(quality_scores)) > 30
+One step = one pass of the hot path over the whole file image:
+    exb_fastq_scan (single-pass line/record scan, Phred sums)  ->  exb_fastq_filter (predicate + COUNT)
+`value`  : input already resident in HBM, CUDA events on the launching stream, max over ranks.
+`e2e`    : the same query through the host-buffer engine (exb_engine_fastq_count): pinned host
+           buffer -> chunked H2D overlapped with the scans -> aggregates read back, every step.
+`--impl reference` : the reference's CPU implementation of the path.  Its scan cannot be built here
+           (Rust crates absent), so this arm times the oracle's record-at-a-time port
+           (oracle/exon_oracle.c) on all host cores, one shard of whole records per thread.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "read_fastq + mean-quality filter (COUNT) throughput, input file bytes"
+UNIT = "GB/s"
+READS = 20_000_000
+READ_LEN = 150
+SEED = 20
+THRESH = 30.0
+
+
+def workload_config(n_gpus, reads):
+    return {
+        "workload": "C2: synthetic Illumina FASTQ %d reads x %d bp per GPU, COUNT(*) WHERE mean quality > %g" % (reads, READ_LEN, THRESH),
+        "reads_per_gpu": reads,
+        "query": "SELECT COUNT(*) FROM read_fastq(f) WHERE list_avg(quality_score_string_to_list(quality_scores)) > 30",
+        "sharding": "byte-range / record shards, one per GPU, no data-path collective; NCCL all-reduce of the aggregates"
+        if n_gpus > 1 else "single GPU",
+        "l2": "input (~7 GB) is larger than L2 (126 MB); no flush needed between steps",
+    }
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def run_reference(args):
+    """CPU arm: the oracle's record-at-a-time port, one shard of whole records per host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from exon_duckdb_b200 import _lib
+    from oracle import oracle as O
+    L = _lib.lib()
+    O.lib()
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    # bounded sample: ~1 s of work per thread per step
+    per_thread = int(os.environ.get("EXB_REF_READS_PER_THREAD", "1500000"))
+    shards = []
+    for t in range(cores):
+        p = _lib.gen_params("illumina", per_thread, seed=SEED, first_record=t * per_thread, len_min=READ_LEN, len_max=READ_LEN)
+        n = L.exb_gen_size(C.byref(p))
+        a = np.empty(n, np.uint8)
+        shards.append((p, a, n))
+    # generation is outside the timed region; do it threaded as well
+    def gen(i):
+        p, a, n = shards[i]
+        L.exb_gen_host(C.byref(p), a.ctypes.data, n)
+    ths = [threading.Thread(target=gen, args=(i,)) for i in range(cores)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    total_bytes = sum(s[2] for s in shards)
+    results = [None] * cores
+
+    def work(i):
+        results[i] = O.fastq_count_mean_quality(shards[i][1], ">", THRESH)
+
+    def step():
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = total_bytes / dt / 1e9
+    reads = per_thread * cores
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": workload_config(args.gpus, READS),
+        "reads_per_s": reads / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d reads (%d per thread x %d threads, %.2f GB) of the C2 generator per step; "
+                                   "oracle/exon_oracle.c orc_fastq_count_mean_quality; the reference's own scan needs Rust crates that are absent" %
+                                   (reads, per_thread, cores, total_bytes / 1e9)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pass": int(sum(r[0] for r in results)), "records": int(sum(r[1] for r in results)),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("EXB_BENCH_READS", READS)))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from exon_duckdb_b200 import _lib, device as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    # ---- synthetic input, generated on the device (each rank its own shard of the record space)
+    p = _lib.gen_params("illumina", args.reads, seed=SEED, first_record=rank * args.reads, len_min=READ_LEN, len_max=READ_LEN)
+    buf = D.gen_device(p, dev)
+    n_bytes = buf.numel()
+    preds = [("mean_quality", ">", THRESH)]
+    flags = _lib.F_QUAL  # projection push-down: the query needs the quality line only
+    rec_cap = args.reads + 1024
+    scan = D.fastq_scan(buf, flags, rec_cap=rec_cap)
+    n_rec = scan.validate()
+    assert n_rec == args.reads
+    agg = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def step(timers=None):
+        if timers is not None:
+            timers[0].record()
+        D.fastq_scan(buf, flags, out=scan)
+        if timers is not None:
+            timers[1].record()
+        D.fastq_filter(scan, rec_cap, preds, agg=agg, device_count=True)
+        if world > 1:
+            dist.all_reduce(agg)  # COUNT / sums across shards: the query's only exchange step (64 bytes over NVLink)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    scan_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        step(scan_ev[i])
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.stop()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    scan_ms = sum(a.elapsed_time(b) for a, b in scan_ev) / args.steps
+    got = agg.cpu().tolist()
+    tmax = torch.tensor([ms_total, scan_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, scan_ms = tmax.tolist()
+    ms_step = ms_total / args.steps
+    total_bytes = n_bytes * world
+    value = total_bytes / (ms_step * 1e-3) / 1e9
+    n_pass = got[0]  # after the all-reduce this is already the global count
+
+    # ---- end to end: pinned host image -> engine -> aggregates, every step
+    e2e = None
+    host_ptr = None
+    if not args.no_e2e:
+        host_ptr = L.exb_host_alloc(n_bytes)
+        if not host_ptr:
+            raise SystemExit("exb_host_alloc failed")
+        host = np.ctypeslib.as_array(C.cast(host_ptr, C.POINTER(C.c_uint8)), shape=(n_bytes,))
+        torch.from_numpy(host).copy_(buf)  # untimed: put the file image where a host application would have it
+        eng = C.c_void_p()
+        _lib.check(L.exb_engine_create(local, 64 << 20, C.byref(eng)))
+        parr, k = _lib.predicates(preds)
+        eagg = (C.c_int64 * 8)()
+        for _ in range(3):
+            _lib.check(L.exb_engine_fastq_count(eng, host_ptr, n_bytes, parr, k, eagg, None))
+        if world > 1:
+            dist.barrier()
+        e2e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            _lib.check(L.exb_engine_fastq_count(eng, host_ptr, n_bytes, parr, k, eagg, None))
+        dt = (time.perf_counter() - t0) / e2e_steps
+        assert eagg[5] == args.reads
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = tt.item()
+        e2e = {"value": total_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": 64 + C.sizeof(_lib.ScanResult),
+               "ms_per_step": dt * 1e3, "steps": e2e_steps, "pass": int(eagg[0]),
+               "note": "host wall clock around exb_engine_fastq_count (synchronous call), max over ranks"}
+        L.exb_engine_destroy(eng)
+
+    # ---- CPU baseline beside it: oracle port, 1 thread, bounded sample of the same bytes (rank 0 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        sample_reads = min(args.reads, 8_000_000)
+        if host_ptr:
+            # cut the sample at a record boundary: the records are generated in order, so re-measure its size
+            q = _lib.gen_params("illumina", sample_reads, seed=SEED, first_record=0, len_min=READ_LEN, len_max=READ_LEN)
+            sample_bytes = L.exb_gen_size(C.byref(q)) if sample_reads < args.reads else n_bytes
+            sample = host[:sample_bytes]
+        else:
+            sample = buf[:0].cpu().numpy()
+            sample_bytes = 0
+        if sample_bytes:
+            t0 = time.perf_counter()
+            r = O.fastq_count_mean_quality(sample, ">", THRESH)
+            dt = time.perf_counter() - t0
+            cpu = {"value": sample_bytes / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "first %d reads (%.2f GB) of the same workload, oracle/exon_oracle.c record-at-a-time port, 1 thread, %.1f s"
+                             % (sample_reads, sample_bytes / 1e9, dt),
+                   "pass": int(r[0])}
+    if host_ptr:
+        L.exb_host_free(host_ptr)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = n_bytes / (scan_ms * 1e-3) / 1e9
+        tr = ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(world, args.reads),
+            "reads_per_s": args.reads * world / (ms_step * 1e-3),
+            "bytes_per_gpu": n_bytes, "records_passing": int(n_pass),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": tr.get("dram_bytes_per_launch") if tr else None, "kernel": "fastq_scan_kernel<uint32_t|uint64_t, F_QUAL>",
+                         "algorithmic_bytes_per_launch": n_bytes, "kernel_ms": scan_ms, "peak_source": peak_src,
+                         "note": "algorithmic bytes = input file bytes read once (SURVEY 8d); kernel_ms spans workspace clear + scan kernel"},
+            "clocks": sampler.summary(),
+            "gpu_launches": 3 * args.steps,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -79,7 +79,7 @@ SIGNATURES = {
     "exb_scan_workspace_bytes": (_i64, [_i64]),
     "exb_fastq_scan": (_i32, [_vp, _i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_scan_result_fetch": (_i32, [_vp, C.POINTER(ScanResult), _vp]),
-    "exb_fastq_filter": (_i32, [_vp, _vp, _vp, _vp, _i64, C.POINTER(Predicate), _i32, _vp, _vp, _vp]),
+    "exb_fastq_filter": (_i32, [_vp, _vp, _vp, _vp, _i64, C.POINTER(Predicate), _i32, _vp, _vp, _vp, _vp]),
     "exb_fastq_fields": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "exb_exclusive_scan_u32": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "exb_select_rows": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),

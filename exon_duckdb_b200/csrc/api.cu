@@ -23,7 +23,7 @@ cudaError_t fastq_gather_launch(const uint8_t*, int64_t, int64_t, const void*, b
                                 const int64_t*, uint8_t*, cudaStream_t);
 cudaError_t gather_ranges_launch(const uint8_t*, const int64_t*, const uint32_t*, const int64_t*, int64_t, uint8_t*, cudaStream_t);
 cudaError_t fastq_filter_launch(const uint32_t*, const uint32_t*, const uint32_t*, const int32_t*, int64_t, const exb_predicate*, int,
-                                uint8_t*, int64_t*, cudaStream_t);
+                                uint8_t*, int64_t*, const void*, cudaStream_t);
 cudaError_t fasta_headers_launch(const uint8_t*, const int64_t*, const int64_t*, int64_t, int64_t, uint32_t*, int64_t*, uint8_t*,
                                  unsigned long long*, cudaStream_t);
 cudaError_t gc_from_prefix_launch(const int64_t*, const int64_t*, int64_t, float*, cudaStream_t);
@@ -157,7 +157,8 @@ int exb_scan_result_fetch(const void* d_workspace, exb_scan_result* out, void* s
 }
 
 int exb_fastq_filter(const uint32_t* d_seq_len, const uint32_t* d_gc, const uint32_t* d_qual_len, const int32_t* d_qsum,
-                     int64_t n_records, const exb_predicate* preds, int n_preds, uint8_t* d_pass, int64_t* d_agg, void* stream) {
+                     int64_t n_records, const exb_predicate* preds, int n_preds, uint8_t* d_pass, int64_t* d_agg,
+                     const void* d_scan_workspace, void* stream) {
     if (n_preds < 0 || n_preds > EXB_MAX_PREDICATES) return set_err(EXB_ERR_ARG, "exb_fastq_filter: at most %d predicates", EXB_MAX_PREDICATES);
     for (int i = 0; i < n_preds; i++) {
         int f = preds[i].field;
@@ -168,7 +169,8 @@ int exb_fastq_filter(const uint32_t* d_seq_len, const uint32_t* d_gc, const uint
         if (f == EXB_P_QUAL_LEN && !d_qual_len) return set_err(EXB_ERR_ARG, "length(quality_scores) predicate needs qual_len");
     }
     if (!d_agg) return set_err(EXB_ERR_ARG, "exb_fastq_filter: d_agg is required");
-    cudaError_t e = fastq_filter_launch(d_seq_len, d_gc, d_qual_len, d_qsum, n_records, preds, n_preds, d_pass, d_agg, (cudaStream_t)stream);
+    cudaError_t e = fastq_filter_launch(d_seq_len, d_gc, d_qual_len, d_qsum, n_records, preds, n_preds, d_pass, d_agg, d_scan_workspace,
+                                        (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "fastq_filter launch");
     return 0;
 }

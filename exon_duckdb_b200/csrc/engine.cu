@@ -176,7 +176,7 @@ int exb_engine_fastq_count(exb_engine* g, const void* host_buf, int64_t n, const
         if (res.overflow) return set_err(EXB_ERR_CAPACITY, "per-record capacity exceeded");
         const int64_t n_rec = (int64_t)(res.total_lines / 4);
         rc = exb_fastq_filter((uint32_t*)g->d_arr[0], (uint32_t*)g->d_arr[1], (uint32_t*)g->d_arr[2], (int32_t*)g->d_arr[3], n_rec, preds,
-                              n_preds, nullptr, (int64_t*)g->d_agg, g->sk);
+                              n_preds, nullptr, (int64_t*)g->d_agg, nullptr, g->sk);
         if (rc) return rc;
         int64_t agg[8];
         e = cudaMemcpyAsync(agg, g->d_agg, sizeof(agg), cudaMemcpyDeviceToHost, g->sk);

@@ -420,7 +420,7 @@ struct Reader {
             exb_predicate p{nd.field, nd.op, nd.value};
             if (!d_selscratch.need(64)) return fail("out of device memory");
             return rc(exb_fastq_filter(d_arr[0].as<uint32_t>(), d_arr[1].as<uint32_t>(), d_arr[2].as<uint32_t>(), d_arr[3].as<int32_t>(), c.n,
-                                       &p, 1, d_out, d_selscratch.as<int64_t>(), st));
+                                       &p, 1, d_out, d_selscratch.as<int64_t>(), nullptr, st));
         }
         if (nd.field != EXB_P_GC_CONTENT && nd.field != EXB_P_SEQ_LEN) return fail("predicate not applicable to FASTA");
         return cu(fasta_num_pred_launch(d_seq_off.as<int64_t>(), d_gc_prefix.as<int64_t>(), c.n, nd.field, nd.op, nd.value, d_out, st),

@@ -24,6 +24,7 @@ struct FilterArgs {
     int n_preds;
     uint8_t* pass;
     long long* agg;
+    const ScanResult* scan;  // optional: take the record count from a scan's result block (no host round trip)
 };
 
 __device__ __forceinline__ float gc_fraction(uint32_t gc, uint32_t len) {
@@ -33,7 +34,12 @@ __device__ __forceinline__ float gc_fraction(uint32_t gc, uint32_t len) {
 
 __global__ void __launch_bounds__(256) fastq_filter_kernel(FilterArgs a) {
     long long v[5] = {0, 0, 0, 0, 0};
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = a.n;
+    if (a.scan) {
+        const int64_t have = (int64_t)(a.scan->total_lines >> 2);
+        n = have < n ? have : n;
+    }
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t sl = a.seq_len ? a.seq_len[r] : 0, g = a.gc ? a.gc[r] : 0;
         const uint32_t ql = a.qual_len ? a.qual_len[r] : 0;
         const int32_t qs = a.qsum ? a.qsum[r] : 0;
@@ -293,8 +299,10 @@ cudaError_t gather_ranges_launch(const uint8_t* buf, const int64_t* start, const
 }
 
 cudaError_t fastq_filter_launch(const uint32_t* seq_len, const uint32_t* gc, const uint32_t* qual_len, const int32_t* qsum, int64_t n,
-                                const exb_predicate* preds, int n_preds, uint8_t* pass, int64_t* agg, cudaStream_t st) {
+                                const exb_predicate* preds, int n_preds, uint8_t* pass, int64_t* agg, const void* scan_ws,
+                                cudaStream_t st) {
     FilterArgs a;
+    a.scan = reinterpret_cast<const ScanResult*>(scan_ws);
     a.seq_len = seq_len;
     a.gc = gc;
     a.qual_len = qual_len;

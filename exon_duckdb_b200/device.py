@@ -134,7 +134,7 @@ def fastq_scan_sync(buf, flags=F_SEQ | F_QUAL, **kw):
     return s
 
 
-def fastq_filter(scan, n_records, preds, want_pass=False, agg=None):
+def fastq_filter(scan, n_records, preds, want_pass=False, agg=None, device_count=False):
     """Per-record predicates (ANDed) + aggregates over the passing records (asynchronous).
 
     Returns (agg int64[8] tensor: count, sum seq_len, sum gc, sum qsum, sum qual_len; pass uint8 tensor or None)."""
@@ -144,7 +144,7 @@ def fastq_filter(scan, n_records, preds, want_pass=False, agg=None):
         agg = torch.empty(8, dtype=torch.int64, device=dev)
     pas = _empty(n_records, torch.uint8, dev) if want_pass else None
     check(lib().exb_fastq_filter(_ptr(scan.seq_len), _ptr(scan.gc), _ptr(scan.qual_len), _ptr(scan.qsum), n_records,
-                                 arr, k, _ptr(pas), _ptr(agg), _stream()))
+                                 arr, k, _ptr(pas), _ptr(agg), _ptr(scan.ws) if device_count else None, _stream()))
     return agg, pas
 
 

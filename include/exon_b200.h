@@ -197,10 +197,13 @@ typedef struct exb_predicate {
 /* d_agg (int64_t[8], zeroed by the call): over the PASSING records
  *   [0] count  [1] sum seq_len  [2] sum gc  [3] sum qsum  [4] sum qual_len
  * d_pass (optional): uint8_t[n_records] 1 = passes.  Arrays a predicate or an
- * aggregate does not need may be NULL. */
+ * aggregate does not need may be NULL.  d_scan_workspace (optional): the
+ * workspace of the exb_fastq_scan that produced the arrays; the kernel then
+ * takes min(n_records, total_lines / 4) from it, so scan + filter can be
+ * enqueued back to back without a host round trip. */
 EXB_API int exb_fastq_filter(const uint32_t *d_seq_len, const uint32_t *d_gc, const uint32_t *d_qual_len,
                              const int32_t *d_qsum, int64_t n_records, const exb_predicate *preds, int n_preds,
-                             uint8_t *d_pass, int64_t *d_agg, void *stream);
+                             uint8_t *d_pass, int64_t *d_agg, const void *d_scan_workspace, void *stream);
 
 /* Field extents of FASTQ records from the line index: d_lens is uint32_t[4][n_records]
  * (name, description, sequence, quality_scores); d_desc_valid uint8_t[n_records]

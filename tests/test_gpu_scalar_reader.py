@@ -1,0 +1,186 @@
+"""GPU parity for the sequence scalar functions, the Arrow-stream reader (new_reader) and the host-buffer engine."""
+import ctypes as C
+import os
+import random
+
+import numpy as np
+import pytest
+
+import exb_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def _column(dev, strings):
+    import torch
+    from exon_duckdb_b200 import device as D
+    off = np.zeros(len(strings) + 1, np.int64)
+    off[1:] = np.cumsum([len(s) for s in strings])
+    data = D.to_device(b"".join(strings), dev)
+    return D.Column(torch.from_numpy(off).to(dev), data)
+
+
+def test_gc_content_column(cuda_device):
+    from exon_duckdb_b200 import device as D
+    from oracle import oracle as O
+    rng = random.Random(1)
+    seqs = [b"ATGC", b"ATGCGC", b"", b"GGGG", b"gcGC", b"GCN", b"ATGCGCA"]  # test_scalar_functions.test:5-28 + SURVEY 8c
+    seqs += [util.rand_seq(rng, rng.choice([0, 1, 15, 16, 17, 31, 150, 1000, 70001]), b"ACGTNacgt") for _ in range(300)]
+    got = D.gc_content(_column(cuda_device, seqs)).cpu().numpy()
+    want = np.array([O.gc_content(s) for s in seqs], dtype=np.float32)
+    assert got.tobytes() == want.tobytes()
+    assert got[0] == np.float32(0.5) and got[3] == np.float32(1.0) and got[2] == np.float32(0.0)
+
+
+def test_reverse_complement_and_complement(cuda_device):
+    from exon_duckdb_b200 import device as D
+    from oracle import oracle as O
+    rng = random.Random(2)
+    seqs = [b"ATCG", b"GGGG", b"ATGC", b"AACG", b"ATGCGC", b""] + [util.rand_seq(rng, rng.randint(0, 5000)) for _ in range(200)]
+    col = _column(cuda_device, seqs)
+    assert D.reverse_complement(col).to_pylist() == [O.reverse_complement(s) for s in seqs]
+    assert D.complement(col).to_pylist() == [O.complement(s) for s in seqs]
+    assert D.reverse_complement(col).to_pylist()[:2] == [b"CGAT", b"TTTT"]  # test_scalar_functions.test:41-46
+    for bad in (b"acgt", b"ACGN", b"ATCGQ"):
+        bad_col = _column(cuda_device, [b"ACGT" * 100, bad, b"GG"])
+        for fn in (D.reverse_complement, D.complement):
+            with pytest.raises(D.InvalidInput) as ei:
+                fn(bad_col)
+            with pytest.raises(O.InvalidInput) as eo:
+                (O.reverse_complement if fn is D.reverse_complement else O.complement)(bad)
+            assert str(ei.value) == str(eo.value)  # "Invalid character in sequence: <c>" names the first bad byte
+
+
+def test_quality_score_string_to_list(cuda_device):
+    from exon_duckdb_b200 import device as D
+    from oracle import oracle as O
+    rng = random.Random(3)
+    quals = [b"!'*5I~", b"IIII5555", bytes([0x80, 0xFF, 0x21])] + [util.rand_qual(rng, rng.randint(0, 3000), 0, 255) for _ in range(100)]
+    col = _column(cuda_device, quals)
+    got = D.quality_score_string_to_list(col).cpu().numpy()
+    want = np.concatenate([O.quality_score_string_to_list(q) for q in quals])
+    assert got.dtype == np.int32 and np.array_equal(got, want)
+    assert got[:6].tolist() == [0, 6, 9, 20, 40, 93]
+
+
+# ---------------------------------------------------------------- new_reader
+class _Stream(C.Structure):
+    _fields_ = [("get_schema", C.c_void_p), ("get_next", C.c_void_p), ("get_last_error", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+def _read(uri, fmt, filters=None, compression=None, batch=2048):
+    import pyarrow as pa
+    from exon_duckdb_b200 import _lib
+    s = _Stream()
+    r = _lib.lib().new_reader(C.byref(s), uri.encode(), batch, compression, fmt.encode(), filters)
+    if r.error:
+        raise RuntimeError(C.cast(r.error, C.c_char_p).value.decode())
+    rd = pa.RecordBatchReader._import_from_c(C.addressof(s))
+    batches = list(rd)
+    assert all(0 < b.num_rows <= batch for b in batches)
+    return pa.Table.from_batches(batches, schema=rd.schema)
+
+
+def _rows(table):
+    cols = [[None if v is None else v.encode("latin-1") for v in table.column(i).to_pylist()] for i in range(table.num_columns)]
+    return list(zip(*cols))
+
+
+def test_reader_reference_queries(cuda_device, golden_dir):
+    from oracle import oracle as O
+    fq = os.path.join(golden_dir, "test.fastq")
+    t = _read(fq, "fastq")
+    assert t.num_rows == 2  # test_fastq_scan.test:5-8
+    assert _rows(t) == O.parse_fastq(open(fq, "rb").read()).rows()  # :34-41 incl. column order
+    fa = os.path.join(golden_dir, "test.fasta")
+    assert _read(fa, "fasta").num_rows == 2  # test_fasta_scan.test:5-8
+    assert _read(fa, "fasta", b"id='a'").num_rows == 1  # :34-37 (FilterToString output for WHERE id = 'a')
+    md = _read(os.path.join(golden_dir, "test.mixed-desc.fasta"), "fasta")
+    assert md.column("description").to_pylist() == ["description", None]
+    assert _read(os.path.join(golden_dir, "test.mixed-desc.fasta"), "fasta", b"description IS NULL").column("id").to_pylist() == ["b"]
+    assert _read(os.path.join(golden_dir, "fastq") + "/", "fastq").num_rows == 4  # test_fastq_scan.test:64-68
+
+
+def test_reader_gzip(cuda_device, tmp_path):
+    import gzip
+    from oracle import oracle as O
+    text, _ = util.random_fastq(5, 500)
+    p = tmp_path / "x.fastq.gz"
+    with gzip.open(p, "wb") as f:
+        f.write(text)
+    assert _rows(_read(str(p), "fastq")) == O.parse_fastq(text).rows()          # auto-detect from ".gz"
+    q = tmp_path / "y.fastq.gzip"
+    q.write_bytes(p.read_bytes())
+    assert _read(str(q), "fastq", compression=b"gzip").num_rows == 500          # explicit option
+
+
+@pytest.mark.parametrize("chunk", [None, 4096, 70000])
+def test_reader_chunk_carry_fastq(cuda_device, tmp_path, monkeypatch, chunk):
+    """Records straddling chunk edges are re-read with the next chunk; tiny chunks force that on every record."""
+    from oracle import oracle as O
+    if chunk:
+        monkeypatch.setenv("EXON_B200_CHUNK_BYTES", str(chunk))
+    text, _ = util.random_fastq(6, 3000, max_len=400, tricky=False)
+    p = tmp_path / "a.fastq"
+    p.write_bytes(text)
+    want = O.parse_fastq(text)
+    assert _rows(_read(str(p), "fastq")) == want.rows()
+    got = _read(str(p), "fastq", b"mean_quality(quality_scores) > 45 AND name>='r2'")
+    keep = [r for r in want.rows() if O.mean_quality_pass(r[3], ">", 45) and r[0] >= b"r2"]
+    assert 0 < len(keep) < want.n and _rows(got) == keep
+
+
+@pytest.mark.parametrize("chunk", [None, 8192, 100000])
+def test_reader_chunk_carry_fasta(cuda_device, tmp_path, monkeypatch, chunk):
+    from oracle import oracle as O
+    if chunk:
+        monkeypatch.setenv("EXON_B200_CHUNK_BYTES", str(chunk))
+    text, _ = util.random_fasta(7, 800, max_len=3000, tricky=False)
+    p = tmp_path / "a.fasta"
+    p.write_bytes(text)
+    want = O.parse_fasta(text)
+    assert _rows(_read(str(p), "fasta")) == want.rows()
+    got = _read(str(p), "fasta", b"gc_content(sequence) > 0.5 OR description IS NULL")
+    keep = [r for r in want.rows() if float(O.gc_content(r[2])) > 0.5 or r[1] is None]
+    assert 0 < len(keep) < want.n and _rows(got) == keep
+
+
+def test_reader_reports_malformed_input(cuda_device, tmp_path):
+    p = tmp_path / "bad.fastq"
+    p.write_bytes(b"@a\nACGT\n+\nIIII\nACGT\n")
+    with pytest.raises(Exception) as e:
+        _read(str(p), "fastq")
+    assert "invalid FASTQ record at byte 15" in str(e.value)
+
+
+# ---------------------------------------------------------------- host-buffer engine
+@pytest.mark.parametrize("pinned", [False, True])
+def test_engine_fastq_count_host(cuda_device, pinned):
+    from exon_duckdb_b200 import _lib
+    from oracle import oracle as O
+    L = _lib.lib()
+    p = _lib.gen_params("illumina", 40000, seed=20)
+    n = L.exb_gen_size(C.byref(p))
+    if pinned:
+        ptr = L.exb_host_alloc(n)
+        host = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,))
+    else:
+        host = np.empty(n, np.uint8)
+    assert L.exb_gen_host(C.byref(p), host.ctypes.data, n) == 0
+    preds, k = _lib.predicates([("mean_quality", ">", 30.0)])
+    agg = (C.c_int64 * 8)()
+    res = _lib.ScanResult()
+    # 1 MiB chunks: 14 chained ranges, records straddle every edge
+    _lib.check(L.exb_fastq_count_host(host.ctypes.data, n, preds, k, 1 << 20, 0, agg, C.byref(res)))
+    want = O.fastq_count_mean_quality(host, ">", 30.0)
+    assert (agg[0], agg[5]) == want[:2] and res.total_lines == 4 * 40000
+    eng = C.c_void_p()
+    _lib.check(L.exb_engine_create(0, 1 << 22, C.byref(eng)))
+    for _ in range(2):
+        agg2 = (C.c_int64 * 8)()
+        _lib.check(L.exb_engine_fastq_count(eng, host.ctypes.data, n, preds, k, agg2, None))
+        assert list(agg2)[:6] == list(agg)[:6]
+    L.exb_engine_destroy(eng)
+    if pinned:
+        L.exb_host_free(ptr)
