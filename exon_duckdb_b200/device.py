@@ -32,7 +32,10 @@ def _stream():
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    if t is None:
+        return C.c_void_p(0)
+    # data_ptr() of a zero-length view is NULL; the storage address is what the C ABI wants
+    return C.c_void_p(t.untyped_storage().data_ptr() + t.storage_offset() * t.element_size())
 
 
 def _empty(n, dtype, device):
