@@ -8,9 +8,14 @@
 //     line's LF (and a CR directly before that LF) removed; blank lines add nothing.
 // Every input byte is read once.  Per tile (16 KiB in shared memory) each thread
 // classifies its 64-byte run into bit masks {newline, header start, header span,
-// kept sequence byte, G/C}; a decoupled look-back carries
-//   {records so far, kept sequence bytes so far, G/C so far, "inside a header line"}
-// so every record gets its sequence offset / G/C prefix as a plain store and the
+// kept sequence byte, G/C}.  Two things cross tile boundaries:
+//   (1) "is the line that is open at my first byte a header line?" -- local to the
+//       nearest predecessor that contains a line start, so every tile publishes a
+//       one-word record {sets the flag, flag} with no dependency and reads its
+//       predecessor's (walking further back only across tiles without a newline);
+//   (2) three plain running sums {records, kept sequence bytes, G/C among them},
+//       chained with the block-wide decoupled look-back.
+// So every record gets its sequence offset / G/C prefix as a plain store and the
 // kept bytes are compacted straight into the output column at their final place
 // (staged through shared memory so the global stores are 16-byte coalesced).
 // gc_content per contig is then (gc_prefix[r+1]-gc_prefix[r]) / (seq_off[r+1]-seq_off[r])
@@ -20,67 +25,38 @@
 
 namespace exb {
 
-struct alignas(16) FaState {
-    uint64_t n_hdr;     // header lines started
-    uint64_t seq;       // sequence bytes kept (aggregates: assuming the carried-in line is NOT a header)
-    uint64_t gc;        // G/C among them (same assumption)
-    uint64_t head_seq;  // aggregates: part of `seq` that lies before the first newline
-    uint64_t head_gc;
-    uint32_t has_nl;    // a newline was seen => tail_hdr is resolved (prefix states: always 1)
-    uint32_t tail_hdr;  // the line open at the end is a header line
-    uint64_t pad;
-    __device__ static FaState combine(const FaState& p, const FaState& t) {
-        FaState r;
-        r.n_hdr = p.n_hdr + t.n_hdr;
-        if (p.has_nl) {
-            const bool h = p.tail_hdr != 0;
-            r.seq = p.seq + t.seq - (h ? t.head_seq : 0);
-            r.gc = p.gc + t.gc - (h ? t.head_gc : 0);
-            r.head_seq = p.head_seq;
-            r.head_gc = p.head_gc;
-        } else {
-            r.seq = p.seq + t.seq;
-            r.gc = p.gc + t.gc;
-            r.head_seq = p.head_seq + t.head_seq;
-            r.head_gc = p.head_gc + t.head_gc;
-        }
-        r.has_nl = p.has_nl | t.has_nl;
-        r.tail_hdr = t.has_nl ? t.tail_hdr : p.tail_hdr;
-        r.pad = 0;
-        return r;
-    }
-};
-static_assert(sizeof(FaState) == 64, "FaState");
-
-// five 12-bit fields in one scan word: header starts, kept, gc, head_kept, head_gc (each <= 2048 per warp)
-__device__ __forceinline__ uint64_t pack5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) {
-    return (uint64_t)a | ((uint64_t)b << 12) | ((uint64_t)c << 24) | ((uint64_t)d << 36) | ((uint64_t)e << 48);
+// three 20-bit fields in one scan word: header starts, kept, gc (each <= 2048 per warp)
+__device__ __forceinline__ uint64_t pack3u(uint32_t a, uint32_t b, uint32_t c) {
+    return (uint64_t)a | ((uint64_t)b << 20) | ((uint64_t)c << 40);
 }
-struct U5 {
-    int hs, kept, gc, hkept, hgc;
+struct U3 {
+    int hs, kept, gc;
 };
-__device__ __forceinline__ U5 unpack5(uint64_t v) {
-    U5 u;
-    u.hs = (int)(v & 0xFFF);
-    u.kept = (int)((v >> 12) & 0xFFF);
-    u.gc = (int)((v >> 24) & 0xFFF);
-    u.hkept = (int)((v >> 36) & 0xFFF);
-    u.hgc = (int)((v >> 48) & 0xFFF);
+__device__ __forceinline__ U3 unpack3u(uint64_t v) {
+    U3 u;
+    u.hs = (int)(v & 0xFFFFF);
+    u.kept = (int)((v >> 20) & 0xFFFFF);
+    u.gc = (int)((v >> 40) & 0xFFFFF);
     return u;
 }
+
+constexpr uint64_t REC_VALID = 1ull << 63;
 
 template <bool kCompact>
 __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs a) {
     __shared__ uint4 s_tile[TILE_CHUNKS];
-    __shared__ uint8_t s_out[kCompact ? TILE_BYTES + 16 : 16];
+    __shared__ __align__(16) uint8_t s_out[kCompact ? TILE_BYTES + 16 : 16];
     __shared__ uint64_t s_warp_tot[WARPS];
-    __shared__ int s_warp_flag[WARPS];  // -1: no newline in the warp; else tail_hdr after its last newline
-    __shared__ FaState s_excl;
+    __shared__ int s_warp_flag[WARPS];  // -1: the warp's 2 KiB has no line start; else "open line is a header" at its end
+    __shared__ LookbackSmem<3> s_lb;
+    __shared__ int s_carry;
     __shared__ int64_t s_tile_id;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint8_t* __restrict__ buf = a.buf;
     const int64_t origin = a.begin & ~(int64_t)15;
+    uint64_t* chain = reinterpret_cast<uint64_t*>(a.slots);
+    uint64_t* recs = chain + 3 * a.n_tiles;
 
     if (t == 0) s_tile_id = (int64_t)atomicAdd(a.ticket, 1ull);
     __syncthreads();
@@ -137,9 +113,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs
     if (run_base + RUN_BYTES > a.n) valid = run_base >= a.n ? 0ull : low_bits64((int)(a.n - run_base));
     if (run_base < a.begin) valid &= (a.begin - run_base >= 64) ? 0ull : ~low_bits64((int)(a.begin - run_base));
 
-    // header starts: '>' right after a newline (or at `begin`)
-    const bool fresh = a.prev == nullptr;  // `begin` is the start of the input (a line start)
-    const int prev = (fresh && run_base == a.begin) ? '\n' : (run_base > a.begin || !fresh ? tile_byte(run_base - 1) : 0);
+    // header starts: '>' right after a newline (or at `begin` of an unchained range)
+    const bool fresh = a.prev == nullptr;
+    const int prev = (fresh && run_base == a.begin) ? '\n' : ((run_base > a.begin || !fresh) ? tile_byte(run_base - 1) : 0);
     const uint64_t after_nl = (pm << 1) | (prev == '\n' ? 1ull : 0ull);
     uint64_t hs = gt & after_nl & valid;
     if (fresh && a.begin >= run_base && a.begin < run_base + RUN_BYTES) {  // the byte at `begin` starts a line
@@ -156,7 +132,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs
 
     // header spans that START in this run: from the '>' through the line's newline
     uint64_t hm = 0;
-    int tail_hdr = 0;  // line open at the end of the run is a header (only meaningful if the run has a newline or a header start)
+    int tail_hdr = 0;  // the line open at the end of the run is a header
     {
         uint64_t s = hs;
         while (s) {
@@ -174,12 +150,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs
     }
     const int cnt = __popcll(pm);
     const int first_nl = cnt ? __ffsll((long long)pm) - 1 : 64;
-    const uint64_t head_span = low_bits64(first_nl == 64 ? 64 : first_nl + 1);  // bytes of the carried-in line (incl. its newline)
-    // a header start inside the head region cannot exist (it needs a preceding newline) except at `begin`
-    const uint64_t base_keep = ~pm & ~crlf & ~hm & valid;
+    const uint64_t head_span = low_bits64(first_nl == 64 ? 64 : first_nl + 1);  // the carried-in line (incl. its newline)
+    uint64_t keep = ~pm & ~crlf & ~hm & valid;
 
-    // ---- resolve "carried-in line is a header" from the nearest earlier newline / header start in the tile
-    // a run changes the flag iff it contains a newline or a header start (hs at `begin` without newline)
+    // ---- "carried-in line is a header": nearest earlier run that contains a line start decides
     const bool sets_flag = cnt > 0 || hs != 0;
     const uint32_t setters = __ballot_sync(0xffffffffu, sets_flag);
     const uint32_t before = setters & ((1u << lane) - 1u);
@@ -189,93 +163,79 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs
     __syncwarp();
     if (setters && lane == 31 - __clz(setters)) s_warp_flag[warp] = tail_hdr;
     __syncthreads();
-    int f_in = -1;  // -1 unresolved (depends on the tile's carry-in)
+    if (t == 0) {
+        // publish this tile's record first (it depends on nobody), then resolve the carry from the predecessors'
+        int last = -1;
+        for (int w = 0; w < WARPS; w++)
+            if (s_warp_flag[w] >= 0) last = s_warp_flag[w];
+        __threadfence();
+        st_release_u64(&recs[tile], REC_VALID | (last >= 0 ? 2ull : 0ull) | (last > 0 ? 1ull : 0ull));
+        int carry = -1;
+        for (int64_t k = tile - 1; k >= 0 && carry < 0; k--) {
+            uint64_t w;
+            do {
+                w = ld_acquire_u64(&recs[k]);
+            } while (!(w & REC_VALID));
+            if (w & 2ull) carry = (int)(w & 1ull);
+        }
+        if (carry < 0) carry = a.prev ? (int)a.prev->tail_hdr : 0;
+        s_carry = carry;
+        if (a.prev && tile == 0) {
+            if (a.prev->err_pos != ~0ull) atomicMin(&a.result->err_pos, a.prev->err_pos);
+            if (a.prev->overflow) a.result->overflow = 1;
+        }
+    }
+    __syncthreads();
+    int f_in;
     if (before) f_in = src_flag;
-    else
+    else {
+        f_in = s_carry;
         for (int w = warp - 1; w >= 0; w--)
             if (s_warp_flag[w] >= 0) {
                 f_in = s_warp_flag[w];
                 break;
             }
-    uint64_t keep = base_keep;
-    uint32_t hkept = 0, hgc = 0;
-    if (f_in == 1) keep &= ~head_span;
-    else if (f_in < 0) {
-        hkept = (uint32_t)__popcll(keep & head_span);
-        hgc = (uint32_t)__popcll(keep & head_span & gm);
     }
+    if (f_in) keep &= ~head_span;
     const uint32_t n_hs = (uint32_t)__popcll(hs);
 
-    // ---- scans
-    const uint64_t packed = pack5(n_hs, (uint32_t)__popcll(keep), (uint32_t)__popcll(keep & gm), hkept, hgc);
+    // ---- scans of (records, kept bytes, G/C)
+    const uint64_t packed = pack3u(n_hs, (uint32_t)__popcll(keep), (uint32_t)__popcll(keep & gm));
     const uint64_t incl = warp_incl_scan_u64(packed);
     if (lane == 31) s_warp_tot[warp] = incl;
     __syncthreads();
-    // cross-warp sums can exceed 12 bits, so unpack per warp and add as ints
-    U5 ex = unpack5(incl - packed);
-    {
-        U5 o{0, 0, 0, 0, 0};
-        for (int w = 0; w < warp; w++) {
-            U5 u = unpack5(s_warp_tot[w]);
-            o.hs += u.hs; o.kept += u.kept; o.gc += u.gc; o.hkept += u.hkept; o.hgc += u.hgc;
+    uint64_t wsum = 0, tsum = 0;  // 20-bit fields: eight warps of <= 2048 each cannot overflow
+    for (int w = 0; w < WARPS; w++) {
+        if (w < warp) wsum += s_warp_tot[w];
+        tsum += s_warp_tot[w];
+    }
+    const U3 ex = unpack3u(wsum + incl - packed);
+    const U3 tot = unpack3u(tsum);
+    const uint64_t agg[3] = {(uint64_t)tot.hs, (uint64_t)tot.kept, (uint64_t)tot.gc};
+    const uint64_t init[3] = {a.prev ? a.prev->n_records : 0ull, a.prev ? a.prev->seq_bytes : 0ull, a.prev ? a.prev->gc_total : 0ull};
+    uint64_t excl[3];
+    block_lookback<3>(chain, tile, agg, init, excl, &s_lb);
+
+    if (tile == a.n_tiles - 1 && t == 0) {
+        const uint64_t n_hdr = excl[0] + tot.hs, seq = excl[1] + tot.kept, gc = excl[2] + tot.gc;
+        int last = s_carry;
+        for (int w = 0; w < WARPS; w++)
+            if (s_warp_flag[w] >= 0) last = s_warp_flag[w];
+        a.result->n_records = n_hdr;
+        a.result->seq_bytes = seq;
+        a.result->gc_total = gc;
+        a.result->tail_hdr = (uint64_t)last;
+        if ((int64_t)n_hdr <= a.rec_cap) {
+            a.seq_off[n_hdr] = (int64_t)seq;
+            a.gc_prefix[n_hdr] = (int64_t)gc;
+        } else {
+            a.result->overflow = 1;
         }
-        ex.hs += o.hs; ex.kept += o.kept; ex.gc += o.gc; ex.hkept += o.hkept; ex.hgc += o.hgc;
     }
 
-    if (t == 0) {
-        U5 tot{0, 0, 0, 0, 0};
-        int last_flag = -1;
-        for (int w = 0; w < WARPS; w++) {
-            U5 u = unpack5(s_warp_tot[w]);
-            tot.hs += u.hs; tot.kept += u.kept; tot.gc += u.gc; tot.hkept += u.hkept; tot.hgc += u.hgc;
-            if (s_warp_flag[w] >= 0) last_flag = s_warp_flag[w];
-        }
-        FaState agg;
-        agg.n_hdr = tot.hs;
-        agg.seq = tot.kept;
-        agg.gc = tot.gc;
-        agg.head_seq = tot.hkept;
-        agg.head_gc = tot.hgc;
-        agg.has_nl = last_flag >= 0;
-        agg.tail_hdr = last_flag > 0;
-        agg.pad = 0;
-        FaState init;
-        init.n_hdr = 0; init.seq = 0; init.gc = 0; init.head_seq = 0; init.head_gc = 0;
-        init.has_nl = 1; init.tail_hdr = 0; init.pad = 0;
-        if (a.prev && tile == 0) {
-            if (a.prev->err_pos != ~0ull) atomicMin(&a.result->err_pos, a.prev->err_pos);
-            if (a.prev->overflow) a.result->overflow = 1;
-            init.n_hdr = a.prev->n_records;
-            init.seq = a.prev->seq_bytes;
-            init.gc = a.prev->gc_total;
-            init.tail_hdr = (uint32_t)a.prev->tail_hdr;
-        }
-        FaState excl = lookback<FaState>(a.slots, tile, agg, init);
-        s_excl = excl;
-        if (tile == a.n_tiles - 1) {
-            FaState fin = FaState::combine(excl, agg);
-            a.result->n_records = fin.n_hdr;
-            a.result->seq_bytes = fin.seq;
-            a.result->gc_total = fin.gc;
-            a.result->tail_hdr = fin.tail_hdr;
-            if ((int64_t)fin.n_hdr <= a.rec_cap) {
-                a.seq_off[fin.n_hdr] = (int64_t)fin.seq;
-                a.gc_prefix[fin.n_hdr] = (int64_t)fin.gc;
-            } else {
-                a.result->overflow = 1;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- finalise with the tile's carry-in
-    const FaState excl = s_excl;
-    const bool carry_hdr = excl.tail_hdr != 0;
-    if (f_in < 0 && carry_hdr) keep &= ~head_span;
-    const int64_t my_hdr = (int64_t)excl.n_hdr + ex.hs;
-    const int64_t my_seq = (int64_t)excl.seq + ex.kept - (carry_hdr ? ex.hkept : 0);
-    const int64_t my_gc = (int64_t)excl.gc + ex.gc - (carry_hdr ? ex.hgc : 0);
-    const bool in_hdr_at_start = f_in < 0 ? carry_hdr : (f_in == 1);
+    const int64_t my_hdr = (int64_t)excl[0] + ex.hs;
+    const int64_t my_seq = (int64_t)excl[1] + ex.kept;
+    const int64_t my_gc = (int64_t)excl[2] + ex.gc;
 
     // record starts
     {
@@ -296,7 +256,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs
     }
     // header line terminators
     {
-        uint64_t hmask = hm | (in_hdr_at_start ? head_span : 0ull);
+        uint64_t hmask = hm | (f_in ? head_span : 0ull);
         uint64_t s = pm & hmask;
         while (s) {
             const int k = __ffsll((long long)s) - 1;
@@ -308,13 +268,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs
 
     // ---- compaction of the kept bytes
     if (kCompact) {
-        // tile's kept count and output base after resolving the carry
-        __shared__ int s_tile_kept;
-        if (t == BLOCK_THREADS - 1) s_tile_kept = (ex.kept + __popcll(keep)) - (carry_hdr ? ex.hkept : 0);
-        // NB: for the last thread ex.* are exclusive; its own head part is already removed from `keep`
-        const int64_t obase = (int64_t)excl.seq;
+        const int64_t obase = (int64_t)excl[1];
         const int shift = (int)(obase & 15);
-        int pos = shift + (int)(my_seq - obase);
+        int pos = shift + ex.kept;
         const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_tile);
         uint64_t m = keep;
         while (m) {
@@ -324,7 +280,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs
             s_out[pos++] = sb[swz(li >> 4) * 16 + (li & 15)];
         }
         __syncthreads();
-        const int total = s_tile_kept;
+        const int total = tot.kept;
         if (obase + total > a.seq_cap) {
             if (t == 0) a.result->overflow = 1;
         } else {

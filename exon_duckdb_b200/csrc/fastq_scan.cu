@@ -7,11 +7,18 @@
 //
 //   tile (16 KiB) -> shared memory (cp.async, swizzled)
 //   per thread: 64 contiguous bytes -> newline bitmask, signed byte sum, G/C mask
-//   warp scan + cross-warp totals   -> tile aggregate {newlines, open-line tail}
-//   decoupled look-back over tiles  -> global line index of every newline
+//   warp scan + cross-warp totals   -> tile aggregate = number of newlines
+//   block-wide decoupled look-back  -> global line index of every newline
 //   per newline: line length, G/C count (sequence lines), Phred sum (quality
 //   lines) as differences of prefix sums; FASTQ's strict 4-line phase
 //   (line index mod 4) disambiguates '@'/'+' inside quality strings.
+//
+// Only the newline COUNT is chained between tiles (one 64-bit word, status in
+// the top bits).  What a tile needs to finish the line that was open at its
+// start -- where that line began and its partial sums -- is purely local to
+// the predecessor that holds the line's start, so each tile publishes a
+// 32-byte "tail record" with no dependency on anybody and the one thread that
+// owns the tile's first newline reads its predecessor's record directly.
 //
 // Outputs are single-writer stores (no atomics except the rare error path):
 //   line_end[g]            position of the newline ending line g      (F_LINES)
@@ -23,31 +30,16 @@
 
 namespace exb {
 
-struct alignas(16) FqState {
-    uint64_t nl;         // newlines seen
-    int64_t line_start;  // absolute offset of the first byte of the open line
-    int64_t tail_s;      // signed byte sum of the open line so far
-    int64_t tail_g;      // G/C count of the open line so far
-    __device__ static FqState combine(const FqState& p, const FqState& t) {
-        FqState r;
-        r.nl = p.nl + t.nl;
-        if (t.nl > 0) {
-            r.line_start = t.line_start;
-            r.tail_s = t.tail_s;
-            r.tail_g = t.tail_g;
-        } else {
-            r.line_start = p.line_start;
-            r.tail_s = p.tail_s + t.tail_s;
-            r.tail_g = p.tail_g + t.tail_g;
-        }
-        return r;
-    }
+struct alignas(16) TailRec {  // the part of a tile after its last newline (the whole tile if it has none)
+    int64_t line_start;       // absolute offset of the byte after the tile's last newline
+    int64_t tail_s;           // signed byte sum of that part
+    int64_t tail_g;           // G/C count of that part
+    uint64_t has_nl;
 };
-static_assert(sizeof(FqState) == 32, "FqState");
 
 struct WarpLast {  // where the line open at the end of a warp's 2 KiB started
     int start_local;   // tile-local index of the byte after the warp's last newline
-    int a_s, a_g;      // tile-local prefix sums up to and including that newline
+    int a_s, a_g;      // warp-relative prefix sums up to and including that newline
     int valid;
 };
 
@@ -63,6 +55,41 @@ __device__ __forceinline__ void unpack3(uint64_t v, int& cnt, int& g, int& s) {
     cnt = (int)(rest >> 21);
 }
 
+__device__ __forceinline__ TailRec ld_rec(const TailRec* p) {
+    TailRec r;
+    uint4 a = ld_cg_u4(reinterpret_cast<const uint4*>(p));
+    uint4 b = ld_cg_u4(reinterpret_cast<const uint4*>(p) + 1);
+    r.line_start = (int64_t)(((uint64_t)a.y << 32) | a.x);
+    r.tail_s = (int64_t)(((uint64_t)a.w << 32) | a.z);
+    r.tail_g = (int64_t)(((uint64_t)b.y << 32) | b.x);
+    r.has_nl = ((uint64_t)b.w << 32) | b.z;
+    return r;
+}
+
+// State of the line that is open at the start of `tile`: walk the predecessors' tail
+// records back to the one that holds the line's start (usually tile-1).
+__device__ __forceinline__ void open_line_before(const TailRec* recs, int64_t tile, const FastqScanArgs& a, int64_t& start, int64_t& ts,
+                                                 int64_t& tg) {
+    ts = 0;
+    tg = 0;
+    for (int64_t k = tile - 1; k >= 0; k--) {
+        TailRec r = ld_rec(&recs[k]);
+        ts += r.tail_s;
+        tg += r.tail_g;
+        if (r.has_nl) {
+            start = r.line_start;
+            return;
+        }
+    }
+    if (a.prev) {
+        start = a.prev->open_line_start;
+        ts += a.prev->tail_s;
+        tg += a.prev->tail_g;
+    } else {
+        start = a.begin;
+    }
+}
+
 template <typename OffT, int FLAGS>
 __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs a) {
     constexpr bool kLines = (FLAGS & EXB_F_LINES) != 0;
@@ -72,14 +99,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
     __shared__ uint4 s_tile[TILE_CHUNKS];
     __shared__ uint64_t s_warp_tot[WARPS];
     __shared__ WarpLast s_warp_last[WARPS];
-    __shared__ FqState s_excl;
+    __shared__ LookbackSmem<1> s_lb;
     __shared__ int64_t s_tile_id;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint8_t* __restrict__ buf = a.buf;
     const int64_t origin = a.begin & ~(int64_t)15;
+    uint64_t* chain = reinterpret_cast<uint64_t*>(a.slots);
+    TailRec* recs = reinterpret_cast<TailRec*>(chain + ((a.n_tiles + 1) & ~(int64_t)1));
 
-    if (t == 0) s_tile_id = (int64_t)atomicAdd((unsigned long long*)a.ticket, 1ull);
+    if (t == 0) s_tile_id = (int64_t)atomicAdd(a.ticket, 1ull);
     __syncthreads();
     const int64_t tile = s_tile_id;
     const int64_t tile_base = origin + tile * TILE_BYTES;
@@ -104,13 +133,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
         }
         __syncthreads();
     }
-    auto tile_byte = [&](int64_t abs_pos) -> int {  // byte at an absolute offset (>= begin, < n+1)
+    const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(s_tile);
+    auto smem_byte = [&](int li) -> int { return sbytes[swz(li >> 4) * 16 + (li & 15)]; };
+    auto any_byte = [&](int64_t abs_pos) -> int {  // byte at an absolute offset that may lie before this tile
         int64_t li = abs_pos - tile_base;
-        if (li >= 0 && li < TILE_BYTES && (abs_pos < a.n || (a.is_final && abs_pos == a.n))) {
-            const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_tile);
-            return sb[swz((int)(li >> 4)) * 16 + (int)(li & 15)];
-        }
-        return (abs_pos >= (a.prev ? 0 : a.begin) && abs_pos < a.n) ? (int)buf[abs_pos] : -1;
+        if (li >= 0) return smem_byte((int)li);
+        return (abs_pos >= (a.prev ? 0 : a.begin)) ? (int)buf[abs_pos] : -1;
     };
 
     // ---- per-thread analysis of its 64-byte run
@@ -141,8 +169,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
     auto run_prefix_s = [&](int k) -> int {
         if (!kQual) return 0;
         int j = k >> 4;
-        int base = j == 0 ? 0 : (j == 1 ? cs0 : (j == 2 ? cs1 : (j == 3 ? cs2 : cs3)));
-        if (j >= 4) return base;
+        int base = j == 0 ? 0 : (j == 1 ? cs0 : (j == 2 ? cs1 : cs2));
         uint4 ch = s_tile[swz(4 * t + j)];
         return base + sbyte_sum_prefix16(ch, k & 15);
     };
@@ -171,80 +198,77 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
     }
     __syncthreads();
 
-    // ---- tile aggregate + look-back (thread 0), warp offsets (everyone)
+    // ---- tile totals, tail record, look-back of the newline count
     int off_cnt = 0, off_g = 0, off_s = 0;  // totals of the preceding warps
-    for (int w = 0; w < warp; w++) {
+    int tc = 0, tg = 0, ts = 0;             // tile totals
+    int lw = -1, lw_s = 0, lw_g = 0;        // last warp with a newline and the totals before it
+    for (int w = 0; w < WARPS; w++) {
+        if (w == warp) {
+            off_cnt = tc;
+            off_g = tg;
+            off_s = ts;
+        }
+        if (s_warp_last[w].valid) {
+            lw = w;
+            lw_s = ts;
+            lw_g = tg;
+        }
         int c_, g_, s_;
         unpack3(s_warp_tot[w], c_, g_, s_);
-        off_cnt += c_;
-        off_g += g_;
-        off_s += s_;
+        tc += c_;
+        tg += g_;
+        ts += s_;
     }
-    if (t == 0) {
-        int tc = 0, tg = 0, ts = 0;
-        int lw = -1, lw_s = 0, lw_g = 0;
-        for (int w = 0; w < WARPS; w++) {
-            if (s_warp_last[w].valid) {
-                lw = w;
-                lw_s = ts;
-                lw_g = tg;
-            }
-            int c_, g_, s_;
-            unpack3(s_warp_tot[w], c_, g_, s_);
-            tc += c_;
-            tg += g_;
-            ts += s_;
-        }
-        FqState agg;
-        agg.nl = (uint64_t)tc;
-        if (lw >= 0) {
-            agg.line_start = tile_base + s_warp_last[lw].start_local;
-            agg.tail_s = ts - (lw_s + s_warp_last[lw].a_s);
-            agg.tail_g = tg - (lw_g + s_warp_last[lw].a_g);
-        } else {
-            agg.line_start = 0;
-            agg.tail_s = ts;
-            agg.tail_g = tg;
-        }
+    TailRec mine;
+    mine.has_nl = lw >= 0;
+    if (lw >= 0) {
+        mine.line_start = tile_base + s_warp_last[lw].start_local;
+        mine.tail_s = ts - (lw_s + s_warp_last[lw].a_s);
+        mine.tail_g = tg - (lw_g + s_warp_last[lw].a_g);
+    } else {
+        mine.line_start = 0;
+        mine.tail_s = ts;
+        mine.tail_g = tg;
+    }
+    if (t == 0) {  // published by block_lookback's release (thread 0 stores, fences, then writes the chain word)
+        recs[tile] = mine;
         if (a.prev && tile == 0) {  // chained range: errors of earlier ranges stay visible in the last result
             if (a.prev->err_pos != ~0ull) atomicMin(&a.result->err_pos, a.prev->err_pos);
             if (a.prev->overflow) a.result->overflow = 1;
         }
-        FqState init;
-        if (a.prev && tile == 0) {
-            init.nl = a.prev->total_lines;
-            init.line_start = a.prev->open_line_start;
-            init.tail_s = a.prev->tail_s;
-            init.tail_g = a.prev->tail_g;
-        } else {
-            init.nl = 0;
-            init.line_start = a.begin;
-            init.tail_s = 0;
-            init.tail_g = 0;
-        }
-        FqState excl = lookback<FqState>(a.slots, tile, agg, init);
-        s_excl = excl;
-        if (tile == a.n_tiles - 1) {
-            FqState fin = FqState::combine(excl, agg);
-            a.result->total_lines = fin.nl;
-            a.result->open_line_start = fin.line_start;
-            a.result->tail_s = fin.tail_s;
-            a.result->tail_g = fin.tail_g;
-        }
     }
-    __syncthreads();
+    const uint64_t agg[1] = {(uint64_t)tc};
+    const uint64_t init[1] = {a.prev ? a.prev->total_lines : 0ull};
+    uint64_t excl[1];
+    block_lookback<1>(chain, tile, agg, init, excl, &s_lb);
+
+    if (tile == a.n_tiles - 1 && t == 0) {  // final state of this range (chaining / host)
+        int64_t st, s2, g2;
+        if (mine.has_nl) {
+            st = mine.line_start;
+            s2 = mine.tail_s;
+            g2 = mine.tail_g;
+        } else {
+            open_line_before(recs, tile, a, st, s2, g2);
+            s2 += mine.tail_s;
+            g2 += mine.tail_g;
+        }
+        a.result->total_lines = excl[0] + (uint64_t)tc;
+        a.result->open_line_start = st;
+        a.result->tail_s = s2;
+        a.result->tail_g = g2;
+    }
     if (cnt == 0) return;
 
     // ---- per-newline emission
-    const FqState excl = s_excl;
     const int tile_ex_s = off_s + ex_s, tile_ex_g = off_g + ex_g;
-    uint64_t g = excl.nl + (uint64_t)(off_cnt + ex_cnt);  // global index of my first line end
+    uint64_t g = excl[0] + (uint64_t)(off_cnt + ex_cnt);  // global index of my first line end
 
     int64_t cur_start, cur_as, cur_ag;  // the line open at the start of my run
     {
         const uint32_t before = has & ((1u << lane) - 1u);
         const int src = before ? 31 - __clz(before) : lane;
-        // all lanes with newlines reach here; lanes without returned above, so use the mask of live lanes
+        // lanes without newlines returned above: `has` is exactly the mask of live lanes
         int st = __shfl_sync(has, my_start, src);
         int as_ = __shfl_sync(has, my_as, src);
         int ag_ = __shfl_sync(has, my_ag, src);
@@ -266,15 +290,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
                 cur_start = tile_base + s_warp_last[w].start_local;
                 cur_as = ws + s_warp_last[w].a_s;
                 cur_ag = wg + s_warp_last[w].a_g;
-            } else {
-                cur_start = excl.line_start;
-                cur_as = -excl.tail_s;
-                cur_ag = -excl.tail_g;
+            } else {  // my first newline closes the line that was open when the tile began
+                int64_t st0, s0, g0;
+                open_line_before(recs, tile, a, st0, s0, g0);
+                cur_start = st0;
+                cur_as = -s0;
+                cur_ag = -g0;
             }
         }
     }
 
-    const int64_t run_base = tile_base + (int64_t)t * RUN_BYTES;
+    const int run0 = t * RUN_BYTES;
+    const int64_t run_base = tile_base + run0;
     uint64_t m = pm;
     while (m) {
         const int k = __ffsll((long long)m) - 1;
@@ -284,8 +311,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
         const int64_t pg = tile_ex_g + run_prefix_g(k);
         if (g < a.max_lines) {
             int64_t len = e - cur_start;
-            // the virtual '\n' at EOF strips no '\r' (read_line only strips CR before a real LF)
-            const int cr = (len > 0 && !(a.is_final && e == a.n) && tile_byte(e - 1) == '\r') ? 1 : 0;
+            // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing
+            int cr = 0;
+            if (len > 0 && !(a.is_final && e == a.n)) cr = (run0 + k > 0 ? smem_byte(run0 + k - 1) : any_byte(e - 1)) == '\r';
             len -= cr;
             const int ph = (int)(g & 3);
             const uint64_t r = g >> 2;
@@ -295,10 +323,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
                 else
                     a.result->overflow = 1;
             }
-            if (ph == 0) {
-                if (tile_byte(cur_start) != '@') atomicMin((unsigned long long*)&a.result->err_pos, (unsigned long long)cur_start);
-            } else if (ph == 2) {
-                if (tile_byte(cur_start) != '+') atomicMin((unsigned long long*)&a.result->err_pos, (unsigned long long)cur_start);
+            if ((ph & 1) == 0) {  // header / plus line: its first byte must be '@' / '+'
+                if (any_byte(cur_start) != (ph == 0 ? '@' : '+')) atomicMin(&a.result->err_pos, (unsigned long long)cur_start);
             } else if (r < (uint64_t)a.rec_cap) {
                 if (ph == 1) {
                     if (kSeq) {

@@ -115,13 +115,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) exclusive_scan_kernel(const T* 
         if (w < warp) woff += s_warp[w];
         tot += s_warp[w];
     }
-    if (t == 0) {
-        SumState excl = lookback<SumState>(slots, tile, SumState{(int64_t)tot, 0}, SumState{0, 0});
-        s_excl = excl.sum;
-        if (tile == n_tiles - 1) out[n] = excl.sum + (int64_t)tot;
-    }
-    __syncthreads();
-    int64_t run = s_excl + (int64_t)(woff + incl - loc);
+    __shared__ LookbackSmem<1> s_lb;
+    const uint64_t agg[1] = {tot}, init[1] = {0};
+    uint64_t excl[1];
+    block_lookback<1>(reinterpret_cast<uint64_t*>(slots), tile, agg, init, excl, &s_lb);
+    if (t == 0 && tile == n_tiles - 1) out[n] = (int64_t)(excl[0] + tot);
+    (void)s_excl;
+    int64_t run = (int64_t)excl[0] + (int64_t)(woff + incl - loc);
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
         if (base + i < n) out[base + i] = run;
