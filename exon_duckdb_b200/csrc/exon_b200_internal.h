@@ -6,6 +6,11 @@
 
 #include "../../include/exon_b200.h"
 
+// 16 KiB sub-tiles per CTA tile of the FASTQ scan (tuning knob; <= 4 because event positions are 16 bit)
+#ifndef EXB_FASTQ_SUBS
+#define EXB_FASTQ_SUBS 2
+#endif
+
 namespace exb {
 
 struct TileSlot;

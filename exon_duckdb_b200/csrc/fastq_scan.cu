@@ -3,22 +3,25 @@
 // Replaces the record loop of noodles-fastq 0.8 Reader::read_record as driven
 // by exon 0.2.6's FASTQ batch reader (call sites: rust/src/arrow_reader.rs:
 // 104-118,125-153 in the reference).  Instead of reading a
-// record at a time it reads every input byte exactly once:
+// record at a time it reads every input byte exactly once.
 //
-//   tile (16 KiB) -> shared memory (cp.async, swizzled)
-//   per thread: 64 contiguous bytes -> newline bitmask, signed byte sum, G/C mask
-//   warp scan + cross-warp totals   -> tile aggregate = number of newlines
-//   block-wide decoupled look-back  -> global line index of every newline
-//   per newline: line length, G/C count (sequence lines), Phred sum (quality
-//   lines) as differences of prefix sums; FASTQ's strict 4-line phase
-//   (line index mod 4) disambiguates '@'/'+' inside quality strings.
+// One CTA (256 threads) owns a tile of SUBS x 16 KiB staged in shared memory
+// (cp.async, XOR-swizzled).  Three phases:
 //
-// Only the newline COUNT is chained between tiles (one 64-bit word, status in
-// the top bits).  What a tile needs to finish the line that was open at its
-// start -- where that line began and its partial sums -- is purely local to
-// the predecessor that holds the line's start, so each tile publishes a
-// 32-byte "tail record" with no dependency on anybody and the one thread that
-// owns the tile's first newline reads its predecessor's record directly.
+//  A. analysis (byte-parallel, branch-free): thread t owns the 64 contiguous
+//     bytes [t*64, t*64+64) of each 16 KiB sub-tile -> 64-bit newline mask,
+//     signed byte sum, G/C mask; one packed warp scan + an 8-entry cross-warp
+//     scan give every run its tile-level prefix (newlines, byte sum, G/C).
+//     Newline positions are scattered, in order, into an event list.
+//  B. chaining: only the newline COUNT is chained between tiles (one 64-bit
+//     word, status in the top bits, block-wide decoupled look-back).  What a
+//     tile needs to finish the line that was open at its start is local to the
+//     predecessor holding that line's start, which publishes a 32-byte tail
+//     record with no dependency on anybody.
+//  C. emission (event-parallel): one newline per lane.  Line length, G/C count
+//     (sequence lines) and Phred sum (quality lines) are differences of the
+//     prefix sums at consecutive newlines; FASTQ's strict 4-line phase (global
+//     line index mod 4) disambiguates '@'/'+' inside quality strings.
 //
 // Outputs are single-writer stores (no atomics except the rare error path):
 //   line_end[g]            position of the newline ending line g      (F_LINES)
@@ -30,6 +33,8 @@
 
 namespace exb {
 
+constexpr int SUB_BYTES = TILE_BYTES;  // 16 KiB analysed per pass of the 256 threads
+
 struct alignas(16) TailRec {  // the part of a tile after its last newline (the whole tile if it has none)
     int64_t line_start;       // absolute offset of the byte after the tile's last newline
     int64_t tail_s;           // signed byte sum of that part
@@ -37,22 +42,22 @@ struct alignas(16) TailRec {  // the part of a tile after its last newline (the 
     uint64_t has_nl;
 };
 
-struct WarpLast {  // where the line open at the end of a warp's 2 KiB started
-    int start_local;   // tile-local index of the byte after the warp's last newline
-    int a_s, a_g;      // warp-relative prefix sums up to and including that newline
+struct WarpLast {  // the last newline inside a warp's 2 KiB
+    int start_local;  // tile-local index of the byte after it
+    int a_s, a_g;     // warp-relative prefix sums up to and including it
     int valid;
 };
 
-// packed (count, gc, signed sum) in one 64-bit lane value: 21 bits each
+// packed (count, gc, signed sum): 18 + 18 + 24 bits
 __device__ __forceinline__ uint64_t pack3(int cnt, int g, int s) {
-    return ((uint64_t)cnt << 42) + ((uint64_t)g << 21) + (uint64_t)(int64_t)s;
+    return ((uint64_t)cnt << 42) + ((uint64_t)g << 24) + (uint64_t)(int64_t)s;
 }
 __device__ __forceinline__ void unpack3(uint64_t v, int& cnt, int& g, int& s) {
-    int64_t sv = ((int64_t)(v << 43)) >> 43;  // sign-extend low 21 bits
-    uint64_t rest = (v - (uint64_t)sv) >> 21;
+    int64_t sv = ((int64_t)(v << 40)) >> 40;  // sign-extend low 24 bits
+    uint64_t rest = (v - (uint64_t)sv) >> 24;
     s = (int)sv;
-    g = (int)(rest & 0x1FFFFFu);
-    cnt = (int)(rest >> 21);
+    g = (int)(rest & 0x3FFFFu);
+    cnt = (int)(rest >> 18);
 }
 
 __device__ __forceinline__ TailRec ld_rec(const TailRec* p) {
@@ -68,8 +73,8 @@ __device__ __forceinline__ TailRec ld_rec(const TailRec* p) {
 
 // State of the line that is open at the start of `tile`: walk the predecessors' tail
 // records back to the one that holds the line's start (usually tile-1).
-__device__ __forceinline__ void open_line_before(const TailRec* recs, int64_t tile, const FastqScanArgs& a, int64_t& start, int64_t& ts,
-                                                 int64_t& tg) {
+__device__ __noinline__ void open_line_before(const TailRec* recs, int64_t tile, const FastqScanArgs& a, int64_t& start, int64_t& ts,
+                                              int64_t& tg) {
     ts = 0;
     tg = 0;
     for (int64_t k = tile - 1; k >= 0; k--) {
@@ -90,17 +95,58 @@ __device__ __forceinline__ void open_line_before(const TailRec* recs, int64_t ti
     }
 }
 
-template <typename OffT, int FLAGS>
-__global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs a) {
-    constexpr bool kLines = (FLAGS & EXB_F_LINES) != 0;
-    constexpr bool kSeq = (FLAGS & EXB_F_SEQ) != 0;
-    constexpr bool kQual = (FLAGS & EXB_F_QUAL) != 0;
+// 16-bit equality mask of a 16-byte chunk, bits in byte order.  The 0x80 flags of two
+// words are folded into one byte by IDP.4A with weights 1,2,4,8 / 16,32,64,128 (the
+// products carry a factor 128 that one shift removes): 4 IDP + 2 ops instead of 12.
+__device__ __forceinline__ uint32_t flags_to_mask16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    uint32_t lo = __dp4a(m0, 0x08040201u, 0u);
+    lo = __dp4a(m1, 0x80402010u, lo);
+    uint32_t hi = __dp4a(m2, 0x08040201u, 0u);
+    hi = __dp4a(m3, 0x80402010u, hi);
+    return (lo >> 7) | (hi << 1);
+}
+__device__ __forceinline__ uint32_t nl_mask16(const uint4& v) {
+    return flags_to_mask16(eq_bytes(v.x, 0x0A0A0A0Au), eq_bytes(v.y, 0x0A0A0A0Au), eq_bytes(v.z, 0x0A0A0A0Au), eq_bytes(v.w, 0x0A0A0A0Au));
+}
+__device__ __forceinline__ uint32_t gc_mask16b(const uint4& v) {
+    return flags_to_mask16(gc_bytes(v.x), gc_bytes(v.y), gc_bytes(v.z), gc_bytes(v.w));
+}
 
-    __shared__ uint4 s_tile[TILE_CHUNKS];
+template <int FLAGS, int SUBS>
+struct FqSmem {
+    static constexpr bool kSeq = (FLAGS & EXB_F_SEQ) != 0, kQual = (FLAGS & EXB_F_QUAL) != 0;
+    static constexpr int EV_CAP = 512 * SUBS;
+    static constexpr int off_data = 0;
+    static constexpr int off_sexcl = off_data + SUBS * SUB_BYTES;
+    static constexpr int off_gexcl = off_sexcl + (kQual ? SUBS * BLOCK_THREADS * 4 : 0);
+    static constexpr int off_gm = off_gexcl + (kSeq ? SUBS * BLOCK_THREADS * 4 : 0);
+    static constexpr int off_evps = off_gm + (kSeq ? SUBS * BLOCK_THREADS * 8 : 0);
+    static constexpr int off_evpg = off_evps + (kQual ? EV_CAP * 4 : 0);
+    static constexpr int off_evpos = off_evpg + (kSeq ? EV_CAP * 4 : 0);
+    static constexpr int total = off_evpos + EV_CAP * 2;
+};
+
+template <typename OffT, int FLAGS, int SUBS>
+__global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs a) {
+    using SM = FqSmem<FLAGS, SUBS>;
+    constexpr bool kLines = (FLAGS & EXB_F_LINES) != 0;
+    constexpr bool kSeq = SM::kSeq, kQual = SM::kQual;
+    constexpr int TILE = SUBS * SUB_BYTES;
+    constexpr int EV_CAP = SM::EV_CAP;
+
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint4* s_data = reinterpret_cast<uint4*>(smem + SM::off_data);
+    int* s_sexcl = reinterpret_cast<int*>(smem + SM::off_sexcl);
+    int* s_gexcl = reinterpret_cast<int*>(smem + SM::off_gexcl);
+    uint64_t* s_gm = reinterpret_cast<uint64_t*>(smem + SM::off_gm);
+    int* ev_ps = reinterpret_cast<int*>(smem + SM::off_evps);
+    int* ev_pg = reinterpret_cast<int*>(smem + SM::off_evpg);
+    uint16_t* ev_pos = reinterpret_cast<uint16_t*>(smem + SM::off_evpos);
     __shared__ uint64_t s_warp_tot[WARPS];
     __shared__ WarpLast s_warp_last[WARPS];
     __shared__ LookbackSmem<1> s_lb;
     __shared__ int64_t s_tile_id;
+    __shared__ int s_batch_carry[3];  // last event of the previous batch: pos, ps (incl. newline), pg
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint8_t* __restrict__ buf = a.buf;
@@ -111,209 +157,205 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
     if (t == 0) s_tile_id = (int64_t)atomicAdd(a.ticket, 1ull);
     __syncthreads();
     const int64_t tile = s_tile_id;
-    const int64_t tile_base = origin + tile * TILE_BYTES;
+    const int64_t tile_base = origin + tile * TILE;
 
-    stage_tile(s_tile, buf, tile_base, origin, a.n);
+#pragma unroll
+    for (int s = 0; s < SUBS; s++) stage_tile(s_data + s * TILE_CHUNKS, buf, tile_base + (int64_t)s * SUB_BYTES, origin, a.n);
     cp_async_wait<0>();
     __syncthreads();
+
+    uint8_t* sbytes = reinterpret_cast<uint8_t*>(s_data);
+    // tile-local byte index -> shared memory byte (the swizzle permutes chunks inside a sub-tile only)
+    auto sidx = [](int li) -> int { return ((li >> 14) << 14) + swz((li >> 4) & (TILE_CHUNKS - 1)) * 16 + (li & 15); };
 
     // Rare per-launch patches (uniform per CTA): bytes before `begin` in the first
     // chunk are filler; an unterminated last line gets a virtual '\n' at index n.
     const bool has_begin_pad = (tile == 0 && a.begin != origin);
-    const bool has_eof = a.is_final && (a.n >= tile_base && a.n < tile_base + TILE_BYTES);
+    const bool has_eof = a.is_final && (a.n >= tile_base && a.n < tile_base + TILE);
     if (has_begin_pad || has_eof) {
         if (t == 0) {
-            uint8_t* sb = reinterpret_cast<uint8_t*>(s_tile);
             if (has_begin_pad)
-                for (int64_t i = origin; i < a.begin; i++) sb[swz(0) * 16 + (int)(i - origin)] = 0;
-            if (has_eof && a.n > a.begin && buf[a.n - 1] != '\n') {
-                int li = (int)(a.n - tile_base);
-                sb[swz(li >> 4) * 16 + (li & 15)] = '\n';
-            }
+                for (int64_t i = origin; i < a.begin; i++) sbytes[sidx((int)(i - origin))] = 0;
+            if (has_eof && a.n > a.begin && buf[a.n - 1] != '\n') sbytes[sidx((int)(a.n - tile_base))] = '\n';
         }
         __syncthreads();
     }
-    const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(s_tile);
-    auto smem_byte = [&](int li) -> int { return sbytes[swz(li >> 4) * 16 + (li & 15)]; };
-    auto any_byte = [&](int64_t abs_pos) -> int {  // byte at an absolute offset that may lie before this tile
+    auto any_byte = [&](int64_t abs_pos) -> int {  // byte at an absolute offset < tile end that may lie before this tile
         int64_t li = abs_pos - tile_base;
-        if (li >= 0) return smem_byte((int)li);
+        if (li >= 0) return sbytes[sidx((int)li)];
         return (abs_pos >= (a.prev ? 0 : a.begin)) ? (int)buf[abs_pos] : -1;
     };
 
-    // ---- per-thread analysis of its 64-byte run
-    uint64_t pm = 0, gm = 0;
-    int cs0 = 0, cs1 = 0, cs2 = 0, cs3 = 0;
-    {
-        uint4 c0 = s_tile[swz(4 * t + 0)], c1 = s_tile[swz(4 * t + 1)];
-        uint4 c2 = s_tile[swz(4 * t + 2)], c3 = s_tile[swz(4 * t + 3)];
-        uint32_t lo = eq_mask16(c0, 0x0A0A0A0Au) | (eq_mask16(c1, 0x0A0A0A0Au) << 16);
-        uint32_t hi = eq_mask16(c2, 0x0A0A0A0Au) | (eq_mask16(c3, 0x0A0A0A0Au) << 16);
-        pm = ((uint64_t)hi << 32) | lo;
-        if (kSeq) {
-            uint32_t glo = gc_mask16(c0) | (gc_mask16(c1) << 16);
-            uint32_t ghi = gc_mask16(c2) | (gc_mask16(c3) << 16);
-            gm = ((uint64_t)ghi << 32) | glo;
+    // ---- A. analysis of the SUBS sub-tiles; scatters the events with rank in [win_lo, win_lo + EV_CAP)
+    int total_cnt = 0, total_s = 0, total_g = 0;
+    int last_start = -1, last_as = 0, last_ag = 0;  // after the tile's last newline: tile-local start, prefixes incl. that newline
+    auto analyse = [&](int win_lo) {
+        total_cnt = total_s = total_g = 0;
+        last_start = -1;
+#pragma unroll 1
+        for (int s = 0; s < SUBS; s++) {
+            const uint4* d = s_data + s * TILE_CHUNKS;
+            uint64_t pm, gm = 0;
+            int cs0 = 0, cs1 = 0, cs2 = 0, cs3 = 0;
+            {
+                uint4 c0 = d[swz(4 * t + 0)], c1 = d[swz(4 * t + 1)], c2 = d[swz(4 * t + 2)], c3 = d[swz(4 * t + 3)];
+                pm = ((uint64_t)(nl_mask16(c2) | (nl_mask16(c3) << 16)) << 32) | (nl_mask16(c0) | (nl_mask16(c1) << 16));
+                if (kSeq) gm = ((uint64_t)(gc_mask16b(c2) | (gc_mask16b(c3) << 16)) << 32) | (gc_mask16b(c0) | (gc_mask16b(c1) << 16));
+                if (kQual) {
+                    cs0 = sbyte_sum16(c0, 0);
+                    cs1 = sbyte_sum16(c1, cs0);
+                    cs2 = sbyte_sum16(c2, cs1);
+                    cs3 = sbyte_sum16(c3, cs2);
+                }
+            }
+            const int cnt = __popcll(pm);
+            const int gtot = kSeq ? __popcll(gm) : 0;
+            const uint64_t packed = pack3(cnt, gtot, cs3);
+            const uint64_t incl = warp_incl_scan_u64(packed);
+            if (lane == 31) s_warp_tot[warp] = incl;
+            int ex_cnt, ex_g, ex_s;  // warp-relative exclusive prefix of this run
+            unpack3(incl - packed, ex_cnt, ex_g, ex_s);
+            const uint32_t has = __ballot_sync(0xffffffffu, cnt > 0);
+            if (has == 0) {
+                if (lane == 0) s_warp_last[warp].valid = 0;
+            } else if (lane == 31 - __clz(has)) {
+                const int k = 63 - __clzll((long long)pm);
+                int as_ = 0;
+                if (kQual) {
+                    const int j = k >> 4;
+                    as_ = ex_s + (j == 0 ? 0 : (j == 1 ? cs0 : (j == 2 ? cs1 : cs2))) + sbyte_sum_prefix16(d[swz(4 * t + j)], k & 15) + 10;
+                }
+                s_warp_last[warp] = WarpLast{s * SUB_BYTES + t * RUN_BYTES + k + 1, as_, kSeq ? ex_g + __popcll(gm & low_bits64(k)) : 0, 1};
+            }
+            __syncthreads();
+            // cross-warp exclusive scan of the 8 warp totals (every warp does it redundantly in its low lanes)
+            uint64_t wt = lane < WARPS ? s_warp_tot[lane] : 0ull;
+            uint64_t wincl = wt;
+#pragma unroll
+            for (int dd = 1; dd < WARPS; dd <<= 1) {
+                uint64_t o = __shfl_up_sync(0xffffffffu, wincl, dd);
+                if (lane >= dd) wincl += o;
+            }
+            const uint64_t wex = __shfl_sync(0xffffffffu, wincl - wt, warp);
+            const uint64_t wtot = __shfl_sync(0xffffffffu, wincl, WARPS - 1);
+            const int lvalid = lane < WARPS ? s_warp_last[lane].valid : 0;
+            const uint32_t vmask = __ballot_sync(0xffffffffu, lvalid != 0);
+            int off_cnt, off_g, off_s, sc, sg, ss;
+            unpack3(wex, off_cnt, off_g, off_s);
+            unpack3(wtot, sc, sg, ss);
+            const int run = s * BLOCK_THREADS + t;
+            const int my_cnt = total_cnt + off_cnt + ex_cnt;
+            if (kQual) s_sexcl[run] = total_s + off_s + ex_s;
+            if (kSeq) {
+                s_gexcl[run] = total_g + off_g + ex_g;
+                s_gm[run] = gm;
+            }
+            {  // events of this run, in order
+                int rank = my_cnt - win_lo;
+                uint64_t m = pm;
+                const int p0 = s * SUB_BYTES + t * RUN_BYTES;
+                while (m) {
+                    const int k = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if ((unsigned)rank < (unsigned)EV_CAP) ev_pos[rank] = (uint16_t)(p0 + k);
+                    rank++;
+                }
+            }
+            if (vmask) {  // the sub-tile's last newline (uniform)
+                const int lw = 31 - __clz(vmask);
+                const uint64_t before = __shfl_sync(0xffffffffu, wincl - wt, lw);
+                int bc, bg, bs;
+                unpack3(before, bc, bg, bs);
+                last_start = s_warp_last[lw].start_local;
+                last_as = total_s + bs + s_warp_last[lw].a_s;
+                last_ag = total_g + bg + s_warp_last[lw].a_g;
+            }
+            total_cnt += sc;
+            total_s += ss;
+            total_g += sg;
+            __syncthreads();
         }
-        if (kQual) {
-            cs0 = sbyte_sum16(c0, 0);
-            cs1 = sbyte_sum16(c1, cs0);
-            cs2 = sbyte_sum16(c2, cs1);
-            cs3 = sbyte_sum16(c3, cs2);
-        }
-    }
-    const int cnt = __popcll(pm);
-    const int gtot = kSeq ? __popcll(gm) : 0;
-
-    // prefix sums inside the run: signed byte sum / G/C count of run bytes [0, k)
-    auto run_prefix_s = [&](int k) -> int {
-        if (!kQual) return 0;
-        int j = k >> 4;
-        int base = j == 0 ? 0 : (j == 1 ? cs0 : (j == 2 ? cs1 : cs2));
-        uint4 ch = s_tile[swz(4 * t + j)];
-        return base + sbyte_sum_prefix16(ch, k & 15);
     };
-    auto run_prefix_g = [&](int k) -> int { return kSeq ? __popcll(gm & low_bits64(k)) : 0; };
+    analyse(0);
 
-    // ---- warp scan of (newlines, G/C, byte sum)
-    const uint64_t packed = pack3(cnt, gtot, cs3);
-    const uint64_t incl = warp_incl_scan_u64(packed);
-    if (lane == 31) s_warp_tot[warp] = incl;
-    int ex_cnt, ex_g, ex_s;  // warp-relative exclusive prefix of this thread
-    unpack3(incl - packed, ex_cnt, ex_g, ex_s);
-
-    // line-start info after this thread's last newline (warp-relative sums)
-    const uint32_t has = __ballot_sync(0xffffffffu, cnt > 0);
-    int my_start = 0, my_as = 0, my_ag = 0;
-    if (cnt > 0) {
-        int k = 63 - __clzll((long long)pm);
-        my_start = t * RUN_BYTES + k + 1;
-        my_as = ex_s + run_prefix_s(k) + (kQual ? 10 : 0);
-        my_ag = ex_g + run_prefix_g(k);
-    }
-    if (has == 0) {
-        if (lane == 0) s_warp_last[warp].valid = 0;
-    } else if (lane == 31 - __clz(has)) {
-        s_warp_last[warp] = WarpLast{my_start, my_as, my_ag, 1};  // sums still warp-relative
-    }
-    __syncthreads();
-
-    // ---- tile totals, tail record, look-back of the newline count
-    int off_cnt = 0, off_g = 0, off_s = 0;  // totals of the preceding warps
-    int tc = 0, tg = 0, ts = 0;             // tile totals
-    int lw = -1, lw_s = 0, lw_g = 0;        // last warp with a newline and the totals before it
-    for (int w = 0; w < WARPS; w++) {
-        if (w == warp) {
-            off_cnt = tc;
-            off_g = tg;
-            off_s = ts;
-        }
-        if (s_warp_last[w].valid) {
-            lw = w;
-            lw_s = ts;
-            lw_g = tg;
-        }
-        int c_, g_, s_;
-        unpack3(s_warp_tot[w], c_, g_, s_);
-        tc += c_;
-        tg += g_;
-        ts += s_;
-    }
+    // ---- B. tail record + look-back of the newline count
     TailRec mine;
-    mine.has_nl = lw >= 0;
-    if (lw >= 0) {
-        mine.line_start = tile_base + s_warp_last[lw].start_local;
-        mine.tail_s = ts - (lw_s + s_warp_last[lw].a_s);
-        mine.tail_g = tg - (lw_g + s_warp_last[lw].a_g);
-    } else {
-        mine.line_start = 0;
-        mine.tail_s = ts;
-        mine.tail_g = tg;
-    }
-    if (t == 0) {  // published by block_lookback's release (thread 0 stores, fences, then writes the chain word)
+    mine.has_nl = last_start >= 0;
+    mine.line_start = last_start >= 0 ? tile_base + last_start : 0;
+    mine.tail_s = last_start >= 0 ? total_s - last_as : total_s;
+    mine.tail_g = last_start >= 0 ? total_g - last_ag : total_g;
+    if (t == 0) {  // made visible by block_lookback's release (thread 0 stores, fences, then writes the chain word)
         recs[tile] = mine;
         if (a.prev && tile == 0) {  // chained range: errors of earlier ranges stay visible in the last result
             if (a.prev->err_pos != ~0ull) atomicMin(&a.result->err_pos, a.prev->err_pos);
             if (a.prev->overflow) a.result->overflow = 1;
         }
     }
-    const uint64_t agg[1] = {(uint64_t)tc};
+    const uint64_t agg[1] = {(uint64_t)total_cnt};
     const uint64_t init[1] = {a.prev ? a.prev->total_lines : 0ull};
     uint64_t excl[1];
     block_lookback<1>(chain, tile, agg, init, excl, &s_lb);
 
     if (tile == a.n_tiles - 1 && t == 0) {  // final state of this range (chaining / host)
-        int64_t st, s2, g2;
-        if (mine.has_nl) {
-            st = mine.line_start;
-            s2 = mine.tail_s;
-            g2 = mine.tail_g;
-        } else {
+        int64_t st = mine.line_start, s2 = mine.tail_s, g2 = mine.tail_g;
+        if (!mine.has_nl) {
             open_line_before(recs, tile, a, st, s2, g2);
             s2 += mine.tail_s;
             g2 += mine.tail_g;
         }
-        a.result->total_lines = excl[0] + (uint64_t)tc;
+        a.result->total_lines = excl[0] + (uint64_t)total_cnt;
         a.result->open_line_start = st;
         a.result->tail_s = s2;
         a.result->tail_g = g2;
     }
-    if (cnt == 0) return;
 
-    // ---- per-newline emission
-    const int tile_ex_s = off_s + ex_s, tile_ex_g = off_g + ex_g;
-    uint64_t g = excl[0] + (uint64_t)(off_cnt + ex_cnt);  // global index of my first line end
-
-    int64_t cur_start, cur_as, cur_ag;  // the line open at the start of my run
-    {
-        const uint32_t before = has & ((1u << lane) - 1u);
-        const int src = before ? 31 - __clz(before) : lane;
-        // lanes without newlines returned above: `has` is exactly the mask of live lanes
-        int st = __shfl_sync(has, my_start, src);
-        int as_ = __shfl_sync(has, my_as, src);
-        int ag_ = __shfl_sync(has, my_ag, src);
-        if (before) {
-            cur_start = tile_base + st;
-            cur_as = off_s + as_;
-            cur_ag = off_g + ag_;
-        } else {
-            int w = warp - 1;
-            while (w >= 0 && !s_warp_last[w].valid) w--;
-            if (w >= 0) {
-                int ws = 0, wg = 0;
-                for (int i = 0; i < w; i++) {
-                    int c_, g_, s_;
-                    unpack3(s_warp_tot[i], c_, g_, s_);
-                    ws += s_;
-                    wg += g_;
+    // ---- C. emission, one newline per lane
+    const int n_events = total_cnt;
+    for (int lo = 0; lo < n_events; lo += EV_CAP) {
+        if (lo > 0) analyse(lo);  // newline-dense tile: refill the event window (rare)
+        const int nev = min(EV_CAP, n_events - lo);
+        if (kQual || kSeq) {
+            for (int i = t; i < nev; i += BLOCK_THREADS) {  // prefix sums at my newline
+                const int pos = ev_pos[i];
+                const int run = pos >> 6, k = pos & 63;
+                if (kQual) {
+                    const uint4* d = s_data + (run >> 8) * TILE_CHUNKS;
+                    const int q = 4 * (run & 255);
+                    int ps = s_sexcl[run];
+                    const int j = k >> 4;
+                    if (j > 0) ps = sbyte_sum16(d[swz(q)], ps);
+                    if (j > 1) ps = sbyte_sum16(d[swz(q + 1)], ps);
+                    if (j > 2) ps = sbyte_sum16(d[swz(q + 2)], ps);
+                    ev_ps[i] = ps + sbyte_sum_prefix16(d[swz(q + j)], k & 15);
                 }
-                cur_start = tile_base + s_warp_last[w].start_local;
-                cur_as = ws + s_warp_last[w].a_s;
-                cur_ag = wg + s_warp_last[w].a_g;
-            } else {  // my first newline closes the line that was open when the tile began
+                if (kSeq) ev_pg[i] = s_gexcl[run] + __popcll(s_gm[run] & low_bits64(k));
+            }
+            __syncthreads();
+        }
+        for (int i = t; i < nev; i += BLOCK_THREADS) {
+            const uint64_t g = excl[0] + (uint64_t)(lo + i);  // global index of the line this newline ends
+            if (g >= a.max_lines) continue;
+            const int pos = ev_pos[i];
+            const int64_t e = tile_base + pos;
+            long long len, ssum = 0, gsum = 0;
+            int first_byte;  // first byte of the line
+            if (i > 0 || lo > 0) {
+                const int ppos = i > 0 ? (int)ev_pos[i - 1] : s_batch_carry[0];
+                len = pos - ppos - 1;
+                if (kQual) ssum = ev_ps[i] - (i > 0 ? ev_ps[i - 1] + 10 : s_batch_carry[1]);
+                if (kSeq) gsum = ev_pg[i] - (i > 0 ? ev_pg[i - 1] : s_batch_carry[2]);
+                first_byte = sbytes[sidx(ppos + 1)];
+            } else {  // the line that was open when the tile began
                 int64_t st0, s0, g0;
                 open_line_before(recs, tile, a, st0, s0, g0);
-                cur_start = st0;
-                cur_as = -s0;
-                cur_ag = -g0;
+                len = e - st0;
+                if (kQual) ssum = ev_ps[i] + s0;
+                if (kSeq) gsum = ev_pg[i] + g0;
+                first_byte = any_byte(st0);
             }
-        }
-    }
-
-    const int run0 = t * RUN_BYTES;
-    const int64_t run_base = tile_base + run0;
-    uint64_t m = pm;
-    while (m) {
-        const int k = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const int64_t e = run_base + k;  // absolute position of this newline
-        const int64_t ps = tile_ex_s + run_prefix_s(k);
-        const int64_t pg = tile_ex_g + run_prefix_g(k);
-        if (g < a.max_lines) {
-            int64_t len = e - cur_start;
             // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing
             int cr = 0;
-            if (len > 0 && !(a.is_final && e == a.n)) cr = (run0 + k > 0 ? smem_byte(run0 + k - 1) : any_byte(e - 1)) == '\r';
+            if (len > 0 && !(a.is_final && e == a.n)) cr = (pos > 0 ? (int)sbytes[sidx(pos - 1)] : any_byte(e - 1)) == '\r';
             len -= cr;
             const int ph = (int)(g & 3);
             const uint64_t r = g >> 2;
@@ -324,50 +366,58 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
                     a.result->overflow = 1;
             }
             if ((ph & 1) == 0) {  // header / plus line: its first byte must be '@' / '+'
-                if (any_byte(cur_start) != (ph == 0 ? '@' : '+')) atomicMin(&a.result->err_pos, (unsigned long long)cur_start);
+                if (first_byte != (ph == 0 ? '@' : '+')) atomicMin(&a.result->err_pos, (unsigned long long)(e - len - cr));
             } else if (r < (uint64_t)a.rec_cap) {
                 if (ph == 1) {
                     if (kSeq) {
                         a.seq_len[r] = (uint32_t)len;
-                        a.gc[r] = (uint32_t)(pg - cur_ag);
+                        a.gc[r] = (uint32_t)gsum;
                     }
-                } else {
-                    if (kQual) {
-                        a.qual_len[r] = (uint32_t)len;
-                        a.qsum[r] = (int32_t)((ps - cur_as) - 13 * cr - 33 * len);
-                    }
+                } else if (kQual) {
+                    a.qual_len[r] = (uint32_t)len;
+                    a.qsum[r] = (int32_t)(ssum - 13 * cr - 33 * len);
                 }
             } else {
                 a.result->overflow = 1;
             }
         }
-        cur_start = e + 1;
-        cur_as = ps + (kQual ? 10 : 0);
-        cur_ag = pg;
-        g++;
+        if (lo + EV_CAP < n_events) {  // carry the window's last event into the next batch
+            __syncthreads();
+            if (t == 0) {
+                s_batch_carry[0] = ev_pos[nev - 1];
+                s_batch_carry[1] = kQual ? ev_ps[nev - 1] + 10 : 0;
+                s_batch_carry[2] = kSeq ? ev_pg[nev - 1] : 0;
+            }
+            __syncthreads();
+        }
     }
 }
 
 // ------------------------------------------------------------------ launcher
+template <typename OffT, int FLAGS, int SUBS>
+static cudaError_t launch_one(FastqScanArgs a, cudaStream_t st) {
+    constexpr int smem = FqSmem<FLAGS, SUBS>::total;
+    auto kern = fastq_scan_kernel<OffT, FLAGS, SUBS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    a.n_tiles = (a.n_tiles + SUBS - 1) / SUBS;  // the caller counted 16 KiB sub-tiles
+    kern<<<dim3((unsigned)a.n_tiles), dim3(BLOCK_THREADS), smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <typename OffT>
 static cudaError_t launch_fastq(const FastqScanArgs& a, int flags, cudaStream_t st) {
-    dim3 grid((unsigned)a.n_tiles), block(BLOCK_THREADS);
-#define EXB_CASE(F)                                                   \
-    case F:                                                           \
-        fastq_scan_kernel<OffT, F><<<grid, block, 0, st>>>(a);        \
-        break;
+    constexpr int SUBS = EXB_FASTQ_SUBS;
     switch (flags & 7) {
-        EXB_CASE(0)
-        EXB_CASE(1)
-        EXB_CASE(2)
-        EXB_CASE(3)
-        EXB_CASE(4)
-        EXB_CASE(5)
-        EXB_CASE(6)
-        EXB_CASE(7)
+    case 0: return launch_one<OffT, 0, SUBS>(a, st);
+    case 1: return launch_one<OffT, 1, SUBS>(a, st);
+    case 2: return launch_one<OffT, 2, SUBS>(a, st);
+    case 3: return launch_one<OffT, 3, SUBS>(a, st);
+    case 4: return launch_one<OffT, 4, SUBS>(a, st);
+    case 5: return launch_one<OffT, 5, SUBS>(a, st);
+    case 6: return launch_one<OffT, 6, SUBS>(a, st);
+    default: return launch_one<OffT, 7, SUBS>(a, st);
     }
-#undef EXB_CASE
-    return cudaGetLastError();
 }
 
 cudaError_t fastq_scan_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st) {
