@@ -330,6 +330,49 @@ __device__ __forceinline__ void block_lookback(uint64_t* chain, int64_t tile, co
     }
 }
 
+// One-word look-back run by ONE warp (all 32 lanes call it; the other warps of the block
+// wait at a barrier and execute nothing meanwhile).  Each lane inspects two predecessors,
+// so a round covers 64 tiles.  The caller has already published this tile's aggregate
+// (CH_AGG | agg) -- as early as it was known -- and tile 0 publishes CH_INC itself.
+// Aggregates must fit 32 bits (they are per-tile counts).  Returns the exclusive prefix
+// in every lane and publishes the inclusive word.
+__device__ __forceinline__ uint64_t warp_lookback(uint64_t* chain, int64_t tile, uint64_t agg, uint64_t init) {
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) return init;
+    uint64_t acc = 0;
+    int64_t base = tile - 1;
+    while (true) {
+        const int64_t i0 = base - lane, i1 = base - 32 - lane;
+        const uint64_t w0 = i0 >= 0 ? ld_acquire_u64(&chain[i0]) : (CH_INC | (i0 == -1 ? (init & CH_VAL) : 0ull));
+        const uint64_t w1 = i1 >= 0 ? ld_acquire_u64(&chain[i1]) : (CH_INC | (i1 == -1 ? (init & CH_VAL) : 0ull));
+        const uint32_t f0 = (uint32_t)(w0 >> 62), f1 = (uint32_t)(w1 >> 62);
+        const uint32_t inc0 = __ballot_sync(0xffffffffu, f0 == 2), emp0 = __ballot_sync(0xffffffffu, f0 == 0);
+        const int first0 = inc0 ? __ffs(inc0) - 1 : 32;
+        const uint32_t need0 = first0 >= 32 ? 0xffffffffu : ((1u << first0) - 1u);
+        if (emp0 & need0) continue;  // a predecessor nearer than the first inclusive word has not published yet: poll again
+        acc += __reduce_add_sync(0xffffffffu, lane < first0 ? (uint32_t)w0 : 0u);
+        if (inc0) {
+            acc += __shfl_sync(0xffffffffu, w0 & CH_VAL, first0);
+            break;
+        }
+        const uint32_t inc1 = __ballot_sync(0xffffffffu, f1 == 2), emp1 = __ballot_sync(0xffffffffu, f1 == 0);
+        const int first1 = inc1 ? __ffs(inc1) - 1 : 32;
+        const uint32_t need1 = first1 >= 32 ? 0xffffffffu : ((1u << first1) - 1u);
+        if (emp1 & need1) {  // first window was all aggregates and is consumed; re-poll from the second one
+            base -= 32;
+            continue;
+        }
+        acc += __reduce_add_sync(0xffffffffu, lane < first1 ? (uint32_t)w1 : 0u);
+        if (inc1) {
+            acc += __shfl_sync(0xffffffffu, w1 & CH_VAL, first1);
+            break;
+        }
+        base -= 64;
+    }
+    if (lane == 0) st_release_u64(&chain[tile], CH_INC | ((acc + agg) & CH_VAL));
+    return acc;
+}
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v) {
     const int lane = threadIdx.x & 31;

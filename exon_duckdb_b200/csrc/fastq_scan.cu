@@ -6,22 +6,26 @@
 // record at a time it reads every input byte exactly once.
 //
 // One CTA (256 threads) owns a tile of SUBS x 16 KiB staged in shared memory
-// (cp.async, XOR-swizzled).  Three phases:
+// (cp.async, XOR-swizzled).  Phases:
 //
 //  A. analysis (byte-parallel, branch-free): thread t owns the 64 contiguous
 //     bytes [t*64, t*64+64) of each 16 KiB sub-tile -> 64-bit newline mask,
 //     signed byte sum, G/C mask; one packed warp scan + an 8-entry cross-warp
 //     scan give every run its tile-level prefix (newlines, byte sum, G/C).
 //     Newline positions are scattered, in order, into an event list.
-//  B. chaining: only the newline COUNT is chained between tiles (one 64-bit
-//     word, status in the top bits, block-wide decoupled look-back).  What a
-//     tile needs to finish the line that was open at its start is local to the
-//     predecessor holding that line's start, which publishes a 32-byte tail
-//     record with no dependency on anybody.
-//  C. emission (event-parallel): one newline per lane.  Line length, G/C count
-//     (sequence lines) and Phred sum (quality lines) are differences of the
-//     prefix sums at consecutive newlines; FASTQ's strict 4-line phase (global
-//     line index mod 4) disambiguates '@'/'+' inside quality strings.
+//     The tile's newline count is published at once (CH_AGG).
+//  B. event prefixes (event-parallel): one newline per lane computes the byte
+//     sum / G,C count of everything before it in the tile.  The part after the
+//     last newline becomes the tile's 32-byte "tail record": what a successor
+//     needs to finish the line that is open at its start.  It depends on
+//     nobody, so it is published without waiting for any other tile.
+//  C. chaining: only the newline COUNT is chained (one 64-bit word, status in
+//     the top bits, decoupled look-back by warp 0, 64 predecessors per round;
+//     the other seven warps sleep at a barrier).
+//  D. emission (event-parallel): line length, G/C count (sequence lines) and
+//     Phred sum (quality lines) are differences of the prefixes at consecutive
+//     newlines; FASTQ's strict 4-line phase (global line index mod 4)
+//     disambiguates '@'/'+' inside quality strings.
 //
 // Outputs are single-writer stores (no atomics except the rare error path):
 //   line_end[g]            position of the newline ending line g      (F_LINES)
@@ -39,37 +43,8 @@ struct alignas(16) TailRec {  // the part of a tile after its last newline (the 
     int64_t line_start;       // absolute offset of the byte after the tile's last newline
     int64_t tail_s;           // signed byte sum of that part
     int64_t tail_g;           // G/C count of that part
-    uint64_t has_nl;
+    uint64_t state;           // 0 = not published yet, 1 = no newline in the tile, 2 = line_start valid
 };
-
-struct WarpLast {  // the last newline inside a warp's 2 KiB
-    int start_local;  // tile-local index of the byte after it
-    int a_s, a_g;     // warp-relative prefix sums up to and including it
-    int valid;
-};
-
-// packed (count, gc, signed sum): 18 + 18 + 24 bits
-__device__ __forceinline__ uint64_t pack3(int cnt, int g, int s) {
-    return ((uint64_t)cnt << 42) + ((uint64_t)g << 24) + (uint64_t)(int64_t)s;
-}
-__device__ __forceinline__ void unpack3(uint64_t v, int& cnt, int& g, int& s) {
-    int64_t sv = ((int64_t)(v << 40)) >> 40;  // sign-extend low 24 bits
-    uint64_t rest = (v - (uint64_t)sv) >> 24;
-    s = (int)sv;
-    g = (int)(rest & 0x3FFFFu);
-    cnt = (int)(rest >> 18);
-}
-
-__device__ __forceinline__ TailRec ld_rec(const TailRec* p) {
-    TailRec r;
-    uint4 a = ld_cg_u4(reinterpret_cast<const uint4*>(p));
-    uint4 b = ld_cg_u4(reinterpret_cast<const uint4*>(p) + 1);
-    r.line_start = (int64_t)(((uint64_t)a.y << 32) | a.x);
-    r.tail_s = (int64_t)(((uint64_t)a.w << 32) | a.z);
-    r.tail_g = (int64_t)(((uint64_t)b.y << 32) | b.x);
-    r.has_nl = ((uint64_t)b.w << 32) | b.z;
-    return r;
-}
 
 // State of the line that is open at the start of `tile`: walk the predecessors' tail
 // records back to the one that holds the line's start (usually tile-1).
@@ -78,11 +53,16 @@ __device__ __noinline__ void open_line_before(const TailRec* recs, int64_t tile,
     ts = 0;
     tg = 0;
     for (int64_t k = tile - 1; k >= 0; k--) {
-        TailRec r = ld_rec(&recs[k]);
-        ts += r.tail_s;
-        tg += r.tail_g;
-        if (r.has_nl) {
-            start = r.line_start;
+        uint64_t st;
+        do {
+            st = ld_acquire_u64(&recs[k].state);
+        } while (st == 0);
+        const uint4 v0 = ld_cg_u4(reinterpret_cast<const uint4*>(&recs[k]));
+        const uint4 v1 = ld_cg_u4(reinterpret_cast<const uint4*>(&recs[k]) + 1);
+        ts += (int64_t)(((uint64_t)v0.w << 32) | v0.z);
+        tg += (int64_t)(((uint64_t)v1.y << 32) | v1.x);
+        if (st == 2) {
+            start = (int64_t)(((uint64_t)v0.y << 32) | v0.x);
             return;
         }
     }
@@ -142,11 +122,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
     int* ev_ps = reinterpret_cast<int*>(smem + SM::off_evps);
     int* ev_pg = reinterpret_cast<int*>(smem + SM::off_evpg);
     uint16_t* ev_pos = reinterpret_cast<uint16_t*>(smem + SM::off_evpos);
-    __shared__ uint64_t s_warp_tot[WARPS];
-    __shared__ WarpLast s_warp_last[WARPS];
-    __shared__ LookbackSmem<1> s_lb;
+    __shared__ int s_wt[SUBS][3][WARPS];  // per sub-tile: warp totals of (newlines, byte sum, G/C)
     __shared__ int64_t s_tile_id;
-    __shared__ int s_batch_carry[3];  // last event of the previous batch: pos, ps (incl. newline), pg
+    __shared__ uint64_t s_excl;
+    __shared__ int s_batch_carry[3];  // last event of the previous window: pos, ps (incl. newline), pg
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint8_t* __restrict__ buf = a.buf;
@@ -159,8 +138,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
     const int64_t tile = s_tile_id;
     const int64_t tile_base = origin + tile * TILE;
 
+    // ---- staging: interior tiles take the cheap path (one 64-bit base, 32-bit offsets)
+    if (tile_base >= a.begin && tile_base + TILE <= a.n) {
+        const uint8_t* src = buf + tile_base + t * 16;
 #pragma unroll
-    for (int s = 0; s < SUBS; s++) stage_tile(s_data + s * TILE_CHUNKS, buf, tile_base + (int64_t)s * SUB_BYTES, origin, a.n);
+        for (int s = 0; s < SUBS; s++)
+#pragma unroll
+            for (int i = 0; i < RUN_CHUNKS; i++)
+                cp_async16(&s_data[s * TILE_CHUNKS + swz(i * BLOCK_THREADS + t)], src + (s * SUB_BYTES + i * BLOCK_THREADS * 16), 16);
+        cp_async_commit();
+    } else {
+#pragma unroll 1
+        for (int s = 0; s < SUBS; s++) stage_tile(s_data + s * TILE_CHUNKS, buf, tile_base + (int64_t)s * SUB_BYTES, origin, a.n);
+    }
     cp_async_wait<0>();
     __syncthreads();
 
@@ -188,70 +178,65 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
 
     // ---- A. analysis of the SUBS sub-tiles; scatters the events with rank in [win_lo, win_lo + EV_CAP)
     int total_cnt = 0, total_s = 0, total_g = 0;
-    int last_start = -1, last_as = 0, last_ag = 0;  // after the tile's last newline: tile-local start, prefixes incl. that newline
     auto analyse = [&](int win_lo) {
         total_cnt = total_s = total_g = 0;
-        last_start = -1;
 #pragma unroll 1
         for (int s = 0; s < SUBS; s++) {
             const uint4* d = s_data + s * TILE_CHUNKS;
             uint64_t pm, gm = 0;
-            int cs0 = 0, cs1 = 0, cs2 = 0, cs3 = 0;
+            int rs = 0;  // signed byte sum of the run
             {
-                uint4 c0 = d[swz(4 * t + 0)], c1 = d[swz(4 * t + 1)], c2 = d[swz(4 * t + 2)], c3 = d[swz(4 * t + 3)];
+                const uint4 c0 = d[swz(4 * t + 0)], c1 = d[swz(4 * t + 1)], c2 = d[swz(4 * t + 2)], c3 = d[swz(4 * t + 3)];
                 pm = ((uint64_t)(nl_mask16(c2) | (nl_mask16(c3) << 16)) << 32) | (nl_mask16(c0) | (nl_mask16(c1) << 16));
                 if (kSeq) gm = ((uint64_t)(gc_mask16b(c2) | (gc_mask16b(c3) << 16)) << 32) | (gc_mask16b(c0) | (gc_mask16b(c1) << 16));
-                if (kQual) {
-                    cs0 = sbyte_sum16(c0, 0);
-                    cs1 = sbyte_sum16(c1, cs0);
-                    cs2 = sbyte_sum16(c2, cs1);
-                    cs3 = sbyte_sum16(c3, cs2);
-                }
+                if (kQual) rs = sbyte_sum16(c3, sbyte_sum16(c2, sbyte_sum16(c1, sbyte_sum16(c0, 0))));
             }
             const int cnt = __popcll(pm);
             const int gtot = kSeq ? __popcll(gm) : 0;
-            const uint64_t packed = pack3(cnt, gtot, cs3);
-            const uint64_t incl = warp_incl_scan_u64(packed);
-            if (lane == 31) s_warp_tot[warp] = incl;
-            int ex_cnt, ex_g, ex_s;  // warp-relative exclusive prefix of this run
-            unpack3(incl - packed, ex_cnt, ex_g, ex_s);
-            const uint32_t has = __ballot_sync(0xffffffffu, cnt > 0);
-            if (has == 0) {
-                if (lane == 0) s_warp_last[warp].valid = 0;
-            } else if (lane == 31 - __clz(has)) {
-                const int k = 63 - __clzll((long long)pm);
-                int as_ = 0;
-                if (kQual) {
-                    const int j = k >> 4;
-                    as_ = ex_s + (j == 0 ? 0 : (j == 1 ? cs0 : (j == 2 ? cs1 : cs2))) + sbyte_sum_prefix16(d[swz(4 * t + j)], k & 15) + 10;
-                }
-                s_warp_last[warp] = WarpLast{s * SUB_BYTES + t * RUN_BYTES + k + 1, as_, kSeq ? ex_g + __popcll(gm & low_bits64(k)) : 0, 1};
+            // warp scan: newlines (<= 2048 per warp: 12 bits) and byte sum (|.| <= 2^18: 20 bits signed) share one word
+            const uint32_t packed = ((uint32_t)cnt << 20) + (uint32_t)rs;
+            const uint32_t incl = warp_incl_scan_u32(packed);
+            const uint32_t ex = incl - packed;
+            const int ex_s = ((int)(ex << 12)) >> 12;
+            const int ex_cnt = (int)((ex - (uint32_t)ex_s) >> 20);
+            int ex_g = 0, in_g = 0;
+            if (kSeq) {
+                in_g = (int)warp_incl_scan_u32((uint32_t)gtot);
+                ex_g = in_g - gtot;
+            }
+            if (lane == 31) {
+                const int in_s = ((int)(incl << 12)) >> 12;
+                s_wt[s][0][warp] = (int)((incl - (uint32_t)in_s) >> 20);
+                s_wt[s][1][warp] = in_s;
+                s_wt[s][2][warp] = in_g;
             }
             __syncthreads();
-            // cross-warp exclusive scan of the 8 warp totals (every warp does it redundantly in its low lanes)
-            uint64_t wt = lane < WARPS ? s_warp_tot[lane] : 0ull;
-            uint64_t wincl = wt;
+            // cross-warp exclusive scan of the 8 warp totals (every warp redoes it in its low lanes)
+            int wc = lane < WARPS ? s_wt[s][0][lane] : 0, ws = lane < WARPS ? s_wt[s][1][lane] : 0;
+            int wg = (kSeq && lane < WARPS) ? s_wt[s][2][lane] : 0;
+            int ic = wc, is_ = ws, ig = wg;
 #pragma unroll
             for (int dd = 1; dd < WARPS; dd <<= 1) {
-                uint64_t o = __shfl_up_sync(0xffffffffu, wincl, dd);
-                if (lane >= dd) wincl += o;
+                const int oc = __shfl_up_sync(0xffffffffu, ic, dd), os = __shfl_up_sync(0xffffffffu, is_, dd);
+                const int og = kSeq ? __shfl_up_sync(0xffffffffu, ig, dd) : 0;
+                if (lane >= dd) {
+                    ic += oc;
+                    is_ += os;
+                    ig += og;
+                }
             }
-            const uint64_t wex = __shfl_sync(0xffffffffu, wincl - wt, warp);
-            const uint64_t wtot = __shfl_sync(0xffffffffu, wincl, WARPS - 1);
-            const int lvalid = lane < WARPS ? s_warp_last[lane].valid : 0;
-            const uint32_t vmask = __ballot_sync(0xffffffffu, lvalid != 0);
-            int off_cnt, off_g, off_s, sc, sg, ss;
-            unpack3(wex, off_cnt, off_g, off_s);
-            unpack3(wtot, sc, sg, ss);
+            const int off_cnt = __shfl_sync(0xffffffffu, ic - wc, warp), off_s = __shfl_sync(0xffffffffu, is_ - ws, warp);
+            const int off_g = kSeq ? __shfl_sync(0xffffffffu, ig - wg, warp) : 0;
+            const int sc = __shfl_sync(0xffffffffu, ic, WARPS - 1), ss = __shfl_sync(0xffffffffu, is_, WARPS - 1);
+            const int sg = kSeq ? __shfl_sync(0xffffffffu, ig, WARPS - 1) : 0;
             const int run = s * BLOCK_THREADS + t;
-            const int my_cnt = total_cnt + off_cnt + ex_cnt;
             if (kQual) s_sexcl[run] = total_s + off_s + ex_s;
             if (kSeq) {
                 s_gexcl[run] = total_g + off_g + ex_g;
                 s_gm[run] = gm;
             }
             {  // events of this run, in order
-                int rank = my_cnt - win_lo;
+                int rank = total_cnt + off_cnt + ex_cnt - win_lo;
                 uint64_t m = pm;
                 const int p0 = s * SUB_BYTES + t * RUN_BYTES;
                 while (m) {
@@ -261,61 +246,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
                     rank++;
                 }
             }
-            if (vmask) {  // the sub-tile's last newline (uniform)
-                const int lw = 31 - __clz(vmask);
-                const uint64_t before = __shfl_sync(0xffffffffu, wincl - wt, lw);
-                int bc, bg, bs;
-                unpack3(before, bc, bg, bs);
-                last_start = s_warp_last[lw].start_local;
-                last_as = total_s + bs + s_warp_last[lw].a_s;
-                last_ag = total_g + bg + s_warp_last[lw].a_g;
-            }
             total_cnt += sc;
             total_s += ss;
             total_g += sg;
-            __syncthreads();
         }
+        __syncthreads();  // event list complete
     };
-    analyse(0);
-
-    // ---- B. tail record + look-back of the newline count
-    TailRec mine;
-    mine.has_nl = last_start >= 0;
-    mine.line_start = last_start >= 0 ? tile_base + last_start : 0;
-    mine.tail_s = last_start >= 0 ? total_s - last_as : total_s;
-    mine.tail_g = last_start >= 0 ? total_g - last_ag : total_g;
-    if (t == 0) {  // made visible by block_lookback's release (thread 0 stores, fences, then writes the chain word)
-        recs[tile] = mine;
-        if (a.prev && tile == 0) {  // chained range: errors of earlier ranges stay visible in the last result
-            if (a.prev->err_pos != ~0ull) atomicMin(&a.result->err_pos, a.prev->err_pos);
-            if (a.prev->overflow) a.result->overflow = 1;
-        }
-    }
-    const uint64_t agg[1] = {(uint64_t)total_cnt};
-    const uint64_t init[1] = {a.prev ? a.prev->total_lines : 0ull};
-    uint64_t excl[1];
-    block_lookback<1>(chain, tile, agg, init, excl, &s_lb);
-
-    if (tile == a.n_tiles - 1 && t == 0) {  // final state of this range (chaining / host)
-        int64_t st = mine.line_start, s2 = mine.tail_s, g2 = mine.tail_g;
-        if (!mine.has_nl) {
-            open_line_before(recs, tile, a, st, s2, g2);
-            s2 += mine.tail_s;
-            g2 += mine.tail_g;
-        }
-        a.result->total_lines = excl[0] + (uint64_t)total_cnt;
-        a.result->open_line_start = st;
-        a.result->tail_s = s2;
-        a.result->tail_g = g2;
-    }
-
-    // ---- C. emission, one newline per lane
-    const int n_events = total_cnt;
-    for (int lo = 0; lo < n_events; lo += EV_CAP) {
-        if (lo > 0) analyse(lo);  // newline-dense tile: refill the event window (rare)
-        const int nev = min(EV_CAP, n_events - lo);
+    // ---- B. prefix sums at the newlines of the current window (one per lane)
+    auto event_prefixes = [&](int nev) {
         if (kQual || kSeq) {
-            for (int i = t; i < nev; i += BLOCK_THREADS) {  // prefix sums at my newline
+            for (int i = t; i < nev; i += BLOCK_THREADS) {
                 const int pos = ev_pos[i];
                 const int run = pos >> 6, k = pos & 63;
                 if (kQual) {
@@ -330,10 +270,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
                 }
                 if (kSeq) ev_pg[i] = s_gexcl[run] + __popcll(s_gm[run] & low_bits64(k));
             }
-            __syncthreads();
         }
+        __syncthreads();
+    };
+    // ---- D. emission of the current window
+    auto emit = [&](int lo, int nev, uint64_t excl) {
         for (int i = t; i < nev; i += BLOCK_THREADS) {
-            const uint64_t g = excl[0] + (uint64_t)(lo + i);  // global index of the line this newline ends
+            const uint64_t g = excl + (uint64_t)(lo + i);  // global index of the line this newline ends
             if (g >= a.max_lines) continue;
             const int pos = ev_pos[i];
             const int64_t e = tile_base + pos;
@@ -381,14 +324,80 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs
                 a.result->overflow = 1;
             }
         }
-        if (lo + EV_CAP < n_events) {  // carry the window's last event into the next batch
+    };
+
+    analyse(0);
+    const int n_events = total_cnt;
+    const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
+    if (t == 0) {  // the count is all the chain needs: publish it before anything else
+        if (tile == 0) st_release_u64(&chain[0], CH_INC | ((init + (uint64_t)n_events) & CH_VAL));
+        else st_release_u64(&chain[tile], CH_AGG | (uint64_t)n_events);
+        if (a.prev && tile == 0) {  // chained range: errors of earlier ranges stay visible in the last result
+            if (a.prev->err_pos != ~0ull) atomicMin(&a.result->err_pos, a.prev->err_pos);
+            if (a.prev->overflow) a.result->overflow = 1;
+        }
+    }
+    const bool dense = n_events > EV_CAP;  // more newlines than the event window holds (rare): windows are re-analysed
+    if (dense) analyse(((n_events - 1) / EV_CAP) * EV_CAP);
+    const int last_nev = n_events - ((n_events - 1) / EV_CAP) * EV_CAP;  // events in the window that holds the last one
+    event_prefixes(dense ? last_nev : n_events);
+
+    // tail record (local information only), then the look-back of the count by warp 0
+    TailRec mine;
+    if (n_events > 0) {
+        const int li = (dense ? last_nev : n_events) - 1;
+        mine.state = 2;
+        mine.line_start = tile_base + ev_pos[li] + 1;
+        mine.tail_s = kQual ? total_s - (ev_ps[li] + 10) : 0;
+        mine.tail_g = kSeq ? total_g - ev_pg[li] : 0;
+    } else {
+        mine.state = 1;
+        mine.line_start = 0;
+        mine.tail_s = total_s;
+        mine.tail_g = total_g;
+    }
+    if (warp == 0) {
+        if (lane == 0) {
+            recs[tile].line_start = mine.line_start;
+            recs[tile].tail_s = mine.tail_s;
+            recs[tile].tail_g = mine.tail_g;
+            __threadfence();
+            st_release_u64(&recs[tile].state, mine.state);
+        }
+        const uint64_t ex = warp_lookback(chain, tile, (uint64_t)n_events, init);
+        if (lane == 0) s_excl = ex;
+    }
+    __syncthreads();
+    const uint64_t excl = s_excl;
+
+    if (tile == a.n_tiles - 1 && t == 0) {  // final state of this range (chaining / host)
+        int64_t st = mine.line_start, s2 = mine.tail_s, g2 = mine.tail_g;
+        if (mine.state != 2) {
+            open_line_before(recs, tile, a, st, s2, g2);
+            s2 += mine.tail_s;
+            g2 += mine.tail_g;
+        }
+        a.result->total_lines = excl + (uint64_t)n_events;
+        a.result->open_line_start = st;
+        a.result->tail_s = s2;
+        a.result->tail_g = g2;
+    }
+
+    if (!dense) {
+        emit(0, n_events, excl);
+    } else {
+        for (int lo = 0; lo < n_events; lo += EV_CAP) {
+            const int nev = min(EV_CAP, n_events - lo);
             __syncthreads();
-            if (t == 0) {
+            analyse(lo);
+            event_prefixes(nev);
+            emit(lo, nev, excl);
+            __syncthreads();
+            if (t == 0) {  // carry the window's last event into the next one
                 s_batch_carry[0] = ev_pos[nev - 1];
                 s_batch_carry[1] = kQual ? ev_ps[nev - 1] + 10 : 0;
                 s_batch_carry[2] = kSeq ? ev_pg[nev - 1] : 0;
             }
-            __syncthreads();
         }
     }
 }
