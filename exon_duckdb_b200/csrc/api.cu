@@ -61,8 +61,9 @@ struct Workspace {
     unsigned long long* ticket;
     TileSlot* slots;
 };
-int carve(void* ws, int64_t ws_bytes, int64_t n_tiles, cudaStream_t st, Workspace* out) {
-    int64_t need = WS_HEADER + n_tiles * (int64_t)sizeof(TileSlot);
+// `payload` bytes of zeroed chain state behind the header
+int carve_bytes(void* ws, int64_t ws_bytes, int64_t payload, cudaStream_t st, Workspace* out) {
+    int64_t need = WS_HEADER + payload;
     if (!ws || ws_bytes < need) return set_err(EXB_ERR_ARG, "workspace too small: need %lld bytes, have %lld", (long long)need, (long long)ws_bytes);
     cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
@@ -71,8 +72,10 @@ int carve(void* ws, int64_t ws_bytes, int64_t n_tiles, cudaStream_t st, Workspac
     out->slots = reinterpret_cast<TileSlot*>(reinterpret_cast<uint8_t*>(ws) + WS_HEADER);
     return 0;
 }
+int carve(void* ws, int64_t ws_bytes, int64_t n_tiles, cudaStream_t st, Workspace* out) {
+    return carve_bytes(ws, ws_bytes, n_tiles * (int64_t)sizeof(TileSlot), st, out);
+}
 
-__global__ void init_result_kernel(ScanResult* r) { r->err_pos = ~0ull; }
 
 // ---------------------------------------------------------------- generators
 __global__ void gen_sizes_kernel(exb_gen_params p, uint32_t* sizes) {
@@ -104,20 +107,26 @@ int exb_device_available(void) {
 
 int64_t exb_scan_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
-    return WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);
+    const int64_t cta_tiles = WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);      // FASTA scan, offset scans
+    const int64_t warp_tiles = WS_HEADER + fastq_scan_chain_bytes(fastq_scan_tiles(0, n + 16, 1) + 2);  // FASTQ scan
+    return cta_tiles > warp_tiles ? cta_tiles : warp_tiles;
 }
 
-int exb_fastq_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, uint64_t max_lines,
-                   int flags, void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len, uint32_t* d_gc,
-                   uint32_t* d_qual_len, int32_t* d_qsum, int64_t rec_cap, void* d_workspace, int64_t workspace_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!d_buf || begin < 0 || n < begin) return set_err(EXB_ERR_ARG, "exb_fastq_scan: bad buffer range");
-    if (((uintptr_t)d_buf & 15) != 0) return set_err(EXB_ERR_ARG, "exb_fastq_scan: d_buf must be 16-byte aligned");
-    if ((flags & EXB_F_LINES) && !d_line_end) return set_err(EXB_ERR_ARG, "exb_fastq_scan: EXB_F_LINES without d_line_end");
+static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace,
+                             uint64_t max_lines, int flags, void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len,
+                             uint32_t* d_gc, uint32_t* d_qual_len, int32_t* d_qsum, int64_t rec_cap, const exb_predicate* preds, int n_preds,
+                             int64_t* d_agg, void* d_workspace, int64_t workspace_bytes, cudaStream_t st) {
+    if (!d_buf || begin < 0 || n < begin) return set_err(EXB_ERR_ARG, "%s: bad buffer range", who);
+    if (((uintptr_t)d_buf & 15) != 0) return set_err(EXB_ERR_ARG, "%s: d_buf must be 16-byte aligned", who);
+    if (d_prev_workspace && (begin & 15) != 0) return set_err(EXB_ERR_ARG, "%s: `begin` of a chained range must be a multiple of 16", who);
+    if ((flags & EXB_F_LINES) && !d_line_end) return set_err(EXB_ERR_ARG, "%s: EXB_F_LINES without d_line_end", who);
     if ((flags & EXB_F_LINES) && !wide_offsets && n >= (int64_t)0xFFFFFFFFll)
-        return set_err(EXB_ERR_ARG, "exb_fastq_scan: 32-bit line offsets need n < 4 GiB");
-    if ((flags & EXB_F_SEQ) && (!d_seq_len || !d_gc)) return set_err(EXB_ERR_ARG, "exb_fastq_scan: EXB_F_SEQ without outputs");
-    if ((flags & EXB_F_QUAL) && (!d_qual_len || !d_qsum)) return set_err(EXB_ERR_ARG, "exb_fastq_scan: EXB_F_QUAL without outputs");
+        return set_err(EXB_ERR_ARG, "%s: 32-bit line offsets need n < 4 GiB", who);
+    if (!(flags & EXB_F_FUSED)) {
+        if ((flags & EXB_F_SEQ) && (!d_seq_len || !d_gc)) return set_err(EXB_ERR_ARG, "%s: EXB_F_SEQ without outputs", who);
+        if ((flags & EXB_F_QUAL) && (!d_qual_len || !d_qsum)) return set_err(EXB_ERR_ARG, "%s: EXB_F_QUAL without outputs", who);
+    }
+    if (d_prev_workspace == d_workspace) return set_err(EXB_ERR_ARG, "%s: d_prev_workspace must differ from d_workspace", who);
     FastqScanArgs a;
     memset(&a, 0, sizeof(a));
     a.buf = reinterpret_cast<const uint8_t*>(d_buf);
@@ -126,12 +135,10 @@ int exb_fastq_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, co
     a.prev = reinterpret_cast<const ScanResult*>(d_prev_workspace);
     a.is_final = is_final ? 1 : 0;
     a.max_lines = max_lines;
-    a.n_tiles = tiles_for(begin, n, a.is_final);
-    if (d_prev_workspace == d_workspace) return set_err(EXB_ERR_ARG, "exb_fastq_scan: d_prev_workspace must differ from d_workspace");
+    a.n_tiles = fastq_scan_tiles(begin, n, a.is_final);
     Workspace w;
-    int rc = carve(d_workspace, workspace_bytes, a.n_tiles, st, &w);
+    int rc = carve_bytes(d_workspace, workspace_bytes, fastq_scan_chain_bytes(a.n_tiles), st, &w);
     if (rc) return rc;
-    init_result_kernel<<<1, 1, 0, st>>>(w.result);
     a.slots = w.slots;
     a.ticket = w.ticket;
     a.result = w.result;
@@ -142,9 +149,39 @@ int exb_fastq_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, co
     a.qual_len = d_qual_len;
     a.qsum = d_qsum;
     a.rec_cap = rec_cap;
+    a.n_fused = n_preds;
+    for (int i = 0; i < n_preds; i++) a.fused[i] = preds[i];
+    a.fused_agg = reinterpret_cast<long long*>(d_agg);
     cudaError_t e = fastq_scan_launch(a, flags, wide_offsets != 0, st);
     if (e != cudaSuccess) return cuda_fail(e, "fastq_scan launch");
     return 0;
+}
+
+int exb_fastq_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, uint64_t max_lines,
+                   int flags, void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len, uint32_t* d_gc,
+                   uint32_t* d_qual_len, int32_t* d_qsum, int64_t rec_cap, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    return fastq_scan_common("exb_fastq_scan", d_buf, begin, n, is_final, d_prev_workspace, max_lines, flags & 7, d_line_end, line_cap,
+                             wide_offsets, d_seq_len, d_gc, d_qual_len, d_qsum, rec_cap, nullptr, 0, nullptr, d_workspace, workspace_bytes,
+                             (cudaStream_t)stream);
+}
+
+int exb_fastq_scan_filter(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace,
+                          const exb_predicate* preds, int n_preds, int64_t* d_agg, int accumulate, void* d_workspace,
+                          int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_preds < 0 || n_preds > EXB_MAX_PREDICATES) return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter: at most %d predicates", EXB_MAX_PREDICATES);
+    for (int i = 0; i < n_preds; i++) {
+        if (preds[i].field != EXB_P_MEAN_QUALITY && preds[i].field != EXB_P_QUAL_LEN)
+            return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter: predicate %d is not on the quality line (use exb_fastq_scan + exb_fastq_filter)", i);
+        if (preds[i].op < 0 || preds[i].op > 5) return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter: bad operator in predicate %d", i);
+    }
+    if (!d_agg) return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter: d_agg is required");
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(d_agg, 0, 8 * sizeof(int64_t), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(agg)");
+    }
+    return fastq_scan_common("exb_fastq_scan_filter", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_QUAL, nullptr, 0,
+                             0, nullptr, nullptr, nullptr, nullptr, 0, preds, n_preds, d_agg, d_workspace, workspace_bytes, st);
 }
 
 int exb_scan_result_fetch(const void* d_workspace, exb_scan_result* out, void* stream) {
@@ -153,6 +190,7 @@ int exb_scan_result_fetch(const void* d_workspace, exb_scan_result* out, void* s
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(result)");
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    out->err_pos = ~out->err_pos;  // the device keeps it inverted (see ScanResult)
     return 0;
 }
 
@@ -236,7 +274,6 @@ int exb_fasta_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, in
     Workspace w;
     int rc = carve(d_workspace, workspace_bytes, a.n_tiles, st, &w);
     if (rc) return rc;
-    init_result_kernel<<<1, 1, 0, st>>>(w.result);
     a.slots = w.slots;
     a.ticket = w.ticket;
     a.result = w.result;

@@ -6,10 +6,8 @@
 
 #include "../../include/exon_b200.h"
 
-// 16 KiB sub-tiles per CTA tile of the FASTQ scan (tuning knob; <= 4 because event positions are 16 bit)
-#ifndef EXB_FASTQ_SUBS
-#define EXB_FASTQ_SUBS 2
-#endif
+// internal scan flag: evaluate quality-line predicates at emission, only aggregates leave the kernel
+#define EXB_F_FUSED 8
 
 namespace exb {
 
@@ -20,7 +18,8 @@ struct TileSlot;
 struct ScanResult {
     uint64_t total_lines;       // FASTQ: newlines seen (incl. the virtual one at EOF)
     int64_t open_line_start;    // first byte after the last newline
-    unsigned long long err_pos; // smallest offset of a malformed line start; ~0 = none
+    unsigned long long err_pos; // ON THE DEVICE: ~(smallest offset of a malformed line start), 0 = none (atomicMax over a
+                                // zeroed word needs no init kernel); exb_scan_result_fetch inverts it for the host
     uint32_t overflow;          // an output capacity was too small
     uint32_t pad;
     uint64_t n_records;         // FASTA: header lines seen
@@ -37,9 +36,12 @@ struct FastqScanArgs {
     int is_final;               // 1: n is the end of the input (an unterminated last line gets a virtual '\n')
     uint64_t max_lines;         // lines with index >= max_lines are ignored
     int64_t n_tiles;
-    TileSlot* slots;            // n_tiles zeroed slots
+    TileSlot* slots;            // zeroed chain state: u64 count word[n_tiles] | u64 tail word[n_tiles]
     unsigned long long* ticket; // zeroed
     ScanResult* result;
+    int n_fused;                // EXB_F_FUSED: predicates on the quality line (EXB_P_MEAN_QUALITY / EXB_P_QUAL_LEN)
+    exb_predicate fused[EXB_MAX_PREDICATES];
+    long long* fused_agg;       // int64[8] aggregates (same layout as exb_fastq_filter's d_agg)
     void* line_end;             // OffT[line_cap]
     int64_t line_cap;
     uint32_t *seq_len, *gc, *qual_len;
@@ -48,6 +50,8 @@ struct FastqScanArgs {
 };
 
 cudaError_t fastq_scan_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st);
+int64_t fastq_scan_tiles(int64_t begin, int64_t n, int is_final);  // 2 KiB warp tiles
+int64_t fastq_scan_chain_bytes(int64_t n_tiles);
 
 struct FastaScanArgs {
     const uint8_t* buf;

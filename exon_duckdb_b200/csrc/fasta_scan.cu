@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs
     if (fresh && a.begin >= run_base && a.begin < run_base + RUN_BYTES) {  // the byte at `begin` starts a line
         const int kb = (int)(a.begin - run_base);
         if ((gt >> kb) & 1ull) hs |= 1ull << kb;
-        else if (a.n > a.begin) atomicMin(&a.result->err_pos, (unsigned long long)a.begin);  // data before the first '>'
+        else if (a.n > a.begin) atomicMax(&a.result->err_pos, ~(unsigned long long)a.begin);  // data before the first '>'
     }
     // CR directly before a REAL LF is dropped (the virtual terminator at n strips nothing)
     const int next = tile_byte(run_base + RUN_BYTES);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) fasta_scan_kernel(FastaScanArgs
         if (carry < 0) carry = a.prev ? (int)a.prev->tail_hdr : 0;
         s_carry = carry;
         if (a.prev && tile == 0) {
-            if (a.prev->err_pos != ~0ull) atomicMin(&a.result->err_pos, a.prev->err_pos);
+            if (a.prev->err_pos != 0ull) atomicMax(&a.result->err_pos, a.prev->err_pos);
             if (a.prev->overflow) a.result->overflow = 1;
         }
     }

@@ -1,83 +1,83 @@
-// fastq_scan.cu -- single-pass FASTQ line/record scan for sm_100a.
+// fastq_scan.cu -- single-pass FASTQ line/record scan for sm_100a (v5: warp tiles).
 //
 // Replaces the record loop of noodles-fastq 0.8 Reader::read_record as driven
 // by exon 0.2.6's FASTQ batch reader (call sites: rust/src/arrow_reader.rs:
 // 104-118,125-153 in the reference).  Instead of reading a
 // record at a time it reads every input byte exactly once.
 //
-// One CTA (256 threads) owns a tile of SUBS x 16 KiB staged in shared memory
-// (cp.async, XOR-swizzled).  Phases:
+// The unit of work is a WARP TILE: 2 KiB of input, owned by one warp from the
+// global load to the last store.  There is no block-level barrier anywhere in
+// the steady state; a persistent grid of 148 x (CTAs per SM) CTAs pulls tile
+// ids from an atomic ticket, so the 40 warps of an SM are 40 independent
+// pipelines whose stalls (HBM latency, the chain look-back) overlap freely.
+// Each warp double-buffers: the cp.async (LDGSTS, L2-only) of tile k+1 is in
+// flight while tile k is analysed, so ~80 KiB per SM are outstanding at all
+// times -- what Little's law asks for at 6.5 TB/s.
 //
-//  A. analysis (byte-parallel, branch-free): thread t owns the 64 contiguous
-//     bytes [t*64, t*64+64) of each 16 KiB sub-tile -> 64-bit newline mask,
-//     signed byte sum, G/C mask; one packed warp scan + an 8-entry cross-warp
-//     scan give every run its tile-level prefix (newlines, byte sum, G/C).
-//     Newline positions are scattered, in order, into an event list.
-//     The tile's newline count is published at once (CH_AGG).
-//  B. event prefixes (event-parallel): one newline per lane computes the byte
-//     sum / G,C count of everything before it in the tile.  The part after the
-//     last newline becomes the tile's 32-byte "tail record": what a successor
-//     needs to finish the line that is open at its start.  It depends on
-//     nobody, so it is published without waiting for any other tile.
-//  C. chaining: only the newline COUNT is chained (one 64-bit word, status in
-//     the top bits, decoupled look-back by warp 0, 64 predecessors per round;
-//     the other seven warps sleep at a barrier).
-//  D. emission (event-parallel): line length, G/C count (sequence lines) and
-//     Phred sum (quality lines) are differences of the prefixes at consecutive
-//     newlines; FASTQ's strict 4-line phase (global line index mod 4)
-//     disambiguates '@'/'+' inside quality strings.
+// Per tile (lane l owns the 64 contiguous bytes [64l, 64l+64)):
+//  A. analysis, byte-parallel and branch-free: 64-bit newline mask, signed
+//     byte sum, G/C mask; one packed warp scan gives every lane its
+//     tile-level prefix (newlines | byte sum) [+ G/C].  The tile's newline
+//     count is published at once (chain word, status in the top bits).
+//     Per-16-byte-chunk byte-sum prefixes go to shared memory (one STS.128),
+//     newline positions are scattered, in order, into an event list.
+//  B. tail: what follows the tile's last newline (start, byte sum, G/C) is
+//     packed into ONE 64-bit word and published -- it depends on no other tile.
+//  C. events, one newline per lane: prefix byte sum / G,C count at the newline
+//     (chunk prefix + a 0/1-weight IDP.4A over the chunk's head).
+//  D. chaining: decoupled look-back of the newline COUNT only (32 predecessors
+//     per round); the line that is open at the tile's first byte is resolved
+//     from the predecessors' tail words.
+//  E. emission: line length, G/C count (sequence lines) and Phred sum (quality
+//     lines) are differences of the prefixes at consecutive newlines; FASTQ's
+//     strict 4-line phase (global line index mod 4) disambiguates '@' / '+'
+//     inside quality strings.  Optionally the per-record predicate is applied
+//     here and only COUNT / sums leave the kernel (fused filter).
 //
-// Outputs are single-writer stores (no atomics except the rare error path):
+// Outputs are single-writer stores (no atomics except the rare error path and
+// one aggregate flush per warp):
 //   line_end[g]            position of the newline ending line g      (F_LINES)
 //   seq_len[r], gc[r]      per record                                 (F_SEQ)
 //   qual_len[r], qsum[r]   per record; qsum = sum((signed char)c - 33) (F_QUAL)
-// HBM traffic: input once + 4..16 B per line of results.
+// HBM traffic: input once + 16 B of chain state per 2 KiB + 4..16 B per line.
 #include "common.cuh"
 #include "exon_b200_internal.h"
+#include "x87div.h"
 
 namespace exb {
 
-constexpr int SUB_BYTES = TILE_BYTES;  // 16 KiB analysed per pass of the 256 threads
+constexpr int WT_BYTES = 2048;            // bytes per warp tile
+constexpr int WT_CHUNKS = WT_BYTES / 16;  // 128
+constexpr int FQ_WARPS = 8;               // warps per CTA (independent of each other)
+constexpr int FQ_THREADS = FQ_WARPS * 32;
+constexpr int EV_CAP = 128;               // newline positions held at once (4 passes of 32)
 
-struct alignas(16) TailRec {  // the part of a tile after its last newline (the whole tile if it has none)
-    int64_t line_start;       // absolute offset of the byte after the tile's last newline
-    int64_t tail_s;           // signed byte sum of that part
-    int64_t tail_g;           // G/C count of that part
-    uint64_t state;           // 0 = not published yet, 1 = no newline in the tile, 2 = line_start valid
-};
-
-// State of the line that is open at the start of `tile`: walk the predecessors' tail
-// records back to the one that holds the line's start (usually tile-1).
-__device__ __noinline__ void open_line_before(const TailRec* recs, int64_t tile, const FastqScanArgs& a, int64_t& start, int64_t& ts,
-                                              int64_t& tg) {
-    ts = 0;
-    tg = 0;
-    for (int64_t k = tile - 1; k >= 0; k--) {
-        uint64_t st;
-        do {
-            st = ld_acquire_u64(&recs[k].state);
-        } while (st == 0);
-        const uint4 v0 = ld_cg_u4(reinterpret_cast<const uint4*>(&recs[k]));
-        const uint4 v1 = ld_cg_u4(reinterpret_cast<const uint4*>(&recs[k]) + 1);
-        ts += (int64_t)(((uint64_t)v0.w << 32) | v0.z);
-        tg += (int64_t)(((uint64_t)v1.y << 32) | v1.x);
-        if (st == 2) {
-            start = (int64_t)(((uint64_t)v0.y << 32) | v0.x);
-            return;
-        }
-    }
-    if (a.prev) {
-        start = a.prev->open_line_start;
-        ts += a.prev->tail_s;
-        tg += a.prev->tail_g;
-    } else {
-        start = a.begin;
-    }
+// ---------------------------------------------------------------- chain / tail words
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
 
+// tail word: [63:62] state (0 unpublished, 1 no newline in the tile, 2 has one)
+//            [47:36] offset in the tile of the byte after its last newline (0..2048)
+//            [35:24] G/C count of the part after it          (0..2048)
+//            [23:0]  signed byte sum of that part            (|.| <= 2^18)
+// Every field is self-contained in the word, so a relaxed 64-bit store publishes it.
+__device__ __forceinline__ uint64_t tail_pack(uint32_t state, uint32_t rel, uint32_t g, int s) {
+    return ((uint64_t)state << 62) | ((uint64_t)rel << 36) | ((uint64_t)g << 24) | (uint64_t)((uint32_t)s & 0xFFFFFFu);
+}
+__device__ __forceinline__ int tail_s_of(uint64_t w) { return ((int)((uint32_t)w << 8)) >> 8; }
+__device__ __forceinline__ uint32_t tail_g_of(uint64_t w) { return (uint32_t)(w >> 24) & 0xFFFu; }
+__device__ __forceinline__ uint32_t tail_rel_of(uint64_t w) { return (uint32_t)(w >> 36) & 0xFFFu; }
+
+// ---------------------------------------------------------------- byte classification
 // 16-bit equality mask of a 16-byte chunk, bits in byte order.  The 0x80 flags of two
 // words are folded into one byte by IDP.4A with weights 1,2,4,8 / 16,32,64,128 (the
-// products carry a factor 128 that one shift removes): 4 IDP + 2 ops instead of 12.
+// products carry a factor 128 that one shift removes).
 __device__ __forceinline__ uint32_t flags_to_mask16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
     uint32_t lo = __dp4a(m0, 0x08040201u, 0u);
     lo = __dp4a(m1, 0x80402010u, lo);
@@ -85,347 +85,514 @@ __device__ __forceinline__ uint32_t flags_to_mask16(uint32_t m0, uint32_t m1, ui
     hi = __dp4a(m3, 0x80402010u, hi);
     return (lo >> 7) | (hi << 1);
 }
-__device__ __forceinline__ uint32_t nl_mask16(const uint4& v) {
-    return flags_to_mask16(eq_bytes(v.x, 0x0A0A0A0Au), eq_bytes(v.y, 0x0A0A0A0Au), eq_bytes(v.z, 0x0A0A0A0Au), eq_bytes(v.w, 0x0A0A0A0Au));
+// 0x80 per byte equal to the byte replicated in `pat` (< 0x80).  c7f = 0x7F7F7F7F and pat
+// arrive in REGISTERS (the caller launders them through the kernel arguments) so that
+// (x & c7f) ^ pat is one LOP3 instead of two immediate-form ones.
+__device__ __forceinline__ uint32_t eq_flags(uint32_t x, uint32_t c7f, uint32_t pat) {
+    const uint32_t t = (x & c7f) ^ pat;
+    return ~((t + c7f) | x) & 0x80808080u;
 }
-__device__ __forceinline__ uint32_t gc_mask16b(const uint4& v) {
-    return flags_to_mask16(gc_bytes(v.x), gc_bytes(v.y), gc_bytes(v.z), gc_bytes(v.w));
+__device__ __forceinline__ uint32_t nl_mask16r(const uint4& v, uint32_t c7f, uint32_t pat) {
+    return flags_to_mask16(eq_flags(v.x, c7f, pat), eq_flags(v.y, c7f, pat), eq_flags(v.z, c7f, pat), eq_flags(v.w, c7f, pat));
+}
+// 'G' (0x47) and 'C' (0x43) differ only in bit 2
+__device__ __forceinline__ uint32_t gc_flags(uint32_t x, uint32_t c7b, uint32_t c7f, uint32_t pat) {
+    const uint32_t t = (x & c7b) ^ pat;
+    return ~((t + c7f) | x) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t gc_mask16r(const uint4& v, uint32_t c7b, uint32_t c7f, uint32_t pat) {
+    return flags_to_mask16(gc_flags(v.x, c7b, c7f, pat), gc_flags(v.y, c7b, c7f, pat), gc_flags(v.z, c7b, c7f, pat),
+                           gc_flags(v.w, c7b, c7f, pat));
 }
 
-template <int FLAGS, int SUBS>
-struct FqSmem {
+// ---------------------------------------------------------------- shared memory of one warp
+template <int FLAGS>
+struct FqWarpSmem {
     static constexpr bool kSeq = (FLAGS & EXB_F_SEQ) != 0, kQual = (FLAGS & EXB_F_QUAL) != 0;
-    static constexpr int EV_CAP = 512 * SUBS;
-    static constexpr int off_data = 0;
-    static constexpr int off_sexcl = off_data + SUBS * SUB_BYTES;
-    static constexpr int off_gexcl = off_sexcl + (kQual ? SUBS * BLOCK_THREADS * 4 : 0);
-    static constexpr int off_gm = off_gexcl + (kSeq ? SUBS * BLOCK_THREADS * 4 : 0);
-    static constexpr int off_evps = off_gm + (kSeq ? SUBS * BLOCK_THREADS * 8 : 0);
-    static constexpr int off_evpg = off_evps + (kQual ? EV_CAP * 4 : 0);
-    static constexpr int off_evpos = off_evpg + (kSeq ? EV_CAP * 4 : 0);
-    static constexpr int total = off_evpos + EV_CAP * 2;
+    static constexpr int off_data = 0;                                   // 2 x 2 KiB (double buffer)
+    static constexpr int off_cpre = off_data + 2 * WT_BYTES;             // int[128]: byte-sum prefix at each chunk
+    static constexpr int off_gm = off_cpre + (kQual ? WT_CHUNKS * 4 : 0);  // u64[32]: G/C mask of each lane's run
+    static constexpr int off_gex = off_gm + (kSeq ? 32 * 8 : 0);         // int[32]: G/C prefix at each lane's run
+    static constexpr int off_ev = off_gex + (kSeq ? 32 * 4 : 0);         // u16[EV_CAP]: newline positions
+    static constexpr int total = off_ev + EV_CAP * 2;
 };
 
-template <typename OffT, int FLAGS, int SUBS>
-__global__ void __launch_bounds__(BLOCK_THREADS) fastq_scan_kernel(FastqScanArgs a) {
-    using SM = FqSmem<FLAGS, SUBS>;
+// tile-local byte index -> byte offset in the (chunk-swizzled) tile buffer
+__device__ __forceinline__ int sidx(int li) {
+    const int q = li >> 4;
+    return ((q ^ ((q >> 3) & 3)) << 4) | (li & 15);
+}
+
+struct OpenLine {  // the line that is open at a tile's first byte
+    int64_t start;
+    int s, g;      // byte sum / G,C count of its part before the tile (mod 2^32)
+};
+
+// Walk the predecessors' tail words back to the tile that holds the open line's start
+// (tile-1 unless lines are longer than a tile).  All 32 lanes call it; 32 tiles per round.
+__device__ __forceinline__ OpenLine open_line_before(const uint64_t* tails, int64_t tile, int64_t origin, const FastqScanArgs& a) {
+    const int lane = threadIdx.x & 31;
+    OpenLine o;
+    o.s = 0;
+    o.g = 0;
+    int64_t base = tile - 1;
+    while (true) {
+        const int64_t idx = base - lane;
+        uint64_t w;
+        if (idx >= 0) w = ld_relaxed_u64(tails + idx);
+        else w = 2ull << 62;  // the state before tile 0 terminates the walk
+        const uint32_t st = (uint32_t)(w >> 62);
+        const uint32_t has = __ballot_sync(0xffffffffu, st == 2), emp = __ballot_sync(0xffffffffu, st == 0);
+        const int first = has ? __ffs(has) - 1 : 32;
+        const uint32_t need = first >= 32 ? 0xffffffffu : ((2u << first) - 1u);  // lanes up to and including `first`
+        if (emp & need) continue;  // a needed predecessor has not published yet
+        const bool take = lane <= first && idx >= 0;
+        o.s += (int)__reduce_add_sync(0xffffffffu, take ? tail_s_of(w) : 0);
+        o.g += (int)__reduce_add_sync(0xffffffffu, take ? tail_g_of(w) : 0u);
+        if (has) {
+            const int64_t fidx = base - first;
+            const uint32_t rel = __shfl_sync(0xffffffffu, tail_rel_of(w), first);
+            if (fidx >= 0) {
+                o.start = origin + fidx * WT_BYTES + rel;
+            } else if (a.prev) {  // the line began in an earlier range of a chained scan
+                o.start = a.prev->open_line_start;
+                o.s += (int)a.prev->tail_s;
+                o.g += (int)a.prev->tail_g;
+            } else {
+                o.start = a.begin;
+            }
+            return o;
+        }
+        base -= 32;
+    }
+}
+
+// Decoupled look-back over the newline counts; all 32 lanes call it (tile > 0).
+__device__ __forceinline__ uint64_t lookback_count(uint64_t* chain, int64_t tile, uint32_t agg, uint64_t init) {
+    const int lane = threadIdx.x & 31;
+    uint64_t acc = 0;
+    int64_t base = tile - 1;
+    while (true) {
+        const int64_t idx = base - lane;
+        const uint64_t w = idx >= 0 ? ld_relaxed_u64(chain + idx) : (CH_INC | (idx == -1 ? (init & CH_VAL) : 0ull));
+        const uint32_t f = (uint32_t)(w >> 62);
+        const uint32_t inc = __ballot_sync(0xffffffffu, f == 2), emp = __ballot_sync(0xffffffffu, f == 0);
+        const int first = inc ? __ffs(inc) - 1 : 32;
+        const uint32_t need = first >= 32 ? 0xffffffffu : ((1u << first) - 1u);
+        if (emp & need) continue;  // a predecessor nearer than the first inclusive word is unpublished: poll again
+        acc += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)w : 0u);  // aggregates are per-tile counts (<= 2049)
+        if (inc) {
+            acc += __shfl_sync(0xffffffffu, w & CH_VAL, first);
+            break;
+        }
+        base -= 32;
+    }
+    if (lane == 0) st_relaxed_u64(chain + tile, CH_INC | ((acc + agg) & CH_VAL));
+    return acc;
+}
+
+template <typename OffT, int FLAGS>
+__global__ void __launch_bounds__(FQ_THREADS, 5) fastq_scan_kernel(const FastqScanArgs a, const uint32_t c7f, const uint32_t c7b) {
+    using SM = FqWarpSmem<FLAGS>;
     constexpr bool kLines = (FLAGS & EXB_F_LINES) != 0;
     constexpr bool kSeq = SM::kSeq, kQual = SM::kQual;
-    constexpr int TILE = SUBS * SUB_BYTES;
-    constexpr int EV_CAP = SM::EV_CAP;
+    constexpr bool kFused = (FLAGS & EXB_F_FUSED) != 0;
 
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint4* s_data = reinterpret_cast<uint4*>(smem + SM::off_data);
-    int* s_sexcl = reinterpret_cast<int*>(smem + SM::off_sexcl);
-    int* s_gexcl = reinterpret_cast<int*>(smem + SM::off_gexcl);
-    uint64_t* s_gm = reinterpret_cast<uint64_t*>(smem + SM::off_gm);
-    int* ev_ps = reinterpret_cast<int*>(smem + SM::off_evps);
-    int* ev_pg = reinterpret_cast<int*>(smem + SM::off_evpg);
-    uint16_t* ev_pos = reinterpret_cast<uint16_t*>(smem + SM::off_evpos);
-    __shared__ int s_wt[SUBS][3][WARPS];  // per sub-tile: warp totals of (newlines, byte sum, G/C)
-    __shared__ int64_t s_tile_id;
-    __shared__ uint64_t s_excl;
-    __shared__ int s_batch_carry[3];  // last event of the previous window: pos, ps (incl. newline), pg
+    extern __shared__ __align__(16) uint8_t smem_all[];
+    __shared__ uint4 s_wlut[17];  // s_wlut[k]: 0x01 in the first k bytes -- IDP.4A weights of a chunk's head
 
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 17) {
+        const int k = threadIdx.x;
+        auto w = [k](int b) -> uint32_t {  // word holding bytes [b, b+4)
+            const int c = k - b;
+            return c <= 0 ? 0u : (c >= 4 ? 0x01010101u : (0x01010101u >> (8 * (4 - c))));
+        };
+        s_wlut[k] = make_uint4(w(0), w(4), w(8), w(12));
+    }
+    __syncthreads();  // the only block-wide barrier of the kernel
+
+    uint8_t* sm = smem_all + warp * SM::total;
+    int* s_cpre = reinterpret_cast<int*>(sm + SM::off_cpre);
+    uint64_t* s_gm = reinterpret_cast<uint64_t*>(sm + SM::off_gm);
+    int* s_gex = reinterpret_cast<int*>(sm + SM::off_gex);
+    uint16_t* ev_pos = reinterpret_cast<uint16_t*>(sm + SM::off_ev);
+
     const uint8_t* __restrict__ buf = a.buf;
     const int64_t origin = a.begin & ~(int64_t)15;
     uint64_t* chain = reinterpret_cast<uint64_t*>(a.slots);
-    TailRec* recs = reinterpret_cast<TailRec*>(chain + ((a.n_tiles + 1) & ~(int64_t)1));
+    uint64_t* tails = chain + a.n_tiles;
+    const int64_t n_tiles = a.n_tiles;
+    const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
+    const uint32_t pat_nl = c7f & 0x0A0A0A0Au, pat_gc = c7f & 0x43434343u;  // derived from an argument: stay in registers
 
-    if (t == 0) s_tile_id = (int64_t)atomicAdd(a.ticket, 1ull);
-    __syncthreads();
-    const int64_t tile = s_tile_id;
-    const int64_t tile_base = origin + tile * TILE;
+    // fused aggregates of this warp (flushed once at the end)
+    long long f_cnt = 0, f_qs = 0, f_ql = 0;
 
-    // ---- staging: interior tiles take the cheap path (one 64-bit base, 32-bit offsets)
-    if (tile_base >= a.begin && tile_base + TILE <= a.n) {
-        const uint8_t* src = buf + tile_base + t * 16;
+    // ---- staging of one tile into buffer b (asynchronous)
+    const uint32_t dst_lane = (uint32_t)__cvta_generic_to_shared(sm) + (uint32_t)((lane ^ ((lane >> 3) & 3)) << 4);
+    auto issue = [&](int64_t tile, int b) {
+        if (tile < n_tiles) {
+            const int64_t base = origin + tile * WT_BYTES;
+            const uint32_t dst = dst_lane + (uint32_t)(b * WT_BYTES);
+            if (base >= a.begin && base + WT_BYTES <= a.n) {  // interior tile: no clipping
+                const uint8_t* src = buf + base + lane * 16;
 #pragma unroll
-        for (int s = 0; s < SUBS; s++)
+                for (int i = 0; i < 4; i++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + i * 512), "l"(src + i * 512) : "memory");
+            } else {
 #pragma unroll
-            for (int i = 0; i < RUN_CHUNKS; i++)
-                cp_async16(&s_data[s * TILE_CHUNKS + swz(i * BLOCK_THREADS + t)], src + (s * SUB_BYTES + i * BLOCK_THREADS * 16), 16);
-        cp_async_commit();
-    } else {
-#pragma unroll 1
-        for (int s = 0; s < SUBS; s++) stage_tile(s_data + s * TILE_CHUNKS, buf, tile_base + (int64_t)s * SUB_BYTES, origin, a.n);
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-
-    uint8_t* sbytes = reinterpret_cast<uint8_t*>(s_data);
-    // tile-local byte index -> shared memory byte (the swizzle permutes chunks inside a sub-tile only)
-    auto sidx = [](int li) -> int { return ((li >> 14) << 14) + swz((li >> 4) & (TILE_CHUNKS - 1)) * 16 + (li & 15); };
-
-    // Rare per-launch patches (uniform per CTA): bytes before `begin` in the first
-    // chunk are filler; an unterminated last line gets a virtual '\n' at index n.
-    const bool has_begin_pad = (tile == 0 && a.begin != origin);
-    const bool has_eof = a.is_final && (a.n >= tile_base && a.n < tile_base + TILE);
-    if (has_begin_pad || has_eof) {
-        if (t == 0) {
-            if (has_begin_pad)
-                for (int64_t i = origin; i < a.begin; i++) sbytes[sidx((int)(i - origin))] = 0;
-            if (has_eof && a.n > a.begin && buf[a.n - 1] != '\n') sbytes[sidx((int)(a.n - tile_base))] = '\n';
-        }
-        __syncthreads();
-    }
-    auto any_byte = [&](int64_t abs_pos) -> int {  // byte at an absolute offset < tile end that may lie before this tile
-        int64_t li = abs_pos - tile_base;
-        if (li >= 0) return sbytes[sidx((int)li)];
-        return (abs_pos >= (a.prev ? 0 : a.begin)) ? (int)buf[abs_pos] : -1;
-    };
-
-    // ---- A. analysis of the SUBS sub-tiles; scatters the events with rank in [win_lo, win_lo + EV_CAP)
-    int total_cnt = 0, total_s = 0, total_g = 0;
-    auto analyse = [&](int win_lo) {
-        total_cnt = total_s = total_g = 0;
-#pragma unroll 1
-        for (int s = 0; s < SUBS; s++) {
-            const uint4* d = s_data + s * TILE_CHUNKS;
-            uint64_t pm, gm = 0;
-            int rs = 0;  // signed byte sum of the run
-            {
-                const uint4 c0 = d[swz(4 * t + 0)], c1 = d[swz(4 * t + 1)], c2 = d[swz(4 * t + 2)], c3 = d[swz(4 * t + 3)];
-                pm = ((uint64_t)(nl_mask16(c2) | (nl_mask16(c3) << 16)) << 32) | (nl_mask16(c0) | (nl_mask16(c1) << 16));
-                if (kSeq) gm = ((uint64_t)(gc_mask16b(c2) | (gc_mask16b(c3) << 16)) << 32) | (gc_mask16b(c0) | (gc_mask16b(c1) << 16));
-                if (kQual) rs = sbyte_sum16(c3, sbyte_sum16(c2, sbyte_sum16(c1, sbyte_sum16(c0, 0))));
-            }
-            const int cnt = __popcll(pm);
-            const int gtot = kSeq ? __popcll(gm) : 0;
-            // warp scan: newlines (<= 2048 per warp: 12 bits) and byte sum (|.| <= 2^18: 20 bits signed) share one word
-            const uint32_t packed = ((uint32_t)cnt << 20) + (uint32_t)rs;
-            const uint32_t incl = warp_incl_scan_u32(packed);
-            const uint32_t ex = incl - packed;
-            const int ex_s = ((int)(ex << 12)) >> 12;
-            const int ex_cnt = (int)((ex - (uint32_t)ex_s) >> 20);
-            int ex_g = 0, in_g = 0;
-            if (kSeq) {
-                in_g = (int)warp_incl_scan_u32((uint32_t)gtot);
-                ex_g = in_g - gtot;
-            }
-            if (lane == 31) {
-                const int in_s = ((int)(incl << 12)) >> 12;
-                s_wt[s][0][warp] = (int)((incl - (uint32_t)in_s) >> 20);
-                s_wt[s][1][warp] = in_s;
-                s_wt[s][2][warp] = in_g;
-            }
-            __syncthreads();
-            // cross-warp exclusive scan of the 8 warp totals (every warp redoes it in its low lanes)
-            int wc = lane < WARPS ? s_wt[s][0][lane] : 0, ws = lane < WARPS ? s_wt[s][1][lane] : 0;
-            int wg = (kSeq && lane < WARPS) ? s_wt[s][2][lane] : 0;
-            int ic = wc, is_ = ws, ig = wg;
-#pragma unroll
-            for (int dd = 1; dd < WARPS; dd <<= 1) {
-                const int oc = __shfl_up_sync(0xffffffffu, ic, dd), os = __shfl_up_sync(0xffffffffu, is_, dd);
-                const int og = kSeq ? __shfl_up_sync(0xffffffffu, ig, dd) : 0;
-                if (lane >= dd) {
-                    ic += oc;
-                    is_ += os;
-                    ig += og;
+                for (int i = 0; i < 4; i++) {
+                    const int64_t g = base + (int64_t)(i * 32 + lane) * 16;
+                    const int64_t rem = a.n - g;
+                    const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);  // bytes beyond n are zero-filled
+                    const uint8_t* src = nb > 0 ? buf + g : buf;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + i * 512), "l"(src), "r"(nb) : "memory");
                 }
             }
-            const int off_cnt = __shfl_sync(0xffffffffu, ic - wc, warp), off_s = __shfl_sync(0xffffffffu, is_ - ws, warp);
-            const int off_g = kSeq ? __shfl_sync(0xffffffffu, ig - wg, warp) : 0;
-            const int sc = __shfl_sync(0xffffffffu, ic, WARPS - 1), ss = __shfl_sync(0xffffffffu, is_, WARPS - 1);
-            const int sg = kSeq ? __shfl_sync(0xffffffffu, ig, WARPS - 1) : 0;
-            const int run = s * BLOCK_THREADS + t;
-            if (kQual) s_sexcl[run] = total_s + off_s + ex_s;
-            if (kSeq) {
-                s_gexcl[run] = total_g + off_g + ex_g;
-                s_gm[run] = gm;
+        }
+        cp_async_commit();
+    };
+    unsigned long long ticket_raw = 0;
+    auto take_ticket = [&]() {
+        if (lane == 0) ticket_raw = atomicAdd(a.ticket, 1ull);
+    };
+    auto ticket_value = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, ticket_raw, 0); };
+
+    take_ticket();
+    int64_t cur = ticket_value();
+    if (cur == 0 && lane == 0 && a.prev) {  // chained range: errors of earlier ranges stay visible in the last result
+        if (a.prev->err_pos != 0ull) atomicMax(&a.result->err_pos, a.prev->err_pos);
+        if (a.prev->overflow) a.result->overflow = 1;
+    }
+    issue(cur, 0);
+    take_ticket();
+    int b = 0;
+
+    while (cur < n_tiles) {
+        const int64_t nxt = ticket_value();
+        issue(nxt, b ^ 1);
+        take_ticket();  // for the tile after next; its latency hides behind this tile's work
+        cp_async_wait<1>();
+        __syncwarp();
+
+        const int64_t tile = cur;
+        const int64_t tile_base = origin + tile * WT_BYTES;
+        uint8_t* sbytes = sm + b * WT_BYTES;
+        const uint4* d = reinterpret_cast<const uint4*>(sbytes);
+
+        // Rare per-launch patches: bytes before `begin` in the first chunk are filler; an
+        // unterminated last line gets a virtual '\n' at index n.
+        const bool has_begin_pad = (tile == 0 && a.begin != origin);
+        const bool has_eof = a.is_final && (a.n >= tile_base && a.n < tile_base + WT_BYTES);
+        if (has_begin_pad || has_eof) {
+            if (lane == 0) {
+                if (has_begin_pad)
+                    for (int64_t i = origin; i < a.begin; i++) sbytes[sidx((int)(i - origin))] = 0;
+                if (has_eof) {
+                    const bool open = a.n > a.begin ? buf[a.n - 1] != '\n' : (a.prev && a.prev->open_line_start < a.n);
+                    if (open) sbytes[sidx((int)(a.n - tile_base))] = '\n';
+                }
             }
-            {  // events of this run, in order
-                int rank = total_cnt + off_cnt + ex_cnt - win_lo;
-                uint64_t m = pm;
-                const int p0 = s * SUB_BYTES + t * RUN_BYTES;
+            __syncwarp();
+        }
+        auto any_byte = [&](int64_t abs_pos) -> int {  // byte at an absolute offset < tile end that may lie before this tile
+            const int64_t li = abs_pos - tile_base;
+            if (li >= 0) return sbytes[sidx((int)li)];
+            return (abs_pos >= (a.prev ? 0 : a.begin)) ? (int)buf[abs_pos] : -1;
+        };
+
+        // ---- A. analysis of the lane's 64-byte run
+        uint64_t pm, gm = 0;
+        int ex_s = 0, ex_g = 0, ex_cnt, n_events, total_s = 0, total_g = 0;
+        {
+            const int x = (lane >> 1) & 3, rb = 4 * lane;
+            const uint4 c0 = d[rb + (0 ^ x)], c1 = d[rb + (1 ^ x)], c2 = d[rb + (2 ^ x)], c3 = d[rb + (3 ^ x)];
+            pm = ((uint64_t)(nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16)) << 32) |
+                 (nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16));
+            int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            if (kQual) {
+                s0 = sbyte_sum16(c0, 0);
+                s1 = sbyte_sum16(c1, s0);
+                s2 = sbyte_sum16(c2, s1);
+                s3 = sbyte_sum16(c3, s2);
+            }
+            int gtot = 0;
+            if (kSeq) {
+                gm = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
+                     (gc_mask16r(c0, c7b, c7f, pat_gc) | (gc_mask16r(c1, c7b, c7f, pat_gc) << 16));
+                gtot = __popcll(gm);
+            }
+            const int cnt = __popcll(pm);
+            // newlines (<= 2048 per tile: 12 bits) and byte sum (|.| <= 2^18: 20 bits signed) share one scan word
+            const uint32_t packed = ((uint32_t)cnt << 20) + (uint32_t)(kQual ? s3 : gtot);
+            const uint32_t incl = warp_incl_scan_u32(packed);
+            const uint32_t ex = incl - packed;
+            const int ex_lo = ((int)(ex << 12)) >> 12;
+            ex_cnt = (int)((ex - (uint32_t)ex_lo) >> 20);
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            const int tot_lo = ((int)(tot << 12)) >> 12;
+            n_events = (int)((tot - (uint32_t)tot_lo) >> 20);
+            if (kQual) {
+                ex_s = ex_lo;
+                total_s = tot_lo;
+                if (kSeq) {
+                    const uint32_t gi = warp_incl_scan_u32((uint32_t)gtot);
+                    ex_g = (int)(gi - (uint32_t)gtot);
+                    total_g = (int)__shfl_sync(0xffffffffu, gi, 31);
+                }
+            } else if (kSeq) {
+                ex_g = ex_lo;
+                total_g = tot_lo;
+            }
+            // the count is all the chain needs: publish it before anything else
+            if (lane == 0) {
+                if (tile == 0) st_relaxed_u64(chain, CH_INC | ((init + (uint64_t)n_events) & CH_VAL));
+                else st_relaxed_u64(chain + tile, CH_AGG | (uint64_t)n_events);
+            }
+            if (kQual) *reinterpret_cast<int4*>(s_cpre + rb) = make_int4(ex_s, ex_s + s0, ex_s + s1, ex_s + s2);
+            if (kSeq) {
+                s_gm[lane] = gm;
+                s_gex[lane] = ex_g;
+            }
+        }
+        // newline positions with rank in [win_lo, win_lo + EV_CAP), in order
+        auto scatter = [&](int win_lo) {
+            int rank = ex_cnt - win_lo;
+            const int p0 = lane * 64;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t m = h ? (uint32_t)(pm >> 32) : (uint32_t)pm;
                 while (m) {
-                    const int k = __ffsll((long long)m) - 1;
+                    const int k = __ffs((int)m) - 1;
                     m &= m - 1;
-                    if ((unsigned)rank < (unsigned)EV_CAP) ev_pos[rank] = (uint16_t)(p0 + k);
+                    if ((unsigned)rank < (unsigned)EV_CAP) ev_pos[rank] = (uint16_t)(p0 + h * 32 + k);
                     rank++;
                 }
             }
-            total_cnt += sc;
-            total_s += ss;
-            total_g += sg;
+        };
+        scatter(0);
+        __syncwarp();
+
+        // prefix sums at a newline position (tile-local): byte sum / G,C count of everything before it
+        auto event_prefix = [&](int pos, int& ps, int& pg) {
+            if (kQual) {
+                const int q = pos >> 4;
+                const uint4 v = d[q ^ ((q >> 3) & 3)];
+                const uint4 w = s_wlut[pos & 15];
+                int acc = s_cpre[q];
+                acc = __dp4a((int)v.x, (int)w.x, acc);
+                acc = __dp4a((int)v.y, (int)w.y, acc);
+                acc = __dp4a((int)v.z, (int)w.z, acc);
+                acc = __dp4a((int)v.w, (int)w.w, acc);
+                ps = acc;
+            }
+            if (kSeq) pg = s_gex[pos >> 6] + __popcll(s_gm[pos >> 6] & low_bits64(pos & 63));
+        };
+
+        // ---- B. tail word: position / sums after the tile's last newline (local information only)
+        int last_pos = -1, last_ps = 0, last_pg = 0;
+        if (n_events > 0) {
+            const uint32_t have = __ballot_sync(0xffffffffu, pm != 0);
+            const int top = 31 - __clz((int)have);
+            const int hi = 63 - __clzll((long long)pm);  // meaningful in lane `top`
+            last_pos = top * 64 + __shfl_sync(0xffffffffu, hi, top);
+            event_prefix(last_pos, last_ps, last_pg);
+            if (lane == 0)
+                st_relaxed_u64(tails + tile, tail_pack(2, (uint32_t)(last_pos + 1), (uint32_t)(total_g - last_pg), total_s - (last_ps + 10)));
+        } else if (lane == 0) {
+            st_relaxed_u64(tails + tile, tail_pack(1, 0, (uint32_t)total_g, total_s));
         }
-        __syncthreads();  // event list complete
-    };
-    // ---- B. prefix sums at the newlines of the current window (one per lane)
-    auto event_prefixes = [&](int nev) {
-        if (kQual || kSeq) {
-            for (int i = t; i < nev; i += BLOCK_THREADS) {
-                const int pos = ev_pos[i];
-                const int run = pos >> 6, k = pos & 63;
-                if (kQual) {
-                    const uint4* d = s_data + (run >> 8) * TILE_CHUNKS;
-                    const int q = 4 * (run & 255);
-                    int ps = s_sexcl[run];
-                    const int j = k >> 4;
-                    if (j > 0) ps = sbyte_sum16(d[swz(q)], ps);
-                    if (j > 1) ps = sbyte_sum16(d[swz(q + 1)], ps);
-                    if (j > 2) ps = sbyte_sum16(d[swz(q + 2)], ps);
-                    ev_ps[i] = ps + sbyte_sum_prefix16(d[swz(q + j)], k & 15);
-                }
-                if (kSeq) ev_pg[i] = s_gexcl[run] + __popcll(s_gm[run] & low_bits64(k));
-            }
+
+        // ---- C. prefixes of the first 32 events (they do not depend on other tiles)
+        int pos = 0, ps = 0, pg = 0;
+        if (lane < n_events) {
+            pos = ev_pos[lane];
+            event_prefix(pos, ps, pg);
         }
-        __syncthreads();
-    };
-    // ---- D. emission of the current window
-    auto emit = [&](int lo, int nev, uint64_t excl) {
-        for (int i = t; i < nev; i += BLOCK_THREADS) {
-            const uint64_t g = excl + (uint64_t)(lo + i);  // global index of the line this newline ends
-            if (g >= a.max_lines) continue;
-            const int pos = ev_pos[i];
-            const int64_t e = tile_base + pos;
-            long long len, ssum = 0, gsum = 0;
-            int first_byte;  // first byte of the line
-            if (i > 0 || lo > 0) {
-                const int ppos = i > 0 ? (int)ev_pos[i - 1] : s_batch_carry[0];
-                len = pos - ppos - 1;
-                if (kQual) ssum = ev_ps[i] - (i > 0 ? ev_ps[i - 1] + 10 : s_batch_carry[1]);
-                if (kSeq) gsum = ev_pg[i] - (i > 0 ? ev_pg[i - 1] : s_batch_carry[2]);
-                first_byte = sbytes[sidx(ppos + 1)];
-            } else {  // the line that was open when the tile began
-                int64_t st0, s0, g0;
-                open_line_before(recs, tile, a, st0, s0, g0);
-                len = e - st0;
-                if (kQual) ssum = ev_ps[i] + s0;
-                if (kSeq) gsum = ev_pg[i] + g0;
-                first_byte = any_byte(st0);
-            }
-            // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing
-            int cr = 0;
-            if (len > 0 && !(a.is_final && e == a.n)) cr = (pos > 0 ? (int)sbytes[sidx(pos - 1)] : any_byte(e - 1)) == '\r';
-            len -= cr;
-            const int ph = (int)(g & 3);
-            const uint64_t r = g >> 2;
-            if (kLines) {
-                if (g < (uint64_t)a.line_cap)
-                    reinterpret_cast<OffT*>(a.line_end)[g] = (OffT)e;
-                else
-                    a.result->overflow = 1;
-            }
-            if ((ph & 1) == 0) {  // header / plus line: its first byte must be '@' / '+'
-                if (first_byte != (ph == 0 ? '@' : '+')) atomicMin(&a.result->err_pos, (unsigned long long)(e - len - cr));
-            } else if (r < (uint64_t)a.rec_cap) {
-                if (ph == 1) {
-                    if (kSeq) {
-                        a.seq_len[r] = (uint32_t)len;
-                        a.gc[r] = (uint32_t)gsum;
-                    }
-                } else if (kQual) {
-                    a.qual_len[r] = (uint32_t)len;
-                    a.qsum[r] = (int32_t)(ssum - 13 * cr - 33 * len);
-                }
+
+        // ---- D. chaining: global line index of the tile's first newline; the open line
+        uint64_t excl = init;
+        if (tile > 0) excl = lookback_count(chain, tile, (uint32_t)n_events, init);
+        OpenLine open;
+        open.start = 0;
+        open.s = open.g = 0;
+        const bool is_last = tile == n_tiles - 1;
+        if (n_events > 0 || is_last) open = open_line_before(tails, tile, origin, a);
+
+        if (is_last && lane == 0) {  // final state of this range (chaining / host)
+            a.result->total_lines = excl + (uint64_t)n_events;
+            if (n_events > 0) {
+                a.result->open_line_start = tile_base + last_pos + 1;
+                a.result->tail_s = total_s - (last_ps + 10);
+                a.result->tail_g = total_g - last_pg;
             } else {
-                a.result->overflow = 1;
+                a.result->open_line_start = open.start;
+                a.result->tail_s = (int64_t)open.s + total_s;
+                a.result->tail_g = (int64_t)open.g + total_g;
             }
         }
-    };
 
-    analyse(0);
-    const int n_events = total_cnt;
-    const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
-    if (t == 0) {  // the count is all the chain needs: publish it before anything else
-        if (tile == 0) st_release_u64(&chain[0], CH_INC | ((init + (uint64_t)n_events) & CH_VAL));
-        else st_release_u64(&chain[tile], CH_AGG | (uint64_t)n_events);
-        if (a.prev && tile == 0) {  // chained range: errors of earlier ranges stay visible in the last result
-            if (a.prev->err_pos != ~0ull) atomicMin(&a.result->err_pos, a.prev->err_pos);
-            if (a.prev->overflow) a.result->overflow = 1;
-        }
-    }
-    const bool dense = n_events > EV_CAP;  // more newlines than the event window holds (rare): windows are re-analysed
-    if (dense) analyse(((n_events - 1) / EV_CAP) * EV_CAP);
-    const int last_nev = n_events - ((n_events - 1) / EV_CAP) * EV_CAP;  // events in the window that holds the last one
-    event_prefixes(dense ? last_nev : n_events);
-
-    // tail record (local information only), then the look-back of the count by warp 0
-    TailRec mine;
-    if (n_events > 0) {
-        const int li = (dense ? last_nev : n_events) - 1;
-        mine.state = 2;
-        mine.line_start = tile_base + ev_pos[li] + 1;
-        mine.tail_s = kQual ? total_s - (ev_ps[li] + 10) : 0;
-        mine.tail_g = kSeq ? total_g - ev_pg[li] : 0;
-    } else {
-        mine.state = 1;
-        mine.line_start = 0;
-        mine.tail_s = total_s;
-        mine.tail_g = total_g;
-    }
-    if (warp == 0) {
-        if (lane == 0) {
-            recs[tile].line_start = mine.line_start;
-            recs[tile].tail_s = mine.tail_s;
-            recs[tile].tail_g = mine.tail_g;
-            __threadfence();
-            st_release_u64(&recs[tile].state, mine.state);
-        }
-        const uint64_t ex = warp_lookback(chain, tile, (uint64_t)n_events, init);
-        if (lane == 0) s_excl = ex;
-    }
-    __syncthreads();
-    const uint64_t excl = s_excl;
-
-    if (tile == a.n_tiles - 1 && t == 0) {  // final state of this range (chaining / host)
-        int64_t st = mine.line_start, s2 = mine.tail_s, g2 = mine.tail_g;
-        if (mine.state != 2) {
-            open_line_before(recs, tile, a, st, s2, g2);
-            s2 += mine.tail_s;
-            g2 += mine.tail_g;
-        }
-        a.result->total_lines = excl + (uint64_t)n_events;
-        a.result->open_line_start = st;
-        a.result->tail_s = s2;
-        a.result->tail_g = g2;
-    }
-
-    if (!dense) {
-        emit(0, n_events, excl);
-    } else {
-        for (int lo = 0; lo < n_events; lo += EV_CAP) {
-            const int nev = min(EV_CAP, n_events - lo);
-            __syncthreads();
-            analyse(lo);
-            event_prefixes(nev);
-            emit(lo, nev, excl);
-            __syncthreads();
-            if (t == 0) {  // carry the window's last event into the next one
-                s_batch_carry[0] = ev_pos[nev - 1];
-                s_batch_carry[1] = kQual ? ev_ps[nev - 1] + 10 : 0;
-                s_batch_carry[2] = kSeq ? ev_pg[nev - 1] : 0;
+        // ---- E. emission, 32 events per pass
+        int c_pos = 0, c_ps = 0, c_pg = 0;  // last event of the previous pass (ps includes that newline)
+        for (int lo = 0; lo < n_events; lo += 32) {
+            if (lo > 0) {
+                if ((lo & (EV_CAP - 1)) == 0) {  // more newlines than the event window holds (rare): refill it
+                    __syncwarp();
+                    scatter(lo);
+                    __syncwarp();
+                }
+                if (lo + lane < n_events) {
+                    pos = ev_pos[(lo & (EV_CAP - 1)) + lane];
+                    event_prefix(pos, ps, pg);
+                }
             }
+            const bool active = lo + lane < n_events;
+            int ppos = __shfl_up_sync(0xffffffffu, pos, 1), pps = 0, ppg = 0;
+            if (kQual) pps = __shfl_up_sync(0xffffffffu, ps, 1) + 10;
+            if (kSeq) ppg = __shfl_up_sync(0xffffffffu, pg, 1);
+            if (lane == 0) {
+                ppos = c_pos;
+                pps = c_ps;
+                ppg = c_pg;
+            }
+            if (active) {
+                const uint64_t g = excl + (uint64_t)(lo + lane);  // global index of the line this newline ends
+                const bool first_of_tile = (lo + lane) == 0;
+                uint32_t len;
+                int ssum = 0, gsum = 0, first_byte;
+                int64_t line_start;
+                if (!first_of_tile) {
+                    len = (uint32_t)(pos - ppos - 1);
+                    if (kQual) ssum = ps - pps;
+                    if (kSeq) gsum = pg - ppg;
+                    line_start = tile_base + ppos + 1;
+                } else {  // the line that was open when the tile began
+                    line_start = open.start;
+                    len = (uint32_t)(tile_base - open.start) + (uint32_t)pos;
+                    if (kQual) ssum = ps + open.s;
+                    if (kSeq) gsum = pg + open.g;
+                }
+                const int64_t e = tile_base + pos;
+                if (g < a.max_lines) {
+                    // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing
+                    uint32_t cr = 0;
+                    if (len > 0 && !(a.is_final && e == a.n)) cr = (pos > 0 ? (int)sbytes[sidx(pos - 1)] : any_byte(e - 1)) == '\r';
+                    len -= cr;
+                    const int ph = (int)(g & 3);
+                    const uint64_t r = g >> 2;
+                    if (kLines) {
+                        if (g < (uint64_t)a.line_cap) reinterpret_cast<OffT*>(a.line_end)[g] = (OffT)e;
+                        else a.result->overflow = 1;
+                    }
+                    if ((ph & 1) == 0) {  // header / plus line: its first byte must be '@' / '+'
+                        first_byte = first_of_tile ? any_byte(line_start) : (int)sbytes[sidx(ppos + 1)];
+                        if (first_byte != (ph == 0 ? '@' : '+')) atomicMax(&a.result->err_pos, ~(unsigned long long)line_start);
+                    } else if (ph == 1) {
+                        if (kSeq) {
+                            if (r < (uint64_t)a.rec_cap) {
+                                a.seq_len[r] = len;
+                                a.gc[r] = (uint32_t)gsum;
+                            } else {
+                                a.result->overflow = 1;
+                            }
+                        }
+                    } else if (kQual) {
+                        const int qs = ssum - 13 * (int)cr - 33 * (int)len;
+                        if (kFused) {
+                            bool ok = true;
+                            for (int i = 0; i < a.n_fused; i++) {
+                                const exb_predicate p = a.fused[i];
+                                ok = ok && (p.field == EXB_P_MEAN_QUALITY ? exb_mean_cmp((int64_t)qs, len, p.op, p.value)
+                                                                          : exb_cmp((double)len, p.op, p.value));
+                            }
+                            if (ok) {
+                                f_cnt += 1;
+                                f_qs += qs;
+                                f_ql += len;
+                            }
+                        } else if (r < (uint64_t)a.rec_cap) {
+                            a.qual_len[r] = len;
+                            a.qsum[r] = qs;
+                        } else {
+                            a.result->overflow = 1;
+                        }
+                    }
+                }
+            }
+            c_pos = __shfl_sync(0xffffffffu, pos, 31);
+            if (kQual) c_ps = __shfl_sync(0xffffffffu, ps, 31) + 10;
+            if (kSeq) c_pg = __shfl_sync(0xffffffffu, pg, 31);
+        }
+
+        __syncwarp();  // the event list / prefix arrays are rewritten by the next tile
+        cur = nxt;
+        b ^= 1;
+    }
+    cp_async_wait<0>();
+
+    if (kFused) {  // one flush per warp
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) {
+            f_cnt += __shfl_xor_sync(0xffffffffu, f_cnt, dd);
+            f_qs += __shfl_xor_sync(0xffffffffu, f_qs, dd);
+            f_ql += __shfl_xor_sync(0xffffffffu, f_ql, dd);
+        }
+        if (lane == 0 && f_cnt != 0) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.fused_agg) + 0, (unsigned long long)f_cnt);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.fused_agg) + 3, (unsigned long long)f_qs);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.fused_agg) + 4, (unsigned long long)f_ql);
         }
     }
 }
 
 // ------------------------------------------------------------------ launcher
-template <typename OffT, int FLAGS, int SUBS>
-static cudaError_t launch_one(FastqScanArgs a, cudaStream_t st) {
-    constexpr int smem = FqSmem<FLAGS, SUBS>::total;
-    auto kern = fastq_scan_kernel<OffT, FLAGS, SUBS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    a.n_tiles = (a.n_tiles + SUBS - 1) / SUBS;  // the caller counted 16 KiB sub-tiles
-    kern<<<dim3((unsigned)a.n_tiles), dim3(BLOCK_THREADS), smem, st>>>(a);
+int64_t fastq_scan_tiles(int64_t begin, int64_t n, int is_final) {
+    const int64_t origin = begin & ~(int64_t)15;
+    // final range: +1 byte of room for the virtual terminator at n
+    const int64_t t = (n + (is_final ? 1 : 0) - origin + WT_BYTES - 1) / WT_BYTES;
+    return t > 0 ? t : 1;
+}
+int64_t fastq_scan_chain_bytes(int64_t n_tiles) { return n_tiles * 16; }  // count word + tail word per tile
+
+template <typename OffT, int FLAGS>
+static cudaError_t launch_one(const FastqScanArgs& a, cudaStream_t st) {
+    constexpr int smem = FqWarpSmem<FLAGS>::total * FQ_WARPS;
+    auto kern = fastq_scan_kernel<OffT, FLAGS>;
+    static int ctas_per_sm = 0, n_sm = 0;  // per template instance; one device type per process
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, occ = 0, sms = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FQ_THREADS, smem)) != cudaSuccess) return e;
+        n_sm = sms;
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    int64_t grid = (a.n_tiles + FQ_WARPS - 1) / FQ_WARPS;
+    const int64_t persistent = (int64_t)n_sm * ctas_per_sm;
+    if (grid > persistent) grid = persistent;
+    // 0x7F7F7F7F / 0x7B7B7B7B travel as arguments so that ptxas keeps them in registers (see eq_flags)
+    kern<<<dim3((unsigned)grid), dim3(FQ_THREADS), smem, st>>>(a, 0x7F7F7F7Fu, 0x7B7B7B7Bu);
     return cudaGetLastError();
 }
 
 template <typename OffT>
 static cudaError_t launch_fastq(const FastqScanArgs& a, int flags, cudaStream_t st) {
-    constexpr int SUBS = EXB_FASTQ_SUBS;
+    if (flags & EXB_F_FUSED) {  // quality-line predicates + COUNT, nothing per record leaves the kernel
+        return (flags & EXB_F_LINES) ? launch_one<OffT, EXB_F_FUSED | EXB_F_QUAL | EXB_F_LINES>(a, st)
+                                     : launch_one<OffT, EXB_F_FUSED | EXB_F_QUAL>(a, st);
+    }
     switch (flags & 7) {
-    case 0: return launch_one<OffT, 0, SUBS>(a, st);
-    case 1: return launch_one<OffT, 1, SUBS>(a, st);
-    case 2: return launch_one<OffT, 2, SUBS>(a, st);
-    case 3: return launch_one<OffT, 3, SUBS>(a, st);
-    case 4: return launch_one<OffT, 4, SUBS>(a, st);
-    case 5: return launch_one<OffT, 5, SUBS>(a, st);
-    case 6: return launch_one<OffT, 6, SUBS>(a, st);
-    default: return launch_one<OffT, 7, SUBS>(a, st);
+    case 0: return launch_one<OffT, 0>(a, st);
+    case 1: return launch_one<OffT, 1>(a, st);
+    case 2: return launch_one<OffT, 2>(a, st);
+    case 3: return launch_one<OffT, 3>(a, st);
+    case 4: return launch_one<OffT, 4>(a, st);
+    case 5: return launch_one<OffT, 5>(a, st);
+    case 6: return launch_one<OffT, 6>(a, st);
+    default: return launch_one<OffT, 7>(a, st);
     }
 }
 

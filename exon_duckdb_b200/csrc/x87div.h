@@ -97,6 +97,20 @@ EXB_HD bool exb_cmp(double v, int op, double c) {
 // list_avg(...) <op> c for a list of n ints summing to `sum`; empty list = NULL = false.
 EXB_HD bool exb_mean_cmp(int64_t sum, uint32_t n, int op, double c) {
     if (n == 0) return false;
+    // Division-free verdict when sum/n is clearly on one side of c: D = sum - c*n has the sign of
+    // sum/n - c, and |D| > 1e-14 |c n| puts the exact quotient more than 40 ulp away from c, which
+    // neither of the two roundings can cross.  (t and d carry <= 2 ulp of error themselves.)
+    {
+        const double t = c * (double)n, d = (double)sum - t;
+        if (fabs(d) > fabs(t) * 1e-14) {
+            switch (op) {
+            case 0: case 1: return d > 0;
+            case 2: case 3: return d < 0;
+            case 4: return false;
+            default: return true;
+            }
+        }
+    }
     double q = (double)sum / (double)n;  // correctly rounded once; x87 may differ by 1 ulp
     double d = fabs(q - c);
     if (d > fabs(q) * 8.8817841970012523e-16) return exb_cmp(q, op, c);  // > 4 ulp away: same verdict

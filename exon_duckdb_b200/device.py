@@ -151,6 +151,45 @@ def fastq_filter(scan, n_records, preds, want_pass=False, agg=None, device_count
     return agg, pas
 
 
+class FastqCount:
+    """Outputs of one fused exb_fastq_scan_filter launch: `agg` (int64[8] device tensor) and the scan's result block."""
+
+    def __init__(self):
+        self.agg = None
+        self.ws = None
+        self._res = None
+
+    @property
+    def result(self):
+        if self._res is None:
+            self._res = fetch_result(self.ws)
+        return self._res
+
+    def validate(self):
+        r = self.result
+        if r.err_pos != NO_POS:
+            raise FormatError("malformed FASTQ record at byte %d" % r.err_pos, r.err_pos)
+        if r.total_lines % 4 != 0:
+            raise FormatError("truncated FASTQ record: %d lines" % r.total_lines)
+        return int(r.total_lines // 4)
+
+
+def fastq_scan_filter(buf, preds, n=None, out=None):
+    """COUNT-style read_fastq + quality-line predicates in ONE kernel (asynchronous): nothing per record is written.
+
+    preds: [(field, op, value)] with field 'mean_quality' or 'qual_len'.  Returns a FastqCount (reuse it through `out`)."""
+    n = buf.numel() if n is None else int(n)
+    dev = buf.device
+    c = out if out is not None else FastqCount()
+    if out is None:
+        c.agg = torch.zeros(8, dtype=torch.int64, device=dev)
+        c.ws = workspace(n + 16, dev)
+    c._res = None
+    arr, k = _lib.predicates(preds)
+    check(lib().exb_fastq_scan_filter(_ptr(buf), 0, n, 1, None, arr, k, _ptr(c.agg), 0, _ptr(c.ws), c.ws.numel(), _stream()))
+    return c
+
+
 def exclusive_scan_u32(x, n=None):
     n = x.numel() if n is None else n
     out = torch.empty(n + 1, dtype=torch.int64, device=x.device)

@@ -205,6 +205,21 @@ EXB_API int exb_fastq_filter(const uint32_t *d_seq_len, const uint32_t *d_gc, co
                              const int32_t *d_qsum, int64_t n_records, const exb_predicate *preds, int n_preds,
                              uint8_t *d_pass, int64_t *d_agg, const void *d_scan_workspace, void *stream);
 
+/*
+ * Scan and filter in one kernel, for COUNT-style queries whose predicates only
+ * read the quality line (EXB_P_MEAN_QUALITY, EXB_P_QUAL_LEN) -- the C2 query
+ *   SELECT COUNT(*) FROM read_fastq(f) WHERE list_avg(quality_score_string_to_list(quality_scores)) > c
+ * Same scan as exb_fastq_scan (same chaining rules, same result block: check
+ * err_pos and total_lines % 4 after exb_scan_result_fetch), but each quality
+ * line is tested as it is emitted and nothing per record is written:
+ *   d_agg[0] = passing records, d_agg[3] = sum qsum, d_agg[4] = sum qual_len over
+ *   them (the other entries stay 0).  accumulate = 0 clears d_agg (int64_t[8])
+ *   first; 1 adds to it (later ranges of a chained scan).
+ */
+EXB_API int exb_fastq_scan_filter(const void *d_buf, int64_t begin, int64_t n, int is_final, const void *d_prev_workspace,
+                                  const exb_predicate *preds, int n_preds, int64_t *d_agg, int accumulate,
+                                  void *d_workspace, int64_t workspace_bytes, void *stream);
+
 /* Field extents of FASTQ records from the line index: d_lens is uint32_t[4][n_records]
  * (name, description, sequence, quality_scores); d_desc_valid uint8_t[n_records]
  * (0 = NULL description).  d_sel (optional) lists the records to take; d_starts (optional)

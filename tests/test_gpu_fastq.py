@@ -213,3 +213,54 @@ def test_chained_ranges_equal_one_pass(cuda_device):
     for a, b in ((line[:4 * n], one.line_end[:4 * n]), (sl[:n], one.seq_len[:n]), (gc[:n], one.gc[:n]), (ql[:n], one.qual_len[:n]),
                  (qs[:n], one.qsum[:n])):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("seed,n,kw", [(61, 3000, {}), (62, 500, dict(crlf=True, final_eol=False)), (63, 40, dict(min_len=3000, max_len=40000)),
+                                         (64, 5000, dict(max_len=0)), (65, 1, {})])
+def test_fused_scan_filter_equals_scan_then_filter(cuda_device, seed, n, kw):
+    """exb_fastq_scan_filter (one kernel, nothing per record written) == exb_fastq_scan + exb_fastq_filter == oracle."""
+    from exon_duckdb_b200 import device as D
+    from oracle import oracle as O
+    text, _ = util.random_fastq(seed, n, **kw)
+    buf = D.to_device(text, cuda_device)
+    scan = D.fastq_scan_sync(buf)
+    assert scan.validate() == n
+    quals = O.parse_fastq(text).strings("quality_scores")
+    for preds in ([("mean_quality", ">", 45.0)], [("mean_quality", "<=", 46.5), ("qual_len", ">", 10)], [], [("qual_len", "=", 0)]):
+        want, _ = D.fastq_filter(scan, n, preds)
+        got = D.fastq_scan_filter(buf, preds)
+        assert got.validate() == n
+        w, g = want.cpu().tolist(), got.agg.cpu().tolist()
+        assert (g[0], g[3], g[4]) == (w[0], w[3], w[4]), preds
+        ops = {"mean_quality": lambda q, op, v: O.mean_quality_pass(q, op, v),
+               "qual_len": lambda q, op, v: {">": len(q) > v, "=": len(q) == v}[op]}
+        assert g[0] == sum(all(ops[f](q, op, v) for f, op, v in preds) for q in quals)
+
+
+def test_fused_scan_filter_generated_illumina(cuda_device):
+    from exon_duckdb_b200 import device as D
+    from oracle import oracle as O
+    buf, text = _gen(cuda_device, "illumina", 30000, seed=20)
+    c = D.fastq_scan_filter(buf, [("mean_quality", ">", 30.0)])
+    assert c.validate() == 30000
+    assert c.agg.cpu().tolist()[0] == O.fastq_count_mean_quality(text, ">", 30.0)[0]
+    # reuse of the workspace / aggregate buffers across launches (what bench.py does every step)
+    for _ in range(3):
+        D.fastq_scan_filter(buf, [("mean_quality", ">", 30.0)], out=c)
+    assert c.validate() == 30000
+    assert c.agg.cpu().tolist()[0] == O.fastq_count_mean_quality(text, ">", 30.0)[0]
+
+
+def test_fused_scan_filter_rejects_malformed(cuda_device):
+    from exon_duckdb_b200 import device as D
+    bad = b"@a\nACGT\n+\nIIII\n" * 300 + b"a\nACGT\n+\nIIII\n"
+    with pytest.raises(D.FormatError) as e:
+        D.fastq_scan_filter(D.to_device(bad, cuda_device), [("mean_quality", ">", 1.0)]).validate()
+    assert e.value.pos == 15 * 300
+    with pytest.raises(_lib_error()):
+        D.fastq_scan_filter(D.to_device(bad, cuda_device), [("gc_content", ">", 0.5)])
+
+
+def _lib_error():
+    from exon_duckdb_b200 import _lib
+    return _lib.ExonError
