@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libexon_b200.so")
+LIB_PATH = os.environ.get("EXON_B200_LIB") or os.path.join(_HERE, "libexon_b200.so")  # override: debug builds only
 
 # flags / enums (mirror include/exon_b200.h)
 F_LINES, F_SEQ, F_QUAL = 1, 2, 4

@@ -123,6 +123,18 @@ __device__ __forceinline__ int sidx(int li) {
     return ((q ^ ((q >> 3) & 3)) << 4) | (li & 15);
 }
 
+#ifdef EXB_FQ_TRACE
+__device__ unsigned long long* g_fq_trace;  // 4 words per tile: t(publish), t(resolved), spins | last<<32, t(ticket)
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FQ_TRACE(slot, val) do { if (lane == 0 && g_fq_trace) g_fq_trace[tile * 4 + (slot)] = (val); } while (0)
+#else
+#define FQ_TRACE(slot, val) do { } while (0)
+#endif
+
 struct OpenLine {  // the line that is open at a tile's first byte
     int64_t start;
     int s, g;      // byte sum / G,C count of its part before the tile (mod 2^32)
@@ -167,28 +179,65 @@ __device__ __forceinline__ OpenLine open_line_before(const uint64_t* tails, int6
     }
 }
 
-// Decoupled look-back over the newline counts; all 32 lanes call it (tile > 0).
-__device__ __forceinline__ uint64_t lookback_count(uint64_t* chain, int64_t tile, uint32_t agg, uint64_t init) {
+// ---------------------------------------------------------------- two-level chain of the newline counts
+// A decoupled look-back advances its frontier by (window x tile bytes) per L2 round trip.
+// With 2 KiB warp tiles that is far too slow for a flat chain (32 x 2 KiB per ~0.6 us =
+// 0.1 TB/s), so the counts are chained at two levels:
+//   level 1  cnt1[t]   = 0x80000000 | newlines of warp tile t            (plain store)
+//   level 2  super[j]  = accumulator of the SUPER_TILES = 32 warp tiles [32j, 32j+32):
+//                        (arrivals << 32 | sum), built with one atomicAdd per warp tile.
+//                        The warp whose atomicAdd completes the group runs the look-back
+//                        over super words (128 per round = 8 MiB of input per round trip)
+//                        and overwrites the word with SUP_INC | inclusive line count.
+// A warp tile's exclusive prefix = inclusive(super j-1) + sum of cnt1 of its earlier siblings.
+constexpr int SUPER_TILES = 32;
+constexpr uint64_t SUP_INC = 1ull << 63, SUP_VAL = (1ull << 62) - 1ull;
+constexpr uint32_t CNT1_VALID = 0x80000000u;
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// Run by the warp that completed super tile j (j > 0): lines before the super tile.
+__device__ __forceinline__ uint64_t super_lookback(const uint64_t* sup, int64_t j, uint64_t init) {
     const int lane = threadIdx.x & 31;
     uint64_t acc = 0;
-    int64_t base = tile - 1;
+    int64_t base = j - 1;
     while (true) {
-        const int64_t idx = base - lane;
-        const uint64_t w = idx >= 0 ? ld_relaxed_u64(chain + idx) : (CH_INC | (idx == -1 ? (init & CH_VAL) : 0ull));
-        const uint32_t f = (uint32_t)(w >> 62);
-        const uint32_t inc = __ballot_sync(0xffffffffu, f == 2), emp = __ballot_sync(0xffffffffu, f == 0);
-        const int first = inc ? __ffs(inc) - 1 : 32;
-        const uint32_t need = first >= 32 ? 0xffffffffu : ((1u << first) - 1u);
-        if (emp & need) continue;  // a predecessor nearer than the first inclusive word is unpublished: poll again
-        acc += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)w : 0u);  // aggregates are per-tile counts (<= 2049)
-        if (inc) {
-            acc += __shfl_sync(0xffffffffu, w & CH_VAL, first);
-            break;
+        uint64_t w[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const int64_t idx = base - (32 * m + lane);
+            w[m] = idx >= 0 ? ld_relaxed_u64(sup + idx) : (SUP_INC | (idx == -1 ? (init & SUP_VAL) : 0ull));
         }
-        base -= 32;
+        bool done = false, stalled = false;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            if (done || stalled) continue;
+            const bool is_inc = (w[m] >> 63) != 0;
+            const bool complete = !is_inc && (uint32_t)(w[m] >> 32) == (uint32_t)SUPER_TILES;  // every earlier super tile is full
+            const uint32_t inc = __ballot_sync(0xffffffffu, is_inc), emp = __ballot_sync(0xffffffffu, !is_inc && !complete);
+            const int first = inc ? __ffs(inc) - 1 : 32;
+            const uint32_t need = first >= 32 ? 0xffffffffu : ((1u << first) - 1u);
+            if (emp & need) {  // a needed group is still counting: poll again from this window
+                stalled = true;
+                base -= 32 * m;
+                continue;
+            }
+            acc += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)w[m] : 0u);
+            if (inc) {
+                acc += __shfl_sync(0xffffffffu, w[m] & SUP_VAL, first);
+                done = true;
+            }
+        }
+        if (done) return acc;
+        if (!stalled) base -= 128;
     }
-    if (lane == 0) st_relaxed_u64(chain + tile, CH_INC | ((acc + agg) & CH_VAL));
-    return acc;
 }
 
 template <typename OffT, int FLAGS>
@@ -220,9 +269,11 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) fastq_scan_kernel(const FastqSc
 
     const uint8_t* __restrict__ buf = a.buf;
     const int64_t origin = a.begin & ~(int64_t)15;
-    uint64_t* chain = reinterpret_cast<uint64_t*>(a.slots);
-    uint64_t* tails = chain + a.n_tiles;
     const int64_t n_tiles = a.n_tiles;
+    const int64_t n_super = (n_tiles + SUPER_TILES - 1) / SUPER_TILES;
+    uint64_t* tails = reinterpret_cast<uint64_t*>(a.slots);
+    uint64_t* sup = tails + n_tiles;
+    uint32_t* cnt1 = reinterpret_cast<uint32_t*>(sup + n_super);
     const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
     const uint32_t pat_nl = c7f & 0x0A0A0A0Au, pat_gc = c7f & 0x43434343u;  // derived from an argument: stay in registers
 
@@ -278,6 +329,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) fastq_scan_kernel(const FastqSc
 
         const int64_t tile = cur;
         const int64_t tile_base = origin + tile * WT_BYTES;
+        FQ_TRACE(3, gtime());
         uint8_t* sbytes = sm + b * WT_BYTES;
         const uint4* d = reinterpret_cast<const uint4*>(sbytes);
 
@@ -304,6 +356,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) fastq_scan_kernel(const FastqSc
 
         // ---- A. analysis of the lane's 64-byte run
         uint64_t pm, gm = 0;
+        unsigned long long sup_old = 0;  // lane 0: the super tile's accumulator before this tile joined
         int ex_s = 0, ex_g = 0, ex_cnt, n_events, total_s = 0, total_g = 0;
         {
             const int x = (lane >> 1) & 3, rb = 4 * lane;
@@ -346,9 +399,10 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) fastq_scan_kernel(const FastqSc
                 total_g = tot_lo;
             }
             // the count is all the chain needs: publish it before anything else
+            FQ_TRACE(0, gtime());
             if (lane == 0) {
-                if (tile == 0) st_relaxed_u64(chain, CH_INC | ((init + (uint64_t)n_events) & CH_VAL));
-                else st_relaxed_u64(chain + tile, CH_AGG | (uint64_t)n_events);
+                st_relaxed_u32(cnt1 + tile, CNT1_VALID | (uint32_t)n_events);
+                sup_old = atomicAdd(reinterpret_cast<unsigned long long*>(sup + (tile >> 5)), (1ull << 32) | (unsigned long long)n_events);
             }
             if (kQual) *reinterpret_cast<int4*>(s_cpre + rb) = make_int4(ex_s, ex_s + s0, ex_s + s1, ex_s + s2);
             if (kSeq) {
@@ -412,8 +466,37 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) fastq_scan_kernel(const FastqSc
         }
 
         // ---- D. chaining: global line index of the tile's first newline; the open line
-        uint64_t excl = init;
-        if (tile > 0) excl = lookback_count(chain, tile, (uint32_t)n_events, init);
+        uint64_t excl;
+        {
+            const int64_t j = tile >> 5;
+            const int i = (int)(tile & 31);
+            const int group = (int)((n_tiles - j * SUPER_TILES) < SUPER_TILES ? (n_tiles - j * SUPER_TILES) : SUPER_TILES);
+            const unsigned long long old = __shfl_sync(0xffffffffu, sup_old, 0);
+            uint64_t sup_excl = init;
+            bool have_sup = j == 0;
+            if ((int)(old >> 32) == group - 1) {  // this warp completed the super tile: chain it
+                if (j > 0) sup_excl = super_lookback(sup, j, init);
+                have_sup = true;
+                if (lane == 0) st_relaxed_u64(sup + j, SUP_INC | ((sup_excl + (old & 0xffffffffull) + (uint64_t)n_events) & SUP_VAL));
+            }
+            uint32_t c = 0;
+            unsigned long long spins = 0;
+            while (true) {
+                spins++;
+                if (lane < i && !(c & CNT1_VALID)) c = ld_relaxed_u32(cnt1 + j * SUPER_TILES + lane);
+                uint64_t w = SUP_INC;
+                if (!have_sup) w = ld_relaxed_u64(sup + j - 1);
+                const bool ok1 = __all_sync(0xffffffffu, lane >= i || (c & CNT1_VALID));
+                if (!have_sup && (w >> 63)) {
+                    sup_excl = w & SUP_VAL;
+                    have_sup = true;
+                }
+                if (ok1 && have_sup) break;
+            }
+            excl = sup_excl + __reduce_add_sync(0xffffffffu, lane < i ? (c & ~CNT1_VALID) : 0u);
+            FQ_TRACE(1, gtime());
+            FQ_TRACE(2, spins | ((unsigned long long)((int)(old >> 32) == group - 1) << 32));
+        }
         OpenLine open;
         open.start = 0;
         open.s = open.g = 0;
@@ -553,7 +636,9 @@ int64_t fastq_scan_tiles(int64_t begin, int64_t n, int is_final) {
     const int64_t t = (n + (is_final ? 1 : 0) - origin + WT_BYTES - 1) / WT_BYTES;
     return t > 0 ? t : 1;
 }
-int64_t fastq_scan_chain_bytes(int64_t n_tiles) { return n_tiles * 16; }  // count word + tail word per tile
+int64_t fastq_scan_chain_bytes(int64_t n_tiles) {  // tail word + count word per tile, one accumulator per 32 tiles
+    return n_tiles * 12 + ((n_tiles + SUPER_TILES - 1) / SUPER_TILES) * 8 + 16;
+}
 
 template <typename OffT, int FLAGS>
 static cudaError_t launch_one(const FastqScanArgs& a, cudaStream_t st) {
@@ -595,6 +680,13 @@ static cudaError_t launch_fastq(const FastqScanArgs& a, int flags, cudaStream_t 
     default: return launch_one<OffT, 7>(a, st);
     }
 }
+
+#ifdef EXB_FQ_TRACE
+extern "C" __attribute__((visibility("default"))) int exb_debug_set_fq_trace(void* d_trace) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(d_trace);
+    return (int)cudaMemcpyToSymbol(g_fq_trace, &p, sizeof(p));
+}
+#endif
 
 cudaError_t fastq_scan_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st) {
     return wide_offsets ? launch_fastq<uint64_t>(a, flags, st) : launch_fastq<uint32_t>(a, flags, st);
