@@ -77,6 +77,7 @@ SIGNATURES = {
     "replacement_scan": (ReplacementScanResult, [C.c_char_p]),
     "exb_free_string": (None, [_vp]),
     "exb_scan_workspace_bytes": (_i64, [_i64]),
+    "exb_fastq_workspace_bytes": (_i64, [_i64, _i64]),
     "exb_fastq_scan": (_i32, [_vp, _i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_fastq_scan_filter": (_i32, [_vp, _i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i32, _vp, _i64, _vp]),
     "exb_scan_result_fetch": (_i32, [_vp, C.POINTER(ScanResult), _vp]),

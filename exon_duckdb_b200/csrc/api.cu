@@ -91,6 +91,7 @@ __global__ void gen_fill_kernel(exb_gen_params p, const int64_t* off, uint8_t* o
 using namespace exb;
 
 extern "C" {
+static int64_t fastq_workspace_bytes(int64_t n, int64_t max_lines);
 
 const char* exb_last_error(void) { return g_err; }
 const char* exb_version(void) { return "exon-b200 0.1.0 (sm_100a)"; }
@@ -107,9 +108,34 @@ int exb_device_available(void) {
 
 int64_t exb_scan_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
-    const int64_t cta_tiles = WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);      // FASTA scan, offset scans
-    const int64_t warp_tiles = WS_HEADER + fastq_scan_chain_bytes(fastq_scan_tiles(0, n + 16, 1) + 2);  // FASTQ scan
-    return cta_tiles > warp_tiles ? cta_tiles : warp_tiles;
+    const int64_t cta_tiles = WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);  // FASTA scan, offset scans
+    const int64_t fastq = fastq_workspace_bytes(n, n / 24 + 16384);  // FASTQ scan: lines of >= 24 bytes on average
+    return cta_tiles > fastq ? cta_tiles : fastq;
+}
+
+// FASTQ workspace: [0,256) header (ScanResult | +128 record bump counter)
+//                  [256, 256+S) sub-workspace of the offset scan (its own 256-byte header + slots)
+//                  tails u64[T] | tile_rec i64[T] | line_base i64[T+1] | tile_cnt u32[T] | records (8 B each) or fused tiles
+struct FastqLayout {
+    int64_t n_tiles, scan_ws, off_tails, off_rec, off_base, off_cnt, off_payload, fixed;
+};
+static FastqLayout fastq_layout(int64_t n_tiles) {
+    FastqLayout L;
+    L.n_tiles = n_tiles;
+    L.scan_ws = WS_HEADER + scan_tiles(n_tiles) * (int64_t)sizeof(TileSlot);
+    L.off_tails = WS_HEADER + L.scan_ws;
+    L.off_rec = L.off_tails + n_tiles * 8;
+    L.off_base = L.off_rec + n_tiles * 8;
+    L.off_cnt = L.off_base + (n_tiles + 1) * 8;
+    L.off_payload = (L.off_cnt + n_tiles * 4 + 15) & ~(int64_t)15;
+    L.fixed = L.off_payload;
+    return L;
+}
+static int64_t fastq_workspace_bytes(int64_t n, int64_t max_lines) {
+    const FastqLayout L = fastq_layout(fastq_scan_tiles(0, n + 16, 1) + 1);
+    const int64_t recs = (max_lines + fastq_record_slack(L.n_tiles)) * 8;
+    const int64_t fused = L.n_tiles * (int64_t)sizeof(FusedTile);
+    return L.fixed + (recs > fused ? recs : fused) + 64;
 }
 
 static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace,
@@ -127,6 +153,7 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
         if ((flags & EXB_F_QUAL) && (!d_qual_len || !d_qsum)) return set_err(EXB_ERR_ARG, "%s: EXB_F_QUAL without outputs", who);
     }
     if (d_prev_workspace == d_workspace) return set_err(EXB_ERR_ARG, "%s: d_prev_workspace must differ from d_workspace", who);
+    if (!d_workspace || ((uintptr_t)d_workspace & 15) != 0) return set_err(EXB_ERR_ARG, "%s: d_workspace must be 16-byte aligned", who);
     FastqScanArgs a;
     memset(&a, 0, sizeof(a));
     a.buf = reinterpret_cast<const uint8_t*>(d_buf);
@@ -136,12 +163,28 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
     a.is_final = is_final ? 1 : 0;
     a.max_lines = max_lines;
     a.n_tiles = fastq_scan_tiles(begin, n, a.is_final);
-    Workspace w;
-    int rc = carve_bytes(d_workspace, workspace_bytes, fastq_scan_chain_bytes(a.n_tiles), st, &w);
-    if (rc) return rc;
-    a.slots = w.slots;
-    a.ticket = w.ticket;
-    a.result = w.result;
+    const FastqLayout L = fastq_layout(a.n_tiles);
+    const int64_t payload = workspace_bytes - L.fixed;
+    const int64_t min_payload = (flags & EXB_F_FUSED) ? a.n_tiles * (int64_t)sizeof(FusedTile) : fastq_record_slack(a.n_tiles) * 8;
+    if (payload < min_payload)
+        return set_err(EXB_ERR_ARG, "%s: workspace too small: need at least %lld bytes, have %lld", who, (long long)(L.fixed + min_payload),
+                       (long long)workspace_bytes);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(d_workspace);
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)WS_HEADER, st);  // result block + record bump counter
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace header)");
+    a.result = reinterpret_cast<ScanResult*>(ws);
+    a.rec_bump = reinterpret_cast<unsigned long long*>(ws + 128);
+    a.tails = reinterpret_cast<uint64_t*>(ws + L.off_tails);
+    a.tile_rec = reinterpret_cast<int64_t*>(ws + L.off_rec);
+    int64_t* line_base = reinterpret_cast<int64_t*>(ws + L.off_base);
+    a.line_base = line_base;
+    a.tile_cnt = reinterpret_cast<uint32_t*>(ws + L.off_cnt);
+    a.records = reinterpret_cast<uint2*>(ws + L.off_payload);
+    a.rec_space = payload / 8;
+    a.fused_tiles = reinterpret_cast<FusedTile*>(ws + L.off_payload);
+    a.n_fused = n_preds;
+    for (int i = 0; i < n_preds; i++) a.fused[i] = preds[i];
+    a.fused_agg = reinterpret_cast<long long*>(d_agg);
     a.line_end = d_line_end;
     a.line_cap = line_cap;
     a.seq_len = d_seq_len;
@@ -149,12 +192,28 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
     a.qual_len = d_qual_len;
     a.qsum = d_qsum;
     a.rec_cap = rec_cap;
-    a.n_fused = n_preds;
-    for (int i = 0; i < n_preds; i++) a.fused[i] = preds[i];
-    a.fused_agg = reinterpret_cast<long long*>(d_agg);
-    cudaError_t e = fastq_scan_launch(a, flags, wide_offsets != 0, st);
-    if (e != cudaSuccess) return cuda_fail(e, "fastq_scan launch");
+    // K1: every byte once, no inter-tile dependency
+    e = fastq_tile_launch(a, flags, st);
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_tile launch");
+    // global line index of every tile
+    Workspace w;
+    int rc = carve(ws + WS_HEADER, L.scan_ws, scan_tiles(a.n_tiles), st, &w);
+    if (rc) return rc;
+    e = exclusive_scan_launch_u32(a.tile_cnt, a.n_tiles, line_base, w.slots, w.ticket, st);
+    if (e != cudaSuccess) return cuda_fail(e, "line offset scan launch");
+    // K2: records -> per-line / per-record outputs (or bucket selection, fused)
+    e = fastq_emit_launch(a, flags, wide_offsets != 0, st);
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_emit launch");
     return 0;
+}
+
+int64_t exb_fastq_workspace_bytes(int64_t n, int64_t max_lines) {
+    if (n < 0) n = 0;
+    if (max_lines < 0) max_lines = 0;
+    if (max_lines > n + 1) max_lines = n + 1;
+    const int64_t generic = WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);
+    const int64_t fastq = fastq_workspace_bytes(n, max_lines);
+    return generic > fastq ? generic : fastq;
 }
 
 int exb_fastq_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, uint64_t max_lines,

@@ -165,9 +165,16 @@ int exb_engine_fastq_count(exb_engine* g, const void* host_buf, int64_t n, const
         exb_scan_result res;
         rc = exb_scan_result_fetch(prev_ws, &res, g->sk);
         if (rc) return rc;
-        if (res.overflow && attempt == 0) {  // denser records than estimated: redo with the hard upper bound
+        if (res.overflow && attempt == 0) {  // denser records than estimated: redo with the hard upper bounds
             want_cap = n / 4 + 16;
             cudaStreamSynchronize(g->sc);
+            const int64_t ws_need = exb_fastq_workspace_bytes(g->chunk_bytes, g->chunk_bytes + 1);
+            for (int i = 0; i < 2; i++) {
+                cudaFree(g->d_ws[i]);
+                g->d_ws[i] = nullptr;
+                if ((e = cudaMalloc(&g->d_ws[i], (size_t)ws_need)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+            }
+            g->ws_bytes = ws_need;
             continue;
         }
         if (res_out) *res_out = res;

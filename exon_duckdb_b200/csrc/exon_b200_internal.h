@@ -21,7 +21,7 @@ struct ScanResult {
     unsigned long long err_pos; // ON THE DEVICE: ~(smallest offset of a malformed line start), 0 = none (atomicMax over a
                                 // zeroed word needs no init kernel); exb_scan_result_fetch inverts it for the host
     uint32_t overflow;          // an output capacity was too small
-    uint32_t pad;
+    uint32_t pad;               // FASTQ: first byte of the open line is '@' (bit 1) / '+' (bit 0) (chunk chaining)
     uint64_t n_records;         // FASTA: header lines seen
     uint64_t seq_bytes;         // FASTA: sequence bytes kept (newlines / CR stripped)
     uint64_t gc_total;          // FASTA: G/C among them
@@ -29,19 +29,40 @@ struct ScanResult {
     uint64_t tail_hdr;          // FASTA: the open line is a header line (chunk chaining)
 };
 
+// per-tile aggregates of the fused COUNT flavour: one bucket per phase hypothesis h = (global index of the
+// tile's first newline-terminated line) & 3.  Lines 1.. of the tile only; line 0 is completed by K2.
+struct alignas(16) FusedTile {
+    uint32_t cq[4];   // lines that are quality lines under h and pass the predicates | sum of their lengths << 12
+    int32_t qs[4];    // sum of their Phred sums
+    int32_t ps0;      // record of the tile's first newline (what K2 needs to finish line 0)
+    uint32_t y0;
+    uint32_t bad4;    // bit h: a line start contradicts h ('@' / '+' expected)
+    uint32_t pad;
+};
+static_assert(sizeof(FusedTile) == 48, "FusedTile layout");
+
 struct FastqScanArgs {
     const uint8_t* buf;
     int64_t begin, n;           // parse bytes [begin, n)
     const ScanResult* prev;     // null: `begin` starts line 0; else continue from that scan's final state
     int is_final;               // 1: n is the end of the input (an unterminated last line gets a virtual '\n')
     uint64_t max_lines;         // lines with index >= max_lines are ignored
-    int64_t n_tiles;
-    TileSlot* slots;            // zeroed chain state: u64 count word[n_tiles] | u64 tail word[n_tiles]
-    unsigned long long* ticket; // zeroed
+    int64_t n_tiles;            // 4 KiB warp tiles
+    int64_t tma_rows;           // 128-byte rows the tensor map covers (set by the launcher)
     ScanResult* result;
+    // K1 -> K2 (all inside the caller's workspace; nothing needs zeroing except *rec_bump)
+    uint32_t* tile_cnt;         // [n_tiles] newlines per tile
+    int64_t* tile_rec;          // [n_tiles] index of the tile's first record
+    uint64_t* tails;            // [n_tiles] tail words
+    const int64_t* line_base;   // [n_tiles + 1] exclusive scan of tile_cnt (written between K1 and K2)
+    uint2* records;             // [rec_space] 8 bytes per newline, bump-allocated per warp
+    int64_t rec_space;
+    unsigned long long* rec_bump;
+    FusedTile* fused_tiles;     // [n_tiles] (EXB_F_FUSED instead of records)
     int n_fused;                // EXB_F_FUSED: predicates on the quality line (EXB_P_MEAN_QUALITY / EXB_P_QUAL_LEN)
     exb_predicate fused[EXB_MAX_PREDICATES];
     long long* fused_agg;       // int64[8] aggregates (same layout as exb_fastq_filter's d_agg)
+    // outputs
     void* line_end;             // OffT[line_cap]
     int64_t line_cap;
     uint32_t *seq_len, *gc, *qual_len;
@@ -49,9 +70,10 @@ struct FastqScanArgs {
     int64_t rec_cap;
 };
 
-cudaError_t fastq_scan_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st);
-int64_t fastq_scan_tiles(int64_t begin, int64_t n, int is_final);  // 2 KiB warp tiles
-int64_t fastq_scan_chain_bytes(int64_t n_tiles);
+cudaError_t fastq_tile_launch(const FastqScanArgs& a, int flags, cudaStream_t st);                     // K1
+cudaError_t fastq_emit_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st);  // K2
+int64_t fastq_scan_tiles(int64_t begin, int64_t n, int is_final);  // 4 KiB warp tiles
+int64_t fastq_record_slack(int64_t n_tiles);                       // record slots the bump allocation may waste
 
 struct FastaScanArgs {
     const uint8_t* buf;

@@ -1,78 +1,89 @@
-// fastq_scan.cu -- single-pass FASTQ line/record scan for sm_100a (v5: warp tiles).
+// fastq_scan.cu -- FASTQ line/record scan for sm_100a (v7: TMA-fed chain-free tile pass + emit pass).
 //
 // Replaces the record loop of noodles-fastq 0.8 Reader::read_record as driven
 // by exon 0.2.6's FASTQ batch reader (call sites: rust/src/arrow_reader.rs:
 // 104-118,125-153 in the reference).  Instead of reading a
 // record at a time it reads every input byte exactly once.
 //
-// The unit of work is a WARP TILE: 2 KiB of input, owned by one warp from the
-// global load to the last store.  There is no block-level barrier anywhere in
-// the steady state; a persistent grid of 148 x (CTAs per SM) CTAs pulls tile
-// ids from an atomic ticket, so the 40 warps of an SM are 40 independent
-// pipelines whose stalls (HBM latency, the chain look-back) overlap freely.
-// Each warp double-buffers: the cp.async (LDGSTS, L2-only) of tile k+1 is in
-// flight while tile k is analysed, so ~80 KiB per SM are outstanding at all
-// times -- what Little's law asks for at 6.5 TB/s.
+// Why two kernels.  What a FASTQ line MEANS depends on its global line index
+// (strict 4-line records: index mod 4 picks header / sequence / plus / quality,
+// index / 4 is the record).  A single-pass kernel therefore has to chain a
+// prefix count across tiles; measured on B200 (profiles/r01c_*_trace.txt) the
+// chain costs ~10 us per tile even with a two-level look-back, because every
+// tile waits for the slowest earlier one, and any warp that waits while holding
+// a prefetched tile makes that tile late for everybody else.  So the work is
+// split where the dependency is:
 //
-// Per tile (lane l owns the 64 contiguous bytes [64l, 64l+64)):
-//  A. analysis, byte-parallel and branch-free: 64-bit newline mask, signed
-//     byte sum, G/C mask; one packed warp scan gives every lane its
-//     tile-level prefix (newlines | byte sum) [+ G/C].  The tile's newline
-//     count is published at once (chain word, status in the top bits).
-//     Per-16-byte-chunk byte-sum prefixes go to shared memory (one STS.128),
-//     newline positions are scattered, in order, into an event list.
-//  B. tail: what follows the tile's last newline (start, byte sum, G/C) is
-//     packed into ONE 64-bit word and published -- it depends on no other tile.
-//  C. events, one newline per lane: prefix byte sum / G,C count at the newline
-//     (chunk prefix + a 0/1-weight IDP.4A over the chunk's head).
-//  D. chaining: decoupled look-back of the newline COUNT only (32 predecessors
-//     per round); the line that is open at the tile's first byte is resolved
-//     from the predecessors' tail words.
-//  E. emission: line length, G/C count (sequence lines) and Phred sum (quality
-//     lines) are differences of the prefixes at consecutive newlines; FASTQ's
-//     strict 4-line phase (global line index mod 4) disambiguates '@' / '+'
-//     inside quality strings.  Optionally the per-record predicate is applied
-//     here and only COUNT / sums leave the kernel (fused filter).
+//  K1  fastq_tile_kernel   (all the byte work, NO inter-tile dependency)
+//      A warp owns a 4 KiB tile.  A persistent grid walks the tiles with a
+//      static stride; each warp double-buffers its tiles with TMA: one elected
+//      lane issues ONE cp.async.bulk.tensor (UTMALDG) per tile -- a 32 x 128 B
+//      box of the file viewed as rows of 128 bytes, SWIZZLE_128B -- completing
+//      on an mbarrier.  Lane l owns row l (128 contiguous bytes); the hardware
+//      swizzle makes its eight LDS.128 bank-conflict free.  Per lane: two
+//      64-bit newline masks, signed byte sums, G/C masks; warp scans.  Then,
+//      one newline per lane, the prefix byte sum / G,C count at the newline
+//      (per-chunk prefixes + a 0/1-weight IDP.4A over the chunk's head).
+//      Per tile it writes: the newline count, one 8-byte record per newline and
+//      one 64-bit tail word describing what follows the last newline.
+//  --  exclusive scan of the per-tile counts (1.7 M words for 7 GB: microseconds)
+//  K2  fastq_emit_kernel   (light: 8 bytes per LINE instead of ~90)
+//      With the global line index known, line length, G/C count (sequence
+//      lines) and Phred sum (quality lines) are differences of consecutive
+//      records; the line that straddles a tile edge is completed from the
+//      predecessors' tail words.  '@' / '+' are validated by line phase.
 //
-// Outputs are single-writer stores (no atomics except the rare error path and
-// one aggregate flush per warp):
-//   line_end[g]            position of the newline ending line g      (F_LINES)
-//   seq_len[r], gc[r]      per record                                 (F_SEQ)
-//   qual_len[r], qsum[r]   per record; qsum = sum((signed char)c - 33) (F_QUAL)
-// HBM traffic: input once + 16 B of chain state per 2 KiB + 4..16 B per line.
+//  Fused COUNT flavour (exb_fastq_scan_filter): K1 evaluates the predicate for
+//  every line as if it were a quality line and adds it to one of FOUR buckets
+//  (one per possible phase of the tile's first line); K2 picks the bucket once
+//  the phase is known.  Nothing per line is written at all.
+//
+// HBM traffic: input once + 8 B per line (written once, read once) + 28 B per
+// tile of directory; the fused flavour: input once + 60 B per tile.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "exon_b200_internal.h"
 #include "x87div.h"
 
 namespace exb {
 
-constexpr int WT_BYTES = 2048;            // bytes per warp tile
-constexpr int WT_CHUNKS = WT_BYTES / 16;  // 128
-constexpr int FQ_WARPS = 8;               // warps per CTA (independent of each other)
+constexpr int WT_BYTES = 4096;  // bytes per warp tile = 32 rows of 128 bytes, one row per lane
+constexpr int WT_ROWS = 32;
+constexpr int ROW_BYTES = 128;
+constexpr int FQ_WARPS = 4;     // warps per CTA (independent of each other)
 constexpr int FQ_THREADS = FQ_WARPS * 32;
-constexpr int EV_CAP = 128;               // newline positions held at once (4 passes of 32)
+constexpr int EV_CAP = 64;      // newline positions held at once (2 passes of 32)
+constexpr int REC_BLOCK = 256;  // records a warp reserves per bump allocation
 
-// ---------------------------------------------------------------- chain / tail words
-__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
-    uint64_t v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
-    return v;
+// ---------------------------------------------------------------- tail word
+// [63:62] 1 = no newline in the tile, 2 = has one
+// [61:60] the line open after the last newline starts with '@' (2) / '+' (1) (valid if its start lies in the tile)
+// [59:58] the tile's first byte is '@' / '+'
+// [52:40] offset in the tile of the byte after its last newline (0..4096)
+// [39:27] G/C count of the part after it          (0..4096)
+// [20:0]  signed byte sum of that part            (|.| <= 2^19)
+__device__ __forceinline__ uint64_t tail_pack(uint32_t state, uint32_t flags4, uint32_t rel, uint32_t g, int s) {
+    return ((uint64_t)state << 62) | ((uint64_t)flags4 << 58) | ((uint64_t)rel << 40) | ((uint64_t)g << 27) |
+           (uint64_t)((uint32_t)s & 0x1FFFFFu);
 }
-__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
-}
+__device__ __forceinline__ int tail_s_of(uint64_t w) { return ((int)((uint32_t)w << 11)) >> 11; }
+__device__ __forceinline__ uint32_t tail_g_of(uint64_t w) { return (uint32_t)(w >> 27) & 0x1FFFu; }
+__device__ __forceinline__ uint32_t tail_rel_of(uint64_t w) { return (uint32_t)(w >> 40) & 0x1FFFu; }
+__device__ __forceinline__ uint32_t tail_open_flags(uint64_t w) { return (uint32_t)(w >> 60) & 3u; }
+__device__ __forceinline__ uint32_t tail_byte0_flags(uint64_t w) { return (uint32_t)(w >> 58) & 3u; }
+__device__ __forceinline__ uint32_t at_plus_flags(int byte) { return (byte == '@' ? 2u : 0u) | (byte == '+' ? 1u : 0u); }
 
-// tail word: [63:62] state (0 unpublished, 1 no newline in the tile, 2 has one)
-//            [47:36] offset in the tile of the byte after its last newline (0..2048)
-//            [35:24] G/C count of the part after it          (0..2048)
-//            [23:0]  signed byte sum of that part            (|.| <= 2^18)
-// Every field is self-contained in the word, so a relaxed 64-bit store publishes it.
-__device__ __forceinline__ uint64_t tail_pack(uint32_t state, uint32_t rel, uint32_t g, int s) {
-    return ((uint64_t)state << 62) | ((uint64_t)rel << 36) | ((uint64_t)g << 24) | (uint64_t)((uint32_t)s & 0xFFFFFFu);
+// ---------------------------------------------------------------- line record (8 bytes per newline)
+// .x = byte-sum prefix at the newline (tile-relative, excludes the newline)
+// .y = [11:0] position in the tile | [12] CR before it | [14:13] next line starts with '@' / '+' | [27:15] G/C prefix
+__device__ __forceinline__ uint32_t rec_pack(int pos, uint32_t cr, uint32_t next_flags, int pg) {
+    return (uint32_t)pos | (cr << 12) | (next_flags << 13) | ((uint32_t)pg << 15);
 }
-__device__ __forceinline__ int tail_s_of(uint64_t w) { return ((int)((uint32_t)w << 8)) >> 8; }
-__device__ __forceinline__ uint32_t tail_g_of(uint64_t w) { return (uint32_t)(w >> 24) & 0xFFFu; }
-__device__ __forceinline__ uint32_t tail_rel_of(uint64_t w) { return (uint32_t)(w >> 36) & 0xFFFu; }
+__device__ __forceinline__ int rec_pos(uint32_t y) { return (int)(y & 0xFFFu); }
+__device__ __forceinline__ uint32_t rec_cr(uint32_t y) { return (y >> 12) & 1u; }
+__device__ __forceinline__ uint32_t rec_next_flags(uint32_t y) { return (y >> 13) & 3u; }
+__device__ __forceinline__ int rec_pg(uint32_t y) { return (int)(y >> 15); }
 
 // ---------------------------------------------------------------- byte classification
 // 16-bit equality mask of a 16-byte chunk, bits in byte order.  The 0x80 flags of two
@@ -105,149 +116,97 @@ __device__ __forceinline__ uint32_t gc_mask16r(const uint4& v, uint32_t c7b, uin
                            gc_flags(v.w, c7b, c7f, pat));
 }
 
-// ---------------------------------------------------------------- shared memory of one warp
+// ---------------------------------------------------------------- TMA / mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// one 32 x 128 B box of the input (rows [row0, row0 + 32)), swizzled 128B, completing `bytes` on the barrier
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* tmap, int row0, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+                 "l"(tmap), "r"(mbar), "r"(0), "r"(row0)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- shared memory of one warp (K1)
+// Tile data lives in two 4 KiB buffers per warp (1024-byte aligned: the 128B swizzle pattern is a function of
+// address bits [7:9]); the small per-tile arrays follow all the data buffers.
 template <int FLAGS>
-struct FqWarpSmem {
+struct FqWarpAux {
     static constexpr bool kSeq = (FLAGS & EXB_F_SEQ) != 0, kQual = (FLAGS & EXB_F_QUAL) != 0;
-    static constexpr int off_data = 0;                                   // 2 x 2 KiB (double buffer)
-    static constexpr int off_cpre = off_data + 2 * WT_BYTES;             // int[128]: byte-sum prefix at each chunk
-    static constexpr int off_gm = off_cpre + (kQual ? WT_CHUNKS * 4 : 0);  // u64[32]: G/C mask of each lane's run
-    static constexpr int off_gex = off_gm + (kSeq ? 32 * 8 : 0);         // int[32]: G/C prefix at each lane's run
-    static constexpr int off_ev = off_gex + (kSeq ? 32 * 4 : 0);         // u16[EV_CAP]: newline positions
-    static constexpr int total = off_ev + EV_CAP * 2;
+    static constexpr int off_cpre = 0;                                   // int[256]: byte-sum prefix at each 16-byte chunk
+    static constexpr int off_gm = off_cpre + (kQual ? 256 * 4 : 0);      // u64[64]: G/C mask of each 64-byte half row
+    static constexpr int off_gex = off_gm + (kSeq ? 64 * 8 : 0);         // int[64]: G/C prefix at each half row
+    static constexpr int off_ev = off_gex + (kSeq ? 64 * 4 : 0);         // u16[EV_CAP]: newline positions
+    static constexpr int off_bar = off_ev + EV_CAP * 2;                  // 2 mbarriers
+    static constexpr int total = off_bar + 16;
+    static constexpr int cta_bytes = FQ_WARPS * (2 * WT_BYTES + total) + 1024;  // + slack to align the data to 1024
 };
 
-// tile-local byte index -> byte offset in the (chunk-swizzled) tile buffer
+// tile-local byte index -> byte offset in the 128B-swizzled tile buffer
 __device__ __forceinline__ int sidx(int li) {
-    const int q = li >> 4;
-    return ((q ^ ((q >> 3) & 3)) << 4) | (li & 15);
+    return (li & 0xF8F) | ((((li >> 4) ^ (li >> 7)) & 7) << 4);
 }
 
-#ifdef EXB_FQ_TRACE
-__device__ unsigned long long* g_fq_trace;  // 4 words per tile: t(publish), t(resolved), spins | last<<32, t(ticket)
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-#define FQ_TRACE(slot, val) do { if (lane == 0 && g_fq_trace) g_fq_trace[tile * 4 + (slot)] = (val); } while (0)
-#else
-#define FQ_TRACE(slot, val) do { } while (0)
-#endif
-
-struct OpenLine {  // the line that is open at a tile's first byte
-    int64_t start;
-    int s, g;      // byte sum / G,C count of its part before the tile (mod 2^32)
+// single-predicate fast path of the fused flavour, resolved once per kernel
+struct FusedPlan {
+    int simple;  // 1: exactly one EXB_P_MEAN_QUALITY predicate with op in {>, >=, <, <=}
+    double c;
+    int want_pos;  // verdict = (d > 0) == want_pos when |d| is clear of rounding
+    int op;
 };
 
-// Walk the predecessors' tail words back to the tile that holds the open line's start
-// (tile-1 unless lines are longer than a tile).  All 32 lanes call it; 32 tiles per round.
-__device__ __forceinline__ OpenLine open_line_before(const uint64_t* tails, int64_t tile, int64_t origin, const FastqScanArgs& a) {
-    const int lane = threadIdx.x & 31;
-    OpenLine o;
-    o.s = 0;
-    o.g = 0;
-    int64_t base = tile - 1;
-    while (true) {
-        const int64_t idx = base - lane;
-        uint64_t w;
-        if (idx >= 0) w = ld_relaxed_u64(tails + idx);
-        else w = 2ull << 62;  // the state before tile 0 terminates the walk
-        const uint32_t st = (uint32_t)(w >> 62);
-        const uint32_t has = __ballot_sync(0xffffffffu, st == 2), emp = __ballot_sync(0xffffffffu, st == 0);
-        const int first = has ? __ffs(has) - 1 : 32;
-        const uint32_t need = first >= 32 ? 0xffffffffu : ((2u << first) - 1u);  // lanes up to and including `first`
-        if (emp & need) continue;  // a needed predecessor has not published yet
-        const bool take = lane <= first && idx >= 0;
-        o.s += (int)__reduce_add_sync(0xffffffffu, take ? tail_s_of(w) : 0);
-        o.g += (int)__reduce_add_sync(0xffffffffu, take ? tail_g_of(w) : 0u);
-        if (has) {
-            const int64_t fidx = base - first;
-            const uint32_t rel = __shfl_sync(0xffffffffu, tail_rel_of(w), first);
-            if (fidx >= 0) {
-                o.start = origin + fidx * WT_BYTES + rel;
-            } else if (a.prev) {  // the line began in an earlier range of a chained scan
-                o.start = a.prev->open_line_start;
-                o.s += (int)a.prev->tail_s;
-                o.g += (int)a.prev->tail_g;
-            } else {
-                o.start = a.begin;
-            }
-            return o;
-        }
-        base -= 32;
+__device__ __forceinline__ bool fused_pass(const FastqScanArgs& a, const FusedPlan& plan, int qs, uint32_t len) {
+    if (plan.simple) {
+        if (len == 0) return false;
+        // d = sum - c n with ONE rounding.  |sum| < 2^20 inside a tile, so |d| > 1e-7 puts the exact quotient more
+        // than 40 ulp from c whatever |c n| is (see exb_mean_cmp): neither rounding of the x87 path can cross.
+        const double d = fma(-plan.c, (double)len, (double)qs);
+        if (fabs(d) > 1e-7) return (d > 0) == (plan.want_pos != 0);
+        return exb_mean_cmp_close((int64_t)qs, len, plan.op, plan.c);
     }
-}
-
-// ---------------------------------------------------------------- two-level chain of the newline counts
-// A decoupled look-back advances its frontier by (window x tile bytes) per L2 round trip.
-// With 2 KiB warp tiles that is far too slow for a flat chain (32 x 2 KiB per ~0.6 us =
-// 0.1 TB/s), so the counts are chained at two levels:
-//   level 1  cnt1[t]   = 0x80000000 | newlines of warp tile t            (plain store)
-//   level 2  super[j]  = accumulator of the SUPER_TILES = 32 warp tiles [32j, 32j+32):
-//                        (arrivals << 32 | sum), built with one atomicAdd per warp tile.
-//                        The warp whose atomicAdd completes the group runs the look-back
-//                        over super words (128 per round = 8 MiB of input per round trip)
-//                        and overwrites the word with SUP_INC | inclusive line count.
-// A warp tile's exclusive prefix = inclusive(super j-1) + sum of cnt1 of its earlier siblings.
-constexpr int SUPER_TILES = 32;
-constexpr uint64_t SUP_INC = 1ull << 63, SUP_VAL = (1ull << 62) - 1ull;
-constexpr uint32_t CNT1_VALID = 0x80000000u;
-
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-
-// Run by the warp that completed super tile j (j > 0): lines before the super tile.
-__device__ __forceinline__ uint64_t super_lookback(const uint64_t* sup, int64_t j, uint64_t init) {
-    const int lane = threadIdx.x & 31;
-    uint64_t acc = 0;
-    int64_t base = j - 1;
-    while (true) {
-        uint64_t w[4];
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-            const int64_t idx = base - (32 * m + lane);
-            w[m] = idx >= 0 ? ld_relaxed_u64(sup + idx) : (SUP_INC | (idx == -1 ? (init & SUP_VAL) : 0ull));
-        }
-        bool done = false, stalled = false;
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-            if (done || stalled) continue;
-            const bool is_inc = (w[m] >> 63) != 0;
-            const bool complete = !is_inc && (uint32_t)(w[m] >> 32) == (uint32_t)SUPER_TILES;  // every earlier super tile is full
-            const uint32_t inc = __ballot_sync(0xffffffffu, is_inc), emp = __ballot_sync(0xffffffffu, !is_inc && !complete);
-            const int first = inc ? __ffs(inc) - 1 : 32;
-            const uint32_t need = first >= 32 ? 0xffffffffu : ((1u << first) - 1u);
-            if (emp & need) {  // a needed group is still counting: poll again from this window
-                stalled = true;
-                base -= 32 * m;
-                continue;
-            }
-            acc += __reduce_add_sync(0xffffffffu, lane < first ? (uint32_t)w[m] : 0u);
-            if (inc) {
-                acc += __shfl_sync(0xffffffffu, w[m] & SUP_VAL, first);
-                done = true;
-            }
-        }
-        if (done) return acc;
-        if (!stalled) base -= 128;
+    bool ok = true;
+    for (int i = 0; i < a.n_fused; i++) {
+        const exb_predicate p = a.fused[i];
+        ok = ok && (p.field == EXB_P_MEAN_QUALITY ? exb_mean_cmp((int64_t)qs, len, p.op, p.value) : exb_cmp((double)len, p.op, p.value));
     }
+    return ok;
+}
+__device__ __forceinline__ FusedPlan make_plan(const FastqScanArgs& a) {
+    FusedPlan p;
+    p.simple = 0;
+    p.c = 0;
+    p.want_pos = 0;
+    p.op = 0;
+    if (a.n_fused == 1 && a.fused[0].field == EXB_P_MEAN_QUALITY && a.fused[0].op <= EXB_OP_LE) {
+        p.simple = 1;
+        p.c = a.fused[0].value;
+        p.op = a.fused[0].op;
+        p.want_pos = (p.op == EXB_OP_GT || p.op == EXB_OP_GE) ? 1 : 0;
+    }
+    return p;
 }
 
-template <typename OffT, int FLAGS>
-__global__ void __launch_bounds__(FQ_THREADS, 5) fastq_scan_kernel(const FastqScanArgs a, const uint32_t c7f, const uint32_t c7b) {
-    using SM = FqWarpSmem<FLAGS>;
-    constexpr bool kLines = (FLAGS & EXB_F_LINES) != 0;
-    constexpr bool kSeq = SM::kSeq, kQual = SM::kQual;
+// =================================================================== K1
+template <int FLAGS>
+__global__ void __launch_bounds__(FQ_THREADS) fastq_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FastqScanArgs a,
+                                                                const uint32_t c7f, const uint32_t c7b) {
+    using AUX = FqWarpAux<FLAGS>;
+    constexpr bool kSeq = AUX::kSeq, kQual = AUX::kQual;
     constexpr bool kFused = (FLAGS & EXB_F_FUSED) != 0;
 
-    extern __shared__ __align__(16) uint8_t smem_all[];
+    extern __shared__ uint8_t smem_raw[];
     __shared__ uint4 s_wlut[17];  // s_wlut[k]: 0x01 in the first k bytes -- IDP.4A weights of a chunk's head
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -259,395 +218,583 @@ __global__ void __launch_bounds__(FQ_THREADS, 5) fastq_scan_kernel(const FastqSc
         };
         s_wlut[k] = make_uint4(w(0), w(4), w(8), w(12));
     }
-    __syncthreads();  // the only block-wide barrier of the kernel
 
-    uint8_t* sm = smem_all + warp * SM::total;
-    int* s_cpre = reinterpret_cast<int*>(sm + SM::off_cpre);
-    uint64_t* s_gm = reinterpret_cast<uint64_t*>(sm + SM::off_gm);
-    int* s_gex = reinterpret_cast<int*>(sm + SM::off_gex);
-    uint16_t* ev_pos = reinterpret_cast<uint16_t*>(sm + SM::off_ev);
+    const uint32_t raw_u32 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
+    uint8_t* data0 = smem_raw + pad + warp * (2 * WT_BYTES);
+    uint8_t* aux = smem_raw + pad + FQ_WARPS * (2 * WT_BYTES) + warp * AUX::total;
+    int* s_cpre = reinterpret_cast<int*>(aux + AUX::off_cpre);
+    uint64_t* s_gm = reinterpret_cast<uint64_t*>(aux + AUX::off_gm);
+    int* s_gex = reinterpret_cast<int*>(aux + AUX::off_gex);
+    uint16_t* ev_pos = reinterpret_cast<uint16_t*>(aux + AUX::off_ev);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(aux + AUX::off_bar);
+    const uint32_t data0_u32 = (uint32_t)__cvta_generic_to_shared(data0);
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();  // the only block-wide barrier of the kernel (LUT + barriers ready)
 
     const uint8_t* __restrict__ buf = a.buf;
     const int64_t origin = a.begin & ~(int64_t)15;
     const int64_t n_tiles = a.n_tiles;
-    const int64_t n_super = (n_tiles + SUPER_TILES - 1) / SUPER_TILES;
-    uint64_t* tails = reinterpret_cast<uint64_t*>(a.slots);
-    uint64_t* sup = tails + n_tiles;
-    uint32_t* cnt1 = reinterpret_cast<uint32_t*>(sup + n_super);
-    const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
+    const int64_t full_rows = a.tma_rows;  // rows of 128 bytes that lie completely inside [origin, n): what the tensor map covers
     const uint32_t pat_nl = c7f & 0x0A0A0A0Au, pat_gc = c7f & 0x43434343u;  // derived from an argument: stay in registers
+    const int64_t stride = (int64_t)gridDim.x * FQ_WARPS;
+    const FusedPlan plan = kFused ? make_plan(a) : FusedPlan{0, 0.0, 0, 0};
 
-    // fused aggregates of this warp (flushed once at the end)
-    long long f_cnt = 0, f_qs = 0, f_ql = 0;
-
-    // ---- staging of one tile into buffer b (asynchronous)
-    const uint32_t dst_lane = (uint32_t)__cvta_generic_to_shared(sm) + (uint32_t)((lane ^ ((lane >> 3) & 3)) << 4);
+    // ---- staging of one tile into buffer b (asynchronous; one instruction from one lane)
     auto issue = [&](int64_t tile, int b) {
-        if (tile < n_tiles) {
-            const int64_t base = origin + tile * WT_BYTES;
-            const uint32_t dst = dst_lane + (uint32_t)(b * WT_BYTES);
-            if (base >= a.begin && base + WT_BYTES <= a.n) {  // interior tile: no clipping
-                const uint8_t* src = buf + base + lane * 16;
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + i * 512), "l"(src + i * 512) : "memory");
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int64_t g = base + (int64_t)(i * 32 + lane) * 16;
-                    const int64_t rem = a.n - g;
-                    const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);  // bytes beyond n are zero-filled
-                    const uint8_t* src = nb > 0 ? buf + g : buf;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + i * 512), "l"(src), "r"(nb) : "memory");
-                }
-            }
+        if (tile < n_tiles && tile * WT_ROWS < full_rows && lane == 0) {
+            mbar_expect_tx(bar0 + 8 * b, WT_BYTES);
+            tma_load_tile(data0_u32 + b * WT_BYTES, &tmap, (int)(tile * WT_ROWS), bar0 + 8 * b);
         }
-        cp_async_commit();
     };
-    unsigned long long ticket_raw = 0;
-    auto take_ticket = [&]() {
-        if (lane == 0) ticket_raw = atomicAdd(a.ticket, 1ull);
-    };
-    auto ticket_value = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, ticket_raw, 0); };
 
-    take_ticket();
-    int64_t cur = ticket_value();
-    if (cur == 0 && lane == 0 && a.prev) {  // chained range: errors of earlier ranges stay visible in the last result
-        if (a.prev->err_pos != 0ull) atomicMax(&a.result->err_pos, a.prev->err_pos);
-        if (a.prev->overflow) a.result->overflow = 1;
-    }
+    // bump allocation of record space, REC_BLOCK at a time per warp
+    int64_t rec_next = 0;
+    int rec_left = 0;
+
+    int64_t cur = (int64_t)blockIdx.x * FQ_WARPS + warp;
     issue(cur, 0);
-    take_ticket();
     int b = 0;
+    uint32_t phase_bits = 0;  // bit b = parity the next wait on buffer b expects
 
     while (cur < n_tiles) {
-        const int64_t nxt = ticket_value();
+        const int64_t nxt = cur + stride;
         issue(nxt, b ^ 1);
-        take_ticket();  // for the tile after next; its latency hides behind this tile's work
-        cp_async_wait<1>();
-        __syncwarp();
 
         const int64_t tile = cur;
         const int64_t tile_base = origin + tile * WT_BYTES;
-        FQ_TRACE(3, gtime());
-        uint8_t* sbytes = sm + b * WT_BYTES;
+        uint8_t* sbytes = data0 + b * WT_BYTES;
         const uint4* d = reinterpret_cast<const uint4*>(sbytes);
+        const int64_t row0 = tile * WT_ROWS;
 
-        // Rare per-launch patches: bytes before `begin` in the first chunk are filler; an
-        // unterminated last line gets a virtual '\n' at index n.
+        if (row0 < full_rows) {
+            const uint32_t par = (phase_bits >> b) & 1u;
+            while (!mbar_try_wait(bar0 + 8 * b, par)) {
+            }
+            phase_bits ^= 1u << b;
+        }
+        // Rare edge tiles (uniform per warp): rows the tensor map does not cover, bytes before `begin`, the virtual '\n'
+        const bool partial = row0 + WT_ROWS > full_rows;
         const bool has_begin_pad = (tile == 0 && a.begin != origin);
-        const bool has_eof = a.is_final && (a.n >= tile_base && a.n < tile_base + WT_BYTES);
-        if (has_begin_pad || has_eof) {
+        if (partial || has_begin_pad) {
+            if (row0 >= full_rows) {  // nothing came through TMA: clear the buffer
+                for (int i = lane; i < WT_BYTES / 16; i += 32) reinterpret_cast<uint4*>(sbytes)[i] = make_uint4(0, 0, 0, 0);
+                __syncwarp();
+            }
+            if (partial) {  // bytes of the last, incomplete row (TMA zero-filled everything beyond the tensor)
+                const int64_t tail0 = origin + full_rows * ROW_BYTES;
+                const int64_t lo = tail0 > tile_base ? tail0 : tile_base;
+                for (int64_t g = lo + lane; g < a.n && g < tile_base + WT_BYTES; g += 32) sbytes[sidx((int)(g - tile_base))] = buf[g];
+            }
+            __syncwarp();
             if (lane == 0) {
                 if (has_begin_pad)
                     for (int64_t i = origin; i < a.begin; i++) sbytes[sidx((int)(i - origin))] = 0;
-                if (has_eof) {
+                if (a.is_final && a.n >= tile_base && a.n < tile_base + WT_BYTES) {  // an unterminated last line gets a virtual '\n' at n
                     const bool open = a.n > a.begin ? buf[a.n - 1] != '\n' : (a.prev && a.prev->open_line_start < a.n);
                     if (open) sbytes[sidx((int)(a.n - tile_base))] = '\n';
                 }
             }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes before this buffer's next TMA fill
             __syncwarp();
         }
-        auto any_byte = [&](int64_t abs_pos) -> int {  // byte at an absolute offset < tile end that may lie before this tile
-            const int64_t li = abs_pos - tile_base;
-            if (li >= 0) return sbytes[sidx((int)li)];
-            return (abs_pos >= (a.prev ? 0 : a.begin)) ? (int)buf[abs_pos] : -1;
-        };
 
-        // ---- A. analysis of the lane's 64-byte run
-        uint64_t pm, gm = 0;
-        unsigned long long sup_old = 0;  // lane 0: the super tile's accumulator before this tile joined
-        int ex_s = 0, ex_g = 0, ex_cnt, n_events, total_s = 0, total_g = 0;
+        // ---- A. analysis of the lane's row: two 64-byte halves
+        uint64_t pm[2], gm[2] = {0, 0};
+        int ex_cnt, n_events, ex_s = 0, total_s = 0, ex_g = 0, total_g = 0;
         {
-            const int x = (lane >> 1) & 3, rb = 4 * lane;
-            const uint4 c0 = d[rb + (0 ^ x)], c1 = d[rb + (1 ^ x)], c2 = d[rb + (2 ^ x)], c3 = d[rb + (3 ^ x)];
-            pm = ((uint64_t)(nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16)) << 32) |
-                 (nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16));
-            int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            if (kQual) {
-                s0 = sbyte_sum16(c0, 0);
-                s1 = sbyte_sum16(c1, s0);
-                s2 = sbyte_sum16(c2, s1);
-                s3 = sbyte_sum16(c3, s2);
-            }
-            int gtot = 0;
-            if (kSeq) {
-                gm = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
-                     (gc_mask16r(c0, c7b, c7f, pat_gc) | (gc_mask16r(c1, c7b, c7f, pat_gc) << 16));
-                gtot = __popcll(gm);
-            }
-            const int cnt = __popcll(pm);
-            // newlines (<= 2048 per tile: 12 bits) and byte sum (|.| <= 2^18: 20 bits signed) share one scan word
-            const uint32_t packed = ((uint32_t)cnt << 20) + (uint32_t)(kQual ? s3 : gtot);
-            const uint32_t incl = warp_incl_scan_u32(packed);
-            const uint32_t ex = incl - packed;
-            const int ex_lo = ((int)(ex << 12)) >> 12;
-            ex_cnt = (int)((ex - (uint32_t)ex_lo) >> 20);
-            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-            const int tot_lo = ((int)(tot << 12)) >> 12;
-            n_events = (int)((tot - (uint32_t)tot_lo) >> 20);
-            if (kQual) {
-                ex_s = ex_lo;
-                total_s = tot_lo;
-                if (kSeq) {
-                    const uint32_t gi = warp_incl_scan_u32((uint32_t)gtot);
-                    ex_g = (int)(gi - (uint32_t)gtot);
-                    total_g = (int)__shfl_sync(0xffffffffu, gi, 31);
-                }
-            } else if (kSeq) {
-                ex_g = ex_lo;
-                total_g = tot_lo;
-            }
-            // the count is all the chain needs: publish it before anything else
-            FQ_TRACE(0, gtime());
-            if (lane == 0) {
-                st_relaxed_u32(cnt1 + tile, CNT1_VALID | (uint32_t)n_events);
-                sup_old = atomicAdd(reinterpret_cast<unsigned long long*>(sup + (tile >> 5)), (1ull << 32) | (unsigned long long)n_events);
-            }
-            if (kQual) *reinterpret_cast<int4*>(s_cpre + rb) = make_int4(ex_s, ex_s + s0, ex_s + s1, ex_s + s2);
-            if (kSeq) {
-                s_gm[lane] = gm;
-                s_gex[lane] = ex_g;
-            }
-        }
-        // newline positions with rank in [win_lo, win_lo + EV_CAP), in order
-        auto scatter = [&](int win_lo) {
-            int rank = ex_cnt - win_lo;
-            const int p0 = lane * 64;
+            const int sw = lane & 7;
+            const uint4* row = d + lane * 8;
+            int acc = 0;
+            int pre[8];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                uint32_t m = h ? (uint32_t)(pm >> 32) : (uint32_t)pm;
-                while (m) {
-                    const int k = __ffs((int)m) - 1;
-                    m &= m - 1;
-                    if ((unsigned)rank < (unsigned)EV_CAP) ev_pos[rank] = (uint16_t)(p0 + h * 32 + k);
-                    rank++;
+                const uint4 c0 = row[(4 * h + 0) ^ sw], c1 = row[(4 * h + 1) ^ sw], c2 = row[(4 * h + 2) ^ sw], c3 = row[(4 * h + 3) ^ sw];
+                pm[h] = ((uint64_t)(nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16)) << 32) |
+                        (nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16));
+                if (kQual) {
+                    pre[4 * h + 0] = acc;
+                    acc = sbyte_sum16(c0, acc);
+                    pre[4 * h + 1] = acc;
+                    acc = sbyte_sum16(c1, acc);
+                    pre[4 * h + 2] = acc;
+                    acc = sbyte_sum16(c2, acc);
+                    pre[4 * h + 3] = acc;
+                    acc = sbyte_sum16(c3, acc);
+                }
+                if (kSeq)
+                    gm[h] = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
+                            (gc_mask16r(c0, c7b, c7f, pat_gc) | (gc_mask16r(c1, c7b, c7f, pat_gc) << 16));
+            }
+            const int cnt = __popcll(pm[0]) + __popcll(pm[1]);
+            const int g0 = kSeq ? __popcll(gm[0]) : 0, g1 = kSeq ? __popcll(gm[1]) : 0;
+            // newlines and G/C (each <= 4096 per tile: 13 bits) share one scan word; the byte sums get their own
+            const uint32_t packed = ((uint32_t)cnt << 16) + (uint32_t)(g0 + g1);
+            const uint32_t incl = warp_incl_scan_u32(packed);
+            const uint32_t ex = incl - packed;
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            ex_cnt = (int)(ex >> 16);
+            n_events = (int)(tot >> 16);
+            ex_g = (int)(ex & 0xFFFFu);
+            total_g = (int)(tot & 0xFFFFu);
+            if (kQual) {
+                const uint32_t si = warp_incl_scan_u32((uint32_t)acc);
+                ex_s = (int)(si - (uint32_t)acc);
+                total_s = (int)__shfl_sync(0xffffffffu, si, 31);
+                int4* cp = reinterpret_cast<int4*>(s_cpre + lane * 8);
+                cp[0] = make_int4(ex_s + pre[0], ex_s + pre[1], ex_s + pre[2], ex_s + pre[3]);
+                cp[1] = make_int4(ex_s + pre[4], ex_s + pre[5], ex_s + pre[6], ex_s + pre[7]);
+            }
+            if (kSeq) {
+                s_gm[2 * lane] = gm[0];
+                s_gm[2 * lane + 1] = gm[1];
+                s_gex[2 * lane] = ex_g;
+                s_gex[2 * lane + 1] = ex_g + g0;
+            }
+        }
+        if (lane == 0) a.tile_cnt[tile] = (uint32_t)n_events;
+
+        // newline positions with rank in [win_lo, win_lo + EV_CAP), in order.  Two per 32-bit mask word without a
+        // loop (a lane rarely owns more); the remainder, if any lane has one, goes through the generic loop.
+        auto scatter = [&](int win_lo) {
+            int rank = ex_cnt - win_lo;
+            bool more = false;
+#pragma unroll
+            for (int wd = 0; wd < 4; wd++) {
+                const uint32_t m = (uint32_t)(pm[wd >> 1] >> ((wd & 1) * 32));
+                const int base = lane * ROW_BYTES + wd * 32;
+                const uint32_t m1 = m & (m - 1);
+                if (m != 0 && (unsigned)rank < (unsigned)EV_CAP) ev_pos[rank] = (uint16_t)(base + __ffs((int)m) - 1);
+                if (m1 != 0 && (unsigned)(rank + 1) < (unsigned)EV_CAP) ev_pos[rank + 1] = (uint16_t)(base + __ffs((int)m1) - 1);
+                more = more || (m1 & (m1 - 1)) != 0;
+                rank += __popc(m);
+            }
+            if (__any_sync(0xffffffffu, more)) {
+                rank = ex_cnt - win_lo;
+#pragma unroll
+                for (int wd = 0; wd < 4; wd++) {
+                    uint32_t m = (uint32_t)(pm[wd >> 1] >> ((wd & 1) * 32));
+                    const int base = lane * ROW_BYTES + wd * 32;
+                    while (m) {
+                        if ((unsigned)rank < (unsigned)EV_CAP) ev_pos[rank] = (uint16_t)(base + __ffs((int)m) - 1);
+                        m &= m - 1;
+                        rank++;
+                    }
                 }
             }
         };
         scatter(0);
         __syncwarp();
 
-        // prefix sums at a newline position (tile-local): byte sum / G,C count of everything before it
-        auto event_prefix = [&](int pos, int& ps, int& pg) {
-            if (kQual) {
-                const int q = pos >> 4;
-                const uint4 v = d[q ^ ((q >> 3) & 3)];
-                const uint4 w = s_wlut[pos & 15];
-                int acc = s_cpre[q];
-                acc = __dp4a((int)v.x, (int)w.x, acc);
-                acc = __dp4a((int)v.y, (int)w.y, acc);
-                acc = __dp4a((int)v.z, (int)w.z, acc);
-                acc = __dp4a((int)v.w, (int)w.w, acc);
-                ps = acc;
+        // record space for this tile's newlines
+        int64_t rec_off = 0;
+        bool rec_ok = true;
+        if (!kFused) {
+            if (n_events > rec_left) {
+                const int need = n_events > REC_BLOCK ? n_events : REC_BLOCK;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.rec_bump, (unsigned long long)need);
+                rec_next = (int64_t)__shfl_sync(0xffffffffu, base, 0);
+                rec_left = need;
             }
-            if (kSeq) pg = s_gex[pos >> 6] + __popcll(s_gm[pos >> 6] & low_bits64(pos & 63));
-        };
-
-        // ---- B. tail word: position / sums after the tile's last newline (local information only)
-        int last_pos = -1, last_ps = 0, last_pg = 0;
-        if (n_events > 0) {
-            const uint32_t have = __ballot_sync(0xffffffffu, pm != 0);
-            const int top = 31 - __clz((int)have);
-            const int hi = 63 - __clzll((long long)pm);  // meaningful in lane `top`
-            last_pos = top * 64 + __shfl_sync(0xffffffffu, hi, top);
-            event_prefix(last_pos, last_ps, last_pg);
-            if (lane == 0)
-                st_relaxed_u64(tails + tile, tail_pack(2, (uint32_t)(last_pos + 1), (uint32_t)(total_g - last_pg), total_s - (last_ps + 10)));
-        } else if (lane == 0) {
-            st_relaxed_u64(tails + tile, tail_pack(1, 0, (uint32_t)total_g, total_s));
+            rec_off = rec_next;
+            rec_next += n_events;
+            rec_left -= n_events;
+            rec_ok = rec_off + n_events <= a.rec_space;
+            if (!rec_ok && lane == 0) a.result->overflow = 1;
+            if (lane == 0) a.tile_rec[tile] = rec_off;
         }
 
-        // ---- C. prefixes of the first 32 events (they do not depend on other tiles)
-        int pos = 0, ps = 0, pg = 0;
-        if (lane < n_events) {
-            pos = ev_pos[lane];
-            event_prefix(pos, ps, pg);
-        }
-
-        // ---- D. chaining: global line index of the tile's first newline; the open line
-        uint64_t excl;
-        {
-            const int64_t j = tile >> 5;
-            const int i = (int)(tile & 31);
-            const int group = (int)((n_tiles - j * SUPER_TILES) < SUPER_TILES ? (n_tiles - j * SUPER_TILES) : SUPER_TILES);
-            const unsigned long long old = __shfl_sync(0xffffffffu, sup_old, 0);
-            uint64_t sup_excl = init;
-            bool have_sup = j == 0;
-            if ((int)(old >> 32) == group - 1) {  // this warp completed the super tile: chain it
-                if (j > 0) sup_excl = super_lookback(sup, j, init);
-                have_sup = true;
-                if (lane == 0) st_relaxed_u64(sup + j, SUP_INC | ((sup_excl + (old & 0xffffffffull) + (uint64_t)n_events) & SUP_VAL));
-            }
-            uint32_t c = 0;
-            unsigned long long spins = 0;
-            while (true) {
-                spins++;
-                if (lane < i && !(c & CNT1_VALID)) c = ld_relaxed_u32(cnt1 + j * SUPER_TILES + lane);
-                uint64_t w = SUP_INC;
-                if (!have_sup) w = ld_relaxed_u64(sup + j - 1);
-                const bool ok1 = __all_sync(0xffffffffu, lane >= i || (c & CNT1_VALID));
-                if (!have_sup && (w >> 63)) {
-                    sup_excl = w & SUP_VAL;
-                    have_sup = true;
-                }
-                if (ok1 && have_sup) break;
-            }
-            excl = sup_excl + __reduce_add_sync(0xffffffffu, lane < i ? (c & ~CNT1_VALID) : 0u);
-            FQ_TRACE(1, gtime());
-            FQ_TRACE(2, spins | ((unsigned long long)((int)(old >> 32) == group - 1) << 32));
-        }
-        OpenLine open;
-        open.start = 0;
-        open.s = open.g = 0;
-        const bool is_last = tile == n_tiles - 1;
-        if (n_events > 0 || is_last) open = open_line_before(tails, tile, origin, a);
-
-        if (is_last && lane == 0) {  // final state of this range (chaining / host)
-            a.result->total_lines = excl + (uint64_t)n_events;
-            if (n_events > 0) {
-                a.result->open_line_start = tile_base + last_pos + 1;
-                a.result->tail_s = total_s - (last_ps + 10);
-                a.result->tail_g = total_g - last_pg;
-            } else {
-                a.result->open_line_start = open.start;
-                a.result->tail_s = (int64_t)open.s + total_s;
-                a.result->tail_g = (int64_t)open.g + total_g;
-            }
-        }
-
-        // ---- E. emission, 32 events per pass
-        int c_pos = 0, c_ps = 0, c_pg = 0;  // last event of the previous pass (ps includes that newline)
+        // ---- B. one newline per lane: its record (and, fused, the verdict of the line it ends)
+        // fused: in every pass lane l handles a line with tile-local index = l (mod 4), so its bucket
+        // (the phase hypothesis under which that line is a quality line) is fixed: h = (3 - l) & 3.
+        uint32_t f_cq = 0;  // count | length sum << 12
+        int f_qs = 0;
+        uint32_t f_bad = 0;  // hypotheses (bit h) this lane's lines contradict
+        int first_ps = 0;
+        uint32_t first_y = 0;
+        int c_ps = 0;  // last record of the previous pass
+        uint32_t c_y = 0;
+        int ps = 0, pg = 0;
+        uint32_t y = 0;
         for (int lo = 0; lo < n_events; lo += 32) {
-            if (lo > 0) {
-                if ((lo & (EV_CAP - 1)) == 0) {  // more newlines than the event window holds (rare): refill it
-                    __syncwarp();
-                    scatter(lo);
-                    __syncwarp();
-                }
-                if (lo + lane < n_events) {
-                    pos = ev_pos[(lo & (EV_CAP - 1)) + lane];
-                    event_prefix(pos, ps, pg);
-                }
+            if (lo > 0 && (lo & (EV_CAP - 1)) == 0) {  // more newlines than the event window holds: refill it
+                __syncwarp();
+                scatter(lo);
+                __syncwarp();
             }
             const bool active = lo + lane < n_events;
-            int ppos = __shfl_up_sync(0xffffffffu, pos, 1), pps = 0, ppg = 0;
-            if (kQual) pps = __shfl_up_sync(0xffffffffu, ps, 1) + 10;
-            if (kSeq) ppg = __shfl_up_sync(0xffffffffu, pg, 1);
-            if (lane == 0) {
-                ppos = c_pos;
-                pps = c_ps;
-                ppg = c_pg;
-            }
             if (active) {
-                const uint64_t g = excl + (uint64_t)(lo + lane);  // global index of the line this newline ends
-                const bool first_of_tile = (lo + lane) == 0;
-                uint32_t len;
-                int ssum = 0, gsum = 0, first_byte;
-                int64_t line_start;
-                if (!first_of_tile) {
-                    len = (uint32_t)(pos - ppos - 1);
-                    if (kQual) ssum = ps - pps;
-                    if (kSeq) gsum = pg - ppg;
-                    line_start = tile_base + ppos + 1;
-                } else {  // the line that was open when the tile began
-                    line_start = open.start;
-                    len = (uint32_t)(tile_base - open.start) + (uint32_t)pos;
-                    if (kQual) ssum = ps + open.s;
-                    if (kSeq) gsum = pg + open.g;
+                const int pos = ev_pos[(lo & (EV_CAP - 1)) + lane];
+                const int so = sidx(pos);  // byte offset of the newline in the swizzled buffer
+                if (kQual) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(sbytes + (so & ~15));
+                    const uint4 w = s_wlut[pos & 15];
+                    int acc = s_cpre[pos >> 4];
+                    acc = __dp4a((int)v.x, (int)w.x, acc);
+                    acc = __dp4a((int)v.y, (int)w.y, acc);
+                    acc = __dp4a((int)v.z, (int)w.z, acc);
+                    acc = __dp4a((int)v.w, (int)w.w, acc);
+                    ps = acc;
                 }
-                const int64_t e = tile_base + pos;
-                if (g < a.max_lines) {
-                    // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing
-                    uint32_t cr = 0;
-                    if (len > 0 && !(a.is_final && e == a.n)) cr = (pos > 0 ? (int)sbytes[sidx(pos - 1)] : any_byte(e - 1)) == '\r';
-                    len -= cr;
-                    const int ph = (int)(g & 3);
-                    const uint64_t r = g >> 2;
-                    if (kLines) {
-                        if (g < (uint64_t)a.line_cap) reinterpret_cast<OffT*>(a.line_end)[g] = (OffT)e;
-                        else a.result->overflow = 1;
-                    }
-                    if ((ph & 1) == 0) {  // header / plus line: its first byte must be '@' / '+'
-                        first_byte = first_of_tile ? any_byte(line_start) : (int)sbytes[sidx(ppos + 1)];
-                        if (first_byte != (ph == 0 ? '@' : '+')) atomicMax(&a.result->err_pos, ~(unsigned long long)line_start);
-                    } else if (ph == 1) {
-                        if (kSeq) {
-                            if (r < (uint64_t)a.rec_cap) {
-                                a.seq_len[r] = len;
-                                a.gc[r] = (uint32_t)gsum;
-                            } else {
-                                a.result->overflow = 1;
-                            }
-                        }
-                    } else if (kQual) {
-                        const int qs = ssum - 13 * (int)cr - 33 * (int)len;
-                        if (kFused) {
-                            bool ok = true;
-                            for (int i = 0; i < a.n_fused; i++) {
-                                const exb_predicate p = a.fused[i];
-                                ok = ok && (p.field == EXB_P_MEAN_QUALITY ? exb_mean_cmp((int64_t)qs, len, p.op, p.value)
-                                                                          : exb_cmp((double)len, p.op, p.value));
-                            }
-                            if (ok) {
-                                f_cnt += 1;
-                                f_qs += qs;
-                                f_ql += len;
-                            }
-                        } else if (r < (uint64_t)a.rec_cap) {
-                            a.qual_len[r] = len;
-                            a.qsum[r] = qs;
-                        } else {
-                            a.result->overflow = 1;
-                        }
-                    }
-                }
+                if (kSeq) pg = s_gex[pos >> 6] + __popcll(s_gm[pos >> 6] & low_bits64(pos & 63));
+                // a CR directly before a real LF is stripped (when the line is not empty: the consumer checks);
+                // the virtual '\n' at EOF strips nothing
+                int before = -1;
+                if (pos > 0) before = sbytes[(pos & 15) ? so - 1 : sidx(pos - 1)];
+                else if (tile_base - 1 >= (a.prev ? 0 : a.begin)) before = buf[tile_base - 1];
+                const uint32_t cr = (before == '\r' && !(a.is_final && tile_base + pos == a.n)) ? 1u : 0u;
+                uint32_t nf = 0;
+                if (pos + 1 < WT_BYTES) nf = at_plus_flags(sbytes[((pos & 15) != 15) ? so + 1 : sidx(pos + 1)]);
+                y = rec_pack(pos, cr, nf, kSeq ? pg : 0);
+                if (!kFused && rec_ok) a.records[rec_off + lo + lane] = make_uint2((uint32_t)ps, y);
             }
-            c_pos = __shfl_sync(0xffffffffu, pos, 31);
-            if (kQual) c_ps = __shfl_sync(0xffffffffu, ps, 31) + 10;
-            if (kSeq) c_pg = __shfl_sync(0xffffffffu, pg, 31);
+            if (kFused) {
+                int pps = __shfl_up_sync(0xffffffffu, ps, 1);
+                uint32_t py = __shfl_up_sync(0xffffffffu, y, 1);
+                if (lane == 0) {
+                    pps = c_ps;
+                    py = c_y;
+                }
+                if (active && lo + lane > 0) {  // line `lo + lane` of the tile: it starts right after the previous newline
+                    uint32_t len = (uint32_t)(rec_pos(y) - rec_pos(py) - 1);
+                    const uint32_t cr = len > 0 ? rec_cr(y) : 0u;
+                    len -= cr;
+                    const int qs = ps - pps - 10 - 13 * (int)cr - 33 * (int)len;
+                    if (fused_pass(a, plan, qs, len)) {
+                        f_cq += 1u + (len << 12);
+                        f_qs += qs;
+                    }
+                    // the line is a header under hypothesis (0 - li) & 3 and a plus line under (2 - li) & 3, li = lane (mod 4)
+                    const uint32_t nfl = rec_next_flags(py);  // flags of this line's first byte
+                    if (!(nfl & 2u)) f_bad |= 1u << ((0 - lane) & 3);
+                    if (!(nfl & 1u)) f_bad |= 1u << ((2 - lane) & 3);
+                }
+                c_ps = __shfl_sync(0xffffffffu, ps, 31);
+                c_y = __shfl_sync(0xffffffffu, y, 31);
+            }
+            if (lo == 0) {
+                first_ps = __shfl_sync(0xffffffffu, ps, 0);
+                first_y = __shfl_sync(0xffffffffu, y, 0);
+            }
+        }
+
+        // ---- C. tail word: what follows the tile's last newline (local information only)
+        {
+            const uint32_t b0 = at_plus_flags(sbytes[sidx(tile == 0 ? (int)(a.begin - origin) : 0)]);
+            uint64_t tw;
+            if (n_events > 0) {
+                const int src = (n_events - 1) & 31;  // lane holding the last record
+                const int lps = __shfl_sync(0xffffffffu, ps, src);
+                const uint32_t ly = __shfl_sync(0xffffffffu, y, src);
+                tw = tail_pack(2, (rec_next_flags(ly) << 2) | b0, (uint32_t)(rec_pos(ly) + 1), (uint32_t)(total_g - rec_pg(ly)),
+                               total_s - (lps + 10));
+            } else {
+                tw = tail_pack(1, b0, 0, (uint32_t)total_g, total_s);
+            }
+            if (lane == 0) a.tails[tile] = tw;
+        }
+
+        if (kFused) {
+            // fold the lanes that share a bucket (lanes 4 apart); contradictions are OR-ed over the warp
+#pragma unroll
+            for (int dd = 4; dd < 32; dd <<= 1) {
+                f_cq += __shfl_xor_sync(0xffffffffu, f_cq, dd);
+                f_qs += __shfl_xor_sync(0xffffffffu, f_qs, dd);
+            }
+            const uint32_t bad4 = __reduce_or_sync(0xffffffffu, f_bad);
+            FusedTile* ft = a.fused_tiles + tile;
+            if (lane < 4) {
+                const int h = (3 - lane) & 3;  // lane l holds the totals of bucket (3 - l) & 3
+                ft->cq[h] = f_cq;
+                ft->qs[h] = f_qs;
+            } else if (lane == 4) {
+                *reinterpret_cast<uint4*>(&ft->ps0) = make_uint4((uint32_t)first_ps, first_y, bad4, 0u);
+            }
         }
 
         __syncwarp();  // the event list / prefix arrays are rewritten by the next tile
         cur = nxt;
         b ^= 1;
     }
-    cp_async_wait<0>();
+}
 
-    if (kFused) {  // one flush per warp
-#pragma unroll
-        for (int dd = 16; dd > 0; dd >>= 1) {
-            f_cnt += __shfl_xor_sync(0xffffffffu, f_cnt, dd);
-            f_qs += __shfl_xor_sync(0xffffffffu, f_qs, dd);
-            f_ql += __shfl_xor_sync(0xffffffffu, f_ql, dd);
+// =================================================================== K2 helpers
+struct OpenLine {  // the line that is open at a tile's first byte
+    int64_t start;
+    int s, g;        // byte sum / G,C count of its part before the tile (mod 2^32)
+    uint32_t flags;  // first byte is '@' (bit 1) / '+' (bit 0)
+};
+
+// Walk the predecessors' tail words back to the tile that holds the open line's start: tile-1 unless
+// lines are longer than a tile.  Serial per calling thread (K1 has finished: plain loads, no polling).
+__device__ __forceinline__ OpenLine open_line_before(const uint64_t* __restrict__ tails, int64_t tile, int64_t origin, const FastqScanArgs& a) {
+    OpenLine o;
+    o.s = 0;
+    o.g = 0;
+    uint32_t next_b0 = tail_byte0_flags(tails[tile]);  // first-byte flags of the tile after the one being inspected
+    for (int64_t k = tile - 1; k >= 0; k--) {
+        const uint64_t w = tails[k];
+        o.s += tail_s_of(w);
+        o.g += (int)tail_g_of(w);
+        if ((uint32_t)(w >> 62) == 2u) {
+            const uint32_t rel = tail_rel_of(w);
+            o.start = origin + k * WT_BYTES + rel;
+            o.flags = rel < (uint32_t)WT_BYTES ? tail_open_flags(w) : next_b0;  // rel = 4096: the line starts with the next tile
+            return o;
         }
-        if (lane == 0 && f_cnt != 0) {
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.fused_agg) + 0, (unsigned long long)f_cnt);
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.fused_agg) + 3, (unsigned long long)f_qs);
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.fused_agg) + 4, (unsigned long long)f_ql);
+        next_b0 = tail_byte0_flags(w);
+    }
+    if (a.prev && a.prev->open_line_start < a.begin) {  // the line began in an earlier range of a chained scan
+        o.start = a.prev->open_line_start;
+        o.s += (int)a.prev->tail_s;
+        o.g += (int)a.prev->tail_g;
+        o.flags = a.prev->pad & 3u;
+    } else {  // it starts at `begin`: tile 0's byte-0 flags describe that byte
+        o.start = a.begin;
+        o.flags = next_b0;
+    }
+    return o;
+}
+
+__device__ __forceinline__ void write_final_state(const FastqScanArgs& a, uint64_t total_lines, int n_events, int64_t tile_base, uint64_t tw,
+                                                  const OpenLine& open) {
+    a.result->total_lines = total_lines;
+    if (n_events > 0) {
+        a.result->open_line_start = tile_base + tail_rel_of(tw);
+        a.result->tail_s = tail_s_of(tw);
+        a.result->tail_g = tail_g_of(tw);
+        a.result->pad = tail_open_flags(tw);  // meaningless if the open line has no byte yet (it then starts at the next range's begin)
+    } else {
+        a.result->open_line_start = open.start;
+        a.result->tail_s = (int64_t)open.s + tail_s_of(tw);
+        a.result->tail_g = (int64_t)open.g + tail_g_of(tw);
+        a.result->pad = open.flags;
+    }
+}
+
+// =================================================================== K2
+// One warp per tile: turns the tile's records into per-line / per-record outputs.
+template <typename OffT, int FLAGS>
+__global__ void __launch_bounds__(256) fastq_emit_kernel(const FastqScanArgs a) {
+    constexpr bool kLines = (FLAGS & EXB_F_LINES) != 0;
+    constexpr bool kSeq = (FLAGS & EXB_F_SEQ) != 0, kQual = (FLAGS & EXB_F_QUAL) != 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = a.n_tiles;
+    const int64_t origin = a.begin & ~(int64_t)15;
+    const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool overflowed = a.result->overflow != 0;  // K1 ran out of record space: the caller retries with more
+
+    for (int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+        const int n_events = (int)a.tile_cnt[tile];
+        const bool is_last = tile == n_tiles - 1;
+        if (tile == 0 && lane == 0 && a.prev) {  // chained range: errors of earlier ranges stay visible in the last result
+            if (a.prev->err_pos != 0ull) atomicMax(&a.result->err_pos, a.prev->err_pos);
+            if (a.prev->overflow) a.result->overflow = 1;
+        }
+        if (n_events == 0 && !is_last) continue;
+        const int64_t tile_base = origin + tile * WT_BYTES;
+        const uint64_t excl = init + (uint64_t)a.line_base[tile];
+        const OpenLine open = open_line_before(a.tails, tile, origin, a);  // same addresses in every lane: broadcast loads
+        if (is_last && lane == 0) write_final_state(a, excl + (uint64_t)n_events, n_events, tile_base, a.tails[tile], open);
+        if (overflowed) continue;
+
+        const uint2* __restrict__ recs = a.records + a.tile_rec[tile];
+        int c_ps = 0;
+        uint32_t c_y = 0;
+        for (int lo = 0; lo < n_events; lo += 32) {
+            const bool active = lo + lane < n_events;
+            uint2 r = make_uint2(0u, 0u);
+            if (active) r = recs[lo + lane];
+            int pps = __shfl_up_sync(0xffffffffu, (int)r.x, 1);
+            uint32_t py = __shfl_up_sync(0xffffffffu, r.y, 1);
+            if (lane == 0) {
+                pps = c_ps;
+                py = c_y;
+            }
+            if (active) {
+                const int li = lo + lane;
+                const uint64_t g = excl + (uint64_t)li;  // global index of the line this newline ends
+                const int pos = rec_pos(r.y);
+                const int64_t e = tile_base + pos;
+                uint32_t len, first_flags;
+                int ssum = 0, gsum = 0;
+                int64_t line_start;
+                if (li > 0) {
+                    const int ppos = rec_pos(py);
+                    len = (uint32_t)(pos - ppos - 1);
+                    if (kQual) ssum = (int)r.x - pps - 10;
+                    if (kSeq) gsum = rec_pg(r.y) - rec_pg(py);
+                    line_start = tile_base + ppos + 1;
+                    first_flags = rec_next_flags(py);
+                } else {  // the line that was open when the tile began
+                    line_start = open.start;
+                    len = (uint32_t)(tile_base - open.start) + (uint32_t)pos;
+                    if (kQual) ssum = (int)r.x + open.s;
+                    if (kSeq) gsum = rec_pg(r.y) + open.g;
+                    first_flags = open.flags;
+                }
+                if (g < a.max_lines) {
+                    const uint32_t cr = len > 0 ? rec_cr(r.y) : 0u;
+                    len -= cr;
+                    const int ph = (int)(g & 3);
+                    const uint64_t rix = g >> 2;
+                    if (kLines) {
+                        if (g < (uint64_t)a.line_cap) reinterpret_cast<OffT*>(a.line_end)[g] = (OffT)e;
+                        else a.result->overflow = 1;
+                    }
+                    if ((ph & 1) == 0) {  // header / plus line: its first byte must be '@' / '+'
+                        if (!(first_flags & (ph == 0 ? 2u : 1u))) atomicMax(&a.result->err_pos, ~(unsigned long long)line_start);
+                    } else if (ph == 1) {
+                        if (kSeq) {
+                            if (rix < (uint64_t)a.rec_cap) {
+                                a.seq_len[rix] = len;
+                                a.gc[rix] = (uint32_t)gsum;
+                            } else {
+                                a.result->overflow = 1;
+                            }
+                        }
+                    } else if (kQual) {
+                        if (rix < (uint64_t)a.rec_cap) {
+                            a.qual_len[rix] = len;
+                            a.qsum[rix] = ssum - 13 * (int)cr - 33 * (int)len;
+                        } else {
+                            a.result->overflow = 1;
+                        }
+                    }
+                }
+            }
+            c_ps = __shfl_sync(0xffffffffu, (int)r.x, 31);
+            c_y = __shfl_sync(0xffffffffu, r.y, 31);
         }
     }
 }
 
-// ------------------------------------------------------------------ launcher
+// K2 of the fused flavour: one thread per tile picks the bucket of the tile's true phase and finishes the
+// tile's first line; one atomicAdd per warp.
+__global__ void __launch_bounds__(256) fastq_fused_combine_kernel(const FastqScanArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = a.n_tiles;
+    const int64_t origin = a.begin & ~(int64_t)15;
+    const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
+    const int64_t threads = (int64_t)gridDim.x * blockDim.x;
+    const FusedPlan plan = make_plan(a);
+    long long cnt = 0, qs = 0, ql = 0;
+    bool bad = false;
+    for (int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tile < n_tiles; tile += threads) {
+        const int n_events = (int)a.tile_cnt[tile];
+        const bool is_last = tile == n_tiles - 1;
+        if (tile == 0 && a.prev && a.prev->err_pos != 0ull) atomicMax(&a.result->err_pos, a.prev->err_pos);
+        if (n_events == 0 && !is_last) continue;
+        const uint64_t excl = init + (uint64_t)a.line_base[tile];
+        const int64_t tile_base = origin + tile * WT_BYTES;
+        const OpenLine open = open_line_before(a.tails, tile, origin, a);
+        if (n_events > 0) {
+            const FusedTile* ft = a.fused_tiles + tile;
+            const int h = (int)(excl & 3);
+            const uint32_t cq = ft->cq[h];
+            cnt += cq & 0xFFFu;
+            ql += cq >> 12;
+            qs += ft->qs[h];
+            bad = bad || ((ft->bad4 >> h) & 1u) != 0;
+            // the tile's first line (it began in an earlier tile, or exactly at this tile's first byte)
+            const uint32_t y0 = ft->y0;
+            uint32_t len = (uint32_t)(tile_base - open.start) + (uint32_t)rec_pos(y0);
+            const uint32_t cr = len > 0 ? rec_cr(y0) : 0u;
+            len -= cr;
+            if ((h & 1) == 0) {
+                if (!(open.flags & (h == 0 ? 2u : 1u))) bad = true;
+            } else if (h == 3) {
+                const int q1 = ft->ps0 + open.s - 13 * (int)cr - 33 * (int)len;
+                // lines longer than a tile can exceed the |sum| < 2^20 precondition of the fast path: use the general test
+                FusedPlan p1 = plan;
+                if (len > 4096u) p1.simple = 0;
+                if (fused_pass(a, p1, q1, len)) {
+                    cnt += 1;
+                    qs += q1;
+                    ql += len;
+                }
+            }
+        }
+        if (is_last) write_final_state(a, excl + (uint64_t)n_events, n_events, tile_base, a.tails[tile], open);
+    }
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, dd);
+        qs += __shfl_xor_sync(0xffffffffu, qs, dd);
+        ql += __shfl_xor_sync(0xffffffffu, ql, dd);
+    }
+    const bool any_bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(a.fused_agg) + 0, (unsigned long long)cnt);
+        if (qs) atomicAdd(reinterpret_cast<unsigned long long*>(a.fused_agg) + 3, (unsigned long long)qs);
+        if (ql) atomicAdd(reinterpret_cast<unsigned long long*>(a.fused_agg) + 4, (unsigned long long)ql);
+        // malformed input: the fused flavour knows THAT a line start contradicts its phase, not where; the host
+        // wrapper re-runs the general scan for the offset when it sees this mark (err_pos = n)
+        if (any_bad) atomicMax(&a.result->err_pos, ~(unsigned long long)a.n);
+    }
+}
+
+// ------------------------------------------------------------------ launchers
 int64_t fastq_scan_tiles(int64_t begin, int64_t n, int is_final) {
     const int64_t origin = begin & ~(int64_t)15;
     // final range: +1 byte of room for the virtual terminator at n
     const int64_t t = (n + (is_final ? 1 : 0) - origin + WT_BYTES - 1) / WT_BYTES;
     return t > 0 ? t : 1;
 }
-int64_t fastq_scan_chain_bytes(int64_t n_tiles) {  // tail word + count word per tile, one accumulator per 32 tiles
-    return n_tiles * 12 + ((n_tiles + SUPER_TILES - 1) / SUPER_TILES) * 8 + 16;
+int64_t fastq_record_slack(int64_t n_tiles) {  // record slots the per-warp bump allocation may leave unused
+    const int64_t max_warps = (int64_t)160 * 8 * FQ_WARPS;
+    const int64_t warps = n_tiles < max_warps ? n_tiles : max_warps;
+    return warps * REC_BLOCK + REC_BLOCK;
 }
 
-template <typename OffT, int FLAGS>
-static cudaError_t launch_one(const FastqScanArgs& a, cudaStream_t st) {
-    constexpr int smem = FqWarpSmem<FLAGS>::total * FQ_WARPS;
-    auto kern = fastq_scan_kernel<OffT, FLAGS>;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// The input viewed as rows of 128 bytes starting at `origin`; only rows that lie completely inside the range.
+static cudaError_t make_tensor_map(const FastqScanArgs& a, CUtensorMap* tm, int64_t* rows_out) {
+    const int64_t origin = a.begin & ~(int64_t)15;
+    int64_t rows = (a.n - origin) / ROW_BYTES;
+    if (rows < 0) rows = 0;
+    *rows_out = rows;
+    memset(tm, 0, sizeof(*tm));
+    if (rows == 0) return cudaSuccess;  // tiny input: the kernel stages it by hand
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return cudaErrorNotSupported;
+    const cuuint64_t dims[2] = {(cuuint64_t)ROW_BYTES, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ROW_BYTES};
+    const cuuint32_t box[2] = {(cuuint32_t)ROW_BYTES, (cuuint32_t)WT_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(a.buf) + origin, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int FLAGS>
+static cudaError_t launch_tile_kernel(FastqScanArgs a, cudaStream_t st) {
+    constexpr int smem = FqWarpAux<FLAGS>::cta_bytes;
+    auto kern = fastq_tile_kernel<FLAGS>;
     static int ctas_per_sm = 0, n_sm = 0;  // per template instance; one device type per process
+    cudaError_t e;
     if (ctas_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
         int dev = 0, occ = 0, sms = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
@@ -655,41 +802,55 @@ static cudaError_t launch_one(const FastqScanArgs& a, cudaStream_t st) {
         n_sm = sms;
         ctas_per_sm = occ > 0 ? occ : 1;
     }
+    alignas(64) CUtensorMap tm;
+    if ((e = make_tensor_map(a, &tm, &a.tma_rows)) != cudaSuccess) return e;
     int64_t grid = (a.n_tiles + FQ_WARPS - 1) / FQ_WARPS;
     const int64_t persistent = (int64_t)n_sm * ctas_per_sm;
     if (grid > persistent) grid = persistent;
     // 0x7F7F7F7F / 0x7B7B7B7B travel as arguments so that ptxas keeps them in registers (see eq_flags)
-    kern<<<dim3((unsigned)grid), dim3(FQ_THREADS), smem, st>>>(a, 0x7F7F7F7Fu, 0x7B7B7B7Bu);
+    kern<<<dim3((unsigned)grid), dim3(FQ_THREADS), smem, st>>>(tm, a, 0x7F7F7F7Fu, 0x7B7B7B7Bu);
     return cudaGetLastError();
 }
 
+cudaError_t fastq_tile_launch(const FastqScanArgs& a, int flags, cudaStream_t st) {
+    if (flags & EXB_F_FUSED) return launch_tile_kernel<EXB_F_FUSED | EXB_F_QUAL>(a, st);
+    switch (flags & (EXB_F_SEQ | EXB_F_QUAL)) {
+    case 0: return launch_tile_kernel<0>(a, st);
+    case EXB_F_SEQ: return launch_tile_kernel<EXB_F_SEQ>(a, st);
+    case EXB_F_QUAL: return launch_tile_kernel<EXB_F_QUAL>(a, st);
+    default: return launch_tile_kernel<EXB_F_SEQ | EXB_F_QUAL>(a, st);
+    }
+}
+
+template <typename OffT, int FLAGS>
+static cudaError_t launch_emit_kernel(const FastqScanArgs& a, cudaStream_t st) {
+    int64_t blocks = (a.n_tiles + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    fastq_emit_kernel<OffT, FLAGS><<<dim3((unsigned)blocks), dim3(256), 0, st>>>(a);
+    return cudaGetLastError();
+}
 template <typename OffT>
-static cudaError_t launch_fastq(const FastqScanArgs& a, int flags, cudaStream_t st) {
-    if (flags & EXB_F_FUSED) {  // quality-line predicates + COUNT, nothing per record leaves the kernel
-        return (flags & EXB_F_LINES) ? launch_one<OffT, EXB_F_FUSED | EXB_F_QUAL | EXB_F_LINES>(a, st)
-                                     : launch_one<OffT, EXB_F_FUSED | EXB_F_QUAL>(a, st);
-    }
+static cudaError_t launch_emit(const FastqScanArgs& a, int flags, cudaStream_t st) {
     switch (flags & 7) {
-    case 0: return launch_one<OffT, 0>(a, st);
-    case 1: return launch_one<OffT, 1>(a, st);
-    case 2: return launch_one<OffT, 2>(a, st);
-    case 3: return launch_one<OffT, 3>(a, st);
-    case 4: return launch_one<OffT, 4>(a, st);
-    case 5: return launch_one<OffT, 5>(a, st);
-    case 6: return launch_one<OffT, 6>(a, st);
-    default: return launch_one<OffT, 7>(a, st);
+    case 0: return launch_emit_kernel<OffT, 0>(a, st);
+    case 1: return launch_emit_kernel<OffT, 1>(a, st);
+    case 2: return launch_emit_kernel<OffT, 2>(a, st);
+    case 3: return launch_emit_kernel<OffT, 3>(a, st);
+    case 4: return launch_emit_kernel<OffT, 4>(a, st);
+    case 5: return launch_emit_kernel<OffT, 5>(a, st);
+    case 6: return launch_emit_kernel<OffT, 6>(a, st);
+    default: return launch_emit_kernel<OffT, 7>(a, st);
     }
 }
 
-#ifdef EXB_FQ_TRACE
-extern "C" __attribute__((visibility("default"))) int exb_debug_set_fq_trace(void* d_trace) {
-    unsigned long long* p = reinterpret_cast<unsigned long long*>(d_trace);
-    return (int)cudaMemcpyToSymbol(g_fq_trace, &p, sizeof(p));
-}
-#endif
-
-cudaError_t fastq_scan_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st) {
-    return wide_offsets ? launch_fastq<uint64_t>(a, flags, st) : launch_fastq<uint32_t>(a, flags, st);
+cudaError_t fastq_emit_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st) {
+    if (flags & EXB_F_FUSED) {
+        int64_t blocks = (a.n_tiles + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        fastq_fused_combine_kernel<<<dim3((unsigned)blocks), dim3(256), 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    return wide_offsets ? launch_emit<uint64_t>(a, flags, st) : launch_emit<uint32_t>(a, flags, st);
 }
 
 }  // namespace exb

@@ -509,6 +509,7 @@ struct Reader {
             const bool numeric = needs_numeric();
             int64_t rec_cap = n / 32 + 4096;
             for (int attempt = 0;; attempt++) {
+                if (attempt && !d_ws.need(exb_fastq_workspace_bytes(n + 16, n + 1))) return fail("out of device memory");
                 if (!d_line.need(rec_cap * 4 * 4)) return fail("out of device memory");
                 if (numeric)
                     for (int k = 0; k < 4; k++)

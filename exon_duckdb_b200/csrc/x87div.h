@@ -13,8 +13,10 @@
 
 #if defined(__CUDACC__)
 #define EXB_HD __host__ __device__ __forceinline__
+#define EXB_HD_COLD static __host__ __device__ __noinline__
 #else
 #define EXB_HD static inline
+#define EXB_HD_COLD static
 #endif
 
 EXB_HD int exb_clz64(uint64_t v) {
@@ -94,25 +96,29 @@ EXB_HD bool exb_cmp(double v, int op, double c) {
     }
 }
 
+// The rare part of exb_mean_cmp: sum/n is within a few ulp of c, so the two roundings of the x87 path decide.
+// Kept out of line: it is ~200 instructions that almost no record executes.
+EXB_HD_COLD bool exb_mean_cmp_close(int64_t sum, uint32_t n, int op, double c) {
+    double q = (double)sum / (double)n;  // correctly rounded once; x87 may differ by 1 ulp
+    double d = fabs(q - c);
+    if (d > fabs(q) * 8.8817841970012523e-16) return exb_cmp(q, op, c);  // > 4 ulp away: same verdict
+    return exb_cmp(exb_x87_div(sum, n), op, c);
+}
+
 // list_avg(...) <op> c for a list of n ints summing to `sum`; empty list = NULL = false.
 EXB_HD bool exb_mean_cmp(int64_t sum, uint32_t n, int op, double c) {
     if (n == 0) return false;
     // Division-free verdict when sum/n is clearly on one side of c: D = sum - c*n has the sign of
     // sum/n - c, and |D| > 1e-14 |c n| puts the exact quotient more than 40 ulp away from c, which
     // neither of the two roundings can cross.  (t and d carry <= 2 ulp of error themselves.)
-    {
-        const double t = c * (double)n, d = (double)sum - t;
-        if (fabs(d) > fabs(t) * 1e-14) {
-            switch (op) {
-            case 0: case 1: return d > 0;
-            case 2: case 3: return d < 0;
-            case 4: return false;
-            default: return true;
-            }
+    const double t = c * (double)n, d = (double)sum - t;
+    if (fabs(d) > fabs(t) * 1e-14) {
+        switch (op) {
+        case 0: case 1: return d > 0;
+        case 2: case 3: return d < 0;
+        case 4: return false;
+        default: return true;
         }
     }
-    double q = (double)sum / (double)n;  // correctly rounded once; x87 may differ by 1 ulp
-    double d = fabs(q - c);
-    if (d > fabs(q) * 8.8817841970012523e-16) return exb_cmp(q, op, c);  // > 4 ulp away: same verdict
-    return exb_cmp(exb_x87_div(sum, n), op, c);
+    return exb_mean_cmp_close(sum, n, op, c);
 }

@@ -117,7 +117,8 @@ def fastq_scan(buf, flags=F_SEQ | F_QUAL, rec_cap=None, begin=0, n=None, max_lin
         if flags & F_QUAL:
             s.qual_len = _empty(rec_cap, torch.int32, dev)
             s.qsum = _empty(rec_cap, torch.int32, dev)
-        s.ws = workspace(span + 16, dev)
+        # the workspace carries one 8-byte record per line between the scan's two kernels
+        s.ws = torch.empty(lib().exb_fastq_workspace_bytes(span + 16, 4 * rec_cap + 4), dtype=torch.uint8, device=dev)
         s.rec_cap = rec_cap
     s.buf, s.n, s.begin, s.flags, s._res = buf, n, begin, flags, None
     check(lib().exb_fastq_scan(_ptr(buf), begin, n, 1, None, max_lines, flags, _ptr(s.line_end),

@@ -140,8 +140,8 @@ typedef struct exb_scan_result {
     uint64_t total_lines;     /* FASTQ: lines seen, the unterminated last line included  */
     int64_t open_line_start;  /* offset of the first byte after the last newline         */
     uint64_t err_pos;         /* smallest offset of a malformed line start; ~0 = none    */
-    uint32_t overflow;        /* 1 = an output capacity was too small                    */
-    uint32_t pad;
+    uint32_t overflow;        /* 1 = an output capacity (or the workspace) was too small */
+    uint32_t pad;             /* FASTQ chaining: first byte of the open line is '@' (2) / '+' (1) */
     uint64_t n_records;       /* FASTA: number of '>' header lines                       */
     uint64_t seq_bytes;       /* FASTA: sequence bytes kept (line terminators stripped)  */
     uint64_t gc_total;        /* FASTA: G/C among them                                   */
@@ -149,8 +149,13 @@ typedef struct exb_scan_result {
     uint64_t tail_hdr;        /* FASTA: the open line is a header line (chaining)          */
 } exb_scan_result;
 
-/* Bytes of zero-initialised scratch a scan over n input bytes needs. */
+/* Bytes of scratch a scan over n input bytes needs (the calls clear what they need cleared).
+ * For a FASTQ scan the workspace also holds one 8-byte record per line between the
+ * two kernels of the scan; this size assumes lines of >= 24 bytes on average.  A
+ * scan that meets more lines reports overflow = 1: retry with a workspace of
+ * exb_fastq_workspace_bytes(n, max_lines) (max_lines = n + 1 always suffices). */
 EXB_API int64_t exb_scan_workspace_bytes(int64_t n);
+EXB_API int64_t exb_fastq_workspace_bytes(int64_t n, int64_t max_lines);
 
 /*
  * FASTQ scan of d_buf[begin, n) (noodles-fastq read_record semantics):
@@ -159,10 +164,11 @@ EXB_API int64_t exb_scan_workspace_bytes(int64_t n);
  * passing the previous call's workspace as d_prev_workspace (NULL for the first
  * range, whose `begin` must be a record start) and is_final = 1 only for the
  * range that ends the input; line / record indices and the outputs they address
- * continue across the calls.  Lines with index >= max_lines are ignored
+ * continue across the calls.  The previous workspace must stay untouched until
+ * this call has completed on `stream`.  Lines with index >= max_lines are ignored
  * (UINT64_MAX = all).  d_buf must be 16-byte aligned and `begin` of a chained
  * range a multiple of 16.  d_workspace: exb_scan_workspace_bytes(n)
- * bytes; it is cleared on `stream` by this call.  The scalar results land in
+ * bytes, 16-byte aligned.  The scalar results land in
  * the first sizeof(exb_scan_result) bytes of the workspace; fetch them with
  * exb_scan_result_fetch.
  *   d_line_end : uint32_t[line_cap] (wide_offsets = 0, n < 4 GiB) or uint64_t[line_cap]

@@ -8,16 +8,19 @@ from collections import defaultdict
 
 rep = sys.argv[1]
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
+units = float(sys.argv[3]) if len(sys.argv) > 3 else 0  # normalise per this many work units (e.g. tiles) instead of per warp
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 d = dict(zip(rows[0], rows[2]))
 warps = int(d["launch__grid_size"].replace(",", "")) * int(d["launch__block_size"].replace(",", "")) // 32
+if units:
+    warps = units
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 per = defaultdict(lambda: [0, 0, ""])
 cur = None; fname = ""; cols = None
 for row in csv.reader(io.StringIO(src)):
     if not row: continue
-    if row[0] == "File Name": fname = row[1].split("/")[-1]; continue
+    if row[0] in ("File Name", "File Path"): fname = row[1].split("/")[-1]; continue
     if row[0] == "Line No": cols = row; continue
     if cols is None or len(row) < len(cols): continue
     if row[0]:

@@ -51,7 +51,7 @@ def main():
     for row in csv.reader(io.StringIO(src)):
         if not row:
             continue
-        if row[0] == "File Name":
+        if row[0] in ("File Name", "File Path"):
             fname = row[1].split("/")[-1]
             continue
         if row[0] == "Line No":
