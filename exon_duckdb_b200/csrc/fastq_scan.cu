@@ -148,10 +148,13 @@ struct FqWarpAux {
     static constexpr int off_cpre = 0;                                   // int[256]: byte-sum prefix at each 16-byte chunk
     static constexpr int off_gm = off_cpre + (kQual ? 256 * 4 : 0);      // u64[64]: G/C mask of each 64-byte half row
     static constexpr int off_gex = off_gm + (kSeq ? 64 * 8 : 0);         // int[64]: G/C prefix at each half row
-    static constexpr int off_ev = off_gex + (kSeq ? 64 * 4 : 0);         // u16[EV_CAP]: newline positions
-    static constexpr int off_bar = off_ev + EV_CAP * 2;                  // 2 mbarriers
+    static constexpr int off_ev = off_gex + (kSeq ? 64 * 4 : 0);         // u16[EV_CAP + 2]: newline positions (+ a dump slot)
+    static constexpr int off_bar = off_ev + EV_CAP * 2 + 16;             // 2 mbarriers
     static constexpr int total = off_bar + 16;
-    static constexpr int cta_bytes = FQ_WARPS * (2 * WT_BYTES + total) + 1024;  // + slack to align the data to 1024
+    // the kernel has no static shared memory, so the dynamic region starts right after the 1 KiB the system
+    // reserves per CTA: 1024-byte aligned, which the 128B swizzle needs (the kernel traps if that ever changes)
+    static constexpr int off_wlut = FQ_WARPS * (2 * WT_BYTES + total);   // uint4[17], shared by the CTA
+    static constexpr int cta_bytes = off_wlut + 17 * 16;
 };
 
 // tile-local byte index -> byte offset in the 128B-swizzled tile buffer
@@ -200,14 +203,14 @@ __device__ __forceinline__ FusedPlan make_plan(const FastqScanArgs& a) {
 
 // =================================================================== K1
 template <int FLAGS>
-__global__ void __launch_bounds__(FQ_THREADS) fastq_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FastqScanArgs a,
+__global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FastqScanArgs a,
                                                                 const uint32_t c7f, const uint32_t c7b) {
     using AUX = FqWarpAux<FLAGS>;
     constexpr bool kSeq = AUX::kSeq, kQual = AUX::kQual;
     constexpr bool kFused = (FLAGS & EXB_F_FUSED) != 0;
 
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint4 s_wlut[17];  // s_wlut[k]: 0x01 in the first k bytes -- IDP.4A weights of a chunk's head
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint4* s_wlut = reinterpret_cast<uint4*>(smem_raw + AUX::off_wlut);  // s_wlut[k]: 0x01 in the first k bytes -- IDP.4A weights
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 17) {
@@ -219,10 +222,9 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_tile_kernel(const __grid_con
         s_wlut[k] = make_uint4(w(0), w(4), w(8), w(12));
     }
 
-    const uint32_t raw_u32 = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t pad = ((raw_u32 + 1023u) & ~1023u) - raw_u32;
-    uint8_t* data0 = smem_raw + pad + warp * (2 * WT_BYTES);
-    uint8_t* aux = smem_raw + pad + FQ_WARPS * (2 * WT_BYTES) + warp * AUX::total;
+    if (((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u) != 0) __trap();
+    uint8_t* data0 = smem_raw + warp * (2 * WT_BYTES);
+    uint8_t* aux = smem_raw + FQ_WARPS * (2 * WT_BYTES) + warp * AUX::total;
     int* s_cpre = reinterpret_cast<int*>(aux + AUX::off_cpre);
     uint64_t* s_gm = reinterpret_cast<uint64_t*>(aux + AUX::off_gm);
     int* s_gex = reinterpret_cast<int*>(aux + AUX::off_gex);
@@ -243,6 +245,10 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_tile_kernel(const __grid_con
     const uint32_t pat_nl = c7f & 0x0A0A0A0Au, pat_gc = c7f & 0x43434343u;  // derived from an argument: stay in registers
     const int64_t stride = (int64_t)gridDim.x * FQ_WARPS;
     const FusedPlan plan = kFused ? make_plan(a) : FusedPlan{0, 0.0, 0, 0};
+    // fused: a line handled by lane l has tile-local index = l (mod 4): it is a header under hypothesis (0 - l) & 3
+    // and a plus line under (2 - l) & 3
+    const uint32_t bit_hdr = 1u << ((0 - lane) & 3), bit_plus = 1u << ((2 - lane) & 3);
+    const int64_t lower = a.prev ? 0 : a.begin;  // first readable byte of the buffer
 
     // ---- staging of one tile into buffer b (asynchronous; one instruction from one lane)
     auto issue = [&](int64_t tile, int b) {
@@ -366,14 +372,17 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_tile_kernel(const __grid_con
 #pragma unroll
             for (int wd = 0; wd < 4; wd++) {
                 const uint32_t m = (uint32_t)(pm[wd >> 1] >> ((wd & 1) * 32));
-                const int base = lane * ROW_BYTES + wd * 32;
+                const int base = lane * ROW_BYTES + wd * 32 - 1;
                 const uint32_t m1 = m & (m - 1);
-                if (m != 0 && (unsigned)rank < (unsigned)EV_CAP) ev_pos[rank] = (uint16_t)(base + __ffs((int)m) - 1);
-                if (m1 != 0 && (unsigned)(rank + 1) < (unsigned)EV_CAP) ev_pos[rank + 1] = (uint16_t)(base + __ffs((int)m1) - 1);
+                // stores that have nothing to say go to the dump slot ev_pos[EV_CAP]: no branches
+                const int i0 = (m != 0 && (unsigned)rank < (unsigned)EV_CAP) ? rank : EV_CAP;
+                const int i1 = (m1 != 0 && (unsigned)(rank + 1) < (unsigned)EV_CAP) ? rank + 1 : EV_CAP;
+                ev_pos[i0] = (uint16_t)(base + __ffs((int)m));
+                ev_pos[i1] = (uint16_t)(base + __ffs((int)m1));
                 more = more || (m1 & (m1 - 1)) != 0;
                 rank += __popc(m);
             }
-            if (__any_sync(0xffffffffu, more)) {
+            if (__any_sync(0xffffffffu, more)) {  // a lane with 3+ newlines in one 32-byte word: the generic loop redoes it
                 rank = ex_cnt - win_lo;
 #pragma unroll
                 for (int wd = 0; wd < 4; wd++) {
@@ -443,13 +452,12 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_tile_kernel(const __grid_con
                 }
                 if (kSeq) pg = s_gex[pos >> 6] + __popcll(s_gm[pos >> 6] & low_bits64(pos & 63));
                 // a CR directly before a real LF is stripped (when the line is not empty: the consumer checks);
-                // the virtual '\n' at EOF strips nothing
-                int before = -1;
-                if (pos > 0) before = sbytes[(pos & 15) ? so - 1 : sidx(pos - 1)];
-                else if (tile_base - 1 >= (a.prev ? 0 : a.begin)) before = buf[tile_base - 1];
+                // the virtual '\n' at EOF strips nothing.  Both neighbours are fetched unconditionally (clamped).
+                int before = sbytes[sidx(pos > 0 ? pos - 1 : 0)];
+                const int after = sbytes[sidx(pos + 1 < WT_BYTES ? pos + 1 : pos)];
+                if (pos == 0) before = tile_base - 1 >= lower ? (int)buf[tile_base - 1] : -1;  // rare: first byte of the tile
                 const uint32_t cr = (before == '\r' && !(a.is_final && tile_base + pos == a.n)) ? 1u : 0u;
-                uint32_t nf = 0;
-                if (pos + 1 < WT_BYTES) nf = at_plus_flags(sbytes[((pos & 15) != 15) ? so + 1 : sidx(pos + 1)]);
+                const uint32_t nf = pos + 1 < WT_BYTES ? at_plus_flags(after) : 0u;
                 y = rec_pack(pos, cr, nf, kSeq ? pg : 0);
                 if (!kFused && rec_ok) a.records[rec_off + lo + lane] = make_uint2((uint32_t)ps, y);
             }
@@ -469,10 +477,9 @@ __global__ void __launch_bounds__(FQ_THREADS) fastq_tile_kernel(const __grid_con
                         f_cq += 1u + (len << 12);
                         f_qs += qs;
                     }
-                    // the line is a header under hypothesis (0 - li) & 3 and a plus line under (2 - li) & 3, li = lane (mod 4)
                     const uint32_t nfl = rec_next_flags(py);  // flags of this line's first byte
-                    if (!(nfl & 2u)) f_bad |= 1u << ((0 - lane) & 3);
-                    if (!(nfl & 1u)) f_bad |= 1u << ((2 - lane) & 3);
+                    f_bad |= (nfl & 2u) ? 0u : bit_hdr;
+                    f_bad |= (nfl & 1u) ? 0u : bit_plus;
                 }
                 c_ps = __shfl_sync(0xffffffffu, ps, 31);
                 c_y = __shfl_sync(0xffffffffu, y, 31);

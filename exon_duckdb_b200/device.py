@@ -158,6 +158,8 @@ class FastqCount:
     def __init__(self):
         self.agg = None
         self.ws = None
+        self.buf = None
+        self.n = 0
         self._res = None
 
     @property
@@ -169,6 +171,8 @@ class FastqCount:
     def validate(self):
         r = self.result
         if r.err_pos != NO_POS:
+            # the fused flavour knows that a line start contradicts its phase, not where: the plain scan locates it
+            fastq_scan_sync(self.buf, 0, n=self.n).validate()
             raise FormatError("malformed FASTQ record at byte %d" % r.err_pos, r.err_pos)
         if r.total_lines % 4 != 0:
             raise FormatError("truncated FASTQ record: %d lines" % r.total_lines)
@@ -186,6 +190,7 @@ def fastq_scan_filter(buf, preds, n=None, out=None):
         c.agg = torch.zeros(8, dtype=torch.int64, device=dev)
         c.ws = workspace(n + 16, dev)
     c._res = None
+    c.buf, c.n = buf, n
     arr, k = _lib.predicates(preds)
     check(lib().exb_fastq_scan_filter(_ptr(buf), 0, n, 1, None, arr, k, _ptr(c.agg), 0, _ptr(c.ws), c.ws.numel(), _stream()))
     return c
