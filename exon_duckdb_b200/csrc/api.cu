@@ -115,9 +115,9 @@ int64_t exb_scan_workspace_bytes(int64_t n) {
 
 // FASTQ workspace: [0,256) header (ScanResult | +128 record bump counter)
 //                  [256, 256+S) sub-workspace of the offset scan (its own 256-byte header + slots)
-//                  tails u64[T] | tile_rec i64[T] | line_base i64[T+1] | tile_cnt u32[T] | records (8 B each) or fused tiles
+//                  tails u64[T] | tile_rec i64[T] | tile_rec2 i64[T] | line_base i64[T+1] | tile_cnt u32[T] | records (8 B each) or fused tiles
 struct FastqLayout {
-    int64_t n_tiles, scan_ws, off_tails, off_rec, off_base, off_cnt, off_payload, fixed;
+    int64_t n_tiles, scan_ws, off_tails, off_rec, off_rec2, off_base, off_cnt, off_payload, fixed;
 };
 static FastqLayout fastq_layout(int64_t n_tiles) {
     FastqLayout L;
@@ -125,7 +125,8 @@ static FastqLayout fastq_layout(int64_t n_tiles) {
     L.scan_ws = WS_HEADER + scan_tiles(n_tiles) * (int64_t)sizeof(TileSlot);
     L.off_tails = WS_HEADER + L.scan_ws;
     L.off_rec = L.off_tails + n_tiles * 8;
-    L.off_base = L.off_rec + n_tiles * 8;
+    L.off_rec2 = L.off_rec + n_tiles * 8;
+    L.off_base = L.off_rec2 + n_tiles * 8;
     L.off_cnt = L.off_base + (n_tiles + 1) * 8;
     L.off_payload = (L.off_cnt + n_tiles * 4 + 15) & ~(int64_t)15;
     L.fixed = L.off_payload;
@@ -176,6 +177,7 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
     a.rec_bump = reinterpret_cast<unsigned long long*>(ws + 128);
     a.tails = reinterpret_cast<uint64_t*>(ws + L.off_tails);
     a.tile_rec = reinterpret_cast<int64_t*>(ws + L.off_rec);
+    a.tile_rec2 = reinterpret_cast<int64_t*>(ws + L.off_rec2);
     int64_t* line_base = reinterpret_cast<int64_t*>(ws + L.off_base);
     a.line_base = line_base;
     a.tile_cnt = reinterpret_cast<uint32_t*>(ws + L.off_cnt);

@@ -53,6 +53,7 @@ struct FastqScanArgs {
     // K1 -> K2 (all inside the caller's workspace; nothing needs zeroing except *rec_bump)
     uint32_t* tile_cnt;         // [n_tiles] newlines per tile
     int64_t* tile_rec;          // [n_tiles] index of the tile's first record
+    int64_t* tile_rec2;         // [n_tiles] index of the second run of records | records in the first run << 48
     uint64_t* tails;            // [n_tiles] tail words
     const int64_t* line_base;   // [n_tiles + 1] exclusive scan of tile_cnt (written between K1 and K2)
     uint2* records;             // [rec_space] 8 bytes per newline, bump-allocated per warp

@@ -54,7 +54,7 @@ constexpr int ROW_BYTES = 128;
 constexpr int FQ_WARPS = 4;     // warps per CTA (independent of each other)
 constexpr int FQ_THREADS = FQ_WARPS * 32;
 constexpr int EV_CAP = 64;      // newline positions held at once (2 passes of 32)
-constexpr int REC_BLOCK = 256;  // records a warp reserves per bump allocation
+constexpr int REC_BLOCK = 512;  // records a warp reserves per bump allocation
 
 // ---------------------------------------------------------------- tail word
 // [63:62] 1 = no newline in the tile, 2 = has one
@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
 
     // bump allocation of record space, REC_BLOCK at a time per warp
     int64_t rec_next = 0;
-    int rec_left = 0;
+    int rec_left = 0;  // a warp that has not allocated yet owns nothing: a record is never written through off0 then
+    bool blk_ok = true;  // the current block lies inside the record space
 
     int64_t cur = (int64_t)blockIdx.x * FQ_WARPS + warp;
     issue(cur, 0);
@@ -399,23 +400,31 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         scatter(0);
         __syncwarp();
 
-        // record space for this tile's newlines
-        int64_t rec_off = 0;
-        bool rec_ok = true;
+        // record space for this tile's newlines: the warp's current block first, the rest in a fresh block
+        // (a tile's records are at most two runs, so no slot of a block is ever abandoned)
+        int64_t rec_off0 = 0, rec_off1 = 0;
+        int rec_n0 = 0;
+        const bool rec_ok0 = blk_ok;  // the first run lives in the block allocated earlier
         if (!kFused) {
-            if (n_events > rec_left) {
-                const int need = n_events > REC_BLOCK ? n_events : REC_BLOCK;
+            rec_off0 = rec_next;
+            rec_n0 = n_events < rec_left ? n_events : rec_left;
+            rec_next += rec_n0;
+            rec_left -= rec_n0;
+            const int rest = n_events - rec_n0;
+            if (rest > 0) {
+                const int need = rest > REC_BLOCK ? rest : REC_BLOCK;
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(a.rec_bump, (unsigned long long)need);
-                rec_next = (int64_t)__shfl_sync(0xffffffffu, base, 0);
-                rec_left = need;
+                rec_off1 = (int64_t)__shfl_sync(0xffffffffu, base, 0);
+                rec_next = rec_off1 + rest;
+                rec_left = need - rest;
+                blk_ok = rec_off1 + need <= a.rec_space;
+                if (!blk_ok && lane == 0) a.result->overflow = 1;
             }
-            rec_off = rec_next;
-            rec_next += n_events;
-            rec_left -= n_events;
-            rec_ok = rec_off + n_events <= a.rec_space;
-            if (!rec_ok && lane == 0) a.result->overflow = 1;
-            if (lane == 0) a.tile_rec[tile] = rec_off;
+            if (lane == 0) {
+                a.tile_rec[tile] = rec_off0;
+                a.tile_rec2[tile] = rec_off1 | ((int64_t)rec_n0 << 48);
+            }
         }
 
         // ---- B. one newline per lane: its record (and, fused, the verdict of the line it ends)
@@ -459,7 +468,10 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                 const uint32_t cr = (before == '\r' && !(a.is_final && tile_base + pos == a.n)) ? 1u : 0u;
                 const uint32_t nf = pos + 1 < WT_BYTES ? at_plus_flags(after) : 0u;
                 y = rec_pack(pos, cr, nf, kSeq ? pg : 0);
-                if (!kFused && rec_ok) a.records[rec_off + lo + lane] = make_uint2((uint32_t)ps, y);
+                if (!kFused) {
+                    const int i = lo + lane;
+                    if (i < rec_n0 ? rec_ok0 : blk_ok) a.records[i < rec_n0 ? rec_off0 + i : rec_off1 + (i - rec_n0)] = make_uint2((uint32_t)ps, y);
+                }
             }
             if (kFused) {
                 int pps = __shfl_up_sync(0xffffffffu, ps, 1);
@@ -611,13 +623,18 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const FastqScanArgs a) 
         if (is_last && lane == 0) write_final_state(a, excl + (uint64_t)n_events, n_events, tile_base, a.tails[tile], open);
         if (overflowed) continue;
 
-        const uint2* __restrict__ recs = a.records + a.tile_rec[tile];
+        const int64_t off0 = a.tile_rec[tile], w1 = a.tile_rec2[tile];
+        const int64_t off1 = w1 & 0xFFFFFFFFFFFFll;
+        const int n0 = (int)(w1 >> 48);
         int c_ps = 0;
         uint32_t c_y = 0;
         for (int lo = 0; lo < n_events; lo += 32) {
             const bool active = lo + lane < n_events;
             uint2 r = make_uint2(0u, 0u);
-            if (active) r = recs[lo + lane];
+            if (active) {
+                const int i = lo + lane;
+                r = a.records[i < n0 ? off0 + i : off1 + (i - n0)];
+            }
             int pps = __shfl_up_sync(0xffffffffu, (int)r.x, 1);
             uint32_t py = __shfl_up_sync(0xffffffffu, r.y, 1);
             if (lane == 0) {
