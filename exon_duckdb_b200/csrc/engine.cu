@@ -219,3 +219,133 @@ void exb_host_free(void* p) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ scalar functions over host columns
+// One context per calling thread (DuckDB calls scalar functions concurrently from its worker threads):
+// a stream, growable device buffers and pinned staging, kept for the life of the thread.
+namespace {
+struct HostCtx {
+    cudaStream_t st = nullptr;
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+    void* d_off = nullptr;
+    void* d_flag = nullptr;
+    void* h_stage = nullptr;
+    int64_t in_cap = 0, out_cap = 0, off_cap = 0, stage_cap = 0;
+    bool ok = false;
+    ~HostCtx() {
+        if (d_in) cudaFree(d_in);
+        if (d_out) cudaFree(d_out);
+        if (d_off) cudaFree(d_off);
+        if (d_flag) cudaFree(d_flag);
+        if (h_stage) cudaFreeHost(h_stage);
+        if (st) cudaStreamDestroy(st);
+    }
+    int init() {
+        if (ok) return 0;
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+            cudaGetLastError();
+            return set_err(EXB_ERR_CUDA, "no CUDA device: the exon_b200 scalar functions have no CPU fallback");
+        }
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        if ((e = cudaMalloc(&d_flag, 16)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        ok = true;
+        return 0;
+    }
+    int grow(void** p, int64_t* cap, int64_t need, const char* what) {
+        if (*p && *cap >= need) return 0;
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        const int64_t want = need + need / 2 + 4096;
+        cudaError_t e = cudaMalloc(p, (size_t)want);
+        if (e != cudaSuccess) {
+            *cap = 0;
+            return cuda_fail(e, what);
+        }
+        *cap = want;
+        return 0;
+    }
+    int grow_stage(int64_t need) {
+        if (h_stage && stage_cap >= need) return 0;
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr;
+        const int64_t want = need + need / 2 + 4096;
+        cudaError_t e = cudaHostAlloc(&h_stage, (size_t)want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            stage_cap = 0;
+            return cuda_fail(e, "cudaHostAlloc(staging)");
+        }
+        stage_cap = want;
+        return 0;
+    }
+};
+thread_local HostCtx g_host;
+}  // namespace
+
+extern "C" {
+
+int exb_gc_content_host(const int64_t* offsets, const uint8_t* data, int64_t n_rows, float* out) {
+    if (n_rows < 0 || (n_rows > 0 && (!offsets || !out))) return set_err(EXB_ERR_ARG, "exb_gc_content_host: bad arguments");
+    if (n_rows == 0) return 0;
+    HostCtx& c = g_host;
+    int rc = c.init();
+    if (rc) return rc;
+    const int64_t base = offsets[0], nb = offsets[n_rows] - base;
+    if ((rc = c.grow(&c.d_in, &c.in_cap, nb + 64, "cudaMalloc(in)")) || (rc = c.grow(&c.d_off, &c.off_cap, (n_rows + 1) * 8, "cudaMalloc(off)")) ||
+        (rc = c.grow(&c.d_out, &c.out_cap, n_rows * 4, "cudaMalloc(out)")))
+        return rc;
+    cudaError_t e = cudaMemcpyAsync(c.d_off, offsets, (size_t)(n_rows + 1) * 8, cudaMemcpyHostToDevice, c.st);
+    if (e == cudaSuccess && nb > 0) e = cudaMemcpyAsync(c.d_in, data + base, (size_t)nb, cudaMemcpyHostToDevice, c.st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+    // the offsets keep their base: the kernel addresses d_data[off], so hand it a pointer shifted by -base
+    rc = exb_gc_content((const int64_t*)c.d_off, (const uint8_t*)c.d_in - base, n_rows, (float*)c.d_out, c.st);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(out, c.d_out, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, c.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);
+    if (e != cudaSuccess) return cuda_fail(e, "gc_content D2H");
+    return 0;
+}
+
+int exb_seq_map_host(const uint8_t* data, int64_t n_bytes, int mode, uint8_t* out, int64_t* bad_pos) {
+    if (n_bytes < 0 || (n_bytes > 0 && (!data || !out)) || !bad_pos) return set_err(EXB_ERR_ARG, "exb_seq_map_host: bad arguments");
+    *bad_pos = -1;
+    if (n_bytes == 0) return 0;
+    HostCtx& c = g_host;
+    int rc = c.init();
+    if (rc) return rc;
+    if ((rc = c.grow(&c.d_in, &c.in_cap, n_bytes + 64, "cudaMalloc(in)")) || (rc = c.grow(&c.d_out, &c.out_cap, n_bytes + 64, "cudaMalloc(out)")))
+        return rc;
+    cudaError_t e = cudaMemcpyAsync(c.d_in, data, (size_t)n_bytes, cudaMemcpyHostToDevice, c.st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+    rc = exb_seq_map((const uint8_t*)c.d_in, n_bytes, mode, (uint8_t*)c.d_out, (uint64_t*)c.d_flag, c.st);
+    if (rc) return rc;
+    uint64_t bad = 0;
+    e = cudaMemcpyAsync(out, c.d_out, (size_t)n_bytes, cudaMemcpyDeviceToHost, c.st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, c.d_flag, 8, cudaMemcpyDeviceToHost, c.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);
+    if (e != cudaSuccess) return cuda_fail(e, "seq_map D2H");
+    *bad_pos = bad == ~0ull ? -1 : (int64_t)bad;
+    return 0;
+}
+
+int exb_quality_decode_host(const uint8_t* data, int64_t n_bytes, int32_t* out) {
+    if (n_bytes < 0 || (n_bytes > 0 && (!data || !out))) return set_err(EXB_ERR_ARG, "exb_quality_decode_host: bad arguments");
+    if (n_bytes == 0) return 0;
+    HostCtx& c = g_host;
+    int rc = c.init();
+    if (rc) return rc;
+    if ((rc = c.grow(&c.d_in, &c.in_cap, n_bytes + 64, "cudaMalloc(in)")) || (rc = c.grow(&c.d_out, &c.out_cap, n_bytes * 4 + 64, "cudaMalloc(out)")))
+        return rc;
+    cudaError_t e = cudaMemcpyAsync(c.d_in, data, (size_t)n_bytes, cudaMemcpyHostToDevice, c.st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+    rc = exb_quality_decode((const uint8_t*)c.d_in, n_bytes, (int32_t*)c.d_out, c.st);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(out, c.d_out, (size_t)n_bytes * 4, cudaMemcpyDeviceToHost, c.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);
+    if (e != cudaSuccess) return cuda_fail(e, "quality_decode D2H");
+    return 0;
+}
+
+}  // extern "C"

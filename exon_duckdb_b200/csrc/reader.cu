@@ -270,6 +270,12 @@ struct ChunkColumn {  // one column of the rows a chunk produced (host copies)
     std::vector<int64_t> off;
     std::vector<uint8_t> data;
 };
+// The rows one input chunk produced.  Shared: every batch view handed out (exb_batch) holds a reference, so a
+// host that borrows the strings (DuckDB string_t pointers) keeps the buffers alive past the reader's next step.
+struct ChunkResult {
+    std::vector<ChunkColumn> cols;
+    std::vector<uint8_t> valid;  // description validity, one byte per row
+};
 
 // ------------------------------------------------------------------ the stream
 struct Reader {
@@ -298,9 +304,11 @@ struct Reader {
         d_valid2, d_off, d_data, d_cst, d_hdr_start, d_hdr_end, d_seq_off, d_gc_prefix, d_seq, d_err;
     HBuf h_off, h_data, h_valid;
     // rows ready to be handed out
-    std::vector<ChunkColumn> cols;
-    std::vector<uint8_t> valid;
+    std::shared_ptr<ChunkResult> cur;
     int64_t rows = 0, next_row = 0;
+    uint32_t column_mask = 0xF;  // bit c: column c is materialised (projection push-down)
+    bool count_only = false;     // COUNT(*): rows are counted, nothing is gathered or copied back
+    int64_t counted = 0;
     std::string error;
 
     ~Reader() {
@@ -437,6 +445,14 @@ struct Reader {
 
     // gather the selected rows of all columns and bring them to the host
     bool materialise(const uint8_t* const* col_buf, const int64_t* d_st, const uint32_t* d_ln, const uint8_t* d_val, int64_t n) {
+        if (count_only) {
+            counted += n;
+            rows = next_row = 0;
+            return true;
+        }
+        cur = std::make_shared<ChunkResult>();
+        std::vector<ChunkColumn>& cols = cur->cols;
+        std::vector<uint8_t>& valid = cur->valid;
         cols.assign(ncols, ChunkColumn());
         valid.assign((size_t)n, 1);
         rows = n;
@@ -445,6 +461,7 @@ struct Reader {
         const int64_t ws_bytes = exb_scan_workspace_bytes(4 * n + 16);
         if (!d_ws2.need(ws_bytes) || !d_off.need((n + 1) * 8) || !h_off.need((n + 1) * 8) || !h_valid.need(n)) return fail("out of memory");
         for (int c = 0; c < ncols; c++) {
+            if (!((column_mask >> c) & 1u)) continue;  // projected out: the column stays empty
             if (!rc(exb_exclusive_scan_u32(d_ln + (int64_t)c * n, n, d_off.as<int64_t>(), d_ws2.p, d_ws2.cap, st))) return false;
             if (!cu(cudaMemcpyAsync(h_off.p, d_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets")) return false;
             if (!cu(cudaStreamSynchronize(st), "sync")) return false;
@@ -546,13 +563,19 @@ struct Reader {
             return materialise(bufs, o_st, o_ln, o_val, o_n);
         }
         // ---- FASTA
+        // the sequence column is compacted by the scan itself; skip that when nobody reads the bytes
+        // (projection push-down, COUNT(*); string predicates on `sequence` still need them)
+        bool want_seq = ((column_mask >> 2) & 1u) != 0 && !count_only;
+        for (const Node& nd : nodes)
+            if (nd.kind == N_STR && nd.col == 2) want_seq = true;
         int64_t rec_cap = n / 64 + 4096;
         for (int attempt = 0;; attempt++) {
             if (!d_hdr_start.need(rec_cap * 8) || !d_hdr_end.need(rec_cap * 8) || !d_seq_off.need((rec_cap + 1) * 8) ||
-                !d_gc_prefix.need((rec_cap + 1) * 8) || !d_seq.need(n + 64))
+                !d_gc_prefix.need((rec_cap + 1) * 8) || (want_seq && !d_seq.need(n + 64)))
                 return fail("out of device memory");
             if (!rc(exb_fasta_scan(d_in.p, 0, n, is_final ? 1 : 0, n, nullptr, d_hdr_start.as<int64_t>(), d_hdr_end.as<int64_t>(),
-                                   d_seq_off.as<int64_t>(), d_gc_prefix.as<int64_t>(), rec_cap, d_seq.as<uint8_t>(), n + 64, d_ws.p, d_ws.cap, st)))
+                                   d_seq_off.as<int64_t>(), d_gc_prefix.as<int64_t>(), rec_cap, want_seq ? d_seq.as<uint8_t>() : nullptr,
+                                   want_seq ? n + 64 : 0, d_ws.p, d_ws.cap, st)))
                 return false;
             if (!rc(exb_scan_result_fetch(d_ws.p, &res, st))) return false;
             if (!res.overflow) break;
@@ -592,6 +615,7 @@ struct Reader {
 
     // make rows available; false = end of stream or error (check `error`)
     bool advance() {
+        if (!ensure_device()) return false;  // before any pinned allocation: "no CUDA device" is the message a CPU-only host must see
         while (next_row >= rows) {
             rows = next_row = 0;
             if (file_eof && in_len == 0) {
@@ -681,7 +705,7 @@ int stream_get_next(ArrowArrayStream* s, ArrowArray* out) {
     // rows [next_row, next_row + k): at most batch_size rows and < 2 GiB per column (utf8 has int32 offsets)
     int64_t b = r->next_row, e = std::min(r->rows, b + r->batch_size);
     for (int c = 0; c < r->ncols; c++) {
-        const std::vector<int64_t>& off = r->cols[c].off;
+        const std::vector<int64_t>& off = r->cur->cols[c].off;
         while (e > b + 1 && off[e] - off[b] > 0x7FFFFFF0ll) e = b + (e - b) / 2;
         if (off[e] - off[b] > 0x7FFFFFF0ll) {
             r->error = "a single " + r->col_names[c] + " value exceeds the 2 GiB limit of Arrow utf8";
@@ -694,11 +718,11 @@ int stream_get_next(ArrowArrayStream* s, ArrowArray* out) {
     int64_t nulls = 0;
     h->validity.assign((size_t)((k + 7) / 8), 0);
     for (int64_t i = 0; i < k; i++) {
-        if (r->valid[b + i]) h->validity[i >> 3] |= (uint8_t)(1u << (i & 7));
+        if (r->cur->valid[b + i]) h->validity[i >> 3] |= (uint8_t)(1u << (i & 7));
         else nulls++;
     }
     for (int c = 0; c < r->ncols; c++) {
-        const ChunkColumn& col = r->cols[c];
+        const ChunkColumn& col = r->cur->cols[c];
         h->off[c].resize((size_t)k + 1);
         const int64_t base = col.off[b];
         for (int64_t i = 0; i <= k; i++) h->off[c][i] = (int32_t)(col.off[b + i] - base);
@@ -770,9 +794,13 @@ ReplacementScanResult replacement_scan(const char* uri) {
     return r;
 }
 
-ReaderResult new_reader(ArrowArrayStream* stream_ptr, const char* uri, uintptr_t batch_size, const char* compression,
-                        const char* file_format, const char* filters) {
-    if (!stream_ptr || !uri || !file_format) return reader_error("new_reader: null argument");
+// Shared by new_reader and exb_reader_open: resolves compression / format, lists the files, parses the filter.
+static Reader* open_reader(const char* uri, uintptr_t batch_size, const char* compression, const char* file_format, const char* filters,
+                           std::string* err) {
+    if (!uri || !file_format) {
+        *err = "new_reader: null argument";
+        return nullptr;
+    }
     std::string u(uri);
     // arrow_reader.rs:60-91: NULL compression = infer from the text after the last '.'
     int comp;
@@ -784,7 +812,10 @@ ReaderResult new_reader(ArrowArrayStream* stream_ptr, const char* uri, uintptr_t
         comp = compression_from_str(compression);
     }
     const int ft = file_type_from_str(file_format);
-    if (ft == 0) return reader_error(std::string("could not parse file_format ") + file_format);
+    if (ft == 0) {
+        *err = std::string("could not parse file_format ") + file_format;
+        return nullptr;
+    }
 
     std::unique_ptr<Reader> r(new Reader());
     r->format = ft;
@@ -794,13 +825,19 @@ ReaderResult new_reader(ArrowArrayStream* stream_ptr, const char* uri, uintptr_t
     r->ncols = (int)r->col_names.size();
 
     struct stat sb;
-    if (u.empty() || stat(u.c_str(), &sb) != 0) return reader_error("could not register table: no such file or directory: " + u);
+    if (u.empty() || stat(u.c_str(), &sb) != 0) {
+        *err = "could not register table: no such file or directory: " + u;
+        return nullptr;
+    }
     if (S_ISDIR(sb.st_mode)) {
         // listing table: every file whose name carries the format's extension (+ the codec's)
         std::vector<std::string> exts = ft == 1 ? std::vector<std::string>{".fasta", ".fa", ".fna"} : std::vector<std::string>{".fastq", ".fq"};
         const char* csuf = comp == 1 ? ".gz" : (comp == 2 ? ".zst" : "");
         DIR* d = opendir(u.c_str());
-        if (!d) return reader_error("could not list " + u);
+        if (!d) {
+            *err = "could not list " + u;
+            return nullptr;
+        }
         std::vector<std::string> names;
         while (dirent* de = readdir(d)) {
             std::string nm = de->d_name;
@@ -821,27 +858,121 @@ ReaderResult new_reader(ArrowArrayStream* stream_ptr, const char* uri, uintptr_t
         r->file_comp.push_back(comp);
     }
     for (int c : r->file_comp)
-        if (c >= 2) return reader_error("could not register table: zstd / bzip2 / xz input is not supported by this build");
+        if (c >= 2) {
+            *err = "could not register table: zstd / bzip2 / xz input is not supported by this build";
+            return nullptr;
+        }
 
     if (filters && filters[0]) {
         std::string f(filters);
         Parser p(f, r->nodes, r->col_names);
         r->root = p.parse_or();
         p.ws();
-        if (r->root < 0 || p.i != f.size())
-            return reader_error("could not execute sql: cannot parse filter `" + f + "`: " + (p.err.empty() ? "trailing text" : p.err));
+        if (r->root < 0 || p.i != f.size()) {
+            *err = "could not execute sql: cannot parse filter `" + f + "`: " + (p.err.empty() ? "trailing text" : p.err);
+            return nullptr;
+        }
     }
     const char* cb = getenv("EXON_B200_CHUNK_BYTES");
     if (cb && atoll(cb) > 0) r->chunk_bytes = atoll(cb);
+    return r.release();
+}
 
+ReaderResult new_reader(ArrowArrayStream* stream_ptr, const char* uri, uintptr_t batch_size, const char* compression,
+                        const char* file_format, const char* filters) {
+    if (!stream_ptr) return reader_error("new_reader: null argument");
+    std::string err;
+    Reader* r = open_reader(uri, batch_size, compression, file_format, filters, &err);
+    if (!r) return reader_error(err);
     stream_ptr->get_schema = stream_get_schema;
     stream_ptr->get_next = stream_get_next;
     stream_ptr->get_last_error = stream_last_error;
     stream_ptr->release = stream_release;
-    stream_ptr->private_data = r.release();
+    stream_ptr->private_data = r;
     ReaderResult ok;
     ok.error = nullptr;
     return ok;
+}
+
+// ---- the same reader without the Arrow detour (include/exon_b200.h, "native reader")
+struct exb_reader {
+    Reader* r;
+    std::string err;
+};
+
+int exb_reader_open(const char* uri, const char* file_format, const char* compression, int64_t batch_rows, const char* filters,
+                    uint32_t column_mask, exb_reader** out) {
+    if (!out) return set_err(EXB_ERR_ARG, "exb_reader_open: null out");
+    *out = nullptr;
+    std::string err;
+    Reader* r = open_reader(uri, (uintptr_t)(batch_rows > 0 ? batch_rows : 2048), compression, file_format, filters, &err);
+    if (!r) return set_err(err.find("no such file") != std::string::npos || err.find("could not list") != std::string::npos ? EXB_ERR_IO : EXB_ERR_ARG,
+                           "%s", err.c_str());
+    r->column_mask = column_mask;
+    exb_reader* h = new exb_reader();
+    h->r = r;
+    *out = h;
+    return 0;
+}
+
+int exb_reader_columns(const exb_reader* h, const char** names, int cap) {
+    if (!h) return 0;
+    for (int c = 0; c < h->r->ncols && c < cap; c++) names[c] = h->r->col_names[c].c_str();
+    return h->r->ncols;
+}
+
+int exb_reader_next(exb_reader* h, exb_batch* out) {
+    if (!h || !out) return set_err(EXB_ERR_ARG, "exb_reader_next: null argument");
+    Reader* r = h->r;
+    memset(out, 0, sizeof(*out));
+    if (!r->advance()) {
+        if (!r->error.empty()) {
+            h->err = r->error;
+            const bool fmt = r->error.find("invalid FAST") != std::string::npos || r->error.find("unexpected EOF") != std::string::npos ||
+                             r->error.find("without a name") != std::string::npos;
+            return set_err(fmt ? EXB_ERR_FORMAT : (r->error.find("CUDA") != std::string::npos ? EXB_ERR_CUDA : EXB_ERR_IO), "%s", r->error.c_str());
+        }
+        return 0;  // end of stream: n_rows = 0
+    }
+    const int64_t b = r->next_row, e = std::min(r->rows, b + r->batch_size);
+    out->n_rows = e - b;
+    out->n_cols = r->ncols;
+    for (int c = 0; c < r->ncols; c++) {
+        const ChunkColumn& col = r->cur->cols[c];
+        if (col.off.empty()) continue;  // projected out
+        out->cols[c].offsets = col.off.data() + b;
+        out->cols[c].data = col.data.data();
+        if (r->col_names[c] == "description") out->cols[c].valid = r->cur->valid.data() + b;
+    }
+    out->owner = new std::shared_ptr<ChunkResult>(r->cur);
+    r->next_row = e;
+    return 0;
+}
+
+void exb_batch_release(exb_batch* b) {
+    if (!b || !b->owner) return;
+    delete reinterpret_cast<std::shared_ptr<ChunkResult>*>(b->owner);
+    b->owner = nullptr;
+}
+
+int exb_reader_count(exb_reader* h, int64_t* n_rows) {
+    if (!h || !n_rows) return set_err(EXB_ERR_ARG, "exb_reader_count: null argument");
+    Reader* r = h->r;
+    r->count_only = true;
+    while (r->advance()) {
+    }
+    if (!r->error.empty()) {
+        h->err = r->error;
+        return set_err(r->error.find("CUDA") != std::string::npos ? EXB_ERR_CUDA : EXB_ERR_FORMAT, "%s", r->error.c_str());
+    }
+    *n_rows = r->counted;
+    return 0;
+}
+
+void exb_reader_close(exb_reader* h) {
+    if (!h) return;
+    delete h->r;
+    delete h;
 }
 
 }  // extern "C"

@@ -127,6 +127,39 @@ EXB_API ReaderResult new_reader(struct ArrowArrayStream *stream_ptr, const char 
 EXB_API ReplacementScanResult replacement_scan(const char *uri);
 EXB_API void exb_free_string(const char *s);
 
+/*
+ * Native reader: the same engine as new_reader without the Arrow detour, for hosts that fill their own vectors
+ * (exon_duckdb_b200/duckdb_ext/exon_extension.cpp: bind / init_global / scan callbacks).  Replaces the
+ * new_reader + ArrowScanParallelStateNext + ArrowToDuckDB chain of the reference
+ * (arrow_table_function/module.cpp:95-103,235-252,257-294; duckdb/src/function/table/arrow.cpp:248-268).
+ *   column_mask: bit c set = column c is wanted (projection push-down); others come back as NULL views.
+ *   A batch borrows the reader's host buffers: offsets[i] .. offsets[i+1] index `data` for row i
+ *   (offsets are NOT rebased to 0).  The buffers stay alive until exb_batch_release, even after
+ *   exb_reader_next / exb_reader_close -- a host may hand out pointers into them (DuckDB string_t).
+ */
+typedef struct exb_reader exb_reader;
+typedef struct exb_column_view {
+    const int64_t *offsets; /* n_rows + 1 entries, NULL if the column was projected out */
+    const uint8_t *data;
+    const uint8_t *valid;   /* one byte per row (0 = NULL), or NULL = all rows valid      */
+} exb_column_view;
+typedef struct exb_batch {
+    int64_t n_rows;         /* 0 = end of stream */
+    int32_t n_cols;
+    exb_column_view cols[4];
+    void *owner;
+} exb_batch;
+EXB_API int exb_reader_open(const char *uri, const char *file_format, const char *compression, int64_t batch_rows,
+                            const char *filters, uint32_t column_mask, exb_reader **out);
+/* column names in schema order; returns the number of columns */
+EXB_API int exb_reader_columns(const exb_reader *reader, const char **names, int cap);
+EXB_API int exb_reader_next(exb_reader *reader, exb_batch *out);
+EXB_API void exb_batch_release(exb_batch *batch);
+/* COUNT(*): consumes the rest of the stream; rows that pass the filters are counted on the device and nothing
+ * is gathered or copied back (arrow_conversion.cpp:813-816 is the reference's row-id-only case). */
+EXB_API int exb_reader_count(exb_reader *reader, int64_t *n_rows);
+EXB_API void exb_reader_close(exb_reader *reader);
+
 /* ---------------------------------------------------------------------------
  * (2) Device layer
  * ------------------------------------------------------------------------- */
@@ -301,6 +334,14 @@ EXB_API int exb_seq_map(const uint8_t *d_in, int64_t n_bytes, int mode, uint8_t 
 /* fastq_functions/module.cpp:32-50: out[i] = (signed char)in[i] - 33 (list child vector;
  * the list offsets are the string offsets). */
 EXB_API int exb_quality_decode(const uint8_t *d_in, int64_t n_bytes, int32_t *d_out, void *stream);
+
+/* ---- the same scalar functions over HOST columns: what a DuckDB scalar-function callback holds for one
+ * DataChunk (<= 2048 rows).  H2D copy, kernel, D2H copy on a stream owned by the calling thread; synchronous.
+ * Callers: exon_duckdb_b200/duckdb_ext (gc_content, reverse_complement, complement, quality_score_string_to_list). */
+EXB_API int exb_gc_content_host(const int64_t *offsets, const uint8_t *data, int64_t n_rows, float *out);
+/* *bad_pos = -1, or the smallest index of a byte outside ACGT (out is then unspecified) */
+EXB_API int exb_seq_map_host(const uint8_t *data, int64_t n_bytes, int mode, uint8_t *out, int64_t *bad_pos);
+EXB_API int exb_quality_decode_host(const uint8_t *data, int64_t n_bytes, int32_t *out);
 
 /* ---- deterministic synthetic inputs, counter-based RNG ---- */
 #define EXB_GEN_ILLUMINA 2 /* C2/C5: 150 bp reads, '@SIM:1:FC1:lane:tile:x:y 1:N:0:ACGTACGT' */

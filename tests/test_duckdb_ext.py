@@ -1,0 +1,253 @@
+"""The DuckDB-facing boundary: `LOAD exon`, read_fasta / read_fastq, replacement scans and the scalar functions.
+
+Two extensions are driven through build/rt/sqlrun (a DuckDB v0.8.1 host, tools/sqlrun.cpp):
+  PRODUCT  exon_duckdb_b200/duckdb_ext/exon.duckdb_extension  -- our host code over the exb_reader_* C ABI;
+  REFGLUE  oracle/_ref/exon.duckdb_extension                   -- the REFERENCE's unmodified C++ glue
+           (arrow_table_function/module.cpp) linked against libexon_b200.so's new_reader / replacement_scan:
+           the drop-in proof.  Its scalar functions are the reference's own CPU code (the live oracle).
+The queries and expectations replay the reference's sqllogictests
+(test/sql/exondb-release-with-deb-info/test_fastq_scan.test, test_fasta_scan.test, test_scalar_functions.test);
+zstd cases are out of scope this round.
+
+The binaries are built in the development container (they need the reference's vendored DuckDB headers) and travel
+to the GPU box with the snapshot; the tests skip when they are absent.
+"""
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import exb_testutil as util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SQLRUN = os.path.join(ROOT, "build", "rt", "sqlrun")
+PRODUCT = os.path.join(ROOT, "exon_duckdb_b200", "duckdb_ext", "exon.duckdb_extension")
+REFGLUE = os.path.join(ROOT, "oracle", "_ref", "exon.duckdb_extension")
+G = os.path.join(ROOT, "tests", "golden")
+
+SEQ60 = "GATTTGGGGTTCAAAGCAGTATCGATCAAATAGTAAATCCATTTGTTCAACTCACAGTTT"
+QUAL60 = "!''*((((***+))%%%++)(%%%%).1***-+*''))**55CCF>>>>>>CCCCCCC65"
+
+
+def _need(*paths):
+    for p in paths:
+        if not os.path.exists(p):
+            pytest.skip("%s not built (needs the reference's DuckDB headers: bash oracle/build_ref.sh; make -C exon_duckdb_b200/duckdb_ext)" % os.path.relpath(p, ROOT))
+
+
+def run_sql(ext, statements, threads=None, env=None):
+    _need(SQLRUN, ext)
+    text = "LOAD '%s';\n" % ext + "\n".join(s.rstrip().rstrip(";") + ";" for s in statements) + "\n"
+    cmd = [SQLRUN] + (["-threads", str(threads)] if threads else [])
+    e = dict(os.environ)
+    e.update(env or {})
+    out = subprocess.run(cmd, input=text.encode("utf-8"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, env=e)
+    assert out.returncode == 0, out.stderr.decode()
+    res = [json.loads(l) for l in out.stdout.decode("utf-8").splitlines()]
+    assert res and res[0]["ok"], res[:1]
+    assert len(res) == len(statements) + 1, (len(res), len(statements))
+    return res[1:]
+
+
+def rows(r):
+    assert r["ok"], r.get("error")
+    return r["rows"]
+
+
+def scalar(r):
+    return rows(r)[0][0]
+
+
+# ------------------------------------------------------------------ no GPU needed: registration, bind, plans
+def test_load_registers_the_path_functions():
+    r = run_sql(PRODUCT, ["SELECT function_name, function_type, return_type FROM duckdb_functions() WHERE function_name IN "
+                          "('read_fasta','read_fastq','gc_content','reverse_complement','complement','quality_score_string_to_list') ORDER BY 1"])
+    assert rows(r[0]) == [["complement", "scalar", "VARCHAR"], ["gc_content", "scalar", "FLOAT"],
+                          ["quality_score_string_to_list", "scalar", "INTEGER[]"], ["read_fasta", "table", None],
+                          ["read_fastq", "table", None], ["reverse_complement", "scalar", "VARCHAR"]]
+
+
+@pytest.mark.parametrize("ext", [PRODUCT, REFGLUE], ids=["product", "refglue"])
+def test_schema_matches_the_reference(ext):
+    # FileTypeBind: FASTQ (name, description, sequence, quality_scores), FASTA (id, description, sequence), all VARCHAR
+    r = run_sql(ext, ["DESCRIBE SELECT * FROM read_fastq('%s/test.fastq')" % G, "DESCRIBE SELECT * FROM '%s/test.fasta'" % G,
+                      "DESCRIBE SELECT * FROM read_fasta('%s/test.fasta.gzip', compression='gzip')" % G])
+    assert [(x[0], x[1]) for x in rows(r[0])] == [("name", "VARCHAR"), ("description", "VARCHAR"), ("sequence", "VARCHAR"), ("quality_scores", "VARCHAR")]
+    assert [(x[0], x[1]) for x in rows(r[1])] == [("id", "VARCHAR"), ("description", "VARCHAR"), ("sequence", "VARCHAR")]
+    assert [(x[0], x[1]) for x in rows(r[2])] == [("id", "VARCHAR"), ("description", "VARCHAR"), ("sequence", "VARCHAR")]
+
+
+@pytest.mark.parametrize("ext", [PRODUCT, REFGLUE], ids=["product", "refglue"])
+def test_missing_file_is_a_bind_error(ext):
+    # test_fastq_scan.test:61-62, test_fasta_scan.test:51-53: `statement error`
+    r = run_sql(ext, ["SELECT count(*) FROM read_fastq('')", "SELECT count(*) FROM read_fasta('')", "SELECT count(*) FROM read_fastq('/nonexistent/x.fastq')"])
+    assert not r[0]["ok"] and not r[1]["ok"] and not r[2]["ok"]
+
+
+def test_complex_filters_are_absorbed_by_the_scan():
+    r = run_sql(PRODUCT, [
+        "EXPLAIN SELECT count(*) FROM read_fastq('%s/test.fastq') WHERE list_avg(quality_score_string_to_list(quality_scores)) > 30" % G,
+        "EXPLAIN SELECT name FROM read_fastq('%s/test.fastq') WHERE gc_content(sequence) >= 0.25 AND name = 'SEQ_ID'" % G,
+        "EXPLAIN SELECT name FROM read_fastq('%s/test.fastq') WHERE length(sequence) > 3" % G])
+    plan0, plan1, plan2 = (scalar(x) if len(rows(x)[0]) == 1 else rows(x)[0][1] for x in r)
+    assert "Device filters" in plan0 and "mean_quality" in plan0 and "FILTER" not in plan0
+    assert "gc_content" in plan1 and "Device filters" in plan1 and "FILTER" not in plan1
+    assert "Device filters" not in plan2 and "FILTER" in plan2  # length() counts code points, not bytes: stays in DuckDB
+
+
+def test_no_gpu_is_a_loud_error():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    r = run_sql(PRODUCT, ["SELECT count(*) FROM read_fastq('%s/test.fastq')" % G, "SELECT gc_content('ATGC')"])
+    assert not r[0]["ok"] and "no CUDA device" in r[0]["error"]
+    assert not r[1]["ok"] and "no CUDA device" in r[1]["error"]
+
+
+# ------------------------------------------------------------------ GPU: the reference's sqllogictests replayed
+FASTQ_SCAN = [  # test_fastq_scan.test (zstd cases omitted)
+    ("SELECT count(*) FROM read_fastq('{G}/test.fastq')", [["2"]]),
+    ("SELECT count(*) FROM read_fastq('{G}/test.fastq.gz')", [["2"]]),
+    ("SELECT count(*) FROM read_fastq('{G}/test.fastq.gzip', compression='gzip')", [["2"]]),
+    ("SELECT * FROM read_fastq('{G}/test.fastq') LIMIT 1", [["SEQ_ID", "This is a description", SEQ60, QUAL60]]),
+    ("SELECT count(*) FROM '{G}/test.fastq'", [["2"]]),
+    ("SELECT count(*) FROM '{G}/test.fastq.gz'", [["2"]]),
+    ("SELECT COUNT(*) FROM read_fastq('{G}/fastq/') LIMIT 1", [["4"]]),
+]
+FASTA_SCAN = [  # test_fasta_scan.test (zstd cases omitted)
+    ("SELECT count(*) FROM read_fasta('{G}/test.fasta')", [["2"]]),
+    ("SELECT count(*) FROM read_fasta('{G}/test.fasta.gzip', compression='gzip')", [["2"]]),
+    ("SELECT count(*) FROM read_fasta('{G}/test.fasta.gz')", [["2"]]),
+    ("SELECT count(*) FROM '{G}/test.fasta'", [["2"]]),
+    ("SELECT count(*) FROM '{G}/test.fasta' WHERE id = 'a'", [["1"]]),
+    ("SELECT count(*) FROM '{G}/test.fasta.gz'", [["2"]]),
+    ("SELECT COUNT(*) FROM read_fasta('{G}/fasta/', compression='gzip')", [["4"]]),
+    # test_fasta_copy.test:74-80 (documented expectation): a header without description gives NULL
+    ("SELECT id, description, sequence FROM read_fasta('{G}/test.mixed-desc.fasta')", [["a", "description", "ATCG"], ["b", None, "ATCG"]]),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ext", [PRODUCT, REFGLUE], ids=["product", "refglue"])
+def test_reference_scan_sqllogictests(cuda_device, ext):
+    cases = FASTQ_SCAN + FASTA_SCAN
+    res = run_sql(ext, [q.format(G=G) for q, _ in cases])
+    for (q, want), r in zip(cases, res):
+        assert rows(r) == want, q
+
+
+@pytest.mark.gpu
+def test_reference_scalar_sqllogictests(cuda_device):
+    # test_scalar_functions.test:5-46 through the PRODUCT's CUDA scalar functions
+    r = run_sql(PRODUCT, [
+        "SELECT gc_content(seq) FROM (SELECT 'ATGC' AS seq UNION ALL SELECT 'ATGCGC' AS seq)",
+        "SELECT gc_content('')", "SELECT gc_content(NULL) IS NULL",
+        "WITH two_seqs AS (SELECT 'ATCG' AS sequence UNION ALL SELECT 'GGGG') SELECT gc_content(sequence) FROM two_seqs",
+        "SELECT complement(seq) FROM (SELECT 'ATGC' AS seq UNION ALL SELECT 'ATGCGC' AS seq)",
+        "SELECT complement('ATCGQ')",
+        "SELECT reverse_complement(seq) FROM (SELECT 'ATCG' AS seq UNION ALL SELECT 'GGGG' AS seq)",
+        "SELECT quality_score_string_to_list('!''*5I~')",
+        "SELECT list_avg(quality_score_string_to_list('IIII5555'))",
+        "SELECT typeof(quality_score_string_to_list('II'))",
+    ])
+    assert rows(r[0]) == [["0.5"], ["0.6666667"]]
+    assert rows(r[1]) == [["0.0"]] and rows(r[2]) == [["true"]]
+    assert rows(r[3]) == [["0.5"], ["1.0"]]
+    assert rows(r[4]) == [["TACG"], ["TACGCG"]]
+    assert not r[5]["ok"] and "Invalid character in sequence: Q" in r[5]["error"]
+    assert rows(r[6]) == [["CGAT"], ["TTTT"]]
+    assert rows(r[7]) == [["[0, 6, 9, 20, 40, 93]"]] and rows(r[8]) == [["30.0"]] and rows(r[9]) == [["INTEGER[]"]]
+
+
+@pytest.mark.gpu
+def test_scalar_functions_against_reference_vectors(cuda_device):
+    """The product's CUDA scalar functions inside DuckDB vs the reference's own functions (golden vectors), in ONE multi-row table."""
+    with open(os.path.join(G, "scalar_ref_vectors.json")) as f:
+        cases = json.load(f)["cases"]
+    seqs = [c for c in cases if "gc" in c and len(c["seq"]) < 6000]
+    lit = lambda s: "'" + s.encode("latin-1").decode("utf-8").replace("'", "''") + "'"
+    values = ", ".join("(%d, %s)" % (i, lit(c["seq"])) for i, c in enumerate(seqs))
+    ok = [i for i, c in enumerate(seqs) if c.get("rc") is not None]
+    quals = [c for c in cases if "qual" in c]
+    qvalues = ", ".join("(%d, %s)" % (i, lit(c["seq"])) for i, c in enumerate(quals))
+    r = run_sql(PRODUCT, [
+        "CREATE TABLE s AS SELECT * FROM (VALUES %s) t(i, seq)" % values,
+        "SELECT i, gc_content(seq)::DOUBLE FROM s ORDER BY i",
+        "SELECT i, reverse_complement(seq), complement(seq) FROM s WHERE i IN (%s) ORDER BY i" % ",".join(map(str, ok)),
+        "CREATE TABLE q AS SELECT * FROM (VALUES %s) t(i, qual)" % qvalues,
+        "SELECT i, quality_score_string_to_list(qual), list_avg(quality_score_string_to_list(qual)) FROM q ORDER BY i",
+    ])
+    got = rows(r[1])
+    assert len(got) == len(seqs)
+    for (i, g), c in zip(got, seqs):
+        assert np.float32(float(g)) == np.float32(c["gc"]), c["seq"][:40]
+    for (i, rc, comp) in rows(r[2]):
+        c = seqs[int(i)]
+        assert rc.encode("utf-8").decode("latin-1") == c["rc"] and comp.encode("utf-8").decode("latin-1") == c["comp"]
+    for (i, lst, avg), c in zip(rows(r[4]), quals):
+        assert json.loads(lst) == c["qual"]
+        assert float(avg) == c["mean_q"]
+    bad = [c for c in seqs if c.get("rc") is None][:5]
+    r = run_sql(PRODUCT, ["SELECT reverse_complement(%s)" % lit(c["seq"]) for c in bad])
+    assert all((not x["ok"]) and "Invalid character in sequence" in x["error"] for x in r)
+
+
+def _write(tmp_path, name, data):
+    p = os.path.join(str(tmp_path), name)
+    with open(p, "wb") as f:
+        f.write(data)
+    return p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ext", [PRODUCT, REFGLUE], ids=["product", "refglue"])
+def test_fastq_rows_filters_and_projection(cuda_device, tmp_path, ext):
+    """A multi-chunk synthetic file through DuckDB: every row, projections, simple + complex filters, COUNT(*), vs the oracle."""
+    from oracle import oracle as O
+    text, _ = util.random_fastq(11, 5000, min_len=1, max_len=200, tricky=False)
+    path = _write(tmp_path, "r.fastq", text)
+    ref = O.parse_fastq(text)
+    want = [tuple(None if v is None else v.decode() for v in row) for row in ref.rows()]
+    env = {"EXON_B200_CHUNK_BYTES": str(200_000)}  # several device chunks, records straddling their edges
+    mq = [O.mean_quality_pass(q, ">", 60.0) for q in ref.strings("quality_scores")]
+    gcv = [O.gc_content(s) for s in ref.strings("sequence")]
+    res = run_sql(ext, [
+        "SELECT count(*) FROM read_fastq('%s')" % path,
+        "SELECT * FROM read_fastq('%s')" % path,
+        "SELECT sequence, name FROM read_fastq('%s') WHERE description IS NULL" % path,
+        "SELECT count(*) FROM read_fastq('%s') WHERE list_avg(quality_score_string_to_list(quality_scores)) > 60" % path,
+        "SELECT name FROM read_fastq('%s') WHERE list_avg(quality_score_string_to_list(quality_scores)) > 60" % path,
+        # the reference's own gc_content collapses multi-row chunks (SURVEY finding 4): only the product evaluates this one per row
+        ("SELECT count(*), sum(length(sequence)) FROM read_fastq('%s') WHERE gc_content(sequence) < 0.45" if ext == PRODUCT else "SELECT 0, 0 FROM read_fastq('%s') LIMIT 0") % path,
+    ], env=env)
+    assert rows(res[0]) == [[str(len(want))]]
+    assert [tuple(r) for r in rows(res[1])] == want
+    assert [tuple(r) for r in rows(res[2])] == [(w[2], w[0]) for w in want if w[1] is None]
+    assert rows(res[3]) == [[str(sum(mq))]]
+    assert [r[0] for r in rows(res[4])] == [w[0] for w, m in zip(want, mq) if m]
+    sel = [w for w, g in zip(want, gcv) if float(g) < 0.45]
+    if ext == PRODUCT:
+        assert rows(res[5]) == [[str(len(sel)), str(sum(len(w[2]) for w in sel))]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ext", [PRODUCT, REFGLUE], ids=["product", "refglue"])
+def test_fasta_rows_and_gc_per_contig(cuda_device, tmp_path, ext):
+    from oracle import oracle as O
+    text, _ = util.random_fasta(5, 300, min_len=0, max_len=5000, tricky=False)
+    path = _write(tmp_path, "g.fasta", text)
+    ref = O.parse_fasta(text)
+    want = [tuple(None if v is None else v.decode() for v in row) for row in ref.rows()]
+    env = {"EXON_B200_CHUNK_BYTES": str(150_000)}
+    res = run_sql(ext, ["SELECT * FROM read_fasta('%s')" % path, "SELECT count(*) FROM read_fasta('%s')" % path,
+                        "SELECT id FROM read_fasta('%s') WHERE id >= 's2' AND id < 's3'" % path], env=env)
+    assert [tuple(r) for r in rows(res[0])] == want
+    assert rows(res[1]) == [[str(len(want))]]
+    assert [r[0] for r in rows(res[2])] == [w[0] for w in want if "s2" <= w[0] < "s3"]
+    if ext == PRODUCT:  # C3's query; one query per row would pin the reference (its gc_content collapses chunks, SURVEY finding 4)
+        r = run_sql(ext, ["SELECT id, gc_content(sequence)::DOUBLE FROM read_fasta('%s')" % path], env=env)
+        for (i, g), w in zip(rows(r[0]), want):
+            assert i == w[0] and np.float32(float(g)) == O.gc_content(w[2].encode())
