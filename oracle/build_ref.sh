@@ -19,6 +19,7 @@ if [ ! -f $ROOT/build/rt/libduckdb.so ]; then
     ninja -C $ROOT/build/duckdb -j8 src/libduckdb.so > $ROOT/build/ninja.log 2>&1
     cp $ROOT/build/duckdb/src/libduckdb.so $ROOT/build/rt/libduckdb.so
     strip $ROOT/build/rt/libduckdb.so
+    rm -rf $ROOT/build/duckdb
 fi
 CXXF="-O2 -std=c++17 -fPIC -w -I$REF/duckdb/src/include -I$REF/duckdb/third_party/re2 -I$REF/duckdb/third_party/fmt/include -I$REF/duckdb/third_party/utf8proc/include"
 if [ ! -f $ROOT/build/rt/sqlrun ] || [ $ROOT/tools/sqlrun.cpp -nt $ROOT/build/rt/sqlrun ]; then
