@@ -60,6 +60,14 @@ class ReplacementScanResult(C.Structure):
     _fields_ = [("file_type", C.c_void_p)]
 
 
+class ColumnView(C.Structure):
+    _fields_ = [("offsets", C.POINTER(C.c_int64)), ("data", C.POINTER(C.c_uint8)), ("valid", C.POINTER(C.c_uint8))]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int32), ("cols", ColumnView * 4), ("owner", C.c_void_p)]
+
+
 class ExonError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("exon_b200 error %d: %s" % (code, msg))
@@ -76,6 +84,12 @@ SIGNATURES = {
     "new_reader": (ReaderResult, [_vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_char_p, C.c_char_p]),
     "replacement_scan": (ReplacementScanResult, [C.c_char_p]),
     "exb_free_string": (None, [_vp]),
+    "exb_reader_open": (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, _i64, C.c_char_p, C.c_uint32, C.POINTER(_vp)]),
+    "exb_reader_columns": (_i32, [_vp, C.POINTER(C.c_char_p), _i32]),
+    "exb_reader_next": (_i32, [_vp, C.POINTER(Batch)]),
+    "exb_batch_release": (None, [C.POINTER(Batch)]),
+    "exb_reader_count": (_i32, [_vp, C.POINTER(_i64)]),
+    "exb_reader_close": (None, [_vp]),
     "exb_scan_workspace_bytes": (_i64, [_i64]),
     "exb_fastq_workspace_bytes": (_i64, [_i64, _i64]),
     "exb_fastq_scan": (_i32, [_vp, _i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
@@ -94,6 +108,9 @@ SIGNATURES = {
     "exb_gc_content": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_seq_map": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "exb_quality_decode": (_i32, [_vp, _i64, _vp, _vp]),
+    "exb_gc_content_host": (_i32, [_vp, _vp, _i64, _vp]),
+    "exb_seq_map_host": (_i32, [_vp, _i64, _i32, _vp, C.POINTER(_i64)]),
+    "exb_quality_decode_host": (_i32, [_vp, _i64, _vp]),
     "exb_gen_size": (_i64, [C.POINTER(GenParams)]),
     "exb_gen_device": (_i32, [C.POINTER(GenParams), _vp, _i64, _vp]),
     "exb_gen_host": (_i32, [C.POINTER(GenParams), _vp, _i64]),
