@@ -113,6 +113,15 @@ def ncu_traffic():
         return None
 
 
+def traffic_per_launch(tr, n_bytes):
+    """DRAM bytes of one launch of the dominant kernel at THIS input size.  The capture may have been taken on a
+    smaller file of the same generator (ncu replays each kernel ~40x); the kernel streams, so traffic scales with the input."""
+    if not tr or not tr.get("dram_bytes_per_launch"):
+        return None
+    cap = tr.get("input_bytes") or n_bytes
+    return tr["dram_bytes_per_launch"] * (n_bytes / cap)
+
+
 def run_reference(args):
     """CPU arm: the oracle's record-at-a-time port, one shard of whole records per host thread."""
     rank = int(os.environ.get("RANK", "0"))
@@ -321,7 +330,7 @@ def main():
             "reads_per_s": args.reads * world / (ms_step * 1e-3),
             "bytes_per_gpu": n_bytes, "records_passing": int(n_pass),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": tr.get("dram_bytes_per_launch") if tr else None, "kernel": "fastq_tile_kernel<F_FUSED|F_QUAL> (TMA-fed byte pass; + offset scan + bucket-combine kernels, ~4% of the step)",
+                         "traffic": traffic_per_launch(tr, n_bytes), "kernel": "fastq_tile_kernel<F_FUSED|F_QUAL> (TMA-fed byte pass; + offset scan + bucket-combine kernels, ~4% of the step)",
                          "algorithmic_bytes_per_launch": n_bytes, "kernel_ms": scan_ms, "peak_source": peak_src,
                          "note": "algorithmic bytes = input file bytes read once (SURVEY 8d); kernel_ms = CUDA events on the launching stream around one exb_fastq_scan_filter call (3 small memsets + tile kernel + offset scan + combine kernel), i.e. an upper bound of the tile kernel's own duration"},
             "clocks": sampler.summary(),

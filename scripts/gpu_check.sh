@@ -17,3 +17,5 @@ echo "ncu launches exit $?"
 EXB_BENCH_READS=4000000 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fastq_tile_kernel -s 3 -c 1 \
     -f -o gpurun_out/${TAG}_fastq_scan python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
+timeout 600 python scripts/bench_paths.py --out gpurun_out/${TAG}_paths.json > gpurun_out/${TAG}_paths.log 2>&1
+echo "paths exit $?"; tail -30 gpurun_out/${TAG}_paths.log
