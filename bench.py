@@ -38,7 +38,9 @@ def workload_config(n_gpus, reads):
         "workload": "C2: synthetic Illumina FASTQ %d reads x %d bp per GPU, COUNT(*) WHERE mean quality > %g" % (reads, READ_LEN, THRESH),
         "reads_per_gpu": reads,
         "query": "SELECT COUNT(*) FROM read_fastq(f) WHERE list_avg(quality_score_string_to_list(quality_scores)) > 30",
-        "sharding": "byte-range / record shards, one per GPU, no data-path collective; NCCL all-reduce of the aggregates"
+        "sharding": "one file of n_gpus x reads_per_gpu records cut into byte ranges whose edges fall inside records; per step: scan under a "
+                    "provisional phase, NCCL all-gather of the 128-byte result blocks, device-side composition + resolve kernel "
+                    "(exon_duckdb_b200/dist.py), NCCL all-reduce of the aggregates; no data-path collective"
         if n_gpus > 1 else "single GPU",
         "l2": "input (~7 GB) is larger than L2 (126 MB); no flush needed between steps",
     }
@@ -212,26 +214,87 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    # ---- synthetic input, generated on the device (each rank its own shard of the record space)
-    p = _lib.gen_params("illumina", args.reads, seed=SEED, first_record=rank * args.reads, len_min=READ_LEN, len_max=READ_LEN)
-    buf = D.gen_device(p, dev)
-    n_bytes = buf.numel()
+    # ---- synthetic input, generated on the device
     preds = [("mean_quality", ">", THRESH)]
-    # COUNT(*) + a predicate on the quality line: scan and filter run as ONE kernel (exb_fastq_scan_filter);
-    # projection push-down means nothing per record is written at all.
-    cnt = D.fastq_scan_filter(buf, preds)
-    n_rec = cnt.validate()
-    assert n_rec == args.reads
-    agg = cnt.agg
+    sharded = None
+    if world == 1:
+        p = _lib.gen_params("illumina", args.reads, seed=SEED, first_record=0, len_min=READ_LEN, len_max=READ_LEN)
+        buf = D.gen_device(p, dev)
+        n_bytes = buf.numel()
+        # COUNT(*) + a predicate on the quality line: scan and filter run as ONE kernel (exb_fastq_scan_filter);
+        # projection push-down means nothing per record is written at all.
+        cnt = D.fastq_scan_filter(buf, preds)
+        n_rec = cnt.validate()
+        assert n_rec == args.reads
+        agg = cnt.agg
+        want_pass = None
+        e2e_src = buf
 
-    def step(timers=None):
-        if timers is not None:
-            timers[0].record()
-        D.fastq_scan_filter(buf, preds, out=cnt)
-        if timers is not None:
-            timers[1].record()
-        if world > 1:
-            dist.all_reduce(agg)  # COUNT / sums across shards: the query's only exchange step (64 bytes over NVLink)
+        def step(timers=None):
+            if timers is not None:
+                timers[0].record()
+            D.fastq_scan_filter(buf, preds, out=cnt)
+            if timers is not None:
+                timers[1].record()
+    else:
+        # ONE file of world x reads records, cut into byte ranges whose edges fall INSIDE records (about 100 bytes past a
+        # record start), so every step runs the boundary-resync protocol of exon_duckdb_b200/dist.py: scan under a
+        # provisional phase, all-gather of the 128-byte result blocks, device-side composition, resolve kernel, all-reduce.
+        from exon_duckdb_b200 import dist as XD
+
+        R = args.reads
+
+        def rec_size(i):
+            q = _lib.gen_params("illumina", 1, seed=SEED, first_record=i, len_min=READ_LEN, len_max=READ_LEN)
+            return L.exb_gen_size(C.byref(q))
+
+        def delta(k):  # offset of shard k's first byte inside record k*R; local offset of that byte is a multiple of 16
+            if k == 0:
+                return 0
+            s_prev = rec_size(k * R - 1)
+            return 96 + ((-(s_prev + 96)) % 16)
+
+        first = rank * R - (1 if rank else 0)
+        count = R + (1 if rank else 0) + (1 if rank < world - 1 else 0)
+        p = _lib.gen_params("illumina", count, seed=SEED, first_record=first, len_min=READ_LEN, len_max=READ_LEN)
+        gbuf = D.gen_device(p, dev)
+        s_prev = rec_size(rank * R - 1) if rank else 0
+        s_next = rec_size((rank + 1) * R) if rank < world - 1 else 0
+        own = gbuf.numel() - s_prev - s_next  # bytes of records [rank*R, (rank+1)*R)
+        grp = XD.TorchGroup(dev)
+        owns = grp.all_gather_rows([own])[:, 0]
+        off0 = int(owns[:rank].sum())  # file offset of record rank*R
+        lo = off0 + delta(rank)
+        hi = off0 + own + (delta(rank + 1) if rank < world - 1 else 0)
+        begin = XD.HALO if rank else 0
+        local0 = s_prev + delta(rank) - begin  # view: file byte lo sits at local offset `begin`
+        assert local0 % 16 == 0
+        buf = gbuf[local0:local0 + begin + (hi - lo)]
+        shard = XD.Shard(buf, lo, hi, begin, rank == world - 1)
+        n_bytes = hi - lo
+        sharded = XD.ShardedFastqCount(shard, preds, grp)
+        # cross-check: the same records counted shard-locally on whole-record ranges
+        whole = gbuf[s_prev:s_prev + own]
+        if (s_prev % 16) != 0:
+            whole = D.to_device(whole.cpu().numpy(), dev)
+        chk = D.fastq_scan_filter(whole, preds)
+        assert chk.validate() == R
+        want = chk.agg.clone()
+        dist.all_reduce(want)
+        want_pass = int(want[0].item())
+        del chk
+        e2e_src = gbuf[s_prev:s_prev + own]  # the rank's whole records: the file image a host application would hold
+        agg = sharded.total
+
+        def step(timers=None):
+            if timers is not None:
+                timers[0].record()
+            blk = sharded.scan()
+            if timers is not None:
+                timers[1].record()
+            dist.all_gather_into_tensor(sharded.blocks, blk)
+            sharded.resolve(sharded.blocks, rank)
+            dist.all_reduce(sharded.total)  # COUNT / sums across shards (64 bytes over NVLink)
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -259,38 +322,45 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total, scan_ms = tmax.tolist()
     ms_step = ms_total / args.steps
-    total_bytes = n_bytes * world
+    tb = torch.tensor([n_bytes], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb)
+    total_bytes = int(tb.item())
     value = total_bytes / (ms_step * 1e-3) / 1e9
     n_pass = got[0]  # after the all-reduce this is already the global count
+    if sharded is not None:
+        XD.check_count(agg)
+        assert n_pass == want_pass, (n_pass, want_pass)
 
     # ---- end to end: pinned host image -> engine -> aggregates, every step
     e2e = None
     host_ptr = None
     if not args.no_e2e:
-        host_ptr = L.exb_host_alloc(n_bytes)
+        e2e_bytes = e2e_src.numel()
+        host_ptr = L.exb_host_alloc(e2e_bytes)
         if not host_ptr:
             raise SystemExit("exb_host_alloc failed")
-        host = np.ctypeslib.as_array(C.cast(host_ptr, C.POINTER(C.c_uint8)), shape=(n_bytes,))
-        torch.from_numpy(host).copy_(buf)  # untimed: put the file image where a host application would have it
+        host = np.ctypeslib.as_array(C.cast(host_ptr, C.POINTER(C.c_uint8)), shape=(e2e_bytes,))
+        torch.from_numpy(host).copy_(e2e_src)  # untimed: put the file image where a host application would have it
         eng = C.c_void_p()
         _lib.check(L.exb_engine_create(local, 64 << 20, C.byref(eng)))
         parr, k = _lib.predicates(preds)
         eagg = (C.c_int64 * 8)()
         for _ in range(3):
-            _lib.check(L.exb_engine_fastq_count(eng, host_ptr, n_bytes, parr, k, eagg, None))
+            _lib.check(L.exb_engine_fastq_count(eng, host_ptr, e2e_bytes, parr, k, eagg, None))
         if world > 1:
             dist.barrier()
         e2e_steps = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            _lib.check(L.exb_engine_fastq_count(eng, host_ptr, n_bytes, parr, k, eagg, None))
+            _lib.check(L.exb_engine_fastq_count(eng, host_ptr, e2e_bytes, parr, k, eagg, None))
         dt = (time.perf_counter() - t0) / e2e_steps
         assert eagg[5] == args.reads
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = tt.item()
-        e2e = {"value": total_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": 64 + C.sizeof(_lib.ScanResult),
+        e2e = {"value": total_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": 64 + C.sizeof(_lib.ScanResult),
                "ms_per_step": dt * 1e3, "steps": e2e_steps, "pass": int(eagg[0]),
                "note": "host wall clock around exb_engine_fastq_count (synchronous call), max over ranks"}
         L.exb_engine_destroy(eng)
@@ -334,7 +404,9 @@ def main():
                          "algorithmic_bytes_per_launch": n_bytes, "kernel_ms": scan_ms, "peak_source": peak_src,
                          "note": "algorithmic bytes = input file bytes read once (SURVEY 8d); kernel_ms = CUDA events on the launching stream around one exb_fastq_scan_filter call (3 small memsets + tile kernel + offset scan + combine kernel), i.e. an upper bound of the tile kernel's own duration"},
             "clocks": sampler.summary(),
-            "gpu_launches": 3 * args.steps,  # fastq_tile_kernel, exclusive_scan_kernel, fastq_fused_combine_kernel (+ 3 cudaMemsetAsync)
+            # N=1: fastq_tile_kernel, exclusive_scan_kernel, fastq_fused_combine_kernel (+ 3 cudaMemsetAsync);
+            # N>1 adds per rank: fastq_compose_prev_kernel + a second fastq_fused_combine_kernel (ranks >= 1)
+            "gpu_launches": (3 if world == 1 else 5) * args.steps,
         }
         if e2e:
             line["e2e"] = e2e

@@ -86,6 +86,44 @@ __global__ void gen_fill_kernel(exb_gen_params p, const int64_t* off, uint8_t* o
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_records; i += (int64_t)gridDim.x * blockDim.x)
         exb_gen_record(&p, (uint64_t)(p.first_record + i), out + off[i]);
 }
+
+// True predecessor state of shard `rank` from the all-gathered result blocks of all shards (one thread: the walk is
+// over at most `world` blocks).  Host mirror with the derivation: exon_duckdb_b200/dist.py compose_prev.
+__global__ void fastq_compose_prev_kernel(const uint8_t* blocks, const int64_t* ranges, int world, int rank, ScanResult* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    auto blk = [&](int j) { return reinterpret_cast<const ScanResult*>(blocks + (size_t)j * 128); };
+    auto lo = [&](int j) { return ranges[3 * j]; };
+    auto hi = [&](int j) { return ranges[3 * j + 1]; };
+    auto begin = [&](int j) { return ranges[3 * j + 2]; };
+    auto open_start = [&](int j) { return lo(j) + (blk(j)->open_line_start - begin(j)); };  // global offset
+    ScanResult r;
+    memset(&r, 0, sizeof(r));
+    uint64_t lines = 0;
+    for (int j = 0; j < rank; j++) lines += blk(j)->total_lines;
+    int64_t tail_s = 0, tail_g = 0, start = lo(0);
+    for (int j = rank - 1; j >= 0; j--) {  // back to the last shard that saw a newline: the open line starts after it
+        tail_s += blk(j)->tail_s;
+        tail_g += blk(j)->tail_g;
+        if (blk(j)->total_lines > 0) {
+            start = open_start(j);
+            break;
+        }
+    }
+    uint32_t flags = 0;
+    if (start < lo(rank)) {  // the shard that holds the open line's first byte knows what it is
+        for (int j = 0; j < rank; j++)
+            if (lo(j) <= start && start < hi(j)) {
+                flags = blk(j)->pad & 3u;
+                break;
+            }
+    }
+    r.total_lines = lines;
+    r.open_line_start = begin(rank) + (start - lo(rank));
+    r.tail_s = tail_s;
+    r.tail_g = tail_g;
+    r.pad = flags;
+    *out = r;
+}
 }  // namespace exb
 
 using namespace exb;
@@ -142,8 +180,8 @@ static int64_t fastq_workspace_bytes(int64_t n, int64_t max_lines) {
 static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace,
                              uint64_t max_lines, int flags, void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len,
                              uint32_t* d_gc, uint32_t* d_qual_len, int32_t* d_qsum, int64_t rec_cap, const exb_predicate* preds, int n_preds,
-                             int64_t* d_agg, void* d_workspace, int64_t workspace_bytes, cudaStream_t st) {
-    if (!d_buf || begin < 0 || n < begin) return set_err(EXB_ERR_ARG, "%s: bad buffer range", who);
+                             int64_t* d_agg, void* d_workspace, int64_t workspace_bytes, cudaStream_t st, bool resolve_only = false) {
+    if ((!d_buf && !resolve_only) || begin < 0 || n < begin) return set_err(EXB_ERR_ARG, "%s: bad buffer range", who);
     if (((uintptr_t)d_buf & 15) != 0) return set_err(EXB_ERR_ARG, "%s: d_buf must be 16-byte aligned", who);
     if (d_prev_workspace && (begin & 15) != 0) return set_err(EXB_ERR_ARG, "%s: `begin` of a chained range must be a multiple of 16", who);
     if ((flags & EXB_F_LINES) && !d_line_end) return set_err(EXB_ERR_ARG, "%s: EXB_F_LINES without d_line_end", who);
@@ -171,7 +209,12 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
         return set_err(EXB_ERR_ARG, "%s: workspace too small: need at least %lld bytes, have %lld", who, (long long)(L.fixed + min_payload),
                        (long long)workspace_bytes);
     uint8_t* ws = reinterpret_cast<uint8_t*>(d_workspace);
-    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)WS_HEADER, st);  // result block + record bump counter
+    cudaError_t e;
+    if (resolve_only) {  // K1's products stay; only the error mark of the earlier resolution is withdrawn (overflow is K1's)
+        e = cudaMemsetAsync(ws + offsetof(ScanResult, err_pos), 0, sizeof(unsigned long long), st);
+    } else {
+        e = cudaMemsetAsync(ws, 0, (size_t)WS_HEADER, st);  // result block + record bump counter
+    }
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace header)");
     a.result = reinterpret_cast<ScanResult*>(ws);
     a.rec_bump = reinterpret_cast<unsigned long long*>(ws + 128);
@@ -194,15 +237,17 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
     a.qual_len = d_qual_len;
     a.qsum = d_qsum;
     a.rec_cap = rec_cap;
-    // K1: every byte once, no inter-tile dependency
-    e = fastq_tile_launch(a, flags, st);
-    if (e != cudaSuccess) return cuda_fail(e, "fastq_tile launch");
-    // global line index of every tile
-    Workspace w;
-    int rc = carve(ws + WS_HEADER, L.scan_ws, scan_tiles(a.n_tiles), st, &w);
-    if (rc) return rc;
-    e = exclusive_scan_launch_u32(a.tile_cnt, a.n_tiles, line_base, w.slots, w.ticket, st);
-    if (e != cudaSuccess) return cuda_fail(e, "line offset scan launch");
+    if (!resolve_only) {
+        // K1: every byte once, no inter-tile dependency
+        e = fastq_tile_launch(a, flags, st);
+        if (e != cudaSuccess) return cuda_fail(e, "fastq_tile launch");
+        // global line index of every tile
+        Workspace w;
+        int rc = carve(ws + WS_HEADER, L.scan_ws, scan_tiles(a.n_tiles), st, &w);
+        if (rc) return rc;
+        e = exclusive_scan_launch_u32(a.tile_cnt, a.n_tiles, line_base, w.slots, w.ticket, st);
+        if (e != cudaSuccess) return cuda_fail(e, "line offset scan launch");
+    }
     // K2: records -> per-line / per-record outputs (or bucket selection, fused)
     e = fastq_emit_launch(a, flags, wide_offsets != 0, st);
     if (e != cudaSuccess) return cuda_fail(e, "fastq_emit launch");
@@ -243,6 +288,47 @@ int exb_fastq_scan_filter(const void* d_buf, int64_t begin, int64_t n, int is_fi
     }
     return fastq_scan_common("exb_fastq_scan_filter", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_QUAL, nullptr, 0,
                              0, nullptr, nullptr, nullptr, nullptr, 0, preds, n_preds, d_agg, d_workspace, workspace_bytes, st);
+}
+
+int exb_fastq_scan_resolve(int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, uint64_t max_lines, int flags,
+                           void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len, uint32_t* d_gc, uint32_t* d_qual_len,
+                           int32_t* d_qsum, int64_t rec_cap, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    return fastq_scan_common("exb_fastq_scan_resolve", nullptr, begin, n, is_final, d_prev_workspace, max_lines, flags & 7, d_line_end, line_cap,
+                             wide_offsets, d_seq_len, d_gc, d_qual_len, d_qsum, rec_cap, nullptr, 0, nullptr, d_workspace, workspace_bytes,
+                             (cudaStream_t)stream, true);
+}
+
+int exb_fastq_scan_filter_resolve(int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, const exb_predicate* preds,
+                                  int n_preds, int64_t* d_agg, int accumulate, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_preds < 0 || n_preds > EXB_MAX_PREDICATES || !d_agg) return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter_resolve: bad arguments");
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(d_agg, 0, 8 * sizeof(int64_t), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(agg)");
+    }
+    return fastq_scan_common("exb_fastq_scan_filter_resolve", nullptr, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_QUAL,
+                             nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, preds, n_preds, d_agg, d_workspace, workspace_bytes, st, true);
+}
+
+int exb_fastq_compose_prev(const void* d_blocks, const int64_t* d_ranges, int world, int rank, void* d_prev_out, void* stream) {
+    if (!d_blocks || !d_ranges || !d_prev_out || world < 1 || rank < 0 || rank >= world)
+        return set_err(EXB_ERR_ARG, "exb_fastq_compose_prev: bad arguments");
+    fastq_compose_prev_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(d_blocks), d_ranges, world, rank,
+                                                                  reinterpret_cast<ScanResult*>(d_prev_out));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_compose_prev launch");
+    return 0;
+}
+
+int exb_scan_result_store(void* d_dst, const exb_scan_result* src, void* stream) {
+    if (!d_dst || !src) return set_err(EXB_ERR_ARG, "exb_scan_result_store: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    exb_scan_result tmp = *src;
+    tmp.err_pos = ~tmp.err_pos;  // device representation (see exb_scan_result_fetch)
+    // pageable source: the runtime stages the bytes before the call returns, so `tmp` may go out of scope
+    cudaError_t e = cudaMemcpyAsync(d_dst, &tmp, sizeof(tmp), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(result store)");
+    return 0;
 }
 
 int exb_scan_result_fetch(const void* d_workspace, exb_scan_result* out, void* stream) {

@@ -1,0 +1,347 @@
+"""dist.py -- one FASTA/FASTQ file across ranks: contiguous byte ranges, a boundary-resync step at each shard edge,
+and tiny collectives for what the shards must agree on.
+
+One process per GPU.  Rank k owns bytes [lo_k, hi_k) = [k*N/G, (k+1)*N/G) of the file; a record belongs to the shard that
+holds its first byte.  Data never moves between GPUs; what is exchanged is one 128-byte block per shard:
+
+  FASTQ phase (exact)     '@' and '+' are legal quality characters, so a shard cannot tell from its own bytes which
+                          of its lines are headers.  Every shard counts its newlines; the exclusive sum over the
+                          earlier shards is the absolute index of its first line, and index mod 4 is the phase.
+  aggregates              COUNT / sums are reduced with one all-reduce of 8 int64.
+
+Two protocols are built on that exchange:
+
+  ShardedFastqCount       COUNT-style queries, ONE pass over the bytes: the byte kernel (K1) of the fused scan does not
+                          depend on the phase, so each shard runs it right away under a provisional predecessor; the
+                          shards all-gather their result blocks, compose their true predecessor state (compose_prev)
+                          and re-run only the light resolve kernel (exb_fastq_scan_filter_resolve).
+  fastq_record_bounds /   Row-returning queries: the shards agree on record-aligned bounds S_0 <= ... <= S_G = N
+  fasta_record_bounds     (S_k = first record start at or after lo_k); [S_k, S_{k+1}) is then a complete file image
+                          for every other entry point of the library (tables, filters, projections).
+
+The collectives go through a group object: TorchGroup (torch.distributed: NCCL on the GPU box, gloo in the CPU tests) or
+LocalGroup, which holds G shards in one process.  The composition rules are pure functions over the gathered matrix,
+so the CPU tests drive them with world_size 2 over gloo without a GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+# one row of shard state, int64 each (global file offsets)
+LO, HI, NEWLINES, OPEN_START, TAIL_S, TAIL_G, OPEN_FLAGS, LS0 = 0, 1, 2, 3, 4, 5, 6, 7
+N_LS = 5  # LS0..LS0+4: offsets of the first five line starts inside the shard (-1 = none)
+STATE_WORDS = LS0 + N_LS
+HALO = 16  # bytes of the file kept in front of a shard's first byte (the scan looks one byte back for CRLF)
+RESULT_WORDS = 16  # the 128-byte result block of a scan as int64 words
+
+
+def byte_range(n_bytes, rank, world):
+    """[lo, hi) of rank's shard: contiguous, disjoint, covering [0, n_bytes)."""
+    return n_bytes * rank // world, n_bytes * (rank + 1) // world
+
+
+# ------------------------------------------------------------------ groups
+class TorchGroup:
+    """torch.distributed process group (NCCL: tensors on the rank's GPU; gloo: CPU tensors)."""
+
+    def __init__(self, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device if device is not None else torch.device("cpu")
+
+    def all_gather_rows(self, row):
+        """row: sequence of int64 or an int64 tensor on the group's device -> (world, len) numpy matrix, same on every rank."""
+        t = row if hasattr(row, "numel") else self.torch.tensor([int(x) for x in row], dtype=self.torch.int64, device=self.device)
+        t = t.contiguous().view(-1)
+        out = self.torch.empty(self.world * t.numel(), dtype=self.torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.view(self.world, t.numel()).cpu().numpy()
+
+    def all_reduce_sum(self, t):
+        """In-place sum (the tensor stays on its device: 64 bytes over NVLink for the aggregates)."""
+        self.dist.all_reduce(t, group=self.group)
+        return t
+
+
+class LocalGroup:
+    """G shards held by one process (tests, multi-shard runs on one GPU): the "collective" completes once every shard
+    has contributed its row."""
+
+    def __init__(self, world):
+        self.world = world
+        self.rows = [None] * world
+
+    def contribute(self, rank, row):
+        self.rows[rank] = [int(x) for x in (row.tolist() if hasattr(row, "tolist") else row)]
+
+    def matrix(self):
+        assert all(r is not None for r in self.rows), "every shard must contribute before the exchange completes"
+        return np.array(self.rows, dtype=np.int64)
+
+
+# ------------------------------------------------------------------ pure composition rules
+def state_row(lo, hi, begin, total_lines, open_line_start, tail_s, tail_g, pad, line_starts=()):
+    """Shard state in GLOBAL file offsets from the scan's result block (local offsets: file byte lo = local `begin`)."""
+    row = [0] * STATE_WORDS
+    row[LO], row[HI], row[NEWLINES] = int(lo), int(hi), int(total_lines)
+    row[OPEN_START] = int(lo) + (int(open_line_start) - int(begin))
+    row[TAIL_S], row[TAIL_G], row[OPEN_FLAGS] = int(tail_s), int(tail_g), int(pad) & 3
+    ls = [int(x) for x in line_starts][:N_LS]
+    row[LS0:LS0 + N_LS] = ls + [-1] * (N_LS - len(ls))
+    return row
+
+
+def compose_prev(states, k, begin=HALO):
+    """True predecessor state of shard k from the gathered shard states (pure).
+
+    states[j] describes shard j scanned on its own: NEWLINES in [lo_j, hi_j); OPEN_START = offset of the first byte
+    after its last newline (lo_j if it has none); TAIL_S / TAIL_G = byte sum / G,C count of the bytes after that;
+    OPEN_FLAGS = '@'(2) / '+'(1) of the byte at OPEN_START when that byte lies in the shard.
+    Returns an exb_scan_result in shard k's LOCAL coordinates (file byte lo_k sits at local offset `begin`), or None
+    for shard 0, which has no predecessor."""
+    if k == 0:
+        return None
+    lo_k = int(states[k][LO])
+    tail_s = tail_g = 0
+    start = int(states[0][LO])
+    for j in range(k - 1, -1, -1):  # back to the last shard that saw a newline: the open line starts after it
+        tail_s += int(states[j][TAIL_S])
+        tail_g += int(states[j][TAIL_G])
+        if int(states[j][NEWLINES]) > 0:
+            start = int(states[j][OPEN_START])
+            break
+    flags = 0
+    if start < lo_k:  # the shard that holds the open line's first byte knows what it is
+        holder = next(j for j in range(k) if int(states[j][LO]) <= start < int(states[j][HI]))
+        flags = int(states[holder][OPEN_FLAGS]) & 3
+    # start == lo_k: the line starts with this shard's own first byte; the scan reads it itself (open_line_start == begin)
+    res = _lib.ScanResult()
+    res.total_lines = int(sum(int(states[j][NEWLINES]) for j in range(k)))
+    res.open_line_start = begin + (start - lo_k)
+    res.tail_s, res.tail_g, res.pad = tail_s, tail_g, flags
+    res.err_pos = _lib.NO_POS
+    return res
+
+
+def fastq_record_bounds(states, n_bytes):
+    """Record-aligned shard bounds S_0..S_G from the gathered states (pure).  S_k = offset of the first line that starts
+    in [lo_k, hi_k) and whose absolute index is a multiple of 4; a shard without one is empty (S_k = S_{k+1})."""
+    G = len(states)
+    bounds = [0] * G + [int(n_bytes)]
+    first = [None] * G
+    lines_before = 0
+    for k in range(G):
+        lo, hi = int(states[k][LO]), int(states[k][HI])
+        ls = [int(x) for x in states[k][LS0:LS0 + N_LS] if int(x) >= 0]
+        if ls:
+            # index of the first line that starts inside the shard: the line open at lo is `lines_before`; it starts
+            # inside the shard only if it starts AT lo
+            idx0 = lines_before if ls[0] == lo else lines_before + 1
+            j = (-idx0) % 4
+            if j < len(ls) and ls[j] < hi:
+                first[k] = ls[j]
+        lines_before += int(states[k][NEWLINES])
+    for k in range(G - 1, -1, -1):
+        bounds[k] = first[k] if first[k] is not None else bounds[k + 1]
+    return bounds
+
+
+def fasta_record_bounds(first_headers, n_bytes):
+    """S_0..S_G for FASTA: first_headers[k] = offset of the first line-initial '>' in [lo_k, hi_k), or -1."""
+    G = len(first_headers)
+    bounds = [0] * G + [int(n_bytes)]
+    for k in range(G - 1, -1, -1):
+        bounds[k] = int(first_headers[k]) if int(first_headers[k]) >= 0 else bounds[k + 1]
+    return bounds
+
+
+# ------------------------------------------------------------------ device side
+class Shard:
+    """A shard's bytes in HBM: file bytes [lo - begin, hi) so that file byte lo sits at local offset `begin`
+    (0 for the first shard, HALO for the others)."""
+
+    def __init__(self, buf, lo, hi, begin, is_last):
+        self.buf, self.lo, self.hi, self.begin, self.is_last = buf, int(lo), int(hi), int(begin), bool(is_last)
+        self.n = self.begin + (self.hi - self.lo)
+
+    @staticmethod
+    def from_bytes(data, rank, world, device):
+        """Cut rank's shard out of a host image of the whole file (tests / tools; a real host preads just this range)."""
+        from . import device as D
+
+        lo, hi = byte_range(len(data), rank, world)
+        begin = 0 if rank == 0 else HALO
+        halo = bytes(max(0, begin - lo)) + bytes(data[max(0, lo - begin):lo]) if begin else b""
+        return Shard(D.to_device(halo + bytes(data[lo:hi]), device), lo, hi, begin, rank == world - 1)
+
+
+def _result_block(ws):
+    """The scan's 128-byte result block (first bytes of its workspace) viewed as 16 int64 words, on the device."""
+    import torch
+
+    return ws[:128].view(torch.int64)
+
+
+def _state_from_block(words, lo, hi, begin, line_starts=()):
+    # exb_scan_result: total_lines, open_line_start, err_pos, overflow|pad, n_records, seq_bytes, gc_total, tail_s, tail_g
+    pad = (int(words[3]) >> 32) & 3
+    return state_row(lo, hi, begin, int(words[0]), int(words[1]), int(words[7]), int(words[8]), pad, line_starts)
+
+
+class ShardedFastqCount:
+    """SELECT COUNT(*), sums FROM read_fastq(file) WHERE <quality-line predicates> over this rank's shard of the file.
+
+    step() enqueues, with no host round trip: fused scan (K1 + provisional resolve) -> all-gather of the 128-byte result
+    blocks -> exb_fastq_compose_prev (device) -> resolve kernel -> all-reduce of the aggregates.  `total` (int64[8],
+    device) then holds the GLOBAL aggregates on every rank: [0] passing records, [3] sum of their Phred sums, [4] sum of
+    their quality lengths, [6] lines of the file mod 4 (must be 0), [7] shards that met a malformed record (must be 0)."""
+
+    def __init__(self, shard, preds, group, ranges=None):
+        import torch
+
+        from . import device as D
+
+        self.shard, self.preds, self.group = shard, list(preds), group
+        dev = shard.buf.device
+        self.c = D.FastqCount()
+        self.c.agg = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.c.ws = D.workspace(shard.n + 16, dev)
+        self.c.buf, self.c.n = shard.buf, shard.n
+        self.total = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.true_prev = torch.zeros(128, dtype=torch.uint8, device=dev)
+        self.prov = None
+        if shard.begin:  # provisional predecessor: "no line is open before `begin`"
+            r = _lib.ScanResult()
+            r.open_line_start = shard.begin
+            r.err_pos = _lib.NO_POS
+            self.prov = torch.zeros(128, dtype=torch.uint8, device=dev)
+            _lib.check(_lib.lib().exb_scan_result_store(D._ptr(self.prov), C.byref(r), D._stream()))
+        self.arr, self.k = _lib.predicates(self.preds)
+        # every shard's (lo, hi, begin): static, exchanged once
+        self.ranges = np.asarray(ranges if ranges is not None else group.all_gather_rows([shard.lo, shard.hi, shard.begin]), dtype=np.int64)
+        self.world = len(self.ranges)
+        self.d_ranges = torch.from_numpy(self.ranges.copy()).to(dev)
+        self.blocks = torch.zeros(self.world * RESULT_WORDS, dtype=torch.int64, device=dev)
+
+    # -- the phases (tests drive them shard by shard through a LocalGroup-style loop; step() chains them for a TorchGroup)
+    def scan(self):
+        """K1 + provisional resolve; returns the shard's result block (int64[16] view of the workspace, on the device)."""
+        from . import device as D
+
+        s = self.shard
+        _lib.check(_lib.lib().exb_fastq_scan_filter(D._ptr(s.buf), s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.prov), self.arr, self.k,
+                                                    D._ptr(self.c.agg), 0, D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
+        self.c._res = None
+        return _result_block(self.c.ws)
+
+    def states_from(self, blocks):
+        """Host view of gathered blocks as state rows (diagnostics / the host mirror compose_prev)."""
+        return [_state_from_block(blocks[j], *self.ranges[j]) for j in range(len(blocks))]
+
+    def resolve(self, blocks, rank):
+        """blocks: int64[world * 16] device tensor, every shard's result block in shard order."""
+        from . import device as D
+
+        s = self.shard
+        if rank > 0:
+            L = _lib.lib()
+            _lib.check(L.exb_fastq_compose_prev(D._ptr(blocks), D._ptr(self.d_ranges), self.world, rank, D._ptr(self.true_prev), D._stream()))
+            _lib.check(L.exb_fastq_scan_filter_resolve(s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.true_prev), self.arr, self.k,
+                                                       D._ptr(self.c.agg), 0, D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
+            self.c._res = None
+        blk = _result_block(self.c.ws)
+        self.total.copy_(self.c.agg)
+        self.total[7] = (blk[2] != 0).to(self.total.dtype)  # device err_pos word: 0 = no malformed record
+        self.total[6] = (blk[0] & 3) if s.is_last else 0
+        return self.total
+
+    def step(self):
+        g = self.group
+        blk = self.scan()
+        g.dist.all_gather_into_tensor(self.blocks, blk, group=g.group)
+        self.resolve(self.blocks, g.rank)
+        g.all_reduce_sum(self.total)
+        return self.total
+
+
+def check_count(total):
+    """Raise for a malformed / truncated file; returns the aggregates as a list of ints."""
+    from .device import FormatError
+
+    t = [int(x) for x in total.tolist()]
+    if t[7]:
+        raise FormatError("malformed FASTQ record (in %d shard(s))" % t[7])
+    if t[6]:
+        raise FormatError("truncated FASTQ record: the file's line count is not a multiple of 4")
+    return t
+
+
+def fastq_shard_state(shard):
+    """State row of a shard for fastq_record_bounds: newline count + the first N_LS line starts (one line-only scan, no
+    per-record output; TAIL_S / TAIL_G are not computed by that flavour and must not be used from this row)."""
+    import torch
+
+    from . import device as D
+
+    dev = shard.buf.device
+    line_end = torch.empty(N_LS, dtype=torch.int64, device=dev)
+    ws = torch.empty(_lib.lib().exb_fastq_workspace_bytes(shard.n + 16, shard.n // 24 + 16384), dtype=torch.uint8, device=dev)
+    prov = None
+    if shard.begin:
+        r = _lib.ScanResult()
+        r.open_line_start = shard.begin
+        r.err_pos = _lib.NO_POS
+        prov = torch.zeros(128, dtype=torch.uint8, device=dev)
+        _lib.check(_lib.lib().exb_scan_result_store(D._ptr(prov), C.byref(r), D._stream()))
+    for attempt in range(2):
+        _lib.check(_lib.lib().exb_fastq_scan(D._ptr(shard.buf), shard.begin, shard.n, 0, D._ptr(prov), N_LS, _lib.F_LINES, D._ptr(line_end), N_LS, 1,
+                                             None, None, None, None, 0, D._ptr(ws), ws.numel(), D._stream()))
+        res = D.fetch_result(ws)
+        if not res.overflow:
+            break
+        ws = torch.empty(_lib.lib().exb_fastq_workspace_bytes(shard.n + 16, shard.n + 1), dtype=torch.uint8, device=dev)
+    k = min(N_LS, int(res.total_lines))
+    ends = line_end[:k].cpu().tolist() if k else []
+    prev_byte = int(shard.buf[shard.begin - 1].item()) if shard.begin and shard.lo > 0 else None
+    ls = []
+    if shard.hi > shard.lo and (shard.lo == 0 or prev_byte == 10):
+        ls.append(shard.lo)
+    for e in ends:
+        g = shard.lo + (int(e) - shard.begin) + 1
+        if g < shard.hi and len(ls) < N_LS:
+            ls.append(g)
+    return state_row(shard.lo, shard.hi, shard.begin, res.total_lines, res.open_line_start, res.tail_s, res.tail_g, res.pad, ls)
+
+
+def fasta_first_header(shard, window=1 << 20):
+    """Offset in the file of the first line-initial '>' in [lo, hi), or -1 (scans a growing window of the shard)."""
+    import torch
+
+    from . import device as D
+
+    dev = shard.buf.device
+    cap = 4096
+    arrs = [torch.empty(cap + 1, dtype=torch.int64, device=dev) for _ in range(4)]
+    b0 = shard.begin - 1 if shard.begin and shard.lo > 0 else shard.begin  # one byte back: is `lo` the start of a line?
+    w = window
+    while True:
+        end = min(shard.n, shard.begin + w)
+        ws = D.workspace(end + 16, dev)
+        _lib.check(_lib.lib().exb_fasta_scan(D._ptr(shard.buf), b0, end, 1 if (end == shard.n and shard.is_last) else 0, shard.n, None,
+                                             D._ptr(arrs[0]), D._ptr(arrs[1]), D._ptr(arrs[2]), D._ptr(arrs[3]), cap, None, 0,
+                                             D._ptr(ws), ws.numel(), D._stream()))
+        res = D.fetch_result(ws)
+        k = min(cap, int(res.n_records))
+        if k:
+            hs = arrs[0][:k].cpu().numpy()
+            hs = hs[hs >= shard.begin]
+            if hs.size:
+                return shard.lo + int(hs[0]) - shard.begin
+        if end == shard.n:
+            return -1
+        w *= 4

@@ -259,6 +259,34 @@ EXB_API int exb_fastq_scan_filter(const void *d_buf, int64_t begin, int64_t n, i
                                   const exb_predicate *preds, int n_preds, int64_t *d_agg, int accumulate,
                                   void *d_workspace, int64_t workspace_bytes, void *stream);
 
+/*
+ * Byte-range shards and any other case where the state BEFORE a range is only known after the range
+ * has been read: K1 of the scan (the byte pass) never depends on that state, so
+ *   1. run exb_fastq_scan / exb_fastq_scan_filter on the range with a PROVISIONAL predecessor (a 128-byte device
+ *      block written by exb_scan_result_store from a zeroed exb_scan_result whose open_line_start = begin), fetch the
+ *      result: total_lines = newlines in the range, open_line_start / tail_s / tail_g / pad = its open last line;
+ *   2. exchange those blocks (one all-gather of 88 bytes per shard), compose the true predecessor state;
+ *   3. call the matching *_resolve function with the same begin / n / outputs / workspace and the true predecessor:
+ *      only the light second kernel runs again (8 bytes per line, or 48 bytes per tile for the fused flavour); the
+ *      input bytes are not read a second time.  d_agg / per-record outputs of step 1 are overwritten.
+ * exon_duckdb_b200/dist.py is the host side of this protocol.
+ */
+EXB_API int exb_fastq_scan_resolve(int64_t begin, int64_t n, int is_final, const void *d_prev_workspace, uint64_t max_lines,
+                                   int flags, void *d_line_end, int64_t line_cap, int wide_offsets, uint32_t *d_seq_len,
+                                   uint32_t *d_gc, uint32_t *d_qual_len, int32_t *d_qsum, int64_t rec_cap,
+                                   void *d_workspace, int64_t workspace_bytes, void *stream);
+EXB_API int exb_fastq_scan_filter_resolve(int64_t begin, int64_t n, int is_final, const void *d_prev_workspace,
+                                          const exb_predicate *preds, int n_preds, int64_t *d_agg, int accumulate,
+                                          void *d_workspace, int64_t workspace_bytes, void *stream);
+/* Step 2 on the device (no host round trip): d_blocks = the result blocks of all `world` shards in shard order
+ * (128 bytes each, e.g. the output of an NCCL all-gather of the first 128 bytes of each shard's workspace), d_ranges =
+ * int64[world][3] {lo, hi, begin} of every shard (file offsets of its range; local offset of byte lo).  Writes the true
+ * predecessor of shard `rank` (>= 1) to d_prev_out (128 bytes), ready to be passed as d_prev_workspace. */
+EXB_API int exb_fastq_compose_prev(const void *d_blocks, const int64_t *d_ranges, int world, int rank, void *d_prev_out,
+                                   void *stream);
+/* Writes *src where a scan expects a predecessor's result block (d_dst: >= 128 bytes of device memory). */
+EXB_API int exb_scan_result_store(void *d_dst, const exb_scan_result *src, void *stream);
+
 /* Field extents of FASTQ records from the line index: d_lens is uint32_t[4][n_records]
  * (name, description, sequence, quality_scores); d_desc_valid uint8_t[n_records]
  * (0 = NULL description).  d_sel (optional) lists the records to take; d_starts (optional)

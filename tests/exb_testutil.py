@@ -89,3 +89,60 @@ def random_fasta(seed, n_records, min_len=0, max_len=500, wrap=60, crlf=False, f
     eol = b"\r\n" if crlf else b"\n"
     text = fasta_text(recs, wrap, eol, final_eol, blank_lines=tricky, rng=rng)
     return text, recs
+
+
+# ---------------------------------------------------------------- host stand-ins for the shard exchange (tests only)
+def host_shard_state(data, lo, hi, begin=16):
+    """What a shard's scan reports about bytes [lo, hi) of `data`, computed on the host with numpy: the stand-in the CPU
+    tests feed into exon_duckdb_b200.dist's composition rules (the product computes the same row on the device)."""
+    import numpy as np
+
+    from exon_duckdb_b200 import dist
+
+    v = np.frombuffer(bytes(data[lo:hi]), dtype=np.uint8)
+    nl = np.flatnonzero(v == 10)
+    open_start = lo + (int(nl[-1]) + 1 if nl.size else 0)
+    tail = v[open_start - lo:]
+    tail_s = int(tail.astype(np.int8).astype(np.int64).sum())
+    tail_g = int(((tail == ord("G")) | (tail == ord("C"))).sum())
+    flags = 0
+    if open_start < hi:
+        b = data[open_start]
+        flags = 2 if b == ord("@") else (1 if b == ord("+") else 0)
+    ls = []
+    if hi > lo and (lo == 0 or data[lo - 1] == 10):
+        ls.append(lo)
+    for p in nl[: dist.N_LS]:
+        if lo + int(p) + 1 < hi and len(ls) < dist.N_LS:
+            ls.append(lo + int(p) + 1)
+    local_open = begin + (open_start - lo)
+    return dist.state_row(lo, hi, begin, int(nl.size), local_open, tail_s, tail_g, flags, ls)
+
+
+def sequential_state_at(data, pos):
+    """Ground truth of the scan state just before byte `pos`: (lines before, start of the open line, byte sum, G/C, flags)."""
+    import numpy as np
+
+    v = np.frombuffer(bytes(data[:pos]), dtype=np.uint8)
+    nl = np.flatnonzero(v == 10)
+    start = int(nl[-1]) + 1 if nl.size else 0
+    tail = v[start:]
+    flags = 0
+    if start < pos:
+        flags = 2 if data[start] == ord("@") else (1 if data[start] == ord("+") else 0)
+    return int(nl.size), start, int(tail.astype(np.int8).astype(np.int64).sum()), int(((tail == 71) | (tail == 67)).sum()), flags
+
+
+def fastq_record_starts(data):
+    """Offsets of the first byte of every record of a well-formed FASTQ (every 4th line start)."""
+    starts, pos, line = [], 0, 0
+    n = len(data)
+    while pos < n:
+        if line % 4 == 0:
+            starts.append(pos)
+        nxt = data.find(b"\n", pos)
+        if nxt < 0:
+            break
+        pos = nxt + 1
+        line += 1
+    return starts
