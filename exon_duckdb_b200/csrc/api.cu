@@ -146,7 +146,9 @@ int exb_device_available(void) {
 
 int64_t exb_scan_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
-    const int64_t cta_tiles = WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);  // FASTA scan, offset scans
+    int64_t cta_tiles = WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);  // offset scans
+    const int64_t fasta = WS_HEADER + fasta_workspace_payload(fasta_scan_tiles(0, n + 16, 1) + 1);  // FASTA scan
+    if (fasta > cta_tiles) cta_tiles = fasta;
     const int64_t fastq = fastq_workspace_bytes(n, n / 24 + 16384);  // FASTQ scan: lines of >= 24 bytes on average
     return cta_tiles > fastq ? cta_tiles : fastq;
 }
@@ -258,7 +260,9 @@ int64_t exb_fastq_workspace_bytes(int64_t n, int64_t max_lines) {
     if (n < 0) n = 0;
     if (max_lines < 0) max_lines = 0;
     if (max_lines > n + 1) max_lines = n + 1;
-    const int64_t generic = WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);
+    int64_t generic = WS_HEADER + (n / TILE_BYTES + 3) * (int64_t)sizeof(TileSlot);
+    const int64_t fasta = WS_HEADER + fasta_workspace_payload(fasta_scan_tiles(0, n + 16, 1) + 1);
+    if (fasta > generic) generic = fasta;
     const int64_t fastq = fastq_workspace_bytes(n, max_lines);
     return generic > fastq ? generic : fastq;
 }
@@ -416,14 +420,17 @@ int exb_fasta_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, in
     a.prev = reinterpret_cast<const ScanResult*>(d_prev_workspace);
     a.is_final = is_final ? 1 : 0;
     a.halo_n = halo_n > n ? halo_n : n;
-    a.n_tiles = tiles_for(begin, n, a.is_final);
+    a.n_tiles = fasta_scan_tiles(begin, n, a.is_final);
     if (d_prev_workspace == d_workspace) return set_err(EXB_ERR_ARG, "exb_fasta_scan: d_prev_workspace must differ from d_workspace");
-    Workspace w;
-    int rc = carve(d_workspace, workspace_bytes, a.n_tiles, st, &w);
-    if (rc) return rc;
-    a.slots = w.slots;
-    a.ticket = w.ticket;
-    a.result = w.result;
+    if (d_prev_workspace && (begin & 15) != 0) return set_err(EXB_ERR_ARG, "exb_fasta_scan: `begin` of a chained range must be a multiple of 16");
+    if (!d_workspace || ((uintptr_t)d_workspace & 15) != 0) return set_err(EXB_ERR_ARG, "exb_fasta_scan: d_workspace must be 16-byte aligned");
+    const int64_t need = WS_HEADER + fasta_workspace_payload(a.n_tiles);
+    if (workspace_bytes < need)
+        return set_err(EXB_ERR_ARG, "exb_fasta_scan: workspace too small: need %lld bytes, have %lld", (long long)need, (long long)workspace_bytes);
+    cudaError_t e0 = cudaMemsetAsync(d_workspace, 0, (size_t)WS_HEADER, st);  // result block (err_pos / overflow accumulate)
+    if (e0 != cudaSuccess) return cuda_fail(e0, "cudaMemsetAsync(workspace header)");
+    a.result = reinterpret_cast<ScanResult*>(d_workspace);
+    a.payload = reinterpret_cast<uint8_t*>(d_workspace) + WS_HEADER;
     a.hdr_start = d_hdr_start;
     a.hdr_end = d_hdr_end;
     a.seq_off = d_seq_off;

@@ -76,15 +76,19 @@ cudaError_t fastq_emit_launch(const FastqScanArgs& a, int flags, bool wide_offse
 int64_t fastq_scan_tiles(int64_t begin, int64_t n, int is_final);  // 4 KiB warp tiles
 int64_t fastq_record_slack(int64_t n_tiles);                       // record slots the bump allocation may waste
 
+struct FaTile;
 struct FastaScanArgs {
     const uint8_t* buf;
     int64_t begin, n;
     const ScanResult* prev;
     int is_final;
     int64_t halo_n;             // bytes of buf that are readable (>= n): the CRLF test looks one byte ahead
-    int64_t n_tiles;
-    TileSlot* slots;
-    unsigned long long* ticket;
+    int64_t n_tiles;            // 4 KiB warp tiles
+    int64_t tma_rows;           // 128-byte rows the tensor map covers (set by the launcher)
+    void* payload;              // workspace behind the header: fasta_workspace_payload(n_tiles) bytes, carved by the launcher
+    FaTile* tiles;              // [n_tiles] K1's summaries
+    uint8_t* tile_state;        // [n_tiles] state at the tile's first byte | 4 = the tile has per-record outputs
+    int64_t* tile_base3;        // [n_tiles][3] records / kept bytes / G,C before the tile
     ScanResult* result;
     // per record r (single writer = the thread that owns the '>' / the header's newline)
     int64_t* hdr_start;         // offset of '>'
@@ -97,5 +101,7 @@ struct FastaScanArgs {
 };
 
 cudaError_t fasta_scan_launch(const FastaScanArgs& a, int flags, cudaStream_t st);
+int64_t fasta_scan_tiles(int64_t begin, int64_t n, int is_final);
+int64_t fasta_workspace_payload(int64_t n_tiles);
 
 }  // namespace exb
