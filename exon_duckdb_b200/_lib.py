@@ -106,7 +106,7 @@ SIGNATURES = {
     "exb_fastq_gather": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "exb_fasta_scan": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "exb_fasta_headers": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "exb_gather_ranges": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "exb_gather_ranges": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_gc_from_prefix": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_gc_from_counts": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_gc_content": (_i32, [_vp, _vp, _i64, _vp, _vp]),

@@ -21,7 +21,7 @@ cudaError_t fastq_fields_launch(const uint8_t*, int64_t, int64_t, const void*, b
                                 int64_t*, cudaStream_t);
 cudaError_t fastq_gather_launch(const uint8_t*, int64_t, int64_t, const void*, bool, const int64_t*, int64_t, int, const uint32_t*,
                                 const int64_t*, uint8_t*, cudaStream_t);
-cudaError_t gather_ranges_launch(const uint8_t*, const int64_t*, const uint32_t*, const int64_t*, int64_t, uint8_t*, cudaStream_t);
+cudaError_t gather_ranges_launch(const uint8_t*, const int64_t*, const uint32_t*, const int64_t*, int64_t, int64_t, uint8_t*, cudaStream_t);
 cudaError_t fastq_filter_launch(const uint32_t*, const uint32_t*, const uint32_t*, const int32_t*, int64_t, const exb_predicate*, int,
                                 uint8_t*, int64_t*, const void*, cudaStream_t);
 cudaError_t fasta_headers_launch(const uint8_t*, const int64_t*, const int64_t*, int64_t, int64_t, uint32_t*, int64_t*, uint8_t*,
@@ -455,8 +455,11 @@ int exb_fasta_headers(const void* d_buf, int64_t n, const int64_t* d_hdr_start, 
 }
 
 int exb_gather_ranges(const void* d_buf, const int64_t* d_start, const uint32_t* d_len, const int64_t* d_off, int64_t n_rows,
-                      uint8_t* d_out, void* stream) {
-    cudaError_t e = gather_ranges_launch(reinterpret_cast<const uint8_t*>(d_buf), d_start, d_len, d_off, n_rows, d_out, (cudaStream_t)stream);
+                      uint8_t* d_out, int64_t out_bytes, void* stream) {
+    if (n_rows < 0 || out_bytes < 0 || (n_rows > 0 && (!d_buf || !d_start || !d_off || !d_out)))
+        return set_err(EXB_ERR_ARG, "exb_gather_ranges: bad arguments");
+    cudaError_t e = gather_ranges_launch(reinterpret_cast<const uint8_t*>(d_buf), d_start, d_len, d_off, n_rows, out_bytes, d_out,
+                                         (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gather_ranges launch");
     return 0;
 }

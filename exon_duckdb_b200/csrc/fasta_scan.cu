@@ -181,6 +181,30 @@ __device__ __forceinline__ void fa_fix_edges(const FastaScanArgs& a, uint8_t* sb
     __syncwarp();
 }
 
+// Copy `len` bytes from tile position `src` (128B-swizzled buffer) to staging offset `dst`: dst-aligned 4-byte words in
+// the body (two aligned source words + funnel shift), bytes at the ragged ends.  Work items first, first + step, ...
+// so that one lane (0, 1) or a whole warp (lane, 32) can run the same line.
+__device__ __forceinline__ void fa_copy(uint8_t* s_out, const uint8_t* sbytes, int dst, int src, int len, int first, int step) {
+    int head = (4 - (dst & 3)) & 3;
+    if (head > len) head = len;
+    for (int i = first; i < head; i += step) s_out[dst + i] = sbytes[sidx(src + i)];
+    dst += head;
+    src += head;
+    len -= head;
+    const int nw = len >> 2;
+    const int bs = (src & 3) * 8, sa = src & ~3;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(s_out + dst);
+    for (int k = first; k < nw; k += step) {
+        const int p0 = sa + 4 * k;
+        const int p1 = p0 + 4 < WT_BYTES ? p0 + 4 : p0;  // bs == 0 whenever the clamp matters (the line ends at the tile's end)
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(sbytes + sidx(p0));
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(sbytes + sidx(p1));
+        ow[k] = __funnelshift_r(w0, w1, bs);
+    }
+    const int done = nw * 4;
+    for (int i = done + first; i < len; i += step) s_out[dst + i] = sbytes[sidx(src + i)];
+}
+
 // ---------------------------------------------------------------- the tile analysis (shared by K1 / K2 / K3)
 // MODE 0: summary.  MODE 1: per-record outputs (state and bases known).  MODE 2: compaction (state and kept base known).
 struct FaTileIn {  // what K2 / K3 know about the tile from the scan
@@ -351,9 +375,7 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
             if (MODE == 2 && active && !line_is_hdr && len > 0) {  // copy the line to its place in the staging row
                 const int dst = (int)(kept_before - in.kept_base) + (int)(in.kept_base & 15);
                 const int src = ppos + 1;
-                if (len <= 192u) {
-                    for (uint32_t i = 0; i < len; i++) s_out[dst + i] = sbytes[sidx(src + (int)i)];
-                }
+                if (len <= 192u) fa_copy(s_out, sbytes, dst, src, (int)len, 0, 1);
             }
             if (MODE == 2) {  // long lines: the whole warp copies them, one after the other
                 uint32_t longs = __ballot_sync(0xffffffffu, active && !line_is_hdr && len > 192u);
@@ -363,7 +385,7 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
                     const int dst = (int)(__shfl_sync(0xffffffffu, kept_before, l) - in.kept_base) + (int)(in.kept_base & 15);
                     const int src = __shfl_sync(0xffffffffu, ppos, l) + 1;
                     const int ln = (int)__shfl_sync(0xffffffffu, len, l);
-                    for (int i = lane; i < ln; i += 32) s_out[dst + i] = sbytes[sidx(src + i)];
+                    fa_copy(s_out, sbytes, dst, src, ln, lane, 32);
                 }
             }
             run_kept += (int64_t)(tot2 >> 40);
@@ -423,7 +445,7 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
         if (!tail_is_hdr && tail_len > 0) {
             const int dst = (int)(run_kept - in.kept_base) + (int)(in.kept_base & 15);
             const int src = c_pos + 1;
-            for (int i = lane; i < tail_len; i += 32) s_out[dst + i] = sbytes[sidx(src + i)];
+            fa_copy(s_out, sbytes, dst, src, tail_len, lane, 32);
             run_kept += tail_len;
         }
         __syncwarp();

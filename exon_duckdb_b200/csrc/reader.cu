@@ -467,7 +467,7 @@ struct Reader {
             if (!cu(cudaStreamSynchronize(st), "sync")) return false;
             const int64_t total = h_off.as<int64_t>()[n];
             if (!d_data.need(total + 16) || !h_data.need(total + 16)) return fail("out of memory");
-            if (!rc(exb_gather_ranges(col_buf[c], d_st + (int64_t)c * n, d_ln + (int64_t)c * n, d_off.as<int64_t>(), n, d_data.as<uint8_t>(), st)))
+            if (!rc(exb_gather_ranges(col_buf[c], d_st + (int64_t)c * n, d_ln + (int64_t)c * n, d_off.as<int64_t>(), n, d_data.as<uint8_t>(), total, st)))
                 return false;
             if (total > 0 && !cu(cudaMemcpyAsync(h_data.p, d_data.p, (size_t)total, cudaMemcpyDeviceToHost, st), "D2H data")) return false;
             if (!cu(cudaStreamSynchronize(st), "sync")) return false;

@@ -253,10 +253,13 @@ def fastq_table(buf, columns=None, preds=(), n=None):
     wide = 1 if scan.wide else 0
     check(lib().exb_fastq_fields(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, _ptr(lens), _ptr(valid), None, _stream()))
     out = {}
-    for name in columns:
+    # offsets of every requested column first, then ONE host round trip for the column sizes
+    offs = {name: exclusive_scan_u32(lens[FASTQ_COLUMNS.index(name) * n_rows:(FASTQ_COLUMNS.index(name) + 1) * n_rows] if n_rows else lens, n_rows)
+            for name in columns}
+    totals = torch.stack([offs[name][n_rows] for name in columns]).cpu().tolist() if columns else []
+    for name, total in zip(columns, totals):
         c = FASTQ_COLUMNS.index(name)
-        off = exclusive_scan_u32(lens[c * n_rows:(c + 1) * n_rows] if n_rows else lens, n_rows)
-        total = int(off[n_rows].item())
+        off = offs[name]
         data = _empty(total, torch.uint8, dev)
         check(lib().exb_fastq_gather(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, c, _ptr(lens), _ptr(off),
                                      _ptr(data), _stream()))
@@ -340,7 +343,7 @@ def fasta_table(buf, columns=None, n=None):
             total = int(off[n_rows].item())
             data = _empty(total, torch.uint8, dev)
             start = starts[c * n_rows:(c + 1) * n_rows] if n_rows else starts
-            check(lib().exb_gather_ranges(_ptr(buf), _ptr(start), _ptr(ln), _ptr(off), n_rows, _ptr(data), _stream()))
+            check(lib().exb_gather_ranges(_ptr(buf), _ptr(start), _ptr(ln), _ptr(off), n_rows, _ptr(data), total, _stream()))
             out[name] = Column(off, data, valid if c == 1 else None)
     if "sequence" in columns:
         out["sequence"] = Column(s.seq_off[:n_rows + 1], s.seq[:int(s.result.seq_bytes)])

@@ -335,9 +335,11 @@ EXB_API int exb_fasta_headers(const void *d_buf, int64_t n, const int64_t *d_hdr
                               int64_t n_rows, uint32_t *d_lens, int64_t *d_starts, uint8_t *d_desc_valid,
                               uint64_t *d_err_pos, void *stream);
 
-/* Generic gather of byte ranges: d_out[d_off[i] .. +d_len[i]) = d_buf[d_start[i] ..). */
+/* Generic gather of byte ranges: d_out[d_off[i] .. d_off[i+1]) = d_buf[d_start[i] ..).  d_off = the exclusive prefix sum
+ * of the row lengths, n_rows + 1 entries (exb_exclusive_scan_u32); out_bytes = size of d_out (>= d_off[n_rows]).
+ * d_len is unused (kept for symmetry with the other calls; may be NULL). */
 EXB_API int exb_gather_ranges(const void *d_buf, const int64_t *d_start, const uint32_t *d_len,
-                              const int64_t *d_off, int64_t n_rows, uint8_t *d_out, void *stream);
+                              const int64_t *d_off, int64_t n_rows, uint8_t *d_out, int64_t out_bytes, void *stream);
 
 /* gc_content per record from FASTA scan prefixes: out[r] = (float)gc / (float)len, '' -> 0. */
 EXB_API int exb_gc_from_prefix(const int64_t *d_seq_off, const int64_t *d_gc_prefix, int64_t n_rows, float *d_out,
