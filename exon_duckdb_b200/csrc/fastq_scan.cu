@@ -42,6 +42,8 @@
 // tile of directory; the fused flavour: input once + 60 B per tile.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tma_tile.cuh"
 #include "exon_b200_internal.h"
@@ -51,7 +53,6 @@ namespace exb {
 
 constexpr int FQ_WARPS = 4;     // warps per CTA (independent of each other)
 constexpr int FQ_THREADS = FQ_WARPS * 32;
-constexpr int EV_CAP = 64;      // newline positions held at once (2 passes of 32)
 constexpr int REC_BLOCK = 512;  // records a warp reserves per bump allocation
 
 // ---------------------------------------------------------------- tail word
@@ -89,41 +90,56 @@ __device__ __forceinline__ int rec_pg(uint32_t y) { return (int)(y >> 15); }
 template <int FLAGS>
 struct FqWarpAux {
     static constexpr bool kSeq = (FLAGS & EXB_F_SEQ) != 0, kQual = (FLAGS & EXB_F_QUAL) != 0;
-    static constexpr int off_cpre = 0;                                   // int[256]: byte-sum prefix at each 16-byte chunk
-    static constexpr int off_gm = off_cpre + (kQual ? 256 * 4 : 0);      // u64[64]: G/C mask of each 64-byte half row
-    static constexpr int off_gex = off_gm + (kSeq ? 64 * 8 : 0);         // int[64]: G/C prefix at each half row
-    static constexpr int off_ev = off_gex + (kSeq ? 64 * 4 : 0);         // u16[EV_CAP + 2]: newline positions (+ a dump slot)
-    static constexpr int off_bar = off_ev + EV_CAP * 2 + 16;             // 2 mbarriers
+    static constexpr int off_cpre = 0;                                   // int[256]: byte-sum prefix at each 16-byte chunk (lane l owns [8l, 8l+8))
+    static constexpr int off_bar = off_cpre + (kQual ? 256 * 4 : 0);     // 2 mbarriers
     static constexpr int total = off_bar + 16;
     // the kernel has no static shared memory, so the dynamic region starts right after the 1 KiB the system
     // reserves per CTA: 1024-byte aligned, which the 128B swizzle needs (the kernel traps if that ever changes)
     static constexpr int off_wlut = FQ_WARPS * (2 * WT_BYTES + total);   // uint4[17], shared by the CTA
-    static constexpr int cta_bytes = off_wlut + 17 * 16;
+    static constexpr int off_preds = off_wlut + 17 * 16;                 // exb_predicate[EXB_MAX_PREDICATES] (fused flavour)
+    static constexpr int off_nflut = off_preds + EXB_MAX_PREDICATES * (int)sizeof(exb_predicate);  // u8[256]: byte -> '@' (2) / '+' (1) flags
+    static constexpr int cta_bytes = off_nflut + 256;
 };
 
-// single-predicate fast path of the fused flavour, resolved once per kernel
+// single-predicate fast paths of the fused flavour, resolved once per kernel
 struct FusedPlan {
-    int simple;  // 1: exactly one EXB_P_MEAN_QUALITY predicate with op in {>, >=, <, <=}
+    int simple;    // 1: exactly one EXB_P_MEAN_QUALITY predicate with op in {>, >=, <, <=}; 2: and c * 2^20 is a 32-bit integer
     double c;
     int want_pos;  // verdict = (d > 0) == want_pos when |d| is clear of rounding
     int op;
+    int c20;       // simple == 2: c * 2^20
+    int mul_q, mul_n;  // i32 != 0: e = sum * mul_q + n * mul_n has the sign of the verdict, exactly, in 32 bits
+    int i32;
 };
 
-__device__ __forceinline__ bool fused_pass(const FastqScanArgs& a, const FusedPlan& plan, int qs, uint32_t len) {
-    if (plan.simple) {
+// the general form: any number of predicates, any constant (out of line, scalar arguments only: the hot loop
+// inlines just the integer fast path).  `preds` points to shared memory.
+__device__ __noinline__ bool fused_pass_general(const exb_predicate* preds, int n_preds, int simple, double c, int op, int want_pos, int qs,
+                                                uint32_t len) {
+    if (simple) {
         if (len == 0) return false;
         // d = sum - c n with ONE rounding.  |sum| < 2^20 inside a tile, so |d| > 1e-7 puts the exact quotient more
         // than 40 ulp from c whatever |c n| is (see exb_mean_cmp): neither rounding of the x87 path can cross.
-        const double d = fma(-plan.c, (double)len, (double)qs);
-        if (fabs(d) > 1e-7) return (d > 0) == (plan.want_pos != 0);
-        return exb_mean_cmp_close((int64_t)qs, len, plan.op, plan.c);
+        const double d = fma(-c, (double)len, (double)qs);
+        if (fabs(d) > 1e-7) return (d > 0) == (want_pos != 0);
+        return exb_mean_cmp_close((int64_t)qs, len, op, c);
     }
     bool ok = true;
-    for (int i = 0; i < a.n_fused; i++) {
-        const exb_predicate p = a.fused[i];
+    for (int i = 0; i < n_preds; i++) {
+        const exb_predicate p = preds[i];
         ok = ok && (p.field == EXB_P_MEAN_QUALITY ? exb_mean_cmp((int64_t)qs, len, p.op, p.value) : exb_cmp((double)len, p.op, p.value));
     }
     return ok;
+}
+__device__ __forceinline__ bool fused_pass(const exb_predicate* preds, int n_preds, const FusedPlan& plan, int qs, uint32_t len) {
+    if (plan.simple == 2) {
+        // D = 2^20 (sum - c n), exact in 64-bit integers (|sum| < 2^20 and n <= 4096 inside a tile).  D != 0 means
+        // |sum - c n| >= 2^-20 > 1e-7: the exact quotient is more than 40 ulp from c (see exb_mean_cmp), so neither
+        // rounding of the x87 path can cross and the sign of D is the verdict.  (n = 0: D = 0 -> general form -> false.)
+        const long long D = ((long long)qs << 20) - (long long)plan.c20 * (long long)len;
+        if (D != 0) return (D > 0) == (plan.want_pos != 0);
+    }
+    return fused_pass_general(preds, n_preds, plan.simple, plan.c, plan.op, plan.want_pos, qs, len);
 }
 __device__ __forceinline__ FusedPlan make_plan(const FastqScanArgs& a) {
     FusedPlan p;
@@ -131,11 +147,32 @@ __device__ __forceinline__ FusedPlan make_plan(const FastqScanArgs& a) {
     p.c = 0;
     p.want_pos = 0;
     p.op = 0;
+    p.c20 = 0;
+    p.mul_q = p.mul_n = p.i32 = 0;
     if (a.n_fused == 1 && a.fused[0].field == EXB_P_MEAN_QUALITY && a.fused[0].op <= EXB_OP_LE) {
         p.simple = 1;
         p.c = a.fused[0].value;
         p.op = a.fused[0].op;
         p.want_pos = (p.op == EXB_OP_GT || p.op == EXB_OP_GE) ? 1 : 0;
+        const double s = p.c * 1048576.0;
+        if (fabs(s) < 2147483648.0 && s == rint(s)) {
+            p.simple = 2;
+            p.c20 = (int)s;
+            // c = cq / 2^sh with sh <= 10 and |cq| < 2^18: 2^sh (sum - c n) = sum 2^sh - cq n stays below 2^31 for
+            // |sum| < 2^20, n <= 4096 (one tile); multiplied by +-1 so that "e > 0" is "passes"
+            int sh = 20, cq = p.c20;
+            while (sh > 0 && (cq & 1) == 0) {
+                cq >>= 1;
+                sh--;
+            }
+            if (cq == 0) sh = 0;
+            if (sh <= 10 && cq > -(1 << 18) && cq < (1 << 18)) {
+                const int sgn = p.want_pos ? 1 : -1;
+                p.i32 = 1;
+                p.mul_q = sgn * (1 << sh);
+                p.mul_n = -sgn * cq;
+            }
+        }
     }
     return p;
 }
@@ -160,14 +197,15 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         };
         s_wlut[k] = make_uint4(w(0), w(4), w(8), w(12));
     }
+    exb_predicate* s_preds = reinterpret_cast<exb_predicate*>(smem_raw + AUX::off_preds);
+    if (kFused && threadIdx.x < a.n_fused) s_preds[threadIdx.x] = a.fused[threadIdx.x];
+    uint8_t* s_nflut = smem_raw + AUX::off_nflut;
+    for (int i = threadIdx.x; i < 256; i += FQ_THREADS) s_nflut[i] = (uint8_t)at_plus_flags(i);
 
     if (((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u) != 0) __trap();
     uint8_t* data0 = smem_raw + warp * (2 * WT_BYTES);
     uint8_t* aux = smem_raw + FQ_WARPS * (2 * WT_BYTES) + warp * AUX::total;
-    int* s_cpre = reinterpret_cast<int*>(aux + AUX::off_cpre);
-    uint64_t* s_gm = reinterpret_cast<uint64_t*>(aux + AUX::off_gm);
-    int* s_gex = reinterpret_cast<int*>(aux + AUX::off_gex);
-    uint16_t* ev_pos = reinterpret_cast<uint16_t*>(aux + AUX::off_ev);
+    int* s_cpre = reinterpret_cast<int*>(aux + AUX::off_cpre) + lane * 8;  // this lane's eight chunk prefixes
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(aux + AUX::off_bar);
     const uint32_t data0_u32 = (uint32_t)__cvta_generic_to_shared(data0);
     if (lane == 0) {
@@ -183,11 +221,10 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
     const int64_t full_rows = a.tma_rows;  // rows of 128 bytes that lie completely inside [origin, n): what the tensor map covers
     const uint32_t pat_nl = c7f & 0x0A0A0A0Au, pat_gc = c7f & 0x43434343u;  // derived from an argument: stay in registers
     const int64_t stride = (int64_t)gridDim.x * FQ_WARPS;
-    const FusedPlan plan = kFused ? make_plan(a) : FusedPlan{0, 0.0, 0, 0};
-    // fused: a line handled by lane l has tile-local index = l (mod 4): it is a header under hypothesis (0 - l) & 3
-    // and a plus line under (2 - l) & 3
-    const uint32_t bit_hdr = 1u << ((0 - lane) & 3), bit_plus = 1u << ((2 - lane) & 3);
+    const FusedPlan plan = kFused ? make_plan(a) : FusedPlan{0, 0.0, 0, 0, 0, 0, 0, 0};
     const int64_t lower = a.prev ? 0 : a.begin;  // first readable byte of the buffer
+    const int sw = lane & 7;                     // 128B swizzle: chunk c of row `lane` sits at chunk slot c ^ sw
+    const int row_off = lane * ROW_BYTES;
 
     // ---- staging of one tile into buffer b (asynchronous; one instruction from one lane)
     auto issue = [&](int64_t tile, int b) {
@@ -226,6 +263,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         // Rare edge tiles (uniform per warp): rows the tensor map does not cover, bytes before `begin`, the virtual '\n'
         const bool partial = row0 + WT_ROWS > full_rows;
         const bool has_begin_pad = (tile == 0 && a.begin != origin);
+        int virt = -1;  // tile-local position of the virtual '\n' that terminates an unterminated last line
         if (partial || has_begin_pad) {
             if (row0 >= full_rows) {  // nothing came through TMA: clear the buffer
                 for (int i = lane; i < WT_BYTES / 16; i += 32) reinterpret_cast<uint4*>(sbytes)[i] = make_uint4(0, 0, 0, 0);
@@ -247,14 +285,14 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes before this buffer's next TMA fill
             __syncwarp();
+            if (a.is_final && a.n >= tile_base && a.n < tile_base + WT_BYTES) virt = (int)(a.n - tile_base);
         }
 
         // ---- A. analysis of the lane's row: two 64-byte halves
         uint64_t pm[2], gm[2] = {0, 0};
-        int ex_cnt, n_events, ex_s = 0, total_s = 0, ex_g = 0, total_g = 0;
+        int ex_cnt, n_events, cnt, ex_s = 0, total_s = 0, ex_g = 0, total_g = 0, g0 = 0;
+        const uint4* row = d + lane * 8;
         {
-            const int sw = lane & 7;
-            const uint4* row = d + lane * 8;
             int acc = 0;
             int pre[8];
 #pragma unroll
@@ -276,68 +314,44 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                     gm[h] = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
                             (gc_mask16r(c0, c7b, c7f, pat_gc) | (gc_mask16r(c1, c7b, c7f, pat_gc) << 16));
             }
-            const int cnt = __popcll(pm[0]) + __popcll(pm[1]);
-            const int g0 = kSeq ? __popcll(gm[0]) : 0, g1 = kSeq ? __popcll(gm[1]) : 0;
-            // newlines and G/C (each <= 4096 per tile: 13 bits) share one scan word; the byte sums get their own
-            const uint32_t packed = ((uint32_t)cnt << 16) + (uint32_t)(g0 + g1);
-            const uint32_t incl = warp_incl_scan_u32(packed);
-            const uint32_t ex = incl - packed;
-            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-            ex_cnt = (int)(ex >> 16);
-            n_events = (int)(tot >> 16);
-            ex_g = (int)(ex & 0xFFFFu);
-            total_g = (int)(tot & 0xFFFFu);
+            cnt = __popcll(pm[0]) + __popcll(pm[1]);
+            g0 = kSeq ? __popcll(gm[0]) : 0;
+            const int g1 = kSeq ? __popcll(gm[1]) : 0;
+            if (kQual && !kSeq) {
+                // ONE scan: newline count << 20 | byte sum, the sum biased by 2^14 per lane so that it is never negative
+                // (a row of 128 signed bytes sums to [-2^14, 2^14); 32 rows stay below 2^20)
+                const uint32_t packed = ((uint32_t)cnt << 20) + (uint32_t)(acc + 16384);
+                const uint32_t incl = warp_incl_scan_u32(packed);
+                const uint32_t ex = incl - packed;
+                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                ex_cnt = (int)(ex >> 20);
+                n_events = (int)(tot >> 20);
+                ex_s = (int)(ex & 0xFFFFFu) - 16384 * lane;
+                total_s = (int)(tot & 0xFFFFFu) - 16384 * 32;
+            } else {
+                // newlines and G/C (each <= 4096 per tile: 13 bits) share one scan word; the byte sums get their own
+                const uint32_t packed = ((uint32_t)cnt << 16) + (uint32_t)(g0 + g1);
+                const uint32_t incl = warp_incl_scan_u32(packed);
+                const uint32_t ex = incl - packed;
+                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                ex_cnt = (int)(ex >> 16);
+                n_events = (int)(tot >> 16);
+                ex_g = (int)(ex & 0xFFFFu);
+                total_g = (int)(tot & 0xFFFFu);
+                if (kQual) {
+                    const uint32_t si = warp_incl_scan_u32((uint32_t)acc);
+                    ex_s = (int)(si - (uint32_t)acc);
+                    total_s = (int)__shfl_sync(0xffffffffu, si, 31);
+                }
+            }
             if (kQual) {
-                const uint32_t si = warp_incl_scan_u32((uint32_t)acc);
-                ex_s = (int)(si - (uint32_t)acc);
-                total_s = (int)__shfl_sync(0xffffffffu, si, 31);
-                int4* cp = reinterpret_cast<int4*>(s_cpre + lane * 8);
+                // read back by this lane only (dynamic index at each newline): no warp barrier needed
+                int4* cp = reinterpret_cast<int4*>(s_cpre);
                 cp[0] = make_int4(ex_s + pre[0], ex_s + pre[1], ex_s + pre[2], ex_s + pre[3]);
                 cp[1] = make_int4(ex_s + pre[4], ex_s + pre[5], ex_s + pre[6], ex_s + pre[7]);
             }
-            if (kSeq) {
-                s_gm[2 * lane] = gm[0];
-                s_gm[2 * lane + 1] = gm[1];
-                s_gex[2 * lane] = ex_g;
-                s_gex[2 * lane + 1] = ex_g + g0;
-            }
         }
         if (lane == 0) a.tile_cnt[tile] = (uint32_t)n_events;
-
-        // newline positions with rank in [win_lo, win_lo + EV_CAP), in order.  Two per 32-bit mask word without a
-        // loop (a lane rarely owns more); the remainder, if any lane has one, goes through the generic loop.
-        auto scatter = [&](int win_lo) {
-            int rank = ex_cnt - win_lo;
-            bool more = false;
-#pragma unroll
-            for (int wd = 0; wd < 4; wd++) {
-                const uint32_t m = (uint32_t)(pm[wd >> 1] >> ((wd & 1) * 32));
-                const int base = lane * ROW_BYTES + wd * 32 - 1;
-                const uint32_t m1 = m & (m - 1);
-                // stores that have nothing to say go to the dump slot ev_pos[EV_CAP]: no branches
-                const int i0 = (m != 0 && (unsigned)rank < (unsigned)EV_CAP) ? rank : EV_CAP;
-                const int i1 = (m1 != 0 && (unsigned)(rank + 1) < (unsigned)EV_CAP) ? rank + 1 : EV_CAP;
-                ev_pos[i0] = (uint16_t)(base + __ffs((int)m));
-                ev_pos[i1] = (uint16_t)(base + __ffs((int)m1));
-                more = more || (m1 & (m1 - 1)) != 0;
-                rank += __popc(m);
-            }
-            if (__any_sync(0xffffffffu, more)) {  // a lane with 3+ newlines in one 32-byte word: the generic loop redoes it
-                rank = ex_cnt - win_lo;
-#pragma unroll
-                for (int wd = 0; wd < 4; wd++) {
-                    uint32_t m = (uint32_t)(pm[wd >> 1] >> ((wd & 1) * 32));
-                    const int base = lane * ROW_BYTES + wd * 32;
-                    while (m) {
-                        if ((unsigned)rank < (unsigned)EV_CAP) ev_pos[rank] = (uint16_t)(base + __ffs((int)m) - 1);
-                        m &= m - 1;
-                        rank++;
-                    }
-                }
-            }
-        };
-        scatter(0);
-        __syncwarp();
 
         // record space for this tile's newlines: the warp's current block first, the rest in a fresh block
         // (a tile's records are at most two runs, so no slot of a block is ever abandoned)
@@ -366,89 +380,153 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             }
         }
 
-        // ---- B. one newline per lane: its record (and, fused, the verdict of the line it ends)
-        // fused: in every pass lane l handles a line with tile-local index = l (mod 4), so its bucket
-        // (the phase hypothesis under which that line is a quality line) is fixed: h = (3 - l) & 3.
-        uint32_t f_cq = 0;  // count | length sum << 12
-        int f_qs = 0;
-        uint32_t f_bad = 0;  // hypotheses (bit h) this lane's lines contradict
-        int first_ps = 0;
-        uint32_t first_y = 0;
-        int c_ps = 0;  // last record of the previous pass
-        uint32_t c_y = 0;
-        int ps = 0, pg = 0;
-        uint32_t y = 0;
-        for (int lo = 0; lo < n_events; lo += 32) {
-            if (lo > 0 && (lo & (EV_CAP - 1)) == 0) {  // more newlines than the event window holds: refill it
-                __syncwarp();
-                scatter(lo);
-                __syncwarp();
+        // ---- B. every lane walks the newlines of ITS OWN row, one per round; the number of rounds is the newline count
+        // of the fullest row (2 for 150 bp reads, 1 for long reads).  The k-th newline of the row has tile-local line
+        // index ex_cnt + k.  Fused: the line a newline ends is judged as soon as both of its ends are known -- at once
+        // for k >= 1 (the previous newline is in this row), after the loop for k = 0 (it is the last newline of an
+        // earlier row).  Buckets are kept in the LANE's frame (hypothesis h' = phase of the row's first line, so
+        // everything is indexed by the unrolled round number) and rotated by ex_cnt into the tile's frame once,
+        // before the warp reduction.
+        uint32_t f_cq[4] = {0, 0, 0, 0};  // [h'] lines that are quality lines under h' and pass: count | length sum << 12
+        int f_qs[4] = {0, 0, 0, 0};       // [h'] their Phred sums
+        uint32_t f_bad = 0;               // bit h': a line start contradicts h'
+        uint64_t mlo = pm[0], mhi = pm[1];
+        // the row's latest / first newline: byte-sum prefix, position, CR flag (the packed word y is formed on demand)
+        int l_ps = 0, l_pos = 0, r0_ps = 0;
+        uint32_t l_y = 0, r0_y = 0;
+        int kk = 0;  // newlines of this row already handled
+        // first tile-local position whose NEXT byte lies outside the parse range (the partial last tile only)
+        const int last_known = (partial && a.n - tile_base < WT_BYTES) ? (int)(a.n - tile_base) - 1 : WT_BYTES - 1;
+
+        // the line between the newline at `ppos` (byte-sum prefix pps) and the newline at `pos` (ps, CR flag cr) is
+        // line `j` (mod 4) of the lane's frame.  A CR flag implies a non-empty line (the byte before an empty line's
+        // newline is the previous newline), so the length needs no clamp.
+        // Called by the whole warp (it votes); `valid` = this lane has such a line.
+        auto judge = [&](auto jc, bool valid, int ps, int pos, uint32_t cr, int pps, int ppos) {
+            constexpr int j = decltype(jc)::value;
+            const uint32_t len = (uint32_t)(pos - ppos - 1) - cr;
+            const int qs = ps - pps - 10 - 13 * (int)cr - 33 * (int)len;
+            bool pass;
+            if (plan.i32) {
+                // e = +-2^sh (sum - c n), exact in 32 bits; e != 0 means |sum - c n| >= 2^-20 > 1e-7, which puts the exact
+                // quotient more than 40 ulp from c (see exb_mean_cmp): the sign of e is the verdict.  n = 0 gives e = 0.
+                const int e = qs * plan.mul_q + (int)len * plan.mul_n;
+                pass = valid && e > 0;
+                if (__any_sync(0xffffffffu, valid && e == 0)) {
+                    if (valid && e == 0) pass = fused_pass_general(s_preds, a.n_fused, plan.simple, plan.c, plan.op, plan.want_pos, qs, len);
+                }
+            } else {
+                pass = valid && fused_pass(s_preds, a.n_fused, plan, qs, len);
             }
-            const bool active = lo + lane < n_events;
-            if (active) {
-                const int pos = ev_pos[(lo & (EV_CAP - 1)) + lane];
-                const int so = sidx(pos);  // byte offset of the newline in the swizzled buffer
+            if (pass) {
+                f_cq[(3 - j) & 3] += 1u + (len << 12);
+                f_qs[(3 - j) & 3] += qs;
+            }
+        };
+        auto step = [&](auto jc, bool first_round) {
+            constexpr int j = decltype(jc)::value;
+            const bool act = kk < cnt;
+            int ps = 0, pg = 0, pos = 0;
+            uint32_t cr = 0, y = 0;
+            if (act) {
+                const bool use_hi = mlo == 0;
+                const uint64_t m = use_hi ? mhi : mlo;
+                const int p = __ffsll((long long)m) - 1 + (use_hi ? 64 : 0);  // position in the row
+                const uint64_t rest = m & (m - 1);
+                mlo = use_hi ? mlo : rest;
+                mhi = use_hi ? rest : mhi;
+                pos = row_off + p;
                 if (kQual) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(sbytes + (so & ~15));
-                    const uint4 w = s_wlut[pos & 15];
-                    int acc = s_cpre[pos >> 4];
+                    const uint4 v = row[(p >> 4) ^ sw];
+                    const uint4 w = s_wlut[p & 15];
+                    int acc = s_cpre[p >> 4];
                     acc = __dp4a((int)v.x, (int)w.x, acc);
                     acc = __dp4a((int)v.y, (int)w.y, acc);
                     acc = __dp4a((int)v.z, (int)w.z, acc);
                     acc = __dp4a((int)v.w, (int)w.w, acc);
                     ps = acc;
                 }
-                if (kSeq) pg = s_gex[pos >> 6] + __popcll(s_gm[pos >> 6] & low_bits64(pos & 63));
-                // a CR directly before a real LF is stripped (when the line is not empty: the consumer checks);
-                // the virtual '\n' at EOF strips nothing.  Both neighbours are fetched unconditionally (clamped).
-                int before = sbytes[sidx(pos > 0 ? pos - 1 : 0)];
-                const int after = sbytes[sidx(pos + 1 < WT_BYTES ? pos + 1 : pos)];
-                if (pos == 0) before = tile_base - 1 >= lower ? (int)buf[tile_base - 1] : -1;  // rare: first byte of the tile
-                const uint32_t cr = (before == '\r' && !(a.is_final && tile_base + pos == a.n)) ? 1u : 0u;
-                const uint32_t nf = pos + 1 < WT_BYTES ? at_plus_flags(after) : 0u;
+                if (kSeq) pg = p < 64 ? ex_g + __popcll(gm[0] & low_bits64(p)) : ex_g + g0 + __popcll(gm[1] & low_bits64(p - 64));
+                // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing.  Both neighbours
+                // are fetched unconditionally (clamped); the byte before the tile's first byte is patched in below.
+                const int before = sbytes[sidx(pos > 0 ? pos - 1 : 0)];
+                const int after = sbytes[sidx(pos < WT_BYTES - 1 ? pos + 1 : pos)];
+                cr = (before == '\r' && pos != virt) ? 1u : 0u;
+                // '@' / '+' flags of the next line's first byte; 3 = that byte is not in this tile or range: no verdict here
+                const uint32_t nf = pos < last_known ? (uint32_t)s_nflut[after] : 3u;
                 y = rec_pack(pos, cr, nf, kSeq ? pg : 0);
+                if (kFused) {
+                    // the line that STARTS after this newline is line j + 1 of the lane's frame: a header under
+                    // h' = -(j + 1), a plus line under h' = 2 - (j + 1).  (The tile's line 0 is checked by K2.)
+                    constexpr uint32_t bad_hdr = 1u << ((0 - (j + 1)) & 3), bad_plus = 1u << ((2 - (j + 1)) & 3);
+                    // nf: 0 -> both, 1 ('+') -> hdr, 2 ('@') -> plus, 3 -> none
+                    constexpr uint32_t lut = (bad_hdr | bad_plus) | (bad_hdr << 4) | (bad_plus << 8);
+                    f_bad |= (lut >> (4 * nf)) & 15u;
+                }
                 if (!kFused) {
-                    const int i = lo + lane;
+                    const int i = ex_cnt + kk;
                     if (i < rec_n0 ? rec_ok0 : blk_ok) a.records[i < rec_n0 ? rec_off0 + i : rec_off1 + (i - rec_n0)] = make_uint2((uint32_t)ps, y);
                 }
             }
-            if (kFused) {
-                int pps = __shfl_up_sync(0xffffffffu, ps, 1);
-                uint32_t py = __shfl_up_sync(0xffffffffu, y, 1);
-                if (lane == 0) {
-                    pps = c_ps;
-                    py = c_y;
-                }
-                if (active && lo + lane > 0) {  // line `lo + lane` of the tile: it starts right after the previous newline
-                    uint32_t len = (uint32_t)(rec_pos(y) - rec_pos(py) - 1);
-                    const uint32_t cr = len > 0 ? rec_cr(y) : 0u;
-                    len -= cr;
-                    const int qs = ps - pps - 10 - 13 * (int)cr - 33 * (int)len;
-                    if (fused_pass(a, plan, qs, len)) {
-                        f_cq += 1u + (len << 12);
-                        f_qs += qs;
-                    }
-                    const uint32_t nfl = rec_next_flags(py);  // flags of this line's first byte
-                    f_bad |= (nfl & 2u) ? 0u : bit_hdr;
-                    f_bad |= (nfl & 1u) ? 0u : bit_plus;
-                }
-                c_ps = __shfl_sync(0xffffffffu, ps, 31);
-                c_y = __shfl_sync(0xffffffffu, y, 31);
+            if (j == 0 && first_round) {
+                r0_ps = ps;
+                r0_y = y;
+            } else if (kFused) {
+                judge(jc, act, ps, pos, cr, l_ps, l_pos);
             }
-            if (lo == 0) {
-                first_ps = __shfl_sync(0xffffffffu, ps, 0);
-                first_y = __shfl_sync(0xffffffffu, y, 0);
+            if (act) {
+                l_ps = ps;
+                l_pos = pos;
+                l_y = y;
+                kk++;
             }
+        };
+        {
+            const int rounds = __reduce_max_sync(0xffffffffu, cnt);
+            bool first_round = true;
+            for (int r = 0; r < rounds; r += 4) {
+                step(std::integral_constant<int, 0>(), first_round);
+                if (r + 1 < rounds) step(std::integral_constant<int, 1>(), false);
+                if (r + 2 < rounds) step(std::integral_constant<int, 2>(), false);
+                if (r + 3 < rounds) step(std::integral_constant<int, 3>(), false);
+                first_round = false;
+            }
+        }
+        // the byte before the tile's first byte lives in global memory: a newline at position 0 of the tile (lane 0's
+        // first) learns its CR flag here (rare, so it is kept out of the rounds)
+        if (lane == 0 && (pm[0] & 1ull) && virt != 0 && tile_base - 1 >= lower && buf[tile_base - 1] == '\r') {
+            r0_y |= 1u << 12;
+            if (cnt == 1) l_y |= 1u << 12;
+            if (!kFused) {
+                const int i = 0;
+                if (i < rec_n0 ? rec_ok0 : blk_ok) a.records[i < rec_n0 ? rec_off0 + i : rec_off1 + (i - rec_n0)] = make_uint2((uint32_t)r0_ps, r0_y);
+            }
+        }
+        // rows that hold a newline; the row's first line started after the last newline of the nearest such row below
+        const uint32_t has = __ballot_sync(0xffffffffu, cnt > 0);
+        const uint32_t below = has & ((1u << lane) - 1u);
+        if (kFused) {
+            const int src = below ? 31 - __clz((int)below) : 0;
+            const int pps = __shfl_sync(0xffffffffu, l_ps, src);
+            const int ppos = __shfl_sync(0xffffffffu, l_pos, src);
+            judge(std::integral_constant<int, 0>(), cnt > 0 && below != 0, r0_ps, rec_pos(r0_y), rec_cr(r0_y), pps, ppos);
+        }
+        int first_ps = 0;
+        uint32_t first_y = 0;
+        if (kFused && has) {  // the tile's first newline: K2 finishes the line it ends
+            const int f = __ffs((int)has) - 1;
+            first_ps = __shfl_sync(0xffffffffu, r0_ps, f);
+            first_y = __shfl_sync(0xffffffffu, r0_y, f);
         }
 
         // ---- C. tail word: what follows the tile's last newline (local information only)
         {
-            const uint32_t b0 = at_plus_flags(sbytes[sidx(tile == 0 ? (int)(a.begin - origin) : 0)]);
+            const uint32_t b0 = s_nflut[sbytes[tile == 0 ? sidx((int)(a.begin - origin)) : 0]];
             uint64_t tw;
-            if (n_events > 0) {
-                const int src = (n_events - 1) & 31;  // lane holding the last record
-                const int lps = __shfl_sync(0xffffffffu, ps, src);
-                const uint32_t ly = __shfl_sync(0xffffffffu, y, src);
+            if (has) {
+                const int src = 31 - __clz((int)has);  // lane holding the last record
+                const int lps = __shfl_sync(0xffffffffu, l_ps, src);
+                const uint32_t ly = __shfl_sync(0xffffffffu, l_y, src);
                 tw = tail_pack(2, (rec_next_flags(ly) << 2) | b0, (uint32_t)(rec_pos(ly) + 1), (uint32_t)(total_g - rec_pg(ly)),
                                total_s - (lps + 10));
             } else {
@@ -458,24 +536,31 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         }
 
         if (kFused) {
-            // fold the lanes that share a bucket (lanes 4 apart); contradictions are OR-ed over the warp
+            // lane frame -> tile frame: tile hypothesis h (phase of the tile's line 0) is lane hypothesis (h + ex_cnt) & 3
+            const int r = ex_cnt & 3;
+            uint32_t cq[4];
+            int qs[4];
 #pragma unroll
-            for (int dd = 4; dd < 32; dd <<= 1) {
-                f_cq += __shfl_xor_sync(0xffffffffu, f_cq, dd);
-                f_qs += __shfl_xor_sync(0xffffffffu, f_qs, dd);
+            for (int i = 0; i < 4; i++) {
+                const uint32_t c1 = (r & 1) ? f_cq[(i + 1) & 3] : f_cq[i], c3 = (r & 1) ? f_cq[(i + 3) & 3] : f_cq[(i + 2) & 3];
+                const int q1 = (r & 1) ? f_qs[(i + 1) & 3] : f_qs[i], q3 = (r & 1) ? f_qs[(i + 3) & 3] : f_qs[(i + 2) & 3];
+                cq[i] = (r & 2) ? c3 : c1;
+                qs[i] = (r & 2) ? q3 : q1;
             }
-            const uint32_t bad4 = __reduce_or_sync(0xffffffffu, f_bad);
-            FusedTile* ft = a.fused_tiles + tile;
-            if (lane < 4) {
-                const int h = (3 - lane) & 3;  // lane l holds the totals of bucket (3 - l) & 3
-                ft->cq[h] = f_cq;
-                ft->qs[h] = f_qs;
-            } else if (lane == 4) {
-                *reinterpret_cast<uint4*>(&ft->ps0) = make_uint4((uint32_t)first_ps, first_y, bad4, 0u);
+            const uint32_t bad_t = ((f_bad | (f_bad << 4)) >> r) & 15u;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                cq[i] = __reduce_add_sync(0xffffffffu, cq[i]);
+                qs[i] = __reduce_add_sync(0xffffffffu, qs[i]);
             }
+            const uint32_t bad4 = __reduce_or_sync(0xffffffffu, bad_t);
+            uint4* ft = reinterpret_cast<uint4*>(a.fused_tiles + tile);
+            if (lane == 0) ft[0] = make_uint4(cq[0], cq[1], cq[2], cq[3]);
+            if (lane == 1) ft[1] = make_uint4((uint32_t)qs[0], (uint32_t)qs[1], (uint32_t)qs[2], (uint32_t)qs[3]);
+            if (lane == 2) ft[2] = make_uint4((uint32_t)first_ps, first_y, bad4, 0u);
         }
 
-        __syncwarp();  // the event list / prefix arrays are rewritten by the next tile
+        __syncwarp();  // every lane is done with this buffer before lane 0 lets TMA refill it
         cur = nxt;
         b ^= 1;
     }
@@ -647,6 +732,9 @@ __global__ void __launch_bounds__(256) fastq_fused_combine_kernel(const FastqSca
     const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
     const int64_t threads = (int64_t)gridDim.x * blockDim.x;
     const FusedPlan plan = make_plan(a);
+    __shared__ exb_predicate s_preds[EXB_MAX_PREDICATES];
+    if (threadIdx.x < a.n_fused) s_preds[threadIdx.x] = a.fused[threadIdx.x];
+    __syncthreads();
     long long cnt = 0, qs = 0, ql = 0;
     bool bad = false;
     for (int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tile < n_tiles; tile += threads) {
@@ -677,7 +765,7 @@ __global__ void __launch_bounds__(256) fastq_fused_combine_kernel(const FastqSca
                 // lines longer than a tile can exceed the |sum| < 2^20 precondition of the fast path: use the general test
                 FusedPlan p1 = plan;
                 if (len > 4096u) p1.simple = 0;
-                if (fused_pass(a, p1, q1, len)) {
+                if (fused_pass(s_preds, a.n_fused, p1, q1, len)) {
                     cnt += 1;
                     qs += q1;
                     ql += len;
