@@ -177,6 +177,28 @@ __device__ __forceinline__ FusedPlan make_plan(const FastqScanArgs& a) {
     return p;
 }
 
+// shared-memory accessors on 32-bit shared-window addresses: the hot loop does no generic-pointer arithmetic
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, int x, int y, int z, int w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// tile-local byte index -> byte offset in the 128B-swizzled tile buffer (same map as sidx, two instructions)
+__device__ __forceinline__ uint32_t swz(uint32_t li) { return li ^ ((li >> 3) & 0x70u); }
+
 // =================================================================== K1
 template <int FLAGS>
 __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_constant__ CUtensorMap tmap, const FastqScanArgs a,
@@ -199,38 +221,41 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
     }
     exb_predicate* s_preds = reinterpret_cast<exb_predicate*>(smem_raw + AUX::off_preds);
     if (kFused && threadIdx.x < a.n_fused) s_preds[threadIdx.x] = a.fused[threadIdx.x];
-    uint8_t* s_nflut = smem_raw + AUX::off_nflut;
-    for (int i = threadIdx.x; i < 256; i += FQ_THREADS) s_nflut[i] = (uint8_t)at_plus_flags(i);
+    for (int i = threadIdx.x; i < 256; i += FQ_THREADS) (smem_raw + AUX::off_nflut)[i] = (uint8_t)at_plus_flags(i);
 
-    if (((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u) != 0) __trap();
-    uint8_t* data0 = smem_raw + warp * (2 * WT_BYTES);
-    uint8_t* aux = smem_raw + FQ_WARPS * (2 * WT_BYTES) + warp * AUX::total;
-    int* s_cpre = reinterpret_cast<int*>(aux + AUX::off_cpre) + lane * 8;  // this lane's eight chunk prefixes
-    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(aux + AUX::off_bar);
-    const uint32_t data0_u32 = (uint32_t)__cvta_generic_to_shared(data0);
+    const uint32_t smem_u32 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    if ((smem_u32 & 1023u) != 0) __trap();
+    const uint32_t data0_u32 = smem_u32 + warp * (2 * WT_BYTES);
+    const uint32_t aux_u32 = smem_u32 + FQ_WARPS * (2 * WT_BYTES) + warp * AUX::total;
+    const uint32_t cpre_u32 = aux_u32 + AUX::off_cpre + lane * 32;  // this lane's eight chunk prefixes
+    const uint32_t bar0 = aux_u32 + AUX::off_bar;
+    const uint32_t wlut_u32 = smem_u32 + AUX::off_wlut, nflut_u32 = smem_u32 + AUX::off_nflut;
     if (lane == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    __syncthreads();  // the only block-wide barrier of the kernel (LUT + barriers ready)
+    __syncthreads();  // the only block-wide barrier of the kernel (LUTs + barriers ready)
 
     const uint8_t* __restrict__ buf = a.buf;
     const int64_t origin = a.begin & ~(int64_t)15;
-    const int64_t n_tiles = a.n_tiles;
+    // tile indices are 32-bit in the loop (the launcher refuses inputs of 2^31 tiles = 8 TiB)
+    const int n_tiles = (int)a.n_tiles;
     const int64_t full_rows = a.tma_rows;  // rows of 128 bytes that lie completely inside [origin, n): what the tensor map covers
+    const int first_edge = (int)(full_rows / WT_ROWS);  // first tile with rows the tensor map does not cover
+    const int tma_tiles = (int)((full_rows + WT_ROWS - 1) / WT_ROWS) < n_tiles ? (int)((full_rows + WT_ROWS - 1) / WT_ROWS) : n_tiles;
+    const bool pad0 = a.begin != origin;
     const uint32_t pat_nl = c7f & 0x0A0A0A0Au, pat_gc = c7f & 0x43434343u;  // derived from an argument: stay in registers
-    const int64_t stride = (int64_t)gridDim.x * FQ_WARPS;
+    const int stride = (int)gridDim.x * FQ_WARPS;
     const FusedPlan plan = kFused ? make_plan(a) : FusedPlan{0, 0.0, 0, 0, 0, 0, 0, 0};
-    const int64_t lower = a.prev ? 0 : a.begin;  // first readable byte of the buffer
-    const int sw = lane & 7;                     // 128B swizzle: chunk c of row `lane` sits at chunk slot c ^ sw
-    const int row_off = lane * ROW_BYTES;
+    const int lane_off = lane * ROW_BYTES;
+    const uint32_t lane_part = (uint32_t)lane_off | ((uint32_t)(lane & 7) << 4);  // chunk c of the lane's row sits at (buffer + lane_part) ^ (c << 4)
 
     // ---- staging of one tile into buffer b (asynchronous; one instruction from one lane)
-    auto issue = [&](int64_t tile, int b) {
-        if (tile < n_tiles && tile * WT_ROWS < full_rows && lane == 0) {
+    auto issue = [&](int tile, int b) {
+        if (tile < tma_tiles && lane == 0) {
             mbar_expect_tx(bar0 + 8 * b, WT_BYTES);
-            tma_load_tile(data0_u32 + b * WT_BYTES, &tmap, (int)(tile * WT_ROWS), bar0 + 8 * b);
+            tma_load_tile(data0_u32 + b * WT_BYTES, &tmap, tile * WT_ROWS, bar0 + 8 * b);
         }
     };
 
@@ -239,32 +264,31 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
     int rec_left = 0;  // a warp that has not allocated yet owns nothing: a record is never written through off0 then
     bool blk_ok = true;  // the current block lies inside the record space
 
-    int64_t cur = (int64_t)blockIdx.x * FQ_WARPS + warp;
+    int cur = (int)blockIdx.x * FQ_WARPS + warp;
     issue(cur, 0);
     int b = 0;
     uint32_t phase_bits = 0;  // bit b = parity the next wait on buffer b expects
 
     while (cur < n_tiles) {
-        const int64_t nxt = cur + stride;
+        const int nxt = cur + stride;
         issue(nxt, b ^ 1);
 
-        const int64_t tile = cur;
-        const int64_t tile_base = origin + tile * WT_BYTES;
-        uint8_t* sbytes = data0 + b * WT_BYTES;
-        const uint4* d = reinterpret_cast<const uint4*>(sbytes);
-        const int64_t row0 = tile * WT_ROWS;
-
-        if (row0 < full_rows) {
+        const int tile = cur;
+        const uint32_t sb = data0_u32 + b * WT_BYTES;
+        if (tile < tma_tiles) {
             const uint32_t par = (phase_bits >> b) & 1u;
             while (!mbar_try_wait(bar0 + 8 * b, par)) {
             }
             phase_bits ^= 1u << b;
         }
         // Rare edge tiles (uniform per warp): rows the tensor map does not cover, bytes before `begin`, the virtual '\n'
-        const bool partial = row0 + WT_ROWS > full_rows;
-        const bool has_begin_pad = (tile == 0 && a.begin != origin);
-        int virt = -1;  // tile-local position of the virtual '\n' that terminates an unterminated last line
-        if (partial || has_begin_pad) {
+        int virt = -1;                   // tile-local position of the virtual '\n' that terminates an unterminated last line
+        int last_known = WT_BYTES - 1;   // first tile-local position whose NEXT byte lies outside the tile or the parse range
+        if (tile >= first_edge || (tile == 0 && pad0)) {
+            const int64_t tile_base = origin + (int64_t)tile * WT_BYTES;
+            const int64_t row0 = (int64_t)tile * WT_ROWS;
+            uint8_t* sbytes = smem_raw + (sb - smem_u32);
+            const bool partial = tile >= first_edge;
             if (row0 >= full_rows) {  // nothing came through TMA: clear the buffer
                 for (int i = lane; i < WT_BYTES / 16; i += 32) reinterpret_cast<uint4*>(sbytes)[i] = make_uint4(0, 0, 0, 0);
                 __syncwarp();
@@ -276,7 +300,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             }
             __syncwarp();
             if (lane == 0) {
-                if (has_begin_pad)
+                if (tile == 0 && pad0)
                     for (int64_t i = origin; i < a.begin; i++) sbytes[sidx((int)(i - origin))] = 0;
                 if (a.is_final && a.n >= tile_base && a.n < tile_base + WT_BYTES) {  // an unterminated last line gets a virtual '\n' at n
                     const bool open = a.n > a.begin ? buf[a.n - 1] != '\n' : (a.prev && a.prev->open_line_start < a.n);
@@ -286,18 +310,20 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes before this buffer's next TMA fill
             __syncwarp();
             if (a.is_final && a.n >= tile_base && a.n < tile_base + WT_BYTES) virt = (int)(a.n - tile_base);
+            if (partial && a.n - tile_base < WT_BYTES) last_known = (int)(a.n - tile_base) - 1;
         }
 
         // ---- A. analysis of the lane's row: two 64-byte halves
         uint64_t pm[2], gm[2] = {0, 0};
         int ex_cnt, n_events, cnt, ex_s = 0, total_s = 0, ex_g = 0, total_g = 0, g0 = 0;
-        const uint4* row = d + lane * 8;
+        const uint32_t rowx = sb + lane_part;
         {
             int acc = 0;
             int pre[8];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const uint4 c0 = row[(4 * h + 0) ^ sw], c1 = row[(4 * h + 1) ^ sw], c2 = row[(4 * h + 2) ^ sw], c3 = row[(4 * h + 3) ^ sw];
+                const uint4 c0 = lds128(rowx ^ ((4 * h + 0) << 4)), c1 = lds128(rowx ^ ((4 * h + 1) << 4)), c2 = lds128(rowx ^ ((4 * h + 2) << 4)),
+                            c3 = lds128(rowx ^ ((4 * h + 3) << 4));
                 pm[h] = ((uint64_t)(nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16)) << 32) |
                         (nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16));
                 if (kQual) {
@@ -346,9 +372,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             }
             if (kQual) {
                 // read back by this lane only (dynamic index at each newline): no warp barrier needed
-                int4* cp = reinterpret_cast<int4*>(s_cpre);
-                cp[0] = make_int4(ex_s + pre[0], ex_s + pre[1], ex_s + pre[2], ex_s + pre[3]);
-                cp[1] = make_int4(ex_s + pre[4], ex_s + pre[5], ex_s + pre[6], ex_s + pre[7]);
+                sts128(cpre_u32, ex_s + pre[0], ex_s + pre[1], ex_s + pre[2], ex_s + pre[3]);
+                sts128(cpre_u32 + 16, ex_s + pre[4], ex_s + pre[5], ex_s + pre[6], ex_s + pre[7]);
             }
         }
         if (lane == 0) a.tile_cnt[tile] = (uint32_t)n_events;
@@ -386,39 +411,40 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         // for k >= 1 (the previous newline is in this row), after the loop for k = 0 (it is the last newline of an
         // earlier row).  Buckets are kept in the LANE's frame (hypothesis h' = phase of the row's first line, so
         // everything is indexed by the unrolled round number) and rotated by ex_cnt into the tile's frame once,
-        // before the warp reduction.
+        // before the warp reduction.  The rounds are branch-free: a lane without a newline left computes on a
+        // harmless in-range position and its results are discarded by selects.
         uint32_t f_cq[4] = {0, 0, 0, 0};  // [h'] lines that are quality lines under h' and pass: count | length sum << 12
         int f_qs[4] = {0, 0, 0, 0};       // [h'] their Phred sums
         uint32_t f_bad = 0;               // bit h': a line start contradicts h'
         uint64_t mlo = pm[0], mhi = pm[1];
-        // the row's latest / first newline: byte-sum prefix, position, CR flag (the packed word y is formed on demand)
-        int l_ps = 0, l_pos = 0, r0_ps = 0;
-        uint32_t l_y = 0, r0_y = 0;
-        int kk = 0;  // newlines of this row already handled
-        // first tile-local position whose NEXT byte lies outside the parse range (the partial last tile only)
-        const int last_known = (partial && a.n - tile_base < WT_BYTES) ? (int)(a.n - tile_base) - 1 : WT_BYTES - 1;
+        int l_ps = 0, r0_ps = 0;          // byte-sum prefix at the row's latest / first newline
+        uint32_t l_y = 0, r0_y = 0;       // their packed words
+        int kk = 0;                       // rounds done
 
         // the line between the newline at `ppos` (byte-sum prefix pps) and the newline at `pos` (ps, CR flag cr) is
         // line `j` (mod 4) of the lane's frame.  A CR flag implies a non-empty line (the byte before an empty line's
-        // newline is the previous newline), so the length needs no clamp.
-        // Called by the whole warp (it votes); `valid` = this lane has such a line.
+        // newline is the previous newline), so the length needs no clamp.  Called by the whole warp (it votes);
+        // `valid` = this lane has such a line.
         auto judge = [&](auto jc, bool valid, int ps, int pos, uint32_t cr, int pps, int ppos) {
             constexpr int j = decltype(jc)::value;
             const uint32_t len = (uint32_t)(pos - ppos - 1) - cr;
             const int qs = ps - pps - 10 - 13 * (int)cr - 33 * (int)len;
-            bool pass;
             if (plan.i32) {
                 // e = +-2^sh (sum - c n), exact in 32 bits; e != 0 means |sum - c n| >= 2^-20 > 1e-7, which puts the exact
                 // quotient more than 40 ulp from c (see exb_mean_cmp): the sign of e is the verdict.  n = 0 gives e = 0.
                 const int e = qs * plan.mul_q + (int)len * plan.mul_n;
-                pass = valid && e > 0;
-                if (__any_sync(0xffffffffu, valid && e == 0)) {
-                    if (valid && e == 0) pass = fused_pass_general(s_preds, a.n_fused, plan.simple, plan.c, plan.op, plan.want_pos, qs, len);
+                if (valid && e > 0) {
+                    f_cq[(3 - j) & 3] += 1u + (len << 12);
+                    f_qs[(3 - j) & 3] += qs;
                 }
-            } else {
-                pass = valid && fused_pass(s_preds, a.n_fused, plan, qs, len);
-            }
-            if (pass) {
+                const bool close = valid && e == 0;
+                if (__any_sync(0xffffffffu, close)) {  // rare: the two roundings of the reference decide
+                    if (close && fused_pass_general(s_preds, a.n_fused, plan.simple, plan.c, plan.op, plan.want_pos, qs, len)) {
+                        f_cq[(3 - j) & 3] += 1u + (len << 12);
+                        f_qs[(3 - j) & 3] += qs;
+                    }
+                }
+            } else if (valid && fused_pass(s_preds, a.n_fused, plan, qs, len)) {
                 f_cq[(3 - j) & 3] += 1u + (len << 12);
                 f_qs[(3 - j) & 3] += qs;
             }
@@ -426,60 +452,54 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         auto step = [&](auto jc, bool first_round) {
             constexpr int j = decltype(jc)::value;
             const bool act = kk < cnt;
-            int ps = 0, pg = 0, pos = 0;
-            uint32_t cr = 0, y = 0;
-            if (act) {
-                const bool use_hi = mlo == 0;
-                const uint64_t m = use_hi ? mhi : mlo;
-                const int p = __ffsll((long long)m) - 1 + (use_hi ? 64 : 0);  // position in the row
-                const uint64_t rest = m & (m - 1);
-                mlo = use_hi ? mlo : rest;
-                mhi = use_hi ? rest : mhi;
-                pos = row_off + p;
-                if (kQual) {
-                    const uint4 v = row[(p >> 4) ^ sw];
-                    const uint4 w = s_wlut[p & 15];
-                    int acc = s_cpre[p >> 4];
-                    acc = __dp4a((int)v.x, (int)w.x, acc);
-                    acc = __dp4a((int)v.y, (int)w.y, acc);
-                    acc = __dp4a((int)v.z, (int)w.z, acc);
-                    acc = __dp4a((int)v.w, (int)w.w, acc);
-                    ps = acc;
-                }
-                if (kSeq) pg = p < 64 ? ex_g + __popcll(gm[0] & low_bits64(p)) : ex_g + g0 + __popcll(gm[1] & low_bits64(p - 64));
-                // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing.  Both neighbours
-                // are fetched unconditionally (clamped); the byte before the tile's first byte is patched in below.
-                const int before = sbytes[sidx(pos > 0 ? pos - 1 : 0)];
-                const int after = sbytes[sidx(pos < WT_BYTES - 1 ? pos + 1 : pos)];
-                cr = (before == '\r' && pos != virt) ? 1u : 0u;
-                // '@' / '+' flags of the next line's first byte; 3 = that byte is not in this tile or range: no verdict here
-                const uint32_t nf = pos < last_known ? (uint32_t)s_nflut[after] : 3u;
-                y = rec_pack(pos, cr, nf, kSeq ? pg : 0);
-                if (kFused) {
-                    // the line that STARTS after this newline is line j + 1 of the lane's frame: a header under
-                    // h' = -(j + 1), a plus line under h' = 2 - (j + 1).  (The tile's line 0 is checked by K2.)
-                    constexpr uint32_t bad_hdr = 1u << ((0 - (j + 1)) & 3), bad_plus = 1u << ((2 - (j + 1)) & 3);
-                    // nf: 0 -> both, 1 ('+') -> hdr, 2 ('@') -> plus, 3 -> none
-                    constexpr uint32_t lut = (bad_hdr | bad_plus) | (bad_hdr << 4) | (bad_plus << 8);
-                    f_bad |= (lut >> (4 * nf)) & 15u;
-                }
-                if (!kFused) {
-                    const int i = ex_cnt + kk;
-                    if (i < rec_n0 ? rec_ok0 : blk_ok) a.records[i < rec_n0 ? rec_off0 + i : rec_off1 + (i - rec_n0)] = make_uint2((uint32_t)ps, y);
-                }
+            const bool use_hi = mlo == 0;  // also when no newline is left: p = 63 then
+            const uint64_t m = use_hi ? mhi : mlo;
+            const int p = __ffsll((long long)m) - 1 + (use_hi ? 64 : 0);  // position in the row
+            mlo &= mlo - 1;
+            mhi = use_hi ? (mhi & (mhi - 1)) : mhi;
+            const int pos = lane_off + p;
+            int ps = 0, pg = 0;
+            if (kQual) {
+                const uint4 v = lds128(rowx ^ (uint32_t)(p & 0x70));
+                const uint4 w = lds128(wlut_u32 + (uint32_t)((p & 15) << 4));
+                int acc = (int)lds32(cpre_u32 + (uint32_t)((p >> 4) << 2));
+                acc = __dp4a((int)v.x, (int)w.x, acc);
+                acc = __dp4a((int)v.y, (int)w.y, acc);
+                acc = __dp4a((int)v.z, (int)w.z, acc);
+                acc = __dp4a((int)v.w, (int)w.w, acc);
+                ps = acc;
             }
-            if (j == 0 && first_round) {
+            if (kSeq) pg = p < 64 ? ex_g + __popcll(gm[0] & low_bits64(p)) : ex_g + g0 + __popcll(gm[1] & low_bits64(p - 64));
+            // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing.  Both neighbours
+            // are fetched unconditionally (clamped); the byte before the tile's first byte is patched in below.
+            const uint32_t before = lds8(sb + swz((uint32_t)max(pos - 1, 0)));
+            const uint32_t after = lds8(sb + swz((uint32_t)min(pos + 1, WT_BYTES - 1)));
+            const uint32_t cr = (before == '\r' && pos != virt) ? 1u : 0u;
+            // '@' / '+' flags of the next line's first byte; 3 = that byte is not in this tile or range: no verdict here
+            const uint32_t nfk = lds8(nflut_u32 + after);
+            const uint32_t nf = pos < last_known ? nfk : 3u;
+            const uint32_t y = rec_pack(pos, cr, nf, kSeq ? pg : 0);
+            if (kFused) {
+                // the line that STARTS after this newline is line j + 1 of the lane's frame: a header under
+                // h' = -(j + 1), a plus line under h' = 2 - (j + 1).  (The tile's line 0 is checked by K2.)
+                constexpr uint32_t bad_hdr = 1u << ((0 - (j + 1)) & 3), bad_plus = 1u << ((2 - (j + 1)) & 3);
+                // nf: 0 -> both, 1 ('+') -> hdr, 2 ('@') -> plus, 3 -> none
+                constexpr uint32_t lut = (bad_hdr | bad_plus) | (bad_hdr << 4) | (bad_plus << 8);
+                f_bad |= (lut >> (4 * (act ? nf : 3u))) & 15u;
+            }
+            if (!kFused) {
+                const int i = ex_cnt + kk;
+                if (act && (i < rec_n0 ? rec_ok0 : blk_ok)) a.records[i < rec_n0 ? rec_off0 + i : rec_off1 + (i - rec_n0)] = make_uint2((uint32_t)ps, y);
+            }
+            if (j == 0 && first_round) {  // a lane without a newline keeps garbage here and never uses it
                 r0_ps = ps;
                 r0_y = y;
             } else if (kFused) {
-                judge(jc, act, ps, pos, cr, l_ps, l_pos);
+                judge(jc, act, ps, pos, cr, l_ps, rec_pos(l_y));
             }
-            if (act) {
-                l_ps = ps;
-                l_pos = pos;
-                l_y = y;
-                kk++;
-            }
+            l_ps = act ? ps : l_ps;
+            l_y = act ? y : l_y;
+            kk++;
         };
         {
             const int rounds = __reduce_max_sync(0xffffffffu, cnt);
@@ -494,12 +514,12 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         }
         // the byte before the tile's first byte lives in global memory: a newline at position 0 of the tile (lane 0's
         // first) learns its CR flag here (rare, so it is kept out of the rounds)
-        if (lane == 0 && (pm[0] & 1ull) && virt != 0 && tile_base - 1 >= lower && buf[tile_base - 1] == '\r') {
-            r0_y |= 1u << 12;
-            if (cnt == 1) l_y |= 1u << 12;
-            if (!kFused) {
-                const int i = 0;
-                if (i < rec_n0 ? rec_ok0 : blk_ok) a.records[i < rec_n0 ? rec_off0 + i : rec_off1 + (i - rec_n0)] = make_uint2((uint32_t)r0_ps, r0_y);
+        if (lane == 0 && (pm[0] & 1ull) && virt != 0) {
+            const int64_t tile_base = origin + (int64_t)tile * WT_BYTES;
+            if (tile_base - 1 >= (a.prev ? 0 : a.begin) && buf[tile_base - 1] == '\r') {
+                r0_y |= 1u << 12;
+                if (cnt == 1) l_y |= 1u << 12;
+                if (!kFused && (0 < rec_n0 ? rec_ok0 : blk_ok)) a.records[0 < rec_n0 ? rec_off0 : rec_off1] = make_uint2((uint32_t)r0_ps, r0_y);
             }
         }
         // rows that hold a newline; the row's first line started after the last newline of the nearest such row below
@@ -508,8 +528,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         if (kFused) {
             const int src = below ? 31 - __clz((int)below) : 0;
             const int pps = __shfl_sync(0xffffffffu, l_ps, src);
-            const int ppos = __shfl_sync(0xffffffffu, l_pos, src);
-            judge(std::integral_constant<int, 0>(), cnt > 0 && below != 0, r0_ps, rec_pos(r0_y), rec_cr(r0_y), pps, ppos);
+            const uint32_t py = __shfl_sync(0xffffffffu, l_y, src);
+            judge(std::integral_constant<int, 0>(), cnt > 0 && below != 0, r0_ps, rec_pos(r0_y), rec_cr(r0_y), pps, rec_pos(py));
         }
         int first_ps = 0;
         uint32_t first_y = 0;
@@ -521,7 +541,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
 
         // ---- C. tail word: what follows the tile's last newline (local information only)
         {
-            const uint32_t b0 = s_nflut[sbytes[tile == 0 ? sidx((int)(a.begin - origin)) : 0]];
+            const uint32_t b0 = lds8(nflut_u32 + lds8(sb + ((tile == 0 && pad0) ? swz((uint32_t)(a.begin - origin)) : 0u)));
             uint64_t tw;
             if (has) {
                 const int src = 31 - __clz((int)has);  // lane holding the last record
@@ -819,6 +839,8 @@ static cudaError_t launch_tile_kernel(FastqScanArgs a, cudaStream_t st) {
         n_sm = sms;
         ctas_per_sm = occ > 0 ? occ : 1;
     }
+    // the kernel keeps tile and row indices in 32 bits: 2^26 tiles = 256 GiB per launch, more than one GPU's HBM
+    if (a.n_tiles >= ((int64_t)1 << 26)) return cudaErrorInvalidValue;
     alignas(64) CUtensorMap tm;
     if ((e = make_tensor_map(a.buf, a.begin, a.n, &tm, &a.tma_rows)) != cudaSuccess) return e;
     int64_t grid = (a.n_tiles + FQ_WARPS - 1) / FQ_WARPS;
