@@ -39,8 +39,8 @@ def workload_config(n_gpus, reads):
         "reads_per_gpu": reads,
         "query": "SELECT COUNT(*) FROM read_fastq(f) WHERE list_avg(quality_score_string_to_list(quality_scores)) > 30",
         "sharding": "one file of n_gpus x reads_per_gpu records cut into byte ranges whose edges fall inside records; per step: scan under a "
-                    "provisional phase, NCCL all-gather of the 128-byte result blocks, device-side composition + resolve kernel "
-                    "(exon_duckdb_b200/dist.py), NCCL all-reduce of the aggregates; no data-path collective"
+                    "provisional phase, exchange of the 128-byte result blocks, device-side composition + resolve kernel "
+                    "(exon_duckdb_b200/dist.py), reduce of the 8 int64 aggregates (over NVLink peer memory, else NCCL: see `exchange`); no data-path collective"
         if n_gpus > 1 else "single GPU",
         "l2": "input (~7 GB) is larger than L2 (126 MB); no flush needed between steps",
     }
@@ -211,6 +211,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
@@ -261,7 +263,20 @@ def main():
         s_prev = rec_size(rank * R - 1) if rank else 0
         s_next = rec_size((rank + 1) * R) if rank < world - 1 else 0
         own = gbuf.numel() - s_prev - s_next  # bytes of records [rank*R, (rank+1)*R)
-        grp = XD.TorchGroup(dev)
+        exchange = "nvlink peer memory (symmetric buffers, exb_peer_allgather_block + exb_peer_count_reduce)"
+        try:
+            if os.environ.get("EXB_EXCHANGE", "peer") != "peer":
+                raise RuntimeError("EXB_EXCHANGE=%s" % os.environ["EXB_EXCHANGE"])
+            grp = XD.PeerGroup(dev)
+            ok = 1
+        except Exception as ex:  # not NVLink peers of one box / symmetric memory unavailable
+            sys.stderr.write("rank %d: peer-memory exchange unavailable (%s); using NCCL\n" % (rank, ex))
+            grp, ok = None, 0
+        okt = torch.tensor([ok], dtype=torch.int64, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()) == 0:  # all ranks take the same path
+            grp = XD.TorchGroup(dev)
+            exchange = "nccl all-gather (128 B per shard) + all-reduce (64 B)"
         owns = grp.all_gather_rows([own])[:, 0]
         off0 = int(owns[:rank].sum())  # file offset of record rank*R
         lo = off0 + delta(rank)
@@ -289,12 +304,8 @@ def main():
         def step(timers=None):
             if timers is not None:
                 timers[0].record()
-            blk = sharded.scan()
-            if timers is not None:
-                timers[1].record()
-            dist.all_gather_into_tensor(sharded.blocks, blk)
-            sharded.resolve(sharded.blocks, rank)
-            dist.all_reduce(sharded.total)  # COUNT / sums across shards (64 bytes over NVLink)
+            # scan -> exchange of the result blocks -> compose + resolve -> reduce of COUNT / sums (dist.py)
+            sharded.step(after_scan=timers[1].record if timers is not None else None)
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -406,8 +417,11 @@ def main():
             "clocks": sampler.summary(),
             # N=1: fastq_tile_kernel, exclusive_scan_kernel, fastq_fused_combine_kernel (+ 3 cudaMemsetAsync);
             # N>1 adds per rank: fastq_compose_prev_kernel + a second fastq_fused_combine_kernel (ranks >= 1)
-            "gpu_launches": (3 if world == 1 else 5) * args.steps,
+            # peer-memory exchange adds exb_peer_allgather_block + exb_peer_count_reduce (7 of this library's kernels per step)
+            "gpu_launches": (3 if world == 1 else (7 if exchange.startswith("nvlink") else 5)) * args.steps,
         }
+        if world > 1:
+            line["exchange"] = exchange
         if e2e:
             line["e2e"] = e2e
         if cpu:

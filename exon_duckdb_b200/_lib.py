@@ -97,11 +97,16 @@ SIGNATURES = {
     "exb_fastq_scan_resolve": (_i32, [_i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_fastq_scan_filter_resolve": (_i32, [_i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i32, _vp, _i64, _vp]),
     "exb_fastq_compose_prev": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
+    "exb_peer_bytes": (_i64, []),
+    "exb_peer_blocks_offset": (_i64, [_u64]),
+    "exb_peer_allgather_block": (_i32, [_vp, _i32, _i32, _vp, _u64, _vp]),
+    "exb_peer_count_reduce": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _u64, _vp, _vp]),
     "exb_scan_result_store": (_i32, [_vp, C.POINTER(ScanResult), _vp]),
     "exb_scan_result_fetch": (_i32, [_vp, C.POINTER(ScanResult), _vp]),
     "exb_fastq_filter": (_i32, [_vp, _vp, _vp, _vp, _i64, C.POINTER(Predicate), _i32, _vp, _vp, _vp, _vp]),
     "exb_fastq_fields": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "exb_exclusive_scan_u32": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp]),
+    "exb_exclusive_scan_u32_multi": (_i32, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _i64, _vp]),
     "exb_select_rows": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "exb_fastq_gather": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "exb_fasta_scan": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),

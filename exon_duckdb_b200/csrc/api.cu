@@ -14,6 +14,7 @@
 namespace exb {
 // record_ops.cu
 cudaError_t exclusive_scan_launch_u32(const uint32_t*, int64_t, int64_t*, TileSlot*, unsigned long long*, cudaStream_t);
+cudaError_t exclusive_scan_launch_u32_multi(const uint32_t*, int64_t, int, int64_t, int64_t*, int64_t, TileSlot*, unsigned long long*, cudaStream_t);
 cudaError_t exclusive_scan_launch_u8(const uint8_t*, int64_t, int64_t*, TileSlot*, unsigned long long*, cudaStream_t);
 int64_t scan_tiles(int64_t n);
 cudaError_t select_rows_launch(const uint8_t*, const int64_t*, int64_t, int64_t*, cudaStream_t);
@@ -378,6 +379,18 @@ int exb_exclusive_scan_u32(const uint32_t* d_in, int64_t n, int64_t* d_out, void
     int rc = carve(d_workspace, workspace_bytes, scan_tiles(n), st, &w);
     if (rc) return rc;
     cudaError_t e = exclusive_scan_launch_u32(d_in, n, d_out, w.slots, w.ticket, st);
+    if (e != cudaSuccess) return cuda_fail(e, "exclusive_scan launch");
+    return 0;
+}
+
+int exb_exclusive_scan_u32_multi(const uint32_t* d_in, int64_t n, int cols, int64_t in_stride, int64_t* d_out, int64_t out_stride,
+                                 void* d_workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cols < 1 || cols > 8) return set_err(EXB_ERR_ARG, "exb_exclusive_scan_u32_multi: cols must be 1..8");
+    Workspace w;  // chains are one 8-byte word per tile and column, packed column after column; tickets sit in the header
+    int rc = carve_bytes(d_workspace, workspace_bytes, (int64_t)cols * scan_tiles(n) * 8 + 64, st, &w);
+    if (rc) return rc;
+    cudaError_t e = exclusive_scan_launch_u32_multi(d_in, n, cols, in_stride, d_out, out_stride, w.slots, w.ticket, st);
     if (e != cudaSuccess) return cuda_fail(e, "exclusive_scan launch");
     return 0;
 }

@@ -205,6 +205,15 @@ __device__ __forceinline__ void fa_copy(uint8_t* s_out, const uint8_t* sbytes, i
     for (int i = done + first; i < len; i += step) s_out[dst + i] = sbytes[sidx(src + i)];
 }
 
+// 128 x (number of bytes < 0x40 among the 16): bit 7 of x | x << 1 is set iff bit 7 or bit 6 of the byte is
+__device__ __forceinline__ uint32_t low_count128(const uint4& v, uint32_t acc) {
+    acc = __dp4a(~(v.x | (v.x << 1)) & 0x80808080u, 0x01010101u, acc);
+    acc = __dp4a(~(v.y | (v.y << 1)) & 0x80808080u, 0x01010101u, acc);
+    acc = __dp4a(~(v.z | (v.z << 1)) & 0x80808080u, 0x01010101u, acc);
+    acc = __dp4a(~(v.w | (v.w << 1)) & 0x80808080u, 0x01010101u, acc);
+    return acc;
+}
+
 // ---------------------------------------------------------------- the tile analysis (shared by K1 / K2 / K3)
 // MODE 0: summary.  MODE 1: per-record outputs (state and bases known).  MODE 2: compaction (state and kept base known).
 struct FaTileIn {  // what K2 / K3 know about the tile from the scan
@@ -225,12 +234,19 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
 
     // ---- A. dense masks of the lane's row
     uint64_t pm[2], gm[2];
+    uint32_t low128 = 0;  // 128 x the number of bytes < 0x40 in the row (MODE 0: anything but LF among them = irregular tile)
     {
         const int sw = lane & 7;
         const uint4* row = d + lane * 8;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint4 c0 = row[(4 * h + 0) ^ sw], c1 = row[(4 * h + 1) ^ sw], c2 = row[(4 * h + 2) ^ sw], c3 = row[(4 * h + 3) ^ sw];
+            if (MODE == 0) {
+                low128 = low_count128(c0, low128);
+                low128 = low_count128(c1, low128);
+                low128 = low_count128(c2, low128);
+                low128 = low_count128(c3, low128);
+            }
             pm[h] = ((uint64_t)(nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16)) << 32) |
                     (nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16));
             gm[h] = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
@@ -245,6 +261,39 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
     const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
     const int ex_cnt = (int)(ex >> 16), n_events = (int)(tot >> 16);
     const int ex_g = (int)(ex & 0xFFFFu), total_g = (int)(tot & 0xFFFFu);
+
+    // ---- fast path of the summary pass: a full interior tile whose only bytes below 0x40 are its LFs has no '>' (no
+    // record starts, no header), no CR and no padding, so its summary follows from the dense masks alone -- the
+    // per-newline walk below (2-3 rounds for 60-column lines) is skipped.  Header tiles carry digits / spaces / '>' and
+    // take the general path.  C3: 739 k of 745 k tiles are regular.
+    if (MODE == 0) {
+        const bool regular = tile != 0 && g.s0 == 0 && g.data_end == WT_BYTES && !g.virt;
+        const bool odd = (int)(low128 >> 7) != cnt;
+        if (regular && !__any_sync(0xffffffffu, odd)) {
+            const uint32_t have = __ballot_sync(0xffffffffu, cnt > 0);
+            FaTile t;
+            if (have == 0) {  // one piece of a long line
+                t.a = 0;
+                t.rest = 0;
+                t.head = (uint32_t)WT_BYTES | ((uint32_t)total_g << 16);
+                t.pos0 = 0xFFFFu;
+            } else {
+                const int first = __ffs((int)have) - 1, last = 31 - __clz((int)have);
+                const int fr = pm[0] ? __ffsll((long long)pm[0]) - 1 : 64 + __ffsll((long long)pm[1]) - 1;       // first LF of my row
+                const int lr = pm[1] ? 127 - __clzll((long long)pm[1]) : 63 - __clzll((long long)pm[0]);        // last LF of my row
+                const int gb = ex_g + (fr < 64 ? __popcll(gm[0] & low_bits64(fr)) : g0 + __popcll(gm[1] & low_bits64(fr - 64)));
+                const int pos0 = __shfl_sync(0xffffffffu, lane * ROW_BYTES + fr, first);
+                const int head_g = __shfl_sync(0xffffffffu, gb, first);
+                const int c_last = __shfl_sync(0xffffffffu, lane * ROW_BYTES + lr, last);
+                t.a = FT_HAS_NL | (c_last + 1 >= WT_BYTES ? FT_ENDS_NL : 0u);
+                t.rest = (uint32_t)(WT_BYTES - pos0 - n_events) | ((uint32_t)(total_g - head_g) << 16);
+                t.head = (uint32_t)pos0 | ((uint32_t)head_g << 16);
+                t.pos0 = (uint32_t)pos0;
+            }
+            if (lane == 0) *summary = t;
+            return;
+        }
+    }
     s_gm[2 * lane] = gm[0];
     s_gm[2 * lane + 1] = gm[1];
     s_gex[2 * lane] = ex_g;

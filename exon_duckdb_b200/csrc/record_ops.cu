@@ -11,6 +11,7 @@
 //                              Definition::from_str (not in the reference tree)
 #include "common.cuh"
 #include "exon_b200_internal.h"
+#include "tma_tile.cuh"
 #include "x87div.h"
 
 namespace exb {
@@ -89,13 +90,20 @@ struct alignas(16) SumState {
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = BLOCK_THREADS * SCAN_ITEMS;
 
+// blockIdx.y = column: `cols` independent scans (their own chain and ticket) share one launch -- the four field-length
+// columns of a FASTQ table cost one launch latency instead of four.
 template <typename T>
 __global__ void __launch_bounds__(BLOCK_THREADS) exclusive_scan_kernel(const T* __restrict__ in, int64_t n, int64_t* __restrict__ out,
-                                                                      TileSlot* slots, unsigned long long* ticket, int64_t n_tiles) {
+                                                                      TileSlot* slots, unsigned long long* ticket, int64_t n_tiles,
+                                                                      int64_t in_stride, int64_t out_stride) {
     __shared__ int64_t s_tile_id;
     __shared__ uint64_t s_warp[WARPS];
     __shared__ int64_t s_excl;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    in += (int64_t)blockIdx.y * in_stride;
+    out += (int64_t)blockIdx.y * out_stride;
+    slots = reinterpret_cast<TileSlot*>(reinterpret_cast<uint64_t*>(slots) + (int64_t)blockIdx.y * n_tiles);
+    ticket += blockIdx.y;
     if (t == 0) s_tile_id = (int64_t)atomicAdd(ticket, 1ull);
     __syncthreads();
     const int64_t tile = s_tile_id;
@@ -133,14 +141,22 @@ cudaError_t exclusive_scan_launch_u32(const uint32_t* in, int64_t n, int64_t* ou
                                       cudaStream_t st) {
     int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (n_tiles == 0) n_tiles = 1;
-    exclusive_scan_kernel<uint32_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles);
+    exclusive_scan_kernel<uint32_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles, 0, 0);
+    return cudaGetLastError();
+}
+cudaError_t exclusive_scan_launch_u32_multi(const uint32_t* in, int64_t n, int cols, int64_t in_stride, int64_t* out, int64_t out_stride,
+                                            TileSlot* slots, unsigned long long* ticket, cudaStream_t st) {
+    int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (n_tiles == 0) n_tiles = 1;
+    exclusive_scan_kernel<uint32_t><<<dim3((unsigned)n_tiles, (unsigned)cols), BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles,
+                                                                                                    in_stride, out_stride);
     return cudaGetLastError();
 }
 cudaError_t exclusive_scan_launch_u8(const uint8_t* in, int64_t n, int64_t* out, TileSlot* slots, unsigned long long* ticket,
                                      cudaStream_t st) {
     int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (n_tiles == 0) n_tiles = 1;
-    exclusive_scan_kernel<uint8_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles);
+    exclusive_scan_kernel<uint8_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles, 0, 0);
     return cudaGetLastError();
 }
 int64_t scan_tiles(int64_t n) {
@@ -176,6 +192,30 @@ struct FqLines {
     }
 };
 
+// Position of the first ' ' in [hs, e0), or e0.  A thread reads its header in 64-byte windows of four ALIGNED 16-byte
+// loads issued together (a byte-at-a-time walk is ~35 dependent loads for an Illumina header), builds the 64-bit
+// equality mask with the tile kernels' SWAR + IDP.4A helpers and takes the first set bit inside the range.  The last
+// window may read up to 15 bytes past e0 <= n: inside the 64-byte slack every input buffer carries.
+__device__ __forceinline__ int64_t first_space(const uint8_t* __restrict__ buf, int64_t hs, int64_t e0) {
+    const uint32_t c7f = 0x7F7F7F7Fu, pat = 0x20202020u;
+    int64_t base = hs - (int64_t)((uintptr_t)(buf + hs) & 15);
+    while (base < e0) {
+        uint64_t m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (base + 16 * k < e0) {
+                const uint4 v = *reinterpret_cast<const uint4*>(buf + base + 16 * k);
+                m |= (uint64_t)nl_mask16r(v, c7f, pat) << (16 * k);
+            }
+        }
+        if (hs > base) m &= ~0ull << (int)(hs - base);
+        if (e0 - base < 64) m &= (1ull << (int)(e0 - base)) - 1ull;
+        if (m) return base + (__ffsll((long long)m) - 1);
+        base += 64;
+    }
+    return e0;
+}
+
 template <typename OffT>
 __global__ void __launch_bounds__(256) fastq_fields_kernel(FqLines<OffT> L, const int64_t* __restrict__ sel, int64_t n_rows,
                                                            uint32_t* __restrict__ lens, uint8_t* __restrict__ desc_valid,
@@ -185,8 +225,7 @@ __global__ void __launch_bounds__(256) fastq_fields_kernel(FqLines<OffT> L, cons
         const int64_t g = 4 * r;
         int64_t s0 = L.start(g), e0 = L.end(g, s0);
         int64_t hs = s0 + 1;  // skip '@'
-        int64_t sp = hs;
-        while (sp < e0 && L.buf[sp] != ' ') sp++;  // first SPACE splits name / description
+        const int64_t sp = first_space(L.buf, hs, e0);  // first SPACE splits name / description
         uint32_t name_len = (uint32_t)(sp - hs);
         uint32_t desc_len = sp < e0 ? (uint32_t)(e0 - sp - 1) : 0u;
         int64_t s1 = (int64_t)L.line_end[g] + 1, e1 = L.end(g + 1, s1);
@@ -283,59 +322,76 @@ __global__ void __launch_bounds__(GS_THREADS) gather_span_kernel(const uint8_t* 
                                                                  int64_t n_rows, uint8_t* __restrict__ out) {
     __shared__ int64_t s_off[GS_ROWS + 1];
     __shared__ int64_t s_src[GS_ROWS];
-    __shared__ int64_t s_row0;
     const int t = threadIdx.x;
     const int64_t total = off[n_rows];
     // spans are aligned to 16 bytes of the OUTPUT ADDRESS so that chunk stores are aligned whatever `out` is
     const int mis = (int)((uintptr_t)out & 15);
-    const int64_t span_lo = (int64_t)blockIdx.x * GS_SPAN - mis;  // may be negative for block 0
-    int64_t lo = span_lo < 0 ? 0 : span_lo;
-    const int64_t hi = span_lo + GS_SPAN < total ? span_lo + GS_SPAN : total;
-    if (lo >= hi) return;
-    if (t == 0) {  // last row r with off[r] <= lo
-        int64_t a = 0, b = n_rows;  // invariant: off[a] <= lo < off[b] (off[n_rows] = total > lo)
-        while (b - a > 1) {
-            const int64_t m = (a + b) >> 1;
-            if (off[m] <= lo) a = m;
-            else b = m;
-        }
-        s_row0 = a;
-    }
-    __syncthreads();
-    int64_t row0 = s_row0;
-    while (lo < hi) {
-        // rows row0 .. row0 + cnt cover [lo, batch_hi)
-        const int64_t left = n_rows - row0;
-        const int cnt = left < GS_ROWS ? (int)left : GS_ROWS;
-        __syncthreads();
-        for (int i = t; i <= cnt; i += GS_THREADS) s_off[i] = off[row0 + i];
-        for (int i = t; i < cnt; i += GS_THREADS) s_src[i] = srcfn(row0 + i);
-        __syncthreads();
-        int64_t batch_hi = s_off[cnt] < hi ? s_off[cnt] : hi;
-        // chunks: dst address of byte p is out + p; chunk boundaries at (p + mis) % 16 == 0
-        const int64_t c0 = (lo + mis) >> 4, c1 = (batch_hi + mis + 15) >> 4;
-        for (int64_t c = c0 + t; c < c1; c += GS_THREADS) {
-            int64_t p0 = (c << 4) - mis, p1 = p0 + 16;
-            if (p0 < lo) p0 = lo;
-            if (p1 > batch_hi) p1 = batch_hi;
-            // local row of p0: last i with s_off[i] <= p0
-            int a = 0, b = cnt;
+    // persistent blocks: the column's size is known only on the device, so the grid is sized for the machine and
+    // every block walks the spans blockIdx.x, blockIdx.x + gridDim.x, ... (all loop bounds are block-uniform)
+    for (int64_t span = blockIdx.x;; span += gridDim.x) {
+        const int64_t span_lo = span * GS_SPAN - mis;  // negative for span 0 when out is misaligned
+        if (span_lo >= total) break;
+        int64_t lo = span_lo < 0 ? 0 : span_lo;
+        const int64_t hi = span_lo + GS_SPAN < total ? span_lo + GS_SPAN : total;
+        if (lo >= hi) continue;
+        // last row r with off[r] <= lo: a GS_THREADS-ary search by the whole block (3 rounds of one global load each
+        // for 16 M rows; a one-thread binary search costs ~22 dependent loads and was 2/3 of the kernel's time)
+        int64_t row0;
+        {
+            int64_t a = 0, b = n_rows;  // invariant: off[a] <= lo < off[b] (off[n_rows] = total > lo)
             while (b - a > 1) {
-                const int m = (a + b) >> 1;
-                if (s_off[m] <= p0) a = m;
-                else b = m;
+                const int64_t step = (b - a + GS_THREADS - 1) / GS_THREADS;
+                const int64_t m = a + (int64_t)(t + 1) * step;
+                const int c = __syncthreads_count(m < b && off[m] <= lo);  // off is monotone: the true probes are a prefix
+                const int64_t na = a + (int64_t)c * step;
+                b = na + step < b ? na + step : b;
+                a = na;
             }
-            if (p1 - p0 == 16 && p1 <= s_off[a + 1]) {
-                *reinterpret_cast<uint4*>(out + p0) = load16_unaligned(buf + s_src[a] + (p0 - s_off[a]));
-            } else {
-                for (int64_t p = p0; p < p1; p++) {
-                    while (s_off[a + 1] <= p) a++;  // skips empty rows; p < batch_hi <= s_off[cnt] bounds it
-                    out[p] = buf[s_src[a] + (p - s_off[a])];
+            row0 = a;
+        }
+        while (lo < hi) {
+            const int64_t left = n_rows - row0;
+            const int cap = left < GS_ROWS ? (int)left : GS_ROWS;
+            __syncthreads();
+            for (int i = t; i <= cap; i += GS_THREADS) s_off[i] = off[row0 + i];
+            __syncthreads();
+            // rows that begin before `hi` are the ones this span needs (s_off[0] <= lo < hi, so at least one); only
+            // those pay for their source address (SrcFastq: two dependent scattered loads per row)
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < GS_ROWS / GS_THREADS; k++) {
+                const int i = t + k * GS_THREADS;
+                cnt += __syncthreads_count(i < cap && s_off[i] < hi);
+            }
+            for (int i = t; i < cnt; i += GS_THREADS) s_src[i] = srcfn(row0 + i);
+            __syncthreads();
+            // rows row0 .. row0 + cnt cover [lo, batch_hi)
+            const int64_t batch_hi = s_off[cnt] < hi ? s_off[cnt] : hi;
+            // chunks: dst address of byte p is out + p; chunk boundaries at (p + mis) % 16 == 0
+            const int64_t c0 = (lo + mis) >> 4, c1 = (batch_hi + mis + 15) >> 4;
+            for (int64_t c = c0 + t; c < c1; c += GS_THREADS) {
+                int64_t p0 = (c << 4) - mis, p1 = p0 + 16;
+                if (p0 < lo) p0 = lo;
+                if (p1 > batch_hi) p1 = batch_hi;
+                // local row of p0: last i with s_off[i] <= p0
+                int a = 0, b = cnt;
+                while (b - a > 1) {
+                    const int m = (a + b) >> 1;
+                    if (s_off[m] <= p0) a = m;
+                    else b = m;
+                }
+                if (p1 - p0 == 16 && p1 <= s_off[a + 1]) {
+                    *reinterpret_cast<uint4*>(out + p0) = load16_unaligned(buf + s_src[a] + (p0 - s_off[a]));
+                } else {
+                    for (int64_t p = p0; p < p1; p++) {
+                        while (s_off[a + 1] <= p) a++;  // skips empty rows; p < batch_hi <= s_off[cnt] bounds it
+                        out[p] = buf[s_src[a] + (p - s_off[a])];
+                    }
                 }
             }
+            lo = batch_hi;
+            row0 += cnt;  // the batch ended on its last row (lo = off[row0 + cnt]), or lo == hi and the loop ends
         }
-        lo = batch_hi;
-        row0 += cnt;  // the batch ended on its last row (lo = off[row0 + cnt]), or lo == hi and the loop ends
     }
 }
 
@@ -343,8 +399,10 @@ template <typename SrcFn>
 static cudaError_t gather_span_launch(const uint8_t* buf, SrcFn fn, const int64_t* off, int64_t n_rows, int64_t total_hint, uint8_t* out,
                                       cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
-    // the grid must cover off[n_rows] bytes, which only the device knows: callers pass an upper bound
+    // off[n_rows] is known only on the device; total_hint (an upper bound) merely keeps tiny columns from launching a full grid
     int64_t blocks = (total_hint + 15 + GS_SPAN - 1) / GS_SPAN + 1;
+    const int64_t machine = 148 * 8;  // 8 resident blocks of 256 threads per SM
+    if (blocks > machine) blocks = machine;
     if (blocks < 1) blocks = 1;
     gather_span_kernel<SrcFn><<<(unsigned)blocks, GS_THREADS, 0, st>>>(buf, fn, off, n_rows, out);
     return cudaGetLastError();

@@ -204,6 +204,14 @@ def exclusive_scan_u32(x, n=None):
     return out
 
 
+def exclusive_scan_u32_multi(x, n, cols):
+    """cols exclusive scans in one launch: x = uint32[cols * n] (column after column) -> int64[cols, n + 1]."""
+    out = torch.empty((cols, n + 1), dtype=torch.int64, device=x.device)
+    ws = workspace(4 * n * cols + 16, x.device)
+    check(lib().exb_exclusive_scan_u32_multi(_ptr(x), n, cols, n, _ptr(out), n + 1, _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
 def select_rows(pas):
     n = pas.numel()
     off = torch.empty(n + 1, dtype=torch.int64, device=pas.device)
@@ -253,13 +261,12 @@ def fastq_table(buf, columns=None, preds=(), n=None):
     wide = 1 if scan.wide else 0
     check(lib().exb_fastq_fields(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, _ptr(lens), _ptr(valid), None, _stream()))
     out = {}
-    # offsets of every requested column first, then ONE host round trip for the column sizes
-    offs = {name: exclusive_scan_u32(lens[FASTQ_COLUMNS.index(name) * n_rows:(FASTQ_COLUMNS.index(name) + 1) * n_rows] if n_rows else lens, n_rows)
-            for name in columns}
-    totals = torch.stack([offs[name][n_rows] for name in columns]).cpu().tolist() if columns else []
-    for name, total in zip(columns, totals):
+    # Arrow offsets of all four columns in ONE launch, then ONE host round trip for the column sizes
+    offs = exclusive_scan_u32_multi(lens, n_rows, 4)
+    totals = offs[:, n_rows].cpu().tolist()
+    for name in columns:
         c = FASTQ_COLUMNS.index(name)
-        off = offs[name]
+        off, total = offs[c], totals[c]
         data = _empty(total, torch.uint8, dev)
         check(lib().exb_fastq_gather(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, c, _ptr(lens), _ptr(off),
                                      _ptr(data), _stream()))
@@ -335,12 +342,13 @@ def fasta_table(buf, columns=None, n=None):
         bad = int(err.item())
         if bad != -1:
             raise FormatError("FASTA definition without a name at byte %d" % bad, bad)
+        offs = exclusive_scan_u32_multi(lens, n_rows, 2)
+        totals = offs[:, n_rows].cpu().tolist()
         for c, name in enumerate(["id", "description"]):
             if name not in columns:
                 continue
             ln = lens[c * n_rows:(c + 1) * n_rows] if n_rows else lens
-            off = exclusive_scan_u32(ln, n_rows)
-            total = int(off[n_rows].item())
+            off, total = offs[c], totals[c]
             data = _empty(total, torch.uint8, dev)
             start = starts[c * n_rows:(c + 1) * n_rows] if n_rows else starts
             check(lib().exb_gather_ranges(_ptr(buf), _ptr(start), _ptr(ln), _ptr(off), n_rows, _ptr(data), total, _stream()))

@@ -68,6 +68,38 @@ class TorchGroup:
         return t
 
 
+class PeerGroup(TorchGroup):
+    """TorchGroup whose per-step exchange runs over NVLink peer memory with the library's own kernels
+    (csrc/peer_exchange.cu) instead of NCCL: every rank owns a symmetric buffer (torch symmetric memory: cuMem
+    allocations mapped into every peer of the box) and stores its 128-byte block / 64-byte aggregates straight into
+    its peers' buffers.  torch.distributed still does the plumbing (rendezvous, the one-off exchange of the static
+    shard ranges, barriers).  Raises if the ranks are not NVLink peers of one box -- callers fall back to TorchGroup."""
+
+    def __init__(self, device, group=None):
+        super().__init__(device, group)
+        import torch.distributed._symmetric_memory as symm_mem
+
+        torch, dist = self.torch, self.dist
+        try:  # needed by older torch releases, a deprecated no-op in newer ones
+            symm_mem.enable_symm_mem_for_group((group if group is not None else dist.group.WORLD).group_name)
+        except Exception:
+            pass
+        nbytes = int(_lib.lib().exb_peer_bytes())
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        assert self.handle.world_size == self.world and self.handle.rank == self.rank
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # nobody stores into a peer's buffer before every buffer has been zeroed
+        self.d_peers = int(self.handle.buffer_ptrs_dev)
+        self.seq = 0
+
+    def blocks_view(self, seq):
+        """The gathered result blocks of step `seq` in this rank's own buffer: int64[world * 16]."""
+        off = int(_lib.lib().exb_peer_blocks_offset(seq))
+        return self.buf[off:off + 128 * self.world].view(self.torch.int64)
+
+
 class LocalGroup:
     """G shards held by one process (tests, multi-shard runs on one GPU): the "collective" completes once every shard
     has contributed its row."""
@@ -260,9 +292,35 @@ class ShardedFastqCount:
         self.total[6] = (blk[0] & 3) if s.is_last else 0
         return self.total
 
-    def step(self):
+    def resolve_local(self, blocks, rank):
+        """compose + resolve kernels only (no aggregate bookkeeping): the peer-memory reduce does that on the device."""
+        from . import device as D
+
+        s = self.shard
+        if rank > 0:
+            L = _lib.lib()
+            _lib.check(L.exb_fastq_compose_prev(D._ptr(blocks), D._ptr(self.d_ranges), self.world, rank, D._ptr(self.true_prev), D._stream()))
+            _lib.check(L.exb_fastq_scan_filter_resolve(s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.true_prev), self.arr, self.k,
+                                                       D._ptr(self.c.agg), 0, D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
+            self.c._res = None
+
+    def step(self, after_scan=None):
+        """One pass over the shard + the exchange; every launch is asynchronous on the current stream.
+        after_scan: optional callable invoked between the scan and the exchange (bench.py records a CUDA event there)."""
+        from . import device as D
+
         g = self.group
         blk = self.scan()
+        if after_scan is not None:
+            after_scan()
+        if isinstance(g, PeerGroup):  # 5 launches of this library per step, no NCCL
+            L = _lib.lib()
+            g.seq += 1
+            _lib.check(L.exb_peer_allgather_block(g.d_peers, g.rank, g.world, D._ptr(blk), g.seq, D._stream()))
+            self.resolve_local(g.blocks_view(g.seq), g.rank)
+            _lib.check(L.exb_peer_count_reduce(g.d_peers, g.rank, g.world, D._ptr(self.c.ws), D._ptr(self.c.agg), 1 if self.shard.is_last else 0,
+                                               g.seq, D._ptr(self.total), D._stream()))
+            return self.total
         g.dist.all_gather_into_tensor(self.blocks, blk, group=g.group)
         self.resolve(self.blocks, g.rank)
         g.all_reduce_sum(self.total)
@@ -274,6 +332,8 @@ def check_count(total):
     from .device import FormatError
 
     t = [int(x) for x in total.tolist()]
+    if t[7] < 0:
+        raise RuntimeError("peer-memory exchange timed out: a rank of the box did not answer")
     if t[7]:
         raise FormatError("malformed FASTQ record (in %d shard(s))" % t[7])
     if t[6]:

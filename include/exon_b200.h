@@ -284,6 +284,25 @@ EXB_API int exb_fastq_scan_filter_resolve(int64_t begin, int64_t n, int is_final
  * predecessor of shard `rank` (>= 1) to d_prev_out (128 bytes), ready to be passed as d_prev_workspace. */
 EXB_API int exb_fastq_compose_prev(const void *d_blocks, const int64_t *d_ranges, int world, int rank, void *d_prev_out,
                                    void *stream);
+/* ---- shard exchange over NVLink peer memory (exon_duckdb_b200/csrc/peer_exchange.cu) ----------------
+ * What byte-range shards must agree on is one 128-byte scan result block per shard and 8 int64 aggregates.  Every
+ * rank owns a symmetric buffer of exb_peer_bytes() bytes (zeroed, then a barrier, before step 1) that every peer
+ * has mapped; d_peers = device array of `world` pointers to those buffers in rank order (torch symmetric memory:
+ * handle.buffer_ptrs_dev).  `seq` = step number, 1, 2, ... identical on every rank.  world <= 16.
+ *   exb_peer_allgather_block  stores d_block (128 B) into every peer's buffer and waits for every peer's block:
+ *                             afterwards the `world` blocks sit, in rank order and 128 B apart, at
+ *                             own_buffer + exb_peer_blocks_offset(seq) (the input of exb_fastq_compose_prev).
+ *   exb_peer_count_reduce     d_total[0..8) = sum over ranks of {d_agg[0..6), lines of the file mod 4 (last shard),
+ *                             1 if the shard's result block (first 128 B of d_workspace) reports a malformed record};
+ *                             d_total[7] = -1 if a peer did not answer within 10 s.
+ * Replaces ncclAllGather + ncclAllReduce of the same bytes (2 x ~150 us at 8 ranks) with two ~10 us launches. */
+EXB_API int64_t exb_peer_bytes(void);
+EXB_API int64_t exb_peer_blocks_offset(uint64_t seq);
+EXB_API int exb_peer_allgather_block(void *const *d_peers, int rank, int world, const void *d_block, uint64_t seq,
+                                     void *stream);
+EXB_API int exb_peer_count_reduce(void *const *d_peers, int rank, int world, const void *d_workspace,
+                                  const int64_t *d_agg, int is_last, uint64_t seq, int64_t *d_total, void *stream);
+
 /* Writes *src where a scan expects a predecessor's result block (d_dst: >= 128 bytes of device memory). */
 EXB_API int exb_scan_result_store(void *d_dst, const exb_scan_result *src, void *stream);
 
@@ -299,6 +318,11 @@ EXB_API int exb_fastq_fields(const void *d_buf, int64_t begin, int64_t n, const 
  * d_workspace: exb_scan_workspace_bytes(4 * n) zero-initialised by the call. */
 EXB_API int exb_exclusive_scan_u32(const uint32_t *d_in, int64_t n, int64_t *d_out, void *d_workspace,
                                    int64_t workspace_bytes, void *stream);
+/* The same for `cols` (<= 8) independent columns in ONE launch: column c reads d_in + c * in_stride and writes
+ * d_out + c * out_stride (n + 1 entries each).  The four field-length columns of exb_fastq_fields become the
+ * four Arrow offset arrays of a read_fastq batch this way.  d_workspace: exb_scan_workspace_bytes(4 * n * cols). */
+EXB_API int exb_exclusive_scan_u32_multi(const uint32_t *d_in, int64_t n, int cols, int64_t in_stride, int64_t *d_out,
+                                         int64_t out_stride, void *d_workspace, int64_t workspace_bytes, void *stream);
 
 /* Row ids of the records whose d_pass byte is set: d_sel[0..count), count -> d_offsets[n]
  * where d_offsets (int64[n+1]) is scratch. */

@@ -15,7 +15,13 @@ import torch
 from exon_duckdb_b200 import _lib, device as D
 
 
+ITERS = None  # --iters overrides every call (profiling runs under ncu)
+WARM = None
+
+
 def timeit(fn, iters=10, warm=3):
+    iters = ITERS or iters
+    warm = warm if WARM is None else WARM
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -38,7 +44,12 @@ def main():
     ap.add_argument("--contigs", type=int, default=2400)
     ap.add_argument("--contig-len", type=int, default=500_000)
     ap.add_argument("--out", default="gpurun_out/paths.json")
+    ap.add_argument("--iters", type=int, default=0)
+    ap.add_argument("--warm", type=int, default=-1)
     args = ap.parse_args()
+    global ITERS, WARM
+    ITERS = args.iters or None
+    WARM = args.warm if args.warm >= 0 else None
     dev = torch.device("cuda:0")
     peak = 6548.2
     try:
