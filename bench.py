@@ -208,11 +208,17 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    from exon_duckdb_b200.dist import bind_to_gpu_numa_node
+    numa_node = bind_to_gpu_numa_node(local)  # before any pinned allocation: host buffers land next to the GPU
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries exactly one JSON line
+        # NCCL writes its version banner to fd 1 at communicator creation; stdout carries exactly one JSON line, so fd 1
+        # points at stderr until that line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
@@ -422,10 +428,14 @@ def main():
         }
         if world > 1:
             line["exchange"] = exchange
+        line["numa_node"] = numa_node
         if e2e:
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

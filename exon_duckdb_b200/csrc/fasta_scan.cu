@@ -234,14 +234,14 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
 
     // ---- A. dense masks of the lane's row
     uint64_t pm[2], gm[2];
-    uint32_t low128 = 0;  // 128 x the number of bytes < 0x40 in the row (MODE 0: anything but LF among them = irregular tile)
+    uint32_t low128 = 0;  // 128 x the number of bytes < 0x40 in the row (MODE 0 / 2: anything but LF among them = irregular tile)
     {
         const int sw = lane & 7;
         const uint4* row = d + lane * 8;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint4 c0 = row[(4 * h + 0) ^ sw], c1 = row[(4 * h + 1) ^ sw], c2 = row[(4 * h + 2) ^ sw], c3 = row[(4 * h + 3) ^ sw];
-            if (MODE == 0) {
+            if (MODE == 0 || MODE == 2) {
                 low128 = low_count128(c0, low128);
                 low128 = low_count128(c1, low128);
                 low128 = low_count128(c2, low128);
@@ -292,6 +292,62 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
             }
             if (lane == 0) *summary = t;
             return;
+        }
+    }
+    // ---- fast path of the compaction pass: the same regular tile, entered in a sequence line (or at a line start: no
+    // '>' in the tile, so that line is sequence too).  Every byte but the LFs is kept, so the lane copies the (up to
+    // four) LF-free pieces of ITS OWN row to the staging row at lane * 128 - (LFs before the row): no newline walk, no
+    // scans, and source words come from one swizzled row (address math is 3 ops a word).
+    bool fast2 = false;
+    if (MODE == 2) {
+        const bool regular = tile != 0 && g.s0 == 0 && g.data_end == WT_BYTES && !g.virt && in.st != ST_H;
+        const bool odd = (int)(low128 >> 7) != cnt;
+        fast2 = regular && !__any_sync(0xffffffffu, odd);
+        if (fast2) {
+            const uint32_t* rowp = reinterpret_cast<const uint32_t*>(sbytes + lane * ROW_BYTES);
+            const int swz = lane & 7;
+            auto src_word = [&](int w) -> uint32_t { return rowp[((((w >> 2) ^ swz) << 2) | (w & 3))]; };
+            int dst = (int)(in.kept_base & 15) + lane * ROW_BYTES - ex_cnt;
+            int start = 0;
+            uint64_t m0 = pm[0], m1 = pm[1];
+            while (start < ROW_BYTES) {
+                int end;
+                if (m0) {
+                    end = __ffsll((long long)m0) - 1;
+                    m0 &= m0 - 1;
+                } else if (m1) {
+                    end = 64 + __ffsll((long long)m1) - 1;
+                    m1 &= m1 - 1;
+                } else {
+                    end = ROW_BYTES;
+                }
+                int len = end - start, src = start;
+                // bytes up to the first 4-byte boundary of the destination
+                while (len > 0 && (dst & 3)) {
+                    s_out[dst++] = (uint8_t)(src_word(src >> 2) >> ((src & 3) * 8));
+                    src++;
+                    len--;
+                }
+                const int nw = len >> 2, bs = (src & 3) * 8;
+                uint32_t* ow = reinterpret_cast<uint32_t*>(s_out + dst);
+                int sw = src >> 2;
+                uint32_t w0 = nw > 0 ? src_word(sw) : 0u;
+                for (int k = 0; k < nw; k++) {
+                    const uint32_t w1 = (bs != 0 && sw + 1 < 32) ? src_word(sw + 1) : 0u;  // bs == 0: the word is aligned
+                    ow[k] = __funnelshift_r(w0, w1, bs);
+                    w0 = bs != 0 ? w1 : (sw + 1 < 32 ? src_word(sw + 1) : 0u);
+                    sw++;
+                }
+                dst += nw * 4;
+                src += nw * 4;
+                len -= nw * 4;
+                while (len > 0) {
+                    s_out[dst++] = (uint8_t)(src_word(src >> 2) >> ((src & 3) * 8));
+                    src++;
+                    len--;
+                }
+                start = end + 1;
+            }
         }
     }
     s_gm[2 * lane] = gm[0];
@@ -347,7 +403,7 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
     const int64_t cr_limit = a.is_final ? a.n : (a.halo_n > a.n ? a.halo_n : a.n);  // a CR is dropped iff a REAL LF follows it
     int pos = 0, pg = 0;
     uint32_t hdr_after = 0;
-    for (int lo = 0; lo < n_events; lo += 32) {
+    for (int lo = 0; lo < (fast2 ? 0 : n_events); lo += 32) {
         if (lo > 0 && (lo & (FA_EV_CAP - 1)) == 0) {
             __syncwarp();
             scatter(lo);
@@ -491,7 +547,8 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
     }
     if (MODE == 2) {
         const bool tail_is_hdr = has_nl ? (c_hdr != 0) : (eff == ST_H);
-        if (!tail_is_hdr && tail_len > 0) {
+        if (fast2) run_kept += WT_BYTES - n_events;  // everything but the LFs, already staged
+        if (!fast2 && !tail_is_hdr && tail_len > 0) {
             const int dst = (int)(run_kept - in.kept_base) + (int)(in.kept_base & 15);
             const int src = c_pos + 1;
             fa_copy(s_out, sbytes, dst, src, tail_len, lane, 32);

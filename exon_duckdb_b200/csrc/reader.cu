@@ -18,9 +18,19 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <errno.h>
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "exon_b200_internal.h"
@@ -266,18 +276,137 @@ struct HBuf {  // growable pinned host buffer
     template <typename T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
-struct ChunkColumn {  // one column of the rows a chunk produced (host copies)
-    std::vector<int64_t> off;
-    std::vector<uint8_t> data;
+// Pinned host buffers are expensive to create (cudaHostAlloc pins every page) and cheap to reuse: input blocks and
+// result buffers cycle through this pool.  Shared by the reader and by every ChunkResult still held by the host, so
+// a batch may outlive the reader that produced it.
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<HBuf*> idle;
+    ~PinnedPool() {
+        for (HBuf* b : idle) delete b;
+    }
+    HBuf* get(int64_t bytes) {
+        HBuf* b = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            int best = -1, largest = -1;
+            for (int i = 0; i < (int)idle.size(); i++) {
+                if (idle[i]->cap >= bytes && (best < 0 || idle[i]->cap < idle[best]->cap)) best = i;
+                if (largest < 0 || idle[i]->cap > idle[largest]->cap) largest = i;
+            }
+            if (best < 0) best = largest;  // none fits: grow the largest one instead of leaving it idle forever
+            if (best >= 0) {
+                b = idle[best];
+                idle.erase(idle.begin() + best);
+            }
+        }
+        if (!b) b = new HBuf();
+        if (!b->need(bytes)) {
+            delete b;
+            return nullptr;
+        }
+        return b;
+    }
+    void put(HBuf* b) {
+        if (!b) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            int64_t held = b->cap;
+            for (HBuf* x : idle) held += x->cap;
+            if (held <= max_idle_bytes) {
+                idle.push_back(b);
+                return;
+            }
+        }
+        delete b;  // over the cap: unpin it
+    }
+    // One pool per process: pinning a 64 MiB block costs ~10 ms, so a query that opens a reader right after another
+    // one (DuckDB: bind opens one for the schema, init_global the real one) starts with warm buffers.
+    int64_t max_idle_bytes = 2ll << 30;
+    static std::shared_ptr<PinnedPool> shared() {
+        static std::mutex m;
+        static std::weak_ptr<PinnedPool> weak;
+        static std::shared_ptr<PinnedPool> keep;  // keeps the buffers pinned for the life of the process
+        std::lock_guard<std::mutex> lk(m);
+        if (!keep) keep = std::make_shared<PinnedPool>();
+        return keep;
+    }
+};
+
+struct ChunkColumn {  // one column of the rows a chunk produced: views into the chunk's pinned result buffers
+    const int64_t* off = nullptr;  // rows + 1 entries starting at 0; nullptr = projected out
+    const uint8_t* data = nullptr;
 };
 // The rows one input chunk produced.  Shared: every batch view handed out (exb_batch) holds a reference, so a
 // host that borrows the strings (DuckDB string_t pointers) keeps the buffers alive past the reader's next step.
+// The strings are handed out where the D2H copy put them -- no second host copy.
 struct ChunkResult {
-    std::vector<ChunkColumn> cols;
-    std::vector<uint8_t> valid;  // description validity, one byte per row
+    ChunkColumn cols[4];
+    const uint8_t* valid = nullptr;  // description validity, one byte per row
+    int64_t rows = 0;
+    std::vector<HBuf*> bufs;
+    std::shared_ptr<PinnedPool> pool;
+    ~ChunkResult() {
+        for (HBuf* b : bufs) pool->put(b);
+    }
+};
+
+// One raw block of a file as the IO thread read it: `head` bytes of headroom, then raw_len bytes.  The part of the
+// previous chunk that did not end on a record boundary is copied into the headroom, so a chunk is contiguous
+// without moving the block.
+struct Block {
+    HBuf* h = nullptr;
+    int64_t head = 0, raw_len = 0;
+    int64_t raw_file_pos = 0;  // offset of the first raw byte in the (decompressed) file
+    size_t file_idx = 0;
+    bool eof = false;          // the file ends with this block
+    std::string error;         // IO failure: the stream ends here
+    bool end = false;          // no more files
+};
+struct OutItem {
+    std::shared_ptr<ChunkResult> res;
+    int64_t counted = 0;
+    bool end = false;
+    std::string error;
+};
+template <typename T>
+struct BoundedQueue {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<T> q;
+    size_t cap;
+    bool stop = false;
+    explicit BoundedQueue(size_t c) : cap(c) {}
+    bool push(T&& v) {  // false = stopped
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return stop || q.size() < cap; });
+        if (stop) return false;
+        q.push_back(std::move(v));
+        cv.notify_all();
+        return true;
+    }
+    bool pop(T& out) {  // false = stopped
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return stop || !q.empty(); });
+        if (q.empty()) return false;
+        out = std::move(q.front());
+        q.pop_front();
+        cv.notify_all();
+        return true;
+    }
+    void shutdown() {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+        cv.notify_all();
+    }
 };
 
 // ------------------------------------------------------------------ the stream
+// Three stages, each on its own thread, connected by bounded queues:
+//   IO thread     file -> pinned blocks (plain files: four pread slices in parallel; gzip: inflate)
+//   device thread block -> H2D -> scan / filter / field split / gather kernels -> D2H into pinned result buffers
+//   caller        exb_reader_next / the Arrow stream: hands out <= batch_size-row views of a chunk's result
+// so reading block k+1, the device work of block k and the host's consumption of block k-1 overlap.
 struct Reader {
     int format = 0;  // 1 FASTA, 2 FASTQ
     int ncols = 0;
@@ -285,110 +414,205 @@ struct Reader {
     int64_t batch_size = 2048;
     std::vector<std::string> files;
     std::vector<int> file_comp;
-    size_t file_idx = 0;
-    // current file
-    FILE* fp = nullptr;
-    gzFile gz = nullptr;
-    bool file_eof = true;
-    int64_t file_pos = 0;  // offset in the (decompressed) file of in.p[0]
-    HBuf in;
-    int64_t in_len = 0;  // valid bytes in `in`
     int64_t chunk_bytes = 64ll << 20;
+    int64_t headroom = 1ll << 20;
     // filter
     std::vector<Node> nodes;
     int root = -1;
-    // device state
+    // device state (device thread only, after ensure_device)
     bool dev_ready = false;
     cudaStream_t st = nullptr;
-    DBuf d_in, d_ws, d_ws2, d_line, d_arr[4], d_lens, d_starts, d_valid, d_pass, d_pass2, d_selscratch, d_sel, d_lens2, d_starts2,
+    DBuf d_in, d_ws, d_ws2, d_line, d_arr[4], d_lens, d_starts, d_valid, d_pass, d_selscratch, d_sel, d_lens2, d_starts2,
         d_valid2, d_off, d_data, d_cst, d_hdr_start, d_hdr_end, d_seq_off, d_gc_prefix, d_seq, d_err;
-    HBuf h_off, h_data, h_valid;
-    // rows ready to be handed out
+    std::shared_ptr<PinnedPool> pool = PinnedPool::shared();
+    HBuf h_small;  // a few words for totals / flags read back between launches
+    // rows ready to be handed out (caller's thread)
     std::shared_ptr<ChunkResult> cur;
     int64_t rows = 0, next_row = 0;
     uint32_t column_mask = 0xF;  // bit c: column c is materialised (projection push-down)
     bool count_only = false;     // COUNT(*): rows are counted, nothing is gathered or copied back
     int64_t counted = 0;
-    std::string error;
+    std::string error;  // caller's thread: the failure reported to the host
+    std::string derr;   // device thread: failure of the chunk being processed
+    // pipeline
+    bool started = false, finished = false;
+    std::thread io_thread, dev_thread;
+    BoundedQueue<Block> inq{2};
+    BoundedQueue<OutItem> outq{2};
+    std::atomic<int64_t> block_bytes{0};
+    std::atomic<bool> stopping{false};
+    // device thread: the chunk being processed
+    size_t cur_file = 0;
+    int64_t cur_file_pos = 0;
+    // EXON_B200_TRACE=1: seconds spent per stage, printed when the reader closes
+    double t_io_read = 0, t_io_alloc = 0, t_io_push = 0, t_dev_pop = 0, t_dev_work = 0, t_dev_push = 0, t_call_pop = 0;
+    int64_t n_blocks = 0;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     ~Reader() {
-        close_file();
+        stopping = true;
+        inq.shutdown();
+        outq.shutdown();
+        if (io_thread.joinable()) io_thread.join();
+        if (dev_thread.joinable()) dev_thread.join();
+        for (Block& b : inq.q) pool->put(b.h);
+        cur.reset();
+        outq.q.clear();
         if (st) cudaStreamDestroy(st);
-    }
-    void close_file() {
-        if (fp) fclose(fp);
-        if (gz) gzclose(gz);
-        fp = nullptr;
-        gz = nullptr;
-        file_eof = true;
+        if (getenv("EXON_B200_TRACE"))
+            fprintf(stderr, "exon_b200 reader: %lld blocks | io: alloc %.3f read %.3f push-wait %.3f | device: pop-wait %.3f work %.3f push-wait %.3f | "
+                            "caller: pop-wait %.3f s\n", (long long)n_blocks, t_io_alloc, t_io_read, t_io_push, t_dev_pop, t_dev_work, t_dev_push, t_call_pop);
     }
     bool fail(const std::string& m) {
-        error = m;
+        derr = m;
         return false;
     }
     bool cu(cudaError_t e, const char* what) {
         if (e == cudaSuccess) return true;
-        error = std::string(what) + ": " + cudaGetErrorString(e);
+        derr = std::string(what) + ": " + cudaGetErrorString(e);
         return false;
     }
     bool rc(int code) {
         if (code == 0) return true;
-        error = exb_last_error();
+        derr = exb_last_error();
         return false;
-    }
-
-    bool open_next_file() {
-        close_file();
-        if (file_idx >= files.size()) return false;
-        const std::string& path = files[file_idx];
-        const int comp = file_comp[file_idx];
-        file_idx++;
-        if (comp == 1) {
-            gz = gzopen(path.c_str(), "rb");
-            if (!gz) return fail("could not open " + path);
-            gzbuffer(gz, 1 << 20);
-        } else if (comp == 0) {
-            fp = fopen(path.c_str(), "rb");
-            if (!fp) return fail("could not open " + path);
-        } else {
-            return fail("compression of " + path + " is not supported by this build (gzip and uncompressed are)");
-        }
-        file_eof = false;
-        file_pos = 0;
-        in_len = 0;
-        return true;
-    }
-    // top up `in` to chunk_bytes (or EOF)
-    bool fill() {
-        if (!in.need(chunk_bytes + 64, true, in_len)) return fail("out of pinned host memory");
-        while (!file_eof && in_len < chunk_bytes) {
-            int64_t want = chunk_bytes - in_len;
-            int64_t got;
-            if (gz) {
-                int g = gzread(gz, in.as<uint8_t>() + in_len, (unsigned)std::min<int64_t>(want, 1 << 30));
-                if (g < 0) return fail("gzip read error");
-                got = g;
-            } else {
-                got = (int64_t)fread(in.as<uint8_t>() + in_len, 1, (size_t)want, fp);
-                if (got == 0 && ferror(fp)) return fail("read error");
-            }
-            if (got == 0) file_eof = true;
-            in_len += got;
-        }
-        return true;
     }
     bool ensure_device() {
         if (dev_ready) return true;
         int n = 0;
         if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
             cudaGetLastError();
-            return fail("no CUDA device: the exon_b200 scan engine has no CPU fallback");
+            error = "no CUDA device: the exon_b200 scan engine has no CPU fallback";
+            return false;
         }
-        if (!cu(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+            return false;
+        }
         dev_ready = true;
         return true;
     }
 
+    // ------------------------------------------------------------------ IO thread
+    static void pread_slices(int fd, uint8_t* dst, int64_t pos, int64_t want, int64_t* got_out, bool* err_out) {
+        // page-cache / tmpfs reads are a kernel memcpy: ~6 GB/s from one thread, so a block is read as four slices
+        const int T = want >= (8ll << 20) ? 4 : 1;
+        int64_t got[4] = {0, 0, 0, 0};
+        bool bad[4] = {false, false, false, false};
+        auto work = [&](int k) {
+            const int64_t lo = want * k / T, hi = want * (k + 1) / T;
+            int64_t done = 0;
+            while (lo + done < hi) {
+                const ssize_t r = pread(fd, dst + lo + done, (size_t)(hi - lo - done), (off_t)(pos + lo + done));
+                if (r < 0) {
+                    if (errno == EINTR) continue;
+                    bad[k] = true;
+                    break;
+                }
+                if (r == 0) break;
+                done += r;
+            }
+            got[k] = done;
+        };
+        std::thread th[3];
+        for (int k = 1; k < T; k++) th[k - 1] = std::thread(work, k);
+        work(0);
+        for (int k = 1; k < T; k++) th[k - 1].join();
+        int64_t total = 0;
+        *err_out = false;
+        for (int k = 0; k < T; k++) {
+            *err_out = *err_out || bad[k];
+            total += got[k];
+            if (got[k] < want * (k + 1) / T - want * k / T) break;  // short slice = end of file
+        }
+        *got_out = total;
+    }
+    void io_main() {
+        for (size_t fi = 0; fi < files.size() && !stopping; fi++) {
+            const std::string& path = files[fi];
+            const int comp = file_comp[fi];
+            int fd = -1;
+            gzFile gz = nullptr;
+            std::string err;
+            if (comp == 1) {
+                gz = gzopen(path.c_str(), "rb");
+                if (!gz) err = "could not open " + path;
+                else gzbuffer(gz, 1 << 20);
+            } else if (comp == 0) {
+                fd = open(path.c_str(), O_RDONLY);
+                if (fd < 0) err = "could not open " + path;
+            } else {
+                err = "compression of " + path + " is not supported by this build (gzip and uncompressed are)";
+            }
+            int64_t pos = 0;
+            bool eof = false;
+            while (err.empty() && !eof && !stopping) {
+                const int64_t want = block_bytes.load();
+                Block b;
+                double t0 = now();
+                b.h = pool->get(headroom + want + 64);
+                t_io_alloc += now() - t0;
+                if (!b.h) {
+                    err = "out of pinned host memory";
+                    break;
+                }
+                t0 = now();
+                b.head = headroom;
+                b.file_idx = fi;
+                b.raw_file_pos = pos;
+                uint8_t* dst = b.h->as<uint8_t>() + headroom;
+                int64_t got = 0;
+                if (gz) {
+                    while (got < want) {
+                        const int g = gzread(gz, dst + got, (unsigned)std::min<int64_t>(want - got, 1 << 30));
+                        if (g < 0) {
+                            err = "gzip read error in " + path;
+                            break;
+                        }
+                        if (g == 0) break;
+                        got += g;
+                    }
+                } else {
+                    bool bad = false;
+                    pread_slices(fd, dst, pos, want, &got, &bad);
+                    if (bad) err = "read error in " + path;
+                }
+                if (!err.empty()) {
+                    pool->put(b.h);
+                    break;
+                }
+                t_io_read += now() - t0;
+                n_blocks++;
+                eof = got < want;
+                b.raw_len = got;
+                b.eof = eof;
+                pos += got;
+                HBuf* hb = b.h;
+                t0 = now();
+                const bool pushed = inq.push(std::move(b));
+                t_io_push += now() - t0;
+                if (!pushed) {  // reader closed
+                    pool->put(hb);
+                    break;
+                }
+            }
+            if (fd >= 0) close(fd);
+            if (gz) gzclose(gz);
+            if (!err.empty()) {
+                Block b;
+                b.error = err;
+                b.end = true;
+                inq.push(std::move(b));
+                return;
+            }
+        }
+        Block b;
+        b.end = true;
+        inq.push(std::move(b));
+    }
+
+    // ------------------------------------------------------------------ device thread
     // evaluate node `k` into d_out (uint8 per row) using per-column starts/lens (cols x n) in column buffers
     struct EvalCtx {
         const uint8_t* const* col_buf;  // per column: base buffer the starts index into
@@ -443,40 +667,59 @@ struct Reader {
         return false;
     }
 
-    // gather the selected rows of all columns and bring them to the host
-    bool materialise(const uint8_t* const* col_buf, const int64_t* d_st, const uint32_t* d_ln, const uint8_t* d_val, int64_t n) {
+    // Gather the selected rows of the wanted columns and bring them to the host: ONE launch for the Arrow offsets of all
+    // columns, one gather per wanted column into one device buffer, then offsets + validity + bytes cross PCIe in two
+    // copies into pinned buffers that the batches hand out as they are.  Two stream syncs per chunk.
+    bool materialise(const uint8_t* const* col_buf, const int64_t* d_st, const uint32_t* d_ln, const uint8_t* d_val, int64_t n, OutItem* item) {
         if (count_only) {
-            counted += n;
-            rows = next_row = 0;
+            item->counted = n;
             return true;
         }
-        cur = std::make_shared<ChunkResult>();
-        std::vector<ChunkColumn>& cols = cur->cols;
-        std::vector<uint8_t>& valid = cur->valid;
-        cols.assign(ncols, ChunkColumn());
-        valid.assign((size_t)n, 1);
-        rows = n;
-        next_row = 0;
-        if (n == 0) return true;
-        const int64_t ws_bytes = exb_scan_workspace_bytes(4 * n + 16);
-        if (!d_ws2.need(ws_bytes) || !d_off.need((n + 1) * 8) || !h_off.need((n + 1) * 8) || !h_valid.need(n)) return fail("out of memory");
+        if (n == 0) return true;  // nothing to hand out for this chunk
+        std::shared_ptr<ChunkResult> res = std::make_shared<ChunkResult>();
+        res->pool = pool;
+        res->rows = n;
+        const int64_t ws_bytes = exb_scan_workspace_bytes(4 * n * ncols + 16);
+        if (!d_ws2.need(ws_bytes) || !d_off.need((int64_t)ncols * (n + 1) * 8) || !h_small.need(256)) return fail("out of memory");
+        int64_t* d_offs = d_off.as<int64_t>();
+        if (!rc(exb_exclusive_scan_u32_multi(d_ln, n, ncols, n, d_offs, n + 1, d_ws2.p, d_ws2.cap, st))) return false;
+        int64_t* totals = h_small.as<int64_t>();
+        if (!cu(cudaMemcpy2DAsync(totals, 8, d_offs + n, (size_t)(n + 1) * 8, 8, (size_t)ncols, cudaMemcpyDeviceToHost, st), "D2H totals")) return false;
+        if (!cu(cudaStreamSynchronize(st), "sync")) return false;
+        int64_t base[4] = {0, 0, 0, 0}, all = 0;
+        int wanted = 0;
         for (int c = 0; c < ncols; c++) {
             if (!((column_mask >> c) & 1u)) continue;  // projected out: the column stays empty
-            if (!rc(exb_exclusive_scan_u32(d_ln + (int64_t)c * n, n, d_off.as<int64_t>(), d_ws2.p, d_ws2.cap, st))) return false;
-            if (!cu(cudaMemcpyAsync(h_off.p, d_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets")) return false;
-            if (!cu(cudaStreamSynchronize(st), "sync")) return false;
-            const int64_t total = h_off.as<int64_t>()[n];
-            if (!d_data.need(total + 16) || !h_data.need(total + 16)) return fail("out of memory");
-            if (!rc(exb_gather_ranges(col_buf[c], d_st + (int64_t)c * n, d_ln + (int64_t)c * n, d_off.as<int64_t>(), n, d_data.as<uint8_t>(), total, st)))
-                return false;
-            if (total > 0 && !cu(cudaMemcpyAsync(h_data.p, d_data.p, (size_t)total, cudaMemcpyDeviceToHost, st), "D2H data")) return false;
-            if (!cu(cudaStreamSynchronize(st), "sync")) return false;
-            cols[c].off.assign(h_off.as<int64_t>(), h_off.as<int64_t>() + n + 1);
-            cols[c].data.assign(h_data.as<uint8_t>(), h_data.as<uint8_t>() + total);
+            base[c] = all;
+            all += (totals[c] + 15) & ~(int64_t)15;
+            wanted++;
         }
-        if (!cu(cudaMemcpyAsync(h_valid.p, d_val, (size_t)n, cudaMemcpyDeviceToHost, st), "D2H validity")) return false;
+        // host layout: [wanted][(n + 1)] int64 offsets, then n validity bytes; the bytes in a buffer of their own
+        const int64_t meta_bytes = (int64_t)wanted * (n + 1) * 8 + n;
+        HBuf* h_meta = pool->get(meta_bytes + 64);
+        HBuf* h_bytes = pool->get(all + 64);
+        if (h_meta) res->bufs.push_back(h_meta);
+        if (h_bytes) res->bufs.push_back(h_bytes);
+        if (!h_meta || !h_bytes || !d_data.need(all + 64)) return fail("out of memory");
+        int k = 0;
+        for (int c = 0; c < ncols; c++) {
+            if (!((column_mask >> c) & 1u)) continue;
+            if (totals[c] > 0 &&
+                !rc(exb_gather_ranges(col_buf[c], d_st + (int64_t)c * n, d_ln + (int64_t)c * n, d_offs + (int64_t)c * (n + 1), n,
+                                      d_data.as<uint8_t>() + base[c], totals[c], st)))
+                return false;
+            int64_t* h_off = h_meta->as<int64_t>() + (int64_t)k * (n + 1);
+            if (!cu(cudaMemcpyAsync(h_off, d_offs + (int64_t)c * (n + 1), (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets")) return false;
+            res->cols[c].off = h_off;
+            res->cols[c].data = h_bytes->as<uint8_t>() + base[c];
+            k++;
+        }
+        uint8_t* h_val = h_meta->as<uint8_t>() + (int64_t)wanted * (n + 1) * 8;
+        if (!cu(cudaMemcpyAsync(h_val, d_val, (size_t)n, cudaMemcpyDeviceToHost, st), "D2H validity")) return false;
+        if (all > 0 && !cu(cudaMemcpyAsync(h_bytes->p, d_data.p, (size_t)all, cudaMemcpyDeviceToHost, st), "D2H data")) return false;
         if (!cu(cudaStreamSynchronize(st), "sync")) return false;
-        valid.assign(h_valid.as<uint8_t>(), h_valid.as<uint8_t>() + n);
+        res->valid = h_val;
+        item->res = res;
         return true;
     }
 
@@ -512,13 +755,12 @@ struct Reader {
         return true;
     }
 
-    // process the bytes in `in`; sets `consumed`.  Returns false on error.
-    bool process_chunk(bool is_final, int64_t& consumed, bool& grew) {
+    // process the n bytes at `in` (pinned); sets `consumed`.  Returns false on error (derr).
+    bool process_chunk(const uint8_t* in, int64_t n, bool is_final, int64_t& consumed, bool& grew, OutItem* item) {
         grew = false;
-        const int64_t n = in_len;
-        if (!ensure_device()) return false;
+        const std::string& fname = files[cur_file];
         if (!d_in.need(n + 64)) return fail("out of device memory");
-        if (n > 0 && !cu(cudaMemcpyAsync(d_in.p, in.p, (size_t)n, cudaMemcpyHostToDevice, st), "H2D")) return false;
+        if (n > 0 && !cu(cudaMemcpyAsync(d_in.p, in, (size_t)n, cudaMemcpyHostToDevice, st), "H2D")) return false;
         const int64_t ws_bytes = exb_scan_workspace_bytes(n + 16);
         if (!d_ws.need(ws_bytes)) return fail("out of device memory");
         exb_scan_result res;
@@ -541,10 +783,10 @@ struct Reader {
                 rec_cap = n / 4 + 16;
             }
             if (res.err_pos != ~0ull)
-                return fail("invalid FASTQ record at byte " + std::to_string(file_pos + (int64_t)res.err_pos) + " of " + files[file_idx - 1]);
+                return fail("invalid FASTQ record at byte " + std::to_string(cur_file_pos + (int64_t)res.err_pos) + " of " + fname);
             int64_t R = (int64_t)(res.total_lines / 4);
             if (is_final) {
-                if (res.total_lines % 4 != 0) return fail("unexpected EOF in FASTQ record of " + files[file_idx - 1]);
+                if (res.total_lines % 4 != 0) return fail("unexpected EOF in FASTQ record of " + fname);
                 consumed = n;
             } else {
                 if (R == 0) { grew = true; consumed = 0; return true; }
@@ -553,6 +795,10 @@ struct Reader {
                 if (!cu(cudaStreamSynchronize(st), "sync")) return false;
                 consumed = (int64_t)last + 1;
             }
+            if (count_only && root < 0) {  // COUNT(*) without a filter: the scan's record count is the answer
+                item->counted = R;
+                return true;
+            }
             if (!d_lens.need(std::max<int64_t>(R, 1) * 16) || !d_starts.need(std::max<int64_t>(R, 1) * 32) || !d_valid.need(std::max<int64_t>(R, 1)))
                 return fail("out of device memory");
             if (!rc(exb_fastq_fields(d_in.p, 0, n, d_line.p, 0, nullptr, R, d_lens.as<uint32_t>(), d_valid.as<uint8_t>(), d_starts.as<int64_t>(), st)))
@@ -560,7 +806,7 @@ struct Reader {
             const uint8_t* bufs[4] = {d_in.as<uint8_t>(), d_in.as<uint8_t>(), d_in.as<uint8_t>(), d_in.as<uint8_t>()};
             const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; int64_t o_n;
             if (!select(bufs, R, o_st, o_ln, o_val, o_n)) return false;
-            return materialise(bufs, o_st, o_ln, o_val, o_n);
+            return materialise(bufs, o_st, o_ln, o_val, o_n, item);
         }
         // ---- FASTA
         // the sequence column is compacted by the scan itself; skip that when nobody reads the bytes
@@ -583,7 +829,7 @@ struct Reader {
             rec_cap = n / 2 + 16;
         }
         if (res.err_pos != ~0ull)
-            return fail("invalid FASTA input (missing '>' prefix) at byte " + std::to_string(file_pos + (int64_t)res.err_pos) + " of " + files[file_idx - 1]);
+            return fail("invalid FASTA input (missing '>' prefix) at byte " + std::to_string(cur_file_pos + (int64_t)res.err_pos) + " of " + fname);
         int64_t R = (int64_t)res.n_records;
         if (is_final) consumed = n;
         else {
@@ -606,34 +852,111 @@ struct Reader {
         uint64_t bad = 0;
         if (!cu(cudaMemcpyAsync(&bad, d_err.p, 8, cudaMemcpyDeviceToHost, st), "D2H")) return false;
         if (!cu(cudaStreamSynchronize(st), "sync")) return false;
-        if (bad != ~0ull) return fail("FASTA definition without a name at byte " + std::to_string(file_pos + (int64_t)bad) + " of " + files[file_idx - 1]);
+        if (bad != ~0ull) return fail("FASTA definition without a name at byte " + std::to_string(cur_file_pos + (int64_t)bad) + " of " + fname);
         const uint8_t* bufs[3] = {d_in.as<uint8_t>(), d_in.as<uint8_t>(), d_seq.as<uint8_t>()};
         const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; int64_t o_n;
         if (!select(bufs, R, o_st, o_ln, o_val, o_n)) return false;
-        return materialise(bufs, o_st, o_ln, o_val, o_n);
+        return materialise(bufs, o_st, o_ln, o_val, o_n, item);
     }
 
-    // make rows available; false = end of stream or error (check `error`)
-    bool advance() {
-        if (!ensure_device()) return false;  // before any pinned allocation: "no CUDA device" is the message a CPU-only host must see
-        while (next_row >= rows) {
-            rows = next_row = 0;
-            if (file_eof && in_len == 0) {
-                if (!open_next_file()) return false;
+    void dev_main() {
+        HBuf* prev = nullptr;          // the block that holds the carry (the unconsumed tail of the previous chunk)
+        const uint8_t* carry = nullptr;
+        int64_t carry_len = 0;
+        auto finish = [&](const std::string& err) {
+            if (prev) pool->put(prev);
+            OutItem e;
+            e.end = true;
+            e.error = err;
+            outq.push(std::move(e));
+        };
+        while (!stopping) {
+            Block b;
+            double t0 = now();
+            const bool popped = inq.pop(b);
+            t_dev_pop += now() - t0;
+            if (!popped) break;
+            if (b.end) return finish(b.error);
+            t0 = now();
+            // the chunk = carry ++ raw bytes, contiguous
+            HBuf* hb = b.h;
+            uint8_t* in;
+            if (carry_len <= b.head) {
+                in = hb->as<uint8_t>() + b.head - carry_len;
+                if (carry_len) memcpy(in, carry, (size_t)carry_len);
+            } else {  // a tail longer than the headroom (one record spanning blocks): build the chunk in a bigger buffer
+                HBuf* big = pool->get(carry_len + b.raw_len + 64);
+                if (!big) {
+                    pool->put(hb);
+                    return finish("out of pinned host memory");
+                }
+                memcpy(big->p, carry, (size_t)carry_len);
+                memcpy(big->as<uint8_t>() + carry_len, hb->as<uint8_t>() + b.head, (size_t)b.raw_len);
+                pool->put(hb);
+                hb = big;
+                in = big->as<uint8_t>();
             }
-            if (!fill()) return false;
-            if (in_len == 0 && file_eof) continue;  // empty file
-            const bool is_final = file_eof;
+            if (prev) pool->put(prev);
+            prev = hb;
+            const int64_t n = carry_len + b.raw_len;
+            cur_file = b.file_idx;
+            cur_file_pos = b.raw_file_pos - carry_len;
+            carry = nullptr;
+            carry_len = 0;
+            if (n == 0) continue;  // empty file
             int64_t consumed = 0;
             bool grew = false;
-            if (!process_chunk(is_final, consumed, grew)) return false;
-            if (grew) {  // no complete record in the chunk: read more
-                chunk_bytes *= 2;
-                continue;
+            OutItem item;
+            if (!process_chunk(in, n, b.eof, consumed, grew, &item)) return finish(derr);
+            if (grew) {  // no complete record in the chunk: keep all of it and read bigger blocks from now on
+                consumed = 0;
+                block_bytes.store(std::min<int64_t>(block_bytes.load() * 2, 1ll << 30));
             }
-            if (consumed < in_len) memmove(in.p, in.as<uint8_t>() + consumed, (size_t)(in_len - consumed));
-            in_len -= consumed;
-            file_pos += consumed;
+            carry = in + consumed;
+            carry_len = n - consumed;
+            t_dev_work += now() - t0;
+            if (item.res || item.counted) {
+                t0 = now();
+                const bool pushed = outq.push(std::move(item));
+                t_dev_push += now() - t0;
+                if (!pushed) break;
+            }
+        }
+        if (prev) pool->put(prev);
+    }
+
+    // ------------------------------------------------------------------ caller
+    // make rows available; false = end of stream or error (check `error`)
+    bool advance() {
+        if (finished) return false;
+        if (!ensure_device()) return false;  // before any pinned allocation: "no CUDA device" is the message a CPU-only host must see
+        if (!started) {
+            started = true;
+            block_bytes.store(chunk_bytes);
+            io_thread = std::thread([this] { io_main(); });
+            dev_thread = std::thread([this] { dev_main(); });
+        }
+        while (next_row >= rows) {
+            rows = next_row = 0;
+            cur.reset();
+            OutItem it;
+            const double t0 = now();
+            const bool popped = outq.pop(it);
+            t_call_pop += now() - t0;
+            if (!popped) {
+                finished = true;
+                return false;
+            }
+            if (it.end) {
+                finished = true;
+                error = it.error;
+                return false;
+            }
+            counted += it.counted;
+            if (it.res) {
+                cur = it.res;
+                rows = cur->rows;
+            }
         }
         return true;
     }
@@ -705,7 +1028,8 @@ int stream_get_next(ArrowArrayStream* s, ArrowArray* out) {
     // rows [next_row, next_row + k): at most batch_size rows and < 2 GiB per column (utf8 has int32 offsets)
     int64_t b = r->next_row, e = std::min(r->rows, b + r->batch_size);
     for (int c = 0; c < r->ncols; c++) {
-        const std::vector<int64_t>& off = r->cur->cols[c].off;
+        const int64_t* off = r->cur->cols[c].off;
+        if (!off) continue;
         while (e > b + 1 && off[e] - off[b] > 0x7FFFFFF0ll) e = b + (e - b) / 2;
         if (off[e] - off[b] > 0x7FFFFFF0ll) {
             r->error = "a single " + r->col_names[c] + " value exceeds the 2 GiB limit of Arrow utf8";
@@ -723,10 +1047,12 @@ int stream_get_next(ArrowArrayStream* s, ArrowArray* out) {
     }
     for (int c = 0; c < r->ncols; c++) {
         const ChunkColumn& col = r->cur->cols[c];
-        h->off[c].resize((size_t)k + 1);
-        const int64_t base = col.off[b];
-        for (int64_t i = 0; i <= k; i++) h->off[c][i] = (int32_t)(col.off[b + i] - base);
-        h->data[c].assign(col.data.begin() + base, col.data.begin() + col.off[e]);
+        h->off[c].assign((size_t)k + 1, 0);
+        if (col.off) {
+            const int64_t base = col.off[b];
+            for (int64_t i = 0; i <= k; i++) h->off[c][i] = (int32_t)(col.off[b + i] - base);
+            h->data[c].assign(col.data + base, col.data + col.off[e]);
+        }
         const bool is_desc = r->col_names[c] == "description";
         ArrowArray& a = h->child[c];
         memset(&a, 0, sizeof(a));
@@ -875,6 +1201,8 @@ static Reader* open_reader(const char* uri, uintptr_t batch_size, const char* co
     }
     const char* cb = getenv("EXON_B200_CHUNK_BYTES");
     if (cb && atoll(cb) > 0) r->chunk_bytes = atoll(cb);
+    const char* hr = getenv("EXON_B200_HEADROOM");  // test knob: a tiny headroom forces the "tail longer than the headroom" path
+    if (hr && atoll(hr) >= 0) r->headroom = atoll(hr);
     return r.release();
 }
 
@@ -939,10 +1267,10 @@ int exb_reader_next(exb_reader* h, exb_batch* out) {
     out->n_cols = r->ncols;
     for (int c = 0; c < r->ncols; c++) {
         const ChunkColumn& col = r->cur->cols[c];
-        if (col.off.empty()) continue;  // projected out
-        out->cols[c].offsets = col.off.data() + b;
-        out->cols[c].data = col.data.data();
-        if (r->col_names[c] == "description") out->cols[c].valid = r->cur->valid.data() + b;
+        if (!col.off) continue;  // projected out
+        out->cols[c].offsets = col.off + b;
+        out->cols[c].data = col.data;
+        if (r->col_names[c] == "description") out->cols[c].valid = r->cur->valid + b;
     }
     out->owner = new std::shared_ptr<ChunkResult>(r->cur);
     r->next_row = e;

@@ -90,20 +90,22 @@ struct alignas(16) SumState {
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = BLOCK_THREADS * SCAN_ITEMS;
 
-// blockIdx.y = column: `cols` independent scans (their own chain and ticket) share one launch -- the four field-length
+// blockIdx.x = column: `cols` independent scans (their own chain and ticket) share one launch -- the four field-length
 // columns of a FASTQ table cost one launch latency instead of four.
 template <typename T>
 __global__ void __launch_bounds__(BLOCK_THREADS) exclusive_scan_kernel(const T* __restrict__ in, int64_t n, int64_t* __restrict__ out,
                                                                       TileSlot* slots, unsigned long long* ticket, int64_t n_tiles,
-                                                                      int64_t in_stride, int64_t out_stride) {
+                                                                      int64_t in_stride, int64_t out_stride, int cols) {
     __shared__ int64_t s_tile_id;
     __shared__ uint64_t s_warp[WARPS];
     __shared__ int64_t s_excl;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    in += (int64_t)blockIdx.y * in_stride;
-    out += (int64_t)blockIdx.y * out_stride;
-    slots = reinterpret_cast<TileSlot*>(reinterpret_cast<uint64_t*>(slots) + (int64_t)blockIdx.y * n_tiles);
-    ticket += blockIdx.y;
+    if (cols > 1) {  // grid (cols, n_tiles); a single column is a plain 1-D grid of n_tiles blocks
+        in += (int64_t)blockIdx.x * in_stride;
+        out += (int64_t)blockIdx.x * out_stride;
+        slots = reinterpret_cast<TileSlot*>(reinterpret_cast<uint64_t*>(slots) + (int64_t)blockIdx.x * n_tiles);
+        ticket += blockIdx.x;
+    }
     if (t == 0) s_tile_id = (int64_t)atomicAdd(ticket, 1ull);
     __syncthreads();
     const int64_t tile = s_tile_id;
@@ -141,22 +143,31 @@ cudaError_t exclusive_scan_launch_u32(const uint32_t* in, int64_t n, int64_t* ou
                                       cudaStream_t st) {
     int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (n_tiles == 0) n_tiles = 1;
-    exclusive_scan_kernel<uint32_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles, 0, 0);
+    exclusive_scan_kernel<uint32_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles, 0, 0, 1);
     return cudaGetLastError();
 }
 cudaError_t exclusive_scan_launch_u32_multi(const uint32_t* in, int64_t n, int cols, int64_t in_stride, int64_t* out, int64_t out_stride,
                                             TileSlot* slots, unsigned long long* ticket, cudaStream_t st) {
     int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (n_tiles == 0) n_tiles = 1;
-    exclusive_scan_kernel<uint32_t><<<dim3((unsigned)n_tiles, (unsigned)cols), BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles,
-                                                                                                    in_stride, out_stride);
+    // column = blockIdx.x (fastest): blocks are dispatched x first, so the tiles of the `cols` chains interleave and the
+    // chains advance side by side (with the column in y they ran one after the other: 188 us for 4 x 4 M rows, not 55)
+    if (n_tiles > 65535 || cols == 1) {  // gridDim.y limit: fall back to one launch per column
+        for (int c = 0; c < cols; c++)
+            exclusive_scan_kernel<uint32_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(
+                in + c * in_stride, n, out + c * out_stride, reinterpret_cast<TileSlot*>(reinterpret_cast<uint64_t*>(slots) + c * n_tiles),
+                ticket + c, n_tiles, 0, 0, 1);
+        return cudaGetLastError();
+    }
+    exclusive_scan_kernel<uint32_t><<<dim3((unsigned)cols, (unsigned)n_tiles), BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles,
+                                                                                                    in_stride, out_stride, cols);
     return cudaGetLastError();
 }
 cudaError_t exclusive_scan_launch_u8(const uint8_t* in, int64_t n, int64_t* out, TileSlot* slots, unsigned long long* ticket,
                                      cudaStream_t st) {
     int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (n_tiles == 0) n_tiles = 1;
-    exclusive_scan_kernel<uint8_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles, 0, 0);
+    exclusive_scan_kernel<uint8_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles, 0, 0, 1);
     return cudaGetLastError();
 }
 int64_t scan_tiles(int64_t n) {
@@ -317,11 +328,25 @@ __device__ __forceinline__ uint4 load16_unaligned(const uint8_t* __restrict__ sr
                       __funnelshift_r(r[3], r[4], bs));
 }
 
+// 128-bit byte mask: bytes [s, e) of a 16-byte chunk (0 <= s < e <= 16)
+__device__ __forceinline__ uint64_t bytes_below64(int k) { return k >= 8 ? ~0ull : (k <= 0 ? 0ull : ((1ull << (8 * k)) - 1ull)); }
+__device__ __forceinline__ uint4 byte_range_mask(int s, int e) {
+    const uint64_t lo = bytes_below64(e) & ~bytes_below64(s), hi = bytes_below64(e - 8) & ~bytes_below64(s - 8);
+    return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+
+// Positions inside a span are kept RELATIVE to span_lo (the 16-byte aligned output address the span starts at), so the
+// inner loop runs on 32-bit integers: s_rel[i] = off[row0 + i] - span_lo clamped to +-2^30 (rows that begin before the
+// span compare as "before", which is all the search needs), s_adj[i] = offset in buf of the byte that lands on relative
+// position 0 if row i is extended backwards (64-bit, one add per piece).
+// A 16-byte chunk is assembled from the pieces of the rows that meet in it -- one unaligned 16-byte load + a byte mask
+// per piece -- and stored ONCE.  (The first version copied straddling chunks byte by byte: one chunk in ten for
+// 150-byte rows, but under warp divergence 2/3 of all issued instructions.)
 template <typename SrcFn>
 __global__ void __launch_bounds__(GS_THREADS) gather_span_kernel(const uint8_t* __restrict__ buf, SrcFn srcfn, const int64_t* __restrict__ off,
                                                                  int64_t n_rows, uint8_t* __restrict__ out) {
-    __shared__ int64_t s_off[GS_ROWS + 1];
-    __shared__ int64_t s_src[GS_ROWS];
+    __shared__ int32_t s_rel[GS_ROWS + 1];
+    __shared__ int64_t s_adj[GS_ROWS];
     const int t = threadIdx.x;
     const int64_t total = off[n_rows];
     // spans are aligned to 16 bytes of the OUTPUT ADDRESS so that chunk stores are aligned whatever `out` is
@@ -331,11 +356,11 @@ __global__ void __launch_bounds__(GS_THREADS) gather_span_kernel(const uint8_t* 
     for (int64_t span = blockIdx.x;; span += gridDim.x) {
         const int64_t span_lo = span * GS_SPAN - mis;  // negative for span 0 when out is misaligned
         if (span_lo >= total) break;
-        int64_t lo = span_lo < 0 ? 0 : span_lo;
+        const int64_t lo = span_lo < 0 ? 0 : span_lo;
         const int64_t hi = span_lo + GS_SPAN < total ? span_lo + GS_SPAN : total;
         if (lo >= hi) continue;
         // last row r with off[r] <= lo: a GS_THREADS-ary search by the whole block (3 rounds of one global load each
-        // for 16 M rows; a one-thread binary search costs ~22 dependent loads and was 2/3 of the kernel's time)
+        // for 16 M rows)
         int64_t row0;
         {
             int64_t a = 0, b = n_rows;  // invariant: off[a] <= lo < off[b] (off[n_rows] = total > lo)
@@ -349,47 +374,76 @@ __global__ void __launch_bounds__(GS_THREADS) gather_span_kernel(const uint8_t* 
             }
             row0 = a;
         }
-        while (lo < hi) {
+        int lo_rel = (int)(lo - span_lo);
+        const int hi_rel = (int)(hi - span_lo);
+        uint8_t* const span_out = out + span_lo;  // 16-byte aligned
+        while (lo_rel < hi_rel) {
             const int64_t left = n_rows - row0;
             const int cap = left < GS_ROWS ? (int)left : GS_ROWS;
             __syncthreads();
-            for (int i = t; i <= cap; i += GS_THREADS) s_off[i] = off[row0 + i];
+            for (int i = t; i <= cap; i += GS_THREADS) {
+                int64_t r = off[row0 + i] - span_lo;
+                r = r < -(1 << 30) ? -(1 << 30) : (r > (1 << 30) ? (1 << 30) : r);
+                s_rel[i] = (int32_t)r;
+            }
             __syncthreads();
-            // rows that begin before `hi` are the ones this span needs (s_off[0] <= lo < hi, so at least one); only
-            // those pay for their source address (SrcFastq: two dependent scattered loads per row)
+            // rows that begin before `hi` are the ones this span needs (s_rel[0] <= lo_rel < hi_rel, so at least one);
+            // only those pay for their source address (SrcFastq: two dependent scattered loads per row)
             int cnt = 0;
 #pragma unroll
             for (int k = 0; k < GS_ROWS / GS_THREADS; k++) {
                 const int i = t + k * GS_THREADS;
-                cnt += __syncthreads_count(i < cap && s_off[i] < hi);
+                cnt += __syncthreads_count(i < cap && s_rel[i] < hi_rel);
             }
-            for (int i = t; i < cnt; i += GS_THREADS) s_src[i] = srcfn(row0 + i);
+            for (int i = t; i < cnt; i += GS_THREADS) s_adj[i] = srcfn(row0 + i) - (off[row0 + i] - span_lo);
             __syncthreads();
-            // rows row0 .. row0 + cnt cover [lo, batch_hi)
-            const int64_t batch_hi = s_off[cnt] < hi ? s_off[cnt] : hi;
-            // chunks: dst address of byte p is out + p; chunk boundaries at (p + mis) % 16 == 0
-            const int64_t c0 = (lo + mis) >> 4, c1 = (batch_hi + mis + 15) >> 4;
-            for (int64_t c = c0 + t; c < c1; c += GS_THREADS) {
-                int64_t p0 = (c << 4) - mis, p1 = p0 + 16;
-                if (p0 < lo) p0 = lo;
-                if (p1 > batch_hi) p1 = batch_hi;
-                // local row of p0: last i with s_off[i] <= p0
+            // rows row0 .. row0 + cnt cover [lo_rel, batch_hi)
+            const int batch_hi = s_rel[cnt] < hi_rel ? s_rel[cnt] : hi_rel;
+            for (int k = (lo_rel >> 4) + t; (k << 4) < batch_hi; k += GS_THREADS) {
+                const int c0 = k << 4;
+                const int q0 = c0 < lo_rel ? lo_rel : c0, q1 = c0 + 16 > batch_hi ? batch_hi : c0 + 16;
+                // local row of q0: last i with s_rel[i] <= q0
                 int a = 0, b = cnt;
                 while (b - a > 1) {
                     const int m = (a + b) >> 1;
-                    if (s_off[m] <= p0) a = m;
+                    if (s_rel[m] <= q0) a = m;
                     else b = m;
                 }
-                if (p1 - p0 == 16 && p1 <= s_off[a + 1]) {
-                    *reinterpret_cast<uint4*>(out + p0) = load16_unaligned(buf + s_src[a] + (p0 - s_off[a]));
-                } else {
-                    for (int64_t p = p0; p < p1; p++) {
-                        while (s_off[a + 1] <= p) a++;  // skips empty rows; p < batch_hi <= s_off[cnt] bounds it
-                        out[p] = buf[s_src[a] + (p - s_off[a])];
+                bool whole = q1 - q0 == 16;
+                uint4 acc = make_uint4(0, 0, 0, 0);
+                if (whole) {
+                    int q = q0;
+                    while (q < q1) {
+                        while (s_rel[a + 1] <= q) a++;  // skips empty rows; q < batch_hi <= s_rel[cnt] bounds it
+                        const int e = s_rel[a + 1] < q1 ? s_rel[a + 1] : q1;
+                        const int64_t src = s_adj[a] + c0;  // source of the chunk's byte 0 if row a reached that far back
+                        if (src < 0) {  // would read in front of the buffer (first bytes of the input): take the byte path
+                            whole = false;
+                            break;
+                        }
+                        const uint4 v = load16_unaligned(buf + src);
+                        if (e - q == 16) {
+                            acc = v;
+                        } else {
+                            const uint4 m = byte_range_mask(q - c0, e - c0);
+                            acc.x |= v.x & m.x;
+                            acc.y |= v.y & m.y;
+                            acc.z |= v.z & m.z;
+                            acc.w |= v.w & m.w;
+                        }
+                        q = e;
+                    }
+                }
+                if (whole) {
+                    *reinterpret_cast<uint4*>(span_out + c0) = acc;
+                } else {  // ragged first / last chunk of the column or of a row batch
+                    for (int q = q0; q < q1; q++) {
+                        while (s_rel[a + 1] <= q) a++;
+                        span_out[q] = buf[s_adj[a] + q];
                     }
                 }
             }
-            lo = batch_hi;
+            lo_rel = batch_hi;
             row0 += cnt;  // the batch ended on its last row (lo = off[row0 + cnt]), or lo == hi and the loop ends
         }
     }

@@ -42,6 +42,40 @@ def byte_range(n_bytes, rank, world):
     return n_bytes * rank // world, n_bytes * (rank + 1) // world
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers (first touch) and
+    the threads that fill them are local to the GPU's PCIe root: with 8 ranks streaming 55 GB/s each, buffers on the
+    wrong socket halve the end-to-end rate.  Returns the node, or None when the topology cannot be read."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------ groups
 class TorchGroup:
     """torch.distributed process group (NCCL: tensors on the rank's GPU; gloo: CPU tensors)."""

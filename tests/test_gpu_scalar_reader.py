@@ -146,6 +146,53 @@ def test_reader_chunk_carry_fasta(cuda_device, tmp_path, monkeypatch, chunk):
     assert 0 < len(keep) < want.n and _rows(got) == keep
 
 
+@pytest.mark.parametrize("fmt", ["fastq", "fasta"])
+def test_reader_tail_longer_than_headroom(cuda_device, tmp_path, monkeypatch, fmt):
+    """The unconsumed tail of a chunk normally fits the headroom in front of the next block; a record that spans whole
+    blocks does not, and the chunk is then rebuilt in a bigger buffer (and blocks double).  Both paths, same rows."""
+    from oracle import oracle as O
+    monkeypatch.setenv("EXON_B200_CHUNK_BYTES", "2048")
+    monkeypatch.setenv("EXON_B200_HEADROOM", "64")
+    p = tmp_path / ("a." + fmt)
+    if fmt == "fastq":
+        text, _ = util.random_fastq(11, 300, max_len=5000, min_len=10, tricky=False)
+        want = O.parse_fastq(text)
+    else:
+        text, _ = util.random_fasta(12, 120, max_len=20000, tricky=False)
+        want = O.parse_fasta(text)
+    p.write_bytes(text)
+    assert _rows(_read(str(p), fmt)) == want.rows()
+
+
+def test_reader_batches_outlive_the_reader(cuda_device, tmp_path):
+    """exb_batch views point into pinned result buffers owned by a pool that is shared with the batches: they stay
+    valid after exb_reader_close (include/exon_b200.h, native reader contract)."""
+    import ctypes as C
+    from exon_duckdb_b200 import _lib
+    from oracle import oracle as O
+    text, _ = util.random_fastq(13, 5000, tricky=False)
+    p = tmp_path / "a.fastq"
+    p.write_bytes(text)
+    L = _lib.lib()
+    h = C.c_void_p()
+    _lib.check(L.exb_reader_open(str(p).encode(), b"fastq", None, 2048, None, 0xF, C.byref(h)))
+    batches = []
+    while True:
+        b = _lib.Batch()
+        _lib.check(L.exb_reader_next(h, C.byref(b)))
+        if b.n_rows == 0:
+            break
+        batches.append(b)
+    L.exb_reader_close(h)
+    seqs = []
+    for b in batches:
+        off, data = b.cols[2].offsets, b.cols[2].data
+        for i in range(b.n_rows):
+            seqs.append(bytes(data[off[i]:off[i + 1]]))
+        L.exb_batch_release(C.byref(b))
+    assert seqs == O.parse_fastq(text).strings("sequence")
+
+
 def test_reader_reports_malformed_input(cuda_device, tmp_path):
     p = tmp_path / "bad.fastq"
     p.write_bytes(b"@a\nACGT\n+\nIIII\nACGT\n")
