@@ -351,12 +351,11 @@ struct ChunkResult {
     }
 };
 
-// One raw block of a file as the IO thread read it: `head` bytes of headroom, then raw_len bytes.  The part of the
-// previous chunk that did not end on a record boundary is copied into the headroom, so a chunk is contiguous
-// without moving the block.
+// One raw block of a file as the IO thread read it.  The part of the previous chunk that did not end on a record
+// boundary never comes back to the host: it stays in HBM and the device thread puts the next block behind it.
 struct Block {
     HBuf* h = nullptr;
-    int64_t head = 0, raw_len = 0;
+    int64_t raw_len = 0;
     int64_t raw_file_pos = 0;  // offset of the first raw byte in the (decompressed) file
     size_t file_idx = 0;
     bool eof = false;          // the file ends with this block
@@ -394,6 +393,14 @@ struct BoundedQueue {
         cv.notify_all();
         return true;
     }
+    bool try_pop(T& out) {  // non-blocking: false = nothing queued right now
+        std::lock_guard<std::mutex> lk(mu);
+        if (q.empty()) return false;
+        out = std::move(q.front());
+        q.pop_front();
+        cv.notify_all();
+        return true;
+    }
     void shutdown() {
         std::lock_guard<std::mutex> lk(mu);
         stop = true;
@@ -415,14 +422,16 @@ struct Reader {
     std::vector<std::string> files;
     std::vector<int> file_comp;
     int64_t chunk_bytes = 64ll << 20;
-    int64_t headroom = 1ll << 20;
     // filter
     std::vector<Node> nodes;
     int root = -1;
     // device state (device thread only, after ensure_device)
     bool dev_ready = false;
-    cudaStream_t st = nullptr;
-    DBuf d_in, d_ws, d_ws2, d_line, d_arr[4], d_lens, d_starts, d_valid, d_pass, d_selscratch, d_sel, d_lens2, d_starts2,
+    cudaStream_t st = nullptr, sc = nullptr;  // compute (+ D2H) stream, H2D prefetch stream
+    cudaEvent_t ev_staged = nullptr, ev_stage_free = nullptr;
+    DBuf d_inb[2], d_stage;  // the chunk being scanned / the one being assembled; the prefetched raw block
+    uint8_t* d_cur = nullptr;  // = d_inb[cur].p while a chunk is processed
+    DBuf d_ws, d_ws2, d_line, d_arr[4], d_lens, d_starts, d_valid, d_pass, d_selscratch, d_sel, d_lens2, d_starts2,
         d_valid2, d_off, d_data, d_cst, d_hdr_start, d_hdr_end, d_seq_off, d_gc_prefix, d_seq, d_err;
     std::shared_ptr<PinnedPool> pool = PinnedPool::shared();
     HBuf h_small;  // a few words for totals / flags read back between launches
@@ -459,6 +468,9 @@ struct Reader {
         cur.reset();
         outq.q.clear();
         if (st) cudaStreamDestroy(st);
+        if (sc) cudaStreamDestroy(sc);
+        if (ev_staged) cudaEventDestroy(ev_staged);
+        if (ev_stage_free) cudaEventDestroy(ev_stage_free);
         if (getenv("EXON_B200_TRACE"))
             fprintf(stderr, "exon_b200 reader: %lld blocks | io: alloc %.3f read %.3f push-wait %.3f | device: pop-wait %.3f work %.3f push-wait %.3f | "
                             "caller: pop-wait %.3f s\n", (long long)n_blocks, t_io_alloc, t_io_read, t_io_push, t_dev_pop, t_dev_work, t_dev_push, t_call_pop);
@@ -486,6 +498,9 @@ struct Reader {
             return false;
         }
         cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_staged, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_stage_free, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
             return false;
@@ -496,10 +511,11 @@ struct Reader {
 
     // ------------------------------------------------------------------ IO thread
     static void pread_slices(int fd, uint8_t* dst, int64_t pos, int64_t want, int64_t* got_out, bool* err_out) {
-        // page-cache / tmpfs reads are a kernel memcpy: ~6 GB/s from one thread, so a block is read as four slices
-        const int T = want >= (8ll << 20) ? 4 : 1;
-        int64_t got[4] = {0, 0, 0, 0};
-        bool bad[4] = {false, false, false, false};
+        // page-cache / tmpfs reads are a kernel memcpy: ~5 GB/s from one thread, so a block is read as eight slices
+        constexpr int TMAX = 8;
+        const int T = want >= (8ll << 20) ? TMAX : 1;
+        int64_t got[TMAX] = {0};
+        bool bad[TMAX] = {false};
         auto work = [&](int k) {
             const int64_t lo = want * k / T, hi = want * (k + 1) / T;
             int64_t done = 0;
@@ -515,7 +531,7 @@ struct Reader {
             }
             got[k] = done;
         };
-        std::thread th[3];
+        std::thread th[TMAX - 1];
         for (int k = 1; k < T; k++) th[k - 1] = std::thread(work, k);
         work(0);
         for (int k = 1; k < T; k++) th[k - 1].join();
@@ -551,17 +567,16 @@ struct Reader {
                 const int64_t want = block_bytes.load();
                 Block b;
                 double t0 = now();
-                b.h = pool->get(headroom + want + 64);
+                b.h = pool->get(want + 64);
                 t_io_alloc += now() - t0;
                 if (!b.h) {
                     err = "out of pinned host memory";
                     break;
                 }
                 t0 = now();
-                b.head = headroom;
                 b.file_idx = fi;
                 b.raw_file_pos = pos;
-                uint8_t* dst = b.h->as<uint8_t>() + headroom;
+                uint8_t* dst = b.h->as<uint8_t>();
                 int64_t got = 0;
                 if (gz) {
                     while (got < want) {
@@ -755,12 +770,10 @@ struct Reader {
         return true;
     }
 
-    // process the n bytes at `in` (pinned); sets `consumed`.  Returns false on error (derr).
-    bool process_chunk(const uint8_t* in, int64_t n, bool is_final, int64_t& consumed, bool& grew, OutItem* item) {
+    // process the n bytes at d_cur (already enqueued on `st`); sets `consumed`.  Returns false on error (derr).
+    bool process_chunk(int64_t n, bool is_final, int64_t& consumed, bool& grew, OutItem* item) {
         grew = false;
         const std::string& fname = files[cur_file];
-        if (!d_in.need(n + 64)) return fail("out of device memory");
-        if (n > 0 && !cu(cudaMemcpyAsync(d_in.p, in, (size_t)n, cudaMemcpyHostToDevice, st), "H2D")) return false;
         const int64_t ws_bytes = exb_scan_workspace_bytes(n + 16);
         if (!d_ws.need(ws_bytes)) return fail("out of device memory");
         exb_scan_result res;
@@ -773,7 +786,7 @@ struct Reader {
                 if (numeric)
                     for (int k = 0; k < 4; k++)
                         if (!d_arr[k].need(rec_cap * 4)) return fail("out of device memory");
-                if (!rc(exb_fastq_scan(d_in.p, 0, n, is_final ? 1 : 0, nullptr, ~0ull, EXB_F_LINES | (numeric ? (EXB_F_SEQ | EXB_F_QUAL) : 0),
+                if (!rc(exb_fastq_scan(d_cur, 0, n, is_final ? 1 : 0, nullptr, ~0ull, EXB_F_LINES | (numeric ? (EXB_F_SEQ | EXB_F_QUAL) : 0),
                                        d_line.p, rec_cap * 4, 0, d_arr[0].as<uint32_t>(), d_arr[1].as<uint32_t>(), d_arr[2].as<uint32_t>(),
                                        d_arr[3].as<int32_t>(), rec_cap, d_ws.p, d_ws.cap, st)))
                     return false;
@@ -801,9 +814,9 @@ struct Reader {
             }
             if (!d_lens.need(std::max<int64_t>(R, 1) * 16) || !d_starts.need(std::max<int64_t>(R, 1) * 32) || !d_valid.need(std::max<int64_t>(R, 1)))
                 return fail("out of device memory");
-            if (!rc(exb_fastq_fields(d_in.p, 0, n, d_line.p, 0, nullptr, R, d_lens.as<uint32_t>(), d_valid.as<uint8_t>(), d_starts.as<int64_t>(), st)))
+            if (!rc(exb_fastq_fields(d_cur, 0, n, d_line.p, 0, nullptr, R, d_lens.as<uint32_t>(), d_valid.as<uint8_t>(), d_starts.as<int64_t>(), st)))
                 return false;
-            const uint8_t* bufs[4] = {d_in.as<uint8_t>(), d_in.as<uint8_t>(), d_in.as<uint8_t>(), d_in.as<uint8_t>()};
+            const uint8_t* bufs[4] = {d_cur, d_cur, d_cur, d_cur};
             const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; int64_t o_n;
             if (!select(bufs, R, o_st, o_ln, o_val, o_n)) return false;
             return materialise(bufs, o_st, o_ln, o_val, o_n, item);
@@ -819,7 +832,7 @@ struct Reader {
             if (!d_hdr_start.need(rec_cap * 8) || !d_hdr_end.need(rec_cap * 8) || !d_seq_off.need((rec_cap + 1) * 8) ||
                 !d_gc_prefix.need((rec_cap + 1) * 8) || (want_seq && !d_seq.need(n + 64)))
                 return fail("out of device memory");
-            if (!rc(exb_fasta_scan(d_in.p, 0, n, is_final ? 1 : 0, n, nullptr, d_hdr_start.as<int64_t>(), d_hdr_end.as<int64_t>(),
+            if (!rc(exb_fasta_scan(d_cur, 0, n, is_final ? 1 : 0, n, nullptr, d_hdr_start.as<int64_t>(), d_hdr_end.as<int64_t>(),
                                    d_seq_off.as<int64_t>(), d_gc_prefix.as<int64_t>(), rec_cap, want_seq ? d_seq.as<uint8_t>() : nullptr,
                                    want_seq ? n + 64 : 0, d_ws.p, d_ws.cap, st)))
                 return false;
@@ -843,7 +856,7 @@ struct Reader {
         if (!d_lens.need(std::max<int64_t>(R, 1) * 12) || !d_starts.need(std::max<int64_t>(R, 1) * 24) || !d_valid.need(std::max<int64_t>(R, 1)) ||
             !d_err.need(8))
             return fail("out of device memory");
-        if (!rc(exb_fasta_headers(d_in.p, n, d_hdr_start.as<int64_t>(), d_hdr_end.as<int64_t>(), R, d_lens.as<uint32_t>(), d_starts.as<int64_t>(),
+        if (!rc(exb_fasta_headers(d_cur, n, d_hdr_start.as<int64_t>(), d_hdr_end.as<int64_t>(), R, d_lens.as<uint32_t>(), d_starts.as<int64_t>(),
                                   d_valid.as<uint8_t>(), d_err.as<uint64_t>(), st)))
             return false;
         if (!cu(fasta_seq_ranges_launch(d_seq_off.as<int64_t>(), nullptr, R, d_starts.as<int64_t>() + 2 * R, d_lens.as<uint32_t>() + 2 * R, st),
@@ -853,18 +866,27 @@ struct Reader {
         if (!cu(cudaMemcpyAsync(&bad, d_err.p, 8, cudaMemcpyDeviceToHost, st), "D2H")) return false;
         if (!cu(cudaStreamSynchronize(st), "sync")) return false;
         if (bad != ~0ull) return fail("FASTA definition without a name at byte " + std::to_string(cur_file_pos + (int64_t)bad) + " of " + fname);
-        const uint8_t* bufs[3] = {d_in.as<uint8_t>(), d_in.as<uint8_t>(), d_seq.as<uint8_t>()};
+        const uint8_t* bufs[3] = {d_cur, d_cur, d_seq.as<uint8_t>()};
         const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; int64_t o_n;
         if (!select(bufs, R, o_st, o_ln, o_val, o_n)) return false;
         return materialise(bufs, o_st, o_ln, o_val, o_n, item);
     }
 
+    // A chunk = the unconsumed tail of the previous chunk (it never left HBM: a device-to-device move to the front of
+    // the other input buffer) followed by the next raw block.  While chunk k is scanned, split and copied back, block
+    // k+1 -- if the IO thread already has it -- crosses PCIe on the copy stream into a staging buffer, so H2D of k+1
+    // overlaps the kernels and the D2H of k (two copy engines, opposite directions).
     void dev_main() {
-        HBuf* prev = nullptr;          // the block that holds the carry (the unconsumed tail of the previous chunk)
-        const uint8_t* carry = nullptr;
-        int64_t carry_len = 0;
+        HBuf* host_cur = nullptr;     // pinned block whose bytes may still be in flight to the device
+        Block staged;                 // the prefetched block (its pinned buffer included); valid when have_staged
+        bool have_staged = false, staged_on_device = false;
+        int cur = 0;
+        int64_t carry_off = 0, carry_len = 0;  // the tail lives in d_inb[cur] at [carry_off, carry_off + carry_len)
         auto finish = [&](const std::string& err) {
-            if (prev) pool->put(prev);
+            cudaStreamSynchronize(sc);
+            cudaStreamSynchronize(st);
+            pool->put(host_cur);
+            if (have_staged) pool->put(staged.h);
             OutItem e;
             e.end = true;
             e.error = err;
@@ -872,47 +894,74 @@ struct Reader {
         };
         while (!stopping) {
             Block b;
-            double t0 = now();
-            const bool popped = inq.pop(b);
-            t_dev_pop += now() - t0;
-            if (!popped) break;
-            if (b.end) return finish(b.error);
-            t0 = now();
-            // the chunk = carry ++ raw bytes, contiguous
-            HBuf* hb = b.h;
-            uint8_t* in;
-            if (carry_len <= b.head) {
-                in = hb->as<uint8_t>() + b.head - carry_len;
-                if (carry_len) memcpy(in, carry, (size_t)carry_len);
-            } else {  // a tail longer than the headroom (one record spanning blocks): build the chunk in a bigger buffer
-                HBuf* big = pool->get(carry_len + b.raw_len + 64);
-                if (!big) {
-                    pool->put(hb);
-                    return finish("out of pinned host memory");
-                }
-                memcpy(big->p, carry, (size_t)carry_len);
-                memcpy(big->as<uint8_t>() + carry_len, hb->as<uint8_t>() + b.head, (size_t)b.raw_len);
-                pool->put(hb);
-                hb = big;
-                in = big->as<uint8_t>();
+            bool on_device = false;
+            if (have_staged) {
+                b = std::move(staged);
+                on_device = staged_on_device;
+                have_staged = false;
+            } else {
+                double t0 = now();
+                const bool popped = inq.pop(b);
+                t_dev_pop += now() - t0;
+                if (!popped) break;
             }
-            if (prev) pool->put(prev);
-            prev = hb;
+            if (b.end) return finish(b.error);
+            double t0 = now();
+            // ---- assemble chunk k in the other input buffer
+            const int nxt = cur ^ 1;
             const int64_t n = carry_len + b.raw_len;
+            if (!d_inb[nxt].need(n + 64)) {
+                pool->put(b.h);
+                return finish("out of device memory");
+            }
+            uint8_t* dst = d_inb[nxt].as<uint8_t>();
+            bool ok = true;
+            if (carry_len) ok = cu(cudaMemcpyAsync(dst, d_inb[cur].as<uint8_t>() + carry_off, (size_t)carry_len, cudaMemcpyDeviceToDevice, st), "D2D tail");
+            if (ok && b.raw_len) {
+                if (on_device) {
+                    ok = cu(cudaStreamWaitEvent(st, ev_staged, 0), "wait") &&
+                         cu(cudaMemcpyAsync(dst + carry_len, d_stage.p, (size_t)b.raw_len, cudaMemcpyDeviceToDevice, st), "D2D block") &&
+                         cu(cudaEventRecord(ev_stage_free, st), "record");
+                } else {
+                    ok = cu(cudaMemcpyAsync(dst + carry_len, b.h->p, (size_t)b.raw_len, cudaMemcpyHostToDevice, st), "H2D");
+                }
+            }
+            pool->put(host_cur);  // the previous chunk synchronised `st` after its copies: that block is idle
+            host_cur = b.h;
+            if (!ok) return finish(derr);
+            cur = nxt;
+            d_cur = dst;
             cur_file = b.file_idx;
             cur_file_pos = b.raw_file_pos - carry_len;
-            carry = nullptr;
-            carry_len = 0;
+            carry_off = carry_len = 0;
+            // ---- prefetch block k+1 while chunk k is processed
+            if (!b.eof || b.file_idx + 1 < files.size()) {
+                Block nb;
+                if (inq.try_pop(nb)) {
+                    staged_on_device = false;
+                    if (!nb.end && nb.raw_len > 0 && d_stage.need(nb.raw_len + 64)) {
+                        // the staging buffer is free once the previous staged block has been moved out of it
+                        if (cu(cudaStreamWaitEvent(sc, ev_stage_free, 0), "wait") &&
+                            cu(cudaMemcpyAsync(d_stage.p, nb.h->p, (size_t)nb.raw_len, cudaMemcpyHostToDevice, sc), "H2D prefetch") &&
+                            cu(cudaEventRecord(ev_staged, sc), "record"))
+                            staged_on_device = true;
+                        else
+                            return finish(derr);
+                    }
+                    staged = std::move(nb);
+                    have_staged = true;
+                }
+            }
             if (n == 0) continue;  // empty file
             int64_t consumed = 0;
             bool grew = false;
             OutItem item;
-            if (!process_chunk(in, n, b.eof, consumed, grew, &item)) return finish(derr);
+            if (!process_chunk(n, b.eof, consumed, grew, &item)) return finish(derr);
             if (grew) {  // no complete record in the chunk: keep all of it and read bigger blocks from now on
                 consumed = 0;
                 block_bytes.store(std::min<int64_t>(block_bytes.load() * 2, 1ll << 30));
             }
-            carry = in + consumed;
+            carry_off = consumed;
             carry_len = n - consumed;
             t_dev_work += now() - t0;
             if (item.res || item.counted) {
@@ -922,7 +971,10 @@ struct Reader {
                 if (!pushed) break;
             }
         }
-        if (prev) pool->put(prev);
+        cudaStreamSynchronize(sc);
+        cudaStreamSynchronize(st);
+        pool->put(host_cur);
+        if (have_staged) pool->put(staged.h);
     }
 
     // ------------------------------------------------------------------ caller
@@ -1201,8 +1253,6 @@ static Reader* open_reader(const char* uri, uintptr_t batch_size, const char* co
     }
     const char* cb = getenv("EXON_B200_CHUNK_BYTES");
     if (cb && atoll(cb) > 0) r->chunk_bytes = atoll(cb);
-    const char* hr = getenv("EXON_B200_HEADROOM");  // test knob: a tiny headroom forces the "tail longer than the headroom" path
-    if (hr && atoll(hr) >= 0) r->headroom = atoll(hr);
     return r.release();
 }
 

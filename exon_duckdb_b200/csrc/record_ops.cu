@@ -286,7 +286,7 @@ __device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8
 // 16-byte store; chunks that straddle rows fall back to bytes.  Throughput does not depend on the row length: 12-byte
 // descriptions, 150-byte reads and 250 Mbp contigs all stream.  `off` = exclusive prefix sum of the row lengths,
 // n_rows + 1 entries (monotone; empty rows are fine).
-constexpr int GS_SPAN = 16384, GS_ROWS = 512, GS_THREADS = 256;
+constexpr int GS_SPAN = 65536, GS_ROWS = 512, GS_THREADS = 256, GS_SEG = 64;
 
 struct SrcRanges {  // generic: start[i]
     const int64_t* start;
@@ -307,33 +307,20 @@ struct SrcFastq {  // field `col` of the selected FASTQ records
     }
 };
 
-// 16 bytes from an arbitrary address: two aligned 16-byte loads, shifted
+// 16 bytes from an arbitrary address: five 4-byte aligned words (they share at most two 32-byte sectors, so the extra
+// load instructions hit L1) and four funnel shifts.  An earlier version used two aligned 16-byte loads and a select
+// network to pick the five words: 15 SEL + 6 ISETP per chunk, the hottest lines of the kernel.
 __device__ __forceinline__ uint4 load16_unaligned(const uint8_t* __restrict__ src) {
-    const int sh = (int)((uintptr_t)src & 15);
-    const uint4* base = reinterpret_cast<const uint4*>(src - sh);
-    const uint4 a = base[0];
-    if (sh == 0) return a;
-    const uint4 b = base[1];
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    const int wi = sh >> 2, bs = (sh & 3) * 8;
-    uint32_t r[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) {  // words wi .. wi+4 without dynamic register indexing
-        uint32_t v = w[k];
-#pragma unroll
-        for (int j = 1; j < 4; j++) v = (wi == j) ? w[k + j] : v;
-        r[k] = v;
-    }
-    return make_uint4(__funnelshift_r(r[0], r[1], bs), __funnelshift_r(r[1], r[2], bs), __funnelshift_r(r[2], r[3], bs),
-                      __funnelshift_r(r[3], r[4], bs));
+    const int bs = (int)((uintptr_t)src & 3) * 8;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(src - (bs >> 3));
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    if (bs == 0) return make_uint4(w0, w1, w2, w3);
+    const uint32_t w4 = w[4];
+    return make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
 }
 
-// 128-bit byte mask: bytes [s, e) of a 16-byte chunk (0 <= s < e <= 16)
-__device__ __forceinline__ uint64_t bytes_below64(int k) { return k >= 8 ? ~0ull : (k <= 0 ? 0ull : ((1ull << (8 * k)) - 1ull)); }
-__device__ __forceinline__ uint4 byte_range_mask(int s, int e) {
-    const uint64_t lo = bytes_below64(e) & ~bytes_below64(s), hi = bytes_below64(e - 8) & ~bytes_below64(s - 8);
-    return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
-}
+// 128-bit byte mask as four words: bytes [0, s) of a 16-byte chunk, 0 < s < 16 (32-bit arithmetic only)
+__device__ __forceinline__ uint32_t bytes_below32(int k) { return k >= 4 ? 0xFFFFFFFFu : (k <= 0 ? 0u : ((1u << (8 * k)) - 1u)); }
 
 // Positions inside a span are kept RELATIVE to span_lo (the 16-byte aligned output address the span starts at), so the
 // inner loop runs on 32-bit integers: s_rel[i] = off[row0 + i] - span_lo clamped to +-2^30 (rows that begin before the
@@ -343,10 +330,11 @@ __device__ __forceinline__ uint4 byte_range_mask(int s, int e) {
 // per piece -- and stored ONCE.  (The first version copied straddling chunks byte by byte: one chunk in ten for
 // 150-byte rows, but under warp divergence 2/3 of all issued instructions.)
 template <typename SrcFn>
-__global__ void __launch_bounds__(GS_THREADS) gather_span_kernel(const uint8_t* __restrict__ buf, SrcFn srcfn, const int64_t* __restrict__ off,
+__global__ void __launch_bounds__(GS_THREADS, 8) gather_span_kernel(const uint8_t* __restrict__ buf, SrcFn srcfn, const int64_t* __restrict__ off,
                                                                  int64_t n_rows, uint8_t* __restrict__ out) {
     __shared__ int32_t s_rel[GS_ROWS + 1];
     __shared__ int64_t s_adj[GS_ROWS];
+    __shared__ uint16_t s_seg[GS_SPAN / GS_SEG];  // row (batch-local) that holds relative position GS_SEG * j
     const int t = threadIdx.x;
     const int64_t total = off[n_rows];
     // spans are aligned to 16 bytes of the OUTPUT ADDRESS so that chunk stores are aligned whatever `out` is
@@ -396,19 +384,27 @@ __global__ void __launch_bounds__(GS_THREADS) gather_span_kernel(const uint8_t* 
                 cnt += __syncthreads_count(i < cap && s_rel[i] < hi_rel);
             }
             for (int i = t; i < cnt; i += GS_THREADS) s_adj[i] = srcfn(row0 + i) - (off[row0 + i] - span_lo);
+            // one binary search per 64-byte segment (one per thread) instead of one per 16-byte chunk
+            const int seg_end = ((s_rel[cnt] < hi_rel ? s_rel[cnt] : hi_rel) + GS_SEG - 1) / GS_SEG;  // segments this batch serves
+            for (int j = lo_rel / GS_SEG + t; j < seg_end; j += GS_THREADS) {
+                const int q = j * GS_SEG;
+                int a = 0, b = cnt;  // last i in [0, cnt) with s_rel[i] <= q (s_rel[0] <= lo_rel; positions before lo_rel are never looked up)
+                while (b - a > 1) {
+                    const int m = (a + b) >> 1;
+                    if (s_rel[m] <= q) a = m;
+                    else b = m;
+                }
+                s_seg[j] = (uint16_t)a;
+            }
             __syncthreads();
             // rows row0 .. row0 + cnt cover [lo_rel, batch_hi)
             const int batch_hi = s_rel[cnt] < hi_rel ? s_rel[cnt] : hi_rel;
             for (int k = (lo_rel >> 4) + t; (k << 4) < batch_hi; k += GS_THREADS) {
                 const int c0 = k << 4;
                 const int q0 = c0 < lo_rel ? lo_rel : c0, q1 = c0 + 16 > batch_hi ? batch_hi : c0 + 16;
-                // local row of q0: last i with s_rel[i] <= q0
-                int a = 0, b = cnt;
-                while (b - a > 1) {
-                    const int m = (a + b) >> 1;
-                    if (s_rel[m] <= q0) a = m;
-                    else b = m;
-                }
+                // local row of q0: last i with s_rel[i] <= q0 -- from the segment's row, a step or two forward
+                int a = s_seg[q0 / GS_SEG];
+                while (a + 1 < cnt && s_rel[a + 1] <= q0) a++;
                 bool whole = q1 - q0 == 16;
                 uint4 acc = make_uint4(0, 0, 0, 0);
                 if (whole) {
@@ -422,14 +418,15 @@ __global__ void __launch_bounds__(GS_THREADS) gather_span_kernel(const uint8_t* 
                             break;
                         }
                         const uint4 v = load16_unaligned(buf + src);
-                        if (e - q == 16) {
-                            acc = v;
-                        } else {
-                            const uint4 m = byte_range_mask(q - c0, e - c0);
-                            acc.x |= v.x & m.x;
-                            acc.y |= v.y & m.y;
-                            acc.z |= v.z & m.z;
-                            acc.w |= v.w & m.w;
+                        if (q == c0) {
+                            acc = v;  // bytes past this row's end are garbage until the next piece overwrites them
+                        } else {      // pieces arrive in order and the last one ends the chunk: keep [0, s), take [s, 16)
+                            const int sb = q - c0;
+                            const uint32_t m0 = bytes_below32(sb), m1 = bytes_below32(sb - 4), m2 = bytes_below32(sb - 8), m3 = bytes_below32(sb - 12);
+                            acc.x = (acc.x & m0) | (v.x & ~m0);
+                            acc.y = (acc.y & m1) | (v.y & ~m1);
+                            acc.z = (acc.z & m2) | (v.z & ~m2);
+                            acc.w = (acc.w & m3) | (v.w & ~m3);
                         }
                         q = e;
                     }

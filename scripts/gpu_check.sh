@@ -19,3 +19,5 @@ EXB_BENCH_READS=4000000 timeout 600 ncu --set full --clock-control none --import
 echo "ncu full exit $?"
 timeout 600 python scripts/bench_paths.py --out gpurun_out/${TAG}_paths.json > gpurun_out/${TAG}_paths.log 2>&1
 echo "paths exit $?"; tail -30 gpurun_out/${TAG}_paths.log
+timeout 300 python scripts/bench_reader.py --out gpurun_out/${TAG}_reader.json > gpurun_out/${TAG}_reader.log 2>&1
+echo "reader exit $?"; tail -9 gpurun_out/${TAG}_reader.log

@@ -147,12 +147,11 @@ def test_reader_chunk_carry_fasta(cuda_device, tmp_path, monkeypatch, chunk):
 
 
 @pytest.mark.parametrize("fmt", ["fastq", "fasta"])
-def test_reader_tail_longer_than_headroom(cuda_device, tmp_path, monkeypatch, fmt):
-    """The unconsumed tail of a chunk normally fits the headroom in front of the next block; a record that spans whole
-    blocks does not, and the chunk is then rebuilt in a bigger buffer (and blocks double).  Both paths, same rows."""
+def test_reader_records_longer_than_a_block(cuda_device, tmp_path, monkeypatch, fmt):
+    """The unconsumed tail of a chunk stays in HBM and the next block is appended behind it; a record that spans whole
+    blocks makes the chunk grow (and the blocks double) until it holds a complete record.  Same rows either way."""
     from oracle import oracle as O
     monkeypatch.setenv("EXON_B200_CHUNK_BYTES", "2048")
-    monkeypatch.setenv("EXON_B200_HEADROOM", "64")
     p = tmp_path / ("a." + fmt)
     if fmt == "fastq":
         text, _ = util.random_fastq(11, 300, max_len=5000, min_len=10, tricky=False)
