@@ -5,7 +5,8 @@ Workload (per GPU): synthetic Illumina FASTQ, 20 M reads x 150 bp (~7 GB), query
     SELECT COUNT(*) FROM read_fastq(f) WHERE list_avg(quality_score_string_to_list(quality_scores)) > 30
 One step = one pass of the hot path over the whole file image:
     exb_fastq_scan_filter: TMA-fed tile kernel (every byte once: newline masks, Phred sums, predicate per line into
-    4 phase buckets) -> offset scan of the per-tile line counts -> combine kernel (picks each tile's bucket)
+    4 phase buckets) -> chain-free offset scan of the per-tile line counts (3 short launches) -> combine kernel (picks
+    each tile's bucket)
 `value`  : input already resident in HBM, CUDA events on the launching stream, max over ranks.
 `e2e`    : the same query through the host-buffer engine (exb_engine_fastq_count): pinned host
            buffer -> chunked H2D overlapped with the scans -> aggregates read back, every step.
@@ -419,12 +420,13 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic_per_launch(tr, n_bytes), "kernel": "fastq_tile_kernel<F_FUSED|F_QUAL> (TMA-fed byte pass; + offset scan + bucket-combine kernels, ~4% of the step)",
                          "algorithmic_bytes_per_launch": n_bytes, "kernel_ms": scan_ms, "peak_source": peak_src,
-                         "note": "algorithmic bytes = input file bytes read once (SURVEY 8d); kernel_ms = CUDA events on the launching stream around one exb_fastq_scan_filter call (3 small memsets + tile kernel + offset scan + combine kernel), i.e. an upper bound of the tile kernel's own duration"},
+                         "note": "algorithmic bytes = input file bytes read once (SURVEY 8d); kernel_ms = CUDA events on the launching stream around one exb_fastq_scan_filter call (3 small memsets + tile kernel + 3 offset-scan kernels + combine kernel), i.e. an upper bound of the tile kernel's own duration"},
             "clocks": sampler.summary(),
-            # N=1: fastq_tile_kernel, exclusive_scan_kernel, fastq_fused_combine_kernel (+ 3 cudaMemsetAsync);
-            # N>1 adds per rank: fastq_compose_prev_kernel + a second fastq_fused_combine_kernel (ranks >= 1)
+            # N=1: fastq_tile_kernel, scan_reduce / scan_spine / scan_down (per-tile line offsets), fastq_fused_combine_kernel
+            # (+ 3 cudaMemsetAsync); N>1 adds per rank: fastq_compose_prev_kernel + a second fastq_fused_combine_kernel
+            # (ranks >= 1) and, with the peer-memory exchange, peer_allgather_kernel + peer_count_reduce_kernel
             # peer-memory exchange adds exb_peer_allgather_block + exb_peer_count_reduce (7 of this library's kernels per step)
-            "gpu_launches": (3 if world == 1 else (7 if exchange.startswith("nvlink") else 5)) * args.steps,
+            "gpu_launches": (5 if world == 1 else (9 if exchange.startswith("nvlink") else 7)) * args.steps,
         }
         if world > 1:
             line["exchange"] = exchange

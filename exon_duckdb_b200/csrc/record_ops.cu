@@ -81,98 +81,137 @@ __global__ void __launch_bounds__(256) fastq_filter_kernel(FilterArgs a) {
 }
 
 // ================================================================= exclusive scan (u32 / u8 -> i64)
-struct alignas(16) SumState {
-    int64_t sum;
-    int64_t pad;
-    __device__ static SumState combine(const SumState& p, const SumState& t) { return SumState{p.sum + t.sum, 0}; }
-};
-
+// Chain-free: reduce (one sum per tile of 4096 items) -> spine (one block per column scans the tile sums in place)
+// -> downsweep (local scan + tile base).  The first version was a single-pass decoupled look-back; with 16 KiB tiles a
+// hop costs ~140 ns and the chain serialises (58 us for the 1.7 M per-tile line counts of a 7 GB FASTQ, 150 us for the
+// four 4 M-row offset columns of a table).  Three short launches read the input twice but never wait on a neighbour.
+// `cols` independent columns share the launches (blockIdx.y): column c reads in + c * in_stride, writes
+// out + c * out_stride and keeps its tile sums at sums + c * n_tiles.
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = BLOCK_THREADS * SCAN_ITEMS;
 
-// blockIdx.x = column: `cols` independent scans (their own chain and ticket) share one launch -- the four field-length
-// columns of a FASTQ table cost one launch latency instead of four.
 template <typename T>
-__global__ void __launch_bounds__(BLOCK_THREADS) exclusive_scan_kernel(const T* __restrict__ in, int64_t n, int64_t* __restrict__ out,
-                                                                      TileSlot* slots, unsigned long long* ticket, int64_t n_tiles,
-                                                                      int64_t in_stride, int64_t out_stride, int cols) {
-    __shared__ int64_t s_tile_id;
-    __shared__ uint64_t s_warp[WARPS];
-    __shared__ int64_t s_excl;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (cols > 1) {  // grid (cols, n_tiles); a single column is a plain 1-D grid of n_tiles blocks
-        in += (int64_t)blockIdx.x * in_stride;
-        out += (int64_t)blockIdx.x * out_stride;
-        slots = reinterpret_cast<TileSlot*>(reinterpret_cast<uint64_t*>(slots) + (int64_t)blockIdx.x * n_tiles);
-        ticket += blockIdx.x;
-    }
-    if (t == 0) s_tile_id = (int64_t)atomicAdd(ticket, 1ull);
-    __syncthreads();
-    const int64_t tile = s_tile_id;
-    const int64_t base = tile * SCAN_TILE + (int64_t)t * SCAN_ITEMS;
-    uint32_t x[SCAN_ITEMS];
+__device__ __forceinline__ uint64_t scan_load_items(const T* __restrict__ in, int64_t base, int64_t n, uint32_t (&x)[SCAN_ITEMS]) {
     uint64_t loc = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
         x[i] = (base + i < n) ? (uint32_t)in[base + i] : 0u;
         loc += x[i];
     }
-    uint64_t incl = warp_incl_scan_u64(loc);
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint64_t woff = 0, tot = 0;
-    for (int w = 0; w < WARPS; w++) {
-        if (w < warp) woff += s_warp[w];
-        tot += s_warp[w];
-    }
-    __shared__ LookbackSmem<1> s_lb;
-    const uint64_t agg[1] = {tot}, init[1] = {0};
-    uint64_t excl[1];
-    block_lookback<1>(reinterpret_cast<uint64_t*>(slots), tile, agg, init, excl, &s_lb);
-    if (t == 0 && tile == n_tiles - 1) out[n] = (int64_t)(excl[0] + tot);
-    (void)s_excl;
-    int64_t run = (int64_t)excl[0] + (int64_t)(woff + incl - loc);
+    return loc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BLOCK_THREADS) scan_reduce_kernel(const T* __restrict__ in, int64_t n, uint64_t* __restrict__ sums, int64_t n_tiles,
+                                                                   int64_t in_stride) {
+    __shared__ uint64_t s_warp[WARPS];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    in += (int64_t)blockIdx.y * in_stride;
+    sums += (int64_t)blockIdx.y * n_tiles;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t x[SCAN_ITEMS];
+        uint64_t loc = scan_load_items(in, tile * SCAN_TILE + (int64_t)t * SCAN_ITEMS, n, x);
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        if (base + i < n) out[base + i] = run;
-        run += x[i];
+        for (int d = 16; d > 0; d >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, d);
+        __syncthreads();
+        if (lane == 0) s_warp[warp] = loc;
+        __syncthreads();
+        if (t == 0) {
+            uint64_t tot = 0;
+            for (int w = 0; w < WARPS; w++) tot += s_warp[w];
+            sums[tile] = tot;
+        }
     }
 }
 
-cudaError_t exclusive_scan_launch_u32(const uint32_t* in, int64_t n, int64_t* out, TileSlot* slots, unsigned long long* ticket,
-                                      cudaStream_t st) {
-    int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    if (n_tiles == 0) n_tiles = 1;
-    exclusive_scan_kernel<uint32_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles, 0, 0, 1);
-    return cudaGetLastError();
-}
-cudaError_t exclusive_scan_launch_u32_multi(const uint32_t* in, int64_t n, int cols, int64_t in_stride, int64_t* out, int64_t out_stride,
-                                            TileSlot* slots, unsigned long long* ticket, cudaStream_t st) {
-    int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    if (n_tiles == 0) n_tiles = 1;
-    // column = blockIdx.x (fastest): blocks are dispatched x first, so the tiles of the `cols` chains interleave and the
-    // chains advance side by side (with the column in y they ran one after the other: 188 us for 4 x 4 M rows, not 55)
-    if (n_tiles > 65535 || cols == 1) {  // gridDim.y limit: fall back to one launch per column
-        for (int c = 0; c < cols; c++)
-            exclusive_scan_kernel<uint32_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(
-                in + c * in_stride, n, out + c * out_stride, reinterpret_cast<TileSlot*>(reinterpret_cast<uint64_t*>(slots) + c * n_tiles),
-                ticket + c, n_tiles, 0, 0, 1);
-        return cudaGetLastError();
+// one block per column: tile sums -> exclusive tile bases, in place; the column total goes to out[n]
+__global__ void __launch_bounds__(1024) scan_spine_kernel(uint64_t* __restrict__ sums, int64_t n_tiles, int64_t* __restrict__ out, int64_t n,
+                                                         int64_t out_stride) {
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_run;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    sums += (int64_t)blockIdx.x * n_tiles;
+    out += (int64_t)blockIdx.x * out_stride;
+    if (t == 0) s_run = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_tiles; base += 1024) {
+        const int64_t i = base + t;
+        const uint64_t v = i < n_tiles ? sums[i] : 0ull;
+        const uint64_t incl = warp_incl_scan_u64(v);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint64_t woff = 0, tot = 0;
+        for (int w = 0; w < 32; w++) {
+            if (w < warp) woff += s_warp[w];
+            tot += s_warp[w];
+        }
+        const uint64_t run = s_run;
+        if (i < n_tiles) sums[i] = run + woff + incl - v;
+        __syncthreads();
+        if (t == 0) s_run = run + tot;
+        __syncthreads();
     }
-    exclusive_scan_kernel<uint32_t><<<dim3((unsigned)cols, (unsigned)n_tiles), BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles,
-                                                                                                    in_stride, out_stride, cols);
-    return cudaGetLastError();
+    if (t == 0) out[n] = (int64_t)s_run;
 }
-cudaError_t exclusive_scan_launch_u8(const uint8_t* in, int64_t n, int64_t* out, TileSlot* slots, unsigned long long* ticket,
-                                     cudaStream_t st) {
-    int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    if (n_tiles == 0) n_tiles = 1;
-    exclusive_scan_kernel<uint8_t><<<(unsigned)n_tiles, BLOCK_THREADS, 0, st>>>(in, n, out, slots, ticket, n_tiles, 0, 0, 1);
-    return cudaGetLastError();
+
+template <typename T>
+__global__ void __launch_bounds__(BLOCK_THREADS) scan_down_kernel(const T* __restrict__ in, int64_t n, int64_t* __restrict__ out,
+                                                                 const uint64_t* __restrict__ sums, int64_t n_tiles, int64_t in_stride,
+                                                                 int64_t out_stride) {
+    __shared__ uint64_t s_warp[WARPS];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    in += (int64_t)blockIdx.y * in_stride;
+    out += (int64_t)blockIdx.y * out_stride;
+    sums += (int64_t)blockIdx.y * n_tiles;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * SCAN_TILE + (int64_t)t * SCAN_ITEMS;
+        uint32_t x[SCAN_ITEMS];
+        const uint64_t loc = scan_load_items(in, base, n, x);
+        const uint64_t incl = warp_incl_scan_u64(loc);
+        __syncthreads();
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint64_t woff = 0;
+        for (int w = 0; w < warp; w++) woff += s_warp[w];
+        int64_t run = (int64_t)(sums[tile] + woff + incl - loc);
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            if (base + i < n) out[base + i] = run;
+            run += x[i];
+        }
+    }
 }
+
 int64_t scan_tiles(int64_t n) {
     int64_t t = (n + SCAN_TILE - 1) / SCAN_TILE;
     return t ? t : 1;
+}
+
+template <typename T>
+static cudaError_t exclusive_scan_launch_t(const T* in, int64_t n, int cols, int64_t in_stride, int64_t* out, int64_t out_stride, TileSlot* slots,
+                                           cudaStream_t st) {
+    const int64_t n_tiles = scan_tiles(n);
+    uint64_t* sums = reinterpret_cast<uint64_t*>(slots);  // cols * n_tiles words of the caller's workspace
+    const unsigned gx = (unsigned)(n_tiles < 148 * 16 ? n_tiles : 148 * 16);
+    scan_reduce_kernel<T><<<dim3(gx, (unsigned)cols), BLOCK_THREADS, 0, st>>>(in, n, sums, n_tiles, in_stride);
+    scan_spine_kernel<<<(unsigned)cols, 1024, 0, st>>>(sums, n_tiles, out, n, out_stride);
+    scan_down_kernel<T><<<dim3(gx, (unsigned)cols), BLOCK_THREADS, 0, st>>>(in, n, out, sums, n_tiles, in_stride, out_stride);
+    return cudaGetLastError();
+}
+cudaError_t exclusive_scan_launch_u32(const uint32_t* in, int64_t n, int64_t* out, TileSlot* slots, unsigned long long* ticket,
+                                      cudaStream_t st) {
+    (void)ticket;
+    return exclusive_scan_launch_t<uint32_t>(in, n, 1, 0, out, 0, slots, st);
+}
+cudaError_t exclusive_scan_launch_u32_multi(const uint32_t* in, int64_t n, int cols, int64_t in_stride, int64_t* out, int64_t out_stride,
+                                            TileSlot* slots, unsigned long long* ticket, cudaStream_t st) {
+    (void)ticket;
+    return exclusive_scan_launch_t<uint32_t>(in, n, cols, in_stride, out, out_stride, slots, st);
+}
+cudaError_t exclusive_scan_launch_u8(const uint8_t* in, int64_t n, int64_t* out, TileSlot* slots, unsigned long long* ticket,
+                                     cudaStream_t st) {
+    (void)ticket;
+    return exclusive_scan_launch_t<uint8_t>(in, n, 1, 0, out, 0, slots, st);
 }
 
 __global__ void select_rows_kernel(const uint8_t* __restrict__ pass, const int64_t* __restrict__ off, int64_t n,
@@ -399,12 +438,9 @@ __global__ void __launch_bounds__(GS_THREADS, 8) gather_span_kernel(const uint8_
             __syncthreads();
             // rows row0 .. row0 + cnt cover [lo_rel, batch_hi)
             const int batch_hi = s_rel[cnt] < hi_rel ? s_rel[cnt] : hi_rel;
-            for (int k = (lo_rel >> 4) + t; (k << 4) < batch_hi; k += GS_THREADS) {
-                const int c0 = k << 4;
+            // One chunk, general case: pieces of several rows (or a ragged edge of the column / batch).
+            auto chunk_general = [&](int c0, int a) {
                 const int q0 = c0 < lo_rel ? lo_rel : c0, q1 = c0 + 16 > batch_hi ? batch_hi : c0 + 16;
-                // local row of q0: last i with s_rel[i] <= q0 -- from the segment's row, a step or two forward
-                int a = s_seg[q0 / GS_SEG];
-                while (a + 1 < cnt && s_rel[a + 1] <= q0) a++;
                 bool whole = q1 - q0 == 16;
                 uint4 acc = make_uint4(0, 0, 0, 0);
                 if (whole) {
@@ -439,6 +475,24 @@ __global__ void __launch_bounds__(GS_THREADS, 8) gather_span_kernel(const uint8_
                         span_out[q] = buf[s_adj[a] + q];
                     }
                 }
+            };
+            // local row of a position: last i with s_rel[i] <= q -- from the segment's row, a step or two forward
+            auto row_of = [&](int q) {
+                int a = s_seg[q / GS_SEG];
+                while (a + 1 < cnt && s_rel[a + 1] <= q) a++;
+                return a;
+            };
+            // One chunk per thread and iteration at 8 CTAs / SM.  (Two chunks in flight per thread at 6 CTAs / SM -- the
+            // register cost of the second set of loads -- measured slower: 556 vs 452 us per 600 MB column.)
+            for (int k = (lo_rel >> 4) + t; (k << 4) < batch_hi; k += GS_THREADS) {
+                const int c0 = k << 4;
+                const int q0 = c0 < lo_rel ? lo_rel : c0;
+                const int a = row_of(q0);
+                const int64_t src = s_adj[a] + c0;
+                if (c0 >= lo_rel && c0 + 16 <= batch_hi && s_rel[a + 1] >= c0 + 16 && src >= 0)  // inside one row: load + store
+                    *reinterpret_cast<uint4*>(span_out + c0) = load16_unaligned(buf + src);
+                else
+                    chunk_general(c0, a);
             }
             lo_rel = batch_hi;
             row0 += cnt;  // the batch ended on its last row (lo = off[row0 + cnt]), or lo == hi and the loop ends
