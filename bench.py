@@ -312,18 +312,25 @@ def main():
             if timers is not None:
                 timers[0].record()
             # scan -> exchange of the result blocks -> compose + resolve -> reduce of COUNT / sums (dist.py)
-            sharded.step(after_scan=timers[1].record if timers is not None else None)
+            sharded.step(after_scan=timers[1].record if timers is not None else None,
+                         stage_marks=(timers[2].record, timers[3].record) if timers is not None and len(timers) > 2 else None)
+            if timers is not None and len(timers) > 2:
+                timers[4].record()
 
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    scan_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n_ev = 5 if (world > 1 and os.environ.get("EXB_BENCH_STAGES")) else 2  # stage timing: scan | exchange | resolve | reduce
+    scan_ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(n_ev)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        # the barrier is the LAST thing before the timed region: NVML start-up and event creation take a different time
+        # on every rank, and in a lock-step exchange a rank that starts 2 ms late is charged to every other rank's total
+        dist.barrier()
+        torch.cuda.synchronize()
     e0.record()
     for i in range(args.steps):
         step(scan_ev[i])
@@ -333,7 +340,12 @@ def main():
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
-    scan_ms = sum(a.elapsed_time(b) for a, b in scan_ev) / args.steps
+    scan_ms = sum(ev[0].elapsed_time(ev[1]) for ev in scan_ev) / args.steps
+    if n_ev == 5:
+        st = [sum(ev[i].elapsed_time(ev[i + 1]) for ev in scan_ev) / args.steps for i in range(4)]
+        gap = (ms_total - sum(ev[0].elapsed_time(ev[4]) for ev in scan_ev)) / args.steps
+        sys.stderr.write("rank %d stages (ms/step): scan %.4f  block exchange %.4f  compose+resolve %.4f  reduce %.4f  between steps %.4f\n"
+                         % (rank, st[0], st[1], st[2], st[3], gap))
     got = agg.cpu().tolist()
     tmax = torch.tensor([ms_total, scan_ms], dtype=torch.float64, device=dev)
     if world > 1:

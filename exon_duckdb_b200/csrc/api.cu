@@ -90,8 +90,19 @@ __global__ void gen_fill_kernel(exb_gen_params p, const int64_t* off, uint8_t* o
 
 // True predecessor state of shard `rank` from the all-gathered result blocks of all shards (one thread: the walk is
 // over at most `world` blocks).  Host mirror with the derivation: exon_duckdb_b200/dist.py compose_prev.
-__global__ void fastq_compose_prev_kernel(const uint8_t* blocks, const int64_t* ranges, int world, int rank, ScanResult* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(128) fastq_compose_prev_kernel(const uint8_t* g_blocks, const int64_t* g_ranges, int world, int rank,
+                                                                ScanResult* out) {
+    // stage the (at most 16) blocks and ranges in shared memory with one round of parallel loads: the walk below is a
+    // chain of dependent reads, ~1 us each from global memory and on every rank's critical path once per step
+    __shared__ __align__(16) uint64_t s_blocks[16 * 16];
+    __shared__ int64_t s_ranges[16 * 3];
+    if (world > 16) return;  // the API rejects it
+    for (int i = threadIdx.x; i < world * 16; i += blockDim.x) s_blocks[i] = reinterpret_cast<const uint64_t*>(g_blocks)[i];
+    for (int i = threadIdx.x; i < world * 3; i += blockDim.x) s_ranges[i] = g_ranges[i];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const uint8_t* blocks = reinterpret_cast<const uint8_t*>(s_blocks);
+    const int64_t* ranges = s_ranges;
     auto blk = [&](int j) { return reinterpret_cast<const ScanResult*>(blocks + (size_t)j * 128); };
     auto lo = [&](int j) { return ranges[3 * j]; };
     auto hi = [&](int j) { return ranges[3 * j + 1]; };
@@ -316,9 +327,9 @@ int exb_fastq_scan_filter_resolve(int64_t begin, int64_t n, int is_final, const 
 }
 
 int exb_fastq_compose_prev(const void* d_blocks, const int64_t* d_ranges, int world, int rank, void* d_prev_out, void* stream) {
-    if (!d_blocks || !d_ranges || !d_prev_out || world < 1 || rank < 0 || rank >= world)
-        return set_err(EXB_ERR_ARG, "exb_fastq_compose_prev: bad arguments");
-    fastq_compose_prev_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(d_blocks), d_ranges, world, rank,
+    if (!d_blocks || !d_ranges || !d_prev_out || world < 1 || world > 16 || rank < 0 || rank >= world)
+        return set_err(EXB_ERR_ARG, "exb_fastq_compose_prev: bad arguments (1 <= world <= 16, 0 <= rank < world)");
+    fastq_compose_prev_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(d_blocks), d_ranges, world, rank,
                                                                   reinterpret_cast<ScanResult*>(d_prev_out));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "fastq_compose_prev launch");

@@ -338,20 +338,25 @@ class ShardedFastqCount:
                                                        D._ptr(self.c.agg), 0, D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
             self.c._res = None
 
-    def step(self, after_scan=None):
+    def step(self, after_scan=None, stage_marks=None):
         """One pass over the shard + the exchange; every launch is asynchronous on the current stream.
-        after_scan: optional callable invoked between the scan and the exchange (bench.py records a CUDA event there)."""
+        after_scan: optional callable invoked between the scan and the exchange (bench.py records a CUDA event there);
+        stage_marks: optional pair of callables invoked after the block exchange and after the resolve (stage timing)."""
         from . import device as D
 
         g = self.group
         blk = self.scan()
         if after_scan is not None:
             after_scan()
-        if isinstance(g, PeerGroup):  # 5 launches of this library per step, no NCCL
+        if isinstance(g, PeerGroup):  # 9 launches of this library per step, no NCCL
             L = _lib.lib()
             g.seq += 1
             _lib.check(L.exb_peer_allgather_block(g.d_peers, g.rank, g.world, D._ptr(blk), g.seq, D._stream()))
+            if stage_marks is not None:
+                stage_marks[0]()
             self.resolve_local(g.blocks_view(g.seq), g.rank)
+            if stage_marks is not None:
+                stage_marks[1]()
             _lib.check(L.exb_peer_count_reduce(g.d_peers, g.rank, g.world, D._ptr(self.c.ws), D._ptr(self.c.agg), 1 if self.shard.is_last else 0,
                                                g.seq, D._ptr(self.total), D._stream()))
             return self.total
