@@ -87,18 +87,27 @@ __global__ void __launch_bounds__(256) fastq_filter_kernel(FilterArgs a) {
 // four 4 M-row offset columns of a table).  Three short launches read the input twice but never wait on a neighbour.
 // `cols` independent columns share the launches (blockIdx.y): column c reads in + c * in_stride, writes
 // out + c * out_stride and keeps its tile sums at sums + c * n_tiles.
-constexpr int SCAN_ITEMS = 16;
-constexpr int SCAN_TILE = BLOCK_THREADS * SCAN_ITEMS;
+constexpr int SCAN_VEC = 4, SCAN_ROUNDS = 4;
+constexpr int SCAN_ROUND_ITEMS = BLOCK_THREADS * SCAN_VEC;   // 1024 items per round: a thread owns 4 consecutive ones
+constexpr int SCAN_TILE = SCAN_ROUND_ITEMS * SCAN_ROUNDS;   // 4096 items per tile
 
+// four consecutive items as one 16-byte (u32) / 4-byte (u8) load when the column is aligned for it, so a warp reads
+// 512 (128) contiguous bytes per instruction; the first version read 16 items per thread with 64-byte strides
 template <typename T>
-__device__ __forceinline__ uint64_t scan_load_items(const T* __restrict__ in, int64_t base, int64_t n, uint32_t (&x)[SCAN_ITEMS]) {
-    uint64_t loc = 0;
+__device__ __forceinline__ uint32_t scan_load4(const T* __restrict__ in, int64_t idx, int64_t n, bool vec_ok, uint32_t (&x)[SCAN_VEC]) {
+    if (vec_ok && idx + SCAN_VEC <= n) {
+        if (sizeof(T) == 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(in + idx);
+            x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
+        } else {
+            const uchar4 v = *reinterpret_cast<const uchar4*>(in + idx);
+            x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
+        }
+    } else {
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        x[i] = (base + i < n) ? (uint32_t)in[base + i] : 0u;
-        loc += x[i];
+        for (int i = 0; i < SCAN_VEC; i++) x[i] = (idx + i < n) ? (uint32_t)in[idx + i] : 0u;
     }
-    return loc;
+    return x[0] + x[1] + x[2] + x[3];
 }
 
 template <typename T>
@@ -108,9 +117,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS) scan_reduce_kernel(const T* __r
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     in += (int64_t)blockIdx.y * in_stride;
     sums += (int64_t)blockIdx.y * n_tiles;
+    const bool vec_ok = ((uintptr_t)in & (SCAN_VEC * sizeof(T) - 1)) == 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint32_t x[SCAN_ITEMS];
-        uint64_t loc = scan_load_items(in, tile * SCAN_TILE + (int64_t)t * SCAN_ITEMS, n, x);
+        uint64_t loc = 0;
+#pragma unroll
+        for (int r = 0; r < SCAN_ROUNDS; r++) {
+            uint32_t x[SCAN_VEC];
+            loc += scan_load4(in, tile * SCAN_TILE + r * SCAN_ROUND_ITEMS + t * SCAN_VEC, n, vec_ok, x);
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, d);
         __syncthreads();
@@ -158,27 +172,43 @@ template <typename T>
 __global__ void __launch_bounds__(BLOCK_THREADS) scan_down_kernel(const T* __restrict__ in, int64_t n, int64_t* __restrict__ out,
                                                                  const uint64_t* __restrict__ sums, int64_t n_tiles, int64_t in_stride,
                                                                  int64_t out_stride) {
-    __shared__ uint64_t s_warp[WARPS];
+    __shared__ uint64_t s_warp[2][WARPS];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     in += (int64_t)blockIdx.y * in_stride;
     out += (int64_t)blockIdx.y * out_stride;
     sums += (int64_t)blockIdx.y * n_tiles;
+    const bool vec_ok = ((uintptr_t)in & (SCAN_VEC * sizeof(T) - 1)) == 0;
+    const bool out16 = ((uintptr_t)out & 15) == 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t base = tile * SCAN_TILE + (int64_t)t * SCAN_ITEMS;
-        uint32_t x[SCAN_ITEMS];
-        const uint64_t loc = scan_load_items(in, base, n, x);
-        const uint64_t incl = warp_incl_scan_u64(loc);
-        __syncthreads();
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        uint64_t woff = 0;
-        for (int w = 0; w < warp; w++) woff += s_warp[w];
-        int64_t run = (int64_t)(sums[tile] + woff + incl - loc);
+        uint64_t carry = sums[tile];
 #pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            if (base + i < n) out[base + i] = run;
-            run += x[i];
+        for (int r = 0; r < SCAN_ROUNDS; r++) {
+            const int64_t idx = tile * SCAN_TILE + r * SCAN_ROUND_ITEMS + t * SCAN_VEC;
+            uint32_t x[SCAN_VEC];
+            const uint64_t loc = scan_load4(in, idx, n, vec_ok, x);
+            const uint64_t incl = warp_incl_scan_u64(loc);
+            if (lane == 31) s_warp[r & 1][warp] = incl;  // double-buffered: one barrier per round
+            __syncthreads();
+            uint64_t woff = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) {
+                const uint64_t v = s_warp[r & 1][w];
+                if (w < warp) woff += v;
+                tot += v;
+            }
+            const int64_t o0 = (int64_t)(carry + woff + incl - loc), o1 = o0 + x[0], o2 = o1 + x[1], o3 = o2 + x[2];
+            if (idx + SCAN_VEC <= n && out16) {
+                reinterpret_cast<longlong2*>(out + idx)[0] = make_longlong2(o0, o1);
+                reinterpret_cast<longlong2*>(out + idx)[1] = make_longlong2(o2, o3);
+            } else {
+                if (idx < n) out[idx] = o0;
+                if (idx + 1 < n) out[idx + 1] = o1;
+                if (idx + 2 < n) out[idx + 2] = o2;
+                if (idx + 3 < n) out[idx + 3] = o3;
+            }
+            carry += tot;
         }
+        __syncthreads();  // the next tile reuses s_warp[0]
     }
 }
 
@@ -487,12 +517,9 @@ __global__ void __launch_bounds__(GS_THREADS, 8) gather_span_kernel(const uint8_
             for (int k = (lo_rel >> 4) + t; (k << 4) < batch_hi; k += GS_THREADS) {
                 const int c0 = k << 4;
                 const int q0 = c0 < lo_rel ? lo_rel : c0;
-                const int a = row_of(q0);
-                const int64_t src = s_adj[a] + c0;
-                if (c0 >= lo_rel && c0 + 16 <= batch_hi && s_rel[a + 1] >= c0 + 16 && src >= 0)  // inside one row: load + store
-                    *reinterpret_cast<uint4*>(span_out + c0) = load16_unaligned(buf + src);
-                else
-                    chunk_general(c0, a);
+                // every chunk takes the piece loop; a separate "inside one row: load + store" branch in front of it
+                // measured 14 % slower on the same box (455 vs 518 us; scripts/gpu_ab.sh)
+                chunk_general(c0, row_of(q0));
             }
             lo_rel = batch_hi;
             row0 += cnt;  // the batch ended on its last row (lo = off[row0 + cnt]), or lo == hi and the loop ends
