@@ -109,6 +109,7 @@ SIGNATURES = {
     "exb_exclusive_scan_u32_multi": (_i32, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _i64, _vp]),
     "exb_select_rows": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "exb_fastq_gather": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "exb_fastq_gather_map": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "exb_fasta_scan": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "exb_fasta_headers": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "exb_gather_ranges": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),

@@ -21,7 +21,7 @@ cudaError_t select_rows_launch(const uint8_t*, const int64_t*, int64_t, int64_t*
 cudaError_t fastq_fields_launch(const uint8_t*, int64_t, int64_t, const void*, bool, const int64_t*, int64_t, uint32_t*, uint8_t*,
                                 int64_t*, cudaStream_t);
 cudaError_t fastq_gather_launch(const uint8_t*, int64_t, int64_t, const void*, bool, const int64_t*, int64_t, int, const uint32_t*,
-                                const int64_t*, uint8_t*, cudaStream_t);
+                                const int64_t*, uint8_t*, cudaStream_t, int, unsigned long long*);
 cudaError_t gather_ranges_launch(const uint8_t*, const int64_t*, const uint32_t*, const int64_t*, int64_t, int64_t, uint8_t*, cudaStream_t);
 cudaError_t fastq_filter_launch(const uint32_t*, const uint32_t*, const uint32_t*, const int32_t*, int64_t, const exb_predicate*, int,
                                 uint8_t*, int64_t*, const void*, cudaStream_t);
@@ -423,8 +423,20 @@ int exb_fastq_gather(const void* d_buf, int64_t begin, int64_t n, const void* d_
                      int64_t n_rows, int col, const uint32_t* d_lens, const int64_t* d_off, uint8_t* d_out, void* stream) {
     if (col < 0 || col > 3) return set_err(EXB_ERR_ARG, "exb_fastq_gather: col must be 0..3");
     cudaError_t e = fastq_gather_launch(reinterpret_cast<const uint8_t*>(d_buf), begin, n, d_line_end, wide_offsets != 0, d_sel, n_rows,
-                                        col, d_lens, d_off, d_out, (cudaStream_t)stream);
+                                        col, d_lens, d_off, d_out, (cudaStream_t)stream, 0, nullptr);
     if (e != cudaSuccess) return cuda_fail(e, "fastq_gather launch");
+    return 0;
+}
+
+int exb_fastq_gather_map(const void* d_buf, int64_t begin, int64_t n, const void* d_line_end, int wide_offsets, const int64_t* d_sel,
+                         int64_t n_rows, int col, const uint32_t* d_lens, const int64_t* d_off, int mode, uint8_t* d_out, uint64_t* d_bad,
+                         void* stream) {
+    if (col < 2 || col > 3) return set_err(EXB_ERR_ARG, "exb_fastq_gather_map: col must be 2 (sequence) or 3 (quality_scores)");
+    if ((mode != EXB_MAP_REVERSE_COMPLEMENT && mode != EXB_MAP_COMPLEMENT) || !d_bad)
+        return set_err(EXB_ERR_ARG, "exb_fastq_gather_map: mode must be EXB_MAP_REVERSE_COMPLEMENT or EXB_MAP_COMPLEMENT, d_bad non-null");
+    cudaError_t e = fastq_gather_launch(reinterpret_cast<const uint8_t*>(d_buf), begin, n, d_line_end, wide_offsets != 0, d_sel, n_rows,
+                                        col, d_lens, d_off, d_out, (cudaStream_t)stream, mode, reinterpret_cast<unsigned long long*>(d_bad));
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_gather_map launch");
     return 0;
 }
 

@@ -398,13 +398,41 @@ __device__ __forceinline__ uint32_t bytes_below32(int k) { return k >= 4 ? 0xFFF
 // A 16-byte chunk is assembled from the pieces of the rows that meet in it -- one unaligned 16-byte load + a byte mask
 // per piece -- and stored ONCE.  (The first version copied straddling chunks byte by byte: one chunk in ten for
 // 150-byte rows, but under warp divergence 2/3 of all issued instructions.)
-template <typename SrcFn>
+// kMap: the gathered bytes go through the reverse_complement / complement LUT (sequence_functions/module.cpp:30-121) on
+// their way out -- `SELECT reverse_complement(sequence) FROM read_fastq(...)` on a device-resident file is then ONE pass
+// over the sequence bytes instead of gather + map.  *bad = min over invalid bytes of (output position << 8 | byte).
+template <typename SrcFn, bool kMap>
 __global__ void __launch_bounds__(GS_THREADS, 8) gather_span_kernel(const uint8_t* __restrict__ buf, SrcFn srcfn, const int64_t* __restrict__ off,
-                                                                 int64_t n_rows, uint8_t* __restrict__ out) {
+                                                                 int64_t n_rows, uint8_t* __restrict__ out, int mode, unsigned long long* bad_out) {
     __shared__ int32_t s_rel[GS_ROWS + 1];
     __shared__ int64_t s_adj[GS_ROWS];
     __shared__ uint16_t s_seg[GS_SPAN / GS_SEG];  // row (batch-local) that holds relative position GS_SEG * j
+    __shared__ uint8_t s_lut[kMap ? 256 : 1];
     const int t = threadIdx.x;
+    unsigned long long bad = ~0ull;
+    if (kMap) {
+        s_lut[t] = 0;  // GS_THREADS == 256 entries
+        __syncthreads();
+        if (t == 0) {
+            if (mode == EXB_MAP_REVERSE_COMPLEMENT) {
+                s_lut['A'] = 'C'; s_lut['T'] = 'G'; s_lut['C'] = 'A'; s_lut['G'] = 'T';
+            } else {
+                s_lut['A'] = 'T'; s_lut['T'] = 'A'; s_lut['C'] = 'G'; s_lut['G'] = 'C';
+            }
+        }
+        __syncthreads();
+    }
+    auto map1 = [&](uint32_t c, int64_t pos) -> uint32_t {
+        const uint32_t m = s_lut[c];
+        if (m == 0) {
+            const unsigned long long w = ((unsigned long long)pos << 8) | c;
+            bad = w < bad ? w : bad;
+        }
+        return m;
+    };
+    auto map4 = [&](uint32_t x, int64_t pos) -> uint32_t {
+        return map1(x & 0xFF, pos) | (map1((x >> 8) & 0xFF, pos + 1) << 8) | (map1((x >> 16) & 0xFF, pos + 2) << 16) | (map1(x >> 24, pos + 3) << 24);
+    };
     const int64_t total = off[n_rows];
     // spans are aligned to 16 bytes of the OUTPUT ADDRESS so that chunk stores are aligned whatever `out` is
     const int mis = (int)((uintptr_t)out & 15);
@@ -498,11 +526,16 @@ __global__ void __launch_bounds__(GS_THREADS, 8) gather_span_kernel(const uint8_
                     }
                 }
                 if (whole) {
+                    if (kMap) {
+                        const int64_t p = span_lo + c0;
+                        acc.x = map4(acc.x, p), acc.y = map4(acc.y, p + 4), acc.z = map4(acc.z, p + 8), acc.w = map4(acc.w, p + 12);
+                    }
                     *reinterpret_cast<uint4*>(span_out + c0) = acc;
                 } else {  // ragged first / last chunk of the column or of a row batch
                     for (int q = q0; q < q1; q++) {
                         while (s_rel[a + 1] <= q) a++;
-                        span_out[q] = buf[s_adj[a] + q];
+                        const uint8_t b = buf[s_adj[a] + q];
+                        span_out[q] = kMap ? (uint8_t)map1(b, span_lo + q) : b;
                     }
                 }
             };
@@ -525,18 +558,24 @@ __global__ void __launch_bounds__(GS_THREADS, 8) gather_span_kernel(const uint8_
             row0 += cnt;  // the batch ended on its last row (lo = off[row0 + cnt]), or lo == hi and the loop ends
         }
     }
+    if (kMap && bad != ~0ull) atomicMin(bad_out, bad);
 }
 
 template <typename SrcFn>
 static cudaError_t gather_span_launch(const uint8_t* buf, SrcFn fn, const int64_t* off, int64_t n_rows, int64_t total_hint, uint8_t* out,
-                                      cudaStream_t st) {
+                                      cudaStream_t st, int mode = 0, unsigned long long* bad = nullptr) {
+    if (bad) {  // map requested (mode 0 is a valid map): the invalid-byte word starts at "none"
+        cudaError_t e = cudaMemsetAsync(bad, 0xFF, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+    }
     if (n_rows == 0) return cudaSuccess;
     // off[n_rows] is known only on the device; total_hint (an upper bound) merely keeps tiny columns from launching a full grid
     int64_t blocks = (total_hint + 15 + GS_SPAN - 1) / GS_SPAN + 1;
     const int64_t machine = 148 * 8;  // 8 resident blocks of 256 threads per SM
     if (blocks > machine) blocks = machine;
     if (blocks < 1) blocks = 1;
-    gather_span_kernel<SrcFn><<<(unsigned)blocks, GS_THREADS, 0, st>>>(buf, fn, off, n_rows, out);
+    if (bad) gather_span_kernel<SrcFn, true><<<(unsigned)blocks, GS_THREADS, 0, st>>>(buf, fn, off, n_rows, out, mode, bad);
+    else gather_span_kernel<SrcFn, false><<<(unsigned)blocks, GS_THREADS, 0, st>>>(buf, fn, off, n_rows, out, 0, nullptr);
     return cudaGetLastError();
 }
 
@@ -563,15 +602,16 @@ cudaError_t fastq_fields_launch(const uint8_t* buf, int64_t begin, int64_t n, co
 }
 template <typename OffT>
 static cudaError_t gather_launch_t(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, const int64_t* sel, int64_t n_rows,
-                                   int col, const uint32_t* lens, const int64_t* off, uint8_t* out, cudaStream_t st) {
-    if (n_rows == 0) return cudaSuccess;
+                                   int col, const uint32_t* lens, const int64_t* off, uint8_t* out, cudaStream_t st, int mode,
+                                   unsigned long long* bad) {
     SrcFastq<OffT> fn{FqLines<OffT>{buf, reinterpret_cast<const OffT*>(line_end), begin, n}, sel, lens, col};
-    return gather_span_launch(buf, fn, off, n_rows, n - begin, out, st);  // a column is never larger than the input
+    return gather_span_launch(buf, fn, off, n_rows, n - begin, out, st, mode, bad);  // a column is never larger than the input
 }
 cudaError_t fastq_gather_launch(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, bool wide, const int64_t* sel,
-                                int64_t n_rows, int col, const uint32_t* lens, const int64_t* off, uint8_t* out, cudaStream_t st) {
-    return wide ? gather_launch_t<uint64_t>(buf, begin, n, line_end, sel, n_rows, col, lens, off, out, st)
-                : gather_launch_t<uint32_t>(buf, begin, n, line_end, sel, n_rows, col, lens, off, out, st);
+                                int64_t n_rows, int col, const uint32_t* lens, const int64_t* off, uint8_t* out, cudaStream_t st, int mode,
+                                unsigned long long* bad) {
+    return wide ? gather_launch_t<uint64_t>(buf, begin, n, line_end, sel, n_rows, col, lens, off, out, st, mode, bad)
+                : gather_launch_t<uint32_t>(buf, begin, n, line_end, sel, n_rows, col, lens, off, out, st, mode, bad);
 }
 cudaError_t gather_ranges_launch(const uint8_t* buf, const int64_t* start, const uint32_t* len, const int64_t* off, int64_t n_rows,
                                  int64_t total_bound, uint8_t* out, cudaStream_t st) {

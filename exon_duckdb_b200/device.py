@@ -242,8 +242,10 @@ FASTQ_COLUMNS = ["name", "description", "sequence", "quality_scores"]
 FASTA_COLUMNS = ["id", "description", "sequence"]
 
 
-def fastq_table(buf, columns=None, preds=(), n=None):
-    """read_fastq on a device buffer: {column: Column}, projected to `columns`, filtered by `preds`."""
+def fastq_table(buf, columns=None, preds=(), n=None, seq_map=None):
+    """read_fastq on a device buffer: {column: Column}, projected to `columns`, filtered by `preds`.
+    seq_map = 'reverse_complement' | 'complement': the sequence column comes out already mapped (fused into the gather,
+    exb_fastq_gather_map); raises InvalidInput like the scalar function does."""
     columns = list(columns) if columns is not None else list(FASTQ_COLUMNS)
     dev = buf.device
     n = buf.numel() if n is None else int(n)
@@ -268,8 +270,17 @@ def fastq_table(buf, columns=None, preds=(), n=None):
         c = FASTQ_COLUMNS.index(name)
         off, total = offs[c], totals[c]
         data = _empty(total, torch.uint8, dev)
-        check(lib().exb_fastq_gather(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, c, _ptr(lens), _ptr(off),
-                                     _ptr(data), _stream()))
+        if name == "sequence" and seq_map is not None:
+            mode = {"reverse_complement": _lib.MAP_REVERSE_COMPLEMENT, "complement": _lib.MAP_COMPLEMENT}[seq_map]
+            bad = torch.empty(1, dtype=torch.int64, device=dev)
+            check(lib().exb_fastq_gather_map(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, c, _ptr(lens), _ptr(off),
+                                             mode, _ptr(data), _ptr(bad), _stream()))
+            b = int(bad.item())
+            if b != -1:
+                raise InvalidInput("Invalid character in sequence: %s" % chr(b & 0xFF))
+        else:
+            check(lib().exb_fastq_gather(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, c, _ptr(lens), _ptr(off),
+                                         _ptr(data), _stream()))
         out[name] = Column(off, data, valid if name == "description" else None)
     out["__n_rows__"] = n_rows
     return out

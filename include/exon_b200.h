@@ -333,6 +333,14 @@ EXB_API int exb_select_rows(const uint8_t *d_pass, int64_t n, int64_t *d_offsets
 EXB_API int exb_fastq_gather(const void *d_buf, int64_t begin, int64_t n, const void *d_line_end, int wide_offsets,
                              const int64_t *d_sel, int64_t n_rows, int col, const uint32_t *d_lens,
                              const int64_t *d_off, uint8_t *d_out, void *stream);
+/* The same gather with reverse_complement / complement (sequence_functions/module.cpp:30-121, the reference's LUTs)
+ * applied to the bytes on their way out: `SELECT reverse_complement(sequence) FROM read_fastq(...)` on a
+ * device-resident file is one pass over the sequence bytes instead of gather + exb_seq_map.  mode = EXB_MAP_*.
+ * *d_bad = ~0 if every byte was one of ACGT, else (position in d_out << 8) | offending byte, smallest position. */
+EXB_API int exb_fastq_gather_map(const void *d_buf, int64_t begin, int64_t n, const void *d_line_end, int wide_offsets,
+                                 const int64_t *d_sel, int64_t n_rows, int col, const uint32_t *d_lens,
+                                 const int64_t *d_off, int mode, uint8_t *d_out, uint64_t *d_bad, void *stream);
+
 
 /*
  * FASTA scan of d_buf[begin, n) (noodles-fasta read_definition / read_sequence

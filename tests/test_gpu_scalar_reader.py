@@ -51,6 +51,35 @@ def test_reverse_complement_and_complement(cuda_device):
             assert str(ei.value) == str(eo.value)  # "Invalid character in sequence: <c>" names the first bad byte
 
 
+@pytest.mark.parametrize("mode", ["reverse_complement", "complement"])
+def test_map_fused_into_the_gather(cuda_device, mode):
+    """read_fastq -> reverse_complement(sequence) as one pass (exb_fastq_gather_map) equals gather + scalar function,
+    rows of every length (pieces meeting inside 16-byte chunks, empty sequences), filtered or not, and names the first
+    invalid byte exactly like the reference's scalar function."""
+    from exon_duckdb_b200 import device as D
+    from oracle import oracle as O
+    rng = random.Random(31)
+    ref = O.reverse_complement if mode == "reverse_complement" else O.complement
+    recs = []
+    for i in range(3000):
+        L = rng.choice([0, 1, 3, 15, 16, 17, 31, 150, rng.randint(0, 700)])
+        seq = util.rand_seq(rng, L)
+        recs.append(b"@r%d d\n" % i + seq + b"\n+\n" + bytes(rng.randint(35, 73) for _ in range(L)) + b"\n")
+    text = b"".join(recs)
+    buf = D.to_device(text, cuda_device)
+    want = [ref(s) for s in O.parse_fastq(text).strings("sequence")]
+    assert D.fastq_table(buf, columns=["sequence"], seq_map=mode)["sequence"].to_pylist() == want
+    preds = [("mean_quality", ">", 20.0)]
+    quals = O.parse_fastq(text).strings("quality_scores")
+    keep = [w for w, q in zip(want, quals) if O.mean_quality_pass(q, ">", 20.0)]
+    assert 0 < len(keep) < len(want)
+    assert D.fastq_table(buf, columns=["sequence"], preds=preds, seq_map=mode)["sequence"].to_pylist() == keep
+    bad = text + b"@bad x\nACGNT\n+\nIIIII\n@bad2\nAQ\n+\nII\n"  # two invalid bytes: the first one is reported
+    with pytest.raises(D.InvalidInput) as ei:
+        D.fastq_table(D.to_device(bad, cuda_device), columns=["sequence"], seq_map=mode)
+    assert str(ei.value) == "Invalid character in sequence: N"
+
+
 def test_quality_score_string_to_list(cuda_device):
     from exon_duckdb_b200 import device as D
     from oracle import oracle as O
