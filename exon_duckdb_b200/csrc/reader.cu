@@ -12,6 +12,7 @@
 #include <ctype.h>
 #include <cuda_runtime.h>
 #include <dirent.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -80,6 +81,40 @@ static int compression_from_str(const std::string& s) {
     if (l == "xz") return 4;
     return 0;
 }
+
+// ------------------------------------------------------------------ zstd input
+// The streaming decoder of the system's libzstd (zstd >= 1.0 ABI), bound at run time: the image ships libzstd.so.1 but no
+// header, and the reference's own copy lives in crates that are not on disk.  The declarations below restate the
+// public, stable streaming API (zstd.h "Streaming decompression - HowTo").  Replaces async-compression's ZstdDecoder
+// behind datafusion's FileCompressionType::ZSTD (arrow_reader.rs:60-91).
+struct ZstdIn { const void* src; size_t size, pos; };
+struct ZstdOut { void* dst; size_t size, pos; };
+struct ZstdLib {
+    void* (*create)() = nullptr;
+    size_t (*destroy)(void*) = nullptr;
+    size_t (*init)(void*) = nullptr;
+    size_t (*decompress)(void*, ZstdOut*, ZstdIn*) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    const char* (*error_name)(size_t) = nullptr;
+    bool ok = false;
+    static const ZstdLib& get() {
+        static ZstdLib L = [] {
+            ZstdLib l;
+            void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+            if (!h) h = dlopen("libzstd.so", RTLD_NOW | RTLD_LOCAL);
+            if (!h) return l;
+            l.create = reinterpret_cast<void* (*)()>(dlsym(h, "ZSTD_createDStream"));
+            l.destroy = reinterpret_cast<size_t (*)(void*)>(dlsym(h, "ZSTD_freeDStream"));
+            l.init = reinterpret_cast<size_t (*)(void*)>(dlsym(h, "ZSTD_initDStream"));
+            l.decompress = reinterpret_cast<size_t (*)(void*, ZstdOut*, ZstdIn*)>(dlsym(h, "ZSTD_decompressStream"));
+            l.is_error = reinterpret_cast<unsigned (*)(size_t)>(dlsym(h, "ZSTD_isError"));
+            l.error_name = reinterpret_cast<const char* (*)(size_t)>(dlsym(h, "ZSTD_getErrorName"));
+            l.ok = l.create && l.destroy && l.init && l.decompress && l.is_error && l.error_name;
+            return l;
+        }();
+        return L;
+    }
+};
 
 // ------------------------------------------------------------------ filter expressions
 namespace {
@@ -550,6 +585,10 @@ struct Reader {
             const int comp = file_comp[fi];
             int fd = -1;
             gzFile gz = nullptr;
+            FILE* zf = nullptr;  // zstd: compressed file, decoder, its input window
+            void* zds = nullptr;
+            std::vector<uint8_t> zbuf;
+            ZstdIn zin{nullptr, 0, 0};
             std::string err;
             if (comp == 1) {
                 gz = gzopen(path.c_str(), "rb");
@@ -558,8 +597,15 @@ struct Reader {
             } else if (comp == 0) {
                 fd = open(path.c_str(), O_RDONLY);
                 if (fd < 0) err = "could not open " + path;
+            } else if (comp == 2) {
+                const ZstdLib& Z = ZstdLib::get();
+                if (!Z.ok) err = "zstd input needs the system's libzstd.so.1, which could not be loaded";
+                else if (!(zf = fopen(path.c_str(), "rb"))) err = "could not open " + path;
+                else if (!(zds = Z.create()) || Z.is_error(Z.init(zds))) err = "could not create a zstd decoder";
+                zbuf.resize(1 << 20);
+                zin = ZstdIn{zbuf.data(), 0, 0};
             } else {
-                err = "compression of " + path + " is not supported by this build (gzip and uncompressed are)";
+                err = "compression of " + path + " is not supported by this build (gzip, zstd and uncompressed are)";
             }
             int64_t pos = 0;
             bool eof = false;
@@ -588,6 +634,28 @@ struct Reader {
                         if (g == 0) break;
                         got += g;
                     }
+                } else if (zds) {
+                    const ZstdLib& Z = ZstdLib::get();
+                    bool in_frame = false;  // the decoder still holds state of an unfinished frame
+                    while (got < want) {
+                        if (zin.pos == zin.size) {
+                            const size_t n = fread(zbuf.data(), 1, zbuf.size(), zf);
+                            if (n == 0) {
+                                if (ferror(zf)) err = "read error in " + path;
+                                else if (in_frame) err = "truncated zstd frame in " + path;
+                                break;  // end of the compressed file
+                            }
+                            zin = ZstdIn{zbuf.data(), n, 0};
+                        }
+                        ZstdOut zout{dst + got, (size_t)(want - got), 0};
+                        const size_t r = Z.decompress(zds, &zout, &zin);  // 0 = a frame ended; concatenated frames just continue
+                        if (Z.is_error(r)) {
+                            err = std::string("zstd: ") + Z.error_name(r) + " in " + path;
+                            break;
+                        }
+                        in_frame = r != 0;
+                        got += (int64_t)zout.pos;
+                    }
                 } else {
                     bool bad = false;
                     pread_slices(fd, dst, pos, want, &got, &bad);
@@ -614,6 +682,8 @@ struct Reader {
             }
             if (fd >= 0) close(fd);
             if (gz) gzclose(gz);
+            if (zds) ZstdLib::get().destroy(zds);
+            if (zf) fclose(zf);
             if (!err.empty()) {
                 Block b;
                 b.error = err;
@@ -1236,8 +1306,8 @@ static Reader* open_reader(const char* uri, uintptr_t batch_size, const char* co
         r->file_comp.push_back(comp);
     }
     for (int c : r->file_comp)
-        if (c >= 2) {
-            *err = "could not register table: zstd / bzip2 / xz input is not supported by this build";
+        if (c > 2) {
+            *err = "could not register table: bzip2 / xz input is not supported by this build";
             return nullptr;
         }
 

@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""The drop-in path end to end: SQL through DuckDB v0.8.1 with `LOAD exon`, file on tmpfs -> query result.
+
+Two extensions run the same statements (tests/test_duckdb_ext.py explains them):
+  PRODUCT  exon_duckdb_b200/duckdb_ext/exon.duckdb_extension  our host code over exb_reader_* (projection / filter /
+           complex-filter push-down, COUNT(*) on the device, CUDA scalar functions)
+  REFGLUE  oracle/_ref/exon.duckdb_extension                   the reference's UNMODIFIED C++ glue and CPU scalar
+           functions over libexon_b200.so's new_reader (Arrow stream): what a user of the reference gets by
+           swapping only the reader library
+usage (GPU box): python scripts/bench_duckdb.py [--reads N] [--out gpurun_out/duckdb.json]
+Times are DuckDB's own wall clock per statement (tools/sqlrun.cpp), second run of each statement (warm pinned pool).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SQLRUN = os.path.join(ROOT, "build", "rt", "sqlrun")
+PRODUCT = os.path.join(ROOT, "exon_duckdb_b200", "duckdb_ext", "exon.duckdb_extension")
+REFGLUE = os.path.join(ROOT, "oracle", "_ref", "exon.duckdb_extension")
+
+
+def run(ext, statements, threads=None):
+    text = "LOAD '%s';\n" % ext + "\n".join(s + ";" for s in statements) + "\n"
+    cmd = [SQLRUN] + (["-threads", str(threads)] if threads else [])
+    out = subprocess.run(cmd, input=text.encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200)
+    if out.returncode != 0:
+        raise RuntimeError(out.stderr.decode()[-2000:])
+    return [json.loads(l) for l in out.stdout.decode().splitlines()][1:]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=4_000_000)
+    ap.add_argument("--ref-reads", type=int, default=400_000, help="smaller file for the queries that run the reference's CPU scalar functions")
+    ap.add_argument("--dir", default="/dev/shm")
+    ap.add_argument("--out", default="gpurun_out/duckdb.json")
+    args = ap.parse_args()
+    for p in (SQLRUN, PRODUCT, REFGLUE):
+        if not os.path.exists(p):
+            raise SystemExit("%s is missing (bash oracle/build_ref.sh; make -C exon_duckdb_b200/duckdb_ext)" % p)
+    from exon_duckdb_b200 import _lib, device as D
+
+    big = os.path.join(args.dir, "exb_duck_big.fastq")
+    small = os.path.join(args.dir, "exb_duck_small.fastq")
+    D.gen_host(_lib.gen_params("illumina", args.reads, seed=20)).tofile(big)
+    D.gen_host(_lib.gen_params("illumina", args.ref_reads, seed=20)).tofile(small)
+    mq = "list_avg(quality_score_string_to_list(quality_scores)) > 30"
+    queries = [
+        ("COUNT(*)", "SELECT COUNT(*) FROM read_fastq('%s')"),
+        ("COUNT(*) WHERE mean quality > 30", "SELECT COUNT(*) FROM read_fastq('%s') WHERE " + mq),
+        ("SUM(length(sequence))", "SELECT SUM(length(sequence)) FROM read_fastq('%s')"),
+        ("COUNT(*) WHERE name = one record", "SELECT COUNT(*) FROM read_fastq('%s') WHERE name = 'SIM:1:FC1:1:1:1000:1000'"),
+        ("AVG(gc_content(sequence))", "SELECT AVG(gc_content(sequence)) FROM read_fastq('%s')"),
+        ("SUM(length(reverse_complement(sequence)))", "SELECT SUM(length(reverse_complement(sequence))) FROM read_fastq('%s')"),
+    ]
+    rows = []
+    for label, ext in (("PRODUCT", PRODUCT), ("REFGLUE", REFGLUE)):
+        for name, q in queries:
+            # the reference's CPU scalar functions run at 0.01-0.2 GB/s per core: give them the small file
+            heavy = label == "REFGLUE" and ("quality" in q or "gc_content" in q or "reverse_complement" in q)
+            path = small if heavy else big
+            size = os.path.getsize(path)
+            try:
+                res = run(ext, [q % path, q % path])
+            except Exception as e:
+                print("%-8s %-44s FAILED %s" % (label, name, str(e)[:200]), flush=True)
+                continue
+            r = res[-1]
+            if not r.get("ok"):
+                print("%-8s %-44s ERROR %s" % (label, name, r.get("error", "")[:200]), flush=True)
+                continue
+            ms = r["ms"]
+            gbs = size / (ms * 1e-3) / 1e9
+            rows.append({"extension": label, "query": name, "file_bytes": size, "ms": ms, "GB/s": gbs, "result": r["rows"][0][0]})
+            print("%-8s %-44s %9.1f ms  %7.2f GB/s  (%.2f GB file)  -> %s" % (label, name, ms, gbs, size / 1e9, r["rows"][0][0]), flush=True)
+    os.unlink(big)
+    os.unlink(small)
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump({"rows": rows}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

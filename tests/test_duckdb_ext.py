@@ -7,7 +7,7 @@ Two extensions are driven through build/rt/sqlrun (a DuckDB v0.8.1 host, tools/s
            the drop-in proof.  Its scalar functions are the reference's own CPU code (the live oracle).
 The queries and expectations replay the reference's sqllogictests
 (test/sql/exondb-release-with-deb-info/test_fastq_scan.test, test_fasta_scan.test, test_scalar_functions.test);
-zstd cases are out of scope this round.
+zstd cases included (the system's libzstd.so.1 is bound at run time).
 
 The binaries are built in the development container (they need the reference's vendored DuckDB headers) and travel
 to the GPU box with the snapshot; the tests skip when they are absent.
@@ -108,19 +108,24 @@ def test_no_gpu_is_a_loud_error():
 
 
 # ------------------------------------------------------------------ GPU: the reference's sqllogictests replayed
-FASTQ_SCAN = [  # test_fastq_scan.test (zstd cases omitted)
+FASTQ_SCAN = [  # test_fastq_scan.test
     ("SELECT count(*) FROM read_fastq('{G}/test.fastq')", [["2"]]),
     ("SELECT count(*) FROM read_fastq('{G}/test.fastq.gz')", [["2"]]),
     ("SELECT count(*) FROM read_fastq('{G}/test.fastq.gzip', compression='gzip')", [["2"]]),
+    ("SELECT count(*) FROM read_fastq('{G}/test.fastq.zst')", [["2"]]),                          # :22-26
+    ("SELECT count(*) FROM read_fastq('{G}/test.fastq.zstd', compression='zstd')", [["2"]]),     # :28-32
+    ("SELECT count(*) FROM '{G}/test.fastq.zst'", [["2"]]),                                      # :55-59
     ("SELECT * FROM read_fastq('{G}/test.fastq') LIMIT 1", [["SEQ_ID", "This is a description", SEQ60, QUAL60]]),
     ("SELECT count(*) FROM '{G}/test.fastq'", [["2"]]),
     ("SELECT count(*) FROM '{G}/test.fastq.gz'", [["2"]]),
     ("SELECT COUNT(*) FROM read_fastq('{G}/fastq/') LIMIT 1", [["4"]]),
 ]
-FASTA_SCAN = [  # test_fasta_scan.test (zstd cases omitted)
+FASTA_SCAN = [  # test_fasta_scan.test
     ("SELECT count(*) FROM read_fasta('{G}/test.fasta')", [["2"]]),
     ("SELECT count(*) FROM read_fasta('{G}/test.fasta.gzip', compression='gzip')", [["2"]]),
     ("SELECT count(*) FROM read_fasta('{G}/test.fasta.gz')", [["2"]]),
+    ("SELECT count(*) FROM read_fasta('{G}/test.fasta.zstd', compression='zstd')", [["2"]]),     # :22-26
+    ("SELECT count(*) FROM read_fasta('{G}/test.fasta.zst')", [["2"]]),                          # :45-49
     ("SELECT count(*) FROM '{G}/test.fasta'", [["2"]]),
     ("SELECT count(*) FROM '{G}/test.fasta' WHERE id = 'a'", [["1"]]),
     ("SELECT count(*) FROM '{G}/test.fasta.gz'", [["2"]]),

@@ -144,6 +144,36 @@ def test_reader_gzip(cuda_device, tmp_path):
     assert _read(str(q), "fastq", compression=b"gzip").num_rows == 500          # explicit option
 
 
+def test_reader_zstd(cuda_device, tmp_path, golden_dir, monkeypatch):
+    """zstd input (test_fastq_scan.test:22-32): the reference's own .zst fixtures, a multi-block file
+    written by another zstd implementation, concatenated frames, and a truncated file."""
+    import pyarrow as pa
+    from oracle import oracle as O
+    assert _read(os.path.join(golden_dir, "test.fastq.zst"), "fastq").num_rows == 2
+    assert _read(os.path.join(golden_dir, "test.fasta.zstd"), "fasta", compression=b"zstd").num_rows == 2
+    text, _ = util.random_fastq(8, 4000, tricky=False)
+    p = tmp_path / "x.fastq.zst"
+    with pa.CompressedOutputStream(str(p), "zstd") as f:
+        f.write(text)
+    monkeypatch.setenv("EXON_B200_CHUNK_BYTES", "100000")  # several blocks, records straddling their edges
+    assert _rows(_read(str(p), "fastq")) == O.parse_fastq(text).rows()
+    half = len(text) // 2
+    cut = text.rfind(b"\n@", 0, half) + 1
+    q = tmp_path / "two_frames.fastq.zst"
+    with open(q, "wb") as out:  # two frames back to back decode as one stream
+        for part in (text[:cut], text[cut:]):
+            sink = pa.BufferOutputStream()
+            with pa.CompressedOutputStream(sink, "zstd") as f:
+                f.write(part)
+            out.write(sink.getvalue().to_pybytes())
+    assert _rows(_read(str(q), "fastq")) == O.parse_fastq(text).rows()
+    t = tmp_path / "trunc.fastq.zst"
+    t.write_bytes(p.read_bytes()[: p.stat().st_size // 2])
+    with pytest.raises(Exception) as ei:
+        _read(str(t), "fastq")
+    assert "zstd" in str(ei.value)
+
+
 @pytest.mark.parametrize("chunk", [None, 4096, 70000])
 def test_reader_chunk_carry_fastq(cuda_device, tmp_path, monkeypatch, chunk):
     """Records straddling chunk edges are re-read with the next chunk; tiny chunks force that on every record."""

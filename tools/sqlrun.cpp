@@ -12,6 +12,7 @@
 //
 // usage: sqlrun [-threads N] < script.sql
 #include <iostream>
+#include <chrono>
 #include <sstream>
 #include <string>
 
@@ -66,6 +67,7 @@ int main(int argc, char **argv) {
 		for (char c : sql)
 			if (!isspace((unsigned char)c)) blank = false;
 		if (blank) return;
+		const auto t0 = std::chrono::steady_clock::now();
 		auto res = con.Query(sql);
 		if (res->HasError()) {
 			std::cout << "{\"ok\": false, \"error\": " << json_escape(res->GetError()) << "}" << std::endl;
@@ -90,7 +92,8 @@ int main(int argc, char **argv) {
 				std::cout << "]";
 			}
 		}
-		std::cout << "]}" << std::endl;
+		const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		std::cout << "], \"ms\": " << ms << "}" << std::endl;
 	};
 	while (i < text.size()) {
 		if (!in_str && (stmt.empty() || stmt.back() == '\n')) {
