@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("EXON_B200_LIB") or os.path.join(_HERE, "libexon_b200.
 F_LINES, F_SEQ, F_QUAL = 1, 2, 4
 P_MEAN_QUALITY, P_GC_CONTENT, P_SEQ_LEN, P_QUAL_LEN = 0, 1, 2, 3
 OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "=": 4, "==": 4, "!=": 5, "<>": 5}
-MAP_REVERSE_COMPLEMENT, MAP_COMPLEMENT = 0, 1
+MAP_REVERSE_COMPLEMENT, MAP_COMPLEMENT, MAP_TRANSCRIBE, MAP_REVERSE_TRANSCRIBE = 0, 1, 2, 3
 GEN_FASTA, GEN_ILLUMINA, GEN_ONT = 1, 2, 4
 ERR_CUDA, ERR_ARG, ERR_FORMAT, ERR_CAPACITY, ERR_IO, ERR_INVALID_CHAR = -1, -2, -3, -4, -5, -6
 NO_POS = 0xFFFFFFFFFFFFFFFF
@@ -117,9 +117,11 @@ SIGNATURES = {
     "exb_gc_from_counts": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_gc_content": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_seq_map": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "exb_translate": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "exb_quality_decode": (_i32, [_vp, _i64, _vp, _vp]),
     "exb_gc_content_host": (_i32, [_vp, _vp, _i64, _vp]),
     "exb_seq_map_host": (_i32, [_vp, _i64, _i32, _vp, C.POINTER(_i64)]),
+    "exb_translate_host": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_quality_decode_host": (_i32, [_vp, _i64, _vp]),
     "exb_gen_size": (_i64, [C.POINTER(GenParams)]),
     "exb_gen_device": (_i32, [C.POINTER(GenParams), _vp, _i64, _vp]),

@@ -31,6 +31,7 @@ cudaError_t gc_from_prefix_launch(const int64_t*, const int64_t*, int64_t, float
 cudaError_t gc_from_counts_launch(const uint32_t*, const uint32_t*, int64_t, float*, cudaStream_t);
 cudaError_t gc_content_launch(const int64_t*, const uint8_t*, int64_t, float*, cudaStream_t);
 cudaError_t seq_map_launch(const uint8_t*, int64_t, int, uint8_t*, unsigned long long*, cudaStream_t);
+cudaError_t translate_launch(const int64_t*, const uint8_t*, int64_t, int64_t, uint8_t*, long long*, cudaStream_t);
 cudaError_t quality_decode_launch(const uint8_t*, int64_t, int32_t*, cudaStream_t);
 
 static thread_local char g_err[512] = "";
@@ -432,8 +433,8 @@ int exb_fastq_gather_map(const void* d_buf, int64_t begin, int64_t n, const void
                          int64_t n_rows, int col, const uint32_t* d_lens, const int64_t* d_off, int mode, uint8_t* d_out, uint64_t* d_bad,
                          void* stream) {
     if (col < 2 || col > 3) return set_err(EXB_ERR_ARG, "exb_fastq_gather_map: col must be 2 (sequence) or 3 (quality_scores)");
-    if ((mode != EXB_MAP_REVERSE_COMPLEMENT && mode != EXB_MAP_COMPLEMENT) || !d_bad)
-        return set_err(EXB_ERR_ARG, "exb_fastq_gather_map: mode must be EXB_MAP_REVERSE_COMPLEMENT or EXB_MAP_COMPLEMENT, d_bad non-null");
+    if (mode < EXB_MAP_REVERSE_COMPLEMENT || mode > EXB_MAP_REVERSE_TRANSCRIBE || !d_bad)
+        return set_err(EXB_ERR_ARG, "exb_fastq_gather_map: mode must be one of EXB_MAP_*, d_bad non-null");
     cudaError_t e = fastq_gather_launch(reinterpret_cast<const uint8_t*>(d_buf), begin, n, d_line_end, wide_offsets != 0, d_sel, n_rows,
                                         col, d_lens, d_off, d_out, (cudaStream_t)stream, mode, reinterpret_cast<unsigned long long*>(d_bad));
     if (e != cudaSuccess) return cuda_fail(e, "fastq_gather_map launch");
@@ -516,11 +517,23 @@ int exb_gc_content(const int64_t* d_off, const uint8_t* d_data, int64_t n_rows, 
     return 0;
 }
 int exb_seq_map(const uint8_t* d_in, int64_t n_bytes, int mode, uint8_t* d_out, uint64_t* d_bad_pos, void* stream) {
-    if (mode != EXB_MAP_REVERSE_COMPLEMENT && mode != EXB_MAP_COMPLEMENT) return set_err(EXB_ERR_ARG, "exb_seq_map: bad mode");
+    if (mode < EXB_MAP_REVERSE_COMPLEMENT || mode > EXB_MAP_REVERSE_TRANSCRIBE) return set_err(EXB_ERR_ARG, "exb_seq_map: bad mode");
     cudaError_t e = seq_map_launch(d_in, n_bytes, mode, d_out, reinterpret_cast<unsigned long long*>(d_bad_pos), (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "seq_map launch");
     return 0;
 }
+static int exb_translate_bound(const int64_t* d_off, const uint8_t* d_data, int64_t n_rows, int64_t n_bytes_bound, uint8_t* d_out, int64_t* d_status,
+                        void* stream) {
+    if (n_rows < 0 || !d_status || (n_rows > 0 && (!d_off || !d_out))) return set_err(EXB_ERR_ARG, "exb_translate: bad arguments");
+    cudaError_t e = translate_launch(d_off, d_data, n_rows, n_bytes_bound, d_out, reinterpret_cast<long long*>(d_status), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "translate launch");
+    return 0;
+}
+int exb_translate(const int64_t* d_off, const uint8_t* d_data, int64_t n_rows, uint8_t* d_out, int64_t* d_status, void* stream) {
+    // the column's size is on the device: size the grid for the machine (the kernel is grid-strided)
+    return exb_translate_bound(d_off, d_data, n_rows, (int64_t)148 * 16 * 256 * 3, d_out, d_status, stream);
+}
+
 int exb_quality_decode(const uint8_t* d_in, int64_t n_bytes, int32_t* d_out, void* stream) {
     cudaError_t e = quality_decode_launch(d_in, n_bytes, d_out, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "quality_decode launch");

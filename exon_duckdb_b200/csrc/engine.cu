@@ -330,6 +330,30 @@ int exb_seq_map_host(const uint8_t* data, int64_t n_bytes, int mode, uint8_t* ou
     return 0;
 }
 
+int exb_translate_host(const int64_t* offsets, const uint8_t* data, int64_t n_rows, uint8_t* out, int64_t* status) {
+    if (n_rows < 0 || !status || (n_rows > 0 && (!offsets || !out))) return set_err(EXB_ERR_ARG, "exb_translate_host: bad arguments");
+    status[0] = status[1] = -1;
+    if (n_rows == 0) return 0;
+    const int64_t nb = offsets[n_rows] - offsets[0];
+    HostCtx& c = g_host;
+    int rc = c.init();
+    if (rc) return rc;
+    if ((rc = c.grow(&c.d_in, &c.in_cap, nb + 64, "cudaMalloc(in)")) || (rc = c.grow(&c.d_off, &c.off_cap, (n_rows + 1) * 8 + 16, "cudaMalloc(off)")) ||
+        (rc = c.grow(&c.d_out, &c.out_cap, nb / 3 + 64, "cudaMalloc(out)")))
+        return rc;
+    cudaError_t e = cudaMemcpyAsync(c.d_off, offsets, (size_t)(n_rows + 1) * 8, cudaMemcpyHostToDevice, c.st);
+    if (e == cudaSuccess && nb > 0) e = cudaMemcpyAsync(c.d_in, data + offsets[0], (size_t)nb, cudaMemcpyHostToDevice, c.st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(H2D)");
+    // the offsets keep their base: hand the kernel a data pointer shifted by -offsets[0]
+    rc = exb_translate((const int64_t*)c.d_off, (const uint8_t*)c.d_in - offsets[0], n_rows, (uint8_t*)c.d_out, (int64_t*)c.d_flag, c.st);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(status, c.d_flag, 16, cudaMemcpyDeviceToHost, c.st);
+    if (e == cudaSuccess && nb >= 3) e = cudaMemcpyAsync(out, c.d_out, (size_t)(nb / 3), cudaMemcpyDeviceToHost, c.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);
+    if (e != cudaSuccess) return cuda_fail(e, "translate D2H");
+    return 0;
+}
+
 int exb_quality_decode_host(const uint8_t* data, int64_t n_bytes, int32_t* out) {
     if (n_bytes < 0 || (n_bytes > 0 && (!data || !out))) return set_err(EXB_ERR_ARG, "exb_quality_decode_host: bad arguments");
     if (n_bytes == 0) return 0;

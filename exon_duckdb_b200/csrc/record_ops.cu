@@ -398,6 +398,7 @@ __device__ __forceinline__ uint32_t bytes_below32(int k) { return k >= 4 ? 0xFFF
 // A 16-byte chunk is assembled from the pieces of the rows that meet in it -- one unaligned 16-byte load + a byte mask
 // per piece -- and stored ONCE.  (The first version copied straddling chunks byte by byte: one chunk in ten for
 // 150-byte rows, but under warp divergence 2/3 of all issued instructions.)
+__device__ __forceinline__ void fill_map_lut_fwd(uint8_t* lut, int mode);
 // kMap: the gathered bytes go through the reverse_complement / complement LUT (sequence_functions/module.cpp:30-121) on
 // their way out -- `SELECT reverse_complement(sequence) FROM read_fastq(...)` on a device-resident file is then ONE pass
 // over the sequence bytes instead of gather + map.  *bad = min over invalid bytes of (output position << 8 | byte).
@@ -413,13 +414,7 @@ __global__ void __launch_bounds__(GS_THREADS, 8) gather_span_kernel(const uint8_
     if (kMap) {
         s_lut[t] = 0;  // GS_THREADS == 256 entries
         __syncthreads();
-        if (t == 0) {
-            if (mode == EXB_MAP_REVERSE_COMPLEMENT) {
-                s_lut['A'] = 'C'; s_lut['T'] = 'G'; s_lut['C'] = 'A'; s_lut['G'] = 'T';
-            } else {
-                s_lut['A'] = 'T'; s_lut['T'] = 'A'; s_lut['C'] = 'G'; s_lut['G'] = 'C';
-            }
-        }
+        if (t == 0) fill_map_lut_fwd(s_lut, mode);
         __syncthreads();
     }
     auto map1 = [&](uint32_t c, int64_t pos) -> uint32_t {
@@ -768,18 +763,26 @@ cudaError_t gc_content_launch(const int64_t* off, const uint8_t* data, int64_t n
 
 // ================================================================= LUT map / Phred decode
 // 256-entry table in shared memory; entry 0 = invalid.  16 bytes per thread per step.
+// the reference's per-byte tables (0 = throws): reverse_complement (module.cpp:30-69), complement (:81-121),
+// transcribe (:212-249), reverse_transcribe (:168-203)
+__device__ __forceinline__ void fill_map_lut(uint8_t* lut, int mode) {
+    if (mode == EXB_MAP_REVERSE_COMPLEMENT) {
+        lut['A'] = 'C'; lut['T'] = 'G'; lut['C'] = 'A'; lut['G'] = 'T';
+    } else if (mode == EXB_MAP_COMPLEMENT) {
+        lut['A'] = 'T'; lut['T'] = 'A'; lut['C'] = 'G'; lut['G'] = 'C';
+    } else if (mode == EXB_MAP_TRANSCRIBE) {
+        lut['A'] = 'A'; lut['C'] = 'C'; lut['G'] = 'G'; lut['T'] = 'U';
+    } else {
+        lut['A'] = 'A'; lut['C'] = 'C'; lut['G'] = 'G'; lut['U'] = 'T';
+    }
+}
+
 __global__ void __launch_bounds__(256) seq_map_kernel(const uint8_t* __restrict__ in, int64_t n, int mode, uint8_t* __restrict__ out,
                                                       unsigned long long* bad_pos) {
     __shared__ uint8_t lut[256];
     lut[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (mode == EXB_MAP_REVERSE_COMPLEMENT) {
-            lut['A'] = 'C'; lut['T'] = 'G'; lut['C'] = 'A'; lut['G'] = 'T';
-        } else {
-            lut['A'] = 'T'; lut['T'] = 'A'; lut['C'] = 'G'; lut['G'] = 'C';
-        }
-    }
+    if (threadIdx.x == 0) fill_map_lut(lut, mode);
     __syncthreads();
     const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
     const int64_t nvec = aligned ? (n >> 4) : 0;
@@ -818,6 +821,62 @@ cudaError_t seq_map_launch(const uint8_t* in, int64_t n, int mode, uint8_t* out,
     if (b > 148 * 16) b = 148 * 16;
     if (b < 1) b = 1;
     seq_map_kernel<<<(int)b, 256, 0, st>>>(in, n, mode, out, bad_pos);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ void fill_map_lut_fwd(uint8_t* lut, int mode) { fill_map_lut(lut, mode); }
+
+// ================================================================= translate_dna_to_aa (module.cpp:260-360)
+// Rows whose length is a multiple of 3 tile the byte column in whole codons, so as long as every earlier row is well
+// formed "protein of the concatenation" = "concatenation of the proteins": one thread per amino acid, three bytes in,
+// one byte out through a 64-entry table indexed 16 a + 4 b + c (A C G T = 0 1 2 3).  Errors follow the reference's
+// order (rows in order, a row's length before its codons): kernel 1 finds the first row with a bad length, kernel 2
+// only looks at codons that lie before that row.
+constexpr long long TR_NONE = 0x7F7F7F7F7F7F7F7Fll;  // what cudaMemsetAsync(0x7F) leaves: larger than any row or offset
+__global__ void __launch_bounds__(256) translate_check_kernel(const int64_t* __restrict__ off, int64_t n_rows, long long* __restrict__ status) {
+    long long bad = TR_NONE;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x)
+        if ((off[r + 1] - off[r]) % 3 != 0 && r < bad) bad = r;
+    if (bad != TR_NONE) atomicMin(&status[0], bad);
+}
+__device__ __forceinline__ int base_code(uint32_t c) { return c == 'A' ? 0 : (c == 'C' ? 1 : (c == 'G' ? 2 : (c == 'T' ? 3 : -1))); }
+__global__ void __launch_bounds__(256) translate_kernel(const int64_t* __restrict__ off, const uint8_t* __restrict__ data, int64_t n_rows,
+                                                        uint8_t* __restrict__ out, long long* __restrict__ status) {
+    __shared__ uint8_t table[64];
+    if (threadIdx.x < 64) table[threadIdx.x] = (uint8_t)"KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF"[threadIdx.x];
+    __syncthreads();
+    const int64_t base = off[0];
+    const long long bad_row = status[0];  // written by the kernel before this one on the same stream
+    const int64_t end = bad_row == TR_NONE ? off[n_rows] : off[bad_row];
+    const int64_t n_aa = (end - base) / 3;
+    long long bad = TR_NONE;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_aa; j += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t* p = data + base + 3 * j;
+        const int a = base_code(p[0]), b = base_code(p[1]), c = base_code(p[2]);
+        if ((a | b | c) < 0) {
+            const long long pos = base + 3 * j;
+            bad = pos < bad ? pos : bad;
+            out[j] = 0;
+        } else {
+            out[j] = table[16 * a + 4 * b + c];
+        }
+    }
+    if (bad != TR_NONE) atomicMin(&status[1], bad);
+}
+__global__ void translate_finish_kernel(long long* status) {
+    if (threadIdx.x < 2 && status[threadIdx.x] == TR_NONE) status[threadIdx.x] = -1;
+}
+cudaError_t translate_launch(const int64_t* off, const uint8_t* data, int64_t n_rows, int64_t n_bytes_bound, uint8_t* out, long long* status,
+                             cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(status, 0x7F, 16, st);  // both words = TR_NONE
+    if (e != cudaSuccess) return e;
+    if (n_rows > 0) {
+        translate_check_kernel<<<row_blocks(n_rows, 256), 256, 0, st>>>(off, n_rows, status);
+        const int64_t n_aa = n_bytes_bound / 3 + 1;
+        const int64_t b = (n_aa + 255) / 256;
+        translate_kernel<<<(unsigned)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16), 256, 0, st>>>(off, data, n_rows, out, status);
+    }
+    translate_finish_kernel<<<1, 32, 0, st>>>(status);
     return cudaGetLastError();
 }
 

@@ -411,6 +411,35 @@ def complement(col):
     return _seq_map(col, _lib.MAP_COMPLEMENT)
 
 
+def transcribe(col):
+    """transcribe(VARCHAR) (module.cpp:212-249): T -> U, A C G unchanged, anything else raises."""
+    return _seq_map(col, _lib.MAP_TRANSCRIBE)
+
+
+def reverse_transcribe(col):
+    """reverse_transcribe(VARCHAR) (module.cpp:168-203): U -> T, A C G unchanged, anything else raises."""
+    return _seq_map(col, _lib.MAP_REVERSE_TRANSCRIBE)
+
+
+def translate_dna_to_aa(col):
+    """translate_dna_to_aa(VARCHAR) (module.cpp:260-360) over a device Column; raises InvalidInput with the reference's
+    message for the first offending row (length not a multiple of 3, or a codon outside the standard table)."""
+    dev = col.offsets.device
+    n = len(col)
+    out = alloc_input(col.data.numel() // 3 + 1, dev)
+    status = torch.empty(2, dtype=torch.int64, device=dev)
+    check(lib().exb_translate(_ptr(col.offsets), _ptr(col.data), n, _ptr(out), _ptr(status), _stream()))
+    bad_row, bad_pos = status.cpu().tolist()
+    if bad_pos >= 0:
+        raise InvalidInput("Invalid codon: %s" % bytes(col.data[bad_pos:bad_pos + 3].cpu().tolist()).decode("latin-1"))
+    if bad_row >= 0:
+        ln = int((col.offsets[bad_row + 1] - col.offsets[bad_row]).item())
+        raise InvalidInput("Invalid sequence length: %d" % ln)
+    base = col.offsets[0]
+    off = torch.div(col.offsets - base, 3, rounding_mode="floor")
+    return Column(off, out[:int(off[-1].item())] if n else out[:0], col.valid)
+
+
 def quality_score_string_to_list(col):
     """LIST(INTEGER) child vector: int32 tensor of byte - 33; list offsets are col.offsets (fastq_functions/module.cpp:32-50)."""
     nb = col.data.numel()

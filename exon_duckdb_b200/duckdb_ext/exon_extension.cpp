@@ -5,7 +5,8 @@
 //   read_fasta(VARCHAR, compression := VARCHAR)    <- arrow_table_function/module.cpp:296-318 (Register)
 //   read_fastq(VARCHAR, compression := VARCHAR)       schema as FileTypeBind produces it (:75-156)
 //   FROM 'x.fasta[.gz]' / 'x.fastq[.gz]'           <- ReplacementScan (:320-382)
-//   gc_content, reverse_complement, complement     <- sequence_functions/module.cpp:30-166
+//   gc_content, reverse_complement, complement,
+//   transcribe, reverse_transcribe, translate_dna_to_aa  <- sequence_functions/module.cpp:30-370
 //   quality_score_string_to_list                   <- fastq_functions/module.cpp:28-54
 // It is not the reference's glue: there is no Arrow stream between the engine and DuckDB.  bind / init_global /
 // scan call the C ABI of libexon_b200.so (include/exon_b200.h, exb_reader_*) and fill the DataChunk directly:
@@ -532,6 +533,39 @@ static void SeqMapFunction(DataChunk &args, ExpressionState &state, Vector &resu
 	FinishResult(result, args, count);
 }
 
+// translate_dna_to_aa(VARCHAR) -> VARCHAR (module.cpp:260-360): standard codon table; "Invalid sequence length: <n>" /
+// "Invalid codon: <xyz>" for the first offending row, the length checked before the codons as the reference does
+static void TranslateFunction(DataChunk &args, ExpressionState &state, Vector &result) {
+	const idx_t count = args.size();
+	Packed p;
+	UnifiedVectorFormat fmt;
+	PackStrings(args.data[0], count, p, fmt);
+	const int64_t nb = p.offsets.back();
+	vector<uint8_t> out((size_t)nb / 3 + 16);
+	int64_t status[2] = {-1, -1};
+	if (exb_translate_host(p.offsets.data(), p.data.data(), (int64_t)p.rows.size(), out.data(), status) != 0) {
+		throw InvalidInputException(exb_last_error());
+	}
+	if (status[1] >= 0) {
+		throw InvalidInputException("Invalid codon: " + string(reinterpret_cast<const char *>(p.data.data()) + status[1], 3));
+	}
+	if (status[0] >= 0) {
+		throw InvalidInputException("Invalid sequence length: " + std::to_string(p.offsets[status[0] + 1] - p.offsets[status[0]]));
+	}
+	result.SetVectorType(VectorType::FLAT_VECTOR);
+	auto res = FlatVector::GetData<string_t>(result);
+	auto &validity = FlatVector::Validity(result);
+	for (idx_t i = 0; i < count; i++) {
+		validity.SetInvalid(i);
+	}
+	for (idx_t k = 0; k < p.rows.size(); k++) {
+		const int64_t b = p.offsets[k] / 3, e = p.offsets[k + 1] / 3;
+		res[p.rows[k]] = StringVector::AddString(result, reinterpret_cast<const char *>(out.data()) + b, (idx_t)(e - b));
+		validity.SetValid(p.rows[k]);
+	}
+	FinishResult(result, args, count);
+}
+
 // quality_score_string_to_list(VARCHAR) -> INTEGER[]: (signed char)c - 33 per byte (fastq_functions/module.cpp:32-50).
 // Deviation, documented in DESIGN.md: '' gives [] and NULL gives NULL, where the reference raises INTERNAL errors.
 static void QualityToListFunction(DataChunk &args, ExpressionState &state, Vector &result) {
@@ -578,6 +612,9 @@ static void LoadInternal(DatabaseInstance &instance) {
 	RegisterScalar(context, "gc_content", LogicalType::FLOAT, GcContentFunction);
 	RegisterScalar(context, "reverse_complement", LogicalType::VARCHAR, SeqMapFunction<EXB_MAP_REVERSE_COMPLEMENT>);
 	RegisterScalar(context, "complement", LogicalType::VARCHAR, SeqMapFunction<EXB_MAP_COMPLEMENT>);
+	RegisterScalar(context, "transcribe", LogicalType::VARCHAR, SeqMapFunction<EXB_MAP_TRANSCRIBE>);
+	RegisterScalar(context, "reverse_transcribe", LogicalType::VARCHAR, SeqMapFunction<EXB_MAP_REVERSE_TRANSCRIBE>);
+	RegisterScalar(context, "translate_dna_to_aa", LogicalType::VARCHAR, TranslateFunction);
 	RegisterScalar(context, "quality_score_string_to_list", LogicalType::LIST(LogicalType::INTEGER), QualityToListFunction);
 	RegisterScan(context, "read_fasta", "fasta");
 	RegisterScan(context, "read_fastq", "fastq");

@@ -387,11 +387,23 @@ EXB_API int exb_gc_content(const int64_t *d_off, const uint8_t *d_data, int64_t 
 
 #define EXB_MAP_REVERSE_COMPLEMENT 0 /* module.cpp:30-69  A->C T->G C->A G->T (reference semantics) */
 #define EXB_MAP_COMPLEMENT 1         /* module.cpp:81-121 A<->T C<->G                                 */
+#define EXB_MAP_TRANSCRIBE 2         /* module.cpp:212-249 T->U, A C G unchanged                      */
+#define EXB_MAP_REVERSE_TRANSCRIBE 3 /* module.cpp:168-203 U->T, A C G unchanged                      */
 /* Maps n_bytes bytes through the table; *d_bad_pos (uint64, set to ~0 first)
  * receives the smallest index of a byte outside ACGT (the reference throws
  * InvalidInputException for it). */
 EXB_API int exb_seq_map(const uint8_t *d_in, int64_t n_bytes, int mode, uint8_t *d_out, uint64_t *d_bad_pos,
                         void *stream);
+
+/* translate_dna_to_aa (module.cpp:260-360) over a string column: standard codon table over upper-case ACGT.
+ * d_off = int64[n_rows + 1] offsets into d_data (offsets keep their base, as everywhere).  A row whose length is not a
+ * multiple of 3 is the reference's "Invalid sequence length: <len>"; a codon outside the table "Invalid codon: <xyz>".
+ * Rows are checked in order and a row's length before its codons, so d_status (int64[2], device) receives
+ *   [0] the first row with a bad length, or -1;   [1] the data offset of the first bad codon BEFORE that row, or -1.
+ * When both are -1, d_out holds (d_off[n_rows] - d_off[0]) / 3 bytes and row i's protein is
+ * d_out[(d_off[i] - d_off[0]) / 3 .. (d_off[i+1] - d_off[0]) / 3). */
+EXB_API int exb_translate(const int64_t *d_off, const uint8_t *d_data, int64_t n_rows, uint8_t *d_out,
+                          int64_t *d_status, void *stream);
 
 /* fastq_functions/module.cpp:32-50: out[i] = (signed char)in[i] - 33 (list child vector;
  * the list offsets are the string offsets). */
@@ -403,6 +415,10 @@ EXB_API int exb_quality_decode(const uint8_t *d_in, int64_t n_bytes, int32_t *d_
 EXB_API int exb_gc_content_host(const int64_t *offsets, const uint8_t *data, int64_t n_rows, float *out);
 /* *bad_pos = -1, or the smallest index of a byte outside ACGT (out is then unspecified) */
 EXB_API int exb_seq_map_host(const uint8_t *data, int64_t n_bytes, int mode, uint8_t *out, int64_t *bad_pos);
+/* offsets: n_rows + 1 entries starting at 0 into `data`; out: offsets[n_rows] / 3 bytes; status[2] as exb_translate
+ * (status[1] = offset into `data`). */
+EXB_API int exb_translate_host(const int64_t *offsets, const uint8_t *data, int64_t n_rows, uint8_t *out,
+                               int64_t *status);
 EXB_API int exb_quality_decode_host(const uint8_t *data, int64_t n_bytes, int32_t *out);
 
 /* ---- deterministic synthetic inputs, counter-based RNG ---- */

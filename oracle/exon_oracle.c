@@ -303,6 +303,55 @@ int64_t orc_complement(const uint8_t *s, int64_t len, uint8_t *out) {
     return -1;
 }
 
+/* module.cpp:212-249 (transcribe): T->U, A C G unchanged, same error rule. */
+int64_t orc_transcribe(const uint8_t *s, int64_t len, uint8_t *out) {
+    for (int64_t i = 0; i < len; i++) {
+        switch (s[i]) {
+        case 'T': out[i] = 'U'; break;
+        case 'A': case 'C': case 'G': out[i] = s[i]; break;
+        default: return i;
+        }
+    }
+    return -1;
+}
+
+/* module.cpp:168-203 (reverse_transcribe): U->T, A C G unchanged, same error rule. */
+int64_t orc_reverse_transcribe(const uint8_t *s, int64_t len, uint8_t *out) {
+    for (int64_t i = 0; i < len; i++) {
+        switch (s[i]) {
+        case 'U': out[i] = 'T'; break;
+        case 'A': case 'C': case 'G': out[i] = s[i]; break;
+        default: return i;
+        }
+    }
+    return -1;
+}
+
+/* module.cpp:260-360 (translate_dna_to_aa): the standard codon table over upper-case ACGT.  len % 3 != 0 throws
+ * "Invalid sequence length: <len>" (returns -2); a codon outside the table throws "Invalid codon: <xyz>" (returns the
+ * index of its first byte); success returns -1 with len / 3 bytes in out.  The length is checked before any codon. */
+int64_t orc_translate(const uint8_t *s, int64_t len, uint8_t *out) {
+    /* index = 16 a + 4 b + c with A=0 C=1 G=2 T=3; rows of the reference's map re-ordered accordingly */
+    static const char table[65] = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";
+    if (len % 3 != 0) return -2;
+    for (int64_t i = 0; i < len; i += 3) {
+        int idx = 0;
+        for (int k = 0; k < 3; k++) {
+            int v;
+            switch (s[i + k]) {
+            case 'A': v = 0; break;
+            case 'C': v = 1; break;
+            case 'G': v = 2; break;
+            case 'T': v = 3; break;
+            default: return i;
+            }
+            idx = idx * 4 + v;
+        }
+        out[i / 3] = (uint8_t)table[idx];
+    }
+    return -1;
+}
+
 /* exon/src/exon/fastq_functions/module.cpp:32-50: `for (auto c : string)
  * push INTEGER(c - 33)` with c a (signed) char on x86-64. */
 void orc_quality_to_list(const uint8_t *s, int64_t len, int32_t *out) {

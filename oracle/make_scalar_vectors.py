@@ -32,6 +32,13 @@ def main():
         n = rng.choice([1, 2, 3, 7, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 150, 151, 255, 256, 1000, 4097])
         alpha = rng.choice(["ACGT", "ACGT", "ACGTN", "ACGTacgt", "GC", "AT", "ACGTRYKM-*"])
         seqs.append("".join(rng.choice(alpha) for _ in range(n)))
+    # RNA alphabet and codon-shaped inputs for transcribe / reverse_transcribe / translate_dna_to_aa
+    seqs += ["AUCG", "AUCU", "AUNN", "ATNN", "ATTT", "NNN", "ATGNNN", "ATGCGCA", "ATGCGCAA", "atg", "UUU",
+             "AAAAATAACAAGATAATTATCATGACAACTACCACGAGAAGTAGCAGGTAATATTACTAGTTATTTTTCTTGTCATCTTCCTCGTGATGTTGCTGGCAACATCACCAGCTACTTCTCCTGCCACCTCCCCCGCGACGTCGCCGGGAAGATGACGAGGTAGTTGTCGTGGCAGCTGCCGCGGGAGGTGGCGGG"]
+    for _ in range(60):
+        n = rng.choice([3, 6, 9, 30, 33, 48, 150, 300, 999, 1000, 4098])
+        alpha = rng.choice(["ACGT", "ACGT", "ACGT", "ACGU", "ACGTN"])
+        seqs.append("".join(rng.choice(alpha) for _ in range(n)))
     quals = ["!'*5I~", "IIII5555", "!", "~", "#", "II", "@+>", "é", "Aé~", "ÿ!"]
     for _ in range(60):
         n = rng.choice([1, 2, 5, 16, 33, 100, 150, 301])
@@ -44,6 +51,9 @@ def main():
         stmts.append("SELECT gc_content(%s)::DOUBLE" % lit); plan.append((s, "gc"))
         stmts.append("SELECT reverse_complement(%s)" % lit); plan.append((s, "rc"))
         stmts.append("SELECT complement(%s)" % lit); plan.append((s, "comp"))
+        stmts.append("SELECT transcribe(%s)" % lit); plan.append((s, "tr"))
+        stmts.append("SELECT reverse_transcribe(%s)" % lit); plan.append((s, "rtr"))
+        stmts.append("SELECT translate_dna_to_aa(%s)" % lit); plan.append((s, "aa"))
     for q in quals:
         lit = sql_str(q)
         stmts.append("SELECT quality_score_string_to_list(%s)" % lit); plan.append((q, "qual"))
@@ -65,12 +75,19 @@ def main():
         if kind == "gc":
             assert res["ok"], res
             c["gc"] = float(res["rows"][0][0])  # float32 widened to double: exact
-        elif kind in ("rc", "comp"):
+        elif kind in ("rc", "comp", "tr", "rtr"):
             if res["ok"]:
                 c[kind] = res["rows"][0][0].encode("utf-8").decode("latin-1")
             else:
                 assert "Invalid character in sequence" in res["error"], res
                 c[kind] = None
+        elif kind == "aa":
+            if res["ok"]:
+                c["aa"] = res["rows"][0][0]
+            else:  # keep the reference's message: which of the two checks fired, and on what
+                msg = res["error"].split("Invalid Input Error: ", 1)[-1]
+                assert msg.startswith("Invalid sequence length: ") or msg.startswith("Invalid codon: "), res
+                c["aa_error"] = msg.encode("utf-8").decode("latin-1")
         elif kind == "qual":
             assert res["ok"], res
             c["qual"] = json.loads(res["rows"][0][0])

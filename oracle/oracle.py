@@ -50,7 +50,7 @@ def lib():
         L.orc_gc_content.restype = C.c_float
         L.orc_gc_count.argtypes = [u8p, C.c_int64]
         L.orc_gc_count.restype = C.c_int64
-        for f in (L.orc_reverse_complement, L.orc_complement):
+        for f in (L.orc_reverse_complement, L.orc_complement, L.orc_transcribe, L.orc_reverse_transcribe, L.orc_translate):
             f.argtypes = [u8p, C.c_int64, C.c_char_p]
             f.restype = C.c_int64
         L.orc_quality_to_list.argtypes = [u8p, C.c_int64, C.POINTER(C.c_int32)]
@@ -165,6 +165,27 @@ def reverse_complement(s):
 
 def complement(s):
     return _lut(lib().orc_complement, s)
+
+
+def transcribe(s):
+    return _lut(lib().orc_transcribe, s)
+
+
+def reverse_transcribe(s):
+    return _lut(lib().orc_reverse_transcribe, s)
+
+
+def translate_dna_to_aa(s):
+    if s is None:
+        return None
+    s = bytes(s)
+    out = C.create_string_buffer(len(s) // 3 + 1)
+    bad = lib().orc_translate(s, len(s), out)
+    if bad == -2:
+        raise InvalidInput("Invalid sequence length: %d" % len(s))
+    if bad >= 0:
+        raise InvalidInput("Invalid codon: %s" % s[bad:bad + 3].decode("latin-1"))
+    return out.raw[:len(s) // 3]
 
 
 def quality_score_string_to_list(s):

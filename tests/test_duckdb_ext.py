@@ -168,6 +168,55 @@ def test_reference_scalar_sqllogictests(cuda_device):
 
 
 @pytest.mark.gpu
+def test_reference_scalar_sqllogictests_transcribe_translate(cuda_device):
+    # test_scalar_functions.test:48-89 through the PRODUCT's CUDA scalar functions
+    allc = ("AAAAATAACAAGATAATTATCATGACAACTACCACGAGAAGTAGCAGGTAATATTACTAGTTATTTTTCTTGTCATCTTCCTCGTGATGTTGCTGGCAACATCACCAGC"
+            "TACTTCTCCTGCCACCTCCCCCGCGACGTCGCCGGGAAGATGACGAGGTAGTTGTCGTGGCAGCTGCCGCGGGAGGTGGCGGG")
+    r = run_sql(PRODUCT, [
+        "SELECT transcribe(t) FROM (SELECT 'ATCG' AS t UNION ALL SELECT 'ATCGATCG' AS t)",
+        "SELECT transcribe('ATNN')",
+        "SELECT translate_dna_to_aa(seq) FROM (SELECT 'ATGCGC' AS seq UNION ALL SELECT 'ATGCGC' AS seq)",
+        "SELECT translate_dna_to_aa('%s')" % allc,
+        "SELECT translate_dna_to_aa('NNN')",
+        "SELECT translate_dna_to_aa('ATTT')",
+        "SELECT reverse_transcribe(seq) FROM (SELECT 'AUCG' AS seq UNION ALL SELECT 'AUCU' AS seq)",
+        "SELECT reverse_transcribe('AUNN')",
+        "SELECT translate_dna_to_aa(NULL) IS NULL, translate_dna_to_aa('')",
+    ])
+    assert rows(r[0]) == [["AUCG"], ["AUCGAUCG"]]
+    assert not r[1]["ok"] and "Invalid character in sequence: N" in r[1]["error"]
+    assert rows(r[2]) == [["MR"], ["MR"]]
+    assert rows(r[3]) == [["KNNKIIIMTTTTRSSR*YY*LFFLSSSS*CCWQHHQLLLLPPPPRRRREDDEVVVVAAAAGGGG"]]
+    assert not r[4]["ok"] and "Invalid codon: NNN" in r[4]["error"]
+    assert not r[5]["ok"] and "Invalid sequence length: 4" in r[5]["error"]
+    assert rows(r[6]) == [["ATCG"], ["ATCT"]]
+    assert not r[7]["ok"] and "Invalid character in sequence: N" in r[7]["error"]
+    assert rows(r[8]) == [["true", ""]]
+
+
+@pytest.mark.gpu
+def test_transcribe_translate_against_reference_vectors(cuda_device):
+    """transcribe / reverse_transcribe / translate_dna_to_aa of the PRODUCT inside DuckDB vs the reference's own functions
+    (tests/golden/scalar_ref_vectors.json), the valid inputs in ONE multi-row table, the invalid ones one by one."""
+    with open(os.path.join(G, "scalar_ref_vectors.json")) as f:
+        cases = [c for c in json.load(f)["cases"] if "tr" in c and len(c["seq"]) < 6000]
+    lit = lambda s: "'" + s.encode("latin-1").decode("utf-8").replace("'", "''") + "'"
+    for key, fn in (("tr", "transcribe"), ("rtr", "reverse_transcribe"), ("aa", "translate_dna_to_aa")):
+        good = [c for c in cases if c.get(key) is not None]
+        assert len(good) > 20, key
+        values = ", ".join("(%d, %s)" % (i, lit(c["seq"])) for i, c in enumerate(good))
+        r = run_sql(PRODUCT, ["CREATE TABLE s AS SELECT * FROM (VALUES %s) t(i, seq)" % values, "SELECT i, %s(seq) FROM s ORDER BY i" % fn])
+        got = rows(r[1])
+        assert len(got) == len(good)
+        for (i, v), c in zip(got, good):
+            assert v.encode("utf-8").decode("latin-1") == c[key], (fn, c["seq"][:40])
+    bad = [c for c in cases if "aa_error" in c][:12]
+    r = run_sql(PRODUCT, ["SELECT translate_dna_to_aa(%s)" % lit(c["seq"]) for c in bad])
+    for x, c in zip(r, bad):
+        assert not x["ok"] and c["aa_error"].encode("latin-1").decode("utf-8") in x["error"], (c["seq"][:40], x)
+
+
+@pytest.mark.gpu
 def test_scalar_functions_against_reference_vectors(cuda_device):
     """The product's CUDA scalar functions inside DuckDB vs the reference's own functions (golden vectors), in ONE multi-row table."""
     with open(os.path.join(G, "scalar_ref_vectors.json")) as f:

@@ -51,6 +51,36 @@ def test_reverse_complement_and_complement(cuda_device):
             assert str(ei.value) == str(eo.value)  # "Invalid character in sequence: <c>" names the first bad byte
 
 
+def test_transcribe_reverse_transcribe_translate(cuda_device):
+    """SURVEY 8f rank 3 (sequence_functions/module.cpp:168-360) on device columns vs the oracle, which is pinned on the
+    reference's own functions (tests/golden/scalar_ref_vectors.json): values, and for the first offending row the
+    reference's message -- rows in order, a row's length before its codons."""
+    from exon_duckdb_b200 import device as D
+    from oracle import oracle as O
+    rng = random.Random(5)
+    dna = [b"ATCG", b"ATCGATCG", b""] + [util.rand_seq(rng, rng.randint(0, 3000)) for _ in range(300)]
+    col = _column(cuda_device, dna)
+    assert D.transcribe(col).to_pylist() == [O.transcribe(s) for s in dna]
+    rna = [O.transcribe(s) for s in dna]
+    assert D.reverse_transcribe(_column(cuda_device, rna)).to_pylist() == dna
+    cod = [b"ATGCGC", b"", b"AAA"] + [util.rand_seq(rng, 3 * rng.randint(0, 1500)) for _ in range(300)]
+    assert D.translate_dna_to_aa(_column(cuda_device, cod)).to_pylist() == [O.translate_dna_to_aa(s) for s in cod]
+    for fn, ofn, bad in ((D.transcribe, O.transcribe, b"AUCG"), (D.reverse_transcribe, O.reverse_transcribe, b"ATCG"), (D.transcribe, O.transcribe, b"ACGn")):
+        with pytest.raises(D.InvalidInput) as ei:
+            fn(_column(cuda_device, [b"ACG" * 50, bad, b"GG"]))
+        with pytest.raises(O.InvalidInput) as eo:
+            ofn(bad)
+        assert str(ei.value) == str(eo.value)
+    # first offending row wins; inside a row the length is checked before the codons
+    for rows_, first_bad in (([b"ATG", b"ATGNNN", b"ATGA"], 1), ([b"ATG", b"ATGA", b"NNN"], 1), ([b"ATGNNNA", b"AAA"], 0), ([b"atg"], 0),
+                             ([b"AAA" * 700, b"AAANAAAAT"], 1)):
+        with pytest.raises(D.InvalidInput) as ei:
+            D.translate_dna_to_aa(_column(cuda_device, rows_))
+        with pytest.raises(O.InvalidInput) as eo:
+            O.translate_dna_to_aa(rows_[first_bad])
+        assert str(ei.value) == str(eo.value), rows_
+
+
 @pytest.mark.parametrize("mode", ["reverse_complement", "complement"])
 def test_map_fused_into_the_gather(cuda_device, mode):
     """read_fastq -> reverse_complement(sequence) as one pass (exb_fastq_gather_map) equals gather + scalar function,

@@ -141,6 +141,19 @@ def test_scalar_vectors_from_reference_build(golden_dir):
                     O.complement(s)
             else:
                 assert O.complement(s) == case["comp"].encode("latin-1")
+        for key, fn in (("tr", O.transcribe), ("rtr", O.reverse_transcribe)):
+            if key in case:
+                if case[key] is None:
+                    with pytest.raises(O.InvalidInput):
+                        fn(s)
+                else:
+                    assert fn(s) == case[key].encode("latin-1")
+        if "aa" in case:
+            assert O.translate_dna_to_aa(s) == case["aa"].encode("latin-1")
+        if "aa_error" in case:
+            with pytest.raises(O.InvalidInput) as ei:
+                O.translate_dna_to_aa(s)
+            assert str(ei.value).encode("latin-1", "replace") == case["aa_error"].encode("latin-1") or str(ei.value) == case["aa_error"]
         if "qual" in case:
             assert O.quality_score_string_to_list(s).tolist() == case["qual"]
         if "mean_q" in case:
