@@ -205,6 +205,15 @@ __device__ __forceinline__ void fa_copy(uint8_t* s_out, const uint8_t* sbytes, i
     for (int i = done + first; i < len; i += step) s_out[dst + i] = sbytes[sidx(src + i)];
 }
 
+// shared-memory accessors on 32-bit shared-window addresses
+__device__ __forceinline__ uint32_t fa_lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void fa_sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void fa_sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
+
 // 128 x (number of bytes < 0x40 among the 16): bit 7 of x | x << 1 is set iff bit 7 or bit 6 of the byte is
 __device__ __forceinline__ uint32_t low_count128(const uint4& v, uint32_t acc) {
     acc = __dp4a(~(v.x | (v.x << 1)) & 0x80808080u, 0x01010101u, acc);
@@ -304,9 +313,13 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
         const bool odd = (int)(low128 >> 7) != cnt;
         fast2 = regular && !__any_sync(0xffffffffu, odd);
         if (fast2) {
-            const uint32_t* rowp = reinterpret_cast<const uint32_t*>(sbytes + lane * ROW_BYTES);
-            const int swz = lane & 7;
-            auto src_word = [&](int w) -> uint32_t { return rowp[((((w >> 2) ^ swz) << 2) | (w & 3))]; };
+            // 32-bit shared-window addresses + ld/st.shared: no generic-pointer arithmetic in the copy loop (with generic
+            // pointers the word loop cost ~30 instructions a word: ncu r02b)
+            const uint32_t row_u32 = (uint32_t)__cvta_generic_to_shared(sbytes) + (uint32_t)(lane * ROW_BYTES);
+            const uint32_t out_u32 = (uint32_t)__cvta_generic_to_shared(s_out);
+            // word w of the lane's row: the 128B swizzle XORs the 16-byte chunk index with (row & 7), i.e. bits 2..4 of w
+            const int x4 = (lane & 7) << 2;
+            auto src_word = [&](int w) -> uint32_t { return fa_lds32(row_u32 + (uint32_t)((w ^ x4) << 2)); };
             int dst = (int)(in.kept_base & 15) + lane * ROW_BYTES - ex_cnt;
             int start = 0;
             uint64_t m0 = pm[0], m1 = pm[1];
@@ -324,25 +337,28 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
                 int len = end - start, src = start;
                 // bytes up to the first 4-byte boundary of the destination
                 while (len > 0 && (dst & 3)) {
-                    s_out[dst++] = (uint8_t)(src_word(src >> 2) >> ((src & 3) * 8));
+                    fa_sts8(out_u32 + (uint32_t)dst++, src_word(src >> 2) >> ((src & 3) * 8));
                     src++;
                     len--;
                 }
-                const int nw = len >> 2, bs = (src & 3) * 8;
-                uint32_t* ow = reinterpret_cast<uint32_t*>(s_out + dst);
-                int sw = src >> 2;
-                uint32_t w0 = nw > 0 ? src_word(sw) : 0u;
-                for (int k = 0; k < nw; k++) {
-                    const uint32_t w1 = (bs != 0 && sw + 1 < 32) ? src_word(sw + 1) : 0u;  // bs == 0: the word is aligned
-                    ow[k] = __funnelshift_r(w0, w1, bs);
-                    w0 = bs != 0 ? w1 : (sw + 1 < 32 ? src_word(sw + 1) : 0u);
-                    sw++;
+                const int nw = len >> 2, bs = (src & 3) * 8, sw = src >> 2;
+                const uint32_t ow = out_u32 + (uint32_t)dst;
+                if (bs == 0) {
+                    for (int k = 0; k < nw; k++) fa_sts32(ow + 4u * (uint32_t)k, src_word(sw + k));
+                } else if (nw > 0) {
+                    // the last byte copied lies in word sw + nw of the row, so every word read below exists
+                    uint32_t w0 = src_word(sw);
+                    for (int k = 0; k < nw; k++) {
+                        const uint32_t w1 = src_word(sw + k + 1);
+                        fa_sts32(ow + 4u * (uint32_t)k, __funnelshift_r(w0, w1, bs));
+                        w0 = w1;
+                    }
                 }
                 dst += nw * 4;
                 src += nw * 4;
                 len -= nw * 4;
                 while (len > 0) {
-                    s_out[dst++] = (uint8_t)(src_word(src >> 2) >> ((src & 3) * 8));
+                    fa_sts8(out_u32 + (uint32_t)dst++, src_word(src >> 2) >> ((src & 3) * 8));
                     src++;
                     len--;
                 }
@@ -350,10 +366,12 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
             }
         }
     }
-    s_gm[2 * lane] = gm[0];
-    s_gm[2 * lane + 1] = gm[1];
-    s_gex[2 * lane] = ex_g;
-    s_gex[2 * lane + 1] = ex_g + g0;
+    if (!fast2) {  // only the newline walk reads these
+        s_gm[2 * lane] = gm[0];
+        s_gm[2 * lane + 1] = gm[1];
+        s_gex[2 * lane] = ex_g;
+        s_gex[2 * lane + 1] = ex_g + g0;
+    }
 
     auto scatter = [&](int win_lo) {
         int rank = ex_cnt - win_lo;
@@ -368,7 +386,7 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
             }
         }
     };
-    scatter(0);
+    if (!fast2) scatter(0);
     __syncwarp();
     auto gc_before = [&](int pos) -> int { return s_gex[pos >> 6] + __popcll(s_gm[pos >> 6] & low_bits64(pos & 63)); };
 
