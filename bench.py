@@ -435,8 +435,9 @@ def main():
                          "note": "algorithmic bytes = input file bytes read once (SURVEY 8d); kernel_ms = CUDA events on the launching stream around one exb_fastq_scan_filter call (3 small memsets + tile kernel + 3 offset-scan kernels + combine kernel), i.e. an upper bound of the tile kernel's own duration"},
             "clocks": sampler.summary(),
             # N=1: fastq_tile_kernel, scan_reduce / scan_spine / scan_down (per-tile line offsets), fastq_fused_combine_kernel
-            # (+ 3 cudaMemsetAsync); N>1 adds per rank: fastq_compose_prev_kernel + a second fastq_fused_combine_kernel
-            # (ranks >= 1) and, with the peer-memory exchange, peer_allgather_kernel + peer_count_reduce_kernel
+            # (+ 3 cudaMemsetAsync); N>1: the combine kernel runs once, AFTER the exchange (fastq_final_state_kernel writes
+            # the block that is exchanged), plus fastq_compose_prev_kernel (ranks >= 1) and, with the peer-memory
+            # exchange, peer_allgather_kernel + peer_count_reduce_kernel
             # peer-memory exchange adds exb_peer_allgather_block + exb_peer_count_reduce (7 of this library's kernels per step)
             "gpu_launches": (5 if world == 1 else (9 if exchange.startswith("nvlink") else 7)) * args.steps,
         }

@@ -94,6 +94,7 @@ SIGNATURES = {
     "exb_fastq_workspace_bytes": (_i64, [_i64, _i64]),
     "exb_fastq_scan": (_i32, [_vp, _i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_fastq_scan_filter": (_i32, [_vp, _i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i32, _vp, _i64, _vp]),
+    "exb_fastq_scan_filter_begin": (_i32, [_vp, _i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i64, _vp]),
     "exb_fastq_scan_resolve": (_i32, [_i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_fastq_scan_filter_resolve": (_i32, [_i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i32, _vp, _i64, _vp]),
     "exb_fastq_compose_prev": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),

@@ -31,6 +31,7 @@ cudaError_t gc_from_prefix_launch(const int64_t*, const int64_t*, int64_t, float
 cudaError_t gc_from_counts_launch(const uint32_t*, const uint32_t*, int64_t, float*, cudaStream_t);
 cudaError_t gc_content_launch(const int64_t*, const uint8_t*, int64_t, float*, cudaStream_t);
 cudaError_t seq_map_launch(const uint8_t*, int64_t, int, uint8_t*, unsigned long long*, cudaStream_t);
+cudaError_t fastq_final_state_launch(const FastqScanArgs&, cudaStream_t);
 cudaError_t translate_launch(const int64_t*, const uint8_t*, int64_t, int64_t, uint8_t*, long long*, cudaStream_t);
 cudaError_t quality_decode_launch(const uint8_t*, int64_t, int32_t*, cudaStream_t);
 
@@ -195,7 +196,8 @@ static int64_t fastq_workspace_bytes(int64_t n, int64_t max_lines) {
 static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace,
                              uint64_t max_lines, int flags, void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len,
                              uint32_t* d_gc, uint32_t* d_qual_len, int32_t* d_qsum, int64_t rec_cap, const exb_predicate* preds, int n_preds,
-                             int64_t* d_agg, void* d_workspace, int64_t workspace_bytes, cudaStream_t st, bool resolve_only = false) {
+                             int64_t* d_agg, void* d_workspace, int64_t workspace_bytes, cudaStream_t st, bool resolve_only = false,
+                             bool scan_only = false) {
     if ((!d_buf && !resolve_only) || begin < 0 || n < begin) return set_err(EXB_ERR_ARG, "%s: bad buffer range", who);
     if (((uintptr_t)d_buf & 15) != 0) return set_err(EXB_ERR_ARG, "%s: d_buf must be 16-byte aligned", who);
     if (d_prev_workspace && (begin & 15) != 0) return set_err(EXB_ERR_ARG, "%s: `begin` of a chained range must be a multiple of 16", who);
@@ -263,6 +265,11 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
         e = exclusive_scan_launch_u32(a.tile_cnt, a.n_tiles, line_base, w.slots, w.ticket, st);
         if (e != cudaSuccess) return cuda_fail(e, "line offset scan launch");
     }
+    if (scan_only) {  // the result block only: K2 runs later through the matching *_resolve call
+        e = fastq_final_state_launch(a, st);
+        if (e != cudaSuccess) return cuda_fail(e, "fastq_final_state launch");
+        return 0;
+    }
     // K2: records -> per-line / per-record outputs (or bucket selection, fused)
     e = fastq_emit_launch(a, flags, wide_offsets != 0, st);
     if (e != cudaSuccess) return cuda_fail(e, "fastq_emit launch");
@@ -305,6 +312,20 @@ int exb_fastq_scan_filter(const void* d_buf, int64_t begin, int64_t n, int is_fi
     }
     return fastq_scan_common("exb_fastq_scan_filter", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_QUAL, nullptr, 0,
                              0, nullptr, nullptr, nullptr, nullptr, 0, preds, n_preds, d_agg, d_workspace, workspace_bytes, st);
+}
+
+int exb_fastq_scan_filter_begin(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace,
+                                const exb_predicate* preds, int n_preds, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    if (n_preds < 0 || n_preds > EXB_MAX_PREDICATES || (n_preds > 0 && !preds)) return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter_begin: bad predicates");
+    for (int i = 0; i < n_preds; i++) {
+        if (preds[i].field != EXB_P_MEAN_QUALITY && preds[i].field != EXB_P_QUAL_LEN)
+            return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter_begin: predicate %d is not on the quality line", i);
+        if (preds[i].op < 0 || preds[i].op > 5) return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter_begin: bad operator in predicate %d", i);
+    }
+    // the byte pass judges every line under all four phase hypotheses, so it needs the predicates; K2 only picks buckets
+    return fastq_scan_common("exb_fastq_scan_filter_begin", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_QUAL, nullptr, 0,
+                             0, nullptr, nullptr, nullptr, nullptr, 0, preds, n_preds, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream,
+                             false, true);
 }
 
 int exb_fastq_scan_resolve(int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, uint64_t max_lines, int flags,

@@ -908,6 +908,24 @@ static cudaError_t launch_emit(const FastqScanArgs& a, int flags, cudaStream_t s
     }
 }
 
+// The scan's result block (line count of the range, open last line, tail sums) without running K2: everything it holds
+// follows from the last tile's directory words.  A byte-range shard exchanges this block BEFORE it knows its phase, so
+// the provisional K2 it used to run first (39 us of a 1.45 ms step at C2) was wasted work on every rank but the first.
+__global__ void fastq_final_state_kernel(const FastqScanArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int64_t origin = a.begin & ~(int64_t)15;
+    const int64_t last = a.n_tiles - 1;
+    const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
+    const int n_events = (int)a.tile_cnt[last];
+    const uint64_t excl = init + (uint64_t)a.line_base[last];
+    const OpenLine open = open_line_before(a.tails, last, origin, a);
+    write_final_state(a, excl + (uint64_t)n_events, n_events, origin + last * WT_BYTES, a.tails[last], open);
+}
+cudaError_t fastq_final_state_launch(const FastqScanArgs& a, cudaStream_t st) {
+    fastq_final_state_kernel<<<1, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t fastq_emit_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st) {
     if (flags & EXB_F_FUSED) {
         int64_t blocks = (a.n_tiles + 255) / 256;

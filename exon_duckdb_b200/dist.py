@@ -262,8 +262,9 @@ def _state_from_block(words, lo, hi, begin, line_starts=()):
 class ShardedFastqCount:
     """SELECT COUNT(*), sums FROM read_fastq(file) WHERE <quality-line predicates> over this rank's shard of the file.
 
-    step() enqueues, with no host round trip: fused scan (K1 + provisional resolve) -> all-gather of the 128-byte result
-    blocks -> exb_fastq_compose_prev (device) -> resolve kernel -> all-reduce of the aggregates.  `total` (int64[8],
+    step() enqueues, with no host round trip: byte pass + line offsets + result block (exb_fastq_scan_filter_begin) ->
+    exchange of the 128-byte result blocks -> exb_fastq_compose_prev (device) -> K2 under the true predecessor ->
+    reduce of the aggregates.  `total` (int64[8],
     device) then holds the GLOBAL aggregates on every rank: [0] passing records, [3] sum of their Phred sums, [4] sum of
     their quality lengths, [6] lines of the file mod 4 (must be 0), [7] shards that met a malformed record (must be 0)."""
 
@@ -296,12 +297,13 @@ class ShardedFastqCount:
 
     # -- the phases (tests drive them shard by shard through a LocalGroup-style loop; step() chains them for a TorchGroup)
     def scan(self):
-        """K1 + provisional resolve; returns the shard's result block (int64[16] view of the workspace, on the device)."""
+        """K1 + line offsets; returns the shard's result block (int64[16] view of the workspace, on the device)."""
         from . import device as D
 
         s = self.shard
-        _lib.check(_lib.lib().exb_fastq_scan_filter(D._ptr(s.buf), s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.prov), self.arr, self.k,
-                                                    D._ptr(self.c.agg), 0, D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
+        # K1 + line offsets + the result block; no K2 yet: the phase is only known after the exchange
+        _lib.check(_lib.lib().exb_fastq_scan_filter_begin(D._ptr(s.buf), s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.prov), self.arr, self.k,
+                                                          D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
         self.c._res = None
         return _result_block(self.c.ws)
 
@@ -314,12 +316,7 @@ class ShardedFastqCount:
         from . import device as D
 
         s = self.shard
-        if rank > 0:
-            L = _lib.lib()
-            _lib.check(L.exb_fastq_compose_prev(D._ptr(blocks), D._ptr(self.d_ranges), self.world, rank, D._ptr(self.true_prev), D._stream()))
-            _lib.check(L.exb_fastq_scan_filter_resolve(s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.true_prev), self.arr, self.k,
-                                                       D._ptr(self.c.agg), 0, D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
-            self.c._res = None
+        self.resolve_local(blocks, rank)
         blk = _result_block(self.c.ws)
         self.total.copy_(self.c.agg)
         self.total[7] = (blk[2] != 0).to(self.total.dtype)  # device err_pos word: 0 = no malformed record
@@ -331,12 +328,15 @@ class ShardedFastqCount:
         from . import device as D
 
         s = self.shard
+        L = _lib.lib()
+        prev = None
         if rank > 0:
-            L = _lib.lib()
             _lib.check(L.exb_fastq_compose_prev(D._ptr(blocks), D._ptr(self.d_ranges), self.world, rank, D._ptr(self.true_prev), D._stream()))
-            _lib.check(L.exb_fastq_scan_filter_resolve(s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.true_prev), self.arr, self.k,
-                                                       D._ptr(self.c.agg), 0, D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
-            self.c._res = None
+            prev = self.true_prev
+        # K2 (bucket selection, 48 B per tile) under the true predecessor; the first shard has none
+        _lib.check(L.exb_fastq_scan_filter_resolve(s.begin, s.n, 1 if s.is_last else 0, D._ptr(prev), self.arr, self.k,
+                                                   D._ptr(self.c.agg), 0, D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
+        self.c._res = None
 
     def step(self, after_scan=None, stage_marks=None):
         """One pass over the shard + the exchange; every launch is asynchronous on the current stream.

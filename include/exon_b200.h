@@ -271,6 +271,12 @@ EXB_API int exb_fastq_scan_filter(const void *d_buf, int64_t begin, int64_t n, i
  *      input bytes are not read a second time.  d_agg / per-record outputs of step 1 are overwritten.
  * exon_duckdb_b200/dist.py is the host side of this protocol.
  */
+/* Step 1 of the fused COUNT flavour without its K2: the byte pass, the line-offset scan and the result block only
+ * (a shard does not know its phase yet, so a provisional K2 would be thrown away).  Follow with the exchange and
+ * exb_fastq_scan_filter_resolve on EVERY shard (the first one with d_prev_workspace = NULL). */
+EXB_API int exb_fastq_scan_filter_begin(const void *d_buf, int64_t begin, int64_t n, int is_final,
+                                        const void *d_prev_workspace, const exb_predicate *preds, int n_preds,
+                                        void *d_workspace, int64_t workspace_bytes, void *stream);
 EXB_API int exb_fastq_scan_resolve(int64_t begin, int64_t n, int is_final, const void *d_prev_workspace, uint64_t max_lines,
                                    int flags, void *d_line_end, int64_t line_cap, int wide_offsets, uint32_t *d_seq_len,
                                    uint32_t *d_gc, uint32_t *d_qual_len, int32_t *d_qsum, int64_t rec_cap,
