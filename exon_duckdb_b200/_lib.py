@@ -32,6 +32,7 @@ class ScanResult(C.Structure):
         ("tail_s", C.c_int64),
         ("tail_g", C.c_int64),
         ("tail_hdr", C.c_uint64),
+        ("crlf_lines", C.c_uint64),
     ]
 
 
@@ -105,7 +106,7 @@ SIGNATURES = {
     "exb_scan_result_store": (_i32, [_vp, C.POINTER(ScanResult), _vp]),
     "exb_scan_result_fetch": (_i32, [_vp, C.POINTER(ScanResult), _vp]),
     "exb_fastq_filter": (_i32, [_vp, _vp, _vp, _vp, _i64, C.POINTER(Predicate), _i32, _vp, _vp, _vp, _vp]),
-    "exb_fastq_fields": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "exb_fastq_fields": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "exb_exclusive_scan_u32": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "exb_exclusive_scan_u32_multi": (_i32, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _i64, _vp]),
     "exb_select_rows": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),

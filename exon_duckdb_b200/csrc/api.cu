@@ -19,7 +19,7 @@ cudaError_t exclusive_scan_launch_u8(const uint8_t*, int64_t, int64_t*, TileSlot
 int64_t scan_tiles(int64_t n);
 cudaError_t select_rows_launch(const uint8_t*, const int64_t*, int64_t, int64_t*, cudaStream_t);
 cudaError_t fastq_fields_launch(const uint8_t*, int64_t, int64_t, const void*, bool, const int64_t*, int64_t, uint32_t*, uint8_t*,
-                                int64_t*, cudaStream_t);
+                                int64_t*, const ScanResult*, cudaStream_t);
 cudaError_t fastq_gather_launch(const uint8_t*, int64_t, int64_t, const void*, bool, const int64_t*, int64_t, int, const uint32_t*,
                                 const int64_t*, uint8_t*, cudaStream_t, int, unsigned long long*);
 cudaError_t gather_ranges_launch(const uint8_t*, const int64_t*, const uint32_t*, const int64_t*, int64_t, int64_t, uint8_t*, cudaStream_t);
@@ -399,9 +399,10 @@ int exb_fastq_filter(const uint32_t* d_seq_len, const uint32_t* d_gc, const uint
 }
 
 int exb_fastq_fields(const void* d_buf, int64_t begin, int64_t n, const void* d_line_end, int wide_offsets, const int64_t* d_sel,
-                     int64_t n_rows, uint32_t* d_lens, uint8_t* d_desc_valid, int64_t* d_starts, void* stream) {
+                     int64_t n_rows, uint32_t* d_lens, uint8_t* d_desc_valid, int64_t* d_starts, const void* d_scan_workspace, void* stream) {
     cudaError_t e = fastq_fields_launch(reinterpret_cast<const uint8_t*>(d_buf), begin, n, d_line_end, wide_offsets != 0, d_sel, n_rows,
-                                        d_lens, d_desc_valid, d_starts, (cudaStream_t)stream);
+                                        d_lens, d_desc_valid, d_starts, reinterpret_cast<const ScanResult*>(d_scan_workspace),
+                                        (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "fastq_fields launch");
     return 0;
 }

@@ -27,6 +27,7 @@ struct ScanResult {
     uint64_t gc_total;          // FASTA: G/C among them
     int64_t tail_s, tail_g;     // FASTQ: byte sum / G,C count of the open line (chunk chaining)
     uint64_t tail_hdr;          // FASTA: the open line is a header line (chunk chaining)
+    unsigned long long crlf_lines;  // FASTQ general scan (K2): lines that ended in CR LF
 };
 
 // per-tile aggregates of the fused COUNT flavour: one bucket per phase hypothesis h = (global index of the

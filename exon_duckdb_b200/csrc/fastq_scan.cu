@@ -658,6 +658,7 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const FastqScanArgs a) 
     // per warp iteration paid three dependent global latencies per tile -- count, directory, records -- ~100 us of the
     // kernel's 164 us for a 1.4 GB file.)
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t n_crlf = 0;  // lines of this lane that ended in CR LF (the field split skips its CR probes when the range has none)
     for (int64_t batch = warp_global * 32; batch < n_tiles; batch += warps * 32) {
       const int64_t mine = batch + lane;
       const bool mv = mine < n_tiles;
@@ -735,6 +736,7 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const FastqScanArgs a) 
                 if (g < a.max_lines) {
                     const uint32_t cr = len > 0 ? rec_cr(r.y) : 0u;
                     len -= cr;
+                    n_crlf += cr;
                     const int ph = (int)(g & 3);
                     const uint64_t rix = g >> 2;
                     if (kLines) {
@@ -767,6 +769,8 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const FastqScanArgs a) 
         }
       }
     }
+    n_crlf = __reduce_add_sync(0xffffffffu, n_crlf);
+    if (lane == 0 && n_crlf) atomicAdd(&a.result->crlf_lines, (unsigned long long)n_crlf);
 }
 
 // K2 of the fused flavour: one thread per tile picks the bucket of the tile's true phase and finishes the

@@ -884,7 +884,7 @@ struct Reader {
             }
             if (!d_lens.need(std::max<int64_t>(R, 1) * 16) || !d_starts.need(std::max<int64_t>(R, 1) * 32) || !d_valid.need(std::max<int64_t>(R, 1)))
                 return fail("out of device memory");
-            if (!rc(exb_fastq_fields(d_cur, 0, n, d_line.p, 0, nullptr, R, d_lens.as<uint32_t>(), d_valid.as<uint8_t>(), d_starts.as<int64_t>(), st)))
+            if (!rc(exb_fastq_fields(d_cur, 0, n, d_line.p, 0, nullptr, R, d_lens.as<uint32_t>(), d_valid.as<uint8_t>(), d_starts.as<int64_t>(), d_ws.p, st)))
                 return false;
             const uint8_t* bufs[4] = {d_cur, d_cur, d_cur, d_cur};
             const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; int64_t o_n;

@@ -262,12 +262,13 @@ struct FqLines {
     const uint8_t* buf;
     const OffT* line_end;
     int64_t begin, n;
+    bool probe_cr;  // false: the scan saw no CR LF line ending in this range, so no line end needs the byte before it
     // start of line g and its end with a trailing CR removed
     __device__ __forceinline__ int64_t start(int64_t g) const { return g == 0 ? begin : (int64_t)line_end[g - 1] + 1; }
     __device__ __forceinline__ int64_t end(int64_t g, int64_t s) const {
         int64_t e = (int64_t)line_end[g];
         // e == n is the virtual terminator of an unterminated last line: it strips no CR
-        if (e > s && e < n && buf[e - 1] == '\r') e--;
+        if (probe_cr && e > s && e < n && buf[e - 1] == '\r') e--;
         return e;
     }
 };
@@ -299,7 +300,10 @@ __device__ __forceinline__ int64_t first_space(const uint8_t* __restrict__ buf, 
 template <typename OffT>
 __global__ void __launch_bounds__(256) fastq_fields_kernel(FqLines<OffT> L, const int64_t* __restrict__ sel, int64_t n_rows,
                                                            uint32_t* __restrict__ lens, uint8_t* __restrict__ desc_valid,
-                                                           int64_t* __restrict__ starts) {
+                                                           int64_t* __restrict__ starts, const ScanResult* __restrict__ scan) {
+    // three scattered one-byte probes per record (a 32-byte sector each) are ~40 % of this kernel's traffic; K2 of the
+    // scan counted the CR LF line endings of the range, and almost every file has none
+    L.probe_cr = !scan || scan->crlf_lines != 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = sel ? sel[i] : i;
         const int64_t g = 4 * r;
@@ -584,22 +588,22 @@ static int row_blocks(int64_t n_rows, int rows_per_block) {
 
 template <typename OffT>
 static cudaError_t fields_launch_t(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, const int64_t* sel, int64_t n_rows,
-                                   uint32_t* lens, uint8_t* desc_valid, int64_t* starts, cudaStream_t st) {
+                                   uint32_t* lens, uint8_t* desc_valid, int64_t* starts, const ScanResult* scan, cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
-    FqLines<OffT> L{buf, reinterpret_cast<const OffT*>(line_end), begin, n};
-    fastq_fields_kernel<OffT><<<row_blocks(n_rows, 256), 256, 0, st>>>(L, sel, n_rows, lens, desc_valid, starts);
+    FqLines<OffT> L{buf, reinterpret_cast<const OffT*>(line_end), begin, n, true};
+    fastq_fields_kernel<OffT><<<row_blocks(n_rows, 256), 256, 0, st>>>(L, sel, n_rows, lens, desc_valid, starts, scan);
     return cudaGetLastError();
 }
 cudaError_t fastq_fields_launch(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, bool wide, const int64_t* sel,
-                                int64_t n_rows, uint32_t* lens, uint8_t* desc_valid, int64_t* starts, cudaStream_t st) {
-    return wide ? fields_launch_t<uint64_t>(buf, begin, n, line_end, sel, n_rows, lens, desc_valid, starts, st)
-                : fields_launch_t<uint32_t>(buf, begin, n, line_end, sel, n_rows, lens, desc_valid, starts, st);
+                                int64_t n_rows, uint32_t* lens, uint8_t* desc_valid, int64_t* starts, const ScanResult* scan, cudaStream_t st) {
+    return wide ? fields_launch_t<uint64_t>(buf, begin, n, line_end, sel, n_rows, lens, desc_valid, starts, scan, st)
+                : fields_launch_t<uint32_t>(buf, begin, n, line_end, sel, n_rows, lens, desc_valid, starts, scan, st);
 }
 template <typename OffT>
 static cudaError_t gather_launch_t(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, const int64_t* sel, int64_t n_rows,
                                    int col, const uint32_t* lens, const int64_t* off, uint8_t* out, cudaStream_t st, int mode,
                                    unsigned long long* bad) {
-    SrcFastq<OffT> fn{FqLines<OffT>{buf, reinterpret_cast<const OffT*>(line_end), begin, n}, sel, lens, col};
+    SrcFastq<OffT> fn{FqLines<OffT>{buf, reinterpret_cast<const OffT*>(line_end), begin, n, true}, sel, lens, col};
     return gather_span_launch(buf, fn, off, n_rows, n - begin, out, st, mode, bad);  // a column is never larger than the input
 }
 cudaError_t fastq_gather_launch(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, bool wide, const int64_t* sel,

@@ -261,7 +261,7 @@ def fastq_table(buf, columns=None, preds=(), n=None, seq_map=None):
     lens = _empty(4 * n_rows, torch.int32, dev)
     valid = _empty(n_rows, torch.uint8, dev)
     wide = 1 if scan.wide else 0
-    check(lib().exb_fastq_fields(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, _ptr(lens), _ptr(valid), None, _stream()))
+    check(lib().exb_fastq_fields(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, _ptr(lens), _ptr(valid), None, _ptr(scan.ws), _stream()))
     out = {}
     # Arrow offsets of all four columns in ONE launch, then ONE host round trip for the column sizes
     offs = exclusive_scan_u32_multi(lens, n_rows, 4)

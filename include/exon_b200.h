@@ -180,6 +180,8 @@ typedef struct exb_scan_result {
     uint64_t gc_total;        /* FASTA: G/C among them                                   */
     int64_t tail_s, tail_g;   /* FASTQ: state of the open line (used when chaining chunks) */
     uint64_t tail_hdr;        /* FASTA: the open line is a header line (chaining)          */
+    uint64_t crlf_lines;      /* FASTQ general scan: lines of the range that ended in CR LF (0 lets
+                                 exb_fastq_fields skip its three CR probes per record)       */
 } exb_scan_result;
 
 /* Bytes of scratch a scan over n input bytes needs (the calls clear what they need cleared).
@@ -315,10 +317,12 @@ EXB_API int exb_scan_result_store(void *d_dst, const exb_scan_result *src, void 
 /* Field extents of FASTQ records from the line index: d_lens is uint32_t[4][n_records]
  * (name, description, sequence, quality_scores); d_desc_valid uint8_t[n_records]
  * (0 = NULL description).  d_sel (optional) lists the records to take; d_starts (optional)
- * int64_t[4][n_rows] receives the field offsets in d_buf (input of exb_gather_ranges). */
+ * int64_t[4][n_rows] receives the field offsets in d_buf (input of exb_gather_ranges).
+ * d_scan_workspace (optional): the workspace of the exb_fastq_scan that produced d_line_end over the same range; when
+ * its result block says no line ended in CR LF, the kernel skips the byte it would read before every line end. */
 EXB_API int exb_fastq_fields(const void *d_buf, int64_t begin, int64_t n, const void *d_line_end, int wide_offsets,
                              const int64_t *d_sel, int64_t n_rows, uint32_t *d_lens, uint8_t *d_desc_valid,
-                             int64_t *d_starts, void *stream);
+                             int64_t *d_starts, const void *d_scan_workspace, void *stream);
 
 /* Exclusive prefix sum uint32 -> int64 with the total in d_out[n] (n + 1 outputs).
  * d_workspace: exb_scan_workspace_bytes(4 * n) zero-initialised by the call. */
