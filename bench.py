@@ -439,7 +439,9 @@ def main():
             # the block that is exchanged), plus fastq_compose_prev_kernel (ranks >= 1) and, with the peer-memory
             # exchange, peer_allgather_kernel + peer_count_reduce_kernel
             # peer-memory exchange adds exb_peer_allgather_block + exb_peer_count_reduce (7 of this library's kernels per step)
-            "gpu_launches": (5 if world == 1 else (9 if exchange.startswith("nvlink") else 7)) * args.steps,
+            # launches of THIS library on rank 0 per step: tile + 3 scan + combine; N>1: + final_state (+ allgather + reduce
+            # with the peer-memory exchange; rank 0 has no compose kernel)
+            "gpu_launches": (5 if world == 1 else (8 if exchange.startswith("nvlink") else 6)) * args.steps,
         }
         if world > 1:
             line["exchange"] = exchange
