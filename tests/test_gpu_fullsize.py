@@ -165,3 +165,48 @@ def test_c4_ont_200k_reads(cuda_device):
     a, b = int(col.offsets[k]), int(col.offsets[k + 1])
     s = col.data[a:b].cpu().numpy().tobytes()
     assert rc.data[a:b].cpu().numpy().tobytes() == O.reverse_complement(s)
+
+
+def test_c5_sharded_count_and_gc(cuda_device):
+    """C5 (byte-range shards, COUNT + gc_content): eight shards cut at arbitrary bytes agree on record-aligned bounds
+    from their exchanged states (dist.fastq_record_bounds: newline counts give the exact phase), every shard then
+    scans its own records IN PLACE (unaligned `begin`), and COUNT / SUM(len) / SUM(#GC) add up to the single-shot
+    scan exactly, AVG(gc_content) to within float summation order."""
+    import torch
+    from exon_duckdb_b200 import _lib, device as D, dist
+
+    reads = max(80_000, int(6_000_000 * SCALE))
+    G = 8
+    buf = D.gen_device(_lib.gen_params("illumina", reads, seed=20), cuda_device)
+    n = buf.numel()
+    whole = D.fastq_scan_sync(buf, _lib.F_SEQ, rec_cap=reads + 1024)
+    assert whole.validate() == reads
+    agg, _ = D.fastq_filter(whole, reads, [])
+    want = agg.cpu().tolist()[:3]
+    want_gc = float(D.gc_from_counts(whole.seq_len, whole.gc, reads).double().sum())
+    del whole, agg
+    _free(torch)
+
+    los = [dist.byte_range(n, k, G)[0] & ~15 for k in range(G)] + [n]
+    states = []
+    for k in range(G):
+        lo, hi = los[k], los[k + 1]
+        begin = 0 if k == 0 else dist.HALO
+        states.append(dist.fastq_shard_state(dist.Shard(buf[lo - begin:hi], lo, hi, begin, k == G - 1)))
+    bounds = dist.fastq_record_bounds(states, n)
+    assert bounds[0] == 0 and bounds[-1] == n and bounds == sorted(bounds)
+    assert all(los[k] <= bounds[k] < los[k] + 400 for k in range(G))  # the next record starts within one record's length
+    got = [0, 0, 0]
+    got_gc = 0.0
+    for k in range(G):
+        a, b = bounds[k], bounds[k + 1]
+        if a == b:
+            continue
+        s = D.fastq_scan_sync(buf, _lib.F_SEQ, begin=a, n=b)
+        nrec = s.validate()
+        part, _ = D.fastq_filter(s, nrec, [])
+        got = [x + y for x, y in zip(got, part.cpu().tolist()[:3])]
+        got_gc += float(D.gc_from_counts(s.seq_len, s.gc, nrec).double().sum())
+        del s, part
+    assert got == want == [reads, 150 * reads, want[2]]
+    assert abs(got_gc - want_gc) <= 1e-9 * reads
