@@ -343,13 +343,14 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
                 }
                 const int nw = len >> 2, bs = (src & 3) * 8, sw = src >> 2;
                 const uint32_t ow = out_u32 + (uint32_t)dst;
-                if (bs == 0) {
-                    for (int k = 0; k < nw; k++) fa_sts32(ow + 4u * (uint32_t)k, src_word(sw + k));
-                } else if (nw > 0) {
-                    // the last byte copied lies in word sw + nw of the row, so every word read below exists
+                if (nw > 0) {
+                    // ONE loop for aligned and unaligned sources (the lanes of a warp mix both: two loops ran one after
+                    // the other).  bs != 0: the last byte copied lies in word sw + nw, so every word read exists; bs == 0:
+                    // the funnel shift returns w0 and the look-ahead word, clamped into the row, is never used.
                     uint32_t w0 = src_word(sw);
                     for (int k = 0; k < nw; k++) {
-                        const uint32_t w1 = src_word(sw + k + 1);
+                        const int nx = sw + k + 1;
+                        const uint32_t w1 = src_word(nx < 31 ? nx : 31);
                         fa_sts32(ow + 4u * (uint32_t)k, __funnelshift_r(w0, w1, bs));
                         w0 = w1;
                     }
