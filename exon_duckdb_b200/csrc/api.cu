@@ -78,6 +78,15 @@ int carve_bytes(void* ws, int64_t ws_bytes, int64_t payload, cudaStream_t st, Wo
 int carve(void* ws, int64_t ws_bytes, int64_t n_tiles, cudaStream_t st, Workspace* out) {
     return carve_bytes(ws, ws_bytes, n_tiles * (int64_t)sizeof(TileSlot), st, out);
 }
+// The chain-free scans write every word of their scratch before reading it: same layout, no memset launch.
+int carve_scan(void* ws, int64_t ws_bytes, int64_t payload, Workspace* out) {
+    const int64_t need = WS_HEADER + payload;
+    if (!ws || ws_bytes < need) return set_err(EXB_ERR_ARG, "workspace too small: need %lld bytes, have %lld", (long long)need, (long long)ws_bytes);
+    out->result = reinterpret_cast<ScanResult*>(ws);
+    out->ticket = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + 128);
+    out->slots = reinterpret_cast<TileSlot*>(reinterpret_cast<uint8_t*>(ws) + WS_HEADER);
+    return 0;
+}
 
 
 // ---------------------------------------------------------------- generators
@@ -260,7 +269,7 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
         if (e != cudaSuccess) return cuda_fail(e, "fastq_tile launch");
         // global line index of every tile
         Workspace w;
-        int rc = carve(ws + WS_HEADER, L.scan_ws, scan_tiles(a.n_tiles), st, &w);
+        int rc = carve_scan(ws + WS_HEADER, L.scan_ws, scan_tiles(a.n_tiles) * 8, &w);
         if (rc) return rc;
         e = exclusive_scan_launch_u32(a.tile_cnt, a.n_tiles, line_base, w.slots, w.ticket, st);
         if (e != cudaSuccess) return cuda_fail(e, "line offset scan launch");
@@ -410,7 +419,7 @@ int exb_fastq_fields(const void* d_buf, int64_t begin, int64_t n, const void* d_
 int exb_exclusive_scan_u32(const uint32_t* d_in, int64_t n, int64_t* d_out, void* d_workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     Workspace w;
-    int rc = carve(d_workspace, workspace_bytes, scan_tiles(n), st, &w);
+    int rc = carve_scan(d_workspace, workspace_bytes, scan_tiles(n) * 8, &w);
     if (rc) return rc;
     cudaError_t e = exclusive_scan_launch_u32(d_in, n, d_out, w.slots, w.ticket, st);
     if (e != cudaSuccess) return cuda_fail(e, "exclusive_scan launch");
@@ -422,7 +431,7 @@ int exb_exclusive_scan_u32_multi(const uint32_t* d_in, int64_t n, int cols, int6
     cudaStream_t st = (cudaStream_t)stream;
     if (cols < 1 || cols > 8) return set_err(EXB_ERR_ARG, "exb_exclusive_scan_u32_multi: cols must be 1..8");
     Workspace w;  // chains are one 8-byte word per tile and column, packed column after column; tickets sit in the header
-    int rc = carve_bytes(d_workspace, workspace_bytes, (int64_t)cols * scan_tiles(n) * 8 + 64, st, &w);
+    int rc = carve_scan(d_workspace, workspace_bytes, (int64_t)cols * scan_tiles(n) * 8 + 64, &w);
     if (rc) return rc;
     cudaError_t e = exclusive_scan_launch_u32_multi(d_in, n, cols, in_stride, d_out, out_stride, w.slots, w.ticket, st);
     if (e != cudaSuccess) return cuda_fail(e, "exclusive_scan launch");
@@ -433,7 +442,7 @@ int exb_select_rows(const uint8_t* d_pass, int64_t n, int64_t* d_offsets, int64_
                     void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     Workspace w;
-    int rc = carve(d_workspace, workspace_bytes, scan_tiles(n), st, &w);
+    int rc = carve_scan(d_workspace, workspace_bytes, scan_tiles(n) * 8, &w);
     if (rc) return rc;
     cudaError_t e = exclusive_scan_launch_u8(d_pass, n, d_offsets, w.slots, w.ticket, st);
     if (e != cudaSuccess) return cuda_fail(e, "exclusive_scan launch");

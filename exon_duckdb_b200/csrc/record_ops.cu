@@ -386,9 +386,9 @@ struct SrcFastq {  // field `col` of the selected FASTQ records
 __device__ __forceinline__ uint4 load16_unaligned(const uint8_t* __restrict__ src) {
     const int bs = (int)((uintptr_t)src & 3) * 8;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(src - (bs >> 3));
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-    if (bs == 0) return make_uint4(w0, w1, w2, w3);
-    const uint32_t w4 = w[4];
+    // no branch on bs: the lanes of a warp mix aligned and unaligned sources, and funnelshift_r(x, y, 0) = x (the fifth
+    // word is then read and ignored: 4 bytes into the slack every input buffer carries)
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
     return make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
 }
 
