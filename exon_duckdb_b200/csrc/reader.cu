@@ -116,6 +116,169 @@ struct ZstdLib {
     }
 };
 
+// bzip2 and xz the same way (FileCompressionType::BZIP2 / XZ of datafusion 28: reachable through the `compression`
+// option only, arrow_reader.rs:60-91 infers nothing but gz / zst from the file name).  Public, stable C APIs of
+// libbz2 1.0 (bzlib.h) and liblzma 5 (lzma/base.h); LZMA_STREAM_INIT is all zeros and the struct is over-allocated.
+struct Bz2Stream {
+    char* next_in; unsigned int avail_in, total_in_lo32, total_in_hi32;
+    char* next_out; unsigned int avail_out, total_out_lo32, total_out_hi32;
+    void* state; void* (*bzalloc)(void*, int, int); void (*bzfree)(void*, void*); void* opaque;
+};
+struct XzStream {
+    const uint8_t* next_in; size_t avail_in; uint64_t total_in;
+    uint8_t* next_out; size_t avail_out; uint64_t total_out;
+    const void* allocator; void* internal; void* reserved_ptr[4]; uint64_t reserved_int[2]; size_t reserved_size[2]; int reserved_enum[2];
+    uint8_t slack[64];
+};
+struct Bz2Lib {
+    int (*init)(Bz2Stream*, int, int) = nullptr;
+    int (*run)(Bz2Stream*) = nullptr;
+    int (*end)(Bz2Stream*) = nullptr;
+    bool ok = false;
+    static const Bz2Lib& get() {
+        static Bz2Lib L = [] {
+            Bz2Lib l;
+            void* h = dlopen("libbz2.so.1.0", RTLD_NOW | RTLD_LOCAL);
+            if (!h) h = dlopen("libbz2.so.1", RTLD_NOW | RTLD_LOCAL);
+            if (!h) return l;
+            l.init = reinterpret_cast<int (*)(Bz2Stream*, int, int)>(dlsym(h, "BZ2_bzDecompressInit"));
+            l.run = reinterpret_cast<int (*)(Bz2Stream*)>(dlsym(h, "BZ2_bzDecompress"));
+            l.end = reinterpret_cast<int (*)(Bz2Stream*)>(dlsym(h, "BZ2_bzDecompressEnd"));
+            l.ok = l.init && l.run && l.end;
+            return l;
+        }();
+        return L;
+    }
+};
+struct XzLib {
+    int (*init)(XzStream*, uint64_t, uint32_t) = nullptr;
+    int (*code)(XzStream*, int) = nullptr;
+    void (*end)(XzStream*) = nullptr;
+    bool ok = false;
+    static const XzLib& get() {
+        static XzLib L = [] {
+            XzLib l;
+            void* h = dlopen("liblzma.so.5", RTLD_NOW | RTLD_LOCAL);
+            if (!h) return l;
+            l.init = reinterpret_cast<int (*)(XzStream*, uint64_t, uint32_t)>(dlsym(h, "lzma_stream_decoder"));
+            l.code = reinterpret_cast<int (*)(XzStream*, int)>(dlsym(h, "lzma_code"));
+            l.end = reinterpret_cast<void (*)(XzStream*)>(dlsym(h, "lzma_end"));
+            l.ok = l.init && l.code && l.end;
+            return l;
+        }();
+        return L;
+    }
+};
+
+// One streaming decoder behind the IO thread: consume in[ipos, isize), produce out[opos, ocap).  in_stream() is true while
+// a compressed stream is open (end of file then = truncated input); concatenated streams / frames simply continue.
+struct Decoder {
+    virtual ~Decoder() {}
+    virtual bool step(const uint8_t* in, size_t isize, size_t& ipos, uint8_t* out, size_t ocap, size_t& opos, std::string& err) = 0;
+    virtual bool in_stream() const = 0;
+    virtual const char* name() const = 0;
+};
+struct ZstdDecoder : Decoder {
+    void* ds = nullptr;
+    bool open_ = false;
+    bool init(std::string& err) {
+        const ZstdLib& Z = ZstdLib::get();
+        if (!Z.ok) { err = "zstd input needs the system's libzstd.so.1, which could not be loaded"; return false; }
+        if (!(ds = Z.create()) || Z.is_error(Z.init(ds))) { err = "could not create a zstd decoder"; return false; }
+        return true;
+    }
+    ~ZstdDecoder() override { if (ds) ZstdLib::get().destroy(ds); }
+    bool step(const uint8_t* in, size_t isize, size_t& ipos, uint8_t* out, size_t ocap, size_t& opos, std::string& err) override {
+        const ZstdLib& Z = ZstdLib::get();
+        ZstdIn zin{in, isize, ipos};
+        ZstdOut zout{out, ocap, opos};
+        const size_t r = Z.decompress(ds, &zout, &zin);  // 0 = a frame ended; the next call starts the next frame
+        if (Z.is_error(r)) { err = std::string("zstd: ") + Z.error_name(r); return false; }
+        open_ = r != 0;
+        ipos = zin.pos;
+        opos = zout.pos;
+        return true;
+    }
+    bool in_stream() const override { return open_; }
+    const char* name() const override { return "zstd"; }
+};
+struct Bz2Decoder : Decoder {
+    Bz2Stream st;
+    bool live = false, open_ = false;
+    Bz2Decoder() { memset(&st, 0, sizeof(st)); }
+    bool init(std::string& err) {
+        if (!Bz2Lib::get().ok) { err = "bzip2 input needs the system's libbz2.so.1.0, which could not be loaded"; return false; }
+        return true;
+    }
+    ~Bz2Decoder() override { if (live) Bz2Lib::get().end(&st); }
+    bool step(const uint8_t* in, size_t isize, size_t& ipos, uint8_t* out, size_t ocap, size_t& opos, std::string& err) override {
+        const Bz2Lib& B = Bz2Lib::get();
+        if (!live) {  // first stream, or the one after a stream that ended (bzip2 files may be concatenated)
+            memset(&st, 0, sizeof(st));
+            if (B.init(&st, 0, 0) != 0) { err = "could not create a bzip2 decoder"; return false; }
+            live = true;
+        }
+        const size_t ni = std::min<size_t>(isize - ipos, 1u << 30), no = std::min<size_t>(ocap - opos, 1u << 30);
+        st.next_in = reinterpret_cast<char*>(const_cast<uint8_t*>(in + ipos));
+        st.avail_in = (unsigned)ni;
+        st.next_out = reinterpret_cast<char*>(out + opos);
+        st.avail_out = (unsigned)no;
+        const int r = B.run(&st);
+        if (r != 0 && r != 4) { err = "bzip2: corrupt input (code " + std::to_string(r) + ")"; return false; }  // BZ_OK / BZ_STREAM_END
+        if (ni - st.avail_in > 0 || no - st.avail_out > 0) open_ = true;
+        ipos += ni - st.avail_in;
+        opos += no - st.avail_out;
+        if (r == 4) {
+            B.end(&st);
+            live = false;
+            open_ = false;
+        }
+        return true;
+    }
+    bool in_stream() const override { return open_; }
+    const char* name() const override { return "bzip2"; }
+};
+struct XzDecoder : Decoder {
+    XzStream st;
+    bool live = false, open_ = false;
+    XzDecoder() { memset(&st, 0, sizeof(st)); }
+    bool init(std::string& err) {
+        if (!XzLib::get().ok) { err = "xz input needs the system's liblzma.so.5, which could not be loaded"; return false; }
+        return true;
+    }
+    ~XzDecoder() override { if (live) XzLib::get().end(&st); }
+    bool step(const uint8_t* in, size_t isize, size_t& ipos, uint8_t* out, size_t ocap, size_t& opos, std::string& err) override {
+        const XzLib& X = XzLib::get();
+        if (!live) {
+            while (ipos < isize && in[ipos] == 0) ipos++;  // stream padding between concatenated .xz streams
+            if (ipos == isize) return true;
+            memset(&st, 0, sizeof(st));
+            if (X.init(&st, ~0ull, 0) != 0) { err = "could not create an xz decoder"; return false; }
+            live = true;
+        }
+        st.next_in = in + ipos;
+        st.avail_in = isize - ipos;
+        st.next_out = out + opos;
+        st.avail_out = ocap - opos;
+        const int r = X.code(&st, 0 /* LZMA_RUN */);
+        const size_t used = (isize - ipos) - st.avail_in, made = (ocap - opos) - st.avail_out;
+        // LZMA_OK 0, STREAM_END 1, NO_CHECK 2, UNSUPPORTED_CHECK 3, GET_CHECK 4 carry on; BUF_ERROR 10 = "nothing to do with what
+        // it was given", harmless when it only means that more input is needed
+        if (r > 4 && !(r == 10 && used == 0 && made == 0)) { err = "xz: corrupt input (code " + std::to_string(r) + ")"; return false; }
+        if (used || made) open_ = true;
+        ipos += used;
+        opos += made;
+        if (r == 1) {
+            X.end(&st);
+            live = false;
+            open_ = false;
+        }
+        return true;
+    }
+    bool in_stream() const override { return open_; }
+    const char* name() const override { return "xz"; }
+};
+
 // ------------------------------------------------------------------ filter expressions
 namespace {
 
@@ -585,10 +748,10 @@ struct Reader {
             const int comp = file_comp[fi];
             int fd = -1;
             gzFile gz = nullptr;
-            FILE* zf = nullptr;  // zstd: compressed file, decoder, its input window
-            void* zds = nullptr;
+            FILE* zf = nullptr;  // zstd / bzip2 / xz: compressed file, decoder, its input window [zpos, zsize) of zbuf
+            std::unique_ptr<Decoder> dec;
             std::vector<uint8_t> zbuf;
-            ZstdIn zin{nullptr, 0, 0};
+            size_t zpos = 0, zsize = 0;
             std::string err;
             if (comp == 1) {
                 gz = gzopen(path.c_str(), "rb");
@@ -597,15 +760,21 @@ struct Reader {
             } else if (comp == 0) {
                 fd = open(path.c_str(), O_RDONLY);
                 if (fd < 0) err = "could not open " + path;
-            } else if (comp == 2) {
-                const ZstdLib& Z = ZstdLib::get();
-                if (!Z.ok) err = "zstd input needs the system's libzstd.so.1, which could not be loaded";
-                else if (!(zf = fopen(path.c_str(), "rb"))) err = "could not open " + path;
-                else if (!(zds = Z.create()) || Z.is_error(Z.init(zds))) err = "could not create a zstd decoder";
+            } else if (comp >= 2 && comp <= 4) {
+                if (comp == 2) {
+                    std::unique_ptr<ZstdDecoder> d(new ZstdDecoder());
+                    if (d->init(err)) dec = std::move(d);
+                } else if (comp == 3) {
+                    std::unique_ptr<Bz2Decoder> d(new Bz2Decoder());
+                    if (d->init(err)) dec = std::move(d);
+                } else {
+                    std::unique_ptr<XzDecoder> d(new XzDecoder());
+                    if (d->init(err)) dec = std::move(d);
+                }
+                if (err.empty() && !(zf = fopen(path.c_str(), "rb"))) err = "could not open " + path;
                 zbuf.resize(1 << 20);
-                zin = ZstdIn{zbuf.data(), 0, 0};
             } else {
-                err = "compression of " + path + " is not supported by this build (gzip, zstd and uncompressed are)";
+                err = "compression of " + path + " is not supported by this build";
             }
             int64_t pos = 0;
             bool eof = false;
@@ -634,27 +803,29 @@ struct Reader {
                         if (g == 0) break;
                         got += g;
                     }
-                } else if (zds) {
-                    const ZstdLib& Z = ZstdLib::get();
-                    bool in_frame = false;  // the decoder still holds state of an unfinished frame
+                } else if (dec) {
                     while (got < want) {
-                        if (zin.pos == zin.size) {
+                        if (zpos == zsize) {
                             const size_t n = fread(zbuf.data(), 1, zbuf.size(), zf);
                             if (n == 0) {
                                 if (ferror(zf)) err = "read error in " + path;
-                                else if (in_frame) err = "truncated zstd frame in " + path;
+                                else if (dec->in_stream()) err = std::string("truncated ") + dec->name() + " stream in " + path;
                                 break;  // end of the compressed file
                             }
-                            zin = ZstdIn{zbuf.data(), n, 0};
+                            zpos = 0;
+                            zsize = n;
                         }
-                        ZstdOut zout{dst + got, (size_t)(want - got), 0};
-                        const size_t r = Z.decompress(zds, &zout, &zin);  // 0 = a frame ended; concatenated frames just continue
-                        if (Z.is_error(r)) {
-                            err = std::string("zstd: ") + Z.error_name(r) + " in " + path;
+                        size_t opos = (size_t)got;
+                        const size_t ipos0 = zpos;
+                        if (!dec->step(zbuf.data(), zsize, zpos, dst, (size_t)want, opos, err)) {
+                            err += " in " + path;
                             break;
                         }
-                        in_frame = r != 0;
-                        got += (int64_t)zout.pos;
+                        if (zpos == ipos0 && opos == (size_t)got && zpos < zsize) {  // no progress with input and room available
+                            err = std::string(dec->name()) + ": decoder stalled in " + path;
+                            break;
+                        }
+                        got = (int64_t)opos;
                     }
                 } else {
                     bool bad = false;
@@ -682,7 +853,7 @@ struct Reader {
             }
             if (fd >= 0) close(fd);
             if (gz) gzclose(gz);
-            if (zds) ZstdLib::get().destroy(zds);
+            dec.reset();
             if (zf) fclose(zf);
             if (!err.empty()) {
                 Block b;
@@ -1280,7 +1451,7 @@ static Reader* open_reader(const char* uri, uintptr_t batch_size, const char* co
     if (S_ISDIR(sb.st_mode)) {
         // listing table: every file whose name carries the format's extension (+ the codec's)
         std::vector<std::string> exts = ft == 1 ? std::vector<std::string>{".fasta", ".fa", ".fna"} : std::vector<std::string>{".fastq", ".fq"};
-        const char* csuf = comp == 1 ? ".gz" : (comp == 2 ? ".zst" : "");
+        const char* csuf = comp == 1 ? ".gz" : (comp == 2 ? ".zst" : (comp == 3 ? ".bz2" : (comp == 4 ? ".xz" : "")));
         DIR* d = opendir(u.c_str());
         if (!d) {
             *err = "could not list " + u;
@@ -1305,11 +1476,6 @@ static Reader* open_reader(const char* uri, uintptr_t batch_size, const char* co
         r->files.push_back(u);
         r->file_comp.push_back(comp);
     }
-    for (int c : r->file_comp)
-        if (c > 2) {
-            *err = "could not register table: bzip2 / xz input is not supported by this build";
-            return nullptr;
-        }
 
     if (filters && filters[0]) {
         std::string f(filters);

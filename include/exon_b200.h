@@ -109,8 +109,10 @@ typedef struct ReplacementScanResult {
  * Open `uri` (a local file or a directory of files) as an Arrow stream of
  * record batches of at most `batch_size` rows (the reference passes 2048).
  *   compression: NULL = infer from the last '.'-suffix ("gz" / "zst"), else
- *                "gzip" / "zstd" / anything else = uncompressed
- *                (arrow_reader.rs:60-91).
+ *                "gzip" | "gz", "zstd" | "zst", "bzip2" | "bz2", "xz" (datafusion 28
+ *                FileCompressionType::from_str, case-insensitive); anything else =
+ *                uncompressed (arrow_reader.rs:60-91).  gzip through zlib; zstd, bzip2
+ *                and xz through the system's shared libraries, bound at run time.
  *   file_format: "fasta" or "fastq" (case-insensitive).
  *   filters:     NULL / "" or the predicate text produced by the reference's
  *                FilterToString (module.cpp:158-214): `col<op>'const'` terms

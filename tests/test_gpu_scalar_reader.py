@@ -204,6 +204,34 @@ def test_reader_zstd(cuda_device, tmp_path, golden_dir, monkeypatch):
     assert "zstd" in str(ei.value)
 
 
+@pytest.mark.parametrize("codec", ["bzip2", "xz"])
+def test_reader_bzip2_and_xz(cuda_device, tmp_path, monkeypatch, codec):
+    """FileCompressionType::BZIP2 / XZ of the reference's reader (datafusion 28), reachable through the `compression`
+    option: one stream, two concatenated streams, several device blocks, and a truncated file."""
+    import bz2
+    import lzma
+    from oracle import oracle as O
+    comp = bz2.compress if codec == "bzip2" else lzma.compress
+    text, _ = util.random_fastq(21, 4000, tricky=False)
+    monkeypatch.setenv("EXON_B200_CHUNK_BYTES", "150000")
+    p = tmp_path / "x.fastq.cmp"
+    p.write_bytes(comp(text))
+    assert _rows(_read(str(p), "fastq", compression=codec.encode())) == O.parse_fastq(text).rows()
+    cut = text.rfind(b"\n@", 0, len(text) // 2) + 1
+    q = tmp_path / "two.fastq.cmp"
+    q.write_bytes(comp(text[:cut]) + comp(text[cut:]))
+    assert _rows(_read(str(q), "fastq", compression=codec.encode())) == O.parse_fastq(text).rows()
+    fa, _ = util.random_fasta(22, 300, max_len=2000, tricky=False)
+    f = tmp_path / "x.fasta.cmp"
+    f.write_bytes(comp(fa))
+    assert _rows(_read(str(f), "fasta", compression=(b"BZ2" if codec == "bzip2" else b"XZ"))) == O.parse_fasta(fa).rows()
+    t = tmp_path / "trunc.fastq.cmp"
+    t.write_bytes(p.read_bytes()[: p.stat().st_size // 2])
+    with pytest.raises(Exception) as ei:
+        _read(str(t), "fastq", compression=codec.encode())
+    assert codec in str(ei.value) or "unexpected EOF" in str(ei.value)
+
+
 @pytest.mark.parametrize("chunk", [None, 4096, 70000])
 def test_reader_chunk_carry_fastq(cuda_device, tmp_path, monkeypatch, chunk):
     """Records straddling chunk edges are re-read with the next chunk; tiny chunks force that on every record."""
