@@ -77,8 +77,15 @@ public:
 	exb_batch batch;
 };
 
+// what ArrowScanLocalState::batch_index is to the reference (arrow.hpp, ArrowGetBatchIndex): the position of the chunk a
+// thread is holding in the order of the file, so that order-preserving sinks (batch collector, LIMIT, COPY) can run
+struct ScanLocalState : public LocalTableFunctionState {
+	idx_t batch_index = 0;
+};
+
 struct ScanGlobalState : public GlobalTableFunctionState {
 	std::mutex lock;
+	idx_t next_batch = 0;
 	exb_reader *reader = nullptr;
 	vector<column_t> column_ids;
 	bool count_only = false;
@@ -203,6 +210,9 @@ static void ScanFunction(ClientContext &context, TableFunctionInput &input, Data
 	std::lock_guard<std::mutex> guard(state.lock);
 	if (state.done) {
 		return;
+	}
+	if (input.local_state) {
+		input.local_state->Cast<ScanLocalState>().batch_index = state.next_batch++;
 	}
 	if (state.count_only) {
 		const idx_t n = (idx_t)MinValue<int64_t>(STANDARD_VECTOR_SIZE, state.count_left);
@@ -402,8 +412,26 @@ static void ScanPushdownComplexFilter(ClientContext &context, LogicalGet &get, F
 	}
 }
 
+static unique_ptr<LocalTableFunctionState> ScanInitLocal(ExecutionContext &context, TableFunctionInitInput &input,
+                                                        GlobalTableFunctionState *global_state) {
+	return make_uniq<ScanLocalState>();
+}
+
+// ArrowScanCardinality (arrow.cpp): unknown -- the row count of a text file is not known before it is read
+static unique_ptr<NodeStatistics> ScanCardinality(ClientContext &context, const FunctionData *bind_data) {
+	return make_uniq<NodeStatistics>();
+}
+
+// ArrowGetBatchIndex (arrow.cpp)
+static idx_t ScanGetBatchIndex(ClientContext &context, const FunctionData *bind_data, LocalTableFunctionState *local_state,
+                               GlobalTableFunctionState *global_state) {
+	return local_state->Cast<ScanLocalState>().batch_index;
+}
+
 static void RegisterScan(ClientContext &context, const string &name, const string &file_type) {
-	TableFunction scan(name, {LogicalType::VARCHAR}, ScanFunction, ScanBind, ScanInitGlobal);
+	TableFunction scan(name, {LogicalType::VARCHAR}, ScanFunction, ScanBind, ScanInitGlobal, ScanInitLocal);
+	scan.cardinality = ScanCardinality;        // module.cpp:307
+	scan.get_batch_index = ScanGetBatchIndex;  // module.cpp:308
 	scan.function_info = make_shared<ScanInfo>(file_type);
 	scan.named_parameters["compression"] = LogicalType::VARCHAR;
 	scan.projection_pushdown = true;

@@ -258,6 +258,26 @@ def _write(tmp_path, name, data):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("ext", [PRODUCT, REFGLUE], ids=["product", "refglue"])
+def test_file_order_survives_order_preserving_sinks(cuda_device, tmp_path, ext):
+    """get_batch_index / cardinality are registered like the reference's (module.cpp:307-308): with several DuckDB threads,
+    CREATE TABLE AS, LIMIT / OFFSET and rowid see the records in file order."""
+    from oracle import oracle as O
+    text, _ = util.random_fastq(17, 9000, min_len=1, max_len=120, tricky=False)
+    path = _write(tmp_path, "order.fastq", text)
+    names = [x.decode("latin-1") for x in O.parse_fastq(text).strings("name")]
+    r = run_sql(ext, [
+        "CREATE TABLE t AS SELECT name FROM read_fastq('%s')" % path,
+        "SELECT name FROM t WHERE rowid IN (0, 2047, 2048, 4999, 8999) ORDER BY rowid",
+        "SELECT name FROM read_fastq('%s') LIMIT 3 OFFSET 6000" % path,
+        "SELECT count(*) FROM t",
+    ], threads=4, env={"EXON_B200_CHUNK_BYTES": str(100_000)})
+    assert rows(r[1]) == [[names[i]] for i in (0, 2047, 2048, 4999, 8999)]
+    assert rows(r[2]) == [[n] for n in names[6000:6003]]
+    assert rows(r[3]) == [["9000"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ext", [PRODUCT, REFGLUE], ids=["product", "refglue"])
 def test_fastq_rows_filters_and_projection(cuda_device, tmp_path, ext):
     """A multi-chunk synthetic file through DuckDB: every row, projections, simple + complex filters, COUNT(*), vs the oracle."""
     from oracle import oracle as O
