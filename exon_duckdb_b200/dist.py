@@ -114,10 +114,6 @@ class PeerGroup(TorchGroup):
         import torch.distributed._symmetric_memory as symm_mem
 
         torch, dist = self.torch, self.dist
-        try:  # needed by older torch releases, a deprecated no-op in newer ones
-            symm_mem.enable_symm_mem_for_group((group if group is not None else dist.group.WORLD).group_name)
-        except Exception:
-            pass
         nbytes = int(_lib.lib().exb_peer_bytes())
         self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
         self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
