@@ -726,6 +726,42 @@ __device__ __forceinline__ long long gc_count_range(const uint8_t* __restrict__ 
     return cnt;
 }
 
+// the same count for one thread's own row, in 16-byte aligned chunks (half as many load instructions as 8-byte words)
+__device__ __forceinline__ long long gc_count_row16(const uint8_t* __restrict__ data, int64_t s, int64_t e) {
+    const uintptr_t a0 = (uintptr_t)(data + s) & ~(uintptr_t)15;
+    const int lead = (int)((uintptr_t)(data + s) & 15);
+    const int64_t nbytes = lead + (e - s);
+    const int64_t nch = (nbytes + 15) >> 4;
+    const uint4* __restrict__ base = reinterpret_cast<const uint4*>(a0);
+    long long cnt = 0;
+    for (int64_t i = 0; i < nch; i++) {
+        const uint4 v = base[i];
+        uint32_t m = (gc_bytes(v.x) >> 7) | (gc_bytes(v.y) >> 6) | (gc_bytes(v.z) >> 5) | (gc_bytes(v.w) >> 4);  // 16 flag bits, any order
+        // bit layout: word k's byte b sits at bit 8 b + k; mask the bytes outside [lead, nbytes) of the first / last chunk
+        if (i == 0 && lead) {
+            uint32_t keep = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (4 * k + b >= lead) keep |= 1u << (8 * b + k);
+            m &= keep;
+        }
+        if (i == nch - 1 && (nbytes & 15)) {
+            const int last = (int)(nbytes & 15);
+            uint32_t keep = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (4 * k + b < last) keep |= 1u << (8 * b + k);
+            m &= keep;
+        }
+        cnt += __popc(m);
+    }
+    return cnt;
+}
+
 // One THREAD per row for rows up to GC_THREAD_ROW bytes (a warp's 32 rows are adjacent in the column, so its loads
 // stay inside a few cache lines); longer rows are handed to the whole warp afterwards.
 constexpr int64_t GC_THREAD_ROW = 1024;
@@ -744,7 +780,7 @@ __global__ void __launch_bounds__(256) gc_content_kernel(const int64_t* __restri
         const int64_t len = e - s;
         const bool is_long = len > GC_THREAD_ROW;
         if (r < n_rows && !is_long) {
-            const long long cnt = len > 0 ? gc_count_range(data, s, e, 0, 1) : 0;
+            const long long cnt = len > 0 ? gc_count_row16(data, s, e) : 0;
             out[r] = len == 0 ? 0.0f : __fdiv_rn(__ll2float_rn(cnt), __ll2float_rn((long long)len));
         }
         uint32_t longs = __ballot_sync(0xffffffffu, is_long);
