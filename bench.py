@@ -133,6 +133,7 @@ def run_reference(args):
     import numpy as np
     from exon_duckdb_b200 import _lib
     from oracle import oracle as O
+    from tools import synth
     L = _lib.lib()
     O.lib()
     cores = max(1, min(os.cpu_count() or 1, 64))
@@ -140,14 +141,14 @@ def run_reference(args):
     per_thread = int(os.environ.get("EXB_REF_READS_PER_THREAD", "1500000"))
     shards = []
     for t in range(cores):
-        p = _lib.gen_params("illumina", per_thread, seed=SEED, first_record=t * per_thread, len_min=READ_LEN, len_max=READ_LEN)
-        n = L.exb_gen_size(C.byref(p))
+        p = synth.gen_params("illumina", per_thread, seed=SEED, first_record=t * per_thread, len_min=READ_LEN, len_max=READ_LEN)
+        n = synth.gen_size(p)
         a = np.empty(n, np.uint8)
         shards.append((p, a, n))
     # generation is outside the timed region; do it threaded as well
     def gen(i):
         p, a, n = shards[i]
-        L.exb_gen_host(C.byref(p), a.ctypes.data, n)
+        synth.lib().exb_gen_host(C.byref(p), a.ctypes.data, n)
     ths = [threading.Thread(target=gen, args=(i,)) for i in range(cores)]
     [t.start() for t in ths]
     [t.join() for t in ths]
@@ -203,6 +204,7 @@ def main():
     import torch.distributed as dist
 
     from exon_duckdb_b200 import _lib, device as D
+    from tools import synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,8 +229,8 @@ def main():
     preds = [("mean_quality", ">", THRESH)]
     sharded = None
     if world == 1:
-        p = _lib.gen_params("illumina", args.reads, seed=SEED, first_record=0, len_min=READ_LEN, len_max=READ_LEN)
-        buf = D.gen_device(p, dev)
+        p = synth.gen_params("illumina", args.reads, seed=SEED, first_record=0, len_min=READ_LEN, len_max=READ_LEN)
+        buf = synth.gen_device(p, dev)
         n_bytes = buf.numel()
         # COUNT(*) + a predicate on the quality line: scan and filter run as ONE kernel (exb_fastq_scan_filter);
         # projection push-down means nothing per record is written at all.
@@ -254,8 +256,8 @@ def main():
         R = args.reads
 
         def rec_size(i):
-            q = _lib.gen_params("illumina", 1, seed=SEED, first_record=i, len_min=READ_LEN, len_max=READ_LEN)
-            return L.exb_gen_size(C.byref(q))
+            q = synth.gen_params("illumina", 1, seed=SEED, first_record=i, len_min=READ_LEN, len_max=READ_LEN)
+            return synth.gen_size(q)
 
         def delta(k):  # offset of shard k's first byte inside record k*R; local offset of that byte is a multiple of 16
             if k == 0:
@@ -265,8 +267,8 @@ def main():
 
         first = rank * R - (1 if rank else 0)
         count = R + (1 if rank else 0) + (1 if rank < world - 1 else 0)
-        p = _lib.gen_params("illumina", count, seed=SEED, first_record=first, len_min=READ_LEN, len_max=READ_LEN)
-        gbuf = D.gen_device(p, dev)
+        p = synth.gen_params("illumina", count, seed=SEED, first_record=first, len_min=READ_LEN, len_max=READ_LEN)
+        gbuf = synth.gen_device(p, dev)
         s_prev = rec_size(rank * R - 1) if rank else 0
         s_next = rec_size((rank + 1) * R) if rank < world - 1 else 0
         own = gbuf.numel() - s_prev - s_next  # bytes of records [rank*R, (rank+1)*R)
@@ -402,8 +404,8 @@ def main():
         sample_reads = min(args.reads, 8_000_000)
         if host_ptr:
             # cut the sample at a record boundary: the records are generated in order, so re-measure its size
-            q = _lib.gen_params("illumina", sample_reads, seed=SEED, first_record=0, len_min=READ_LEN, len_max=READ_LEN)
-            sample_bytes = L.exb_gen_size(C.byref(q)) if sample_reads < args.reads else n_bytes
+            q = synth.gen_params("illumina", sample_reads, seed=SEED, first_record=0, len_min=READ_LEN, len_max=READ_LEN)
+            sample_bytes = synth.gen_size(q) if sample_reads < args.reads else n_bytes
             sample = host[:sample_bytes]
         else:
             sample = buf[:0].cpu().numpy()

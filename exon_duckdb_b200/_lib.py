@@ -14,7 +14,6 @@ F_LINES, F_SEQ, F_QUAL = 1, 2, 4
 P_MEAN_QUALITY, P_GC_CONTENT, P_SEQ_LEN, P_QUAL_LEN = 0, 1, 2, 3
 OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "=": 4, "==": 4, "!=": 5, "<>": 5}
 MAP_REVERSE_COMPLEMENT, MAP_COMPLEMENT, MAP_TRANSCRIBE, MAP_REVERSE_TRANSCRIBE = 0, 1, 2, 3
-GEN_FASTA, GEN_ILLUMINA, GEN_ONT = 1, 2, 4
 ERR_CUDA, ERR_ARG, ERR_FORMAT, ERR_CAPACITY, ERR_IO, ERR_INVALID_CHAR = -1, -2, -3, -4, -5, -6
 NO_POS = 0xFFFFFFFFFFFFFFFF
 
@@ -40,19 +39,6 @@ class Predicate(C.Structure):
     _fields_ = [("field", C.c_int32), ("op", C.c_int32), ("value", C.c_double)]
 
 
-class GenParams(C.Structure):
-    _fields_ = [
-        ("kind", C.c_int32),
-        ("seed", C.c_uint64),
-        ("n_records", C.c_int64),
-        ("first_record", C.c_int64),
-        ("len_min", C.c_int32),
-        ("len_max", C.c_int32),
-        ("wrap", C.c_int32),
-        ("crlf", C.c_int32),
-    ]
-
-
 class ReaderResult(C.Structure):
     _fields_ = [("error", C.c_void_p)]
 
@@ -62,11 +48,70 @@ class ReplacementScanResult(C.Structure):
 
 
 class ColumnView(C.Structure):
-    _fields_ = [("offsets", C.POINTER(C.c_int64)), ("data", C.POINTER(C.c_uint8)), ("valid", C.POINTER(C.c_uint8))]
+    _fields_ = [
+        ("offsets", C.POINTER(C.c_int64)),
+        ("data", C.POINTER(C.c_uint8)),
+        ("valid", C.POINTER(C.c_uint8)),
+        ("type", C.c_int32),
+        ("kind", C.c_int32),
+        ("strings", C.c_void_p),
+        ("chunk_nulls", C.c_int64),
+        ("valid_bits", C.POINTER(C.c_uint64)),
+        ("values", C.c_void_p),
+        ("list_entries", C.POINTER(C.c_uint64)),
+        ("n_values", C.c_int64),
+    ]
+
+
+MAX_COMPUTED = 8
+C_GC_CONTENT, C_SEQ_MAP, C_QUALITY_LIST, C_MEAN_QUALITY, C_SEQ_LENGTH, C_QUAL_LENGTH = 1, 2, 3, 4, 5, 6
+RD_STRING_T, RD_NO_OFFSETS = 1, 2
+T_VARCHAR, T_FLOAT, T_DOUBLE, T_INT32_LIST, T_INT64 = 0, 1, 2, 3, 4
 
 
 class Batch(C.Structure):
-    _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int32), ("cols", ColumnView * 4), ("owner", C.c_void_p)]
+    _fields_ = [
+        ("n_rows", C.c_int64),
+        ("n_cols", C.c_int32),
+        ("n_computed", C.c_int32),
+        ("batch_index", C.c_int64),
+        ("cols", ColumnView * (4 + MAX_COMPUTED)),
+        ("owner", C.c_void_p),
+    ]
+
+
+class Computed(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("arg", C.c_int32)]
+
+
+class ReaderOptions(C.Structure):
+    _fields_ = [
+        ("size", C.c_uint32),
+        ("device", C.c_int32),
+        ("range_lo", C.c_int64),
+        ("range_hi", C.c_int64),
+        ("file_lo", C.c_int32),
+        ("file_hi", C.c_int32),
+        ("column_mask", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("n_computed", C.c_int32),
+        ("computed", Computed * MAX_COMPUTED),
+    ]
+
+
+def reader_options(column_mask=0xF, device=-1, range_lo=0, range_hi=0, file_lo=0, file_hi=0, flags=0, computed=()):
+    o = ReaderOptions()
+    o.size = C.sizeof(ReaderOptions)
+    o.device = device
+    o.range_lo, o.range_hi = range_lo, range_hi
+    o.file_lo, o.file_hi = file_lo, file_hi
+    o.column_mask = column_mask
+    o.flags = flags
+    o.n_computed = len(computed)
+    for i, (kind, arg) in enumerate(computed):
+        o.computed[i].kind = kind
+        o.computed[i].arg = arg
+    return o
 
 
 class ExonError(RuntimeError):
@@ -86,6 +131,10 @@ SIGNATURES = {
     "replacement_scan": (ReplacementScanResult, [C.c_char_p]),
     "exb_free_string": (None, [_vp]),
     "exb_reader_open": (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, _i64, C.c_char_p, C.c_uint32, C.POINTER(_vp)]),
+    "exb_reader_open2": (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, _i64, C.c_char_p, C.POINTER(ReaderOptions), C.POINTER(_vp)]),
+    "exb_reader_progress": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "exb_reader_plan": (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(_i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "exb_device_count": (_i32, []),
     "exb_reader_columns": (_i32, [_vp, C.POINTER(C.c_char_p), _i32]),
     "exb_reader_next": (_i32, [_vp, C.POINTER(Batch)]),
     "exb_batch_release": (None, [C.POINTER(Batch)]),
@@ -125,9 +174,6 @@ SIGNATURES = {
     "exb_seq_map_host": (_i32, [_vp, _i64, _i32, _vp, C.POINTER(_i64)]),
     "exb_translate_host": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_quality_decode_host": (_i32, [_vp, _i64, _vp]),
-    "exb_gen_size": (_i64, [C.POINTER(GenParams)]),
-    "exb_gen_device": (_i32, [C.POINTER(GenParams), _vp, _i64, _vp]),
-    "exb_gen_host": (_i32, [C.POINTER(GenParams), _vp, _i64]),
     "exb_fastq_count_host": (_i32, [_vp, _i64, C.POINTER(Predicate), _i32, _i64, _i32, C.POINTER(_i64), C.POINTER(ScanResult)]),
     "exb_engine_create": (_i32, [_i32, _i64, C.POINTER(_vp)]),
     "exb_engine_destroy": (None, [_vp]),
@@ -170,16 +216,3 @@ def predicates(preds):
         arr[i].op = OPS[op] if isinstance(op, str) else int(op)
         arr[i].value = float(v)
     return arr, len(preds)
-
-
-def gen_params(kind, n_records, seed=1, first_record=0, len_min=150, len_max=150, wrap=60, crlf=False):
-    p = GenParams()
-    p.kind = {"fasta": GEN_FASTA, "illumina": GEN_ILLUMINA, "ont": GEN_ONT}[kind] if isinstance(kind, str) else kind
-    p.seed = seed
-    p.n_records = n_records
-    p.first_record = first_record
-    p.len_min = len_min
-    p.len_max = len_max
-    p.wrap = wrap
-    p.crlf = 1 if crlf else 0
-    return p

@@ -9,7 +9,6 @@
 
 #include "common.cuh"
 #include "exon_b200_internal.h"
-#include "gen_common.h"
 
 namespace exb {
 // record_ops.cu
@@ -88,16 +87,6 @@ int carve_scan(void* ws, int64_t ws_bytes, int64_t payload, Workspace* out) {
     return 0;
 }
 
-
-// ---------------------------------------------------------------- generators
-__global__ void gen_sizes_kernel(exb_gen_params p, uint32_t* sizes) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_records; i += (int64_t)gridDim.x * blockDim.x)
-        sizes[i] = (uint32_t)exb_gen_record(&p, (uint64_t)(p.first_record + i), nullptr);
-}
-__global__ void gen_fill_kernel(exb_gen_params p, const int64_t* off, uint8_t* out) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_records; i += (int64_t)gridDim.x * blockDim.x)
-        exb_gen_record(&p, (uint64_t)(p.first_record + i), out + off[i]);
-}
 
 // True predecessor state of shard `rank` from the all-gathered result blocks of all shards (one thread: the walk is
 // over at most `world` blocks).  Host mirror with the derivation: exon_duckdb_b200/dist.py compose_prev.
@@ -569,61 +558,6 @@ int exb_quality_decode(const uint8_t* d_in, int64_t n_bytes, int32_t* d_out, voi
     cudaError_t e = quality_decode_launch(d_in, n_bytes, d_out, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "quality_decode launch");
     return 0;
-}
-
-// ---------------------------------------------------------------- generators
-int64_t exb_gen_size(const exb_gen_params* p) {
-    int64_t tot = 0;
-    for (int64_t i = 0; i < p->n_records; i++) tot += exb_gen_record(p, (uint64_t)(p->first_record + i), nullptr);
-    return tot;
-}
-int exb_gen_host(const exb_gen_params* p, void* out, int64_t cap) {
-    uint8_t* o = reinterpret_cast<uint8_t*>(out);
-    int64_t at = 0;
-    for (int64_t i = 0; i < p->n_records; i++) {
-        int64_t sz = exb_gen_record(p, (uint64_t)(p->first_record + i), nullptr);
-        if (at + sz > cap) return set_err(EXB_ERR_CAPACITY, "exb_gen_host: buffer too small");
-        exb_gen_record(p, (uint64_t)(p->first_record + i), o + at);
-        at += sz;
-    }
-    return 0;
-}
-int exb_gen_device(const exb_gen_params* p, void* d_out, int64_t cap, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n = p->n_records;
-    if (n == 0) return 0;
-    uint32_t* sizes = nullptr;
-    int64_t* off = nullptr;
-    void* ws = nullptr;
-    const int64_t ws_bytes = exb_scan_workspace_bytes(4 * n);
-    cudaError_t e = cudaMalloc(&sizes, (size_t)n * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&off, (size_t)(n + 1) * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&ws, (size_t)ws_bytes);
-    int rc = 0;
-    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(gen scratch)");
-    if (!rc) {
-        int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
-        gen_sizes_kernel<<<blocks, 256, 0, st>>>(*p, sizes);
-        rc = exb_exclusive_scan_u32(sizes, n, off, ws, ws_bytes, st);
-        if (!rc) {
-            int64_t total = 0;
-            e = cudaMemcpyAsync(&total, off + n, 8, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) rc = cuda_fail(e, "gen sizes");
-            else if (total > cap) rc = set_err(EXB_ERR_CAPACITY, "exb_gen_device: need %lld bytes, have %lld", (long long)total, (long long)cap);
-            else {
-                // few long records (genomes): one thread each is still the simplest correct mapping
-                int fblocks = (int)((n + 63) / 64 < 148 * 64 ? (n + 63) / 64 : 148 * 64);
-                gen_fill_kernel<<<fblocks, 64, 0, st>>>(*p, off, reinterpret_cast<uint8_t*>(d_out));
-                e = cudaStreamSynchronize(st);
-                if (e != cudaSuccess) rc = cuda_fail(e, "gen fill");
-            }
-        }
-    }
-    cudaFree(sizes);
-    cudaFree(off);
-    cudaFree(ws);
-    return rc;
 }
 
 }  // extern "C"

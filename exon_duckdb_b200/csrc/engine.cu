@@ -124,7 +124,8 @@ int exb_engine_fastq_count(exb_engine* g, const void* host_buf, int64_t n, const
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
         g->events.push_back(ev);
     }
-    int64_t want_cap = g->rec_cap > 0 ? g->rec_cap : n / 32 + 4096;
+    // the estimate follows the CURRENT input (a capacity kept from an earlier, smaller file would overflow first and redo the pass)
+    int64_t want_cap = g->rec_cap > n / 32 + 4096 ? g->rec_cap : n / 32 + 4096;
     for (int attempt = 0; attempt < 2; attempt++) {
         if (g->rec_cap < want_cap) {
             for (int i = 0; i < 4; i++) {

@@ -21,7 +21,9 @@
 
 #include <errno.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <unistd.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <atomic>
@@ -46,6 +48,15 @@ cudaError_t fasta_seq_ranges_launch(const int64_t*, const int64_t*, int64_t, int
 cudaError_t take_u32_launch(const uint32_t*, const int64_t*, int64_t, uint32_t*, cudaStream_t);
 cudaError_t take_i64_launch(const int64_t*, const int64_t*, int64_t, int64_t*, cudaStream_t);
 cudaError_t take_u8_launch(const uint8_t*, const int64_t*, int64_t, uint8_t*, cudaStream_t);
+// reader_ops.cu
+cudaError_t string_t_launch(const int64_t*, const uint8_t*, uint64_t, int64_t, void*, cudaStream_t);
+cudaError_t valid_bits_launch(const uint8_t*, int64_t, uint64_t*, uint64_t*, cudaStream_t);
+cudaError_t list_entries_launch(const int64_t*, int64_t, int64_t, void*, int64_t*, cudaStream_t);
+cudaError_t gc_sel_launch(const uint32_t*, const uint32_t*, const int64_t*, const int64_t*, const int64_t*, int64_t, float*, cudaStream_t);
+cudaError_t mean_quality_launch(const uint32_t*, const int32_t*, const int64_t*, int64_t, double*, uint8_t*, cudaStream_t);
+cudaError_t lens_i64_launch(const uint32_t*, int64_t, int64_t*, cudaStream_t);
+cudaError_t fastq_chunk_info_launch(const void*, const uint32_t*, int64_t*, cudaStream_t);
+cudaError_t gather_ranges_map_launch(const uint8_t*, const int64_t*, const int64_t*, int64_t, int64_t, uint8_t*, int, unsigned long long*, cudaStream_t);
 }  // namespace exb
 using namespace exb;
 
@@ -440,6 +451,7 @@ struct Parser {
     }
 };
 
+
 // ------------------------------------------------------------------ buffers
 struct DBuf {  // growable device buffer
     void* p = nullptr;
@@ -456,16 +468,15 @@ struct DBuf {  // growable device buffer
     }
     template <typename T> T* as() { return reinterpret_cast<T*>(p); }
 };
-struct HBuf {  // growable pinned host buffer
+struct HBuf {  // growable pinned host buffer (portable: every device of a multi-GPU scan may copy from / to it)
     void* p = nullptr;
     int64_t cap = 0;
     ~HBuf() { if (p) cudaFreeHost(p); }
-    bool need(int64_t n, bool keep = false, int64_t keep_bytes = 0) {
+    bool need(int64_t n) {
         if (n <= cap) return true;
         int64_t want = std::max<int64_t>(n + n / 4 + 256, 4096);
         void* q = nullptr;
-        if (cudaHostAlloc(&q, (size_t)want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
-        if (keep && p && keep_bytes > 0) memcpy(q, p, (size_t)keep_bytes);
+        if (cudaHostAlloc(&q, (size_t)want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return false; }
         if (p) cudaFreeHost(p);
         p = q;
         cap = want;
@@ -475,8 +486,8 @@ struct HBuf {  // growable pinned host buffer
 };
 
 // Pinned host buffers are expensive to create (cudaHostAlloc pins every page) and cheap to reuse: input blocks and
-// result buffers cycle through this pool.  Shared by the reader and by every ChunkResult still held by the host, so
-// a batch may outlive the reader that produced it.
+// result buffers cycle through this pool.  Shared by every reader of the process and by every ChunkResult still held
+// by the host, so a batch may outlive the reader that produced it.
 struct PinnedPool {
     std::mutex mu;
     std::vector<HBuf*> idle;
@@ -491,6 +502,13 @@ struct PinnedPool {
             for (int i = 0; i < (int)idle.size(); i++) {
                 if (idle[i]->cap >= bytes && (best < 0 || idle[i]->cap < idle[best]->cap)) best = i;
                 if (largest < 0 || idle[i]->cap > idle[largest]->cap) largest = i;
+            }
+            // a buffer more than 4x too large stays for a request of its own size class (input blocks vs. small metadata)
+            if (best >= 0 && idle[best]->cap > 4 * bytes + (1 << 20)) {
+                int small = -1;
+                for (int i = 0; i < (int)idle.size(); i++)
+                    if (idle[i]->cap < bytes && (small < 0 || idle[i]->cap > idle[small]->cap)) small = i;
+                if (small >= 0) best = small;  // grow a small one instead
             }
             if (best < 0) best = largest;  // none fits: grow the largest one instead of leaving it idle forever
             if (best >= 0) {
@@ -520,10 +538,9 @@ struct PinnedPool {
     }
     // One pool per process: pinning a 64 MiB block costs ~10 ms, so a query that opens a reader right after another
     // one (DuckDB: bind opens one for the schema, init_global the real one) starts with warm buffers.
-    int64_t max_idle_bytes = 2ll << 30;
+    int64_t max_idle_bytes = 4ll << 30;
     static std::shared_ptr<PinnedPool> shared() {
         static std::mutex m;
-        static std::weak_ptr<PinnedPool> weak;
         static std::shared_ptr<PinnedPool> keep;  // keeps the buffers pinned for the life of the process
         std::lock_guard<std::mutex> lk(m);
         if (!keep) keep = std::make_shared<PinnedPool>();
@@ -531,16 +548,161 @@ struct PinnedPool {
     }
 };
 
-struct ChunkColumn {  // one column of the rows a chunk produced: views into the chunk's pinned result buffers
-    const int64_t* off = nullptr;  // rows + 1 entries starting at 0; nullptr = projected out
-    const uint8_t* data = nullptr;
+// ------------------------------------------------------------------ host copy workers
+// File bytes reach the pinned block through the page cache: mmap + memcpy by a pool of worker threads.  Measured on the
+// B200 box (tools/iobench.cu, profiles/round2_iobench.txt): pread into pinned memory tops out at 43 GB/s with 16
+// threads (one copy_to_user per call), memcpy from a mapping of the same tmpfs file runs at 88 GB/s -- above the
+// 55 GB/s of the PCIe link, so the H2D copy, not the host, bounds the scan.  One pool per process, shared by the
+// readers of a multi-GPU scan.
+struct IoPool {
+    struct Job {
+        std::atomic<int64_t> left{0};
+        std::mutex mu;
+        std::condition_variable cv;
+    };
+    struct Task {
+        uint8_t* dst;
+        const uint8_t* src;
+        size_t n;
+        Job* job;
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Task> q;
+    int nthreads = 1;
+    IoPool() {
+        int hw = (int)std::thread::hardware_concurrency();
+        nthreads = hw > 0 ? std::min(hw, 16) : 4;
+        if (const char* e = getenv("EXON_B200_IO_THREADS"))
+            if (atoi(e) > 0) nthreads = std::min(atoi(e), 64);
+        for (int i = 0; i < nthreads - 1; i++) std::thread([this] { work(); }).detach();  // the caller is the last worker
+    }
+    static IoPool& get() {
+        static IoPool* p = new IoPool();  // never destroyed: detached workers may outlive static destructors
+        return *p;
+    }
+    static void run(const Task& t) {
+        memcpy(t.dst, t.src, t.n);
+        if (t.job->left.fetch_sub(1) == 1) {
+            std::lock_guard<std::mutex> lk(t.job->mu);
+            t.job->cv.notify_all();
+        }
+    }
+    void work() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !q.empty(); });
+                t = q.front();
+                q.pop_front();
+            }
+            run(t);
+        }
+    }
+    void copy(uint8_t* dst, const uint8_t* src, int64_t n) {
+        if (n <= 0) return;
+        if (n < (4 << 20) || nthreads == 1) {
+            memcpy(dst, src, (size_t)n);
+            return;
+        }
+        int64_t slice = (n + nthreads - 1) / nthreads;
+        slice = std::max<int64_t>((slice + 4095) & ~(int64_t)4095, 1 << 20);
+        const int64_t parts = (n + slice - 1) / slice;
+        Job job;
+        job.left.store(parts);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (int64_t k = 0; k < parts; k++) q.push_back(Task{dst + k * slice, src + k * slice, (size_t)std::min(slice, n - k * slice), &job});
+        }
+        cv.notify_all();
+        for (;;) {  // help until the queue is empty, then wait for the slices other workers hold
+            Task t;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (q.empty()) break;
+                t = q.front();
+                q.pop_front();
+            }
+            run(t);
+        }
+        std::unique_lock<std::mutex> lk(job.mu);
+        job.cv.wait(lk, [&] { return job.left.load() == 0; });
+    }
 };
+
+// ------------------------------------------------------------------ shard edges (include/exon_b200.h exb_reader_options)
+// First record start at or after p.  Both ends of a byte-range shard go through the same function, so adjacent shards
+// agree on the cut; a shard is then parsed as a complete input.
+// FASTA: a line whose first byte is '>' always starts a record (noodles-fasta read_sequence stops there): exact.
+static int64_t resync_fasta(const uint8_t* m, int64_t size, int64_t p) {
+    if (p <= 0) return 0;
+    while (p < size) {
+        if (m[p] == '>' && m[p - 1] == '\n') return p;
+        const void* q = memchr(m + p, '\n', (size_t)(size - p));
+        if (!q) return size;
+        p = (const uint8_t*)q - m + 1;
+        if (p < size && m[p] == '>') return p;
+    }
+    return size;
+}
+// FASTQ: '@' and '+' are legal quality characters, so one line proves nothing.  Take the first line start >= p and the
+// line starts after it; hypothesis h = "line h is a header" holds if every 4th line from h starts with '@' and the line
+// two below it with '+', over a window of 16 records.  The smallest h that holds wins.  This is a heuristic for
+// adversarial inputs; it cannot produce a silently wrong answer, because the shard that ENDS at the cut is parsed
+// exactly from its own (inductively exact) start: if the cut is not a record boundary its line count is not a multiple
+// of four or a header / plus line check fails, and the scan reports the malformed shard.
+static int64_t resync_fastq(const uint8_t* m, int64_t size, int64_t p) {
+    if (p <= 0) return 0;
+    if (p >= size) return size;
+    int64_t ls = p;
+    if (m[p - 1] != '\n') {
+        const void* q = memchr(m + p, '\n', (size_t)(size - p));
+        if (!q) return size;
+        ls = (const uint8_t*)q - m + 1;
+    }
+    constexpr int WINDOW = 4 * 16 + 4;
+    int64_t starts[WINDOW];
+    int L = 0;
+    for (int64_t s = ls; s < size && L < WINDOW;) {
+        starts[L++] = s;
+        const void* q = memchr(m + s, '\n', (size_t)(size - s));
+        if (!q) break;
+        s = (const uint8_t*)q - m + 1;
+    }
+    if (L == 0) return size;
+    for (int h = 0; h < 4 && h < L; h++) {
+        bool ok = true;
+        for (int j = h; j < L && ok; j += 4) {
+            if (m[starts[j]] != '@') ok = false;
+            else if (j + 2 < L && m[starts[j + 2]] != '+') ok = false;
+        }
+        if (ok) return starts[h];
+    }
+    return starts[0];  // nothing fits: the scan will report the malformed record
+}
+
+// ------------------------------------------------------------------ results
+struct OutCol {  // one output column of the rows a chunk produced: views into the chunk's pinned result buffers
+    bool present = false;
+    int type = EXB_T_VARCHAR, kind = 0;
+    const int64_t* off = nullptr;    // VARCHAR / list: rows + 1 entries starting at 0 (absent with EXB_RD_NO_OFFSETS)
+    const uint8_t* data = nullptr;   // VARCHAR bytes
+    const uint8_t* str = nullptr;    // rows x 16-byte string_t (EXB_RD_STRING_T)
+    const uint8_t* valid = nullptr;  // one byte per row; nullptr = all valid
+    const uint64_t* vbits = nullptr;
+    const uint64_t* nulls_word = nullptr;  // number of NULL rows of the column in this chunk (valid after the D2H)
+    const uint8_t* values = nullptr;     // numeric: rows x elem; list: child values (int32)
+    int elem = 0;
+    const uint64_t* entries = nullptr;   // list: rows x {offset, length}
+    const int64_t* batch_base = nullptr; // list: first child value of batch k (batches of batch_size rows), closed with the total
+};
+constexpr int MAX_OUT = 4 + EXB_MAX_COMPUTED;
 // The rows one input chunk produced.  Shared: every batch view handed out (exb_batch) holds a reference, so a
 // host that borrows the strings (DuckDB string_t pointers) keeps the buffers alive past the reader's next step.
 // The strings are handed out where the D2H copy put them -- no second host copy.
 struct ChunkResult {
-    ChunkColumn cols[4];
-    const uint8_t* valid = nullptr;  // description validity, one byte per row
+    OutCol cols[MAX_OUT];
     int64_t rows = 0;
     std::vector<HBuf*> bufs;
     std::shared_ptr<PinnedPool> pool;
@@ -556,7 +718,7 @@ struct Block {
     int64_t raw_len = 0;
     int64_t raw_file_pos = 0;  // offset of the first raw byte in the (decompressed) file
     size_t file_idx = 0;
-    bool eof = false;          // the file ends with this block
+    bool eof = false;          // the file (or the shard of it) ends with this block
     std::string error;         // IO failure: the stream ends here
     bool end = false;          // no more files
 };
@@ -606,12 +768,17 @@ struct BoundedQueue {
     }
 };
 
+struct NvtxRange {  // one range per pipeline stage (visible in nsys / ncu --nvtx timelines)
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // ------------------------------------------------------------------ the stream
 // Three stages, each on its own thread, connected by bounded queues:
-//   IO thread     file -> pinned blocks (plain files: four pread slices in parallel; gzip: inflate)
-//   device thread block -> H2D -> scan / filter / field split / gather kernels -> D2H into pinned result buffers
-//   caller        exb_reader_next / the Arrow stream: hands out <= batch_size-row views of a chunk's result
-// so reading block k+1, the device work of block k and the host's consumption of block k-1 overlap.
+//   IO thread     file -> pinned blocks (plain files: mmap + memcpy by the IoPool workers; compressed: inflate)
+//   device thread block -> H2D -> scan / filter / field split / gather / string_t kernels -> D2H into pinned result buffers
+//   caller(s)     exb_reader_next / the Arrow stream: hand out <= batch_size-row views of a chunk's result
+// so reading block k+1, the device work of block k, the D2H of block k-1 and the host's consumption overlap.
 struct Reader {
     int format = 0;  // 1 FASTA, 2 FASTQ
     int ncols = 0;
@@ -620,24 +787,43 @@ struct Reader {
     std::vector<std::string> files;
     std::vector<int> file_comp;
     int64_t chunk_bytes = 64ll << 20;
+    // options
+    int device = -1;
+    int64_t range_lo = 0, range_hi = 0;  // byte-range shard (single plain file); range_hi <= 0: to the end
+    uint32_t flags = 0;
+    std::vector<exb_computed> computed;
+    int n_out() const { return ncols + (int)computed.size(); }
+    bool want_offsets() const { return !(flags & EXB_RD_NO_OFFSETS); }
+    bool want_string_t() const { return (flags & EXB_RD_STRING_T) != 0; }
     // filter
     std::vector<Node> nodes;
     int root = -1;
-    // device state (device thread only, after ensure_device)
-    bool dev_ready = false;
-    cudaStream_t st = nullptr, sc = nullptr;  // compute (+ D2H) stream, H2D prefetch stream
+    // device state (device thread only)
+    cudaStream_t st = nullptr, sc = nullptr, sd = nullptr;  // compute stream, H2D prefetch stream, D2H stream
     cudaEvent_t ev_staged = nullptr, ev_stage_free = nullptr;
     DBuf d_inb[2], d_stage;  // the chunk being scanned / the one being assembled; the prefetched raw block
     uint8_t* d_cur = nullptr;  // = d_inb[cur].p while a chunk is processed
     DBuf d_ws, d_ws2, d_line, d_arr[4], d_lens, d_starts, d_valid, d_pass, d_selscratch, d_sel, d_lens2, d_starts2,
-        d_valid2, d_off, d_data, d_cst, d_hdr_start, d_hdr_end, d_seq_off, d_gc_prefix, d_seq, d_err;
+        d_valid2, d_off, d_cst, d_hdr_start, d_hdr_end, d_seq_off, d_gc_prefix, d_seq, d_err, d_info, d_qtmp, d_bad;
+    // output buffers, double-buffered: the D2H of chunk k (stream sd) overlaps the kernels of chunk k+1 (stream st)
+    struct OutSet {
+        DBuf d_meta, d_data;
+        cudaEvent_t ev_done = nullptr, ev_d2h = nullptr, ev_off = nullptr;
+    } outs[2];
+    int out_cur = 0;
+    OutItem pending;            // result whose D2H is still in flight
+    int pending_set = -1;
+    std::vector<std::pair<int, int>> pending_bad;  // (out column, map mode) whose invalid-byte word must be checked after the D2H
+    const uint64_t* pending_bad_words = nullptr;
     std::shared_ptr<PinnedPool> pool = PinnedPool::shared();
     HBuf h_small;  // a few words for totals / flags read back between launches
-    // rows ready to be handed out (caller's thread)
+    // rows ready to be handed out (caller threads, under call_mu)
+    std::mutex call_mu;
     std::shared_ptr<ChunkResult> cur;
     int64_t rows = 0, next_row = 0;
-    uint32_t column_mask = 0xF;  // bit c: column c is materialised (projection push-down)
-    bool count_only = false;     // COUNT(*): rows are counted, nothing is gathered or copied back
+    int64_t next_batch_index = 0;
+    uint32_t column_mask = 0xF;          // bit c: column c is materialised (projection push-down)
+    std::atomic<bool> count_only{false}; // COUNT(*): rows are counted, nothing is gathered or copied back
     int64_t counted = 0;
     std::string error;  // caller's thread: the failure reported to the host
     std::string derr;   // device thread: failure of the chunk being processed
@@ -645,14 +831,16 @@ struct Reader {
     bool started = false, finished = false;
     std::thread io_thread, dev_thread;
     BoundedQueue<Block> inq{2};
-    BoundedQueue<OutItem> outq{2};
+    BoundedQueue<OutItem> outq{3};
     std::atomic<int64_t> block_bytes{0};
     std::atomic<bool> stopping{false};
+    std::atomic<int64_t> bytes_done{0}, bytes_total{0};
     // device thread: the chunk being processed
     size_t cur_file = 0;
     int64_t cur_file_pos = 0;
     // EXON_B200_TRACE=1: seconds spent per stage, printed when the reader closes
     double t_io_read = 0, t_io_alloc = 0, t_io_push = 0, t_dev_pop = 0, t_dev_work = 0, t_dev_push = 0, t_call_pop = 0;
+    double t_scan = 0, t_select = 0, t_mat = 0, t_flush = 0;
     int64_t n_blocks = 0;
     static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -665,13 +853,11 @@ struct Reader {
         for (Block& b : inq.q) pool->put(b.h);
         cur.reset();
         outq.q.clear();
-        if (st) cudaStreamDestroy(st);
-        if (sc) cudaStreamDestroy(sc);
-        if (ev_staged) cudaEventDestroy(ev_staged);
-        if (ev_stage_free) cudaEventDestroy(ev_stage_free);
         if (getenv("EXON_B200_TRACE"))
-            fprintf(stderr, "exon_b200 reader: %lld blocks | io: alloc %.3f read %.3f push-wait %.3f | device: pop-wait %.3f work %.3f push-wait %.3f | "
-                            "caller: pop-wait %.3f s\n", (long long)n_blocks, t_io_alloc, t_io_read, t_io_push, t_dev_pop, t_dev_work, t_dev_push, t_call_pop);
+            fprintf(stderr, "exon_b200 reader: %lld blocks | io: alloc %.3f read %.3f push-wait %.3f | device: pop-wait %.3f work %.3f "
+                            "(scan %.3f select %.3f materialise %.3f d2h-wait %.3f) push-wait %.3f | caller: pop-wait %.3f s\n",
+                    (long long)n_blocks, t_io_alloc, t_io_read, t_io_push, t_dev_pop, t_dev_work, t_scan, t_select, t_mat, t_flush, t_dev_push,
+                    t_call_pop);
     }
     bool fail(const std::string& m) {
         derr = m;
@@ -687,29 +873,64 @@ struct Reader {
         derr = exb_last_error();
         return false;
     }
-    bool ensure_device() {
-        if (dev_ready) return true;
+    // caller's thread: is there a device at all?  ("no CUDA device" is the message a CPU-only host must see, before any
+    // pinned allocation is attempted)
+    bool check_device() {
         int n = 0;
         if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
             cudaGetLastError();
             error = "no CUDA device: the exon_b200 scan engine has no CPU fallback";
             return false;
         }
-        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_staged, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_stage_free, cudaEventDisableTiming);
-        if (e != cudaSuccess) {
-            error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+        if (device < 0) {
+            if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+        }
+        if (device >= n) {
+            error = "CUDA device " + std::to_string(device) + " does not exist (" + std::to_string(n) + " visible)";
             return false;
         }
-        dev_ready = true;
         return true;
+    }
+    // device thread: streams and events live on THIS reader's device
+    bool init_device() {
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_staged, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_stage_free, cudaEventDisableTiming);
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+            e = cudaEventCreateWithFlags(&outs[i].ev_done, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&outs[i].ev_d2h, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&outs[i].ev_off, cudaEventDisableTiming);
+        }
+        return cu(e, "CUDA stream setup");
+    }
+    void free_device() {  // device thread, at its end: buffers are freed on the device that owns them
+        for (DBuf* b : {&d_inb[0], &d_inb[1], &d_stage, &d_ws, &d_ws2, &d_line, &d_arr[0], &d_arr[1], &d_arr[2], &d_arr[3], &d_lens, &d_starts,
+                        &d_valid, &d_pass, &d_selscratch, &d_sel, &d_lens2, &d_starts2, &d_valid2, &d_off, &d_cst, &d_hdr_start, &d_hdr_end,
+                        &d_seq_off, &d_gc_prefix, &d_seq, &d_err, &d_info, &d_qtmp, &d_bad, &outs[0].d_meta, &outs[0].d_data, &outs[1].d_meta,
+                        &outs[1].d_data}) {
+            if (b->p) cudaFree(b->p);
+            b->p = nullptr;
+            b->cap = 0;
+        }
+        scratch.clear();
+        for (int i = 0; i < 2; i++) {
+            if (outs[i].ev_done) cudaEventDestroy(outs[i].ev_done);
+            if (outs[i].ev_d2h) cudaEventDestroy(outs[i].ev_d2h);
+            if (outs[i].ev_off) cudaEventDestroy(outs[i].ev_off);
+        }
+        if (ev_staged) cudaEventDestroy(ev_staged);
+        if (ev_stage_free) cudaEventDestroy(ev_stage_free);
+        if (st) cudaStreamDestroy(st);
+        if (sc) cudaStreamDestroy(sc);
+        if (sd) cudaStreamDestroy(sd);
     }
 
     // ------------------------------------------------------------------ IO thread
     static void pread_slices(int fd, uint8_t* dst, int64_t pos, int64_t want, int64_t* got_out, bool* err_out) {
-        // page-cache / tmpfs reads are a kernel memcpy: ~5 GB/s from one thread, so a block is read as eight slices
+        // fallback when the file cannot be mapped: ~5 GB/s per thread, so a block is read as eight slices
         constexpr int TMAX = 8;
         const int T = want >= (8ll << 20) ? TMAX : 1;
         int64_t got[TMAX] = {0};
@@ -743,6 +964,8 @@ struct Reader {
         *got_out = total;
     }
     void io_main() {
+        cudaSetDevice(device);  // pinned allocations below belong to a context of this reader's device
+        const bool sharded = range_lo > 0 || range_hi > 0;
         for (size_t fi = 0; fi < files.size() && !stopping; fi++) {
             const std::string& path = files[fi];
             const int comp = file_comp[fi];
@@ -753,13 +976,47 @@ struct Reader {
             std::vector<uint8_t> zbuf;
             size_t zpos = 0, zsize = 0;
             std::string err;
+            const uint8_t* map = nullptr;  // plain files: the whole file mapped read-only
+            int64_t map_size = 0;
+            int64_t pos = 0, end_pos = -1;  // plain files: [pos, end_pos) is what this reader parses
             if (comp == 1) {
                 gz = gzopen(path.c_str(), "rb");
                 if (!gz) err = "could not open " + path;
-                else gzbuffer(gz, 1 << 20);
+                else {
+                    gzbuffer(gz, 1 << 20);
+                    // the reference's GzipDecoder fails on input that is not gzip; gzread would pass it through
+                    if (gzdirect(gz)) {
+                        struct stat sb;
+                        if (stat(path.c_str(), &sb) == 0 && sb.st_size > 0) err = "invalid gzip header in " + path;
+                    }
+                }
             } else if (comp == 0) {
                 fd = open(path.c_str(), O_RDONLY);
                 if (fd < 0) err = "could not open " + path;
+                else {
+                    struct stat sb;
+                    if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+                        void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
+                        if (m != MAP_FAILED) {
+                            map = reinterpret_cast<const uint8_t*>(m);
+                            map_size = sb.st_size;
+                            madvise(m, (size_t)map_size, MADV_SEQUENTIAL);
+                        }
+                    }
+                    if (sharded) {
+                        if (!map) err = "byte-range shards need a mappable regular file: " + path;
+                        else {
+                            auto cut = [&](int64_t p) { return format == 1 ? resync_fasta(map, map_size, p) : resync_fastq(map, map_size, p); };
+                            pos = cut(std::min(range_lo, map_size));
+                            end_pos = range_hi > 0 ? cut(std::min(range_hi, map_size)) : map_size;
+                            if (end_pos < pos) end_pos = pos;
+                            shard_begin = pos;
+                            shard_end = end_pos;
+                        }
+                    } else if (map) {
+                        end_pos = map_size;
+                    }
+                }
             } else if (comp >= 2 && comp <= 4) {
                 if (comp == 2) {
                     std::unique_ptr<ZstdDecoder> d(new ZstdDecoder());
@@ -776,7 +1033,6 @@ struct Reader {
             } else {
                 err = "compression of " + path + " is not supported by this build";
             }
-            int64_t pos = 0;
             bool eof = false;
             while (err.empty() && !eof && !stopping) {
                 const int64_t want = block_bytes.load();
@@ -789,6 +1045,7 @@ struct Reader {
                     break;
                 }
                 t0 = now();
+                NvtxRange nv("exb:io_block");
                 b.file_idx = fi;
                 b.raw_file_pos = pos;
                 uint8_t* dst = b.h->as<uint8_t>();
@@ -800,7 +1057,13 @@ struct Reader {
                             err = "gzip read error in " + path;
                             break;
                         }
-                        if (g == 0) break;
+                        if (g == 0) {
+                            // a truncated stream makes gzread return the partial data and then 0 with only gzerror() set
+                            int zerr = Z_OK;
+                            gzerror(gz, &zerr);
+                            if (zerr == Z_BUF_ERROR || zerr == Z_DATA_ERROR) err = "truncated or corrupt gzip stream in " + path;
+                            break;
+                        }
                         got += g;
                     }
                 } else if (dec) {
@@ -827,7 +1090,10 @@ struct Reader {
                         }
                         got = (int64_t)opos;
                     }
-                } else {
+                } else if (map) {
+                    got = std::min<int64_t>(want, end_pos - pos);
+                    IoPool::get().copy(dst, map + pos, got);
+                } else if (fd >= 0) {
                     bool bad = false;
                     pread_slices(fd, dst, pos, want, &got, &bad);
                     if (bad) err = "read error in " + path;
@@ -838,7 +1104,7 @@ struct Reader {
                 }
                 t_io_read += now() - t0;
                 n_blocks++;
-                eof = got < want;
+                eof = map ? pos + got >= end_pos : got < want;
                 b.raw_len = got;
                 b.eof = eof;
                 pos += got;
@@ -851,6 +1117,7 @@ struct Reader {
                     break;
                 }
             }
+            if (map) munmap(const_cast<uint8_t*>(map), (size_t)map_size);
             if (fd >= 0) close(fd);
             if (gz) gzclose(gz);
             dec.reset();
@@ -867,6 +1134,7 @@ struct Reader {
         b.end = true;
         inq.push(std::move(b));
     }
+    int64_t shard_begin = 0, shard_end = 0;  // where the byte-range shard really starts / ends (after resync)
 
     // ------------------------------------------------------------------ device thread
     // evaluate node `k` into d_out (uint8 per row) using per-column starts/lens (cols x n) in column buffers
@@ -922,16 +1190,80 @@ struct Reader {
             if (n.kind == N_NUM) return true;
         return false;
     }
+    bool has_computed(int kind) const {
+        for (const exb_computed& c : computed)
+            if (c.kind == kind) return true;
+        return false;
+    }
 
-    // Gather the selected rows of the wanted columns and bring them to the host: ONE launch for the Arrow offsets of all
-    // columns, one gather per wanted column into one device buffer, then offsets + validity + bytes cross PCIe in two
-    // copies into pinned buffers that the batches hand out as they are.  Two stream syncs per chunk.
-    bool materialise(const uint8_t* const* col_buf, const int64_t* d_st, const uint32_t* d_ln, const uint8_t* d_val, int64_t n, OutItem* item) {
-        if (count_only) {
+    // hand the finished result of the previous chunk to the caller side once its D2H has drained
+    bool flush_pending() {
+        if (pending_set < 0) return true;
+        const double t0 = now();
+        OutSet& o = outs[pending_set];
+        bool ok = cu(cudaEventSynchronize(o.ev_d2h), "D2H") && cu(cudaEventSynchronize(o.ev_off), "D2H offsets");
+        t_flush += now() - t0;
+        pending_set = -1;
+        if (!ok) return false;
+        for (auto& pb : pending_bad) {  // reverse_complement & co met a byte outside their table (module.cpp:58-62)
+            const uint64_t w = pending_bad_words[pb.first];
+            if (w != ~0ull) return fail(std::string("Invalid character in sequence: ") + std::string(1, (char)(w & 0xFF)));
+        }
+        pending_bad.clear();
+        OutItem it = std::move(pending);
+        pending = OutItem();
+        const double t1 = now();
+        const bool pushed = outq.push(std::move(it));
+        t_dev_push += now() - t1;
+        if (!pushed) stopping = true;
+        return true;
+    }
+
+    // Gather the selected rows of the wanted columns, build what the host's vectors hold (string_t entries, validity
+    // bitmaps, computed columns) and bring it to the host: ONE launch for the Arrow offsets of all file columns, one
+    // gather per wanted column into one device buffer, then metadata and bytes cross PCIe in two copies on the D2H
+    // stream into pinned buffers that the batches hand out as they are.  One stream sync (the column totals).
+    //   col_buf / d_st / d_ln / d_val: source buffer, start, length, description validity of the n selected rows
+    //   sel: the selected records (nullptr = all), for the per-record arrays the computed columns read
+    bool materialise(const uint8_t* const* col_buf, const int64_t* d_st, const uint32_t* d_ln, const uint8_t* d_val, const int64_t* sel, int64_t n,
+                     OutItem* item) {
+        if (count_only.load()) {
             item->counted = n;
             return true;
         }
         if (n == 0) return true;  // nothing to hand out for this chunk
+        NvtxRange nv("exb:materialise");
+        const int seq_col = 2, qual_col = 3;
+        const int nout = n_out();
+        // which file column feeds output column j (-1 = none), and how
+        int src[MAX_OUT], type[MAX_OUT], kind[MAX_OUT], mode[MAX_OUT];
+        bool present[MAX_OUT];
+        for (int j = 0; j < nout; j++) {
+            src[j] = -1;
+            mode[j] = -1;
+            kind[j] = 0;
+            type[j] = EXB_T_VARCHAR;
+            if (j < ncols) {
+                present[j] = ((column_mask >> j) & 1u) != 0;
+                src[j] = j;
+                continue;
+            }
+            const exb_computed& c = computed[j - ncols];
+            present[j] = true;
+            kind[j] = c.kind;
+            switch (c.kind) {
+            case EXB_C_GC_CONTENT: type[j] = EXB_T_FLOAT; break;
+            case EXB_C_SEQ_MAP: type[j] = EXB_T_VARCHAR; src[j] = seq_col; mode[j] = c.arg; break;
+            case EXB_C_QUALITY_LIST: type[j] = EXB_T_INT32_LIST; src[j] = qual_col; break;
+            case EXB_C_MEAN_QUALITY: type[j] = EXB_T_DOUBLE; break;
+            case EXB_C_SEQ_LENGTH: type[j] = EXB_T_INT64; src[j] = seq_col; break;
+            case EXB_C_QUAL_LENGTH: type[j] = EXB_T_INT64; src[j] = qual_col; break;
+            default: return fail("internal: unknown computed column");
+            }
+        }
+        OutSet& o = outs[out_cur];
+        const int set = out_cur;
+        out_cur ^= 1;
         std::shared_ptr<ChunkResult> res = std::make_shared<ChunkResult>();
         res->pool = pool;
         res->rows = n;
@@ -942,50 +1274,160 @@ struct Reader {
         int64_t* totals = h_small.as<int64_t>();
         if (!cu(cudaMemcpy2DAsync(totals, 8, d_offs + n, (size_t)(n + 1) * 8, 8, (size_t)ncols, cudaMemcpyDeviceToHost, st), "D2H totals")) return false;
         if (!cu(cudaStreamSynchronize(st), "sync")) return false;
-        int64_t base[4] = {0, 0, 0, 0}, all = 0;
-        int wanted = 0;
-        for (int c = 0; c < ncols; c++) {
-            if (!((column_mask >> c) & 1u)) continue;  // projected out: the column stays empty
-            base[c] = all;
-            all += (totals[c] + 15) & ~(int64_t)15;
-            wanted++;
+        // ---- layout of the two result buffers
+        auto up = [](int64_t x, int64_t a) { return (x + a - 1) & ~(a - 1); };
+        const int64_t n_batches = (n + batch_size - 1) / batch_size;
+        const int64_t vwords = (n + 63) / 64;
+        int64_t data_base[MAX_OUT] = {0}, all = 0;
+        int64_t m = 0;  // metadata cursor
+        const int64_t m_nulls = m;  m += up((int64_t)MAX_OUT * 8, 64);   // null count per column
+        const int64_t m_bad = m;    m += up((int64_t)MAX_OUT * 8, 64);   // invalid-byte word per mapped column
+        int64_t m_str[MAX_OUT], m_valid[MAX_OUT], m_vbits[MAX_OUT], m_values[MAX_OUT], m_entries[MAX_OUT], m_bases[MAX_OUT];
+        for (int j = 0; j < nout; j++) {
+            m_str[j] = m_valid[j] = m_vbits[j] = m_values[j] = m_entries[j] = m_bases[j] = -1;
+            if (!present[j]) continue;
+            if (type[j] == EXB_T_VARCHAR) {
+                data_base[j] = all;
+                all += up(totals[src[j]], 16);
+                if (want_string_t()) { m_str[j] = m; m += up(n * 16, 64); }
+                if (j < ncols && col_names[j] == "description") {
+                    m_valid[j] = m; m += up(n, 64);
+                    m_vbits[j] = m; m += up(vwords * 8, 64);
+                }
+            } else if (type[j] == EXB_T_INT32_LIST) {
+                data_base[j] = all;
+                all += up(4 * totals[src[j]], 16);
+                m_entries[j] = m; m += up(n * 16, 64);
+                m_bases[j] = m;   m += up((n_batches + 1) * 8, 64);
+            } else {
+                const int elem = type[j] == EXB_T_FLOAT ? 4 : 8;
+                m_values[j] = m; m += up(n * elem, 64);
+                if (kind[j] == EXB_C_MEAN_QUALITY) {
+                    m_valid[j] = m; m += up(n, 64);
+                    m_vbits[j] = m; m += up(vwords * 8, 64);
+                }
+            }
         }
-        // host layout: [wanted][(n + 1)] int64 offsets, then n validity bytes; the bytes in a buffer of their own
-        const int64_t meta_bytes = (int64_t)wanted * (n + 1) * 8 + n;
-        HBuf* h_meta = pool->get(meta_bytes + 64);
+        const int64_t meta_copy = m;  // [0, meta_copy) of the device metadata buffer is mirrored on the host in one copy
+        int64_t m_off[MAX_OUT];       // Arrow offsets: copied column by column from the scan's output, behind the mirror
+        for (int j = 0; j < nout; j++) {
+            m_off[j] = -1;
+            if (present[j] && want_offsets() && (type[j] == EXB_T_VARCHAR || type[j] == EXB_T_INT32_LIST)) { m_off[j] = m; m += up((n + 1) * 8, 64); }
+        }
+        HBuf* h_meta = pool->get(m + 64);
         HBuf* h_bytes = pool->get(all + 64);
         if (h_meta) res->bufs.push_back(h_meta);
         if (h_bytes) res->bufs.push_back(h_bytes);
-        if (!h_meta || !h_bytes || !d_data.need(all + 64)) return fail("out of memory");
-        int k = 0;
-        for (int c = 0; c < ncols; c++) {
-            if (!((column_mask >> c) & 1u)) continue;
-            if (totals[c] > 0 &&
-                !rc(exb_gather_ranges(col_buf[c], d_st + (int64_t)c * n, d_ln + (int64_t)c * n, d_offs + (int64_t)c * (n + 1), n,
-                                      d_data.as<uint8_t>() + base[c], totals[c], st)))
-                return false;
-            int64_t* h_off = h_meta->as<int64_t>() + (int64_t)k * (n + 1);
-            if (!cu(cudaMemcpyAsync(h_off, d_offs + (int64_t)c * (n + 1), (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets")) return false;
-            res->cols[c].off = h_off;
-            res->cols[c].data = h_bytes->as<uint8_t>() + base[c];
-            k++;
+        if (!h_meta || !h_bytes || !o.d_meta.need(meta_copy + 64) || !o.d_data.need(all + 64)) return fail("out of memory");
+        // the set's previous D2H (two chunks ago) has been waited for by flush_pending; order the device side too
+        if (!cu(cudaStreamWaitEvent(st, o.ev_d2h, 0), "wait")) return false;
+        uint8_t* dm = o.d_meta.as<uint8_t>();
+        uint8_t* dd = o.d_data.as<uint8_t>();
+        uint8_t* hm = h_meta->as<uint8_t>();
+        uint8_t* hb = h_bytes->as<uint8_t>();
+        if (!cu(cudaMemsetAsync(dm + m_nulls, 0, (size_t)(m_bad - m_nulls), st), "memset")) return false;
+        if (!cu(cudaMemsetAsync(dm + m_bad, 0xFF, (size_t)up((int64_t)MAX_OUT * 8, 64), st), "memset")) return false;
+        std::vector<std::pair<int, int>> bad_cols;
+        for (int j = 0; j < nout; j++) {
+            if (!present[j]) continue;
+            OutCol& oc = res->cols[j];
+            oc.present = true;
+            oc.nulls_word = reinterpret_cast<const uint64_t*>(hm + m_nulls) + j;
+            oc.type = type[j];
+            oc.kind = kind[j];
+            const int c = src[j];
+            if (type[j] == EXB_T_VARCHAR) {
+                const int64_t* offs = d_offs + (int64_t)c * (n + 1);
+                if (totals[c] > 0) {
+                    if (mode[j] < 0) {
+                        if (!rc(exb_gather_ranges(col_buf[c], d_st + (int64_t)c * n, d_ln + (int64_t)c * n, offs, n, dd + data_base[j], totals[c], st)))
+                            return false;
+                    } else {
+                        if (!cu(gather_ranges_map_launch(col_buf[c], d_st + (int64_t)c * n, offs, n, totals[c], dd + data_base[j], mode[j],
+                                                         reinterpret_cast<unsigned long long*>(dm + m_bad) + j, st),
+                                "gather_map"))
+                            return false;
+                        bad_cols.emplace_back(j, mode[j]);
+                    }
+                }
+                oc.data = hb + data_base[j];
+                if (m_str[j] >= 0) {
+                    if (!cu(string_t_launch(offs, dd + data_base[j], (uint64_t)(uintptr_t)(hb + data_base[j]), n, dm + m_str[j], st), "string_t")) return false;
+                    oc.str = hm + m_str[j];
+                }
+                if (m_valid[j] >= 0) {
+                    if (!cu(cudaMemcpyAsync(dm + m_valid[j], d_val, (size_t)n, cudaMemcpyDeviceToDevice, st), "D2D validity")) return false;
+                    if (!cu(valid_bits_launch(d_val, n, reinterpret_cast<uint64_t*>(dm + m_vbits[j]), reinterpret_cast<uint64_t*>(dm + m_nulls) + j, st),
+                            "valid_bits"))
+                        return false;
+                    oc.valid = hm + m_valid[j];
+                    oc.vbits = reinterpret_cast<const uint64_t*>(hm + m_vbits[j]);
+                }
+            } else if (type[j] == EXB_T_INT32_LIST) {
+                const int64_t* offs = d_offs + (int64_t)c * (n + 1);
+                if (totals[c] > 0) {
+                    if (!d_qtmp.need(totals[c] + 64)) return fail("out of device memory");
+                    if (!rc(exb_gather_ranges(col_buf[c], d_st + (int64_t)c * n, d_ln + (int64_t)c * n, offs, n, d_qtmp.as<uint8_t>(), totals[c], st)))
+                        return false;
+                    if (!rc(exb_quality_decode(d_qtmp.as<uint8_t>(), totals[c], reinterpret_cast<int32_t*>(dd + data_base[j]), st))) return false;
+                }
+                if (!cu(list_entries_launch(offs, n, batch_size, dm + m_entries[j], reinterpret_cast<int64_t*>(dm + m_bases[j]), st), "list_entries"))
+                    return false;
+                oc.values = hb + data_base[j];
+                oc.elem = 4;
+                oc.entries = reinterpret_cast<const uint64_t*>(hm + m_entries[j]);
+                oc.batch_base = reinterpret_cast<const int64_t*>(hm + m_bases[j]);
+            } else {
+                cudaError_t e = cudaSuccess;
+                if (kind[j] == EXB_C_GC_CONTENT) {
+                    if (format == 2)
+                        e = gc_sel_launch(d_arr[0].as<uint32_t>(), d_arr[1].as<uint32_t>(), nullptr, nullptr, sel, n, reinterpret_cast<float*>(dm + m_values[j]), st);
+                    else
+                        e = gc_sel_launch(nullptr, nullptr, d_seq_off.as<int64_t>(), d_gc_prefix.as<int64_t>(), sel, n, reinterpret_cast<float*>(dm + m_values[j]), st);
+                    oc.elem = 4;
+                } else if (kind[j] == EXB_C_MEAN_QUALITY) {
+                    e = mean_quality_launch(d_arr[2].as<uint32_t>(), d_arr[3].as<int32_t>(), sel, n, reinterpret_cast<double*>(dm + m_values[j]),
+                                            dm + m_valid[j], st);
+                    if (e == cudaSuccess)
+                        e = valid_bits_launch(dm + m_valid[j], n, reinterpret_cast<uint64_t*>(dm + m_vbits[j]), reinterpret_cast<uint64_t*>(dm + m_nulls) + j, st);
+                    oc.elem = 8;
+                    oc.valid = hm + m_valid[j];
+                    oc.vbits = reinterpret_cast<const uint64_t*>(hm + m_vbits[j]);
+                } else {
+                    e = lens_i64_launch(d_ln + (int64_t)c * n, n, reinterpret_cast<int64_t*>(dm + m_values[j]), st);
+                    oc.elem = 8;
+                }
+                if (!cu(e, "computed column")) return false;
+                oc.values = hm + m_values[j];
+            }
+            if (m_off[j] >= 0) {
+                if (!cu(cudaMemcpyAsync(hm + m_off[j], d_offs + (int64_t)c * (n + 1), (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets")) return false;
+                oc.off = reinterpret_cast<const int64_t*>(hm + m_off[j]);
+            }
         }
-        uint8_t* h_val = h_meta->as<uint8_t>() + (int64_t)wanted * (n + 1) * 8;
-        if (!cu(cudaMemcpyAsync(h_val, d_val, (size_t)n, cudaMemcpyDeviceToHost, st), "D2H validity")) return false;
-        if (all > 0 && !cu(cudaMemcpyAsync(h_bytes->p, d_data.p, (size_t)all, cudaMemcpyDeviceToHost, st), "D2H data")) return false;
-        if (!cu(cudaStreamSynchronize(st), "sync")) return false;
-        res->valid = h_val;
+        if (!cu(cudaEventRecord(o.ev_off, st), "record") || !cu(cudaEventRecord(o.ev_done, st), "record")) return false;
+        // metadata + bytes on the D2H stream: the next chunk's kernels do not wait for PCIe
+        if (!cu(cudaStreamWaitEvent(sd, o.ev_done, 0), "wait")) return false;
+        if (!cu(cudaMemcpyAsync(hm, dm, (size_t)meta_copy, cudaMemcpyDeviceToHost, sd), "D2H metadata")) return false;
+        if (all > 0 && !cu(cudaMemcpyAsync(hb, dd, (size_t)all, cudaMemcpyDeviceToHost, sd), "D2H data")) return false;
+        if (!cu(cudaEventRecord(o.ev_d2h, sd), "record")) return false;
         item->res = res;
+        pending_bad = bad_cols;
+        pending_bad_words = reinterpret_cast<const uint64_t*>(hm + m_bad);
+        pending_set = set;
         return true;
     }
 
     // apply the filter (if any) to the n rows described by starts/lens/valid; leaves the final arrays in *o_*
-    bool select(const uint8_t* const* col_buf, int64_t n, const int64_t*& o_st, const uint32_t*& o_ln, const uint8_t*& o_val, int64_t& o_n) {
+    bool select(const uint8_t* const* col_buf, int64_t n, const int64_t*& o_st, const uint32_t*& o_ln, const uint8_t*& o_val, const int64_t*& o_sel,
+                int64_t& o_n) {
         o_st = d_starts.as<int64_t>();
         o_ln = d_lens.as<uint32_t>();
         o_val = d_valid.as<uint8_t>();
+        o_sel = nullptr;
         o_n = n;
         if (root < 0 || n == 0) return true;
+        NvtxRange nv("exb:select");
         if (!d_pass.need(n)) return fail("out of device memory");
         EvalCtx c{col_buf, o_st, o_ln, o_val, n};
         cst_keep.clear();
@@ -996,6 +1438,9 @@ struct Reader {
         int64_t cnt = 0;
         if (!cu(cudaMemcpyAsync(&cnt, d_off.as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, st), "D2H count")) return false;
         if (!cu(cudaStreamSynchronize(st), "sync")) return false;
+        o_n = cnt;
+        o_sel = d_sel.as<int64_t>();
+        if (count_only.load()) return true;  // COUNT(*): the number of passing rows is all that is needed
         if (!d_lens2.need(std::max<int64_t>(cnt, 1) * 4 * ncols) || !d_starts2.need(std::max<int64_t>(cnt, 1) * 8 * ncols) ||
             !d_valid2.need(std::max<int64_t>(cnt, 1)))
             return fail("out of device memory");
@@ -1007,7 +1452,6 @@ struct Reader {
         o_st = d_starts2.as<int64_t>();
         o_ln = d_lens2.as<uint32_t>();
         o_val = d_valid2.as<uint8_t>();
-        o_n = cnt;
         return true;
     }
 
@@ -1016,12 +1460,15 @@ struct Reader {
         grew = false;
         const std::string& fname = files[cur_file];
         const int64_t ws_bytes = exb_scan_workspace_bytes(n + 16);
-        if (!d_ws.need(ws_bytes)) return fail("out of device memory");
+        if (!d_ws.need(ws_bytes) || !d_info.need(64)) return fail("out of device memory");
         exb_scan_result res;
+        double t0 = now();
         if (format == 2) {
-            const bool numeric = needs_numeric();
+            const bool numeric = needs_numeric() || has_computed(EXB_C_GC_CONTENT) || has_computed(EXB_C_MEAN_QUALITY);
             int64_t rec_cap = n / 32 + 4096;
+            int64_t info[2] = {0, 0};
             for (int attempt = 0;; attempt++) {
+                NvtxRange nv("exb:scan");
                 if (attempt && !d_ws.need(exb_fastq_workspace_bytes(n + 16, n + 1))) return fail("out of device memory");
                 if (!d_line.need(rec_cap * 4 * 4)) return fail("out of device memory");
                 if (numeric)
@@ -1031,45 +1478,54 @@ struct Reader {
                                        d_line.p, rec_cap * 4, 0, d_arr[0].as<uint32_t>(), d_arr[1].as<uint32_t>(), d_arr[2].as<uint32_t>(),
                                        d_arr[3].as<int32_t>(), rec_cap, d_ws.p, d_ws.cap, st)))
                     return false;
+                // where the last complete record ends: fetched together with the result block (one sync)
+                if (!cu(fastq_chunk_info_launch(d_ws.p, d_line.as<uint32_t>(), d_info.as<int64_t>(), st), "chunk_info")) return false;
+                if (!cu(cudaMemcpyAsync(info, d_info.p, 16, cudaMemcpyDeviceToHost, st), "D2H")) return false;
+                if (attempt == 0 && !flush_pending()) return false;  // the previous chunk's result goes out while this scan runs
                 if (!rc(exb_scan_result_fetch(d_ws.p, &res, st))) return false;
                 if (!res.overflow) break;
                 if (attempt) return fail("internal: record capacity");
                 rec_cap = n / 4 + 16;
             }
+            t_scan += now() - t0;
             if (res.err_pos != ~0ull)
-                return fail("invalid FASTQ record at byte " + std::to_string(cur_file_pos + (int64_t)res.err_pos) + " of " + fname);
+                return fail("invalid FASTQ record at byte " + std::to_string(cur_file_pos + (int64_t)res.err_pos) + " of " + fname + shard_note());
             int64_t R = (int64_t)(res.total_lines / 4);
             if (is_final) {
-                if (res.total_lines % 4 != 0) return fail("unexpected EOF in FASTQ record of " + fname);
+                if (res.total_lines % 4 != 0) return fail("unexpected EOF in FASTQ record of " + fname + shard_note());
                 consumed = n;
             } else {
                 if (R == 0) { grew = true; consumed = 0; return true; }
-                uint32_t last = 0;
-                if (!cu(cudaMemcpyAsync(&last, d_line.as<uint32_t>() + (4 * R - 1), 4, cudaMemcpyDeviceToHost, st), "D2H")) return false;
-                if (!cu(cudaStreamSynchronize(st), "sync")) return false;
-                consumed = (int64_t)last + 1;
+                consumed = info[0];
             }
-            if (count_only && root < 0) {  // COUNT(*) without a filter: the scan's record count is the answer
+            if (count_only.load() && root < 0) {  // COUNT(*) without a filter: the scan's record count is the answer
                 item->counted = R;
                 return true;
             }
+            t0 = now();
             if (!d_lens.need(std::max<int64_t>(R, 1) * 16) || !d_starts.need(std::max<int64_t>(R, 1) * 32) || !d_valid.need(std::max<int64_t>(R, 1)))
                 return fail("out of device memory");
             if (!rc(exb_fastq_fields(d_cur, 0, n, d_line.p, 0, nullptr, R, d_lens.as<uint32_t>(), d_valid.as<uint8_t>(), d_starts.as<int64_t>(), d_ws.p, st)))
                 return false;
             const uint8_t* bufs[4] = {d_cur, d_cur, d_cur, d_cur};
-            const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; int64_t o_n;
-            if (!select(bufs, R, o_st, o_ln, o_val, o_n)) return false;
-            return materialise(bufs, o_st, o_ln, o_val, o_n, item);
+            const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; const int64_t* o_sel; int64_t o_n;
+            if (!select(bufs, R, o_st, o_ln, o_val, o_sel, o_n)) return false;
+            t_select += now() - t0;
+            t0 = now();
+            const bool ok = materialise(bufs, o_st, o_ln, o_val, o_sel, o_n, item);
+            t_mat += now() - t0;
+            return ok;
         }
         // ---- FASTA
         // the sequence column is compacted by the scan itself; skip that when nobody reads the bytes
-        // (projection push-down, COUNT(*); string predicates on `sequence` still need them)
-        bool want_seq = ((column_mask >> 2) & 1u) != 0 && !count_only;
+        // (projection push-down, COUNT(*); string predicates on `sequence` and mapped copies of it still need them)
+        bool want_seq = ((column_mask >> 2) & 1u) != 0 && !count_only.load();
         for (const Node& nd : nodes)
             if (nd.kind == N_STR && nd.col == 2) want_seq = true;
+        if (has_computed(EXB_C_SEQ_MAP) && !count_only.load()) want_seq = true;
         int64_t rec_cap = n / 64 + 4096;
         for (int attempt = 0;; attempt++) {
+            NvtxRange nv("exb:scan");
             if (!d_hdr_start.need(rec_cap * 8) || !d_hdr_end.need(rec_cap * 8) || !d_seq_off.need((rec_cap + 1) * 8) ||
                 !d_gc_prefix.need((rec_cap + 1) * 8) || (want_seq && !d_seq.need(n + 64)))
                 return fail("out of device memory");
@@ -1077,11 +1533,13 @@ struct Reader {
                                    d_seq_off.as<int64_t>(), d_gc_prefix.as<int64_t>(), rec_cap, want_seq ? d_seq.as<uint8_t>() : nullptr,
                                    want_seq ? n + 64 : 0, d_ws.p, d_ws.cap, st)))
                 return false;
+            if (attempt == 0 && !flush_pending()) return false;
             if (!rc(exb_scan_result_fetch(d_ws.p, &res, st))) return false;
             if (!res.overflow) break;
             if (attempt) return fail("internal: record capacity");
             rec_cap = n / 2 + 16;
         }
+        t_scan += now() - t0;
         if (res.err_pos != ~0ull)
             return fail("invalid FASTA input (missing '>' prefix) at byte " + std::to_string(cur_file_pos + (int64_t)res.err_pos) + " of " + fname);
         int64_t R = (int64_t)res.n_records;
@@ -1094,6 +1552,7 @@ struct Reader {
             if (!cu(cudaStreamSynchronize(st), "sync")) return false;
             consumed = hs;
         }
+        t0 = now();
         if (!d_lens.need(std::max<int64_t>(R, 1) * 12) || !d_starts.need(std::max<int64_t>(R, 1) * 24) || !d_valid.need(std::max<int64_t>(R, 1)) ||
             !d_err.need(8))
             return fail("out of device memory");
@@ -1108,31 +1567,46 @@ struct Reader {
         if (!cu(cudaStreamSynchronize(st), "sync")) return false;
         if (bad != ~0ull) return fail("FASTA definition without a name at byte " + std::to_string(cur_file_pos + (int64_t)bad) + " of " + fname);
         const uint8_t* bufs[3] = {d_cur, d_cur, d_seq.as<uint8_t>()};
-        const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; int64_t o_n;
-        if (!select(bufs, R, o_st, o_ln, o_val, o_n)) return false;
-        return materialise(bufs, o_st, o_ln, o_val, o_n, item);
+        const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; const int64_t* o_sel; int64_t o_n;
+        if (!select(bufs, R, o_st, o_ln, o_val, o_sel, o_n)) return false;
+        t_select += now() - t0;
+        t0 = now();
+        const bool ok = materialise(bufs, o_st, o_ln, o_val, o_sel, o_n, item);
+        t_mat += now() - t0;
+        return ok;
+    }
+    std::string shard_note() const {
+        if (range_lo <= 0 && range_hi <= 0) return "";
+        return " (byte-range shard [" + std::to_string(shard_begin) + ", " + std::to_string(shard_end) +
+               "): if the file is well formed, the shard cut could not be resynchronised -- rerun with one reader)";
     }
 
     // A chunk = the unconsumed tail of the previous chunk (it never left HBM: a device-to-device move to the front of
     // the other input buffer) followed by the next raw block.  While chunk k is scanned, split and copied back, block
     // k+1 -- if the IO thread already has it -- crosses PCIe on the copy stream into a staging buffer, so H2D of k+1
-    // overlaps the kernels and the D2H of k (two copy engines, opposite directions).
+    // overlaps the kernels of k and the D2H of k-1 (two copy engines, opposite directions).
     void dev_main() {
         HBuf* host_cur = nullptr;     // pinned block whose bytes may still be in flight to the device
         Block staged;                 // the prefetched block (its pinned buffer included); valid when have_staged
         bool have_staged = false, staged_on_device = false;
         int cur = 0;
         int64_t carry_off = 0, carry_len = 0;  // the tail lives in d_inb[cur] at [carry_off, carry_off + carry_len)
-        auto finish = [&](const std::string& err) {
+        auto finish = [&](const std::string& err_in) {
+            std::string err = err_in;
+            if (err.empty() && !flush_pending()) err = derr;
             cudaStreamSynchronize(sc);
             cudaStreamSynchronize(st);
+            cudaStreamSynchronize(sd);
             pool->put(host_cur);
             if (have_staged) pool->put(staged.h);
+            pending = OutItem();
+            free_device();
             OutItem e;
             e.end = true;
             e.error = err;
             outq.push(std::move(e));
         };
+        if (!init_device()) return finish(derr);
         while (!stopping) {
             Block b;
             bool on_device = false;
@@ -1141,6 +1615,7 @@ struct Reader {
                 on_device = staged_on_device;
                 have_staged = false;
             } else {
+                if (!flush_pending()) return finish(derr);  // nothing to overlap with: do not sit on a finished result
                 double t0 = now();
                 const bool popped = inq.pop(b);
                 t_dev_pop += now() - t0;
@@ -1148,6 +1623,7 @@ struct Reader {
             }
             if (b.end) return finish(b.error);
             double t0 = now();
+            NvtxRange nv("exb:chunk");
             // ---- assemble chunk k in the other input buffer
             const int nxt = cur ^ 1;
             const int64_t n = carry_len + b.raw_len;
@@ -1204,8 +1680,11 @@ struct Reader {
             }
             carry_off = consumed;
             carry_len = n - consumed;
+            bytes_done.fetch_add(consumed);
             t_dev_work += now() - t0;
-            if (item.res || item.counted) {
+            if (item.res) {
+                pending = std::move(item);  // goes out once its D2H has drained (flush_pending)
+            } else if (item.counted) {
                 t0 = now();
                 const bool pushed = outq.push(std::move(item));
                 t_dev_push += now() - t0;
@@ -1214,16 +1693,22 @@ struct Reader {
         }
         cudaStreamSynchronize(sc);
         cudaStreamSynchronize(st);
+        cudaStreamSynchronize(sd);
         pool->put(host_cur);
         if (have_staged) pool->put(staged.h);
+        pending = OutItem();
+        free_device();
     }
 
-    // ------------------------------------------------------------------ caller
+    // ------------------------------------------------------------------ caller (under call_mu)
     // make rows available; false = end of stream or error (check `error`)
     bool advance() {
         if (finished) return false;
-        if (!ensure_device()) return false;  // before any pinned allocation: "no CUDA device" is the message a CPU-only host must see
         if (!started) {
+            if (!check_device()) {
+                finished = true;
+                return false;
+            }
             started = true;
             block_bytes.store(chunk_bytes);
             io_thread = std::thread([this] { io_main(); });
@@ -1313,6 +1798,7 @@ int stream_get_schema(ArrowArrayStream* s, ArrowSchema* out) {
 int stream_get_next(ArrowArrayStream* s, ArrowArray* out) {
     Reader* r = reinterpret_cast<Reader*>(s->private_data);
     memset(out, 0, sizeof(*out));
+    std::lock_guard<std::mutex> guard(r->call_mu);
     if (!r->advance()) {
         if (!r->error.empty()) return 5;  // EIO; message through get_last_error
         out->release = nullptr;           // end of stream
@@ -1334,12 +1820,15 @@ int stream_get_next(ArrowArrayStream* s, ArrowArray* out) {
     h->ncols = r->ncols;
     int64_t nulls = 0;
     h->validity.assign((size_t)((k + 7) / 8), 0);
+    const uint8_t* desc_valid = nullptr;
+    for (int c = 0; c < r->ncols; c++)
+        if (r->cur->cols[c].valid) desc_valid = r->cur->cols[c].valid;
     for (int64_t i = 0; i < k; i++) {
-        if (r->cur->valid[b + i]) h->validity[i >> 3] |= (uint8_t)(1u << (i & 7));
+        if (!desc_valid || desc_valid[b + i]) h->validity[i >> 3] |= (uint8_t)(1u << (i & 7));
         else nulls++;
     }
     for (int c = 0; c < r->ncols; c++) {
-        const ChunkColumn& col = r->cur->cols[c];
+        const OutCol& col = r->cur->cols[c];
         h->off[c].assign((size_t)k + 1, 0);
         if (col.off) {
             const int64_t base = col.off[b];
@@ -1514,19 +2003,119 @@ struct exb_reader {
     std::string err;
 };
 
-int exb_reader_open(const char* uri, const char* file_format, const char* compression, int64_t batch_rows, const char* filters,
-                    uint32_t column_mask, exb_reader** out) {
+static int apply_options(Reader* r, const exb_reader_options* o, std::string* err) {
+    if (!o) return 0;
+    if (o->size < sizeof(exb_reader_options)) {
+        *err = "exb_reader_open2: options struct is older than this library";
+        return -1;
+    }
+    r->device = o->device;
+    r->column_mask = o->column_mask;
+    r->flags = o->flags;
+    if (o->n_computed < 0 || o->n_computed > EXB_MAX_COMPUTED) {
+        *err = "exb_reader_open2: too many computed columns";
+        return -1;
+    }
+    for (int i = 0; i < o->n_computed; i++) {
+        const exb_computed& c = o->computed[i];
+        const bool fastq_only = c.kind == EXB_C_QUALITY_LIST || c.kind == EXB_C_MEAN_QUALITY || c.kind == EXB_C_QUAL_LENGTH;
+        if (c.kind < EXB_C_GC_CONTENT || c.kind > EXB_C_QUAL_LENGTH || (fastq_only && r->format != 2) ||
+            (c.kind == EXB_C_SEQ_MAP && (c.arg < EXB_MAP_REVERSE_COMPLEMENT || c.arg > EXB_MAP_REVERSE_TRANSCRIBE))) {
+            *err = "exb_reader_open2: computed column " + std::to_string(i) + " is not applicable to this file format";
+            return -1;
+        }
+        r->computed.push_back(c);
+    }
+    if (o->range_lo > 0 || o->range_hi > 0) {
+        if (r->files.size() != 1 || r->file_comp[0] != 0) {
+            *err = "exb_reader_open2: byte-range shards need one uncompressed file";
+            return -1;
+        }
+        if (o->range_lo < 0 || (o->range_hi > 0 && o->range_hi < o->range_lo)) {
+            *err = "exb_reader_open2: bad byte range";
+            return -1;
+        }
+        r->range_lo = o->range_lo;
+        r->range_hi = o->range_hi;
+    }
+    if (o->file_hi > 0 || o->file_lo > 0) {
+        const size_t lo = (size_t)std::max(o->file_lo, 0), hi = o->file_hi > 0 ? std::min((size_t)o->file_hi, r->files.size()) : r->files.size();
+        if (lo > hi) {
+            *err = "exb_reader_open2: bad file range";
+            return -1;
+        }
+        r->files = std::vector<std::string>(r->files.begin() + lo, r->files.begin() + hi);
+        r->file_comp = std::vector<int>(r->file_comp.begin() + lo, r->file_comp.begin() + hi);
+    }
+    return 0;
+}
+
+static void measure_input(Reader* r) {
+    int64_t total = 0;
+    for (const std::string& f : r->files) {
+        struct stat sb;
+        if (stat(f.c_str(), &sb) == 0) total += sb.st_size;
+    }
+    if (r->range_lo > 0 || r->range_hi > 0) {
+        const int64_t hi = r->range_hi > 0 ? std::min(r->range_hi, total) : total;
+        total = std::max<int64_t>(hi - std::min(r->range_lo, hi), 0);
+    }
+    r->bytes_total.store(total);
+}
+
+int exb_reader_open2(const char* uri, const char* file_format, const char* compression, int64_t batch_rows, const char* filters,
+                     const exb_reader_options* options, exb_reader** out) {
     if (!out) return set_err(EXB_ERR_ARG, "exb_reader_open: null out");
     *out = nullptr;
     std::string err;
     Reader* r = open_reader(uri, (uintptr_t)(batch_rows > 0 ? batch_rows : 2048), compression, file_format, filters, &err);
     if (!r) return set_err(err.find("no such file") != std::string::npos || err.find("could not list") != std::string::npos ? EXB_ERR_IO : EXB_ERR_ARG,
                            "%s", err.c_str());
-    r->column_mask = column_mask;
+    if (apply_options(r, options, &err) != 0) {
+        delete r;
+        return set_err(EXB_ERR_ARG, "%s", err.c_str());
+    }
+    measure_input(r);
     exb_reader* h = new exb_reader();
     h->r = r;
     *out = h;
     return 0;
+}
+
+int exb_reader_open(const char* uri, const char* file_format, const char* compression, int64_t batch_rows, const char* filters,
+                    uint32_t column_mask, exb_reader** out) {
+    exb_reader_options o;
+    memset(&o, 0, sizeof(o));
+    o.size = sizeof(o);
+    o.device = -1;
+    o.column_mask = column_mask;
+    return exb_reader_open2(uri, file_format, compression, batch_rows, filters, &o, out);
+}
+
+int exb_reader_plan(const char* uri, const char* file_format, const char* compression, int64_t* total_bytes, int32_t* n_files,
+                    int32_t* range_shardable) {
+    std::string err;
+    Reader* r = open_reader(uri, 2048, compression, file_format, nullptr, &err);
+    if (!r) return set_err(err.find("no such file") != std::string::npos || err.find("could not list") != std::string::npos ? EXB_ERR_IO : EXB_ERR_ARG,
+                           "%s", err.c_str());
+    measure_input(r);
+    if (total_bytes) *total_bytes = r->bytes_total.load();
+    if (n_files) *n_files = (int32_t)r->files.size();
+    if (range_shardable) {
+        struct stat sb;
+        *range_shardable = r->files.size() == 1 && r->file_comp[0] == 0 && stat(r->files[0].c_str(), &sb) == 0 && S_ISREG(sb.st_mode) ? 1 : 0;
+    }
+    delete r;
+    return 0;
+}
+
+int exb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
 }
 
 int exb_reader_columns(const exb_reader* h, const char** names, int cap) {
@@ -1535,28 +2124,58 @@ int exb_reader_columns(const exb_reader* h, const char** names, int cap) {
     return h->r->ncols;
 }
 
+static int reader_failure(exb_reader* h) {
+    Reader* r = h->r;
+    h->err = r->error;
+    const bool fmt = r->error.find("invalid FAST") != std::string::npos || r->error.find("unexpected EOF") != std::string::npos ||
+                     r->error.find("without a name") != std::string::npos;
+    const bool chr = r->error.find("Invalid character in sequence") != std::string::npos;
+    return set_err(chr ? EXB_ERR_INVALID_CHAR : (fmt ? EXB_ERR_FORMAT : (r->error.find("CUDA") != std::string::npos ? EXB_ERR_CUDA : EXB_ERR_IO)),
+                   "%s", r->error.c_str());
+}
+
 int exb_reader_next(exb_reader* h, exb_batch* out) {
     if (!h || !out) return set_err(EXB_ERR_ARG, "exb_reader_next: null argument");
     Reader* r = h->r;
     memset(out, 0, sizeof(*out));
+    std::lock_guard<std::mutex> guard(r->call_mu);
     if (!r->advance()) {
-        if (!r->error.empty()) {
-            h->err = r->error;
-            const bool fmt = r->error.find("invalid FAST") != std::string::npos || r->error.find("unexpected EOF") != std::string::npos ||
-                             r->error.find("without a name") != std::string::npos;
-            return set_err(fmt ? EXB_ERR_FORMAT : (r->error.find("CUDA") != std::string::npos ? EXB_ERR_CUDA : EXB_ERR_IO), "%s", r->error.c_str());
-        }
+        if (!r->error.empty()) return reader_failure(h);
         return 0;  // end of stream: n_rows = 0
     }
     const int64_t b = r->next_row, e = std::min(r->rows, b + r->batch_size);
-    out->n_rows = e - b;
+    const int64_t k = e - b;
+    out->n_rows = k;
     out->n_cols = r->ncols;
-    for (int c = 0; c < r->ncols; c++) {
-        const ChunkColumn& col = r->cur->cols[c];
-        if (!col.off) continue;  // projected out
-        out->cols[c].offsets = col.off + b;
-        out->cols[c].data = col.data;
-        if (r->col_names[c] == "description") out->cols[c].valid = r->cur->valid + b;
+    out->n_computed = (int32_t)r->computed.size();
+    out->batch_index = r->next_batch_index++;
+    const bool word_aligned = (b & 63) == 0;
+    for (int c = 0; c < r->n_out(); c++) {
+        const OutCol& col = r->cur->cols[c];
+        exb_column_view& v = out->cols[c];
+        v.type = col.type;
+        v.kind = col.kind;
+        if (!col.present) continue;  // projected out
+        const bool has_nulls = col.valid && col.nulls_word && *col.nulls_word != 0;
+        if (col.type == EXB_T_VARCHAR) {
+            if (col.off) v.offsets = col.off + b;
+            v.data = col.data;
+            if (col.str) v.strings = col.str + 16 * b;
+        } else if (col.type == EXB_T_INT32_LIST) {
+            const int64_t kb = b / r->batch_size;
+            v.values = col.values + 4 * col.batch_base[kb];
+            v.n_values = col.batch_base[kb + 1] - col.batch_base[kb];
+            v.list_entries = col.entries + 2 * b;
+            if (col.off) v.offsets = col.off + b;
+        } else {
+            v.values = col.values + (int64_t)col.elem * b;
+            v.n_values = k;
+        }
+        if (col.valid) {
+            v.valid = col.valid + b;
+            v.chunk_nulls = col.nulls_word ? (int64_t)*col.nulls_word : -1;
+            if (has_nulls && word_aligned) v.valid_bits = col.vbits + (b >> 6);
+        }
     }
     out->owner = new std::shared_ptr<ChunkResult>(r->cur);
     r->next_row = e;
@@ -1572,14 +2191,23 @@ void exb_batch_release(exb_batch* b) {
 int exb_reader_count(exb_reader* h, int64_t* n_rows) {
     if (!h || !n_rows) return set_err(EXB_ERR_ARG, "exb_reader_count: null argument");
     Reader* r = h->r;
-    r->count_only = true;
+    std::lock_guard<std::mutex> guard(r->call_mu);
+    r->count_only.store(true);
+    // rows of chunks that were materialised before the switch are counted where they sit; advance() only returns
+    // true with unread rows in hand, so each iteration consumes them
     while (r->advance()) {
+        r->counted += r->rows - r->next_row;
+        r->next_row = r->rows;
     }
-    if (!r->error.empty()) {
-        h->err = r->error;
-        return set_err(r->error.find("CUDA") != std::string::npos ? EXB_ERR_CUDA : EXB_ERR_FORMAT, "%s", r->error.c_str());
-    }
+    if (!r->error.empty()) return reader_failure(h);
     *n_rows = r->counted;
+    return 0;
+}
+
+int exb_reader_progress(const exb_reader* h, int64_t* bytes_done, int64_t* bytes_total) {
+    if (!h) return set_err(EXB_ERR_ARG, "exb_reader_progress: null reader");
+    if (bytes_done) *bytes_done = h->r->bytes_done.load();
+    if (bytes_total) *bytes_total = h->r->bytes_total.load();
     return 0;
 }
 

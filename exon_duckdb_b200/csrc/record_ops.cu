@@ -618,6 +618,12 @@ cudaError_t gather_ranges_launch(const uint8_t* buf, const int64_t* start, const
     return gather_span_launch(buf, SrcRanges{start}, off, n_rows, total_bound, out, st);
 }
 
+// the same through one of the reference's byte maps (EXB_MAP_*): *bad = ~0, or (position in out << 8) | byte, smallest position
+cudaError_t gather_ranges_map_launch(const uint8_t* buf, const int64_t* start, const int64_t* off, int64_t n_rows, int64_t total_bound,
+                                     uint8_t* out, int mode, unsigned long long* bad, cudaStream_t st) {
+    return gather_span_launch(buf, SrcRanges{start}, off, n_rows, total_bound, out, st, mode, bad);
+}
+
 cudaError_t fastq_filter_launch(const uint32_t* seq_len, const uint32_t* gc, const uint32_t* qual_len, const int32_t* qsum, int64_t n,
                                 const exb_predicate* preds, int n_preds, uint8_t* pass, int64_t* agg, const void* scan_ws,
                                 cudaStream_t st) {

@@ -446,20 +446,3 @@ def quality_score_string_to_list(col):
     out = _empty(nb, torch.int32, col.offsets.device)
     check(lib().exb_quality_decode(_ptr(col.data), nb, _ptr(out), _stream()))
     return out
-
-
-def gen_device(params, device="cuda"):
-    """Synthetic FASTA/FASTQ text generated on the device."""
-    size = lib().exb_gen_size(C.byref(params))
-    buf = alloc_input(size, device)
-    check(lib().exb_gen_device(C.byref(params), _ptr(buf), size, _stream()))
-    return buf
-
-
-def gen_host(params):
-    import numpy as np
-
-    size = lib().exb_gen_size(C.byref(params))
-    out = np.empty(size, dtype=np.uint8)
-    check(lib().exb_gen_host(C.byref(params), C.c_void_p(out.ctypes.data), size))
-    return out

@@ -140,27 +140,100 @@ EXB_API void exb_free_string(const char *s);
  *   exb_reader_next / exb_reader_close -- a host may hand out pointers into them (DuckDB string_t).
  */
 typedef struct exb_reader exb_reader;
+
+/* Computed output columns: a scalar function of the reference applied to a column of the scan, evaluated on the
+ * device while the chunk is in HBM, so that `SELECT gc_content(sequence) FROM read_fasta(..)` never ships the
+ * sequence bytes to the host (north_star kernel (3); the DuckDB extension's OptimizerExtension rewrites such
+ * projections into these).  Replaces the per-row loops of sequence_functions/module.cpp:30-253 and
+ * fastq_functions/module.cpp:32-50 for inputs that come straight from the scan. */
+#define EXB_C_GC_CONTENT 1   /* gc_content(sequence)                       -> FLOAT   (module.cpp:131-158)           */
+#define EXB_C_SEQ_MAP 2      /* reverse_complement | complement | transcribe | reverse_transcribe (sequence)
+                                                                           -> VARCHAR, arg = EXB_MAP_*               */
+#define EXB_C_QUALITY_LIST 3 /* quality_score_string_to_list(quality_scores) -> INTEGER[] (fastq_functions:32-50)   */
+#define EXB_C_MEAN_QUALITY 4 /* list_avg(quality_score_string_to_list(quality_scores)) -> DOUBLE, NULL for ''      */
+#define EXB_C_SEQ_LENGTH 5   /* length(sequence)       -> BIGINT (bytes; equals DuckDB's length() for ASCII only,
+                                so the extension uses it for strlen(), not length())                                */
+#define EXB_C_QUAL_LENGTH 6  /* strlen(quality_scores) -> BIGINT                                                    */
+typedef struct exb_computed {
+    int32_t kind; /* EXB_C_* */
+    int32_t arg;  /* EXB_C_SEQ_MAP: EXB_MAP_* */
+} exb_computed;
+#define EXB_MAX_COMPUTED 8
+
+#define EXB_RD_STRING_T 1 /* VARCHAR columns also come back as arrays of 16-byte DuckDB string_t (string_type.hpp:19-60):
+                             {u32 length, 12 inlined bytes} or {u32 length, 4-byte prefix, pointer into the batch's
+                             host buffer}, built on the device -- the host's SetVectorString loop
+                             (arrow_conversion.cpp:252-266) becomes one pointer assignment per column           */
+#define EXB_RD_NO_OFFSETS 2 /* do not copy the Arrow-style int64 offsets back (hosts that only read string_t)    */
+
+typedef struct exb_reader_options {
+    uint32_t size;       /* sizeof(exb_reader_options) of the caller (versioning)                                  */
+    int32_t device;      /* CUDA device ordinal that runs this reader's pipeline; -1 = the caller's current device */
+    /* Byte-range shard of ONE uncompressed file: this reader owns the records whose first byte lies in
+     * [range_lo, range_hi).  Both ends are moved forward to the next record start by the same host-side rule
+     * (FASTA: next line that starts with '>'; FASTQ: next line start where '@' / '+' alternate two lines apart over a
+     * window of records), so adjacent shards agree on the cut by construction; the shard is then parsed as a complete
+     * input, and a FASTQ cut that is not a true record boundary fails the scan's own line-count / '@' / '+' checks --
+     * an error, never a silently different result.  range_hi <= 0: no upper limit.                               */
+    int64_t range_lo, range_hi;
+    /* Directory inputs: of the sorted file list, this reader takes the files [file_lo, file_hi); file_hi <= 0: all. */
+    int32_t file_lo, file_hi;
+    uint32_t column_mask; /* bit c: file column c is wanted                                                        */
+    uint32_t flags;       /* EXB_RD_*                                                                              */
+    int32_t n_computed;
+    exb_computed computed[EXB_MAX_COMPUTED];
+} exb_reader_options;
+
+#define EXB_T_VARCHAR 0
+#define EXB_T_FLOAT 1
+#define EXB_T_DOUBLE 2
+#define EXB_T_INT32_LIST 3
+#define EXB_T_INT64 4
 typedef struct exb_column_view {
-    const int64_t *offsets; /* n_rows + 1 entries, NULL if the column was projected out */
-    const uint8_t *data;
-    const uint8_t *valid;   /* one byte per row (0 = NULL), or NULL = all rows valid      */
+    const int64_t *offsets; /* VARCHAR: n_rows + 1 entries (NOT rebased to 0), NULL if projected out / not requested */
+    const uint8_t *data;    /* VARCHAR: the bytes `offsets` index                                                     */
+    const uint8_t *valid;   /* one byte per row (0 = NULL), or NULL = all rows valid                                  */
+    int32_t type;           /* EXB_T_*                                                                                */
+    int32_t kind;           /* 0 = column of the file, else EXB_C_*                                                   */
+    const void *strings;    /* VARCHAR with EXB_RD_STRING_T: n_rows 16-byte string_t entries                          */
+    int64_t chunk_nulls;    /* nullable columns: NULL rows in the chunk this batch is a slice of (0: skip `valid`)        */
+    const uint64_t *valid_bits; /* the same validity as a bitmap (bit i%64 of word i/64) when chunk_nulls > 0 and the
+                                   batch starts at a multiple of 64 rows of its chunk (batch_rows % 64 == 0), else NULL */
+    const void *values;     /* FLOAT / DOUBLE / INT64: n_rows values;  INT32_LIST: the n_values child values          */
+    const uint64_t *list_entries; /* INT32_LIST: n_rows x {offset, length} (DuckDB list_entry_t), offsets into values */
+    int64_t n_values;
 } exb_column_view;
 typedef struct exb_batch {
     int64_t n_rows;         /* 0 = end of stream */
-    int32_t n_cols;
-    exb_column_view cols[4];
+    int32_t n_cols;         /* columns of the file; the computed columns follow them in cols[] */
+    int32_t n_computed;
+    int64_t batch_index;    /* position of this batch in the reader's output order (0, 1, 2, ...) */
+    exb_column_view cols[4 + EXB_MAX_COMPUTED];
     void *owner;
 } exb_batch;
 EXB_API int exb_reader_open(const char *uri, const char *file_format, const char *compression, int64_t batch_rows,
                             const char *filters, uint32_t column_mask, exb_reader **out);
+/* The same with a device, a shard and computed columns (options->column_mask replaces the argument). */
+EXB_API int exb_reader_open2(const char *uri, const char *file_format, const char *compression, int64_t batch_rows,
+                             const char *filters, const exb_reader_options *options, exb_reader **out);
 /* column names in schema order; returns the number of columns */
 EXB_API int exb_reader_columns(const exb_reader *reader, const char **names, int cap);
+/* Thread-safe: several host threads may pull batches from one reader (each batch goes to exactly one of them). */
 EXB_API int exb_reader_next(exb_reader *reader, exb_batch *out);
 EXB_API void exb_batch_release(exb_batch *batch);
-/* COUNT(*): consumes the rest of the stream; rows that pass the filters are counted on the device and nothing
- * is gathered or copied back (arrow_conversion.cpp:813-816 is the reference's row-id-only case). */
+/* COUNT(*): consumes the rest of the stream (rows of a batch that was already handed out are not counted again);
+ * rows that pass the filters are counted on the device and nothing is gathered or copied back
+ * (arrow_conversion.cpp:813-816 is the reference's row-id-only case). */
 EXB_API int exb_reader_count(exb_reader *reader, int64_t *n_rows);
+/* Input bytes handed to the device so far / input bytes in total (table_scan_progress). */
+EXB_API int exb_reader_progress(const exb_reader *reader, int64_t *bytes_done, int64_t *bytes_total);
+/* Size in bytes of the (uncompressed, single-file) input a uri names, the number of files of a directory input, and
+ * whether byte-range shards apply (1) -- what a host needs to plan one reader per GPU. */
+EXB_API int exb_reader_plan(const char *uri, const char *file_format, const char *compression, int64_t *total_bytes,
+                            int32_t *n_files, int32_t *range_shardable);
 EXB_API void exb_reader_close(exb_reader *reader);
+/* CUDA devices visible to the process (0 when there is none). */
+EXB_API int exb_device_count(void);
 
 /* ---------------------------------------------------------------------------
  * (2) Device layer
@@ -432,26 +505,6 @@ EXB_API int exb_seq_map_host(const uint8_t *data, int64_t n_bytes, int mode, uin
 EXB_API int exb_translate_host(const int64_t *offsets, const uint8_t *data, int64_t n_rows, uint8_t *out,
                                int64_t *status);
 EXB_API int exb_quality_decode_host(const uint8_t *data, int64_t n_bytes, int32_t *out);
-
-/* ---- deterministic synthetic inputs, counter-based RNG ---- */
-#define EXB_GEN_ILLUMINA 2 /* C2/C5: 150 bp reads, '@SIM:1:FC1:lane:tile:x:y 1:N:0:ACGTACGT' */
-#define EXB_GEN_ONT 4      /* C4: 10-50 kb reads                                               */
-#define EXB_GEN_FASTA 1    /* C1/C3: wrapped FASTA                                              */
-typedef struct exb_gen_params {
-    int32_t kind;
-    uint64_t seed;
-    int64_t n_records;
-    int64_t first_record; /* global index of record 0 of this call (sharded generation) */
-    int32_t len_min, len_max; /* read / contig length range (inclusive) */
-    int32_t wrap;         /* FASTA line width */
-    int32_t crlf;         /* 1 = CRLF line ends */
-} exb_gen_params;
-/* Size in bytes of the text the parameters describe (host computation, exact). */
-EXB_API int64_t exb_gen_size(const exb_gen_params *p);
-/* Generate on the device: d_out must hold exb_gen_size(p) bytes (+16 slack). Synchronous. */
-EXB_API int exb_gen_device(const exb_gen_params *p, void *d_out, int64_t cap, void *stream);
-/* Generate on the host (same bytes), no GPU needed. */
-EXB_API int exb_gen_host(const exb_gen_params *p, void *out, int64_t cap);
 
 /* ---- host-buffer engine (end-to-end path): parse a FASTQ held in host memory ----
  * Streams `n` host bytes through pinned staging buffers with double-buffered

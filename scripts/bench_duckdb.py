@@ -43,11 +43,12 @@ def main():
         if not os.path.exists(p):
             raise SystemExit("%s is missing (bash oracle/build_ref.sh; make -C exon_duckdb_b200/duckdb_ext)" % p)
     from exon_duckdb_b200 import _lib, device as D
+    from tools import synth
 
     big = os.path.join(args.dir, "exb_duck_big.fastq")
     small = os.path.join(args.dir, "exb_duck_small.fastq")
-    D.gen_host(_lib.gen_params("illumina", args.reads, seed=20)).tofile(big)
-    D.gen_host(_lib.gen_params("illumina", args.ref_reads, seed=20)).tofile(small)
+    synth.gen_host(synth.gen_params("illumina", args.reads, seed=20)).tofile(big)
+    synth.gen_host(synth.gen_params("illumina", args.ref_reads, seed=20)).tofile(small)
     mq = "list_avg(quality_score_string_to_list(quality_scores)) > 30"
     queries = [
         ("COUNT(*)", "SELECT COUNT(*) FROM read_fastq('%s')"),

@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from exon_duckdb_b200 import _lib, device as D
+from tools import synth
 
 
 ITERS = None  # --iters overrides every call (profiling runs under ncu)
@@ -65,8 +66,8 @@ def main():
         print("%-58s %9.3f ms  %8.1f GB/s  %5.1f%% of %.0f  %s" % (name, ms_med, gbs, 100 * gbs / peak, peak, note), flush=True)
 
     # ---------------- C2: Illumina FASTQ
-    p = _lib.gen_params("illumina", args.reads, seed=20)
-    buf = D.gen_device(p, dev)
+    p = synth.gen_params("illumina", args.reads, seed=20)
+    buf = synth.gen_device(p, dev)
     n = buf.numel()
     preds = [("mean_quality", ">", 30.0)]
     c = D.fastq_scan_filter(buf, preds)
@@ -109,8 +110,8 @@ def main():
     torch.cuda.empty_cache()
 
     # ---------------- C4: ONT FASTQ, reverse_complement projection
-    p = _lib.gen_params("ont", args.ont_reads, seed=4, len_min=10000, len_max=50000)
-    buf = D.gen_device(p, dev)
+    p = synth.gen_params("ont", args.ont_reads, seed=4, len_min=10000, len_max=50000)
+    buf = synth.gen_device(p, dev)
     n = buf.numel()
     s = D.fastq_scan(buf, _lib.F_LINES | _lib.F_SEQ | _lib.F_QUAL, rec_cap=args.ont_reads + 1024)
     assert s.validate() == args.ont_reads
@@ -134,8 +135,8 @@ def main():
     torch.cuda.empty_cache()
 
     # ---------------- C3: wrapped FASTA, gc_content per contig
-    p = _lib.gen_params("fasta", args.contigs, seed=3, len_min=args.contig_len, len_max=args.contig_len, wrap=60)
-    buf = D.gen_device(p, dev)
+    p = synth.gen_params("fasta", args.contigs, seed=3, len_min=args.contig_len, len_max=args.contig_len, wrap=60)
+    buf = synth.gen_device(p, dev)
     n = buf.numel()
     fs = D.fasta_scan(buf, compact=False)
     assert int(fs.result.n_records) == args.contigs

@@ -15,6 +15,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from exon_duckdb_b200 import _lib
+from tools import synth
 from exon_duckdb_b200._lib import check, lib
 
 
@@ -56,8 +57,8 @@ def main():
     rows = []
     fq = os.path.join(args.dir, "exb_bench.fastq")
     fa = os.path.join(args.dir, "exb_bench.fasta")
-    D.gen_host(_lib.gen_params("illumina", args.reads, seed=20)).tofile(fq)
-    D.gen_host(_lib.gen_params("fasta", args.contigs, seed=3, len_min=500000, len_max=500000, wrap=60)).tofile(fa)
+    synth.gen_host(synth.gen_params("illumina", args.reads, seed=20)).tofile(fq)
+    synth.gen_host(synth.gen_params("fasta", args.contigs, seed=3, len_min=500000, len_max=500000, wrap=60)).tofile(fa)
     cases = [
         ("read_fastq COUNT(*)", fq, "fastq", 0xF, None, True),
         ("read_fastq COUNT(*) WHERE mean quality > 30", fq, "fastq", 0xF, "mean_quality(quality_scores) > 30", True),

@@ -9,10 +9,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from exon_duckdb_b200 import _lib, device as D
+from tools import synth
 
 dev = torch.device("cuda:0")
 reads = int(os.environ.get("EXB_READS", 4_000_000))
-buf = D.gen_device(_lib.gen_params("illumina", reads, seed=20), dev)
+buf = synth.gen_device(synth.gen_params("illumina", reads, seed=20), dev)
 preds = [("mean_quality", ">", 30.0)]
 for it in range(2):
     torch.cuda.synchronize()
@@ -26,7 +27,7 @@ for it in range(2):
     print("fastq_table all: %.3f ms   filtered name+sequence: %.3f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3), flush=True)
 del tab, tab2, buf
 torch.cuda.empty_cache()
-fa = D.gen_device(_lib.gen_params("fasta", 2400, seed=3, len_min=500000, len_max=500000, wrap=60), dev)
+fa = synth.gen_device(synth.gen_params("fasta", 2400, seed=3, len_min=500000, len_max=500000, wrap=60), dev)
 for it in range(2):
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -9,6 +9,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from tools import synth
+
 from exon_duckdb_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -81,39 +83,39 @@ def test_generators_are_deterministic_and_sized():
     L = _lib.lib()
     for kind, kw in (("illumina", {}), ("ont", dict(len_min=1000, len_max=3000)), ("fasta", dict(len_min=0, len_max=500)),
                      ("illumina", dict(crlf=True)), ("fasta", dict(len_min=10, len_max=200, crlf=True, wrap=7))):
-        p = _lib.gen_params(kind, 50, seed=7, **kw)
-        n = L.exb_gen_size(C.byref(p))
+        p = synth.gen_params(kind, 50, seed=7, **kw)
+        n = synth.gen_size(p)
         a = np.zeros(n, np.uint8)
         b = np.zeros(n, np.uint8)
-        assert L.exb_gen_host(C.byref(p), a.ctypes.data, n) == 0
-        assert L.exb_gen_host(C.byref(p), b.ctypes.data, n) == 0
+        assert synth.lib().exb_gen_host(C.byref(p), a.ctypes.data, n) == 0
+        assert synth.lib().exb_gen_host(C.byref(p), b.ctypes.data, n) == 0
         assert (a == b).all() and a[-1] == 10
         # record i of a shard equals record first_record + i of the whole
-        q = _lib.gen_params(kind, 10, seed=7, first_record=40, **kw)
-        m = L.exb_gen_size(C.byref(q))
+        q = synth.gen_params(kind, 10, seed=7, first_record=40, **kw)
+        m = synth.gen_size(q)
         c = np.zeros(m, np.uint8)
-        assert L.exb_gen_host(C.byref(q), c.ctypes.data, m) == 0
+        assert synth.lib().exb_gen_host(C.byref(q), c.ctypes.data, m) == 0
         assert a[n - m:].tobytes() == c.tobytes()
-        assert L.exb_gen_host(C.byref(p), a.ctypes.data, n - 1) == _lib.ERR_CAPACITY
+        assert synth.lib().exb_gen_host(C.byref(p), a.ctypes.data, n - 1) == _lib.ERR_CAPACITY
 
 
 def test_generated_inputs_parse_with_the_oracle():
     from oracle import oracle as O
     L = _lib.lib()
-    p = _lib.gen_params("illumina", 200, seed=20)
-    n = L.exb_gen_size(C.byref(p))
+    p = synth.gen_params("illumina", 200, seed=20)
+    n = synth.gen_size(p)
     a = np.zeros(n, np.uint8)
-    L.exb_gen_host(C.byref(p), a.ctypes.data, n)
+    synth.lib().exb_gen_host(C.byref(p), a.ctypes.data, n)
     t = O.parse_fastq(a.tobytes())
     assert t.n == 200
     assert all(len(s) == 150 for s in t.strings("sequence"))
     assert all(d in (b"1:N:0:ACGTACGT", b"2:N:0:ACGTACGT") for d in t.strings("description"))
     means = [O.mean_quality(q) for q in t.strings("quality_scores")]
     assert 20 < sum(means) / len(means) < 40 and any(m > 30 for m in means) and any(m <= 30 for m in means)
-    p = _lib.gen_params("fasta", 20, seed=3, len_min=100, len_max=5000)
-    n = L.exb_gen_size(C.byref(p))
+    p = synth.gen_params("fasta", 20, seed=3, len_min=100, len_max=5000)
+    n = synth.gen_size(p)
     a = np.zeros(n, np.uint8)
-    L.exb_gen_host(C.byref(p), a.ctypes.data, n)
+    synth.lib().exb_gen_host(C.byref(p), a.ctypes.data, n)
     t = O.parse_fasta(a.tobytes())
     assert t.n == 20 and t.strings("id")[3] == b"contig3"
 

@@ -4,6 +4,8 @@ import random
 
 import numpy as np
 import pytest
+
+from tools import synth
 import torch
 
 import exb_testutil as util
@@ -59,8 +61,8 @@ def test_sharded_count_equals_oracle(cuda_device, seed, kw):
 
 
 def test_sharded_count_generated_illumina(cuda_device):
-    p = _lib.gen_params("illumina", 30000, seed=20)
-    data = D.gen_host(p).tobytes()
+    p = synth.gen_params("illumina", 30000, seed=20)
+    data = synth.gen_host(p).tobytes()
     want = _expect(data)
     for G in (2, 3, 8):
         cuts = [dist.byte_range(len(data), k, G)[0] for k in range(1, G)]

@@ -4,6 +4,8 @@ import os
 import numpy as np
 import pytest
 
+from tools import synth
+
 import exb_testutil as util
 
 pytestmark = pytest.mark.gpu
@@ -90,8 +92,8 @@ def test_one_long_contig_and_header_spanning_tiles(cuda_device):
 
 def test_generated_genome_matches_oracle(cuda_device):
     from exon_duckdb_b200 import _lib, device as D
-    p = _lib.gen_params("fasta", 64, seed=3, len_min=1000, len_max=120000)
-    host = D.gen_host(p)
-    buf = D.gen_device(p, cuda_device)
+    p = synth.gen_params("fasta", 64, seed=3, len_min=1000, len_max=120000)
+    host = synth.gen_host(p)
+    buf = synth.gen_device(p, cuda_device)
     assert buf.cpu().numpy().tobytes() == host.tobytes()
     _check_text(cuda_device, host.tobytes())

@@ -5,6 +5,8 @@ import os
 import numpy as np
 import pytest
 
+from tools import synth
+
 import exb_testutil as util
 
 pytestmark = pytest.mark.gpu
@@ -102,9 +104,9 @@ def test_long_lines_span_many_tiles(cuda_device):
 
 def _gen(dev, kind, n, **kw):
     from exon_duckdb_b200 import _lib, device as D
-    p = _lib.gen_params(kind, n, **kw)
-    host = D.gen_host(p)
-    buf = D.gen_device(p, dev)
+    p = synth.gen_params(kind, n, **kw)
+    host = synth.gen_host(p)
+    buf = synth.gen_device(p, dev)
     assert buf.cpu().numpy().tobytes() == host.tobytes(), "device and host generators must agree byte for byte"
     return buf, host.tobytes()
 

@@ -14,6 +14,8 @@ import os
 import numpy as np
 import pytest
 
+from tools import synth
+
 pytestmark = pytest.mark.gpu
 
 SCALE = float(os.environ.get("EXB_FULLSIZE_SCALE", "1.0"))
@@ -40,8 +42,8 @@ def test_c2_illumina_20m_reads(cuda_device):
     from oracle import oracle as O
 
     reads = max(40_000, int(20_000_000 * SCALE))
-    p = _lib.gen_params("illumina", reads, seed=20)
-    buf = D.gen_device(p, cuda_device)
+    p = synth.gen_params("illumina", reads, seed=20)
+    buf = synth.gen_device(p, cuda_device)
     n = buf.numel()
 
     # (1) the fused COUNT kernel and the general scan + filter kernel are different code: same answer
@@ -63,8 +65,8 @@ def test_c2_illumina_20m_reads(cuda_device):
     _free(torch)
 
     # (3) linearity: two halves cut at a record boundary sum to the whole
-    half = _lib.gen_params("illumina", reads // 2, seed=20)
-    cut = int(_lib.lib().exb_gen_size(C.byref(half)))
+    half = synth.gen_params("illumina", reads // 2, seed=20)
+    cut = int(synth.gen_size(half))
     parts = [D.fastq_scan_filter(buf[:cut], PREDS), D.fastq_scan_filter(_aligned(D, buf[cut:]), PREDS)]
     assert parts[0].validate() + parts[1].validate() == reads
     s = [a + b for a, b in zip(parts[0].agg.cpu().tolist(), parts[1].agg.cpu().tolist())]
@@ -94,8 +96,8 @@ def test_c2_illumina_20m_reads(cuda_device):
 
     # (5) the oracle on a bounded sample from the MIDDLE of the file: records [reads/2, reads/2 + 100k)
     k = min(100_000, reads // 4)
-    mid = _lib.gen_params("illumina", k, seed=20, first_record=reads // 2)
-    text = D.gen_host(mid).tobytes()
+    mid = synth.gen_params("illumina", k, seed=20, first_record=reads // 2)
+    text = synth.gen_host(mid).tobytes()
     assert buf[cut:cut + len(text)].cpu().numpy().tobytes() == text  # the device generator and the host generator agree
     sample = D.fastq_scan_filter(_aligned(D, buf[cut:cut + len(text)]), PREDS)
     assert sample.validate() == k
@@ -110,8 +112,8 @@ def test_c3_genome_3gbp(cuda_device):
 
     contigs = max(12, int(6000 * SCALE))
     L = 500_000
-    p = _lib.gen_params("fasta", contigs, seed=3, len_min=L, len_max=L, wrap=60)
-    buf = D.gen_device(p, cuda_device)
+    p = synth.gen_params("fasta", contigs, seed=3, len_min=L, len_max=L, wrap=60)
+    buf = synth.gen_device(p, cuda_device)
     s = D.fasta_scan_sync(buf, rec_cap=contigs + 16, compact=True)
     r = s.result
     assert int(r.n_records) == contigs and int(r.seq_bytes) == contigs * L
@@ -141,8 +143,8 @@ def test_c4_ont_200k_reads(cuda_device):
     from oracle import oracle as O
 
     reads = max(400, int(200_000 * SCALE))
-    p = _lib.gen_params("ont", reads, seed=4, len_min=10_000, len_max=50_000)
-    buf = D.gen_device(p, cuda_device)
+    p = synth.gen_params("ont", reads, seed=4, len_min=10_000, len_max=50_000)
+    buf = synth.gen_device(p, cuda_device)
     scan = D.fastq_scan_sync(buf, _lib.F_LINES | _lib.F_SEQ | _lib.F_QUAL, rec_cap=reads + 1024)
     assert scan.validate() == reads
     sl, ql = scan.seq_len[:reads], scan.qual_len[:reads]
@@ -177,7 +179,7 @@ def test_c5_sharded_count_and_gc(cuda_device):
 
     reads = max(80_000, int(6_000_000 * SCALE))
     G = 8
-    buf = D.gen_device(_lib.gen_params("illumina", reads, seed=20), cuda_device)
+    buf = synth.gen_device(synth.gen_params("illumina", reads, seed=20), cuda_device)
     n = buf.numel()
     whole = D.fastq_scan_sync(buf, _lib.F_SEQ, rec_cap=reads + 1024)
     assert whole.validate() == reads

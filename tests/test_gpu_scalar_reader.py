@@ -6,6 +6,8 @@ import random
 import numpy as np
 import pytest
 
+from tools import synth
+
 import exb_testutil as util
 
 pytestmark = pytest.mark.gpu
@@ -323,14 +325,14 @@ def test_engine_fastq_count_host(cuda_device, pinned):
     from exon_duckdb_b200 import _lib
     from oracle import oracle as O
     L = _lib.lib()
-    p = _lib.gen_params("illumina", 40000, seed=20)
-    n = L.exb_gen_size(C.byref(p))
+    p = synth.gen_params("illumina", 40000, seed=20)
+    n = synth.gen_size(p)
     if pinned:
         ptr = L.exb_host_alloc(n)
         host = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,))
     else:
         host = np.empty(n, np.uint8)
-    assert L.exb_gen_host(C.byref(p), host.ctypes.data, n) == 0
+    assert synth.lib().exb_gen_host(C.byref(p), host.ctypes.data, n) == 0
     preds, k = _lib.predicates([("mean_quality", ">", 30.0)])
     agg = (C.c_int64 * 8)()
     res = _lib.ScanResult()

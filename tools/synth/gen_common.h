@@ -4,7 +4,7 @@
 #pragma once
 #include <stdint.h>
 
-#include "../../include/exon_b200.h"
+#include "exb_synth.h"
 
 #if defined(__CUDACC__)
 #define EXB_GHD __host__ __device__ inline
