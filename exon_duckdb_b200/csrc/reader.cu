@@ -23,6 +23,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <unistd.h>
+#include <immintrin.h>
 #include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
@@ -572,7 +573,9 @@ struct IoPool {
     int nthreads = 1;
     IoPool() {
         int hw = (int)std::thread::hardware_concurrency();
-        nthreads = hw > 0 ? std::min(hw, 16) : 4;
+        // half the cores (at most 12): 8 threads already copy at 61 GB/s on the 16-core box, above the PCIe rate, and the
+        // device thread and the host's consumers need cores to keep the GPU fed
+        nthreads = hw > 0 ? std::max(2, std::min(hw / 2, 12)) : 4;
         if (const char* e = getenv("EXON_B200_IO_THREADS"))
             if (atoi(e) > 0) nthreads = std::min(atoi(e), 64);
         for (int i = 0; i < nthreads - 1; i++) std::thread([this] { work(); }).detach();  // the caller is the last worker
@@ -581,8 +584,33 @@ struct IoPool {
         static IoPool* p = new IoPool();  // never destroyed: detached workers may outlive static destructors
         return *p;
     }
+    // 64-byte streaming stores: the pinned block is written once and next read by the DMA engine, so there is nothing to
+    // keep in the CPU caches.  Measured pipelined with the H2D copy (tools/iobench2.cu, profiles/round2_iobench2.txt):
+    // 51.6 GB/s with 8 threads against 47.5 GB/s for memcpy and 44.3 GB/s for cached 64-byte stores.
+    __attribute__((target("avx512f"))) static void copy_stream512(uint8_t* d, const uint8_t* s, size_t n) {
+        size_t head = (64 - ((uintptr_t)d & 63)) & 63;
+        if (head > n) head = n;
+        if (head) memcpy(d, s, head);
+        size_t i = head;
+        for (; i + 256 <= n; i += 256) {
+            const __m512i a = _mm512_loadu_si512((const void*)(s + i)), b = _mm512_loadu_si512((const void*)(s + i + 64)),
+                          c = _mm512_loadu_si512((const void*)(s + i + 128)), e = _mm512_loadu_si512((const void*)(s + i + 192));
+            _mm512_stream_si512((__m512i*)(d + i), a);
+            _mm512_stream_si512((__m512i*)(d + i + 64), b);
+            _mm512_stream_si512((__m512i*)(d + i + 128), c);
+            _mm512_stream_si512((__m512i*)(d + i + 192), e);
+        }
+        for (; i + 64 <= n; i += 64) _mm512_stream_si512((__m512i*)(d + i), _mm512_loadu_si512((const void*)(s + i)));
+        _mm_sfence();
+        if (i < n) memcpy(d + i, s + i, n - i);
+    }
+    static bool have_avx512() {
+        static const bool yes = __builtin_cpu_supports("avx512f") && !getenv("EXON_B200_NO_AVX512");
+        return yes;
+    }
     static void run(const Task& t) {
-        memcpy(t.dst, t.src, t.n);
+        if (have_avx512()) copy_stream512(t.dst, t.src, t.n);
+        else memcpy(t.dst, t.src, t.n);
         if (t.job->left.fetch_sub(1) == 1) {
             std::lock_guard<std::mutex> lk(t.job->mu);
             t.job->cv.notify_all();
@@ -603,7 +631,9 @@ struct IoPool {
     void copy(uint8_t* dst, const uint8_t* src, int64_t n) {
         if (n <= 0) return;
         if (n < (4 << 20) || nthreads == 1) {
-            memcpy(dst, src, (size_t)n);
+            Job one;
+            one.left.store(1);
+            run(Task{dst, src, (size_t)n, &one});
             return;
         }
         int64_t slice = (n + nthreads - 1) / nthreads;
@@ -631,6 +661,66 @@ struct IoPool {
     }
 };
 
+// ------------------------------------------------------------------ file mappings
+// A plain input file is mapped once and the mapping is kept for the next scan of the same file (same device, inode,
+// size and mtime): DuckDB opens a reader at bind time and another one at init, a multi-GPU scan opens one per device,
+// and a repeated query finds the page tables already populated (the first pass over a 2.8 GB tmpfs file spends ~20 % of
+// its copy time in page faults, and unmapping it takes 25 ms).  At most four mappings are kept; evicted ones are unmapped
+// off the critical path.
+struct FileMap {
+    const uint8_t* p = nullptr;
+    int64_t size = 0;
+    dev_t dev = 0;
+    ino_t ino = 0;
+    int64_t mtime_ns = 0;
+    ~FileMap() {
+        if (p) munmap(const_cast<uint8_t*>(p), (size_t)size);
+    }
+};
+struct MapCache {
+    std::mutex mu;
+    std::deque<std::shared_ptr<FileMap>> keep;
+    static MapCache& get() {
+        static MapCache* c = new MapCache();  // never destroyed (readers on detached threads may outlive static destructors)
+        return *c;
+    }
+    std::shared_ptr<FileMap> open(int fd) {
+        struct stat sb;
+        if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size <= 0) return nullptr;
+        const int64_t mt = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (auto it = keep.begin(); it != keep.end(); ++it)
+                if ((*it)->dev == sb.st_dev && (*it)->ino == sb.st_ino && (*it)->size == (int64_t)sb.st_size && (*it)->mtime_ns == mt) {
+                    std::shared_ptr<FileMap> hit = *it;
+                    keep.erase(it);
+                    keep.push_front(hit);
+                    return hit;
+                }
+        }
+        void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
+        if (m == MAP_FAILED) return nullptr;
+        madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+        std::shared_ptr<FileMap> fm = std::make_shared<FileMap>();
+        fm->p = reinterpret_cast<const uint8_t*>(m);
+        fm->size = sb.st_size;
+        fm->dev = sb.st_dev;
+        fm->ino = sb.st_ino;
+        fm->mtime_ns = mt;
+        std::shared_ptr<FileMap> evicted;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            keep.push_front(fm);
+            if (keep.size() > 4) {
+                evicted = keep.back();
+                keep.pop_back();
+            }
+        }
+        if (evicted) std::thread([evicted]() mutable { evicted.reset(); }).detach();  // munmap of gigabytes: not on anybody's clock
+        return fm;
+    }
+};
+
 // ------------------------------------------------------------------ shard edges (include/exon_b200.h exb_reader_options)
 // First record start at or after p.  Both ends of a byte-range shard go through the same function, so adjacent shards
 // agree on the cut; a shard is then parsed as a complete input.
@@ -648,7 +738,7 @@ static int64_t resync_fasta(const uint8_t* m, int64_t size, int64_t p) {
 }
 // FASTQ: '@' and '+' are legal quality characters, so one line proves nothing.  Take the first line start >= p and the
 // line starts after it; hypothesis h = "line h is a header" holds if every 4th line from h starts with '@' and the line
-// two below it with '+', over a window of 16 records.  The smallest h that holds wins.  This is a heuristic for
+// two below it with '+', over a window of 16 records (a candidate needs its own four lines).  The smallest h that holds wins.  This is a heuristic for
 // adversarial inputs; it cannot produce a silently wrong answer, because the shard that ENDS at the cut is parsed
 // exactly from its own (inductively exact) start: if the cut is not a record boundary its line count is not a multiple
 // of four or a header / plus line check fails, and the scan reports the malformed shard.
@@ -670,8 +760,9 @@ static int64_t resync_fastq(const uint8_t* m, int64_t size, int64_t p) {
         if (!q) break;
         s = (const uint8_t*)q - m + 1;
     }
-    if (L == 0) return size;
-    for (int h = 0; h < 4 && h < L; h++) {
+    // a record is four lines: with fewer than four lines left, no record starts at or after p
+    if (L < 4) return size;
+    for (int h = 0; h < 4 && h + 3 < L; h++) {
         bool ok = true;
         for (int j = h; j < L && ok; j += 4) {
             if (m[starts[j]] != '@') ok = false;
@@ -811,10 +902,13 @@ struct Reader {
         cudaEvent_t ev_done = nullptr, ev_d2h = nullptr, ev_off = nullptr;
     } outs[2];
     int out_cur = 0;
-    OutItem pending;            // result whose D2H is still in flight
-    int pending_set = -1;
-    std::vector<std::pair<int, int>> pending_bad;  // (out column, map mode) whose invalid-byte word must be checked after the D2H
-    const uint64_t* pending_bad_words = nullptr;
+    struct Pending {            // a result whose D2H is still in flight
+        OutItem item;
+        int set = -1;
+        std::vector<std::pair<int, int>> bad;  // (out column, map mode) whose invalid-byte word must be checked after the D2H
+        const uint64_t* bad_words = nullptr;
+    };
+    std::deque<Pending> pend;   // at most two: chunk k's D2H overlaps the kernels of chunk k+1
     std::shared_ptr<PinnedPool> pool = PinnedPool::shared();
     HBuf h_small;  // a few words for totals / flags read back between launches
     // rows ready to be handed out (caller threads, under call_mu)
@@ -840,8 +934,10 @@ struct Reader {
     int64_t cur_file_pos = 0;
     // EXON_B200_TRACE=1: seconds spent per stage, printed when the reader closes
     double t_io_read = 0, t_io_alloc = 0, t_io_push = 0, t_dev_pop = 0, t_dev_work = 0, t_dev_push = 0, t_call_pop = 0;
-    double t_scan = 0, t_select = 0, t_mat = 0, t_flush = 0;
+    double t_scan = 0, t_select = 0, t_mat = 0, t_flush = 0, t_init = 0, t_free = 0, t_map = 0, t_unmap = 0, t_first_block = 0, t_open = now();
     int64_t n_blocks = 0;
+    int trace = 0;
+    cudaEvent_t tev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // EXON_B200_TRACE=2: GPU-side times per chunk
     static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     ~Reader() {
@@ -855,9 +951,10 @@ struct Reader {
         outq.q.clear();
         if (getenv("EXON_B200_TRACE"))
             fprintf(stderr, "exon_b200 reader: %lld blocks | io: alloc %.3f read %.3f push-wait %.3f | device: pop-wait %.3f work %.3f "
-                            "(scan %.3f select %.3f materialise %.3f d2h-wait %.3f) push-wait %.3f | caller: pop-wait %.3f s\n",
+                            "(scan %.3f select %.3f materialise %.3f d2h-wait %.3f) push-wait %.3f | caller: pop-wait %.3f s | "
+                            "device init %.3f free %.3f, map %.3f unmap %.3f, first block after %.3f, life %.3f s\n",
                     (long long)n_blocks, t_io_alloc, t_io_read, t_io_push, t_dev_pop, t_dev_work, t_scan, t_select, t_mat, t_flush, t_dev_push,
-                    t_call_pop);
+                    t_call_pop, t_init, t_free, t_map, t_unmap, t_first_block, now() - t_open);
     }
     bool fail(const std::string& m) {
         derr = m;
@@ -904,9 +1001,16 @@ struct Reader {
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&outs[i].ev_d2h, cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&outs[i].ev_off, cudaEventDisableTiming);
         }
+        if (const char* t = getenv("EXON_B200_TRACE")) trace = atoi(t);
+        if (trace >= 2)
+            for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&tev[i]);
         return cu(e, "CUDA stream setup");
     }
+    void mark(int i) {
+        if (trace >= 2) cudaEventRecord(tev[i], st);
+    }
     void free_device() {  // device thread, at its end: buffers are freed on the device that owns them
+        const double tf = now();
         for (DBuf* b : {&d_inb[0], &d_inb[1], &d_stage, &d_ws, &d_ws2, &d_line, &d_arr[0], &d_arr[1], &d_arr[2], &d_arr[3], &d_lens, &d_starts,
                         &d_valid, &d_pass, &d_selscratch, &d_sel, &d_lens2, &d_starts2, &d_valid2, &d_off, &d_cst, &d_hdr_start, &d_hdr_end,
                         &d_seq_off, &d_gc_prefix, &d_seq, &d_err, &d_info, &d_qtmp, &d_bad, &outs[0].d_meta, &outs[0].d_data, &outs[1].d_meta,
@@ -926,6 +1030,7 @@ struct Reader {
         if (st) cudaStreamDestroy(st);
         if (sc) cudaStreamDestroy(sc);
         if (sd) cudaStreamDestroy(sd);
+        t_free += now() - tf;
     }
 
     // ------------------------------------------------------------------ IO thread
@@ -976,7 +1081,8 @@ struct Reader {
             std::vector<uint8_t> zbuf;
             size_t zpos = 0, zsize = 0;
             std::string err;
-            const uint8_t* map = nullptr;  // plain files: the whole file mapped read-only
+            std::shared_ptr<FileMap> fmap;  // plain files: the whole file mapped read-only (shared with later scans)
+            const uint8_t* map = nullptr;
             int64_t map_size = 0;
             int64_t pos = 0, end_pos = -1;  // plain files: [pos, end_pos) is what this reader parses
             if (comp == 1) {
@@ -994,15 +1100,13 @@ struct Reader {
                 fd = open(path.c_str(), O_RDONLY);
                 if (fd < 0) err = "could not open " + path;
                 else {
-                    struct stat sb;
-                    if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
-                        void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
-                        if (m != MAP_FAILED) {
-                            map = reinterpret_cast<const uint8_t*>(m);
-                            map_size = sb.st_size;
-                            madvise(m, (size_t)map_size, MADV_SEQUENTIAL);
-                        }
+                    const double tm = now();
+                    fmap = MapCache::get().open(fd);
+                    if (fmap) {
+                        map = fmap->p;
+                        map_size = fmap->size;
                     }
+                    t_map += now() - tm;
                     if (sharded) {
                         if (!map) err = "byte-range shards need a mappable regular file: " + path;
                         else {
@@ -1103,6 +1207,7 @@ struct Reader {
                     break;
                 }
                 t_io_read += now() - t0;
+                if (n_blocks == 0) t_first_block = now() - t_open;
                 n_blocks++;
                 eof = map ? pos + got >= end_pos : got < want;
                 b.raw_len = got;
@@ -1117,7 +1222,7 @@ struct Reader {
                     break;
                 }
             }
-            if (map) munmap(const_cast<uint8_t*>(map), (size_t)map_size);
+            fmap.reset();
             if (fd >= 0) close(fd);
             if (gz) gzclose(gz);
             dec.reset();
@@ -1196,26 +1301,29 @@ struct Reader {
         return false;
     }
 
-    // hand the finished result of the previous chunk to the caller side once its D2H has drained
-    bool flush_pending() {
-        if (pending_set < 0) return true;
-        const double t0 = now();
-        OutSet& o = outs[pending_set];
-        bool ok = cu(cudaEventSynchronize(o.ev_d2h), "D2H") && cu(cudaEventSynchronize(o.ev_off), "D2H offsets");
-        t_flush += now() - t0;
-        pending_set = -1;
-        if (!ok) return false;
-        for (auto& pb : pending_bad) {  // reverse_complement & co met a byte outside their table (module.cpp:58-62)
-            const uint64_t w = pending_bad_words[pb.first];
-            if (w != ~0ull) return fail(std::string("Invalid character in sequence: ") + std::string(1, (char)(w & 0xFF)));
+    // hand finished results to the caller side once their D2H has drained, oldest first, until at most `keep` are in flight
+    bool flush_pending(size_t keep) {
+        while (pend.size() > keep) {
+            Pending pd = std::move(pend.front());
+            pend.pop_front();
+            const double t0 = now();
+            OutSet& o = outs[pd.set];
+            const bool ok = cu(cudaEventSynchronize(o.ev_d2h), "D2H") && cu(cudaEventSynchronize(o.ev_off), "D2H offsets");
+            t_flush += now() - t0;
+            if (!ok) return false;
+            for (auto& pb : pd.bad) {  // reverse_complement & co met a byte outside their table (module.cpp:58-62)
+                const uint64_t w = pd.bad_words[pb.first];
+                if (w != ~0ull) return fail(std::string("Invalid character in sequence: ") + std::string(1, (char)(w & 0xFF)));
+            }
+            const double t1 = now();
+            const bool pushed = outq.push(std::move(pd.item));
+            t_dev_push += now() - t1;
+            if (!pushed) {
+                stopping = true;
+                pend.clear();
+                return true;
+            }
         }
-        pending_bad.clear();
-        OutItem it = std::move(pending);
-        pending = OutItem();
-        const double t1 = now();
-        const bool pushed = outq.push(std::move(it));
-        t_dev_push += now() - t1;
-        if (!pushed) stopping = true;
         return true;
     }
 
@@ -1319,7 +1427,7 @@ struct Reader {
         if (h_meta) res->bufs.push_back(h_meta);
         if (h_bytes) res->bufs.push_back(h_bytes);
         if (!h_meta || !h_bytes || !o.d_meta.need(meta_copy + 64) || !o.d_data.need(all + 64)) return fail("out of memory");
-        // the set's previous D2H (two chunks ago) has been waited for by flush_pending; order the device side too
+        // the set's previous D2H (two chunks ago) was waited for by flush_pending(1) after the last chunk; order the device side too
         if (!cu(cudaStreamWaitEvent(st, o.ev_d2h, 0), "wait")) return false;
         uint8_t* dm = o.d_meta.as<uint8_t>();
         uint8_t* dd = o.d_data.as<uint8_t>();
@@ -1411,11 +1519,14 @@ struct Reader {
         if (!cu(cudaMemcpyAsync(hm, dm, (size_t)meta_copy, cudaMemcpyDeviceToHost, sd), "D2H metadata")) return false;
         if (all > 0 && !cu(cudaMemcpyAsync(hb, dd, (size_t)all, cudaMemcpyDeviceToHost, sd), "D2H data")) return false;
         if (!cu(cudaEventRecord(o.ev_d2h, sd), "record")) return false;
-        item->res = res;
-        pending_bad = bad_cols;
-        pending_bad_words = reinterpret_cast<const uint64_t*>(hm + m_bad);
-        pending_set = set;
-        return true;
+        Pending pd;
+        pd.item.res = res;
+        pd.set = set;
+        pd.bad = bad_cols;
+        pd.bad_words = reinterpret_cast<const uint64_t*>(hm + m_bad);
+        pend.push_back(std::move(pd));
+        // deliver chunk k-1 now: its D2H had all of chunk k's kernels to finish, and chunk k's is already queued behind it
+        return flush_pending(1);
     }
 
     // apply the filter (if any) to the n rows described by starts/lens/valid; leaves the final arrays in *o_*
@@ -1481,13 +1592,15 @@ struct Reader {
                 // where the last complete record ends: fetched together with the result block (one sync)
                 if (!cu(fastq_chunk_info_launch(d_ws.p, d_line.as<uint32_t>(), d_info.as<int64_t>(), st), "chunk_info")) return false;
                 if (!cu(cudaMemcpyAsync(info, d_info.p, 16, cudaMemcpyDeviceToHost, st), "D2H")) return false;
-                if (attempt == 0 && !flush_pending()) return false;  // the previous chunk's result goes out while this scan runs
                 if (!rc(exb_scan_result_fetch(d_ws.p, &res, st))) return false;
                 if (!res.overflow) break;
                 if (attempt) return fail("internal: record capacity");
                 rec_cap = n / 4 + 16;
             }
             t_scan += now() - t0;
+            mark(2);
+            mark(3);
+            mark(4);
             if (res.err_pos != ~0ull)
                 return fail("invalid FASTQ record at byte " + std::to_string(cur_file_pos + (int64_t)res.err_pos) + " of " + fname + shard_note());
             int64_t R = (int64_t)(res.total_lines / 4);
@@ -1511,9 +1624,11 @@ struct Reader {
             const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; const int64_t* o_sel; int64_t o_n;
             if (!select(bufs, R, o_st, o_ln, o_val, o_sel, o_n)) return false;
             t_select += now() - t0;
+            mark(3);
             t0 = now();
             const bool ok = materialise(bufs, o_st, o_ln, o_val, o_sel, o_n, item);
             t_mat += now() - t0;
+            mark(4);
             return ok;
         }
         // ---- FASTA
@@ -1533,13 +1648,15 @@ struct Reader {
                                    d_seq_off.as<int64_t>(), d_gc_prefix.as<int64_t>(), rec_cap, want_seq ? d_seq.as<uint8_t>() : nullptr,
                                    want_seq ? n + 64 : 0, d_ws.p, d_ws.cap, st)))
                 return false;
-            if (attempt == 0 && !flush_pending()) return false;
             if (!rc(exb_scan_result_fetch(d_ws.p, &res, st))) return false;
             if (!res.overflow) break;
             if (attempt) return fail("internal: record capacity");
             rec_cap = n / 2 + 16;
         }
         t_scan += now() - t0;
+        mark(2);
+        mark(3);
+        mark(4);
         if (res.err_pos != ~0ull)
             return fail("invalid FASTA input (missing '>' prefix) at byte " + std::to_string(cur_file_pos + (int64_t)res.err_pos) + " of " + fname);
         int64_t R = (int64_t)res.n_records;
@@ -1593,20 +1710,25 @@ struct Reader {
         int64_t carry_off = 0, carry_len = 0;  // the tail lives in d_inb[cur] at [carry_off, carry_off + carry_len)
         auto finish = [&](const std::string& err_in) {
             std::string err = err_in;
-            if (err.empty() && !flush_pending()) err = derr;
+            if (err.empty() && !flush_pending(0)) err = derr;
             cudaStreamSynchronize(sc);
             cudaStreamSynchronize(st);
             cudaStreamSynchronize(sd);
             pool->put(host_cur);
             if (have_staged) pool->put(staged.h);
-            pending = OutItem();
+            pend.clear();
             free_device();
             OutItem e;
             e.end = true;
             e.error = err;
             outq.push(std::move(e));
         };
-        if (!init_device()) return finish(derr);
+        {
+            const double ti = now();
+            const bool ok = init_device();
+            t_init = now() - ti;
+            if (!ok) return finish(derr);
+        }
         while (!stopping) {
             Block b;
             bool on_device = false;
@@ -1615,7 +1737,7 @@ struct Reader {
                 on_device = staged_on_device;
                 have_staged = false;
             } else {
-                if (!flush_pending()) return finish(derr);  // nothing to overlap with: do not sit on a finished result
+                if (!flush_pending(0)) return finish(derr);  // nothing to overlap with: do not sit on finished results
                 double t0 = now();
                 const bool popped = inq.pop(b);
                 t_dev_pop += now() - t0;
@@ -1625,6 +1747,7 @@ struct Reader {
             double t0 = now();
             NvtxRange nv("exb:chunk");
             // ---- assemble chunk k in the other input buffer
+            mark(0);
             const int nxt = cur ^ 1;
             const int64_t n = carry_len + b.raw_len;
             if (!d_inb[nxt].need(n + 64)) {
@@ -1646,6 +1769,7 @@ struct Reader {
             pool->put(host_cur);  // the previous chunk synchronised `st` after its copies: that block is idle
             host_cur = b.h;
             if (!ok) return finish(derr);
+            mark(1);
             cur = nxt;
             d_cur = dst;
             cur_file = b.file_idx;
@@ -1682,9 +1806,19 @@ struct Reader {
             carry_len = n - consumed;
             bytes_done.fetch_add(consumed);
             t_dev_work += now() - t0;
-            if (item.res) {
-                pending = std::move(item);  // goes out once its D2H has drained (flush_pending)
-            } else if (item.counted) {
+            if (trace >= 2) {
+                mark(5);
+                cudaEventSynchronize(tev[5]);
+                float a = 0, b2 = 0, c = 0, d = 0, e2 = 0;
+                cudaEventElapsedTime(&a, tev[0], tev[1]);
+                cudaEventElapsedTime(&b2, tev[1], tev[2]);
+                cudaEventElapsedTime(&c, tev[2], tev[3]);
+                cudaEventElapsedTime(&d, tev[3], tev[4]);
+                cudaEventElapsedTime(&e2, tev[4], tev[5]);
+                fprintf(stderr, "exon_b200 chunk %lld bytes (%s): host %.3f ms | gpu: copy-in %.3f scan %.3f fields+select %.3f materialise %.3f tail %.3f ms\n",
+                        (long long)n, on_device ? "prefetched" : "direct H2D", (now() - t0) * 1e3, a, b2, c, d, e2);
+            }
+            if (item.counted) {  // (materialised results travel through `pend`)
                 t0 = now();
                 const bool pushed = outq.push(std::move(item));
                 t_dev_push += now() - t0;
@@ -1696,7 +1830,7 @@ struct Reader {
         cudaStreamSynchronize(sd);
         pool->put(host_cur);
         if (have_staged) pool->put(staged.h);
-        pending = OutItem();
+        pend.clear();
         free_device();
     }
 

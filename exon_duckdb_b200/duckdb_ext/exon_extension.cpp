@@ -22,7 +22,10 @@
 // without a CUDA device every one of these functions raises an error.
 #define DUCKDB_EXTENSION_MAIN
 
+#include <cmath>
+#include <cstring>
 #include <mutex>
+#include <thread>
 
 #include "duckdb.hpp"
 #include "duckdb/common/enums/expression_type.hpp"
@@ -43,6 +46,10 @@
 #include "duckdb/planner/expression/bound_function_expression.hpp"
 #include "duckdb/planner/filter/conjunction_filter.hpp"
 #include "duckdb/planner/filter/constant_filter.hpp"
+#include "duckdb/optimizer/optimizer_extension.hpp"
+#include "duckdb/planner/expression_iterator.hpp"
+#include "duckdb/planner/logical_operator_visitor.hpp"
+#include "duckdb/planner/operator/logical_filter.hpp"
 #include "duckdb/planner/operator/logical_get.hpp"
 #include "duckdb/planner/table_filter.hpp"
 
@@ -58,48 +65,75 @@ struct ScanInfo : public TableFunctionInfo {
 	string file_type;
 };
 
+// a scalar function of the reference applied to a column of the scan, served by the scan itself (exb_computed)
+struct ComputedColumn {
+	int32_t kind; // EXB_C_*
+	int32_t arg;  // EXB_C_SEQ_MAP: EXB_MAP_*
+	string name;  // how EXPLAIN shows it
+	LogicalType type;
+};
+
 struct ScanBindData : public TableFunctionData {
 	string file_name;
 	string file_type;
 	string compression; // "auto_detect" = infer from the extension (module.cpp:85,89-101)
+	int32_t gpus = 0;   // named parameter `gpus`: 0 = all visible devices when the input is large enough
 	vector<string> names;
-	vector<string> pushed; // predicates absorbed by pushdown_complex_filter, in the engine's filter syntax
+	vector<string> pushed;           // predicates absorbed by pushdown_complex_filter, in the engine's filter syntax
+	vector<ComputedColumn> computed; // projections absorbed by the optimizer extension: column id names.size() + k
+	vector<bool> dead;               // file columns nothing above the scan reads any more (after the rewrite)
 };
 
 // keeps the reader's host buffers alive for as long as a vector points into them
-class BatchBuffer : public VectorBuffer {
-public:
-	explicit BatchBuffer(exb_batch batch_p) : VectorBuffer(VectorBufferType::OPAQUE_BUFFER), batch(batch_p) {
+struct BatchHolder {
+	explicit BatchHolder(exb_batch batch_p) : batch(batch_p) {
 	}
-	~BatchBuffer() override {
+	~BatchHolder() {
 		exb_batch_release(&batch);
 	}
 	exb_batch batch;
+};
+class BatchBuffer : public VectorBuffer { // VARCHAR vectors: joins the vector's string heap references
+public:
+	explicit BatchBuffer(shared_ptr<BatchHolder> holder_p) : VectorBuffer(VectorBufferType::OPAQUE_BUFFER), holder(std::move(holder_p)) {
+	}
+	shared_ptr<BatchHolder> holder;
+};
+struct BatchAux : public VectorAuxiliaryData { // fixed-width vectors, like ArrowAuxiliaryData (arrow_aux_data.hpp:16-25)
+	explicit BatchAux(shared_ptr<BatchHolder> holder_p) : VectorAuxiliaryData(VectorAuxiliaryDataType::ARROW_AUXILIARY), holder(std::move(holder_p)) {
+	}
+	shared_ptr<BatchHolder> holder;
 };
 
 // what ArrowScanLocalState::batch_index is to the reference (arrow.hpp, ArrowGetBatchIndex): the position of the chunk a
 // thread is holding in the order of the file, so that order-preserving sinks (batch collector, LIMIT, COPY) can run
 struct ScanLocalState : public LocalTableFunctionState {
 	idx_t batch_index = 0;
+	int64_t shard = -1; // the reader this thread pulls from
 };
 
+// The reference streams a file through ONE thread (ArrowScanGlobalState::max_threads = 1, arrow.hpp:107-119).  Here a
+// scan owns one device pipeline (reader) per GPU: readers[k] parses the k-th byte range of the file (or the k-th group
+// of files of a directory) on device k, and every DuckDB scan thread pulls finished 2048-row batches from one of them.
+// Batches are built on the device in DuckDB's own vector layout, so a scan call assigns pointers and returns.
 struct ScanGlobalState : public GlobalTableFunctionState {
 	std::mutex lock;
-	idx_t next_batch = 0;
-	exb_reader *reader = nullptr;
+	vector<exb_reader *> readers;
+	idx_t threads_per_reader = 1;
+	idx_t next_slot = 0; // slot s pulls from readers[s / threads_per_reader]; slots are claimed in increasing order
 	vector<column_t> column_ids;
+	idx_t n_file_cols = 0;
+	vector<bool> dead;
 	bool count_only = false;
 	int64_t count_left = 0;
 	bool done = false;
 	~ScanGlobalState() override {
-		if (reader) {
-			exb_reader_close(reader);
+		for (auto r : readers) {
+			exb_reader_close(r);
 		}
 	}
-	// one scan thread, like the reference (ArrowScanGlobalState::max_threads = 1, arrow.hpp:107-119): the file is
-	// streamed through ONE device pipeline whose chunks are already processed by the whole GPU
 	idx_t MaxThreads() const override {
-		return 1;
+		return count_only ? 1 : readers.size() * threads_per_reader;
 	}
 };
 
@@ -113,6 +147,11 @@ static unique_ptr<FunctionData> ScanBind(ClientContext &context, TableFunctionBi
 	for (auto &kv : input.named_parameters) {
 		if (kv.first == "compression") {
 			result->compression = kv.second.GetValue<string>();
+		} else if (kv.first == "gpus") {
+			result->gpus = kv.second.GetValue<int32_t>();
+			if (result->gpus < 0) {
+				throw InvalidInputException("read_%s: gpus must be >= 0", info.file_type.c_str());
+			}
 		}
 	}
 	// the reference opens a reader at bind time to learn the schema, so a bad path / codec fails here (module.cpp:95-108)
@@ -129,6 +168,7 @@ static unique_ptr<FunctionData> ScanBind(ClientContext &context, TableFunctionBi
 	}
 	exb_reader_close(probe);
 	result->names = names;
+	result->dead.assign(names.size(), false);
 	return std::move(result);
 }
 
@@ -164,10 +204,39 @@ static string FilterToString(const TableFilter &filter, const string &column_nam
 	}
 }
 
+// How many device pipelines a scan gets: `gpus := n` if given, else every visible device as long as each one is left with
+// at least 256 MiB (a smaller share does not amortise a pipeline's start-up).  Byte-range shards need ONE uncompressed
+// file; a directory is split into groups of whole files of about equal size.
+static idx_t PlanReaders(const ScanBindData &bind, const char *comp, int64_t &total_bytes, int32_t &n_files, int32_t &shardable) {
+	total_bytes = 0;
+	n_files = 1;
+	shardable = 0;
+	if (exb_reader_plan(bind.file_name.c_str(), bind.file_type.c_str(), comp, &total_bytes, &n_files, &shardable) != 0) {
+		throw std::runtime_error(exb_last_error());
+	}
+	const int devices = exb_device_count();
+	idx_t want = bind.gpus > 0 ? (idx_t)bind.gpus : (idx_t)MaxValue<int>(devices, 1);
+	if (bind.gpus > 0 && bind.gpus > devices) {
+		throw InvalidInputException("gpus := %d, but only %d CUDA device(s) are visible", bind.gpus, devices);
+	}
+	if (bind.gpus == 0) {
+		want = MinValue<idx_t>(want, (idx_t)MaxValue<int64_t>(1, total_bytes / (256ll << 20)));
+	}
+	if (shardable) {
+		return MaxValue<idx_t>(want, 1);
+	}
+	if (n_files > 1) {
+		return MaxValue<idx_t>(MinValue<idx_t>(want, (idx_t)n_files), 1);
+	}
+	return 1;
+}
+
 static unique_ptr<GlobalTableFunctionState> ScanInitGlobal(ClientContext &context, TableFunctionInitInput &input) {
 	auto &bind = input.bind_data->Cast<ScanBindData>();
 	auto state = make_uniq<ScanGlobalState>();
 	state->column_ids = input.column_ids;
+	state->n_file_cols = bind.names.size();
+	state->dead = bind.dead;
 
 	vector<string> terms;
 	if (input.filters) {
@@ -181,84 +250,164 @@ static unique_ptr<GlobalTableFunctionState> ScanInitGlobal(ClientContext &contex
 	}
 	const string filter_clause = StringUtil::Join(terms, " AND ");
 
-	uint32_t mask = 0;
+	exb_reader_options opt;
+	memset(&opt, 0, sizeof(opt));
+	opt.size = sizeof(opt);
+	opt.flags = EXB_RD_STRING_T | EXB_RD_NO_OFFSETS;
 	bool any_column = false;
+	vector<bool> computed_used(bind.computed.size(), false);
 	for (auto id : input.column_ids) {
-		if (id != COLUMN_IDENTIFIER_ROW_ID) {
-			mask |= 1u << id;
-			any_column = true;
+		if (id == COLUMN_IDENTIFIER_ROW_ID) {
+			continue;
+		}
+		any_column = true;
+		if (id < bind.names.size()) {
+			if (!bind.dead[id]) {
+				opt.column_mask |= 1u << id;
+			}
+		} else {
+			computed_used[id - bind.names.size()] = true;
 		}
 	}
-	const char *comp = bind.compression == "auto_detect" ? nullptr : bind.compression.c_str();
-	if (exb_reader_open(bind.file_name.c_str(), bind.file_type.c_str(), comp, STANDARD_VECTOR_SIZE, filter_clause.c_str(), mask,
-	                    &state->reader) != 0) {
-		throw std::runtime_error(exb_last_error());
+	// the reader numbers its computed columns 0, 1, ...: keep the bind data's numbering (unused ones are still computed;
+	// the optimizer only creates columns that an expression reads)
+	opt.n_computed = (int32_t)bind.computed.size();
+	for (idx_t k = 0; k < bind.computed.size(); k++) {
+		opt.computed[k].kind = bind.computed[k].kind;
+		opt.computed[k].arg = bind.computed[k].arg;
 	}
-	if (!any_column) { // COUNT(*): arrow_conversion.cpp:813-816 is the reference's "row id only" case
-		state->count_only = true;
-		int64_t rows = 0;
-		if (exb_reader_count(state->reader, &rows) != 0) {
+
+	const char *comp = bind.compression == "auto_detect" ? nullptr : bind.compression.c_str();
+	int64_t total_bytes = 0;
+	int32_t n_files = 1, shardable = 0;
+	const idx_t n_readers = PlanReaders(bind, comp, total_bytes, n_files, shardable);
+	for (idx_t k = 0; k < n_readers; k++) {
+		exb_reader_options o = opt;
+		o.device = n_readers > 1 || bind.gpus > 0 ? (int32_t)(k % (idx_t)MaxValue<int>(exb_device_count(), 1)) : -1;
+		if (n_readers > 1 && shardable) {
+			o.range_lo = total_bytes * (int64_t)k / (int64_t)n_readers;
+			o.range_hi = k + 1 == n_readers ? 0 : total_bytes * (int64_t)(k + 1) / (int64_t)n_readers;
+		} else if (n_readers > 1) {
+			o.file_lo = (int32_t)((int64_t)n_files * (int64_t)k / (int64_t)n_readers);
+			o.file_hi = (int32_t)((int64_t)n_files * (int64_t)(k + 1) / (int64_t)n_readers);
+		}
+		exb_reader *reader = nullptr;
+		if (exb_reader_open2(bind.file_name.c_str(), bind.file_type.c_str(), comp, STANDARD_VECTOR_SIZE, filter_clause.c_str(), &o, &reader) != 0) {
 			throw std::runtime_error(exb_last_error());
 		}
-		state->count_left = rows;
+		state->readers.push_back(reader);
+	}
+	// one consumer per device pipeline is enough to hand out pointers; a lone pipeline gets a few so that whatever sits
+	// above the scan (string functions, aggregates) runs on several cores
+	state->threads_per_reader = n_readers == 1 ? 4 : (n_readers == 2 ? 2 : 1);
+
+	if (!any_column) { // COUNT(*): arrow_conversion.cpp:813-816 is the reference's "row id only" case
+		state->count_only = true;
+		vector<int64_t> rows(n_readers, 0);
+		vector<string> errors(n_readers);
+		vector<std::thread> workers;
+		for (idx_t k = 0; k < n_readers; k++) {
+			workers.emplace_back([&, k] {
+				if (exb_reader_count(state->readers[k], &rows[k]) != 0) {
+					errors[k] = exb_last_error();
+				}
+			});
+		}
+		for (auto &w : workers) {
+			w.join();
+		}
+		for (idx_t k = 0; k < n_readers; k++) {
+			if (!errors[k].empty()) {
+				throw std::runtime_error(errors[k]);
+			}
+			state->count_left += rows[k];
+		}
 	}
 	return std::move(state);
 }
 
+// one output vector <- one column view of a device-built batch: pointer assignments, no per-row work
+static void FillVector(Vector &vec, const exb_column_view &col, idx_t n, const shared_ptr<BatchHolder> &holder) {
+	vec.SetVectorType(VectorType::FLAT_VECTOR);
+	auto &validity = FlatVector::Validity(vec);
+	if (col.valid && col.chunk_nulls != 0) {
+		if (col.valid_bits) {
+			validity.Initialize(const_cast<validity_t *>(reinterpret_cast<const validity_t *>(col.valid_bits)));
+		} else {
+			for (idx_t i = 0; i < n; i++) {
+				if (!col.valid[i]) {
+					validity.SetInvalid(i);
+				}
+			}
+		}
+	}
+	switch (col.type) {
+	case EXB_T_VARCHAR:
+		if (!col.strings) {
+			throw InternalException("exon_b200: a column that was projected out is requested");
+		}
+		// string_t entries built on the device: <= 12 bytes inlined, longer values point into the batch's host buffer
+		FlatVector::SetData(vec, const_cast<data_ptr_t>(reinterpret_cast<const_data_ptr_t>(col.strings)));
+		StringVector::AddBuffer(vec, make_buffer<BatchBuffer>(holder));
+		break;
+	case EXB_T_INT32_LIST: {
+		FlatVector::SetData(vec, const_cast<data_ptr_t>(reinterpret_cast<const_data_ptr_t>(col.list_entries)));
+		auto &child = ListVector::GetEntry(vec);
+		child.SetVectorType(VectorType::FLAT_VECTOR);
+		FlatVector::SetData(child, const_cast<data_ptr_t>(reinterpret_cast<const_data_ptr_t>(col.values)));
+		ListVector::SetListSize(vec, (idx_t)col.n_values);
+		child.GetBuffer()->SetAuxiliaryData(make_uniq<BatchAux>(holder));
+		vec.GetBuffer()->SetAuxiliaryData(make_uniq<BatchAux>(holder));
+		break;
+	}
+	default:
+		FlatVector::SetData(vec, const_cast<data_ptr_t>(reinterpret_cast<const_data_ptr_t>(col.values)));
+		vec.GetBuffer()->SetAuxiliaryData(make_uniq<BatchAux>(holder));
+		break;
+	}
+}
+
 static void ScanFunction(ClientContext &context, TableFunctionInput &input, DataChunk &output) {
 	auto &state = input.global_state->Cast<ScanGlobalState>();
-	std::lock_guard<std::mutex> guard(state.lock);
-	if (state.done) {
-		return;
-	}
-	if (input.local_state) {
-		input.local_state->Cast<ScanLocalState>().batch_index = state.next_batch++;
-	}
+	auto &local = input.local_state->Cast<ScanLocalState>();
 	if (state.count_only) {
+		std::lock_guard<std::mutex> guard(state.lock);
 		const idx_t n = (idx_t)MinValue<int64_t>(STANDARD_VECTOR_SIZE, state.count_left);
 		state.count_left -= n;
-		if (n == 0) {
-			state.done = true;
-		}
 		output.SetCardinality(n);
 		return;
 	}
 	exb_batch batch;
-	if (exb_reader_next(state.reader, &batch) != 0) {
-		throw InvalidInputException(exb_last_error());
+	for (;;) {
+		if (local.shard < 0) {
+			std::lock_guard<std::mutex> guard(state.lock);
+			if (state.next_slot >= state.readers.size() * state.threads_per_reader) {
+				output.SetCardinality(0);
+				return;
+			}
+			local.shard = (int64_t)(state.next_slot++ / state.threads_per_reader);
+		}
+		if (exb_reader_next(state.readers[local.shard], &batch) != 0) { // thread safe: a batch goes to exactly one caller
+			throw InvalidInputException(exb_last_error());
+		}
+		if (batch.n_rows > 0) {
+			break;
+		}
+		local.shard = -1; // this pipeline is drained: move on to the next unclaimed one (always a later shard)
 	}
-	if (batch.n_rows == 0) {
-		state.done = true;
-		output.SetCardinality(0);
-		return;
-	}
+	// shard-major order = file order: shard k holds the k-th byte range (or the k-th group of files)
+	local.batch_index = ((idx_t)local.shard << 32) | (idx_t)batch.batch_index;
 	const idx_t n = (idx_t)batch.n_rows;
-	auto holder = make_buffer<BatchBuffer>(batch);
+	auto holder = make_shared<BatchHolder>(batch);
 	for (idx_t out_col = 0; out_col < state.column_ids.size(); out_col++) {
 		const auto id = state.column_ids[out_col];
 		auto &vec = output.data[out_col];
-		if (id == COLUMN_IDENTIFIER_ROW_ID) {
+		if (id == COLUMN_IDENTIFIER_ROW_ID || (id < state.n_file_cols && state.dead[id])) {
 			vec.SetVectorType(VectorType::CONSTANT_VECTOR);
 			ConstantVector::SetNull(vec, true);
 			continue;
 		}
-		const exb_column_view &col = batch.cols[id];
-		if (!col.offsets) {
-			throw InternalException("exon_b200: column %d was projected out but is requested", (int)id);
-		}
-		vec.SetVectorType(VectorType::FLAT_VECTOR);
-		auto strings = FlatVector::GetData<string_t>(vec);
-		auto &validity = FlatVector::Validity(vec);
-		const char *base = reinterpret_cast<const char *>(col.data);
-		for (idx_t i = 0; i < n; i++) {
-			if (col.valid && !col.valid[i]) {
-				validity.SetInvalid(i);
-				continue;
-			}
-			// <= 12 bytes are inlined by string_t; longer values point into the batch's buffer
-			strings[i] = string_t(base + col.offsets[i], (uint32_t)(col.offsets[i + 1] - col.offsets[i]));
-		}
-		StringVector::AddBuffer(vec, holder);
+		FillVector(vec, batch.cols[id], n, holder);
 	}
 	output.SetCardinality(n);
 }
@@ -269,7 +418,37 @@ static string ScanToString(const FunctionData *bind_data_p) {
 	if (!bind.pushed.empty()) {
 		s += "\nDevice filters: " + StringUtil::Join(bind.pushed, " AND ");
 	}
+	if (!bind.computed.empty()) {
+		vector<string> names;
+		for (auto &c : bind.computed) {
+			names.push_back(c.name);
+		}
+		s += "\nDevice columns: " + StringUtil::Join(names, ", ");
+	}
+	vector<string> dead;
+	for (idx_t c = 0; c < bind.dead.size(); c++) {
+		if (bind.dead[c]) {
+			dead.push_back(bind.names[c]);
+		}
+	}
+	if (!dead.empty()) {
+		s += "\nNot read back: " + StringUtil::Join(dead, ", ");
+	}
 	return s;
+}
+
+// table_scan_progress: input bytes the device pipelines have consumed / input bytes (the reference leaves it unset,
+// module.cpp:296-318)
+static double ScanProgress(ClientContext &context, const FunctionData *bind_data, const GlobalTableFunctionState *global_state) {
+	auto &state = global_state->Cast<ScanGlobalState>();
+	int64_t done = 0, total = 0;
+	for (auto r : state.readers) {
+		int64_t d = 0, t = 0;
+		exb_reader_progress(r, &d, &t);
+		done += d;
+		total += t;
+	}
+	return total > 0 ? 100.0 * (double)done / (double)total : 100.0;
 }
 
 // ---- complex filter push-down
@@ -289,7 +468,7 @@ static bool IsColumn(const Expression &e, LogicalGet &get, const ScanBindData &b
 		return false;
 	}
 	auto &ref = e.Cast<BoundColumnRefExpression>();
-	if (ref.binding.table_index != get.table_index || ref.binding.column_index >= get.column_ids.size()) {
+	if (ref.depth != 0 || ref.binding.table_index != get.table_index || ref.binding.column_index >= get.column_ids.size()) {
 		return false;
 	}
 	auto id = get.column_ids[ref.binding.column_index];
@@ -309,7 +488,9 @@ static bool NumericConstant(const Expression &e, double &value, LogicalTypeId &t
 		return false;
 	}
 	value = c.value.GetValue<double>();
-	return true;
+	// DuckDB orders DOUBLE totally (NaN is the largest value, NaN = NaN); the device compares with IEEE semantics, and
+	// nobody re-checks an absorbed predicate: leave NaN / infinite constants to DuckDB's own filter
+	return std::isfinite(value);
 }
 
 static const char *OperatorText(ExpressionType t, bool flipped) {
@@ -331,6 +512,39 @@ static const char *OperatorText(ExpressionType t, bool flipped) {
 	}
 }
 
+// list_avg(quality_score_string_to_list(quality_scores)): list_avg(l) is the macro list_aggr(l, 'avg')
+// (duckdb/src/catalog/default/default_functions.cpp:103)
+static bool IsMeanQuality(const Expression &f, LogicalGet &get, const ScanBindData &bind) {
+	if (bind.file_type != "fastq" || f.expression_class != ExpressionClass::BOUND_FUNCTION) {
+		return false;
+	}
+	auto &fn = f.Cast<BoundFunctionExpression>();
+	const string fname = StringUtil::Lower(fn.function.name);
+	if (!(fname == "list_aggr" || fname == "list_aggregate" || fname == "array_aggr" || fname == "array_aggregate") || fn.children.size() != 2 ||
+	    fn.return_type.id() != LogicalTypeId::DOUBLE) {
+		return false;
+	}
+	auto &name_arg = *fn.children[1];
+	if (name_arg.expression_class != ExpressionClass::BOUND_CONSTANT) {
+		return false;
+	}
+	auto &cv = name_arg.Cast<BoundConstantExpression>().value;
+	if (cv.IsNull() || cv.type().id() != LogicalTypeId::VARCHAR) {
+		return false;
+	}
+	const string agg = StringUtil::Lower(cv.GetValue<string>());
+	if (agg != "avg" && agg != "mean") {
+		return false;
+	}
+	auto &inner = *fn.children[0];
+	if (inner.expression_class != ExpressionClass::BOUND_FUNCTION) {
+		return false;
+	}
+	auto &qfn = inner.Cast<BoundFunctionExpression>();
+	return StringUtil::Lower(qfn.function.name) == "quality_score_string_to_list" && qfn.children.size() == 1 &&
+	       IsColumn(*qfn.children[0], get, bind, "quality_scores");
+}
+
 // returns the engine predicate for `func_side <op> constant`, or "" if the expression is not one we absorb
 static string MatchPredicate(const Expression &func_side, const Expression &const_side, ExpressionType cmp, bool flipped, LogicalGet &get,
                              const ScanBindData &bind) {
@@ -350,35 +564,7 @@ static string MatchPredicate(const Expression &func_side, const Expression &cons
 	const string fname = StringUtil::Lower(fn.function.name);
 	char buf[64];
 	snprintf(buf, sizeof(buf), "%.17g", value);
-	if (bind.file_type == "fastq" && !was_cast && ctype == LogicalTypeId::DOUBLE &&
-	    (fname == "list_aggr" || fname == "list_aggregate" || fname == "array_aggr" || fname == "array_aggregate") && fn.children.size() == 2 &&
-	    fn.return_type.id() == LogicalTypeId::DOUBLE) {
-		// list_avg(l) is the macro list_aggr(l, 'avg') (duckdb/src/catalog/default/default_functions.cpp:103)
-		double dummy;
-		LogicalTypeId t;
-		(void)dummy;
-		(void)t;
-		auto &name_arg = *fn.children[1];
-		if (name_arg.expression_class != ExpressionClass::BOUND_CONSTANT) {
-			return "";
-		}
-		auto &cv = name_arg.Cast<BoundConstantExpression>().value;
-		if (cv.IsNull() || cv.type().id() != LogicalTypeId::VARCHAR) {
-			return "";
-		}
-		const string agg = StringUtil::Lower(cv.GetValue<string>());
-		if (agg != "avg" && agg != "mean") {
-			return "";
-		}
-		auto &inner = *fn.children[0];
-		if (inner.expression_class != ExpressionClass::BOUND_FUNCTION) {
-			return "";
-		}
-		auto &qfn = inner.Cast<BoundFunctionExpression>();
-		if (StringUtil::Lower(qfn.function.name) != "quality_score_string_to_list" || qfn.children.size() != 1 ||
-		    !IsColumn(*qfn.children[0], get, bind, "quality_scores")) {
-			return "";
-		}
+	if (!was_cast && ctype == LogicalTypeId::DOUBLE && IsMeanQuality(f, get, bind)) {
 		return string("mean_quality(quality_scores)") + op + buf;
 	}
 	if (fname == "gc_content" && fn.children.size() == 1 && IsColumn(*fn.children[0], get, bind, "sequence")) {
@@ -428,12 +614,195 @@ static idx_t ScanGetBatchIndex(ClientContext &context, const FunctionData *bind_
 	return local_state->Cast<ScanLocalState>().batch_index;
 }
 
+// ---- projection push-down of the scalar functions (north_star kernel 3)
+// An OptimizerExtension (optimizer_extension.hpp; run at the end of Optimizer::Optimize, optimizer.cpp:162-166) that
+// rewrites  gc_content(sequence), reverse_complement / complement / transcribe / reverse_transcribe(sequence),
+// quality_score_string_to_list(quality_scores) and list_avg(quality_score_string_to_list(quality_scores))
+// directly above a read_fasta / read_fastq scan into hidden computed columns OF THE SCAN: the kernels that would run per
+// DataChunk through the scalar-function callbacks (sequence_functions/module.cpp:30-253, fastq_functions/module.cpp:
+// 32-50) run once per 64 MiB chunk while it is in HBM, and a source column nothing else reads never crosses PCIe.
+// Signatures, results and error messages are unchanged; EXPLAIN lists the columns under "Device columns".
+struct RewriteCtx {
+	LogicalGet &get;
+	ScanBindData &bind;
+	bool allow_throwing; // the LUT maps raise on a byte outside their table: only where every scanned row is evaluated
+	idx_t rewritten = 0;
+};
+
+static bool MatchComputed(const Expression &e, RewriteCtx &ctx, ComputedColumn &out) {
+	if (e.expression_class != ExpressionClass::BOUND_FUNCTION) {
+		return false;
+	}
+	auto &fn = e.Cast<BoundFunctionExpression>();
+	const string fname = StringUtil::Lower(fn.function.name);
+	if (IsMeanQuality(e, ctx.get, ctx.bind)) {
+		out = ComputedColumn {EXB_C_MEAN_QUALITY, 0, "list_avg(quality_score_string_to_list(quality_scores))", LogicalType::DOUBLE};
+		return true;
+	}
+	if (fn.children.size() != 1) {
+		return false;
+	}
+	if (fname == "gc_content" && fn.return_type.id() == LogicalTypeId::FLOAT && IsColumn(*fn.children[0], ctx.get, ctx.bind, "sequence")) {
+		out = ComputedColumn {EXB_C_GC_CONTENT, 0, "gc_content(sequence)", LogicalType::FLOAT};
+		return true;
+	}
+	if (fname == "quality_score_string_to_list" && ctx.bind.file_type == "fastq" && IsColumn(*fn.children[0], ctx.get, ctx.bind, "quality_scores")) {
+		out = ComputedColumn {EXB_C_QUALITY_LIST, 0, "quality_score_string_to_list(quality_scores)", LogicalType::LIST(LogicalType::INTEGER)};
+		return true;
+	}
+	static const struct {
+		const char *name;
+		int mode;
+	} maps[] = {{"reverse_complement", EXB_MAP_REVERSE_COMPLEMENT},
+	            {"complement", EXB_MAP_COMPLEMENT},
+	            {"transcribe", EXB_MAP_TRANSCRIBE},
+	            {"reverse_transcribe", EXB_MAP_REVERSE_TRANSCRIBE}};
+	for (auto &m : maps) {
+		if (fname == m.name && ctx.allow_throwing && fn.return_type.id() == LogicalTypeId::VARCHAR &&
+		    IsColumn(*fn.children[0], ctx.get, ctx.bind, "sequence")) {
+			out = ComputedColumn {EXB_C_SEQ_MAP, m.mode, string(m.name) + "(sequence)", LogicalType::VARCHAR};
+			return true;
+		}
+	}
+	return false;
+}
+
+// the scan column (position in get.column_ids) that serves `c`, created on first use
+static idx_t ComputedBinding(RewriteCtx &ctx, const ComputedColumn &c) {
+	idx_t k = 0;
+	for (; k < ctx.bind.computed.size(); k++) {
+		if (ctx.bind.computed[k].kind == c.kind && ctx.bind.computed[k].arg == c.arg) {
+			break;
+		}
+	}
+	if (k == ctx.bind.computed.size()) {
+		if (k >= EXB_MAX_COMPUTED) {
+			return DConstants::INVALID_INDEX;
+		}
+		ctx.bind.computed.push_back(c);
+		ctx.get.returned_types.push_back(c.type);
+		ctx.get.names.push_back(c.name);
+	}
+	const column_t id = ctx.bind.names.size() + k;
+	for (idx_t i = 0; i < ctx.get.column_ids.size(); i++) {
+		if (ctx.get.column_ids[i] == id) {
+			return i;
+		}
+	}
+	ctx.get.column_ids.push_back(id);
+	return ctx.get.column_ids.size() - 1;
+}
+
+static void RewriteExpression(unique_ptr<Expression> &expr, RewriteCtx &ctx, vector<idx_t> &added) {
+	ComputedColumn c;
+	if (MatchComputed(*expr, ctx, c)) {
+		const idx_t before = ctx.get.column_ids.size();
+		const idx_t pos = ComputedBinding(ctx, c);
+		if (pos != DConstants::INVALID_INDEX) {
+			if (ctx.get.column_ids.size() != before) {
+				added.push_back(pos);
+			}
+			auto ref = make_uniq<BoundColumnRefExpression>(c.name, c.type, ColumnBinding(ctx.get.table_index, pos));
+			ref->alias = expr->alias;
+			expr = std::move(ref);
+			ctx.rewritten++;
+			return;
+		}
+	}
+	ExpressionIterator::EnumerateChildren(*expr, [&](unique_ptr<Expression> &child) { RewriteExpression(child, ctx, added); });
+}
+
+static void CountReferences(const Expression &e, idx_t table_index, vector<idx_t> &refs) {
+	if (e.expression_class == ExpressionClass::BOUND_COLUMN_REF) {
+		auto &ref = e.Cast<BoundColumnRefExpression>();
+		if (ref.binding.table_index == table_index && ref.binding.column_index < refs.size()) {
+			refs[ref.binding.column_index]++;
+		}
+	}
+	ExpressionIterator::EnumerateChildren(e, [&](const Expression &child) { CountReferences(child, table_index, refs); });
+}
+
+static bool IsExonScan(LogicalOperator &op) {
+	if (op.type != LogicalOperatorType::LOGICAL_GET) {
+		return false;
+	}
+	auto &get = op.Cast<LogicalGet>();
+	return get.function.function == ScanFunction && get.bind_data && get.projection_ids.empty() && get.children.empty();
+}
+
+static void OptimizeOperator(LogicalOperator &op) {
+	for (auto &child : op.children) {
+		OptimizeOperator(*child);
+	}
+	// `op` consumes a scan directly, or through a chain of filters that pass the scan's columns up unchanged
+	for (auto &child : op.children) {
+		vector<LogicalFilter *> filters;
+		LogicalOperator *cur = child.get();
+		while (cur->type == LogicalOperatorType::LOGICAL_FILTER && cur->children.size() == 1) {
+			filters.push_back(&cur->Cast<LogicalFilter>());
+			cur = cur->children[0].get();
+		}
+		if (!IsExonScan(*cur) || op.type == LogicalOperatorType::LOGICAL_FILTER) {
+			continue; // a filter is handled from the operator above it
+		}
+		auto &get = cur->Cast<LogicalGet>();
+		auto &bind = get.bind_data->Cast<ScanBindData>();
+		RewriteCtx ctx {get, bind, filters.empty()};
+		vector<idx_t> added; // positions in get.column_ids created by this rewrite
+		LogicalOperatorVisitor::EnumerateExpressions(op, [&](unique_ptr<Expression> *e) { RewriteExpression(*e, ctx, added); });
+		for (auto f : filters) {
+			RewriteCtx fctx {get, bind, false};
+			LogicalOperatorVisitor::EnumerateExpressions(*f, [&](unique_ptr<Expression> *e) { RewriteExpression(*e, fctx, added); });
+			ctx.rewritten += fctx.rewritten;
+		}
+		if (ctx.rewritten == 0) {
+			continue;
+		}
+		// filters that pass only some of their child's columns up must pass the new ones too (bottom filter first)
+		for (idx_t fi = filters.size(); fi-- > 0;) {
+			auto &f = *filters[fi];
+			if (f.projection_map.empty()) {
+				continue; // passes everything
+			}
+			auto below = f.children[0]->GetColumnBindings();
+			for (idx_t pos : added) {
+				for (idx_t b = 0; b < below.size(); b++) {
+					if (below[b].table_index == get.table_index && below[b].column_index == pos) {
+						f.projection_map.push_back(b);
+					}
+				}
+			}
+		}
+		// file columns that nothing reads any more stay in column_ids (table filters and bindings index it) but are not
+		// materialised: the scan hands DuckDB a constant NULL vector for them.  Only when `op` ends the columns' life.
+		if (op.type == LogicalOperatorType::LOGICAL_PROJECTION || op.type == LogicalOperatorType::LOGICAL_AGGREGATE_AND_GROUP_BY) {
+			vector<idx_t> refs(get.column_ids.size(), 0);
+			LogicalOperatorVisitor::EnumerateExpressions(op, [&](unique_ptr<Expression> *e) { CountReferences(**e, get.table_index, refs); });
+			for (auto f : filters) {
+				LogicalOperatorVisitor::EnumerateExpressions(*f, [&](unique_ptr<Expression> *e) { CountReferences(**e, get.table_index, refs); });
+			}
+			for (idx_t i = 0; i < get.column_ids.size(); i++) {
+				const auto id = get.column_ids[i];
+				if (id != COLUMN_IDENTIFIER_ROW_ID && id < bind.names.size() && refs[i] == 0) {
+					bind.dead[id] = true;
+				}
+			}
+		}
+	}
+}
+
+static void ExonOptimize(ClientContext &context, OptimizerExtensionInfo *info, unique_ptr<LogicalOperator> &plan) {
+	OptimizeOperator(*plan);
+}
+
 static void RegisterScan(ClientContext &context, const string &name, const string &file_type) {
 	TableFunction scan(name, {LogicalType::VARCHAR}, ScanFunction, ScanBind, ScanInitGlobal, ScanInitLocal);
 	scan.cardinality = ScanCardinality;        // module.cpp:307
 	scan.get_batch_index = ScanGetBatchIndex;  // module.cpp:308
+	scan.table_scan_progress = ScanProgress;
 	scan.function_info = make_shared<ScanInfo>(file_type);
 	scan.named_parameters["compression"] = LogicalType::VARCHAR;
+	scan.named_parameters["gpus"] = LogicalType::INTEGER; // extension of this build: device pipelines (0 = automatic)
 	scan.projection_pushdown = true;
 	scan.filter_pushdown = true;
 	scan.pushdown_complex_filter = ScanPushdownComplexFilter;
@@ -647,6 +1016,9 @@ static void LoadInternal(DatabaseInstance &instance) {
 	RegisterScan(context, "read_fasta", "fasta");
 	RegisterScan(context, "read_fastq", "fastq");
 	config.replacement_scans.emplace_back(ExonReplacementScan);
+	OptimizerExtension fuse;
+	fuse.optimize_function = ExonOptimize;
+	config.optimizer_extensions.push_back(fuse);
 	con.Commit();
 }
 

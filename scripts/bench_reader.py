@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """End-to-end throughput of the native reader (exb_reader_*: the calls the DuckDB extension's bind / init / scan
-callbacks make, include/exon_b200.h section 1b) from a file on disk (tmpfs) to host-resident 2048-row batches.
+callbacks make, include/exon_b200.h) from a file on disk (tmpfs) to host-resident 2048-row batches in DuckDB's
+vector layout.
 
 usage (GPU box): python scripts/bench_reader.py [--reads N] [--out gpurun_out/reader.json]
 Wall clock around open .. last batch .. close; GB/s = input file bytes / wall time.  The reference's equivalent is
@@ -15,16 +16,16 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from exon_duckdb_b200 import _lib
-from tools import synth
 from exon_duckdb_b200._lib import check, lib
+from tools import synth
 
 
-def run(path, fmt, mask, filters, count_only, batch_rows=2048):
+def run(path, fmt, mask, filters, count_only, computed=(), batch_rows=2048):
     h = C.c_void_p()
     t0 = time.perf_counter()
-    check(lib().exb_reader_open(path.encode(), fmt.encode(), None, batch_rows, filters.encode() if filters else None, mask, C.byref(h)))
+    o = _lib.reader_options(column_mask=mask, flags=_lib.RD_STRING_T | _lib.RD_NO_OFFSETS, computed=computed)
+    check(lib().exb_reader_open2(path.encode(), fmt.encode(), None, batch_rows, filters.encode() if filters else None, C.byref(o), C.byref(h)))
     rows = 0
-    nbytes = 0
     if count_only:
         n = C.c_int64()
         check(lib().exb_reader_count(h, C.byref(n)))
@@ -36,57 +37,53 @@ def run(path, fmt, mask, filters, count_only, batch_rows=2048):
             if b.n_rows == 0:
                 break
             rows += b.n_rows
-            for c in range(b.n_cols):
-                if b.cols[c].offsets:
-                    nbytes += b.cols[c].offsets[b.n_rows] - b.cols[c].offsets[0]
             lib().exb_batch_release(C.byref(b))
     lib().exb_reader_close(h)
-    return time.perf_counter() - t0, rows, nbytes
+    return time.perf_counter() - t0, rows
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--reads", type=int, default=4_000_000)
-    ap.add_argument("--contigs", type=int, default=1200)
+    ap.add_argument("--reads", type=int, default=8_000_000)
+    ap.add_argument("--contigs", type=int, default=2400)
     ap.add_argument("--dir", default="/dev/shm")
     ap.add_argument("--out", default="gpurun_out/reader.json")
-    ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--repeat", type=int, default=5)
     args = ap.parse_args()
-    from exon_duckdb_b200 import device as D
 
     rows = []
     fq = os.path.join(args.dir, "exb_bench.fastq")
     fa = os.path.join(args.dir, "exb_bench.fasta")
-    synth.gen_host(synth.gen_params("illumina", args.reads, seed=20)).tofile(fq)
-    synth.gen_host(synth.gen_params("fasta", args.contigs, seed=3, len_min=500000, len_max=500000, wrap=60)).tofile(fa)
+    if not os.path.exists(fq):
+        synth.gen_host(synth.gen_params("illumina", args.reads, seed=20)).tofile(fq)
+    if not os.path.exists(fa):
+        synth.gen_host(synth.gen_params("fasta", args.contigs, seed=3, len_min=500000, len_max=500000, wrap=60)).tofile(fa)
     cases = [
-        ("read_fastq COUNT(*)", fq, "fastq", 0xF, None, True),
-        ("read_fastq COUNT(*) WHERE mean quality > 30", fq, "fastq", 0xF, "mean_quality(quality_scores) > 30", True),
-        ("read_fastq all 4 columns", fq, "fastq", 0xF, None, False),
-        ("read_fastq sequence only", fq, "fastq", 0x4, None, False),
-        ("read_fastq name, sequence WHERE mean quality > 30", fq, "fastq", 0x5, "mean_quality(quality_scores) > 30", False),
-        ("read_fasta COUNT(*)", fa, "fasta", 0x7, None, True),
-        ("read_fasta id only", fa, "fasta", 0x1, None, False),
-        ("read_fasta all 3 columns", fa, "fasta", 0x7, None, False),
+        ("read_fastq COUNT(*)", fq, "fastq", 0, None, True, ()),
+        ("read_fastq COUNT(*) WHERE mean quality > 30", fq, "fastq", 0, "mean_quality(quality_scores)>30", True, ()),
+        ("read_fastq all 4 columns", fq, "fastq", 0xF, None, False, ()),
+        ("read_fastq sequence only", fq, "fastq", 0x4, None, False, ()),
+        ("read_fastq name, sequence WHERE mean quality > 30", fq, "fastq", 0x5, "mean_quality(quality_scores)>30", False, ()),
+        ("read_fastq gc_content(sequence) [computed, no column read back]", fq, "fastq", 0, None, False, ((_lib.C_GC_CONTENT, 0),)),
+        ("read_fastq reverse_complement(sequence) [computed]", fq, "fastq", 0, None, False, ((_lib.C_SEQ_MAP, 0),)),
+        ("read_fastq quality_score_string_to_list(quality_scores) [computed]", fq, "fastq", 0, None, False, ((_lib.C_QUALITY_LIST, 0),)),
+        ("read_fasta COUNT(*)", fa, "fasta", 0, None, True, ()),
+        ("read_fasta id, gc_content(sequence) [computed]", fa, "fasta", 0x1, None, False, ((_lib.C_GC_CONTENT, 0),)),
+        ("read_fasta all 3 columns", fa, "fasta", 0x7, None, False, ()),
     ]
-    for name, path, fmt, mask, filt, cnt in cases:
+    for name, path, fmt, mask, filt, cnt, comp in cases:
         size = os.path.getsize(path)
-        best = None
-        try:
-            for _ in range(args.repeat):
-                dt, n, nb = run(path, fmt, mask, filt, cnt)
-                best = dt if best is None or dt < best else best
-        except Exception as e:  # a filter spelling the reader does not parse is reported, not fatal
-            print("%-52s  FAILED: %s" % (name, e), flush=True)
-            continue
-        gbs = size / best / 1e9
-        rows.append({"path": name, "file_bytes": size, "rows": n, "column_bytes": nb, "s_best": best, "GB/s": gbs})
-        print("%-52s %8.1f ms  %7.2f GB/s  rows %d  column bytes %d" % (name, best * 1e3, gbs, n, nb), flush=True)
-    os.unlink(fq)
-    os.unlink(fa)
+        times = []
+        for _ in range(args.repeat):
+            dt, n = run(path, fmt, mask, filt, cnt, comp)
+            times.append(dt)
+        best, med = min(times), sorted(times)[len(times) // 2]
+        rows.append({"case": name, "bytes": size, "rows": n, "best_ms": best * 1e3, "median_ms": med * 1e3, "best_gbs": size / 1e9 / best,
+                     "median_gbs": size / 1e9 / med, "all_ms": [t * 1e3 for t in times]})
+        print("%-68s best %7.1f ms %6.2f GB/s | median %7.1f ms %6.2f GB/s  rows %d" % (name, best * 1e3, size / 1e9 / best, med * 1e3, size / 1e9 / med, n), flush=True)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
-        json.dump({"rows": rows}, f, indent=1)
+        json.dump(rows, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -326,3 +326,148 @@ def test_fasta_rows_and_gc_per_contig(cuda_device, tmp_path, ext):
         r = run_sql(ext, ["SELECT id, gc_content(sequence)::DOUBLE FROM read_fasta('%s')" % path], env=env)
         for (i, g), w in zip(rows(r[0]), want):
             assert i == w[0] and np.float32(float(g)) == O.gc_content(w[2].encode())
+
+
+# ------------------------------------------------------------------ projections served by the scan (optimizer extension)
+def _plan(r):
+    return scalar(r) if len(rows(r)[0]) == 1 else rows(r)[0][1]
+
+
+def test_projections_are_fused_into_the_scan():
+    """gc_content / the LUT maps / quality decode / list_avg(decode) over a scan column become computed columns of the scan
+    (EXPLAIN lists them under "Device columns"); anything else keeps the scalar-function path."""
+    fq, fa = "%s/test.fastq" % G, "%s/test.fasta" % G
+    r = run_sql(PRODUCT, [
+        "EXPLAIN SELECT id, gc_content(sequence) FROM read_fasta('%s')" % fa,
+        "EXPLAIN SELECT avg(gc_content(sequence)) FROM read_fastq('%s')" % fq,
+        "EXPLAIN SELECT sum(length(reverse_complement(sequence))) FROM read_fastq('%s')" % fq,
+        "EXPLAIN SELECT name, list_avg(quality_score_string_to_list(quality_scores)) FROM read_fastq('%s')" % fq,
+        # a LUT map raises on a byte outside its table: above a filter that DuckDB evaluates it must only see the surviving rows
+        "EXPLAIN SELECT complement(sequence) FROM read_fastq('%s') WHERE length(sequence) > 3" % fq,
+        # gc_content never raises: fused through the filter
+        "EXPLAIN SELECT gc_content(sequence) FROM read_fastq('%s') WHERE length(sequence) > 3" % fq,
+        # not a plain column underneath: the scalar function runs
+        "EXPLAIN SELECT gc_content(sequence || 'A') FROM read_fastq('%s')" % fq,
+        # DuckDB's common-subexpression pass decodes once and averages the list itself: the decode is the fused column
+        "EXPLAIN SELECT quality_score_string_to_list(quality_scores), list_avg(quality_score_string_to_list(quality_scores)) FROM read_fastq('%s')" % fq,
+    ])
+    p = ["".join(ch for ch in _plan(x) if ch not in "│ \n─┌┐└┘┬┴") for x in r]  # the box renderer wraps long lines
+    assert "Devicecolumns:gc_content(sequence)" in p[0]
+    assert "Devicecolumns:gc_content(sequence)" in p[1] and "Notreadback:sequence" in p[1]
+    assert "Devicecolumns:reverse_complement(se" in p[2] and "Notreadback:sequence" in p[2]
+    assert "Devicecolumns:" in p[3] and "list_avg(quality_score_string_to_list(quality_scores))" in p[3] and "Notreadback:quality_scores" in p[3]
+    assert "Devicecolumns" not in p[4] and "complement" in p[4]
+    assert "Devicecolumns:gc_content(sequence)" in p[5] and "FILTER" in p[5] and "Notreadback" not in p[5]
+    assert "Devicecolumns" not in p[6]
+    assert "Devicecolumns:quality_" in p[7] and "Notreadback:quality_scores" in p[7] and "list_aggr(#" in p[7]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads", [1, 4])
+def test_fused_projections_match_the_oracle(cuda_device, tmp_path, threads):
+    """Every fused projection, row by row, against the oracle's scalar functions; with pushed-down filters, filters DuckDB
+    keeps, several device chunks and several DuckDB threads."""
+    from oracle import oracle as O
+    text, _ = util.random_fastq(23, 6000, min_len=0, max_len=180, tricky=False)
+    path = _write(tmp_path, "p.fastq", text)
+    ref = O.parse_fastq(text)
+    names = [x.decode() for x in ref.strings("name")]
+    seqs, quals = ref.strings("sequence"), ref.strings("quality_scores")
+    env = {"EXON_B200_CHUNK_BYTES": str(150_000)}
+    res = run_sql(PRODUCT, [
+        "SELECT name, gc_content(sequence)::DOUBLE, reverse_complement(sequence), complement(sequence) FROM read_fastq('%s')" % path,
+        "SELECT name, quality_score_string_to_list(quality_scores), list_avg(quality_score_string_to_list(quality_scores)) FROM read_fastq('%s')" % path,
+        "SELECT name, transcribe(sequence), gc_content(sequence)::DOUBLE FROM read_fastq('%s') WHERE list_avg(quality_score_string_to_list(quality_scores)) > 80" % path,
+        "SELECT name, gc_content(sequence)::DOUBLE FROM read_fastq('%s') WHERE length(sequence) > 90" % path,
+        "SELECT count(*), sum(length(reverse_complement(sequence))), avg(gc_content(sequence)) FROM read_fastq('%s')" % path,
+        "SELECT name, gc_content(sequence)::DOUBLE, sequence FROM read_fastq('%s') WHERE name >= 'r3' LIMIT 5 OFFSET 2100" % path,
+    ], threads=threads, env=env)
+    got = rows(res[0])
+    assert [g[0] for g in got] == names
+    for g, s in zip(got, seqs):
+        assert np.float32(float(g[1])) == O.gc_content(s) and g[2].encode() == O.reverse_complement(s) and g[3].encode() == O.complement(s)
+    got = rows(res[1])
+    assert [g[0] for g in got] == names
+    for g, q in zip(got, quals):
+        want = [c - 33 for c in q]
+        assert json.loads(g[1]) == want if isinstance(g[1], str) else list(g[1]) == want
+        if want:
+            assert float(g[2]) == float(np.longdouble(sum(want)) / np.longdouble(len(want)))
+        else:
+            assert g[2] is None
+    keep = [i for i, q in enumerate(quals) if O.mean_quality_pass(q, ">", 80.0)]
+    got = rows(res[2])
+    assert [g[0] for g in got] == [names[i] for i in keep]
+    for g, i in zip(got, keep):
+        assert g[1].encode() == seqs[i].replace(b"T", b"U") and np.float32(float(g[2])) == O.gc_content(seqs[i])
+    keep = [i for i, s in enumerate(seqs) if len(s) > 90]
+    got = rows(res[3])
+    assert [g[0] for g in got] == [names[i] for i in keep]
+    assert all(np.float32(float(g[1])) == O.gc_content(seqs[i]) for g, i in zip(got, keep))
+    cnt, total, avg = rows(res[4])[0]
+    assert (int(cnt), int(total)) == (len(seqs), sum(len(s) for s in seqs))
+    assert abs(float(avg) - float(np.mean([np.float64(O.gc_content(s)) for s in seqs]))) < 1e-9
+    keep = [i for i, n in enumerate(names) if n >= "r3"][2100:2105]
+    assert [(g[0], g[2]) for g in rows(res[5])] == [(names[i], seqs[i].decode()) for i in keep]
+
+
+@pytest.mark.gpu
+def test_fused_map_reports_the_reference_error(cuda_device, tmp_path):
+    """reverse_complement over the scan raises the reference's message for a byte outside ACGT (module.cpp:58-62), fused or not."""
+    text = util.fastq_text([(b"a", None, b"ACGT", b"IIII"), (b"b", b"d", b"ACNT", b"IIII"), (b"c", None, b"ACGT", b"IIII")])
+    path = _write(tmp_path, "n.fastq", text)
+    _need(SQLRUN, PRODUCT)
+    for q in ("SELECT reverse_complement(sequence) FROM read_fastq('%s')", "SELECT reverse_complement(sequence || '') FROM read_fastq('%s')"):
+        out = subprocess.run([SQLRUN], input=("LOAD '%s';\n%s;\n" % (PRODUCT, q % path)).encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+        res = [json.loads(l) for l in out.stdout.decode().splitlines()]
+        assert not res[1]["ok"] and "Invalid character in sequence: N" in res[1]["error"], res[1]
+    r = run_sql(PRODUCT, ["SELECT reverse_complement(sequence) FROM read_fastq('%s') WHERE name <> 'b'" % path])
+    assert rows(r[0]) == [["CATG"], ["CATG"]]  # the pushed-down filter removes the bad row before the map sees it (A->C C->A G->T T->G)
+
+
+@pytest.mark.gpu
+def test_fused_fasta_projections(cuda_device, tmp_path):
+    from oracle import oracle as O
+    text, _ = util.random_fasta(9, 200, min_len=0, max_len=4000, tricky=False)
+    path = _write(tmp_path, "p.fasta", text)
+    ref = O.parse_fasta(text)
+    ids = [x.decode() for x in ref.strings("id")]
+    seqs = ref.strings("sequence")
+    res = run_sql(PRODUCT, ["SELECT id, gc_content(sequence)::DOUBLE FROM read_fasta('%s')" % path,
+                            "SELECT id, gc_content(sequence)::DOUBLE, length(sequence) FROM read_fasta('%s') WHERE gc_content(sequence) > 0.5" % path,
+                            "SELECT count(*), avg(gc_content(sequence)) FROM read_fasta('%s')" % path],
+                  threads=4, env={"EXON_B200_CHUNK_BYTES": str(120_000)})
+    assert [(g[0], np.float32(float(g[1]))) for g in rows(res[0])] == [(i, O.gc_content(s)) for i, s in zip(ids, seqs)]
+    keep = [k for k, s in enumerate(seqs) if O.gc_content(s) > np.float32(0.5)]
+    assert [(g[0], int(g[2])) for g in rows(res[1])] == [(ids[k], len(seqs[k])) for k in keep]
+    assert int(rows(res[2])[0][0]) == len(seqs)
+
+
+@pytest.mark.gpu
+def test_c1_small_fasta_count(cuda_device, tmp_path):
+    """BASELINE configs[0]: SELECT COUNT(*) FROM read_fasta on the 10 000-record synthetic FASTA, at its stated size."""
+    from oracle import oracle as O
+    from tools import synth
+    p = synth.gen_params("fasta", 10_000, seed=1, len_min=200, len_max=2000, wrap=60)
+    text = synth.gen_host(p).tobytes()
+    path = _write(tmp_path, "c1.fasta", text)
+    res = run_sql(PRODUCT, ["SELECT COUNT(*) FROM read_fasta('%s')" % path, "SELECT COUNT(*), SUM(length(sequence)) FROM '%s'" % path])
+    ref = O.parse_fasta(text)
+    assert rows(res[0]) == [["10000"]] and ref.n == 10_000
+    assert rows(res[1]) == [["10000", str(sum(len(s) for s in ref.strings("sequence")))]]
+
+
+@pytest.mark.gpu
+def test_gpus_parameter(cuda_device, tmp_path):
+    """`gpus := n` pins the number of device pipelines; more than the box has is a bind-time error, not a silent fallback."""
+    import torch
+    text, _ = util.random_fastq(31, 4000, min_len=20, max_len=150, tricky=False)
+    path = _write(tmp_path, "g.fastq", text)
+    n_dev = torch.cuda.device_count()
+    r = run_sql(PRODUCT, ["SELECT count(*) FROM read_fastq('%s', gpus := 1)" % path])
+    assert rows(r[0]) == [["4000"]]
+    _need(SQLRUN, PRODUCT)
+    out = subprocess.run([SQLRUN], input=("LOAD '%s';\nSELECT count(*) FROM read_fastq('%s', gpus := %d);\n" % (PRODUCT, path, n_dev + 1)).encode(),
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    res = [json.loads(l) for l in out.stdout.decode().splitlines()]
+    assert not res[1]["ok"] and "CUDA device" in res[1]["error"]
