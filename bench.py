@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-paths", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--tmp", default=os.environ.get("EXB_BENCH_TMP", "/dev/shm"))
     args = ap.parse_args()
     if args.impl == "reference":
@@ -261,25 +262,6 @@ def main():
         # provisional phase, all-gather of the 128-byte result blocks, device-side composition, resolve kernel, all-reduce.
         from exon_duckdb_b200 import dist as XD
 
-        R = args.reads
-
-        def rec_size(i):
-            q = synth.gen_params("illumina", 1, seed=SEED, first_record=i, len_min=READ_LEN, len_max=READ_LEN)
-            return synth.gen_size(q)
-
-        def delta(k):  # offset of shard k's first byte inside record k*R; local offset of that byte is a multiple of 16
-            if k == 0:
-                return 0
-            s_prev = rec_size(k * R - 1)
-            return 96 + ((-(s_prev + 96)) % 16)
-
-        first = rank * R - (1 if rank else 0)
-        count = R + (1 if rank else 0) + (1 if rank < world - 1 else 0)
-        p = synth.gen_params("illumina", count, seed=SEED, first_record=first, len_min=READ_LEN, len_max=READ_LEN)
-        gbuf = synth.gen_device(p, dev)
-        s_prev = rec_size(rank * R - 1) if rank else 0
-        s_next = rec_size((rank + 1) * R) if rank < world - 1 else 0
-        own = gbuf.numel() - s_prev - s_next  # bytes of records [rank*R, (rank+1)*R)
         exchange = "nvlink peer memory (symmetric buffers, exb_peer_allgather_block + exb_peer_count_reduce)"
         try:
             if os.environ.get("EXB_EXCHANGE", "peer") != "peer":
@@ -294,15 +276,40 @@ def main():
         if int(okt.item()) == 0:  # all ranks take the same path
             grp = XD.TorchGroup(dev)
             exchange = "nccl all-gather (128 B per shard) + all-reduce (64 B)"
-        owns = grp.all_gather_rows([own])[:, 0]
-        off0 = int(owns[:rank].sum())  # file offset of record rank*R
-        lo = off0 + delta(rank)
-        hi = off0 + own + (delta(rank + 1) if rank < world - 1 else 0)
-        begin = XD.HALO if rank else 0
-        local0 = s_prev + delta(rank) - begin  # view: file byte lo sits at local offset `begin`
-        assert local0 % 16 == 0
-        buf = gbuf[local0:local0 + begin + (hi - lo)]
-        shard = XD.Shard(buf, lo, hi, begin, rank == world - 1)
+
+        def build_shard(R):
+            """This rank's byte range of ONE file of world x R records whose cuts fall INSIDE records."""
+            def rec_size(i):
+                q = synth.gen_params("illumina", 1, seed=SEED, first_record=i, len_min=READ_LEN, len_max=READ_LEN)
+                return synth.gen_size(q)
+
+            def delta(k):  # offset of shard k's first byte inside record k*R; local offset of that byte is a multiple of 16
+                if k == 0:
+                    return 0
+                s_prev = rec_size(k * R - 1)
+                return 96 + ((-(s_prev + 96)) % 16)
+
+            first = rank * R - (1 if rank else 0)
+            count = R + (1 if rank else 0) + (1 if rank < world - 1 else 0)
+            p = synth.gen_params("illumina", count, seed=SEED, first_record=first, len_min=READ_LEN, len_max=READ_LEN)
+            gbuf = synth.gen_device(p, dev)
+            s_prev = rec_size(rank * R - 1) if rank else 0
+            s_next = rec_size((rank + 1) * R) if rank < world - 1 else 0
+            own = gbuf.numel() - s_prev - s_next  # bytes of records [rank*R, (rank+1)*R)
+            owns = grp.all_gather_rows([own])[:, 0]
+            off0 = int(owns[:rank].sum())  # file offset of record rank*R
+            lo = off0 + delta(rank)
+            hi = off0 + own + (delta(rank + 1) if rank < world - 1 else 0)
+            begin = XD.HALO if rank else 0
+            local0 = s_prev + delta(rank) - begin  # view: file byte lo sits at local offset `begin`
+            assert local0 % 16 == 0
+            buf = gbuf[local0:local0 + begin + (hi - lo)]
+            return XD.Shard(buf, lo, hi, begin, rank == world - 1), gbuf, s_prev, own
+
+        R = args.reads
+        shard, gbuf, s_prev, own = build_shard(R)
+        buf = shard.buf
+        lo, hi = shard.lo, shard.hi
         n_bytes = hi - lo
         sharded = XD.ShardedFastqCount(shard, preds, grp)
         # cross-check: the same records counted shard-locally on whole-record ranges
@@ -493,11 +500,94 @@ def main():
         from tools import paths as P
         rep = P.Report(verbose=False)
         P.c2_paths(rep, buf, args.reads, iters=5, full=False)
-        del buf, cnt
+        buf = cnt = None
         torch.cuda.empty_cache()
         P.c3_paths(rep, dev, int(os.environ.get("EXB_BENCH_CONTIGS", "6000")), 500_000, iters=5)   # C3: 3 Gbp wrapped at 60
         P.c4_paths(rep, dev, int(os.environ.get("EXB_BENCH_ONT_READS", "200000")), iters=3)       # C4: 200 k ONT reads, ~12 GB
         path_rows = rep.rows
+
+    # ---- C5 (BASELINE configs[4]): ~100 GB of the same FASTQ as ONE file cut into byte ranges over the N GPUs (cuts inside
+    # records); SELECT COUNT(*), SUM(#GC), SUM(length(sequence)), AVG(gc_content(sequence)); device-resident, strong scaling
+    c5 = None
+    if not args.no_c5:
+        from exon_duckdb_b200 import dist as XD
+        # release everything C2 held on the device (closures above see the same cells)
+        buf = cnt = e2e_src = None
+        if world > 1:
+            gbuf = sharded = shard = whole = None
+        torch.cuda.empty_cache()
+        total_gb = float(os.environ.get("EXB_BENCH_C5_GB", "100"))
+        R5 = int(total_gb * 1e9 / (n_bytes / args.reads) / world)
+        if world == 1:
+            buf5 = synth.gen_device(synth.gen_params("illumina", R5, seed=SEED, len_min=READ_LEN, len_max=READ_LEN), dev)
+            shard5 = XD.Shard(buf5, 0, buf5.numel(), 0, True)
+            job = XD.ShardedFastqTotals(shard5, None, ranges=[[0, buf5.numel(), 0]], rec_cap=R5 + 4096, max_lines=4 * R5 + 4096)
+
+            def c5_step():
+                job.scan()
+                job.resolve_local(None, 0)
+                job.finish_local()
+            c5_total = job.agg
+        else:
+            shard5, gbuf5, s_prev5, own5 = build_shard(R5)
+            job = XD.ShardedFastqTotals(shard5, grp, rec_cap=R5 + 4096, max_lines=4 * R5 + 4096)
+            c5_step = job.step
+            c5_total = job.total
+        for _ in range(3):
+            c5_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        c5_steps = max(3, min(args.steps, 5))
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(c5_steps):
+            c5_step()
+        c1.record()
+        torch.cuda.synchronize()
+        t5 = torch.tensor([c0.elapsed_time(c1) / c5_steps], dtype=torch.float64, device=dev)
+        b5 = torch.tensor([shard5.hi - shard5.lo], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            dist.all_reduce(b5)
+        got5 = [int(x) for x in c5_total.cpu().tolist()]
+        if world == 1:
+            blk5 = XD._result_block(job.ws).cpu().tolist()
+            got5[6], got5[7] = blk5[0] & 3, int(blk5[2] != 0)
+        XD.check_count(torch.tensor(got5))
+        n5 = R5 * world
+        assert got5[0] == n5 and got5[1] == READ_LEN * n5, (got5, n5)
+        # cross-check of SUM(#GC): the scalar gc_content kernel's counts are not available per shard cut, so compare with an
+        # independent whole-record scan of this rank's own records (exb_fastq_scan + exb_fastq_filter), summed over ranks
+        own_view = buf5 if world == 1 else gbuf5[s_prev5:s_prev5 + own5]
+        if world > 1 and (s_prev5 % 16) != 0:
+            own_view = None  # misaligned view: skip the copy of tens of GB; ranks with an aligned view still check theirs
+        chk = torch.zeros(2, dtype=torch.int64, device=dev)
+        if own_view is not None:
+            s5 = D.fastq_scan(own_view, _lib.F_SEQ, rec_cap=R5 + 4096)
+            a5, _ = D.fastq_filter(s5, R5, [])
+            chk[0], chk[1] = a5[2], 1
+            del s5
+        if world > 1:
+            allchk = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allchk, chk)
+            allchk = allchk.view(world, 2).cpu().tolist()
+        else:
+            allchk = [chk.cpu().tolist()]
+        if all(c[1] for c in allchk):
+            assert sum(c[0] for c in allchk) == got5[2], (allchk, got5)
+        ms5 = t5.item()
+        peak5, _ = measured_peak()
+        c5 = {"workload": "C5: %.1f GB synthetic Illumina FASTQ, ONE file byte-range sharded over %d GPU(s), cuts inside records; "
+                          "SELECT COUNT(*), SUM(#GC), SUM(length(sequence)), AVG(gc_content(sequence))" % (int(b5.item()) / 1e9, world),
+              "total_bytes": int(b5.item()), "reads": n5, "ms_per_step": ms5, "value": int(b5.item()) / (ms5 * 1e-3) / 1e9, "unit": UNIT,
+              "scaling": "strong", "steps": c5_steps, "frac_of_hbm_peak": int(b5.item()) / (ms5 * 1e-3) / 1e9 / (peak5 * world),
+              "count": got5[0], "sum_len": got5[1], "sum_gc": got5[2], "avg_gc_content": got5[5] / 4294967296.0 / n5,
+              "sum_gc_cross_checked": bool(all(c[1] for c in allchk)),
+              "kernels": "exb_fastq_scan_begin (K1 + line offsets) -> block exchange -> exb_fastq_compose_prev -> exb_fastq_scan_resolve "
+                         "(EXB_F_SEQ | EXB_F_LOCAL_RECORDS) -> exb_fastq_seq_totals -> reduce"}
+        del job
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -532,6 +622,8 @@ def main():
             line["e2e_pinned_image"] = e2e_pinned
         if path_rows:
             line["paths"] = path_rows
+        if c5:
+            line["c5"] = c5
         if cpu:
             line["cpu_baseline"] = cpu
         if saved_stdout is not None:

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EXON_B200_LIB") or os.path.join(_HERE, "libexon_b200.so")  # override: debug builds only
 
 # flags / enums (mirror include/exon_b200.h)
-F_LINES, F_SEQ, F_QUAL = 1, 2, 4
+F_LINES, F_SEQ, F_QUAL, F_LOCAL_RECORDS = 1, 2, 4, 16
 P_MEAN_QUALITY, P_GC_CONTENT, P_SEQ_LEN, P_QUAL_LEN = 0, 1, 2, 3
 OPS = {">": 0, ">=": 1, "<": 2, "<=": 3, "=": 4, "==": 4, "!=": 5, "<>": 5}
 MAP_REVERSE_COMPLEMENT, MAP_COMPLEMENT, MAP_TRANSCRIBE, MAP_REVERSE_TRANSCRIBE = 0, 1, 2, 3
@@ -145,6 +145,8 @@ SIGNATURES = {
     "exb_fastq_scan": (_i32, [_vp, _i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_fastq_scan_filter": (_i32, [_vp, _i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i32, _vp, _i64, _vp]),
     "exb_fastq_scan_filter_begin": (_i32, [_vp, _i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i64, _vp]),
+    "exb_fastq_scan_begin": (_i32, [_vp, _i64, _i64, _i32, _vp, _i32, _vp, _i64, _vp]),
+    "exb_fastq_seq_totals": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_fastq_scan_resolve": (_i32, [_i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_fastq_scan_filter_resolve": (_i32, [_i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i32, _vp, _i64, _vp]),
     "exb_fastq_compose_prev": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
@@ -160,6 +162,8 @@ SIGNATURES = {
     "exb_exclusive_scan_u32_multi": (_i32, [_vp, _i64, _i32, _i64, _vp, _i64, _vp, _i64, _vp]),
     "exb_select_rows": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "exb_fastq_gather": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "exb_fastq_split_scratch_bytes": (_i64, [_i64]),
+    "exb_fastq_split": (_i32, [_vp, _i64, _i64, _vp, _i32, _i64, C.c_uint32, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64), _vp, _vp, _i32, _vp, _vp]),
     "exb_fastq_gather_map": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "exb_fasta_scan": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "exb_fasta_headers": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

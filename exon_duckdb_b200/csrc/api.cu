@@ -33,6 +33,10 @@ cudaError_t seq_map_launch(const uint8_t*, int64_t, int, uint8_t*, unsigned long
 cudaError_t fastq_final_state_launch(const FastqScanArgs&, cudaStream_t);
 cudaError_t translate_launch(const int64_t*, const uint8_t*, int64_t, int64_t, uint8_t*, long long*, cudaStream_t);
 cudaError_t quality_decode_launch(const uint8_t*, int64_t, int32_t*, cudaStream_t);
+int64_t fastq_split_scratch_bytes(int64_t);
+cudaError_t seq_totals_launch(const uint32_t*, const uint32_t*, int64_t, int64_t*, cudaStream_t);
+cudaError_t fastq_split_launch(const uint8_t*, int64_t, int64_t, const void*, bool, int64_t, uint32_t, int64_t*, uint8_t*, uint8_t* const*, const int64_t*, void*,
+                               const ScanResult*, int, unsigned long long*, cudaStream_t);
 
 static thread_local char g_err[512] = "";
 int set_err(int code, const char* fmt, ...) {
@@ -252,6 +256,7 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
     a.qual_len = d_qual_len;
     a.qsum = d_qsum;
     a.rec_cap = rec_cap;
+    a.local_records = (flags & EXB_F_LOCAL_RECORDS) ? 1 : 0;
     if (!resolve_only) {
         // K1: every byte once, no inter-tile dependency
         e = fastq_tile_launch(a, flags, st);
@@ -288,7 +293,7 @@ int64_t exb_fastq_workspace_bytes(int64_t n, int64_t max_lines) {
 int exb_fastq_scan(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, uint64_t max_lines,
                    int flags, void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len, uint32_t* d_gc,
                    uint32_t* d_qual_len, int32_t* d_qsum, int64_t rec_cap, void* d_workspace, int64_t workspace_bytes, void* stream) {
-    return fastq_scan_common("exb_fastq_scan", d_buf, begin, n, is_final, d_prev_workspace, max_lines, flags & 7, d_line_end, line_cap,
+    return fastq_scan_common("exb_fastq_scan", d_buf, begin, n, is_final, d_prev_workspace, max_lines, flags & (7 | EXB_F_LOCAL_RECORDS), d_line_end, line_cap,
                              wide_offsets, d_seq_len, d_gc, d_qual_len, d_qsum, rec_cap, nullptr, 0, nullptr, d_workspace, workspace_bytes,
                              (cudaStream_t)stream);
 }
@@ -326,10 +331,19 @@ int exb_fastq_scan_filter_begin(const void* d_buf, int64_t begin, int64_t n, int
                              false, true);
 }
 
+int exb_fastq_scan_begin(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, int flags, void* d_workspace,
+                         int64_t workspace_bytes, void* stream) {
+    // K1 writes nothing per record: the outputs are only validated by the resolve call that runs K2
+    static uint32_t dummy;
+    uint32_t* d = &dummy;  // non-null placeholder for the argument check; K1 never dereferences the output arrays
+    return fastq_scan_common("exb_fastq_scan_begin", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, flags & 7, (flags & EXB_F_LINES) ? d : nullptr, 0,
+                             1, d, d, d, reinterpret_cast<int32_t*>(d), 0, nullptr, 0, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream, false, true);
+}
+
 int exb_fastq_scan_resolve(int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, uint64_t max_lines, int flags,
                            void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len, uint32_t* d_gc, uint32_t* d_qual_len,
                            int32_t* d_qsum, int64_t rec_cap, void* d_workspace, int64_t workspace_bytes, void* stream) {
-    return fastq_scan_common("exb_fastq_scan_resolve", nullptr, begin, n, is_final, d_prev_workspace, max_lines, flags & 7, d_line_end, line_cap,
+    return fastq_scan_common("exb_fastq_scan_resolve", nullptr, begin, n, is_final, d_prev_workspace, max_lines, flags & (7 | EXB_F_LOCAL_RECORDS), d_line_end, line_cap,
                              wide_offsets, d_seq_len, d_gc, d_qual_len, d_qsum, rec_cap, nullptr, 0, nullptr, d_workspace, workspace_bytes,
                              (cudaStream_t)stream, true);
 }
@@ -449,6 +463,27 @@ int exb_fastq_gather(const void* d_buf, int64_t begin, int64_t n, const void* d_
     return 0;
 }
 
+int64_t exb_fastq_split_scratch_bytes(int64_t n_rows) { return fastq_split_scratch_bytes(n_rows); }
+int exb_fastq_split(const void* d_buf, int64_t begin, int64_t n, const void* d_line_end, int wide_offsets, int64_t n_rows, uint32_t column_mask,
+                    int64_t* d_off, uint8_t* d_desc_valid, uint8_t* const* d_out, const int64_t* cap, void* d_scratch, const void* d_scan_workspace,
+                    int map_mode, uint64_t* d_bad, void* stream) {
+    if (!d_buf || !d_line_end || !d_off || !d_desc_valid || !d_out || !cap || !d_scratch || n_rows < 0)
+        return set_err(EXB_ERR_ARG, "exb_fastq_split: null argument");
+    uint8_t* out[4];
+    int64_t caps[4];
+    for (int c = 0; c < 4; c++) {
+        out[c] = d_out[c];
+        caps[c] = cap[c];
+        if (((column_mask >> c) & 1u) && (!out[c] || ((uintptr_t)out[c] & 15))) return set_err(EXB_ERR_ARG, "exb_fastq_split: column %d needs a 16-byte aligned output", c);
+    }
+    if (map_mode >= 0 && (!d_bad || map_mode > EXB_MAP_REVERSE_TRANSCRIBE)) return set_err(EXB_ERR_ARG, "exb_fastq_split: bad map arguments");
+    cudaError_t e = fastq_split_launch(reinterpret_cast<const uint8_t*>(d_buf), begin, n, d_line_end, wide_offsets != 0, n_rows, column_mask, d_off,
+                                       d_desc_valid, out, caps, d_scratch, reinterpret_cast<const ScanResult*>(d_scan_workspace), map_mode,
+                                       map_mode >= 0 ? reinterpret_cast<unsigned long long*>(d_bad) : nullptr, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_split launch");
+    return 0;
+}
+
 int exb_fastq_gather_map(const void* d_buf, int64_t begin, int64_t n, const void* d_line_end, int wide_offsets, const int64_t* d_sel,
                          int64_t n_rows, int col, const uint32_t* d_lens, const int64_t* d_off, int mode, uint8_t* d_out, uint64_t* d_bad,
                          void* stream) {
@@ -531,6 +566,13 @@ int exb_gc_from_counts(const uint32_t* d_seq_len, const uint32_t* d_gc, int64_t 
     if (e != cudaSuccess) return cuda_fail(e, "gc_from_counts launch");
     return 0;
 }
+int exb_fastq_seq_totals(const uint32_t* d_seq_len, const uint32_t* d_gc, int64_t n_records, int64_t* d_totals, void* stream) {
+    if (!d_seq_len || !d_gc || !d_totals || n_records < 0) return set_err(EXB_ERR_ARG, "exb_fastq_seq_totals: bad arguments");
+    cudaError_t e = seq_totals_launch(d_seq_len, d_gc, n_records, d_totals, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "seq_totals launch");
+    return 0;
+}
+
 int exb_gc_content(const int64_t* d_off, const uint8_t* d_data, int64_t n_rows, float* d_out, void* stream) {
     cudaError_t e = gc_content_launch(d_off, d_data, n_rows, d_out, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "gc_content launch");

@@ -70,6 +70,7 @@ struct FastqScanArgs {
     uint32_t *seq_len, *gc, *qual_len;
     int32_t* qsum;
     int64_t rec_cap;
+    int local_records;          // EXB_F_LOCAL_RECORDS: record indices count from the first record the range touches
 };
 
 cudaError_t fastq_tile_launch(const FastqScanArgs& a, int flags, cudaStream_t st);                     // K1

@@ -652,6 +652,7 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const FastqScanArgs a) 
     const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const bool overflowed = a.result->overflow != 0;  // K1 ran out of record space: the caller retries with more
+    const uint64_t rec0 = a.local_records ? (init >> 2) : 0ull;  // byte-range shards index their records from the first one they touch
 
     // A warp takes 32 consecutive tiles at a time: lane l fetches tile (batch + l)'s directory words in ONE round of
     // coalesced loads, then the tiles are processed one after the other with the words broadcast by shuffles.  (One tile
@@ -738,7 +739,7 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const FastqScanArgs a) 
                     len -= cr;
                     n_crlf += cr;
                     const int ph = (int)(g & 3);
-                    const uint64_t rix = g >> 2;
+                    const uint64_t rix = (g >> 2) - rec0;
                     if (kLines) {
                         if (g < (uint64_t)a.line_cap) reinterpret_cast<OffT*>(a.line_end)[g] = (OffT)e;
                         else a.result->overflow = 1;

@@ -57,6 +57,7 @@ cudaError_t gc_sel_launch(const uint32_t*, const uint32_t*, const int64_t*, cons
 cudaError_t mean_quality_launch(const uint32_t*, const int32_t*, const int64_t*, int64_t, double*, uint8_t*, cudaStream_t);
 cudaError_t lens_i64_launch(const uint32_t*, int64_t, int64_t*, cudaStream_t);
 cudaError_t fastq_chunk_info_launch(const void*, const uint32_t*, int64_t*, cudaStream_t);
+cudaError_t copy_words_launch(void*, const void*, int, int64_t, cudaStream_t);
 cudaError_t gather_ranges_map_launch(const uint8_t*, const int64_t*, const int64_t*, int64_t, int64_t, uint8_t*, int, unsigned long long*, cudaStream_t);
 }  // namespace exb
 using namespace exb;
@@ -573,9 +574,9 @@ struct IoPool {
     int nthreads = 1;
     IoPool() {
         int hw = (int)std::thread::hardware_concurrency();
-        // half the cores (at most 12): 8 threads already copy at 61 GB/s on the 16-core box, above the PCIe rate, and the
-        // device thread and the host's consumers need cores to keep the GPU fed
-        nthreads = hw > 0 ? std::max(2, std::min(hw / 2, 12)) : 4;
+        // three quarters of the cores (at most 12): 8 threads already copy faster than the PCIe link takes the bytes on the
+        // 16-core box, 12 are steadier, and the device thread and the host's consumers need cores to keep the GPU fed
+        nthreads = hw > 0 ? std::max(2, std::min(hw * 3 / 4, 12)) : 4;
         if (const char* e = getenv("EXON_B200_IO_THREADS"))
             if (atoi(e) > 0) nthreads = std::min(atoi(e), 64);
         for (int i = 0; i < nthreads - 1; i++) std::thread([this] { work(); }).detach();  // the caller is the last worker
@@ -910,7 +911,10 @@ struct Reader {
     };
     std::deque<Pending> pend;   // at most two: chunk k's D2H overlaps the kernels of chunk k+1
     std::shared_ptr<PinnedPool> pool = PinnedPool::shared();
-    HBuf h_small;  // a few words for totals / flags read back between launches
+    // a few words read back between launches (scan result, totals, counts): mapped pinned memory written by a kernel
+    void* h_small = nullptr;   // host address
+    void* d_small = nullptr;   // the same memory as the device sees it
+    cudaEvent_t ev_small = nullptr;
     // rows ready to be handed out (caller threads, under call_mu)
     std::mutex call_mu;
     std::shared_ptr<ChunkResult> cur;
@@ -1001,6 +1005,9 @@ struct Reader {
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&outs[i].ev_d2h, cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&outs[i].ev_off, cudaEventDisableTiming);
         }
+        if (e == cudaSuccess) e = cudaHostAlloc(&h_small, 4096, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer(&d_small, h_small, 0);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_small, cudaEventDisableTiming);
         if (const char* t = getenv("EXON_B200_TRACE")) trace = atoi(t);
         if (trace >= 2)
             for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&tev[i]);
@@ -1009,6 +1016,13 @@ struct Reader {
     void mark(int i) {
         if (trace >= 2) cudaEventRecord(tev[i], st);
     }
+    // queue the read-back of `count` 8-byte words (d_src[i * stride]) into slot `slot` of the mapped buffer ...
+    bool queue_small(int slot, const void* d_src, int count, int64_t stride = 1) {
+        return cu(copy_words_launch(reinterpret_cast<uint8_t*>(d_small) + 8 * slot, d_src, count, stride, st), "copy_words");
+    }
+    // ... and wait for everything queued on the compute stream so far; the words are then readable at small(slot)
+    bool wait_small() { return cu(cudaEventRecord(ev_small, st), "record") && cu(cudaEventSynchronize(ev_small), "sync"); }
+    const int64_t* small(int slot) const { return reinterpret_cast<const int64_t*>(h_small) + slot; }
     void free_device() {  // device thread, at its end: buffers are freed on the device that owns them
         const double tf = now();
         for (DBuf* b : {&d_inb[0], &d_inb[1], &d_stage, &d_ws, &d_ws2, &d_line, &d_arr[0], &d_arr[1], &d_arr[2], &d_arr[3], &d_lens, &d_starts,
@@ -1027,6 +1041,9 @@ struct Reader {
         }
         if (ev_staged) cudaEventDestroy(ev_staged);
         if (ev_stage_free) cudaEventDestroy(ev_stage_free);
+        if (ev_small) cudaEventDestroy(ev_small);
+        if (h_small) cudaFreeHost(h_small);
+        h_small = nullptr;
         if (st) cudaStreamDestroy(st);
         if (sc) cudaStreamDestroy(sc);
         if (sd) cudaStreamDestroy(sd);
@@ -1376,12 +1393,12 @@ struct Reader {
         res->pool = pool;
         res->rows = n;
         const int64_t ws_bytes = exb_scan_workspace_bytes(4 * n * ncols + 16);
-        if (!d_ws2.need(ws_bytes) || !d_off.need((int64_t)ncols * (n + 1) * 8) || !h_small.need(256)) return fail("out of memory");
+        if (!d_ws2.need(ws_bytes) || !d_off.need((int64_t)ncols * (n + 1) * 8)) return fail("out of memory");
         int64_t* d_offs = d_off.as<int64_t>();
         if (!rc(exb_exclusive_scan_u32_multi(d_ln, n, ncols, n, d_offs, n + 1, d_ws2.p, d_ws2.cap, st))) return false;
-        int64_t* totals = h_small.as<int64_t>();
-        if (!cu(cudaMemcpy2DAsync(totals, 8, d_offs + n, (size_t)(n + 1) * 8, 8, (size_t)ncols, cudaMemcpyDeviceToHost, st), "D2H totals")) return false;
-        if (!cu(cudaStreamSynchronize(st), "sync")) return false;
+        if (!queue_small(32, d_offs + n, ncols, n + 1) || !wait_small()) return false;
+        int64_t totals[4] = {0, 0, 0, 0};
+        for (int c = 0; c < ncols; c++) totals[c] = small(32)[c];
         // ---- layout of the two result buffers
         auto up = [](int64_t x, int64_t a) { return (x + a - 1) & ~(a - 1); };
         const int64_t n_batches = (n + batch_size - 1) / batch_size;
@@ -1546,9 +1563,8 @@ struct Reader {
         const int64_t ws_bytes = exb_scan_workspace_bytes(4 * n + 16);
         if (!d_ws2.need(ws_bytes) || !d_off.need((n + 1) * 8) || !d_sel.need(n * 8)) return fail("out of device memory");
         if (!rc(exb_select_rows(d_pass.as<uint8_t>(), n, d_off.as<int64_t>(), d_sel.as<int64_t>(), d_ws2.p, d_ws2.cap, st))) return false;
-        int64_t cnt = 0;
-        if (!cu(cudaMemcpyAsync(&cnt, d_off.as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, st), "D2H count")) return false;
-        if (!cu(cudaStreamSynchronize(st), "sync")) return false;
+        if (!queue_small(40, d_off.as<int64_t>() + n, 1) || !wait_small()) return false;
+        const int64_t cnt = small(40)[0];
         o_n = cnt;
         o_sel = d_sel.as<int64_t>();
         if (count_only.load()) return true;  // COUNT(*): the number of passing rows is all that is needed
@@ -1591,8 +1607,11 @@ struct Reader {
                     return false;
                 // where the last complete record ends: fetched together with the result block (one sync)
                 if (!cu(fastq_chunk_info_launch(d_ws.p, d_line.as<uint32_t>(), d_info.as<int64_t>(), st), "chunk_info")) return false;
-                if (!cu(cudaMemcpyAsync(info, d_info.p, 16, cudaMemcpyDeviceToHost, st), "D2H")) return false;
-                if (!rc(exb_scan_result_fetch(d_ws.p, &res, st))) return false;
+                if (!queue_small(0, d_ws.p, (int)(sizeof(exb_scan_result) / 8)) || !queue_small(24, d_info.p, 2) || !wait_small()) return false;
+                memcpy(&res, small(0), sizeof(res));
+                res.err_pos = ~res.err_pos;  // the device keeps it inverted (see ScanResult)
+                info[0] = small(24)[0];
+                info[1] = small(24)[1];
                 if (!res.overflow) break;
                 if (attempt) return fail("internal: record capacity");
                 rec_cap = n / 4 + 16;
@@ -1648,7 +1667,9 @@ struct Reader {
                                    d_seq_off.as<int64_t>(), d_gc_prefix.as<int64_t>(), rec_cap, want_seq ? d_seq.as<uint8_t>() : nullptr,
                                    want_seq ? n + 64 : 0, d_ws.p, d_ws.cap, st)))
                 return false;
-            if (!rc(exb_scan_result_fetch(d_ws.p, &res, st))) return false;
+            if (!queue_small(0, d_ws.p, (int)(sizeof(exb_scan_result) / 8)) || !wait_small()) return false;
+            memcpy(&res, small(0), sizeof(res));
+            res.err_pos = ~res.err_pos;  // the device keeps it inverted (see ScanResult)
             if (!res.overflow) break;
             if (attempt) return fail("internal: record capacity");
             rec_cap = n / 2 + 16;
@@ -1664,10 +1685,8 @@ struct Reader {
         else {
             if (R <= 1) { grew = true; consumed = 0; return true; }
             R -= 1;  // the last record may continue in the next chunk
-            int64_t hs = 0;
-            if (!cu(cudaMemcpyAsync(&hs, d_hdr_start.as<int64_t>() + R, 8, cudaMemcpyDeviceToHost, st), "D2H")) return false;
-            if (!cu(cudaStreamSynchronize(st), "sync")) return false;
-            consumed = hs;
+            if (!queue_small(24, d_hdr_start.as<int64_t>() + R, 1) || !wait_small()) return false;
+            consumed = small(24)[0];
         }
         t0 = now();
         if (!d_lens.need(std::max<int64_t>(R, 1) * 12) || !d_starts.need(std::max<int64_t>(R, 1) * 24) || !d_valid.need(std::max<int64_t>(R, 1)) ||
@@ -1679,9 +1698,8 @@ struct Reader {
         if (!cu(fasta_seq_ranges_launch(d_seq_off.as<int64_t>(), nullptr, R, d_starts.as<int64_t>() + 2 * R, d_lens.as<uint32_t>() + 2 * R, st),
                 "fasta_seq_ranges"))
             return false;
-        uint64_t bad = 0;
-        if (!cu(cudaMemcpyAsync(&bad, d_err.p, 8, cudaMemcpyDeviceToHost, st), "D2H")) return false;
-        if (!cu(cudaStreamSynchronize(st), "sync")) return false;
+        if (!queue_small(26, d_err.p, 1) || !wait_small()) return false;
+        const uint64_t bad = (uint64_t)small(26)[0];
         if (bad != ~0ull) return fail("FASTA definition without a name at byte " + std::to_string(cur_file_pos + (int64_t)bad) + " of " + fname);
         const uint8_t* bufs[3] = {d_cur, d_cur, d_seq.as<uint8_t>()};
         const int64_t* o_st; const uint32_t* o_ln; const uint8_t* o_val; const int64_t* o_sel; int64_t o_n;

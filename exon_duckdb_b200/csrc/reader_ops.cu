@@ -159,4 +159,45 @@ cudaError_t fastq_chunk_info_launch(const void* ws, const uint32_t* line_end, in
     return cudaGetLastError();
 }
 
+// COUNT / SUM / AVG over the per-record arrays (BASELINE C5): sum len, sum gc, sum round(gc_content * 2^32)
+__global__ void __launch_bounds__(256) seq_totals_kernel(const uint32_t* __restrict__ seq_len, const uint32_t* __restrict__ gc, int64_t n,
+                                                         unsigned long long* __restrict__ totals) {
+    unsigned long long sl = 0, sg = 0, sf = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t l = seq_len[i], g = gc[i];
+        sl += l;
+        sg += g;
+        if (l) sf += (unsigned long long)__double2ll_rn((double)__fdiv_rn(__uint2float_rn(g), __uint2float_rn(l)) * 4294967296.0);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sl += __shfl_xor_sync(0xffffffffu, sl, d);
+        sg += __shfl_xor_sync(0xffffffffu, sg, d);
+        sf += __shfl_xor_sync(0xffffffffu, sf, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (sl) atomicAdd(totals + 1, sl);
+        if (sg) atomicAdd(totals + 2, sg);
+        if (sf) atomicAdd(totals + 5, sf);
+    }
+}
+cudaError_t seq_totals_launch(const uint32_t* seq_len, const uint32_t* gc, int64_t n, int64_t* totals, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    seq_totals_kernel<<<grid_for(n, 1024), 256, 0, st>>>(seq_len, gc, n, reinterpret_cast<unsigned long long*>(totals));
+    return cudaGetLastError();
+}
+
+// Small read-backs (scan result block, column totals, counts) go to MAPPED pinned host memory through a kernel instead of
+// cudaMemcpyAsync: a 16-byte device-to-host copy queues behind the 64 MiB result copy of the previous chunk in the same
+// copy engine and waited ~1.7 ms per chunk for it (profiles/round2_reader_trace.txt).  dst[i] = src[i * stride], 8-byte words.
+__global__ void copy_words_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, int count, long long stride) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[(long long)i * stride];
+    __threadfence_system();
+}
+cudaError_t copy_words_launch(void* dst_mapped, const void* src, int count, int64_t stride, cudaStream_t st) {
+    copy_words_kernel<<<1, 64, 0, st>>>(reinterpret_cast<unsigned long long*>(dst_mapped), reinterpret_cast<const unsigned long long*>(src), count,
+                                         (long long)stride);
+    return cudaGetLastError();
+}
+
 }  // namespace exb

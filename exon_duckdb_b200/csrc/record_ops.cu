@@ -578,6 +578,403 @@ static cudaError_t gather_span_launch(const uint8_t* buf, SrcFn fn, const int64_
     return cudaGetLastError();
 }
 
+// ================================================================= fused column split (FASTQ, all rows)
+// ONE launch for what used to be the field split, the offset scan and four column gathers: a block takes 256
+// consecutive records (ticket order), works out their field extents, scans the four field lengths inside the block,
+// publishes the block totals, obtains its output offsets with a decoupled look-back over the earlier blocks, writes the
+// Arrow offsets of its rows and then copies all four columns of its rows.  The four gathers of a block read one
+// contiguous ~90 KB window of the input while it is hot in L1 / L2, so every input DRAM atom is fetched once per pass
+// (the per-column gathers fetched the file about three times: profiles/r02r_kernel_traffic.txt), and the header bytes
+// the field split reads are the ones the name / description copies need a moment later.
+// Output layout = a6 / a8 of SURVEY 8: per column int64 offsets[n_rows + 1] (exclusive prefix of the lengths) + bytes.
+constexpr int SP_ROWS = 128, SP_THREADS = 256;
+constexpr int SP_WIN = 32 << 10;  // bytes of input a block stages in shared memory
+struct alignas(128) SplitDesc {  // one per block of rows: its totals, then its inclusive prefix
+    unsigned long long agg[4];
+    unsigned long long incl[4];
+    uint32_t status;  // 0 = nothing yet, 1 = agg valid, 2 = incl valid
+    uint32_t pad[15];
+};
+static_assert(sizeof(SplitDesc) == 128, "SplitDesc layout");
+
+struct SplitArgs {
+    int64_t n_rows;
+    uint32_t mask;            // bit c: column c is copied (its offsets are always produced)
+    int64_t* off;             // [4][n_rows + 1]
+    uint8_t* desc_valid;      // [n_rows]
+    uint8_t* out[4];          // 16-byte aligned
+    int64_t cap[4];
+    SplitDesc* desc;          // [ceil(n_rows / SP_ROWS)] zeroed
+    unsigned int* ticket;     // zeroed
+    unsigned int* overflow;   // set to 1 if a column does not fit its capacity
+    const ScanResult* scan;   // optional: CR LF knowledge of the scan (see fastq_fields_kernel)
+    int map_mode;             // kMap: EXB_MAP_* applied to column 2 (sequence)
+    int rows_per_block;       // <= SP_ROWS: long records get fewer rows per block so that the grid stays full
+    unsigned long long* bad;  // kMap: min over invalid bytes of (output position << 8 | byte)
+};
+
+template <typename OffT, bool kMap>
+__global__ void __launch_bounds__(SP_THREADS, 5) fastq_split_kernel(FqLines<OffT> L, const SplitArgs a) {
+    __shared__ int64_t s_start[4][SP_ROWS];       // source offset of each field
+    __shared__ int64_t s_loc[4][SP_ROWS + 1];     // block-local exclusive offsets, closed with the block totals
+    __shared__ unsigned long long s_warp[4][SP_THREADS / 32];
+    __shared__ unsigned long long s_wmax[4][SP_THREADS / 32];
+    __shared__ unsigned long long s_base[4];
+    __shared__ unsigned long long s_maxlen[4];   // longest field of the block, per column
+    __shared__ uint4 s_below[17];                // s_below[k]: 0xFF in the first k bytes of a 16-byte chunk
+    __shared__ unsigned int s_blk;
+    __shared__ int64_t s_w[2];                   // the block's input window [w0, w1)
+    __shared__ __align__(16) uint8_t s_win[SP_WIN + 64];
+    __shared__ uint8_t s_lut[kMap ? 256 : 1];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned long long bad = ~0ull;
+    if (kMap) {
+        s_lut[t] = 0;
+        __syncthreads();
+        if (t == 0) fill_map_lut_fwd(s_lut, a.map_mode);
+        __syncthreads();
+    }
+    if (t < 17) s_below[t] = make_uint4(bytes_below32(t), bytes_below32(t - 4), bytes_below32(t - 8), bytes_below32(t - 12));
+    L.probe_cr = !a.scan || a.scan->crlf_lines != 0;
+    const bool want_header = (a.mask & 3u) != 0;
+    const uint8_t* __restrict__ buf = L.buf;
+    const int RPB = a.rows_per_block;
+    const int64_t n_blocks = (a.n_rows + RPB - 1) / RPB;
+    for (;;) {
+        __syncthreads();  // the previous iteration's readers of the shared arrays are done
+        if (t == 0) s_blk = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const int64_t blk = s_blk;
+        if (blk >= n_blocks) break;
+        const int64_t r = blk * RPB + t;
+        const int rows_here = (int)((a.n_rows - blk * RPB) < RPB ? (a.n_rows - blk * RPB) : RPB);
+        const bool active = t < rows_here;
+        // ---- the block's input window: the bytes of its records are contiguous in the file.  When they fit, they are staged
+        // in shared memory with one round of coalesced 16-byte asynchronous copies (every thread has several in flight) and
+        // everything below -- header search, CR probes, the copies of all four columns -- reads them from there: the
+        // unaligned source reads of the gathers then cost a shared-memory access instead of a global-memory latency
+        // (a version that read the input straight from global memory was latency bound at 48 % issue utilisation and
+        // 34 % of DRAM bandwidth: profiles/round2_split_v2_ncu.txt).  Long records (ONT) keep the global path.
+        if (t == 0) s_w[0] = L.start(4 * (blk * RPB));
+        if (t == 32) s_w[1] = (int64_t)L.line_end[4 * (blk * RPB + rows_here) - 1] + 1;
+        __syncthreads();
+        const int64_t w0a = s_w[0] & ~(int64_t)15, w1 = s_w[1] > L.n ? L.n : s_w[1];
+        const bool use_win = w1 - w0a <= SP_WIN;
+        if (use_win) {
+            const int chunks = (int)((w1 - w0a + 15 + 32) >> 4);  // 32 bytes of look-ahead for the 16-byte reads at a row's end
+            for (int k = t; k < chunks; k += SP_THREADS) cp_async16(s_win + 16 * k, buf + w0a + 16 * (int64_t)k, 16);
+            cp_async_commit();
+        }
+        // (the input carries 64 bytes of slack behind n, so the look-ahead never leaves the allocation)
+        const uint8_t* __restrict__ rd = use_win ? (const uint8_t*)s_win - w0a : buf;  // rd[file offset] = that byte
+        const int64_t lo_guard = use_win ? w0a + 4 : 4;  // an unaligned 16-byte read must not start below this offset
+        // ---- A. field extents of this thread's record
+        unsigned long long len[4] = {0, 0, 0, 0};
+        bool valid_desc = false;
+        int64_t le[5] = {0, 0, 0, 0, 0};
+        if (active) {
+            const int64_t g = 4 * r;
+            le[0] = g == 0 ? L.begin - 1 : (int64_t)L.line_end[g - 1];
+#pragma unroll
+            for (int k = 0; k < 4; k++) le[k + 1] = (int64_t)L.line_end[g + k];
+        }
+        if (use_win) {
+            cp_async_wait<0>();
+            __syncthreads();
+        }
+        if (active) {
+            // start of line k = le[k] + 1; its end with a trailing CR removed (e == n is the virtual terminator: no CR)
+            auto line_end_of = [&](int k) {
+                int64_t e = le[k + 1];
+                const int64_t sl = le[k] + 1;
+                if (L.probe_cr && e > sl && e < L.n && rd[e - 1] == '\r') e--;
+                return e;
+            };
+            const int64_t s0 = le[0] + 1, e0 = line_end_of(0);
+            const int64_t hs = s0 + 1;  // skip '@'
+            int64_t sp = e0;
+            if (want_header) sp = first_space(rd, hs, e0);  // first SPACE splits name / description
+            const int64_t s1 = le[1] + 1, e1 = line_end_of(1);
+            const int64_t s3 = le[3] + 1, e3 = line_end_of(3);
+            len[0] = (unsigned long long)(sp - hs);
+            len[1] = sp < e0 ? (unsigned long long)(e0 - sp - 1) : 0ull;
+            len[2] = (unsigned long long)(e1 - s1);
+            len[3] = (unsigned long long)(e3 - s3);
+            valid_desc = len[1] > 0;  // exon's builder maps an empty description to NULL
+            s_start[0][t] = hs;
+            s_start[1][t] = sp < e0 ? sp + 1 : e0;
+            s_start[2][t] = s1;
+            s_start[3][t] = s3;
+        }
+        // ---- block-wide exclusive scan of the four lengths
+        unsigned long long incl[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            incl[c] = warp_incl_scan_u64(len[c]);
+            if (lane == 31) s_warp[c][warp] = incl[c];
+            unsigned long long mx = len[c];
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, mx, dd);
+                mx = o > mx ? o : mx;
+            }
+            if (lane == 0) s_wmax[c][warp] = mx;
+        }
+        __syncthreads();
+        unsigned long long tot[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            unsigned long long before = 0, all = 0;
+#pragma unroll
+            for (int w = 0; w < SP_THREADS / 32; w++) {
+                const unsigned long long v = s_warp[c][w];
+                before += w < warp ? v : 0ull;
+                all += v;
+            }
+            tot[c] = all;
+            s_loc[c][t] = (int64_t)(before + incl[c] - len[c]);
+            if (t == 0) {
+                s_loc[c][SP_ROWS] = (int64_t)all;
+                unsigned long long mx = 0;
+#pragma unroll
+                for (int w = 0; w < SP_THREADS / 32; w++) mx = s_wmax[c][w] > mx ? s_wmax[c][w] : mx;
+                s_maxlen[c] = mx;
+            }
+        }
+        // ---- publish the totals, look back for the block's base (warp 0)
+        if (warp == 0) {
+            SplitDesc* d = a.desc + blk;
+            if (lane < 4) d->agg[lane] = tot[lane];
+            if (blk == 0 && lane < 4) d->incl[lane] = tot[lane];
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_u32(&d->status, blk == 0 ? 2u : 1u);
+            unsigned long long ex[4] = {0, 0, 0, 0};
+            if (blk > 0) {
+                int64_t idx = blk - 1;
+                for (;;) {
+                    const int64_t p = idx - lane;
+                    uint32_t st = 2u;
+                    if (p >= 0) {
+                        st = ld_acquire_u32(&a.desc[p].status);
+                        while (st == 0u) st = ld_acquire_u32(&a.desc[p].status);  // an earlier ticket: it is running and will publish
+                    }
+                    const uint32_t has_incl = __ballot_sync(0xffffffffu, st == 2u);
+                    const int first = has_incl ? __ffs((int)has_incl) - 1 : 32;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        unsigned long long v = 0;
+                        if (p >= 0 && lane <= first) v = lane < first ? __ldcg(&a.desc[p].agg[c]) : __ldcg(&a.desc[p].incl[c]);  // written by another SM: L2
+#pragma unroll
+                        for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_xor_sync(0xffffffffu, v, dd);
+                        ex[c] += v;
+                    }
+                    if (has_incl) break;
+                    idx -= 32;
+                }
+                if (lane < 4) d->incl[lane] = ex[lane] + tot[lane];
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) st_release_u32(&d->status, 2u);
+            }
+            if (lane < 4) s_base[lane] = ex[lane];
+        }
+        __syncthreads();
+        // ---- B. Arrow offsets and validity of the block's rows
+        if (active) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int64_t* o = a.off + (int64_t)c * (a.n_rows + 1);
+                o[r] = (int64_t)s_base[c] + s_loc[c][t];
+                if (r == a.n_rows - 1) o[a.n_rows] = (int64_t)s_base[c] + s_loc[c][t] + (int64_t)len[c];
+            }
+            a.desc_valid[r] = valid_desc ? 1 : 0;
+        }
+        // ---- C. the four columns of the block's rows.
+        // Columns of long rows (sequence, quality_scores; ONT reads) are copied ROW-centric: a group of lanes owns a row,
+        // each lane moves whole destination-aligned 16-byte chunks of it (one unaligned 16-byte load, one aligned store) and
+        // then the <= 30 ragged bytes at the row's two ends one by one -- ~20 warp instructions per 150-byte row.
+        // Columns of short rows (name, description) are copied CHUNK-centric: 16-byte destination-aligned chunks assembled
+        // from the pieces of the rows that meet in them (see gather_span_kernel); the ragged bytes at the two ends of the
+        // block's range are written one by one (the neighbouring blocks write the rest of those chunks).
+        // (A chunk-centric copy of all four columns executed 250 thread instructions per chunk, 1.0 G warp instructions for
+        // a 1.4 GB file, and was issue bound at 1.5 ms: profiles/round2_split_v1_ncu.txt.)
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            if (!((a.mask >> c) & 1u)) continue;
+            const int64_t B0 = (int64_t)s_base[c], B1 = B0 + s_loc[c][SP_ROWS];
+            if (B1 > a.cap[c]) {
+                if (t == 0) *a.overflow = 1u;
+                continue;
+            }
+            if (B1 == B0) continue;
+            uint8_t* __restrict__ out = a.out[c];
+            const int64_t* __restrict__ loc = s_loc[c];
+            const int64_t* __restrict__ src0 = s_start[c];
+            const bool map = kMap && c == 2;
+            auto map1 = [&](uint32_t ch, int64_t pos) -> uint32_t {
+                const uint32_t m = s_lut[ch];
+                if (m == 0) {
+                    const unsigned long long w = ((unsigned long long)pos << 8) | ch;
+                    bad = w < bad ? w : bad;
+                }
+                return m;
+            };
+            auto map4 = [&](uint32_t x, int64_t pos) -> uint32_t {
+                return map1(x & 0xFF, pos) | (map1((x >> 8) & 0xFF, pos + 1) << 8) | (map1((x >> 16) & 0xFF, pos + 2) << 16) | (map1(x >> 24, pos + 3) << 24);
+            };
+            const int64_t col_bytes = B1 - B0;
+            const int max_len = (int)(s_maxlen[c] > 0x7FFFFFFFull ? 0x7FFFFFFFull : s_maxlen[c]);
+            if (col_bytes >= 48 * (int64_t)rows_here) {
+                // ---- row-centric
+                const int per_row = (max_len >> 4) + 1;                       // lanes a row can keep busy with whole chunks
+                const int rpi = per_row >= 32 ? 1 : (32 / per_row > 8 ? 8 : 32 / per_row);  // rows per warp iteration
+                const int slot = 32 / rpi;
+                const int g = lane / slot, k = lane - g * slot;
+                for (int base = warp * rpi; base < rows_here; base += (SP_THREADS / 32) * rpi) {
+                    const int i = base + g;
+                    if (g >= rpi || i >= rows_here) continue;
+                    const int64_t D0 = B0 + loc[i], D1 = B0 + loc[i + 1];
+                    const int64_t S0 = src0[i] - D0;  // source = S0 + destination
+                    int64_t a0 = (D0 + 15) & ~(int64_t)15, a1 = D1 & ~(int64_t)15;
+                    if (a0 > a1) a0 = a1 = D1;        // the row holds no whole chunk: all of it is "head"
+                    if (S0 + a0 < lo_guard) a0 = a1 = D1;  // an unaligned load would start in front of the buffer / window: bytes
+                    const int64_t n_ch = (a1 - a0) >> 4;
+                    for (int64_t kk = k; kk < n_ch; kk += slot) {
+                        const int64_t d = a0 + 16 * kk;
+                        uint4 v = load16_unaligned(rd + S0 + d);
+                        if (map) v.x = map4(v.x, d), v.y = map4(v.y, d + 4), v.z = map4(v.z, d + 8), v.w = map4(v.w, d + 12);
+                        *reinterpret_cast<uint4*>(out + d) = v;
+                    }
+                    const int head_n = (int)(a0 - D0), rag = head_n + (int)(D1 - a1);
+                    for (int bb = k; bb < rag; bb += slot) {
+                        const int64_t d = bb < head_n ? D0 + bb : a1 + (bb - head_n);
+                        const uint8_t ch = rd[S0 + d];
+                        out[d] = map ? (uint8_t)map1(ch, d) : ch;
+                    }
+                }
+                continue;
+            }
+            // ---- chunk-centric
+            // block-local row of a block-local position q: last i < rows_here with loc[i] <= q.  Rows of a column are about
+            // the same length, so the proportional guess is a step or two away.
+            const float inv = (float)rows_here / (float)col_bytes;
+            auto row_of = [&](int64_t q) {
+                int i = (int)((float)q * inv);
+                i = i < rows_here - 1 ? i : rows_here - 1;
+                while (loc[i] > q) i--;
+                while (i + 1 < rows_here && loc[i + 1] <= q) i++;
+                return i;
+            };
+            const int64_t A0 = (B0 + 15) & ~(int64_t)15, A1 = B1 & ~(int64_t)15;  // whole chunks: [A0, A1)
+            auto bytes = [&](int64_t from, int64_t to) {  // ragged ends, at most 15 bytes each
+                for (int64_t q = from + t; q < to; q += SP_THREADS) {
+                    const int i = row_of(q - B0);
+                    const uint8_t b = rd[src0[i] + (q - B0 - loc[i])];
+                    out[q] = map ? (uint8_t)map1(b, q) : b;
+                }
+            };
+            if (A0 >= A1) {  // the block's range does not hold a whole chunk
+                bytes(B0, B1);
+                continue;
+            }
+            bytes(B0, A0);
+            bytes(A1, B1);
+            for (int64_t c0 = A0 + 16 * (int64_t)t; c0 < A1; c0 += 16 * SP_THREADS) {
+                int i = row_of(c0 - B0);
+                int64_t q = c0;
+                const int64_t q1 = c0 + 16;
+                uint4 acc = make_uint4(0, 0, 0, 0);
+                bool whole = true;
+                while (q < q1) {
+                    while (loc[i + 1] <= q - B0) i++;  // skips empty rows; q < B1 bounds it
+                    const int64_t row_end = B0 + loc[i + 1];
+                    const int64_t e = row_end < q1 ? row_end : q1;
+                    const int64_t src = src0[i] + (c0 - B0 - loc[i]);  // source of the chunk's byte 0 if row i reached that far back
+                    if (src < lo_guard) {  // would read in front of the buffer / window: bytes
+                        whole = false;
+                        break;
+                    }
+                    const uint4 v = load16_unaligned(rd + src);
+                    if (q == c0) {
+                        acc = v;  // bytes past this row's end are garbage until the next piece overwrites them
+                    } else {      // pieces arrive in order: keep [0, s), take [s, 16)
+                        const uint4 m = s_below[(int)(q - c0)];
+                        acc.x = (acc.x & m.x) | (v.x & ~m.x);
+                        acc.y = (acc.y & m.y) | (v.y & ~m.y);
+                        acc.z = (acc.z & m.z) | (v.z & ~m.z);
+                        acc.w = (acc.w & m.w) | (v.w & ~m.w);
+                    }
+                    q = e;
+                }
+                if (whole) {
+                    if (map) acc.x = map4(acc.x, c0), acc.y = map4(acc.y, c0 + 4), acc.z = map4(acc.z, c0 + 8), acc.w = map4(acc.w, c0 + 12);
+                    *reinterpret_cast<uint4*>(out + c0) = acc;
+                } else {
+                    for (int64_t qq = c0; qq < q1; qq++) {
+                        const int k = row_of(qq - B0);
+                        const uint8_t b = rd[src0[k] + (qq - B0 - loc[k])];
+                        out[qq] = map ? (uint8_t)map1(b, qq) : b;
+                    }
+                }
+            }
+        }
+    }
+    if (kMap && bad != ~0ull) atomicMin(a.bad, bad);
+}
+
+constexpr int SP_MIN_ROWS = 8;
+int64_t fastq_split_scratch_bytes(int64_t n_rows) {
+    return 256 + ((n_rows + SP_MIN_ROWS - 1) / SP_MIN_ROWS + 1) * (int64_t)sizeof(SplitDesc);
+}
+
+template <typename OffT>
+static cudaError_t split_launch_t(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, int64_t n_rows, uint32_t mask, int64_t* off,
+                                  uint8_t* desc_valid, uint8_t* const* out, const int64_t* cap, void* scratch, const ScanResult* scan, int map_mode,
+                                  unsigned long long* bad, cudaStream_t st) {
+    SplitArgs a;
+    a.n_rows = n_rows;
+    a.mask = mask;
+    a.off = off;
+    a.desc_valid = desc_valid;
+    for (int c = 0; c < 4; c++) {
+        a.out[c] = out[c];
+        a.cap[c] = cap[c];
+    }
+    uint8_t* s = reinterpret_cast<uint8_t*>(scratch);
+    a.ticket = reinterpret_cast<unsigned int*>(s);
+    a.overflow = reinterpret_cast<unsigned int*>(s + 8);
+    a.desc = reinterpret_cast<SplitDesc*>(s + 256);
+    a.scan = scan;
+    a.map_mode = map_mode;
+    a.bad = bad;
+    // about 28 KB of input per block, so that its window fits the shared-memory stage: ~80 Illumina records; long
+    // records (ONT) get the minimum and read global memory
+    const int64_t avg = n_rows > 0 ? (n - begin) / n_rows + 1 : 1;
+    int64_t rpb = (28 << 10) / avg;
+    rpb = rpb < SP_MIN_ROWS ? SP_MIN_ROWS : (rpb > SP_ROWS ? SP_ROWS : rpb);
+    a.rows_per_block = (int)rpb;
+    const int64_t n_blocks = (n_rows + rpb - 1) / rpb;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)(256 + (n_blocks + 1) * (int64_t)sizeof(SplitDesc)), st);
+    if (e != cudaSuccess) return e;
+    if (bad && (e = cudaMemsetAsync(bad, 0xFF, 8, st)) != cudaSuccess) return e;
+    FqLines<OffT> L{buf, reinterpret_cast<const OffT*>(line_end), begin, n, true};
+    int64_t blocks = n_blocks;
+    const int64_t machine = 148 * 5;  // 5 resident blocks of 256 threads per SM
+    if (blocks > machine) blocks = machine;
+    if (blocks < 1) blocks = 1;
+    if (bad) fastq_split_kernel<OffT, true><<<(unsigned)blocks, SP_THREADS, 0, st>>>(L, a);
+    else fastq_split_kernel<OffT, false><<<(unsigned)blocks, SP_THREADS, 0, st>>>(L, a);
+    return cudaGetLastError();
+}
+cudaError_t fastq_split_launch(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, bool wide, int64_t n_rows, uint32_t mask,
+                               int64_t* off, uint8_t* desc_valid, uint8_t* const* out, const int64_t* cap, void* scratch, const ScanResult* scan,
+                               int map_mode, unsigned long long* bad, cudaStream_t st) {
+    if (n_rows <= 0) return cudaSuccess;
+    return wide ? split_launch_t<uint64_t>(buf, begin, n, line_end, n_rows, mask, off, desc_valid, out, cap, scratch, scan, map_mode, bad, st)
+                : split_launch_t<uint32_t>(buf, begin, n, line_end, n_rows, mask, off, desc_valid, out, cap, scratch, scan, map_mode, bad, st);
+}
+
 static int row_blocks(int64_t n_rows, int rows_per_block) {
     int64_t b = (n_rows + rows_per_block - 1) / rows_per_block;
     const int64_t cap = 148 * 32;

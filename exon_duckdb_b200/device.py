@@ -258,9 +258,11 @@ def fastq_table(buf, columns=None, preds=(), n=None, seq_map=None):
         _, pas = fastq_filter(scan, n_rec, preds, want_pass=True)
         sel = select_rows(pas)
         n_rows = sel.numel()
+    wide = 1 if scan.wide else 0
+    if sel is None and n_rows > 0:
+        return _fastq_split(buf, n, scan, n_rows, columns, seq_map)
     lens = _empty(4 * n_rows, torch.int32, dev)
     valid = _empty(n_rows, torch.uint8, dev)
-    wide = 1 if scan.wide else 0
     check(lib().exb_fastq_fields(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, _ptr(lens), _ptr(valid), None, _ptr(scan.ws), _stream()))
     out = {}
     # Arrow offsets of all four columns in ONE launch, then ONE host round trip for the column sizes
@@ -282,6 +284,46 @@ def fastq_table(buf, columns=None, preds=(), n=None, seq_map=None):
             check(lib().exb_fastq_gather(_ptr(buf), 0, n, _ptr(scan.line_end), wide, _ptr(sel), n_rows, c, _ptr(lens), _ptr(off),
                                          _ptr(data), _stream()))
         out[name] = Column(off, data, valid if name == "description" else None)
+    out["__n_rows__"] = n_rows
+    return out
+
+
+def _fastq_split(buf, n, scan, n_rows, columns, seq_map):
+    """Unfiltered read_fastq: field split + offsets + all wanted columns in ONE launch (exb_fastq_split)."""
+    dev = buf.device
+    wide = 1 if scan.wide else 0
+    mask = 0
+    for name in columns:
+        mask |= 1 << FASTQ_COLUMNS.index(name)
+    offs = torch.empty((4, n_rows + 1), dtype=torch.int64, device=dev)
+    valid = _empty(n_rows, torch.uint8, dev)
+    scratch = torch.empty(lib().exb_fastq_split_scratch_bytes(n_rows), dtype=torch.uint8, device=dev)
+    mode = -1
+    bad = None
+    if seq_map is not None:
+        mode = {"reverse_complement": _lib.MAP_REVERSE_COMPLEMENT, "complement": _lib.MAP_COMPLEMENT}[seq_map]
+        bad = torch.empty(1, dtype=torch.int64, device=dev)
+    for attempt in range(2):
+        # capacities: a guess that fits ordinary files, then the hard bound (no column is larger than the input)
+        caps = [(n // 4 + 4096, n // 4 + 4096, n // 2 + 4096, n // 2 + 4096), (n + 16,) * 4][attempt]
+        data = [torch.empty(caps[c] + 16, dtype=torch.uint8, device=dev) if (mask >> c) & 1 else None for c in range(4)]
+        outs = (C.c_void_p * 4)(*[_ptr(d) for d in data])
+        capv = (C.c_int64 * 4)(*[caps[c] if (mask >> c) & 1 else 0 for c in range(4)])
+        check(lib().exb_fastq_split(_ptr(buf), 0, n, _ptr(scan.line_end), wide, n_rows, mask, _ptr(offs), _ptr(valid), outs, capv, _ptr(scratch),
+                                    _ptr(scan.ws), mode, _ptr(bad), _stream()))
+        if int(scratch[8:12].view(torch.int32).item()) == 0:
+            break
+    else:
+        raise RuntimeError("exb_fastq_split: column capacity")
+    if bad is not None:
+        b = int(bad.item())
+        if b != -1:
+            raise InvalidInput("Invalid character in sequence: %s" % chr(b & 0xFF))
+    totals = offs[:, n_rows].cpu().tolist()
+    out = {}
+    for name in columns:
+        c = FASTQ_COLUMNS.index(name)
+        out[name] = Column(offs[c], data[c][:totals[c]], valid if name == "description" else None)
     out["__n_rows__"] = n_rows
     return out
 

@@ -440,3 +440,102 @@ def fasta_first_header(shard, window=1 << 20):
         if end == shard.n:
             return -1
         w *= 4
+
+
+class ShardedFastqTotals:
+    """SELECT COUNT(*), SUM(#GC), SUM(length(sequence)), AVG(gc_content(sequence)) FROM read_fastq(file) over this rank's
+    byte-range shard (BASELINE config C5).  Same protocol as ShardedFastqCount with the GENERAL scan flavour:
+
+      byte pass + line offsets + result block (exb_fastq_scan_begin) -> exchange of the 128-byte result blocks ->
+      exb_fastq_compose_prev (device) -> K2 under the true predecessor with shard-local record indices
+      (exb_fastq_scan_resolve, EXB_F_SEQ | EXB_F_LOCAL_RECORDS) -> exb_fastq_seq_totals -> reduce.
+
+    Per-record sequence entries are written by the shard in which the sequence LINE ends, so the sums are additive over
+    shards whatever record the cut falls in.  `total` (int64[8], device) holds the GLOBAL values on every rank:
+    [0] records (lines of the file / 4), [1] sum of sequence lengths, [2] sum of G/C, [5] sum of round(gc_content * 2^32),
+    [6] lines of the file mod 4 (must be 0), [7] shards that met a malformed record (must be 0)."""
+
+    def __init__(self, shard, group, ranges=None, rec_cap=None, max_lines=None):
+        import torch
+
+        from . import device as D
+
+        self.shard, self.group = shard, group
+        dev = shard.buf.device
+        # capacities: estimates that fit any file with records of >= 32 bytes; a caller that knows its records passes tight ones
+        self.ws = torch.empty(_lib.lib().exb_fastq_workspace_bytes(shard.n + 16, max_lines if max_lines else shard.n // 24 + 16384),
+                              dtype=torch.uint8, device=dev)
+        self.rec_cap = rec_cap if rec_cap else shard.n // 32 + 4096
+        self.seq_len = torch.zeros(self.rec_cap, dtype=torch.int32, device=dev)
+        self.gc = torch.zeros(self.rec_cap, dtype=torch.int32, device=dev)
+        self.agg = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.total = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.true_prev = torch.zeros(128, dtype=torch.uint8, device=dev)
+        self.prov = None
+        if shard.begin:  # provisional predecessor: "no line is open before `begin`"
+            r = _lib.ScanResult()
+            r.open_line_start = shard.begin
+            r.err_pos = _lib.NO_POS
+            self.prov = torch.zeros(128, dtype=torch.uint8, device=dev)
+            _lib.check(_lib.lib().exb_scan_result_store(D._ptr(self.prov), C.byref(r), D._stream()))
+        self.ranges = np.asarray(ranges if ranges is not None else group.all_gather_rows([shard.lo, shard.hi, shard.begin]), dtype=np.int64)
+        self.world = len(self.ranges)
+        self.d_ranges = torch.from_numpy(self.ranges.copy()).to(dev)
+        self.blocks = torch.zeros(self.world * RESULT_WORDS, dtype=torch.int64, device=dev)
+        self.flags = _lib.F_SEQ | _lib.F_LOCAL_RECORDS
+
+    def scan(self):
+        from . import device as D
+
+        s = self.shard
+        _lib.check(_lib.lib().exb_fastq_scan_begin(D._ptr(s.buf), s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.prov), self.flags,
+                                                   D._ptr(self.ws), self.ws.numel(), D._stream()))
+        return _result_block(self.ws)
+
+    def resolve_local(self, blocks, rank):
+        from . import device as D
+
+        s = self.shard
+        L = _lib.lib()
+        prev = None
+        if rank > 0:
+            _lib.check(L.exb_fastq_compose_prev(D._ptr(blocks), D._ptr(self.d_ranges), self.world, rank, D._ptr(self.true_prev), D._stream()))
+            prev = self.true_prev
+        # a record that straddles the shard's first byte only gets the fields whose line ends here: start from zeros
+        self.seq_len.zero_()
+        self.gc.zero_()
+        _lib.check(L.exb_fastq_scan_resolve(s.begin, s.n, 1 if s.is_last else 0, D._ptr(prev), D.UINT64_MAX, self.flags, None, 0, 0,
+                                            D._ptr(self.seq_len), D._ptr(self.gc), None, None, self.rec_cap, D._ptr(self.ws), self.ws.numel(), D._stream()))
+        self.agg.zero_()
+        _lib.check(L.exb_fastq_seq_totals(D._ptr(self.seq_len), D._ptr(self.gc), self.rec_cap, D._ptr(self.agg), D._stream()))
+
+    def finish_local(self):
+        """agg[0] = lines this shard contributes to the record count (total lines of the file on the last shard), plus the
+        bookkeeping words exb_peer_count_reduce / the NCCL path expect."""
+        blk = _result_block(self.ws)
+        if self.shard.is_last:
+            self.agg[0] = blk[0] // 4  # total_lines of the last shard = lines of the whole file (its K2 ran under the true predecessor)
+
+    def step(self):
+        from . import device as D
+
+        g = self.group
+        blk = self.scan()
+        if isinstance(g, PeerGroup):
+            L = _lib.lib()
+            g.seq += 1
+            _lib.check(L.exb_peer_allgather_block(g.d_peers, g.rank, g.world, D._ptr(blk), g.seq, D._stream()))
+            self.resolve_local(g.blocks_view(g.seq), g.rank)
+            self.finish_local()
+            _lib.check(L.exb_peer_count_reduce(g.d_peers, g.rank, g.world, D._ptr(self.ws), D._ptr(self.agg), 1 if self.shard.is_last else 0,
+                                               g.seq, D._ptr(self.total), D._stream()))
+            return self.total
+        g.dist.all_gather_into_tensor(self.blocks, blk, group=g.group)
+        self.resolve_local(self.blocks, g.rank)
+        self.finish_local()
+        blk = _result_block(self.ws)
+        self.total.copy_(self.agg)
+        self.total[7] = (blk[2] != 0).to(self.total.dtype)
+        self.total[6] = (blk[0] & 3) if self.shard.is_last else 0
+        g.all_reduce_sum(self.total)
+        return self.total

@@ -222,6 +222,11 @@ static idx_t PlanReaders(const ScanBindData &bind, const char *comp, int64_t &to
 	if (bind.gpus == 0) {
 		want = MinValue<idx_t>(want, (idx_t)MaxValue<int64_t>(1, total_bytes / (256ll << 20)));
 	}
+	if (const char *force = getenv("EXON_B200_FORCE_READERS")) { // tests: several pipelines on however many devices there are
+		if (atoi(force) > 0) {
+			want = (idx_t)atoi(force);
+		}
+	}
 	if (shardable) {
 		return MaxValue<idx_t>(want, 1);
 	}

@@ -243,6 +243,11 @@ EXB_API int exb_device_count(void);
 #define EXB_F_LINES 1 /* line_end[g]: offset of the '\n' that ends line g       */
 #define EXB_F_SEQ 2   /* seq_len[r], gc[r]                                       */
 #define EXB_F_QUAL 4  /* qual_len[r], qsum[r] = sum((signed char)c - 33)         */
+#define EXB_F_LOCAL_RECORDS 16 /* a chained / sharded range indexes its per-record outputs from the FIRST record it touches
+                                  (record of global line prev.total_lines) instead of from record 0 of the file: what a
+                                  byte-range shard needs, whose arrays only cover its own records.  A record that
+                                  straddles the range's first byte gets index 0 and only the fields whose line ENDS in
+                                  the range; zero the arrays first if partial records matter                          */
 
 typedef struct exb_scan_result {
     uint64_t total_lines;     /* FASTQ: lines seen, the unterminated last line included  */
@@ -354,6 +359,10 @@ EXB_API int exb_fastq_scan_filter(const void *d_buf, int64_t begin, int64_t n, i
 EXB_API int exb_fastq_scan_filter_begin(const void *d_buf, int64_t begin, int64_t n, int is_final,
                                         const void *d_prev_workspace, const exb_predicate *preds, int n_preds,
                                         void *d_workspace, int64_t workspace_bytes, void *stream);
+/* Step 1 of the general flavour without its K2 (see exb_fastq_scan_filter_begin): byte pass, line-offset scan and
+ * the result block.  flags = the EXB_F_* the later exb_fastq_scan_resolve will ask for. */
+EXB_API int exb_fastq_scan_begin(const void *d_buf, int64_t begin, int64_t n, int is_final, const void *d_prev_workspace,
+                                 int flags, void *d_workspace, int64_t workspace_bytes, void *stream);
 EXB_API int exb_fastq_scan_resolve(int64_t begin, int64_t n, int is_final, const void *d_prev_workspace, uint64_t max_lines,
                                    int flags, void *d_line_end, int64_t line_cap, int wide_offsets, uint32_t *d_seq_len,
                                    uint32_t *d_gc, uint32_t *d_qual_len, int32_t *d_qsum, int64_t rec_cap,
@@ -418,6 +427,23 @@ EXB_API int exb_select_rows(const uint8_t *d_pass, int64_t n, int64_t *d_offsets
 EXB_API int exb_fastq_gather(const void *d_buf, int64_t begin, int64_t n, const void *d_line_end, int wide_offsets,
                              const int64_t *d_sel, int64_t n_rows, int col, const uint32_t *d_lens,
                              const int64_t *d_off, uint8_t *d_out, void *stream);
+/* The field split, the offset scan and the four column gathers of ALL records of a scanned range as ONE launch
+ * (record_ops.cu fastq_split_kernel): a block of 256 consecutive records computes its field extents, obtains its output
+ * offsets with a decoupled look-back over the earlier blocks and copies its rows of every wanted column while their
+ * input window is hot in L2, so each input DRAM atom is fetched once.  Replaces exb_fastq_fields +
+ * exb_exclusive_scan_u32_multi + 4 x exb_fastq_gather for unfiltered scans.
+ *   column_mask : bit c = copy column c (name, description, sequence, quality_scores); offsets are produced for all four
+ *   d_off       : int64[4][n_rows + 1] Arrow offsets (exclusive prefix of the field lengths), column-major
+ *   d_out[c]    : 16-byte aligned output of column c, cap[c] bytes (NULL / 0 for columns not in the mask)
+ *   d_scratch   : exb_fastq_split_scratch_bytes(n_rows) bytes (zeroed by the call); after the call its word [2] (uint32)
+ *                 is 1 if a column did not fit its capacity
+ *   map_mode    : < 0 = plain copy; else EXB_MAP_* applied to the sequence column on its way out, *d_bad as in
+ *                 exb_fastq_gather_map */
+EXB_API int64_t exb_fastq_split_scratch_bytes(int64_t n_rows);
+EXB_API int exb_fastq_split(const void *d_buf, int64_t begin, int64_t n, const void *d_line_end, int wide_offsets,
+                            int64_t n_rows, uint32_t column_mask, int64_t *d_off, uint8_t *d_desc_valid,
+                            uint8_t *const *d_out, const int64_t *cap, void *d_scratch, const void *d_scan_workspace,
+                            int map_mode, uint64_t *d_bad, void *stream);
 /* The same gather with reverse_complement / complement (sequence_functions/module.cpp:30-121, the reference's LUTs)
  * applied to the bytes on their way out: `SELECT reverse_complement(sequence) FROM read_fastq(...)` on a
  * device-resident file is one pass over the sequence bytes instead of gather + exb_seq_map.  mode = EXB_MAP_*.
@@ -464,6 +490,14 @@ EXB_API int exb_gc_from_prefix(const int64_t *d_seq_off, const int64_t *d_gc_pre
 /* same from FASTQ per-record counts */
 EXB_API int exb_gc_from_counts(const uint32_t *d_seq_len, const uint32_t *d_gc, int64_t n_rows, float *d_out,
                                void *stream);
+
+/* Totals over the per-record arrays of a scan, for COUNT / SUM / AVG queries (BASELINE config C5:
+ * SELECT COUNT(*), SUM(#GC), SUM(length(sequence)), AVG(gc_content(sequence))):  d_totals (int64[8], ADDED to)
+ *   [1] += sum seq_len   [2] += sum gc   [5] += sum round(gc_content(r) * 2^32)  (fixed point: the float average is
+ *   then independent of the summation order and of the number of shards; |error| <= 2^-33 per record)
+ * Entries are additive per sequence LINE, so byte-range shards may simply add theirs (EXB_F_LOCAL_RECORDS arrays). */
+EXB_API int exb_fastq_seq_totals(const uint32_t *d_seq_len, const uint32_t *d_gc, int64_t n_records, int64_t *d_totals,
+                                 void *stream);
 
 /* ---- scalar functions over an Arrow-style string column (int64 offsets + bytes) ----
  * sequence_functions/module.cpp:131-158 (per-row formula; d_valid NULL = all valid;

@@ -464,10 +464,50 @@ def test_gpus_parameter(cuda_device, tmp_path):
     text, _ = util.random_fastq(31, 4000, min_len=20, max_len=150, tricky=False)
     path = _write(tmp_path, "g.fastq", text)
     n_dev = torch.cuda.device_count()
-    r = run_sql(PRODUCT, ["SELECT count(*) FROM read_fastq('%s', gpus := 1)" % path])
+    r = run_sql(PRODUCT, ["SELECT count(*) FROM read_fastq('%s', gpus=1)" % path])
     assert rows(r[0]) == [["4000"]]
     _need(SQLRUN, PRODUCT)
-    out = subprocess.run([SQLRUN], input=("LOAD '%s';\nSELECT count(*) FROM read_fastq('%s', gpus := %d);\n" % (PRODUCT, path, n_dev + 1)).encode(),
+    out = subprocess.run([SQLRUN], input=("LOAD '%s';\nSELECT count(*) FROM read_fastq('%s', gpus=%d);\n" % (PRODUCT, path, n_dev + 1)).encode(),
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     res = [json.loads(l) for l in out.stdout.decode().splitlines()]
     assert not res[1]["ok"] and "CUDA device" in res[1]["error"]
+
+
+@pytest.mark.gpu
+def test_one_pipeline_per_gpu_gives_the_same_answers(cuda_device, tmp_path):
+    """read_fastq / read_fasta with one device pipeline per GPU (byte-range shards of the file): same rows in the same
+    order as a single pipeline.  On a one-GPU box the shards all run on device 0 (gpus=1 pipelines are forced with
+    EXON_B200_FORCE_READERS), which exercises the same shard logic."""
+    import torch
+    from oracle import oracle as O
+    text, _ = util.random_fastq(37, 20000, min_len=30, max_len=150, tricky=False)
+    path = _write(tmp_path, "mg.fastq", text)
+    ftext, _ = util.random_fasta(39, 500, min_len=0, max_len=4000, tricky=False)
+    fpath = _write(tmp_path, "mg.fasta", ftext)
+    ref = O.parse_fastq(text)
+    names = [x.decode() for x in ref.strings("name")]
+    n_dev = torch.cuda.device_count()
+    shards = 4
+    env = {"EXON_B200_CHUNK_BYTES": str(300_000), "EXON_B200_FORCE_READERS": str(shards)}
+    mq = "list_avg(quality_score_string_to_list(quality_scores)) > 60"
+    stmts = [
+        "SELECT count(*) FROM read_fastq('%s')" % path,
+        "SELECT count(*), sum(length(sequence)), sum(length(quality_scores)) FROM read_fastq('%s') WHERE %s" % (path, mq),
+        "CREATE TABLE t AS SELECT name, gc_content(sequence) AS g FROM read_fastq('%s')" % path,
+        "SELECT name FROM t WHERE rowid IN (0, 1, 4999, 5000, 9999, 10000, 15000, 19999) ORDER BY rowid",
+        "SELECT count(*), sum(g::DOUBLE) FROM t",
+        "SELECT name FROM read_fastq('%s') LIMIT 4 OFFSET 12345" % path,
+        "SELECT count(*), sum(length(sequence)), avg(gc_content(sequence)) FROM read_fasta('%s')" % fpath,
+        "SELECT id FROM read_fasta('%s') LIMIT 3 OFFSET 250" % fpath,
+    ]
+    one = run_sql(PRODUCT, stmts, threads=4, env={"EXON_B200_CHUNK_BYTES": str(300_000)})
+    many = run_sql(PRODUCT, stmts, threads=4, env=env)
+    for a, b in zip(one, many):
+        assert rows(a) == rows(b)
+    assert rows(many[0]) == [["20000"]]
+    assert [r[0] for r in rows(many[3])] == [names[i] for i in (0, 1, 4999, 5000, 9999, 10000, 15000, 19999)]
+    assert [r[0] for r in rows(many[5])] == names[12345:12349]
+    if n_dev >= 2:  # real devices
+        real = run_sql(PRODUCT, [s.replace("')", "', gpus=%d)" % n_dev) for s in stmts], threads=n_dev, env={"EXON_B200_CHUNK_BYTES": str(300_000)})
+        for a, b in zip(one, real):
+            assert rows(a) == rows(b)

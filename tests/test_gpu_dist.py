@@ -139,3 +139,43 @@ def test_fasta_first_header_and_bounds(cuda_device):
             if part:
                 ids += D.fasta_table(D.to_device(part, cuda_device), columns=["id"])["id"].to_pylist()
         assert ids == O.parse_fasta(data).strings("id")
+
+
+# ------------------------------------------------------------------ C5: COUNT + SUM(#GC) + SUM(len) + AVG(gc_content) over byte-range shards
+def _sharded_totals(data, cuts, dev):
+    bounds = [0] + list(cuts) + [len(data)]
+    G = len(bounds) - 1
+    shards = []
+    for k in range(G):
+        lo, hi = bounds[k], bounds[k + 1]
+        begin = 0 if k == 0 else dist.HALO
+        halo = bytes(max(0, begin - lo)) + bytes(data[max(0, lo - begin):lo]) if begin else b""
+        shards.append(dist.Shard(D.to_device(halo + bytes(data[lo:hi]), dev), lo, hi, begin, k == G - 1))
+    ranges = [[s.lo, s.hi, s.begin] for s in shards]
+    jobs = [dist.ShardedFastqTotals(s, None, ranges=ranges) for s in shards]
+    blocks = torch.cat([j.scan().clone() for j in jobs])  # the all-gather
+    total = torch.zeros(8, dtype=torch.int64, device=dev)
+    for k, j in enumerate(jobs):
+        j.resolve_local(blocks, k)
+        j.finish_local()
+        blk = dist._result_block(j.ws)
+        t = j.agg.clone()
+        t[7] = (blk[2] != 0).to(t.dtype)
+        t[6] = (blk[0] & 3) if j.shard.is_last else 0
+        total += t  # the all-reduce
+    return total
+
+
+@pytest.mark.parametrize("seed,kw", [(1, {}), (2, {"crlf": True}), (3, {"final_eol": False}), (4, {"max_len": 3}), (5, {"max_len": 9000, "min_len": 3000})])
+def test_sharded_totals_equal_oracle(cuda_device, seed, kw):
+    n = 60 if kw.get("max_len", 0) < 1000 else 12
+    data, _ = util.random_fastq(seed, n, **kw)
+    seqs = O.parse_fastq(data).strings("sequence")
+    want = (len(seqs), sum(len(s) for s in seqs), sum(s.count(b"G") + s.count(b"C") for s in seqs),
+            sum(int(round(float(np.float64(O.gc_content(s)) * 4294967296.0))) for s in seqs if s))
+    rng = random.Random(seed)
+    cut_sets = [[c] for c in range(0, len(data) + 1, max(1, len(data) // 61))]
+    cut_sets += [sorted(rng.randint(0, len(data)) for _ in range(rng.randint(2, 7))) for _ in range(25)]
+    for cuts in cut_sets:
+        t = dist.check_count(_sharded_totals(data, cuts, cuda_device))
+        assert (t[0], t[1], t[2], t[5]) == want, (cuts, t, want)

@@ -120,8 +120,10 @@ int main(int argc, char** argv) {
     for (int kind = 0; kind < 3; kind++) {
         const char* kname = kind == 0 ? "memcpy" : (kind == 1 ? "avx512 cached" : "avx512 streaming");
         for (int T : {8, 12, 16}) {
+            if (getenv("IOB_QUICK") && T != 8) continue;
             Pool pool(T);
             for (int64_t slice : {2ll << 20, 4ll << 20, 8ll << 20, 16ll << 20, 64ll << 20}) {
+                if (getenv("IOB_QUICK") && slice != (64ll << 20)) continue;
                 const int slots = (int)(RING / slice);
                 std::vector<cudaEvent_t> ev(slots);
                 for (auto& e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

@@ -100,6 +100,36 @@ def c2_paths(rep, buf, reads, iters=10, full=True):
     out_b = sum(tab[k].data.numel() for k in D.FASTQ_COLUMNS) + 32 * tab["__n_rows__"]
     med, best = timeit(lambda: D.fastq_table(buf), iters=5)
     rep.add("C2 full 4-column materialisation (fastq_table)", n + out_b, med, best, n, "includes host syncs for sizes")
+    # the same work with the outputs allocated up front and nothing read back in between: what the device itself takes
+    # (the reader allocates its chunk buffers once, too).  exb_fastq_scan(F_LINES) + exb_fastq_split, all four columns.
+    import ctypes as C
+    from exon_duckdb_b200._lib import check, lib
+    dev = buf.device
+    s = D.fastq_scan(buf, _lib.F_LINES, rec_cap=rec_cap)
+    assert s.validate() == reads
+    offs = torch.empty((4, reads + 1), dtype=torch.int64, device=dev)
+    valid = torch.empty(reads, dtype=torch.uint8, device=dev)
+    scratch = torch.empty(lib().exb_fastq_split_scratch_bytes(reads), dtype=torch.uint8, device=dev)
+    caps = [int(tab[k].data.numel()) + 64 for k in D.FASTQ_COLUMNS]
+    data = [torch.empty(c + 16, dtype=torch.uint8, device=dev) for c in caps]
+    outs = (C.c_void_p * 4)(*[D._ptr(d) for d in data])
+    capv = (C.c_int64 * 4)(*caps)
+
+    def direct():
+        D.fastq_scan(buf, _lib.F_LINES, out=s)
+        check(lib().exb_fastq_split(D._ptr(buf), 0, n, D._ptr(s.line_end), 1 if s.wide else 0, reads, 0xF, D._ptr(offs), D._ptr(valid), outs, capv,
+                                    D._ptr(scratch), D._ptr(s.ws), -1, None, D._stream()))
+    direct()
+    torch.cuda.synchronize()
+    assert offs[:, reads].cpu().tolist() == [int(tab[k].data.numel()) for k in D.FASTQ_COLUMNS]
+    assert all(torch.equal(data[c][:caps[c] - 64], tab[k].data) for c, k in enumerate(D.FASTQ_COLUMNS))
+    med, best = timeit(direct, iters)
+    rep.add("C2 full 4-column materialisation, device only (exb_fastq_scan + exb_fastq_split)", n + out_b, med, best, n, "outputs preallocated, no host round trip")
+    med, best = timeit(lambda: check(lib().exb_fastq_split(D._ptr(buf), 0, n, D._ptr(s.line_end), 1 if s.wide else 0, reads, 0xF, D._ptr(offs), D._ptr(valid),
+                                                           outs, capv, D._ptr(scratch), D._ptr(s.ws), -1, None, D._stream())), iters)
+    rep.add("C2 column split alone (exb_fastq_split: fields + offsets + 4 columns)", out_b + (out_b - 32 * reads) + 16 * reads, med, best, n,
+            "reads 4 B per line + the record bytes, writes offsets + columns")
+    del data, offs, valid, scratch, s
     if full:
         seq = tab["sequence"]
         qual = tab["quality_scores"]

@@ -33,6 +33,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.exb_gen_size.restype = C.c_int64
         L.exb_gen_size.argtypes = [C.POINTER(GenParams)]
+        L.exb_gen_size_device.restype = C.c_int
+        L.exb_gen_size_device.argtypes = [C.POINTER(GenParams), C.POINTER(C.c_int64), C.c_void_p]
         L.exb_gen_device.restype = C.c_int
         L.exb_gen_device.argtypes = [C.POINTER(GenParams), C.c_void_p, C.c_int64, C.c_void_p]
         L.exb_gen_host.restype = C.c_int
@@ -74,8 +76,18 @@ def gen_device(params, device="cuda"):
     """The same text generated on the device: a torch uint8 tensor with 64 bytes of zeroed slack behind it."""
     import torch
 
-    size = gen_size(params)
-    buf = torch.zeros(size + 64, dtype=torch.uint8, device=device)
+    dev = torch.device(device)
+    if params.n_records > 2_000_000:  # the host loop takes ~0.1 us per record: count on the device
+        sz = C.c_int64()
+        with torch.cuda.device(dev):
+            rc = lib().exb_gen_size_device(C.byref(params), C.byref(sz), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError("exb_gen_size_device failed: %d" % rc)
+        size = sz.value
+    else:
+        size = gen_size(params)
+    buf = torch.empty(size + 64, dtype=torch.uint8, device=dev)
+    buf[size:].zero_()
     with torch.cuda.device(buf.device):
         rc = lib().exb_gen_device(C.byref(params), C.c_void_p(buf.data_ptr()), size + 16, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:

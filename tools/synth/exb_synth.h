@@ -30,6 +30,8 @@ typedef struct exb_gen_params {
 } exb_gen_params;
 /* Size in bytes of the text the parameters describe (host computation, exact). */
 EXB_API int64_t exb_gen_size(const exb_gen_params *p);
+/* The same size computed on the device (large record counts). Synchronous. */
+EXB_API int exb_gen_size_device(const exb_gen_params *p, int64_t *size_out, void *stream);
 /* Generate on the device: d_out must hold exb_gen_size(p) bytes (+16 slack). Synchronous. */
 EXB_API int exb_gen_device(const exb_gen_params *p, void *d_out, int64_t cap, void *stream);
 /* Generate on the host (same bytes), no GPU needed. */
