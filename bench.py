@@ -262,7 +262,7 @@ def main():
         # provisional phase, all-gather of the 128-byte result blocks, device-side composition, resolve kernel, all-reduce.
         from exon_duckdb_b200 import dist as XD
 
-        exchange = "nvlink peer memory (symmetric buffers, exb_peer_allgather_block + exb_peer_count_reduce)"
+        exchange = "nvlink peer memory (symmetric buffers), ONE exchange per step: exb_fastq_scan_filter_candidates + exb_peer_count_fused"
         try:
             if os.environ.get("EXB_EXCHANGE", "peer") != "peer":
                 raise RuntimeError("EXB_EXCHANGE=%s" % os.environ["EXB_EXCHANGE"])
@@ -275,7 +275,7 @@ def main():
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         if int(okt.item()) == 0:  # all ranks take the same path
             grp = XD.TorchGroup(dev)
-            exchange = "nccl all-gather (128 B per shard) + all-reduce (64 B)"
+            exchange = "nccl all-gather (256 B per shard) + local combine (exb_fastq_combine_records)"
 
         def build_shard(R):
             """This rank's byte range of ONE file of world x R records whose cuts fall INSIDE records."""
@@ -611,7 +611,8 @@ def main():
             # peer-memory exchange adds exb_peer_allgather_block + exb_peer_count_reduce (7 of this library's kernels per step)
             # launches of THIS library on rank 0 per step: tile + 3 scan + combine; N>1: + final_state (+ allgather + reduce
             # with the peer-memory exchange; rank 0 has no compose kernel)
-            "gpu_launches": (5 if world == 1 else (8 if exchange.startswith("nvlink") else 6)) * args.steps,
+            # N>1, single-exchange flavour (default): tile + 3 scan + candidates + peer_count_fused = 6 (NCCL: 5 + combine)
+            "gpu_launches": (5 if world == 1 else 6) * args.steps,
         }
         if world > 1:
             line["exchange"] = exchange

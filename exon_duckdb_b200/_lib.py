@@ -149,6 +149,9 @@ SIGNATURES = {
     "exb_fastq_seq_totals": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_fastq_scan_resolve": (_i32, [_i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_fastq_scan_filter_resolve": (_i32, [_i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i32, _vp, _i64, _vp]),
+    "exb_fastq_scan_filter_candidates": (_i32, [_vp, _i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _vp, _i64, _vp]),
+    "exb_fastq_combine_records": (_i32, [_vp, _vp, _i32, C.POINTER(Predicate), _i32, _vp, _vp]),
+    "exb_peer_count_fused": (_i32, [_vp, _i32, _i32, _vp, _vp, C.POINTER(Predicate), _i32, _u64, _vp, _vp]),
     "exb_fastq_compose_prev": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "exb_peer_bytes": (_i64, []),
     "exb_peer_blocks_offset": (_i64, [_u64]),

@@ -199,7 +199,7 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
                              uint64_t max_lines, int flags, void* d_line_end, int64_t line_cap, int wide_offsets, uint32_t* d_seq_len,
                              uint32_t* d_gc, uint32_t* d_qual_len, int32_t* d_qsum, int64_t rec_cap, const exb_predicate* preds, int n_preds,
                              int64_t* d_agg, void* d_workspace, int64_t workspace_bytes, cudaStream_t st, bool resolve_only = false,
-                             bool scan_only = false) {
+                             bool scan_only = false, long long* d_candidates = nullptr) {
     if ((!d_buf && !resolve_only) || begin < 0 || n < begin) return set_err(EXB_ERR_ARG, "%s: bad buffer range", who);
     if (((uintptr_t)d_buf & 15) != 0) return set_err(EXB_ERR_ARG, "%s: d_buf must be 16-byte aligned", who);
     if (d_prev_workspace && (begin & 15) != 0) return set_err(EXB_ERR_ARG, "%s: `begin` of a chained range must be a multiple of 16", who);
@@ -268,6 +268,11 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
         e = exclusive_scan_launch_u32(a.tile_cnt, a.n_tiles, line_base, w.slots, w.ticket, st);
         if (e != cudaSuccess) return cuda_fail(e, "line offset scan launch");
     }
+    if (d_candidates) {  // K2 for all four phases + the description of the range's first line (single-exchange COUNT)
+        e = fastq_candidates_launch(a, d_candidates, st);
+        if (e != cudaSuccess) return cuda_fail(e, "fastq_candidates launch");
+        return 0;
+    }
     if (scan_only) {  // the result block only: K2 runs later through the matching *_resolve call
         e = fastq_final_state_launch(a, st);
         if (e != cudaSuccess) return cuda_fail(e, "fastq_final_state launch");
@@ -329,6 +334,31 @@ int exb_fastq_scan_filter_begin(const void* d_buf, int64_t begin, int64_t n, int
     return fastq_scan_common("exb_fastq_scan_filter_begin", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_QUAL, nullptr, 0,
                              0, nullptr, nullptr, nullptr, nullptr, 0, preds, n_preds, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream,
                              false, true);
+}
+
+int exb_fastq_scan_filter_candidates(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace,
+                                     const exb_predicate* preds, int n_preds, void* d_record, void* d_workspace, int64_t workspace_bytes,
+                                     void* stream) {
+    if (n_preds < 0 || n_preds > EXB_MAX_PREDICATES || (n_preds > 0 && !preds) || !d_record)
+        return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter_candidates: bad arguments");
+    for (int i = 0; i < n_preds; i++) {
+        if (preds[i].field != EXB_P_MEAN_QUALITY && preds[i].field != EXB_P_QUAL_LEN)
+            return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter_candidates: predicate %d is not on the quality line", i);
+        if (preds[i].op < 0 || preds[i].op > 5) return set_err(EXB_ERR_ARG, "exb_fastq_scan_filter_candidates: bad operator in predicate %d", i);
+    }
+    return fastq_scan_common("exb_fastq_scan_filter_candidates", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_QUAL, nullptr, 0,
+                             0, nullptr, nullptr, nullptr, nullptr, 0, preds, n_preds, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream,
+                             false, true, reinterpret_cast<long long*>(d_record));
+}
+
+int exb_fastq_combine_records(const void* d_records, const int64_t* d_ranges, int world, const exb_predicate* preds, int n_preds,
+                              int64_t* d_total, void* stream) {
+    if (!d_records || !d_ranges || !d_total || world < 1 || world > 16 || n_preds < 0 || n_preds > EXB_MAX_PREDICATES)
+        return set_err(EXB_ERR_ARG, "exb_fastq_combine_records: bad arguments (1 <= world <= 16)");
+    cudaError_t e = fastq_combine_records_launch(reinterpret_cast<const long long*>(d_records), d_ranges, world, preds, n_preds,
+                                                 reinterpret_cast<long long*>(d_total), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "fastq_combine_records launch");
+    return 0;
 }
 
 int exb_fastq_scan_begin(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, int flags, void* d_workspace,
@@ -476,6 +506,7 @@ int exb_fastq_split(const void* d_buf, int64_t begin, int64_t n, const void* d_l
         caps[c] = cap[c];
         if (((column_mask >> c) & 1u) && (!out[c] || ((uintptr_t)out[c] & 15))) return set_err(EXB_ERR_ARG, "exb_fastq_split: column %d needs a 16-byte aligned output", c);
     }
+    if (((uintptr_t)d_buf & 15) != 0) return set_err(EXB_ERR_ARG, "exb_fastq_split: d_buf must be 16-byte aligned");
     if (map_mode >= 0 && (!d_bad || map_mode > EXB_MAP_REVERSE_TRANSCRIBE)) return set_err(EXB_ERR_ARG, "exb_fastq_split: bad map arguments");
     cudaError_t e = fastq_split_launch(reinterpret_cast<const uint8_t*>(d_buf), begin, n, d_line_end, wide_offsets != 0, n_rows, column_mask, d_off,
                                        d_desc_valid, out, caps, d_scratch, reinterpret_cast<const ScanResult*>(d_scan_workspace), map_mode,

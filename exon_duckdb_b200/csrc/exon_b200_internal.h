@@ -73,6 +73,13 @@ struct FastqScanArgs {
     int local_records;          // EXB_F_LOCAL_RECORDS: record indices count from the first record the range touches
 };
 
+struct FusedPreds {  // predicates by value (kernel argument)
+    int n;
+    exb_predicate p[EXB_MAX_PREDICATES];
+};
+cudaError_t fastq_candidates_launch(const FastqScanArgs& a, long long* rec, cudaStream_t st);
+cudaError_t fastq_combine_records_launch(const long long* recs, const int64_t* ranges, int world, const exb_predicate* preds, int n_preds,
+                                         long long* total, cudaStream_t st);
 cudaError_t fastq_tile_launch(const FastqScanArgs& a, int flags, cudaStream_t st);                     // K1
 cudaError_t fastq_emit_launch(const FastqScanArgs& a, int flags, bool wide_offsets, cudaStream_t st);  // K2
 int64_t fastq_scan_tiles(int64_t begin, int64_t n, int is_final);  // 4 KiB warp tiles

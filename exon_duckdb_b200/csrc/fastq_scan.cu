@@ -48,6 +48,7 @@
 #include "tma_tile.cuh"
 #include "exon_b200_internal.h"
 #include "x87div.h"
+#include "combine_records.cuh"
 
 namespace exb {
 
@@ -840,6 +841,132 @@ __global__ void __launch_bounds__(256) fastq_fused_combine_kernel(const FastqSca
         // wrapper re-runs the general scan for the offset when it sees this mark (err_pos = n)
         if (any_bad) atomicMax(&a.result->err_pos, ~(unsigned long long)a.n);
     }
+}
+
+// =================================================================== sharded COUNT with ONE exchange
+// A byte-range shard does not know the phase of its first line until it has heard from its predecessors.  Instead of
+// waiting for that (exchange -> compose -> K2 -> reduce: four dependent launches, two of them spinning on NVLink flags),
+// K2 is run BEFORE the exchange for all four phases at once: candidate c holds the aggregates of every line of the range
+// except its first one under the hypothesis "the range's first line has phase c" (each tile's four buckets are simply
+// added to the candidate they belong to), and the first line -- the only one whose length, Phred sum and first byte
+// depend on the predecessors -- is described instead of judged.  One 256-byte record per shard is then exchanged and
+// EVERY rank combines all records the same way (fastq_combine_records): no second collective.
+//   rec[0] lines of the range   rec[1] open_line_start (local)   rec[2] tail_s   rec[3] open-line first-byte flags
+//   rec[5] local offset of the range's first newline (-1 = none)  rec[6] its CR flag
+//   rec[7] byte sum of the range before that newline              rec[8] first-byte flags of the range
+//   rec[9 + 3c ..] count, Phred sum, length sum of candidate c    rec[21] bit c: a line start contradicts candidate c
+__global__ void __launch_bounds__(256) fastq_fused_candidates_kernel(const FastqScanArgs a, long long* __restrict__ rec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = a.n_tiles;
+    const int64_t origin = a.begin & ~(int64_t)15;
+    const int64_t threads = (int64_t)gridDim.x * blockDim.x;
+    const FusedPlan plan = make_plan(a);
+    __shared__ exb_predicate s_preds[EXB_MAX_PREDICATES];
+    if (threadIdx.x < a.n_fused) s_preds[threadIdx.x] = a.fused[threadIdx.x];
+    __syncthreads();
+    long long cnt[4] = {0, 0, 0, 0}, qs[4] = {0, 0, 0, 0}, ql[4] = {0, 0, 0, 0};
+    uint32_t bad = 0;
+    for (int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tile < n_tiles; tile += threads) {
+        const int n_events = (int)a.tile_cnt[tile];
+        const bool is_last = tile == n_tiles - 1;
+        if (tile == 0) rec[8] = tail_byte0_flags(a.tails[0]);
+        if (n_events == 0 && !is_last) continue;
+        const uint64_t lb = (uint64_t)a.line_base[tile];  // lines of the range before this tile
+        const int64_t tile_base = origin + tile * WT_BYTES;
+        const OpenLine open = open_line_before(a.tails, tile, origin, a);
+        if (n_events > 0) {
+            const FusedTile* ft = a.fused_tiles + tile;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int h = (int)((lb + (uint64_t)c) & 3);
+                const uint32_t cq = ft->cq[h];
+                cnt[c] += cq & 0xFFFu;
+                ql[c] += cq >> 12;
+                qs[c] += ft->qs[h];
+                bad |= ((ft->bad4 >> h) & 1u) << c;
+            }
+            const uint32_t y0 = ft->y0;
+            if (lb == 0) {  // the range's first newline: its line is finished by whoever knows the predecessors
+                rec[5] = tile_base + rec_pos(y0);
+                rec[6] = rec_cr(y0);
+                rec[7] = (long long)ft->ps0 + open.s;
+            } else {  // a line that began inside the range
+                uint32_t len = (uint32_t)(tile_base - open.start) + (uint32_t)rec_pos(y0);
+                const uint32_t cr = len > 0 ? rec_cr(y0) : 0u;
+                len -= cr;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int h = (int)((lb + (uint64_t)c) & 3);
+                    if ((h & 1) == 0 && !(open.flags & (h == 0 ? 2u : 1u))) bad |= 1u << c;
+                }
+                const int c3 = (int)((3 - lb) & 3);  // the candidate under which this line is a quality line
+                const int q1 = ft->ps0 + open.s - 13 * (int)cr - 33 * (int)len;
+                FusedPlan p1 = plan;
+                if (len > 4096u) p1.simple = 0;  // see fastq_fused_combine_kernel
+                if (fused_pass(s_preds, a.n_fused, p1, q1, len)) {
+                    cnt[c3] += 1;
+                    qs[c3] += q1;
+                    ql[c3] += len;
+                }
+            }
+        }
+        if (is_last) {
+            write_final_state(a, lb + (uint64_t)n_events, n_events, tile_base, a.tails[tile], open);
+            rec[0] = (long long)(lb + (uint64_t)n_events);
+            if (n_events > 0) {
+                const uint64_t tw = a.tails[tile];
+                rec[1] = tile_base + tail_rel_of(tw);
+                rec[2] = tail_s_of(tw);
+                rec[3] = tail_open_flags(tw);
+            } else {
+                rec[1] = open.start;
+                rec[2] = (long long)open.s + tail_s_of(a.tails[tile]);
+                rec[3] = open.flags;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) {
+            cnt[c] += __shfl_xor_sync(0xffffffffu, cnt[c], dd);
+            qs[c] += __shfl_xor_sync(0xffffffffu, qs[c], dd);
+            ql[c] += __shfl_xor_sync(0xffffffffu, ql[c], dd);
+        }
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        unsigned long long* r = reinterpret_cast<unsigned long long*>(rec);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (cnt[c]) atomicAdd(r + 9 + 3 * c, (unsigned long long)cnt[c]);
+            if (qs[c]) atomicAdd(r + 10 + 3 * c, (unsigned long long)qs[c]);
+            if (ql[c]) atomicAdd(r + 11 + 3 * c, (unsigned long long)ql[c]);
+        }
+        if (bad) atomicOr(r + 21, (unsigned long long)bad);
+    }
+}
+
+__global__ void fastq_combine_records_kernel(const long long* recs, const int64_t* ranges, int world, FusedPreds fp, long long* total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) fastq_combine_records(recs, ranges, world, fp.p, fp.n, total);
+}
+cudaError_t fastq_combine_records_launch(const long long* recs, const int64_t* ranges, int world, const exb_predicate* preds, int n_preds,
+                                         long long* total, cudaStream_t st) {
+    FusedPreds fp;
+    fp.n = n_preds;
+    for (int i = 0; i < n_preds; i++) fp.p[i] = preds[i];
+    fastq_combine_records_kernel<<<1, 32, 0, st>>>(recs, ranges, world, fp, total);
+    return cudaGetLastError();
+}
+cudaError_t fastq_candidates_launch(const FastqScanArgs& a, long long* rec, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(rec, 0, 256, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(rec + 5, 0xFF, 8, st);  // no newline yet
+    if (e != cudaSuccess) return e;
+    int64_t blocks = (a.n_tiles + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    fastq_fused_candidates_kernel<<<dim3((unsigned)blocks), dim3(256), 0, st>>>(a, rec);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ launchers

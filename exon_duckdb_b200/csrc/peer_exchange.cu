@@ -14,18 +14,22 @@
 //   [4352, 6400)  aggs  [2][16][ 8 x i64] what a slower peer is still reading (it cannot be two steps ahead: it
 //                                         would need this rank's flag of the step in between)
 //   [6400, 6408)  status u64              1 = a wait timed out (a peer died); sticky
+//   [6528, 6656)  record flags u64[16]    (single-exchange COUNT, see peer_count_fused_kernel)
+//   [8192,16384)  records[2][16][256 B]
 // Steps are numbered from 1 on the host (seq); the buffer is zeroed and the ranks barrier once before step 1.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "exon_b200_internal.h"
+#include "combine_records.cuh"
 
 namespace exb {
 
 constexpr int PX_MAX_WORLD = 16;
 constexpr int PX_GFLAG = 0, PX_RFLAG = 128, PX_BLOCKS = 256, PX_AGGS = PX_BLOCKS + 2 * PX_MAX_WORLD * 128;
 constexpr int PX_STATUS = PX_AGGS + 2 * PX_MAX_WORLD * 64;
-constexpr int PX_BYTES = 8192;
+constexpr int PX_FFLAG = 6528, PX_RECS = 8192;
+constexpr int PX_BYTES = 16384;
 constexpr unsigned long long PX_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;  // a dead peer must not hang the GPU
 
 __device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) {
@@ -104,6 +108,37 @@ __global__ void __launch_bounds__(32 * PX_MAX_WORLD) peer_count_reduce_kernel(ui
     }
 }
 
+// The sharded COUNT with ONE exchange (fastq_scan.cu, fastq_fused_candidates_kernel): warp j stores this rank's 256-byte
+// record into rank j's records[parity][rank], raises the flag, waits for rank j's record in its own buffer; then one
+// thread combines the `world` records -- every rank computes the same global aggregates, so nothing has to be reduced.
+// Replaces peer_allgather_kernel -> fastq_compose_prev_kernel -> fastq_fused_combine_kernel -> peer_count_reduce_kernel.
+__global__ void __launch_bounds__(32 * PX_MAX_WORLD) peer_count_fused_kernel(uint8_t* const* __restrict__ peers, int rank, int world,
+                                                                           const uint8_t* __restrict__ record, const int64_t* __restrict__ ranges,
+                                                                           FusedPreds fp, uint64_t seq, long long* __restrict__ total) {
+    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int parity = (int)(seq & 1);
+    uint8_t* mine = peers[rank];
+    if (j < world) {
+        uint8_t* dst = peers[j] + PX_RECS + (parity * PX_MAX_WORLD + rank) * 256;
+        if (lane < 16) reinterpret_cast<uint4*>(dst)[lane] = reinterpret_cast<const uint4*>(record)[lane];
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_system();
+            st_release_sys_u64(reinterpret_cast<uint64_t*>(peers[j] + PX_FFLAG) + rank, seq);
+            if (!wait_flag(reinterpret_cast<const uint64_t*>(mine + PX_FFLAG) + j, seq)) *reinterpret_cast<volatile uint64_t*>(mine + PX_STATUS) = 1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // the records were written by peers over NVLink: read them past L1 (volatile) after the acquire on their flags
+        __shared__ long long s_recs[PX_MAX_WORLD * 32];
+        const volatile long long* src = reinterpret_cast<const volatile long long*>(mine + PX_RECS + parity * PX_MAX_WORLD * 256);
+        for (int i = 0; i < world * 32; i++) s_recs[i] = src[i];
+        fastq_combine_records(s_recs, ranges, world, fp.p, fp.n, total);
+        if (*reinterpret_cast<volatile uint64_t*>(mine + PX_STATUS) != 0) total[7] = -1;  // exchange failed: poison the check word
+    }
+}
+
 int set_err(int code, const char* fmt, ...);
 
 }  // namespace exb
@@ -133,6 +168,22 @@ int exb_peer_count_reduce(void* const* d_peers, int rank, int world, const void*
                                                                         reinterpret_cast<const uint64_t*>(d_workspace), d_agg, is_last, seq, d_total);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(EXB_ERR_CUDA, "peer_count_reduce launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int exb_peer_count_fused(void* const* d_peers, int rank, int world, const void* d_record, const int64_t* d_ranges, const exb_predicate* preds,
+                         int n_preds, uint64_t seq, int64_t* d_total, void* stream) {
+    if (world < 1 || world > PX_MAX_WORLD || rank < 0 || rank >= world || seq == 0 || n_preds < 0 || n_preds > EXB_MAX_PREDICATES || !d_record ||
+        !d_ranges || !d_total)
+        return set_err(EXB_ERR_ARG, "exb_peer_count_fused: bad arguments (world 1..%d, seq >= 1)", PX_MAX_WORLD);
+    FusedPreds fp;
+    fp.n = n_preds;
+    for (int i = 0; i < n_preds; i++) fp.p[i] = preds[i];
+    peer_count_fused_kernel<<<1, 32 * world, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint8_t* const*>(d_peers), rank, world,
+                                                                        reinterpret_cast<const uint8_t*>(d_record), d_ranges, fp, seq,
+                                                                        reinterpret_cast<long long*>(d_total));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(EXB_ERR_CUDA, "peer_count_fused launch: %s", cudaGetErrorString(e));
     return 0;
 }
 

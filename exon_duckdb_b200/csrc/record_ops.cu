@@ -587,8 +587,7 @@ static cudaError_t gather_span_launch(const uint8_t* buf, SrcFn fn, const int64_
 // (the per-column gathers fetched the file about three times: profiles/r02r_kernel_traffic.txt), and the header bytes
 // the field split reads are the ones the name / description copies need a moment later.
 // Output layout = a6 / a8 of SURVEY 8: per column int64 offsets[n_rows + 1] (exclusive prefix of the lengths) + bytes.
-constexpr int SP_ROWS = 128, SP_THREADS = 256;
-constexpr int SP_WIN = 32 << 10;  // bytes of input a block stages in shared memory
+constexpr int SP_ROWS = 256, SP_THREADS = 256;
 struct alignas(128) SplitDesc {  // one per block of rows: its totals, then its inclusive prefix
     unsigned long long agg[4];
     unsigned long long incl[4];
@@ -610,6 +609,8 @@ struct SplitArgs {
     const ScanResult* scan;   // optional: CR LF knowledge of the scan (see fastq_fields_kernel)
     int map_mode;             // kMap: EXB_MAP_* applied to column 2 (sequence)
     int rows_per_block;       // <= SP_ROWS: long records get fewer rows per block so that the grid stays full
+    int win_bytes;            // bytes of input a block may stage in (dynamic) shared memory; 0 = read global memory
+    int prefetch;             // global path: prefetch the block's input window into L2 before the field split
     unsigned long long* bad;  // kMap: min over invalid bytes of (output position << 8 | byte)
 };
 
@@ -624,7 +625,7 @@ __global__ void __launch_bounds__(SP_THREADS, 5) fastq_split_kernel(FqLines<OffT
     __shared__ uint4 s_below[17];                // s_below[k]: 0xFF in the first k bytes of a 16-byte chunk
     __shared__ unsigned int s_blk;
     __shared__ int64_t s_w[2];                   // the block's input window [w0, w1)
-    __shared__ __align__(16) uint8_t s_win[SP_WIN + 64];
+    extern __shared__ __align__(16) uint8_t s_win[];  // a.win_bytes + 64
     __shared__ uint8_t s_lut[kMap ? 256 : 1];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     unsigned long long bad = ~0ull;
@@ -659,11 +660,14 @@ __global__ void __launch_bounds__(SP_THREADS, 5) fastq_split_kernel(FqLines<OffT
         if (t == 32) s_w[1] = (int64_t)L.line_end[4 * (blk * RPB + rows_here) - 1] + 1;
         __syncthreads();
         const int64_t w0a = s_w[0] & ~(int64_t)15, w1 = s_w[1] > L.n ? L.n : s_w[1];
-        const bool use_win = w1 - w0a <= SP_WIN;
+        const bool use_win = w1 - w0a <= a.win_bytes;
         if (use_win) {
             const int chunks = (int)((w1 - w0a + 15 + 32) >> 4);  // 32 bytes of look-ahead for the 16-byte reads at a row's end
             for (int k = t; k < chunks; k += SP_THREADS) cp_async16(s_win + 16 * k, buf + w0a + 16 * (int64_t)k, 16);
             cp_async_commit();
+        }
+        else if (a.prefetch) {  // the block's window will be read piecemeal below: start its trip from DRAM to L2 now
+            for (int64_t o = w0a + 128 * (int64_t)t; o < w1; o += 128 * SP_THREADS) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(buf + o));
         }
         // (the input carries 64 bytes of slack behind n, so the look-ahead never leaves the allocation)
         const uint8_t* __restrict__ rd = use_win ? (const uint8_t*)s_win - w0a : buf;  // rd[file offset] = that byte
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(SP_THREADS, 5) fastq_split_kernel(FqLines<OffT
                 all += v;
             }
             tot[c] = all;
-            s_loc[c][t] = (int64_t)(before + incl[c] - len[c]);
+            s_loc[c][t] = (int64_t)(before + incl[c] - len[c]);  // threads past the block's rows write the total
             if (t == 0) {
                 s_loc[c][SP_ROWS] = (int64_t)all;
                 unsigned long long mx = 0;
@@ -948,10 +952,14 @@ static cudaError_t split_launch_t(const uint8_t* buf, int64_t begin, int64_t n, 
     a.scan = scan;
     a.map_mode = map_mode;
     a.bad = bad;
-    // about 28 KB of input per block, so that its window fits the shared-memory stage: ~80 Illumina records; long
-    // records (ONT) get the minimum and read global memory
+    // A block takes about 110 KB of input (256 Illumina records; long records get fewer rows so that the grid stays full).
+    // EXB_SPLIT_WIN_KB > 0 stages each block's window in shared memory instead (fewer rows per block, sized to fit).
+    static const int win_kb = getenv("EXB_SPLIT_WIN_KB") ? atoi(getenv("EXB_SPLIT_WIN_KB")) : 0;
+    static const int prefetch = getenv("EXB_SPLIT_PREFETCH") ? atoi(getenv("EXB_SPLIT_PREFETCH")) : 1;
     const int64_t avg = n_rows > 0 ? (n - begin) / n_rows + 1 : 1;
-    int64_t rpb = (28 << 10) / avg;
+    a.win_bytes = win_kb > 0 ? (win_kb << 10) : 0;
+    a.prefetch = prefetch;
+    int64_t rpb = a.win_bytes ? (int64_t)(a.win_bytes * 0.85) / avg : (112 << 10) / avg;
     rpb = rpb < SP_MIN_ROWS ? SP_MIN_ROWS : (rpb > SP_ROWS ? SP_ROWS : rpb);
     a.rows_per_block = (int)rpb;
     const int64_t n_blocks = (n_rows + rpb - 1) / rpb;
@@ -963,8 +971,19 @@ static cudaError_t split_launch_t(const uint8_t* buf, int64_t begin, int64_t n, 
     const int64_t machine = 148 * 5;  // 5 resident blocks of 256 threads per SM
     if (blocks > machine) blocks = machine;
     if (blocks < 1) blocks = 1;
-    if (bad) fastq_split_kernel<OffT, true><<<(unsigned)blocks, SP_THREADS, 0, st>>>(L, a);
-    else fastq_split_kernel<OffT, false><<<(unsigned)blocks, SP_THREADS, 0, st>>>(L, a);
+    const size_t dyn = a.win_bytes ? (size_t)a.win_bytes + 64 : 16;
+    if (dyn > 16) {  // beyond the 48 KB default (static arrays included) the kernel must opt in
+        cudaFuncSetAttribute(fastq_split_kernel<OffT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(fastq_split_kernel<OffT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    }
+    int per_sm = 5;
+    if (a.win_bytes) {
+        per_sm = (int)((227 << 10) / ((int64_t)dyn + 18 * 1024));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 5 ? 5 : per_sm);
+    }
+    if (blocks > 148 * per_sm) blocks = 148 * per_sm;
+    if (bad) fastq_split_kernel<OffT, true><<<(unsigned)blocks, SP_THREADS, dyn, st>>>(L, a);
+    else fastq_split_kernel<OffT, false><<<(unsigned)blocks, SP_THREADS, dyn, st>>>(L, a);
     return cudaGetLastError();
 }
 cudaError_t fastq_split_launch(const uint8_t* buf, int64_t begin, int64_t n, const void* line_end, bool wide, int64_t n_rows, uint32_t mask,

@@ -24,6 +24,7 @@ LocalGroup, which holds G shards in one process.  The composition rules are pure
 so the CPU tests drive them with world_size 2 over gloo without a GPU.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -35,6 +36,7 @@ N_LS = 5  # LS0..LS0+4: offsets of the first five line starts inside the shard (
 STATE_WORDS = LS0 + N_LS
 HALO = 16  # bytes of the file kept in front of a shard's first byte (the scan looks one byte back for CRLF)
 RESULT_WORDS = 16  # the 128-byte result block of a scan as int64 words
+RECORD_WORDS = 32  # the 256-byte record of the single-exchange COUNT (exb_fastq_scan_filter_candidates)
 
 
 def byte_range(n_bytes, rank, world):
@@ -290,6 +292,29 @@ class ShardedFastqCount:
         self.world = len(self.ranges)
         self.d_ranges = torch.from_numpy(self.ranges.copy()).to(dev)
         self.blocks = torch.zeros(self.world * RESULT_WORDS, dtype=torch.int64, device=dev)
+        # single-exchange flavour: this shard's 256-byte record, and room for everybody's
+        self.record = torch.zeros(RECORD_WORDS, dtype=torch.int64, device=dev)
+        self.records = torch.zeros(self.world * RECORD_WORDS, dtype=torch.int64, device=dev)
+        self.fused_exchange = os.environ.get("EXB_EXCHANGE_FUSED", "1") != "0"
+
+    # -- the single-exchange flavour: K2 for all four phases BEFORE the exchange, then one all-gather of 256-byte records
+    def scan_candidates(self):
+        """K1 + line offsets + candidates kernel; returns the shard's record (int64[32], device)."""
+        from . import device as D
+
+        s = self.shard
+        _lib.check(_lib.lib().exb_fastq_scan_filter_candidates(D._ptr(s.buf), s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.prov), self.arr, self.k,
+                                                               D._ptr(self.record), D._ptr(self.c.ws), self.c.ws.numel(), D._stream()))
+        self.c._res = None
+        return self.record
+
+    def combine(self, records):
+        """records: int64[world * 32] device tensor, every shard's record in shard order -> self.total (global aggregates)."""
+        from . import device as D
+
+        _lib.check(_lib.lib().exb_fastq_combine_records(D._ptr(records), D._ptr(self.d_ranges), self.world, self.arr, self.k, D._ptr(self.total),
+                                                        D._stream()))
+        return self.total
 
     # -- the phases (tests drive them shard by shard through a LocalGroup-style loop; step() chains them for a TorchGroup)
     def scan(self):
@@ -341,6 +366,18 @@ class ShardedFastqCount:
         from . import device as D
 
         g = self.group
+        if self.fused_exchange and stage_marks is None:
+            # K1 + offsets + K2 for all four phases, then ONE exchange after which every rank holds the global aggregates
+            rec = self.scan_candidates()
+            if after_scan is not None:
+                after_scan()
+            if isinstance(g, PeerGroup):  # 6 launches of this library per step, one wait on NVLink flags, no NCCL
+                g.seq += 1
+                _lib.check(_lib.lib().exb_peer_count_fused(g.d_peers, g.rank, g.world, D._ptr(rec), D._ptr(self.d_ranges), self.arr, self.k, g.seq,
+                                                           D._ptr(self.total), D._stream()))
+                return self.total
+            g.dist.all_gather_into_tensor(self.records, rec, group=g.group)
+            return self.combine(self.records)
         blk = self.scan()
         if after_scan is not None:
             after_scan()

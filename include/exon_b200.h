@@ -370,6 +370,22 @@ EXB_API int exb_fastq_scan_resolve(int64_t begin, int64_t n, int is_final, const
 EXB_API int exb_fastq_scan_filter_resolve(int64_t begin, int64_t n, int is_final, const void *d_prev_workspace,
                                           const exb_predicate *preds, int n_preds, int64_t *d_agg, int accumulate,
                                           void *d_workspace, int64_t workspace_bytes, void *stream);
+/* Byte-range sharded COUNT with ONE exchange.  exb_fastq_scan_filter_candidates = byte pass + line offsets + a K2 that
+ * runs for all four phases at once: d_record (256 bytes, int64[32]) receives the range's line count, its open last line,
+ * four candidate aggregate sets (one per possible phase of the range's first line, that line excluded) and the description
+ * of the first line itself -- the only line whose length / Phred sum / first byte depend on the predecessors.  The records
+ * of all shards (in shard order, 256 bytes apart) + d_ranges (as for exb_fastq_compose_prev) give the aggregates of the
+ * whole file on EVERY rank without a second collective: exb_fastq_combine_records locally (after any all-gather), or
+ * exb_peer_count_fused = all-gather over NVLink peer memory + combine in one launch.
+ *   d_total (int64[8]): [0] passing records [3] their Phred sums [4] their lengths [6] lines of the file mod 4
+ *   [7] 1 = a line start contradicts its phase (malformed), -1 = a peer did not answer.
+ * d_prev_workspace of the candidates call = the PROVISIONAL predecessor (open_line_start = begin), as for
+ * exb_fastq_scan_filter_begin.  Replaces begin -> allgather -> compose -> resolve -> reduce (5 launches, 2 flag waits). */
+EXB_API int exb_fastq_scan_filter_candidates(const void *d_buf, int64_t begin, int64_t n, int is_final,
+                                             const void *d_prev_workspace, const exb_predicate *preds, int n_preds,
+                                             void *d_record, void *d_workspace, int64_t workspace_bytes, void *stream);
+EXB_API int exb_fastq_combine_records(const void *d_records, const int64_t *d_ranges, int world, const exb_predicate *preds,
+                                      int n_preds, int64_t *d_total, void *stream);
 /* Step 2 on the device (no host round trip): d_blocks = the result blocks of all `world` shards in shard order
  * (128 bytes each, e.g. the output of an NCCL all-gather of the first 128 bytes of each shard's workspace), d_ranges =
  * int64[world][3] {lo, hi, begin} of every shard (file offsets of its range; local offset of byte lo).  Writes the true
@@ -392,6 +408,8 @@ EXB_API int64_t exb_peer_bytes(void);
 EXB_API int64_t exb_peer_blocks_offset(uint64_t seq);
 EXB_API int exb_peer_allgather_block(void *const *d_peers, int rank, int world, const void *d_block, uint64_t seq,
                                      void *stream);
+EXB_API int exb_peer_count_fused(void *const *d_peers, int rank, int world, const void *d_record, const int64_t *d_ranges,
+                                 const exb_predicate *preds, int n_preds, uint64_t seq, int64_t *d_total, void *stream);
 EXB_API int exb_peer_count_reduce(void *const *d_peers, int rank, int world, const void *d_workspace,
                                   const int64_t *d_agg, int is_last, uint64_t seq, int64_t *d_total, void *stream);
 

@@ -70,12 +70,13 @@ def c2_paths(rep, buf, reads, iters=10, full=True):
     n = buf.numel()
     preds = [("mean_quality", ">", 30.0)]
     rec_cap = reads + 1024
-    if full:
+    if full and not os.environ.get("EXB_PATHS_SPLIT_ONLY"):
         c = D.fastq_scan_filter(buf, preds)
         assert c.validate() == reads
         med, best = timeit(lambda: D.fastq_scan_filter(buf, preds, out=c), iters)
         rep.add("C2 fused scan+filter COUNT (exb_fastq_scan_filter)", n, med, best, n)
-    variants = ((_lib.F_QUAL, "F_QUAL"), (_lib.F_SEQ | _lib.F_QUAL, "F_SEQ|F_QUAL"), (_lib.F_LINES | _lib.F_SEQ | _lib.F_QUAL, "F_LINES|F_SEQ|F_QUAL"),
+    split_only = bool(os.environ.get("EXB_PATHS_SPLIT_ONLY"))
+    variants = () if split_only else ((_lib.F_QUAL, "F_QUAL"), (_lib.F_SEQ | _lib.F_QUAL, "F_SEQ|F_QUAL"), (_lib.F_LINES | _lib.F_SEQ | _lib.F_QUAL, "F_LINES|F_SEQ|F_QUAL"),
                 (_lib.F_LINES, "F_LINES")) if full else ((_lib.F_SEQ | _lib.F_QUAL, "F_SEQ|F_QUAL"),)
     for flags, nm in variants:
         s = D.fastq_scan(buf, flags, rec_cap=rec_cap)
@@ -91,11 +92,12 @@ def c2_paths(rep, buf, reads, iters=10, full=True):
                 D.fastq_filter(s, rec_cap, preds, agg=agg, device_count=True)
             med, best = timeit(scan_filter, iters)
             rep.add("C2 general scan F_QUAL + exb_fastq_filter COUNT", n, med, best, n)
-    del s
-    tab = D.fastq_table(buf, columns=["name", "sequence"], preds=preds)
-    out_b = tab["name"].data.numel() + tab["sequence"].data.numel() + 16 * tab["__n_rows__"]
-    med, best = timeit(lambda: D.fastq_table(buf, columns=["name", "sequence"], preds=preds), iters=5)
-    rep.add("C2 filter projecting name+sequence (fastq_table)", n + out_b, med, best, n, "includes host syncs for sizes")
+    if not split_only:
+        del s
+        tab = D.fastq_table(buf, columns=["name", "sequence"], preds=preds)
+        out_b = tab["name"].data.numel() + tab["sequence"].data.numel() + 16 * tab["__n_rows__"]
+        med, best = timeit(lambda: D.fastq_table(buf, columns=["name", "sequence"], preds=preds), iters=5)
+        rep.add("C2 filter projecting name+sequence (fastq_table)", n + out_b, med, best, n, "includes host syncs for sizes")
     tab = D.fastq_table(buf)
     out_b = sum(tab[k].data.numel() for k in D.FASTQ_COLUMNS) + 32 * tab["__n_rows__"]
     med, best = timeit(lambda: D.fastq_table(buf), iters=5)
@@ -130,7 +132,7 @@ def c2_paths(rep, buf, reads, iters=10, full=True):
     rep.add("C2 column split alone (exb_fastq_split: fields + offsets + 4 columns)", out_b + (out_b - 32 * reads) + 16 * reads, med, best, n,
             "reads 4 B per line + the record bytes, writes offsets + columns")
     del data, offs, valid, scratch, s
-    if full:
+    if full and not split_only:
         seq = tab["sequence"]
         qual = tab["quality_scores"]
         med, best = timeit(lambda: D.gc_content(seq), iters)
