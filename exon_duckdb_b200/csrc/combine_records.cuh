@@ -15,11 +15,17 @@ __device__ __forceinline__ void fastq_combine_records(const long long* __restric
     long long cnt = 0, qs = 0, ql = 0;
     bool bad = false;
     unsigned long long lines = 0;
-    long long ostart = ranges[0], os = 0;           // the line open at the first byte of shard j: start (file offset), byte sum so far
-    uint32_t oflags = (uint32_t)recs[8] & 3u;       // ... and the '@' / '+' flags of its first byte
+    long long ostart = ranges[0], os = 0;  // the line open at the first byte of shard j: start (file offset), byte sum so far
+    // '@' / '+' flags of the byte at file offset p: the shard that holds the byte knows it -- as its own first byte, or as the
+    // first byte of the line that is open after its last newline (p is always one of the two)
+    auto flags_at = [&](long long p) -> uint32_t {
+        for (int m = 0; m < world; m++)
+            if (ranges[3 * m] <= p && p < ranges[3 * m + 1]) return (uint32_t)(p == ranges[3 * m] ? recs[32 * m + 8] : recs[32 * m + 3]) & 3u;
+        return 0u;
+    };
     for (int j = 0; j < world; j++) {
         const long long* r = recs + 32 * j;
-        const long long lo = ranges[3 * j], hi = ranges[3 * j + 1], begin = ranges[3 * j + 2];
+        const long long lo = ranges[3 * j], begin = ranges[3 * j + 2];
         const int c = (int)(lines & 3);
         cnt += r[9 + 3 * c];
         qs += r[10 + 3 * c];
@@ -31,7 +37,7 @@ __device__ __forceinline__ void fastq_combine_records(const long long* __restric
             const long long cr = len > 0 ? r[6] : 0;
             len -= cr;
             if ((c & 1) == 0) {
-                if (!(oflags & (c == 0 ? 2u : 1u))) bad = true;
+                if (!(flags_at(ostart) & (c == 0 ? 2u : 1u))) bad = true;
             } else if (c == 3) {
                 const long long q1 = r[7] + os - 13 * cr - 33 * len;
                 bool ok = true;
@@ -48,9 +54,6 @@ __device__ __forceinline__ void fastq_combine_records(const long long* __restric
             lines += (unsigned long long)r[0];
             ostart = lo + (r[1] - begin);
             os = r[2];
-            // the shard that holds the open line's first byte knows what it is; a line that starts with the next shard
-            // takes that shard's first-byte flags
-            oflags = ostart < hi ? (uint32_t)r[3] & 3u : (j + 1 < world ? (uint32_t)recs[32 * (j + 1) + 8] & 3u : 0u);
         } else {
             os += r[2];  // no newline: the whole shard belongs to the open line
         }

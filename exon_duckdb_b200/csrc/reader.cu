@@ -455,17 +455,100 @@ struct Parser {
 
 
 // ------------------------------------------------------------------ buffers
-struct DBuf {  // growable device buffer
+// Device buffers are recycled through a process-wide pool, one per device: cudaMalloc / cudaFree are synchronising driver
+// calls that took anything from 0.1 ms to 1 s on the GPU box (VM), once per buffer per query -- a COUNT(*) whose pipeline
+// ran for 150 ms was observed to take 0.4-1.4 s because of them (profiles/round2_e2e_stalls.txt).
+struct DevPool {
+    struct Slab {
+        void* p;
+        int64_t cap;
+    };
+    std::mutex mu;
+    std::vector<Slab> idle[16];
+    int64_t idle_bytes[16] = {0};
+    static constexpr int64_t kMaxIdle = 3ll << 30;  // per device
+    static DevPool& get() {
+        static DevPool* p = new DevPool();  // never destroyed: freeing at exit would race the CUDA runtime's teardown
+        return *p;
+    }
+    static int device() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+        return d < 0 || d >= 16 ? 0 : d;
+    }
+    void* take(int64_t want, int64_t* cap_out) {
+        const int d = device();
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            int best = -1;
+            for (int i = 0; i < (int)idle[d].size(); i++)
+                if (idle[d][i].cap >= want && idle[d][i].cap <= 4 * want + (1 << 20) && (best < 0 || idle[d][i].cap < idle[d][best].cap)) best = i;
+            if (best >= 0) {
+                Slab sl = idle[d][best];
+                idle[d].erase(idle[d].begin() + best);
+                idle_bytes[d] -= sl.cap;
+                *cap_out = sl.cap;
+                return sl.p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, (size_t)want) != cudaSuccess) {
+            cudaGetLastError();
+            trim(d, 0);  // give the idle slabs back and try once more
+            if (cudaMalloc(&p, (size_t)want) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        *cap_out = want;
+        return p;
+    }
+    void give(void* p, int64_t cap) {
+        if (!p) return;
+        const int d = device();
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (idle_bytes[d] + cap <= kMaxIdle) {
+                idle[d].push_back(Slab{p, cap});
+                idle_bytes[d] += cap;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+    void trim(int d, int64_t keep) {
+        std::vector<Slab> drop;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            while (idle_bytes[d] > keep && !idle[d].empty()) {
+                drop.push_back(idle[d].back());
+                idle_bytes[d] -= idle[d].back().cap;
+                idle[d].pop_back();
+            }
+        }
+        for (Slab& sl : drop) cudaFree(sl.p);
+    }
+};
+struct DBuf {  // growable device buffer (the device thread of a reader owns it: its current device is the buffer's device)
     void* p = nullptr;
     int64_t cap = 0;
-    ~DBuf() { if (p) cudaFree(p); }
+    ~DBuf() { release(); }
+    void release() {
+        if (p) DevPool::get().give(p, cap);
+        p = nullptr;
+        cap = 0;
+    }
     bool need(int64_t n) {
         if (n <= cap) return true;
-        if (p) cudaFree(p);
-        p = nullptr;
+        if (p) cudaDeviceSynchronize();  // growing (rare): work in flight may still use the old slab, and cudaFree no longer waits for it
+        release();
         int64_t want = std::max<int64_t>(n + n / 4 + 256, 4096);
-        if (cudaMalloc(&p, (size_t)want) != cudaSuccess) { cap = 0; cudaGetLastError(); return false; }
-        cap = want;
+        want = (want + 65535) & ~(int64_t)65535;
+        p = DevPool::get().take(want, &cap);
+        if (!p) {
+            cap = 0;
+            return false;
+        }
         return true;
     }
     template <typename T> T* as() { return reinterpret_cast<T*>(p); }
@@ -577,6 +660,9 @@ struct IoPool {
         // three quarters of the cores (at most 12): 8 threads already copy faster than the PCIe link takes the bytes on the
         // 16-core box, 12 are steadier, and the device thread and the host's consumers need cores to keep the GPU fed
         nthreads = hw > 0 ? std::max(2, std::min(hw * 3 / 4, 12)) : 4;
+        // one process per GPU on one box (torchrun sets LOCAL_WORLD_SIZE): the processes share the cores
+        if (const char* lws = getenv("LOCAL_WORLD_SIZE"))
+            if (atoi(lws) > 1 && hw > 0) nthreads = std::max(2, std::min(nthreads, hw * 3 / 4 / atoi(lws)));
         if (const char* e = getenv("EXON_B200_IO_THREADS"))
             if (atoi(e) > 0) nthreads = std::min(atoi(e), 64);
         for (int i = 0; i < nthreads - 1; i++) std::thread([this] { work(); }).detach();  // the caller is the last worker
@@ -1029,9 +1115,7 @@ struct Reader {
                         &d_valid, &d_pass, &d_selscratch, &d_sel, &d_lens2, &d_starts2, &d_valid2, &d_off, &d_cst, &d_hdr_start, &d_hdr_end,
                         &d_seq_off, &d_gc_prefix, &d_seq, &d_err, &d_info, &d_qtmp, &d_bad, &outs[0].d_meta, &outs[0].d_data, &outs[1].d_meta,
                         &outs[1].d_data}) {
-            if (b->p) cudaFree(b->p);
-            b->p = nullptr;
-            b->cap = 0;
+            b->release();
         }
         scratch.clear();
         for (int i = 0; i < 2; i++) {
@@ -1156,7 +1240,9 @@ struct Reader {
             }
             bool eof = false;
             while (err.empty() && !eof && !stopping) {
-                const int64_t want = block_bytes.load();
+                // block edges sit on multiples of 16 in file coordinates (the first block of a shard may be a little shorter):
+                // the chained COUNT scan of dev_main_fused needs that of every range but the first
+                const int64_t want = block_bytes.load() - (pos & 15);
                 Block b;
                 double t0 = now();
                 b.h = pool->get(want + 64);
@@ -1852,6 +1938,152 @@ struct Reader {
         free_device();
     }
 
+    // ---- COUNT(*) [WHERE predicates on the quality line]: the C2 query.  Nothing per record is needed, so the chunks are
+    // not re-cut at record boundaries at all: block k goes to the device and is scanned as the next RANGE of a chained
+    // scan (exb_fastq_scan_filter: the fused byte pass judges every quality line as it is emitted; the previous range's
+    // 128-byte result block carries the open line and the line count across the edge), the aggregates accumulate on the
+    // device, and the host looks at them once per file.  No carry copy, no field split, no selection, no per-chunk sync:
+    // the device thread costs one H2D copy + one ~40 us scan per 64 MiB, so the pipeline runs at the rate of its slowest
+    // copy (page cache -> pinned, or PCIe).
+    bool fused_count_plan(std::vector<exb_predicate>* out) const {
+        if (format != 2 || !count_only.load()) return false;
+        if (getenv("EXON_B200_NO_FUSED_COUNT")) return false;
+        out->clear();
+        if (root < 0) return true;
+        // AND-only tree of numeric leaves on the quality line
+        std::vector<int> stack{root};
+        while (!stack.empty()) {
+            const Node& nd = nodes[stack.back()];
+            stack.pop_back();
+            if (nd.kind == N_AND) {
+                stack.push_back(nd.lhs);
+                stack.push_back(nd.rhs);
+            } else if (nd.kind == N_NUM && (nd.field == EXB_P_MEAN_QUALITY || nd.field == EXB_P_QUAL_LEN)) {
+                out->push_back(exb_predicate{nd.field, nd.op, nd.value});
+            } else {
+                return false;
+            }
+        }
+        return out->size() <= EXB_MAX_PREDICATES;
+    }
+    void dev_main_fused(std::vector<exb_predicate> preds) {
+        DBuf d_chunk[2], d_wsx[2], d_agg;
+        struct InFlight {
+            HBuf* h;
+            cudaEvent_t ev;
+        };
+        std::deque<InFlight> inflight;  // pinned blocks whose H2D copy may still be running
+        std::vector<cudaEvent_t> ev_pool;
+        auto release_done = [&](size_t keep) {
+            while (inflight.size() > keep) {
+                cudaEventSynchronize(inflight.front().ev);
+                pool->put(inflight.front().h);
+                ev_pool.push_back(inflight.front().ev);
+                inflight.pop_front();
+            }
+        };
+        auto finish = [&](const std::string& err, int64_t count) {
+            cudaStreamSynchronize(st);
+            release_done(0);
+            for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+            for (DBuf* b : {&d_chunk[0], &d_chunk[1], &d_wsx[0], &d_wsx[1], &d_agg}) b->release();
+            free_device();
+            if (err.empty() && count > 0) {
+                OutItem c;
+                c.counted = count;
+                outq.push(std::move(c));
+            }
+            OutItem e;
+            e.end = true;
+            e.error = err;
+            outq.push(std::move(e));
+        };
+        {
+            const double ti = now();
+            const bool ok = init_device();
+            t_init = now() - ti;
+            if (!ok) return finish(derr, 0);
+        }
+        if (!d_agg.need(64) || !cu(cudaMemsetAsync(d_agg.p, 0, 64, st), "memset")) return finish(derr.empty() ? "out of device memory" : derr, 0);
+        int k = 0;
+        const void* prev_ws = nullptr;
+        int64_t prev_tail = -1;  // which chunk buffer holds the previous range (its last 16 bytes are the next range's halo)
+        int64_t prev_end = 0;    // bytes of it
+        while (!stopping) {
+            Block b;
+            double t0 = now();
+            const bool popped = inq.pop(b);
+            t_dev_pop += now() - t0;
+            if (!popped) break;
+            if (b.end) {
+                if (!b.error.empty()) return finish(b.error, 0);
+                break;
+            }
+            if (b.raw_len == 0 && !prev_ws) {  // empty file
+                pool->put(b.h);
+                continue;
+            }
+            t0 = now();
+            NvtxRange nv("exb:count_chunk");
+            const int i = k & 1;
+            const int64_t n = b.raw_len, pos = b.raw_file_pos;
+            const int64_t ws_bytes = exb_scan_workspace_bytes(n + 64);
+            if (!d_chunk[i].need(n + 128) || !d_wsx[i].need(ws_bytes)) {
+                pool->put(b.h);
+                return finish("out of device memory", 0);
+            }
+            // data at a 16-aligned address + (pos % 16), so that the buffer viewed from file offset 0 is 16-byte aligned;
+            // the 16 bytes in front of it are the end of the previous range (the scan looks one byte back for CR LF)
+            uint8_t* data = d_chunk[i].as<uint8_t>() + 32 + (pos & 15);
+            bool ok = true;
+            if (prev_ws && prev_tail >= 0) {
+                const int64_t h = std::min<int64_t>(16, prev_end);
+                ok = cu(cudaMemcpyAsync(data - h, d_chunk[prev_tail].as<uint8_t>() + 32 + ((pos - prev_end) & 15) + prev_end - h, (size_t)h,
+                                        cudaMemcpyDeviceToDevice, st),
+                        "D2D halo");
+            }
+            if (ok && n) ok = cu(cudaMemcpyAsync(data, b.h->p, (size_t)n, cudaMemcpyHostToDevice, st), "H2D");
+            cudaEvent_t ev = nullptr;
+            if (!ev_pool.empty()) {
+                ev = ev_pool.back();
+                ev_pool.pop_back();
+            } else if (ok) {
+                ok = cu(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+            }
+            if (ok) ok = cu(cudaEventRecord(ev, st), "record");
+            if (!ok) {
+                pool->put(b.h);
+                return finish(derr, 0);
+            }
+            inflight.push_back(InFlight{b.h, ev});
+            const uint8_t* base = data - pos;  // base[file offset] = that byte
+            if (!rc(exb_fastq_scan_filter(base, pos, pos + n, b.eof ? 1 : 0, prev_ws, preds.empty() ? nullptr : preds.data(), (int)preds.size(),
+                                          d_agg.as<int64_t>(), 1, d_wsx[i].p, d_wsx[i].cap, st)))
+                return finish(derr, 0);
+            prev_ws = d_wsx[i].p;
+            prev_tail = i;
+            prev_end = n;
+            bytes_done.fetch_add(n);
+            release_done(2);
+            k++;
+            if (b.eof) {  // the file (or shard) ends here: its line count and error marks, once per file
+                exb_scan_result res;
+                if (!queue_small(0, prev_ws, (int)(sizeof(exb_scan_result) / 8)) || !wait_small()) return finish(derr, 0);
+                memcpy(&res, small(0), sizeof(res));
+                res.err_pos = ~res.err_pos;
+                const std::string& fname = files[b.file_idx];
+                if (res.err_pos != ~0ull) return finish("invalid FASTQ record in " + fname + shard_note(), 0);
+                if (res.total_lines % 4 != 0) return finish("unexpected EOF in FASTQ record of " + fname + shard_note(), 0);
+                prev_ws = nullptr;  // the next file starts a new chain
+                prev_tail = -1;
+            }
+            t_dev_work += now() - t0;
+        }
+        if (stopping) return finish("", 0);
+        if (!queue_small(16, d_agg.p, 8) || !wait_small()) return finish(derr, 0);
+        finish("", small(16)[0]);
+    }
+
     // ------------------------------------------------------------------ caller (under call_mu)
     // make rows available; false = end of stream or error (check `error`)
     bool advance() {
@@ -1862,9 +2094,11 @@ struct Reader {
                 return false;
             }
             started = true;
-            block_bytes.store(chunk_bytes);
+            block_bytes.store(std::max<int64_t>(chunk_bytes & ~(int64_t)15, 4096));
             io_thread = std::thread([this] { io_main(); });
-            dev_thread = std::thread([this] { dev_main(); });
+            std::vector<exb_predicate> fused_preds;
+            if (fused_count_plan(&fused_preds)) dev_thread = std::thread([this, fused_preds] { dev_main_fused(fused_preds); });
+            else dev_thread = std::thread([this] { dev_main(); });
         }
         while (next_row >= rows) {
             rows = next_row = 0;

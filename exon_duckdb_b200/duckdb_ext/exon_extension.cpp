@@ -304,7 +304,8 @@ static unique_ptr<GlobalTableFunctionState> ScanInitGlobal(ClientContext &contex
 	}
 	// one consumer per device pipeline is enough to hand out pointers; a lone pipeline gets a few so that whatever sits
 	// above the scan (string functions, aggregates) runs on several cores
-	state->threads_per_reader = n_readers == 1 ? 4 : (n_readers == 2 ? 2 : 1);
+	const idx_t cores = MaxValue<idx_t>(std::thread::hardware_concurrency(), 1);
+	state->threads_per_reader = n_readers == 1 ? MaxValue<idx_t>(2, MinValue<idx_t>(8, cores / 2)) : (n_readers == 2 ? 2 : 1);
 
 	if (!any_column) { // COUNT(*): arrow_conversion.cpp:813-816 is the reference's "row id only" case
 		state->count_only = true;

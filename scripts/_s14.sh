@@ -1,0 +1,17 @@
+set -x
+mkdir -p gpurun_out/s14
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/s14/gputest.txt 2>&1
+tail -8 gpurun_out/s14/gputest.txt
+EXON_B200_TRACE=1 python scripts/bench_reader.py --out gpurun_out/s14/reader.json > gpurun_out/s14/reader.txt 2>&1
+grep -v "^exon_b200 reader" gpurun_out/s14/reader.txt
+grep "^exon_b200 reader" gpurun_out/s14/reader.txt | sed -n '3p;8p'
+python bench.py --steps 10 --warmup 3 --no-paths --no-c5 > gpurun_out/s14/bench.json 2> gpurun_out/s14/bench.err
+tail -3 gpurun_out/s14/bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/s14/bench.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step')}, d['roofline']['frac'])
+print('e2e',{k:v for k,v in d.get('e2e',{}).items() if k not in ('note','api')})
+print('pinned',d.get('e2e_pinned_image'))
+PY
+python scripts/bench_duckdb.py --out gpurun_out/s14/duckdb.json 2>&1 | grep PRODUCT | tee gpurun_out/s14/duckdb.txt

@@ -37,12 +37,13 @@ def _sharded_count(data, cuts, dev, preds=PREDS):
             got = j.true_prev.view(torch.int64).cpu().tolist()
             assert (got[0], got[1], got[7], got[8], (got[3] >> 32) & 3) == (want.total_lines, want.open_line_start, want.tail_s, want.tail_g, want.pad)
     # the single-exchange flavour must give the same aggregates: K2 for all four phases before the "all-gather", one combine
-    recs = torch.cat([j.scan_candidates().clone() for j in jobs])
-    fused = jobs[-1].combine(recs).clone()
+    jobs2 = [dist.ShardedFastqCount(s, preds, None, ranges=ranges) for s in shards]  # (own workspaces: `jobs` keep their results)
+    recs = torch.cat([j.scan_candidates().clone() for j in jobs2])
+    fused = jobs2[-1].combine(recs).clone()
     assert bool(fused[7]) == bool(total[7]) and int(fused[6]) == int(total[6]), (fused.tolist(), total.tolist(), cuts)
     if not bool(total[7]):  # (a malformed file is an error either way; the partial sums are unspecified)
         assert fused[[0, 3, 4]].tolist() == total[[0, 3, 4]].tolist(), (fused.tolist(), total.tolist(), cuts)
-    assert jobs[0].combine(recs).tolist() == fused.tolist()
+    assert jobs2[0].combine(recs).tolist() == fused.tolist()
     return total, jobs
 
 
