@@ -517,7 +517,7 @@ def main():
             gbuf = sharded = shard = whole = None
         torch.cuda.empty_cache()
         total_gb = float(os.environ.get("EXB_BENCH_C5_GB", "100"))
-        R5 = int(total_gb * 1e9 / (n_bytes / args.reads) / world)
+        R5 = int(total_gb * 1e9 / (total_bytes / (args.reads * world)) / world)  # the same on every rank
         if world == 1:
             buf5 = synth.gen_device(synth.gen_params("illumina", R5, seed=SEED, len_min=READ_LEN, len_max=READ_LEN), dev)
             shard5 = XD.Shard(buf5, 0, buf5.numel(), 0, True)

@@ -36,6 +36,8 @@
 // with the sequence column = input twice + output once.
 #include <cuda.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "exon_b200_internal.h"
 #include "tma_tile.cuh"
@@ -825,8 +827,19 @@ static cudaError_t launch_fa_tile(FastaScanArgs a, cudaStream_t st) {
     auto kern = fasta_tile_kernel<kCompact>;
     static int ctas_per_sm = 0, n_sm = 0;
     cudaError_t e;
+    // function attributes belong to a device's context: every device a reader runs on opts in once (a multi-GPU scan
+    // launched on device 1 with device 0's settings fails with "invalid argument")
+    static std::atomic<unsigned> attr_done{0};
+    {
+        int cur = 0;
+        if ((e = cudaGetDevice(&cur)) != cudaSuccess) return e;
+        const unsigned bit = 1u << (cur & 31);
+        if (!(attr_done.load() & bit)) {
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+            attr_done.fetch_or(bit);
+        }
+    }
     if (ctas_per_sm == 0) {
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
         int dev = 0, occ = 0, sms = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
@@ -865,10 +878,13 @@ cudaError_t fasta_scan_launch(const FastaScanArgs& a0, int /*flags*/, cudaStream
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     {
         constexpr int smem = FA_WARPS * (WT_BYTES + FaAux::total);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<unsigned> attr_done{0};  // per device, see launch_fa_tile
+        int cur = 0;
+        if ((e = cudaGetDevice(&cur)) != cudaSuccess) return e;
+        const unsigned bit = 1u << (cur & 31);
+        if (!(attr_done.load() & bit)) {
             if ((e = cudaFuncSetAttribute(fasta_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-            attr_set = true;
+            attr_done.fetch_or(bit);
         }
         int64_t blocks = (T + FA_WARPS * 32 - 1) / (FA_WARPS * 32);
         if (blocks > 148 * 8) blocks = 148 * 8;

@@ -42,6 +42,8 @@
 // tile of directory; the fused flavour: input once + 60 B per tile.
 #include <cuda.h>
 
+#include <atomic>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -935,15 +937,32 @@ __global__ void __launch_bounds__(256) fastq_fused_candidates_kernel(const Fastq
         }
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
+    // block-level sum before the global atomics: 13 words shared by every warp of the grid would serialise ~9 k
+    // same-address atomics each (measured: the kernel took twice as long as K2 with one set of atomics per warp)
+    __shared__ long long s_part[8][13];
+    const int warp = threadIdx.x >> 5;
     if (lane == 0) {
-        unsigned long long* r = reinterpret_cast<unsigned long long*>(rec);
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            if (cnt[c]) atomicAdd(r + 9 + 3 * c, (unsigned long long)cnt[c]);
-            if (qs[c]) atomicAdd(r + 10 + 3 * c, (unsigned long long)qs[c]);
-            if (ql[c]) atomicAdd(r + 11 + 3 * c, (unsigned long long)ql[c]);
+            s_part[warp][3 * c] = cnt[c];
+            s_part[warp][3 * c + 1] = qs[c];
+            s_part[warp][3 * c + 2] = ql[c];
         }
-        if (bad) atomicOr(r + 21, (unsigned long long)bad);
+        s_part[warp][12] = (long long)bad;
+    }
+    __syncthreads();
+    if (threadIdx.x < 13) {
+        long long v = 0;
+        if (threadIdx.x < 12) {
+            for (int w = 0; w < 8; w++) v += s_part[w][threadIdx.x];
+        } else {
+            for (int w = 0; w < 8; w++) v |= s_part[w][12];
+        }
+        unsigned long long* r = reinterpret_cast<unsigned long long*>(rec);
+        if (v) {
+            if (threadIdx.x < 12) atomicAdd(r + 9 + threadIdx.x, (unsigned long long)v);
+            else atomicOr(r + 21, (unsigned long long)v);
+        }
     }
 }
 
@@ -988,8 +1007,19 @@ static cudaError_t launch_tile_kernel(FastqScanArgs a, cudaStream_t st) {
     auto kern = fastq_tile_kernel<FLAGS>;
     static int ctas_per_sm = 0, n_sm = 0;  // per template instance; one device type per process
     cudaError_t e;
+    // function attributes belong to a device's context: every device a reader runs on opts in once (a multi-GPU scan
+    // launched on device 1 with device 0's settings fails with "invalid argument")
+    static std::atomic<unsigned> attr_done{0};
+    {
+        int cur = 0;
+        if ((e = cudaGetDevice(&cur)) != cudaSuccess) return e;
+        const unsigned bit = 1u << (cur & 31);
+        if (!(attr_done.load() & bit)) {
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+            attr_done.fetch_or(bit);
+        }
+    }
     if (ctas_per_sm == 0) {
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
         int dev = 0, occ = 0, sms = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;

@@ -129,12 +129,18 @@ __global__ void __launch_bounds__(32 * PX_MAX_WORLD) peer_count_fused_kernel(uin
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        // the records were written by peers over NVLink: read them past L1 (volatile) after the acquire on their flags
-        __shared__ long long s_recs[PX_MAX_WORLD * 32];
+    // the records were written by peers over NVLink: every thread fetches a few words past L1 (volatile) after the acquire on
+    // their flags (one thread reading all 32 x world words one after the other cost ~40 us), then one thread combines
+    __shared__ long long s_recs[PX_MAX_WORLD * 32];
+    __shared__ int64_t s_ranges[PX_MAX_WORLD * 3];
+    {
         const volatile long long* src = reinterpret_cast<const volatile long long*>(mine + PX_RECS + parity * PX_MAX_WORLD * 256);
-        for (int i = 0; i < world * 32; i++) s_recs[i] = src[i];
-        fastq_combine_records(s_recs, ranges, world, fp.p, fp.n, total);
+        for (int i = threadIdx.x; i < world * 32; i += blockDim.x) s_recs[i] = src[i];
+        for (int i = threadIdx.x; i < world * 3; i += blockDim.x) s_ranges[i] = ranges[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fastq_combine_records(s_recs, s_ranges, world, fp.p, fp.n, total);
         if (*reinterpret_cast<volatile uint64_t*>(mine + PX_STATUS) != 0) total[7] = -1;  // exchange failed: poison the check word
     }
 }

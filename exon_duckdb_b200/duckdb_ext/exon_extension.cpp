@@ -204,8 +204,7 @@ static string FilterToString(const TableFilter &filter, const string &column_nam
 	}
 }
 
-// How many device pipelines a scan gets: `gpus := n` if given, else every visible device as long as each one is left with
-// at least 256 MiB (a smaller share does not amortise a pipeline's start-up).  Byte-range shards need ONE uncompressed
+// How many device pipelines a scan gets (see the policy below).  Byte-range shards need ONE uncompressed
 // file; a directory is split into groups of whole files of about equal size.
 static idx_t PlanReaders(const ScanBindData &bind, const char *comp, int64_t &total_bytes, int32_t &n_files, int32_t &shardable) {
 	total_bytes = 0;
@@ -215,7 +214,16 @@ static idx_t PlanReaders(const ScanBindData &bind, const char *comp, int64_t &to
 		throw std::runtime_error(exb_last_error());
 	}
 	const int devices = exb_device_count();
-	idx_t want = bind.gpus > 0 ? (idx_t)bind.gpus : (idx_t)MaxValue<int>(devices, 1);
+	// `gpus = n` asks for n device pipelines.  Without it the scan uses ONE unless EXON_B200_GPUS says otherwise ("all" or a
+	// number; then every device gets a pipeline as long as each is left with >= 256 MiB of input).  One is the default
+	// because a pipeline is fed by the host's page-cache copy workers, which several pipelines share: measured on a 2-GPU box
+	// (profiles/round2_duckdb_multigpu.txt) two pipelines help queries that ship little back (AVG(gc_content): 1.35 x) and
+	// hurt the ones that materialise columns for order-preserving sinks.
+	int env_gpus = 1;
+	if (const char *e = getenv("EXON_B200_GPUS")) {
+		env_gpus = StringUtil::Lower(e) == "all" ? devices : atoi(e);
+	}
+	idx_t want = bind.gpus > 0 ? (idx_t)bind.gpus : (idx_t)MaxValue<int>(MinValue<int>(env_gpus, devices), 1);
 	if (bind.gpus > 0 && bind.gpus > devices) {
 		throw InvalidInputException("gpus := %d, but only %d CUDA device(s) are visible", bind.gpus, devices);
 	}
@@ -305,7 +313,8 @@ static unique_ptr<GlobalTableFunctionState> ScanInitGlobal(ClientContext &contex
 	// one consumer per device pipeline is enough to hand out pointers; a lone pipeline gets a few so that whatever sits
 	// above the scan (string functions, aggregates) runs on several cores
 	const idx_t cores = MaxValue<idx_t>(std::thread::hardware_concurrency(), 1);
-	state->threads_per_reader = n_readers == 1 ? MaxValue<idx_t>(2, MinValue<idx_t>(8, cores / 2)) : (n_readers == 2 ? 2 : 1);
+	// consumers in total: up to 8 (half the cores), spread over the pipelines, at least one each
+	state->threads_per_reader = MaxValue<idx_t>(1, MaxValue<idx_t>(2, MinValue<idx_t>(8, cores / 2)) / n_readers);
 
 	if (!any_column) { // COUNT(*): arrow_conversion.cpp:813-816 is the reference's "row id only" case
 		state->count_only = true;
