@@ -90,11 +90,13 @@ __device__ __forceinline__ int rec_pg(uint32_t y) { return (int)(y >> 15); }
 // ---------------------------------------------------------------- shared memory of one warp (K1)
 // Tile data lives in two 4 KiB buffers per warp (1024-byte aligned: the 128B swizzle pattern is a function of
 // address bits [7:9]); the small per-tile arrays follow all the data buffers.
+constexpr int ENT_CAP = 64;  // newline entries a warp keeps per pass (a 4 KiB tile of 150 bp reads has ~45 newlines)
 template <int FLAGS>
 struct FqWarpAux {
     static constexpr bool kSeq = (FLAGS & EXB_F_SEQ) != 0, kQual = (FLAGS & EXB_F_QUAL) != 0;
-    static constexpr int off_cpre = 0;                                   // int[256]: byte-sum prefix at each 16-byte chunk (lane l owns [8l, 8l+8))
-    static constexpr int off_bar = off_cpre + (kQual ? 256 * 4 : 0);     // 2 mbarriers
+    static constexpr int off_cpre = 0;                                   // int16[256]: ROW-relative byte-sum prefix at each 16-byte chunk (lane l owns [8l, 8l+8))
+    static constexpr int off_ent = off_cpre + (kQual ? 256 * 2 : 0);     // uint2[ENT_CAP]: the tile's newlines in tile order {byte-sum prefix, packed word}
+    static constexpr int off_bar = off_ent + ENT_CAP * 8;                // 2 mbarriers
     static constexpr int total = off_bar + 16;
     // the kernel has no static shared memory, so the dynamic region starts right after the 1 KiB the system
     // reserves per CTA: 1024-byte aligned, which the 128B swizzle needs (the kernel traps if that ever changes)
@@ -196,6 +198,33 @@ __device__ __forceinline__ uint32_t lds8(uint32_t addr) {
     asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
     return v;
 }
+// index of the most significant set bit (bfind) / its distance from bit 31 (= clz); 0xFFFFFFFF for 0 in both forms
+__device__ __forceinline__ int bfind_u32(uint32_t x) {
+    int r;
+    asm("bfind.u32 %0, %1;\n" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t bfind_sh(uint32_t x) {
+    uint32_t r;
+    asm("bfind.shiftamt.u32 %0, %1;\n" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ int lds_s16(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};\n" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t x) {
+    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(addr), "r"(x) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, int x, int y, int z, int w) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
@@ -230,7 +259,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
     if ((smem_u32 & 1023u) != 0) __trap();
     const uint32_t data0_u32 = smem_u32 + warp * (2 * WT_BYTES);
     const uint32_t aux_u32 = smem_u32 + FQ_WARPS * (2 * WT_BYTES) + warp * AUX::total;
-    const uint32_t cpre_u32 = aux_u32 + AUX::off_cpre + lane * 32;  // this lane's eight chunk prefixes
+    const uint32_t cpre_u32 = aux_u32 + AUX::off_cpre + lane * 16;  // this lane's eight chunk prefixes (int16, relative to its row)
+    const uint32_t ent_u32 = aux_u32 + AUX::off_ent;
     const uint32_t bar0 = aux_u32 + AUX::off_bar;
     const uint32_t wlut_u32 = smem_u32 + AUX::off_wlut, nflut_u32 = smem_u32 + AUX::off_nflut;
     if (lane == 0) {
@@ -253,6 +283,13 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
     const FusedPlan plan = kFused ? make_plan(a) : FusedPlan{0, 0.0, 0, 0, 0, 0, 0, 0};
     const int lane_off = lane * ROW_BYTES;
     const uint32_t lane_part = (uint32_t)lane_off | ((uint32_t)(lane & 7) << 4);  // chunk c of the lane's row sits at (buffer + lane_part) ^ (c << 4)
+    // the bytes just outside the lane's row: last byte of row lane - 1 / first byte of row lane + 1 (offsets in the swizzled
+    // tile buffer), clamped into the tile
+    const uint32_t o_prev = lane == 0 ? lane_part : swz((uint32_t)(lane_off - 1));
+    const uint32_t o_next = lane == 31 ? (lane_part ^ 127u) : swz((uint32_t)(lane_off + ROW_BYTES));
+    // fused: what the first byte of the line after newline i says about the hypotheses (i = lane mod 4, see B2)
+    const uint32_t bad_hdr = 1u << ((0 - (lane + 1)) & 3), bad_plus = 1u << ((2 - (lane + 1)) & 3);
+    const uint32_t bad_lut = (bad_hdr | bad_plus) | (bad_hdr << 4) | (bad_plus << 8);
 
     // ---- staging of one tile into buffer b (asynchronous; one instruction from one lane)
     auto issue = [&](int tile, int b) {
@@ -317,7 +354,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         }
 
         // ---- A. analysis of the lane's row: two 64-byte halves
-        uint64_t pm[2], gm[2] = {0, 0};
+        uint32_t w_nl[4];  // newline mask of the row, 32 bytes per word
+        uint64_t gm[2] = {0, 0};
         int ex_cnt, n_events, cnt, ex_s = 0, total_s = 0, ex_g = 0, total_g = 0, g0 = 0;
         const uint32_t rowx = sb + lane_part;
         {
@@ -327,8 +365,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             for (int h = 0; h < 2; h++) {
                 const uint4 c0 = lds128(rowx ^ ((4 * h + 0) << 4)), c1 = lds128(rowx ^ ((4 * h + 1) << 4)), c2 = lds128(rowx ^ ((4 * h + 2) << 4)),
                             c3 = lds128(rowx ^ ((4 * h + 3) << 4));
-                pm[h] = ((uint64_t)(nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16)) << 32) |
-                        (nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16));
+                w_nl[2 * h] = nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16);
+                w_nl[2 * h + 1] = nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16);
                 if (kQual) {
                     pre[4 * h + 0] = acc;
                     acc = sbyte_sum16(c0, acc);
@@ -343,7 +381,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                     gm[h] = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
                             (gc_mask16r(c0, c7b, c7f, pat_gc) | (gc_mask16r(c1, c7b, c7f, pat_gc) << 16));
             }
-            cnt = __popcll(pm[0]) + __popcll(pm[1]);
+            cnt = __popc(w_nl[0]) + __popc(w_nl[1]) + __popc(w_nl[2]) + __popc(w_nl[3]);
             g0 = kSeq ? __popcll(gm[0]) : 0;
             const int g1 = kSeq ? __popcll(gm[1]) : 0;
             if (kQual && !kSeq) {
@@ -374,9 +412,10 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                 }
             }
             if (kQual) {
-                // read back by this lane only (dynamic index at each newline): no warp barrier needed
-                sts128(cpre_u32, ex_s + pre[0], ex_s + pre[1], ex_s + pre[2], ex_s + pre[3]);
-                sts128(cpre_u32 + 16, ex_s + pre[4], ex_s + pre[5], ex_s + pre[6], ex_s + pre[7]);
+                // read back by this lane only (dynamic index at each newline): no warp barrier needed.  Row-relative, so
+                // 16 bits are enough (|sum of 128 signed bytes| <= 2^14); pre[0] = 0.
+                sts128(cpre_u32, (int)__byte_perm((uint32_t)pre[0], (uint32_t)pre[1], 0x5410), (int)__byte_perm((uint32_t)pre[2], (uint32_t)pre[3], 0x5410),
+                       (int)__byte_perm((uint32_t)pre[4], (uint32_t)pre[5], 0x5410), (int)__byte_perm((uint32_t)pre[6], (uint32_t)pre[7], 0x5410));
             }
         }
         if (lane == 0) a.tile_cnt[tile] = (uint32_t)n_events;
@@ -408,150 +447,154 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             }
         }
 
-        // ---- B. every lane walks the newlines of ITS OWN row, one per round; the number of rounds is the newline count
-        // of the fullest row (2 for 150 bp reads, 1 for long reads).  The k-th newline of the row has tile-local line
-        // index ex_cnt + k.  Fused: the line a newline ends is judged as soon as both of its ends are known -- at once
-        // for k >= 1 (the previous newline is in this row), after the loop for k = 0 (it is the last newline of an
-        // earlier row).  Buckets are kept in the LANE's frame (hypothesis h' = phase of the row's first line, so
-        // everything is indexed by the unrolled round number) and rotated by ex_cnt into the tile's frame once,
-        // before the warp reduction.  The rounds are branch-free: a lane without a newline left computes on a
-        // harmless in-range position and its results are discarded by selects.
-        uint32_t f_cq[4] = {0, 0, 0, 0};  // [h'] lines that are quality lines under h' and pass: count | length sum << 12
-        int f_qs[4] = {0, 0, 0, 0};       // [h'] their Phred sums
-        uint32_t f_bad = 0;               // bit h': a line start contradicts h'
-        uint64_t mlo = pm[0], mhi = pm[1];
-        int l_ps = 0, r0_ps = 0;          // byte-sum prefix at the row's latest / first newline
-        uint32_t l_y = 0, r0_y = 0;       // their packed words
-        int kk = 0;                       // rounds done
+        // ---- B. the tile's newlines, in two steps.
+        // B1 (row frame): every lane files the newlines of ITS OWN row -- {byte-sum prefix, packed word} of the k-th
+        //    one under its tile-local line index ex_cnt + k -- in the warp's entry table.  Branch-free: a lane without
+        //    a k-th newline computes on a harmless in-range position and stores nothing.  Rows of real FASTQ hold at
+        //    most two newlines ("...\n+\n..."), so the common case needs no bit-clearing walk over the 128-bit row mask:
+        //    the first newline is a min and the last one a max over four per-word find-first / find-last results.
+        // B2 (tile frame): lane l takes entries l, l + 32, ...: line i is what lies between newline i - 1 and newline i,
+        //    whichever rows those are in.  Fused: line i is a quality line under exactly one phase hypothesis of the
+        //    tile's line 0, h = (3 - i) & 3 = (3 - lane) & 3 -- ONE bucket per lane, fixed for the whole kernel.
+        //    General: entry i is record i of the tile (coalesced 8-byte stores).
+        // The table holds ENT_CAP entries; a tile with more newlines (reads shorter than ~60 bp) repeats B1 + B2 per
+        // ENT_CAP indices.  The tile's line 0 began in an earlier tile: K2 finishes it.
+        uint32_t f_cq = 0;   // lines of this lane's bucket that pass: count | length sum << 12
+        int f_qs = 0;        // their Phred sums
+        uint32_t f_bad = 0;  // bit h: a line start contradicts hypothesis h
+        uint2 e_first = make_uint2(0u, 0u), e_last = make_uint2(0u, 0u), carry = make_uint2(0u, 0u);
+        const int rounds = __reduce_max_sync(0xffffffffu, cnt);
+        const uint32_t a_prev = sb + o_prev, a_next = sb + o_next;
 
-        // the line between the newline at `ppos` (byte-sum prefix pps) and the newline at `pos` (ps, CR flag cr) is
-        // line `j` (mod 4) of the lane's frame.  A CR flag implies a non-empty line (the byte before an empty line's
-        // newline is the previous newline), so the length needs no clamp.  Called by the whole warp (it votes);
-        // `valid` = this lane has such a line.
-        auto judge = [&](auto jc, bool valid, int ps, int pos, uint32_t cr, int pps, int ppos) {
-            constexpr int j = decltype(jc)::value;
-            const uint32_t len = (uint32_t)(pos - ppos - 1) - cr;
-            const int qs = ps - pps - 10 - 13 * (int)cr - 33 * (int)len;
-            if (plan.i32) {
-                // e = +-2^sh (sum - c n), exact in 32 bits; e != 0 means |sum - c n| >= 2^-20 > 1e-7, which puts the exact
-                // quotient more than 40 ulp from c (see exb_mean_cmp): the sign of e is the verdict.  n = 0 gives e = 0.
-                const int e = qs * plan.mul_q + (int)len * plan.mul_n;
-                if (valid && e > 0) {
-                    f_cq[(3 - j) & 3] += 1u + (len << 12);
-                    f_qs[(3 - j) & 3] += qs;
-                }
-                const bool close = valid && e == 0;
-                if (__any_sync(0xffffffffu, close)) {  // rare: the two roundings of the reference decide
-                    if (close && fused_pass_general(s_preds, a.n_fused, plan.simple, plan.c, plan.op, plan.want_pos, qs, len)) {
-                        f_cq[(3 - j) & 3] += 1u + (len << 12);
-                        f_qs[(3 - j) & 3] += qs;
-                    }
-                }
-            } else if (valid && fused_pass(s_preds, a.n_fused, plan, qs, len)) {
-                f_cq[(3 - j) & 3] += 1u + (len << 12);
-                f_qs[(3 - j) & 3] += qs;
-            }
-        };
-        auto step = [&](auto jc, bool first_round) {
-            constexpr int j = decltype(jc)::value;
-            const bool act = kk < cnt;
-            const bool use_hi = mlo == 0;  // also when no newline is left: p = 63 then
-            const uint64_t m = use_hi ? mhi : mlo;
-            const int p = __ffsll((long long)m) - 1 + (use_hi ? 64 : 0);  // position in the row
-            mlo &= mlo - 1;
-            mhi = use_hi ? (mhi & (mhi - 1)) : mhi;
+        // B1 for one newline: row position p (0..127), the lane's k-th, table slot ex_cnt + k - base
+        auto file_entry = [&](int k, int p, int base) {
             const int pos = lane_off + p;
             int ps = 0, pg = 0;
             if (kQual) {
                 const uint4 v = lds128(rowx ^ (uint32_t)(p & 0x70));
                 const uint4 w = lds128(wlut_u32 + (uint32_t)((p & 15) << 4));
-                int acc = (int)lds32(cpre_u32 + (uint32_t)((p >> 4) << 2));
+                int acc = lds_s16(cpre_u32 | (uint32_t)((p >> 3) & 0xE));
                 acc = __dp4a((int)v.x, (int)w.x, acc);
                 acc = __dp4a((int)v.y, (int)w.y, acc);
                 acc = __dp4a((int)v.z, (int)w.z, acc);
                 acc = __dp4a((int)v.w, (int)w.w, acc);
-                ps = acc;
+                ps = acc + ex_s;
             }
             if (kSeq) pg = p < 64 ? ex_g + __popcll(gm[0] & low_bits64(p)) : ex_g + g0 + __popcll(gm[1] & low_bits64(p - 64));
-            // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing.  Both neighbours
-            // are fetched unconditionally (clamped); the byte before the tile's first byte is patched in below.
-            const uint32_t before = lds8(sb + swz((uint32_t)max(pos - 1, 0)));
-            const uint32_t after = lds8(sb + swz((uint32_t)min(pos + 1, WT_BYTES - 1)));
+            // neighbours: byte q of the lane's own row sits at rowx ^ q (rowx is 16-byte aligned and the swizzle is an XOR
+            // of bits 4..6); the byte before the row / after it at a per-lane offset of the buffer (lane 0 / 31: clamped
+            // into the row; the byte before the tile's first byte is patched in below, the byte after its last one gets
+            // no verdict: last_known)
+            const uint32_t before = lds8(p == 0 ? a_prev : (rowx ^ (uint32_t)(p - 1)));
+            const uint32_t after = lds8(p == 127 ? a_next : (rowx ^ (uint32_t)(p + 1)));
+            // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing
             const uint32_t cr = (before == '\r' && pos != virt) ? 1u : 0u;
             // '@' / '+' flags of the next line's first byte; 3 = that byte is not in this tile or range: no verdict here
             const uint32_t nfk = lds8(nflut_u32 + after);
             const uint32_t nf = pos < last_known ? nfk : 3u;
-            const uint32_t y = rec_pack(pos, cr, nf, kSeq ? pg : 0);
-            if (kFused) {
-                // the line that STARTS after this newline is line j + 1 of the lane's frame: a header under
-                // h' = -(j + 1), a plus line under h' = 2 - (j + 1).  (The tile's line 0 is checked by K2.)
-                constexpr uint32_t bad_hdr = 1u << ((0 - (j + 1)) & 3), bad_plus = 1u << ((2 - (j + 1)) & 3);
-                // nf: 0 -> both, 1 ('+') -> hdr, 2 ('@') -> plus, 3 -> none
-                constexpr uint32_t lut = (bad_hdr | bad_plus) | (bad_hdr << 4) | (bad_plus << 8);
-                f_bad |= (lut >> (4 * (act ? nf : 3u))) & 15u;
-            }
-            if (!kFused) {
-                const int i = ex_cnt + kk;
-                if (act && (i < rec_n0 ? rec_ok0 : blk_ok)) a.records[i < rec_n0 ? rec_off0 + i : rec_off1 + (i - rec_n0)] = make_uint2((uint32_t)ps, y);
-            }
-            if (j == 0 && first_round) {  // a lane without a newline keeps garbage here and never uses it
-                r0_ps = ps;
-                r0_y = y;
-            } else if (kFused) {
-                judge(jc, act, ps, pos, cr, l_ps, rec_pos(l_y));
-            }
-            l_ps = act ? ps : l_ps;
-            l_y = act ? y : l_y;
-            kk++;
+            const uint32_t idx = (uint32_t)(ex_cnt + k - base);
+            if (k < cnt && idx < (uint32_t)ENT_CAP) sts64(ent_u32 + idx * 8u, (uint32_t)ps, rec_pack(pos, cr, nf, kSeq ? pg : 0));
         };
-        {
-            const int rounds = __reduce_max_sync(0xffffffffu, cnt);
-            bool first_round = true;
-            for (int r = 0; r < rounds; r += 4) {
-                step(std::integral_constant<int, 0>(), first_round);
-                if (r + 1 < rounds) step(std::integral_constant<int, 1>(), false);
-                if (r + 2 < rounds) step(std::integral_constant<int, 2>(), false);
-                if (r + 3 < rounds) step(std::integral_constant<int, 3>(), false);
-                first_round = false;
+        // the byte before the tile's first byte lives in global memory: a newline at position 0 of the tile (entry 0,
+        // filed by lane 0) learns its CR flag here (rare, so it is kept out of file_entry)
+        auto patch_entry0 = [&]() {
+            if (lane == 0 && (w_nl[0] & 1u) && virt != 0) {
+                const int64_t tile_base = origin + (int64_t)tile * WT_BYTES;
+                if (tile_base - 1 >= (a.prev ? 0 : a.begin) && buf[tile_base - 1] == '\r') sts32(ent_u32 + 4u, lds32(ent_u32 + 4u) | (1u << 12));
             }
-        }
-        // the byte before the tile's first byte lives in global memory: a newline at position 0 of the tile (lane 0's
-        // first) learns its CR flag here (rare, so it is kept out of the rounds)
-        if (lane == 0 && (pm[0] & 1ull) && virt != 0) {
-            const int64_t tile_base = origin + (int64_t)tile * WT_BYTES;
-            if (tile_base - 1 >= (a.prev ? 0 : a.begin) && buf[tile_base - 1] == '\r') {
-                r0_y |= 1u << 12;
-                if (cnt == 1) l_y |= 1u << 12;
-                if (!kFused && (0 < rec_n0 ? rec_ok0 : blk_ok)) a.records[0 < rec_n0 ? rec_off0 : rec_off1] = make_uint2((uint32_t)r0_ps, r0_y);
+        };
+        // B2 for entries i0 + lane of a pass that starts at tile-local index `base` and holds nb entries
+        auto lines = [&](int i0, int nb, int base) {
+            const int i = i0 + lane;
+            const bool valid = i < nb;
+            const uint2 e = lds64(ent_u32 + (uint32_t)i * 8u);  // i < ENT_CAP: in range even when not valid
+            uint2 pe = lds64(ent_u32 + (uint32_t)(i > 0 ? i - 1 : 0) * 8u);
+            if (i == 0) pe = carry;  // the last newline of the previous pass (unused for the tile's line 0)
+            if (!kFused) {
+                const int t = base + i;
+                if (valid && (t < rec_n0 ? rec_ok0 : blk_ok)) a.records[t < rec_n0 ? rec_off0 + t : rec_off1 + (t - rec_n0)] = e;
+            } else {
+                // the line that STARTS after newline i is line i + 1 of the tile: a header under h = -(i + 1), a plus
+                // line under h = 2 - (i + 1).  nf: 0 -> both contradicted, 1 ('+') -> header, 2 ('@') -> plus, 3 -> none
+                f_bad |= (bad_lut >> (4u * (valid ? rec_next_flags(e.y) : 3u))) & 15u;
+                // line i: between newline i - 1 and newline i.  A CR flag implies a non-empty line (the byte before an
+                // empty line's newline is the previous newline), so the length needs no clamp.
+                const bool line = valid && (i | base) != 0;
+                const uint32_t cr = rec_cr(e.y);
+                const uint32_t len = (uint32_t)(rec_pos(e.y) - rec_pos(pe.y) - 1) - cr;
+                const int qs = (int)e.x - (int)pe.x - 10 - 13 * (int)cr - 33 * (int)len;
+                if (plan.i32) {
+                    // ee = +-2^sh (sum - c n), exact in 32 bits; ee != 0 means |sum - c n| >= 2^-20 > 1e-7, which puts the
+                    // exact quotient more than 40 ulp from c (see exb_mean_cmp): the sign of ee is the verdict.  n = 0: ee = 0.
+                    const int ee = qs * plan.mul_q + (int)len * plan.mul_n;
+                    if (line && ee > 0) {
+                        f_cq += 1u + (len << 12);
+                        f_qs += qs;
+                    }
+                    const bool close = line && ee == 0;
+                    if (__any_sync(0xffffffffu, close)) {  // rare: the two roundings of the reference decide
+                        if (close && fused_pass_general(s_preds, a.n_fused, plan.simple, plan.c, plan.op, plan.want_pos, qs, len)) {
+                            f_cq += 1u + (len << 12);
+                            f_qs += qs;
+                        }
+                    }
+                } else if (line && fused_pass(s_preds, a.n_fused, plan, qs, len)) {
+                    f_cq += 1u + (len << 12);
+                    f_qs += qs;
+                }
             }
-        }
-        // rows that hold a newline; the row's first line started after the last newline of the nearest such row below
-        const uint32_t has = __ballot_sync(0xffffffffu, cnt > 0);
-        const uint32_t below = has & ((1u << lane) - 1u);
-        if (kFused) {
-            const int src = below ? 31 - __clz((int)below) : 0;
-            const int pps = __shfl_sync(0xffffffffu, l_ps, src);
-            const uint32_t py = __shfl_sync(0xffffffffu, l_y, src);
-            judge(std::integral_constant<int, 0>(), cnt > 0 && below != 0, r0_ps, rec_pos(r0_y), rec_cr(r0_y), pps, rec_pos(py));
-        }
-        int first_ps = 0;
-        uint32_t first_y = 0;
-        if (kFused && has) {  // the tile's first newline: K2 finishes the line it ends
-            const int f = __ffs((int)has) - 1;
-            first_ps = __shfl_sync(0xffffffffu, r0_ps, f);
-            first_y = __shfl_sync(0xffffffffu, r0_y, f);
+        };
+
+        if (rounds <= 2) {  // warp-uniform; at most 64 newlines: one pass
+            if (rounds >= 1) {
+                // first newline of the row: ctz per word (0xFFFFFFFF for an empty word survives the OR), unsigned min
+                const uint32_t c0 = bfind_sh(__brev(w_nl[0])), c1 = bfind_sh(__brev(w_nl[1])) | 32u, c2 = bfind_sh(__brev(w_nl[2])) | 64u,
+                               c3 = bfind_sh(__brev(w_nl[3])) | 96u;
+                file_entry(0, (int)(min(min(c0, c1), min(c2, c3)) & 127u), 0);
+            }
+            if (rounds == 2) {
+                // last newline of the row: find-last per word (-1 for an empty word survives the OR), signed max
+                const int d0 = bfind_u32(w_nl[0]), d1 = bfind_u32(w_nl[1]) | 32, d2 = bfind_u32(w_nl[2]) | 64, d3 = bfind_u32(w_nl[3]) | 96;
+                file_entry(1, max(max(d0, d1), max(d2, d3)) & 127, 0);
+            }
+            patch_entry0();
+            __syncwarp();
+            if (n_events > 0) lines(0, n_events, 0);
+            if (n_events > 32) lines(32, n_events, 0);
+            e_first = lds64(ent_u32);
+            e_last = lds64(ent_u32 + (uint32_t)(n_events > 0 ? n_events - 1 : 0) * 8u);
+        } else {
+            for (int base = 0;; base += ENT_CAP) {
+                uint64_t mlo = ((uint64_t)w_nl[1] << 32) | w_nl[0], mhi = ((uint64_t)w_nl[3] << 32) | w_nl[2];
+                for (int k = 0; k < rounds; k++) {
+                    const bool use_hi = mlo == 0;  // also when no newline is left: p = 63 then
+                    const uint64_t m = use_hi ? mhi : mlo;
+                    const int p = __ffsll((long long)m) - 1 + (use_hi ? 64 : 0);  // position in the row
+                    mlo &= mlo - 1;
+                    mhi = use_hi ? (mhi & (mhi - 1)) : mhi;
+                    file_entry(k, p, base);
+                }
+                if (base == 0) patch_entry0();
+                __syncwarp();
+                const int nb = n_events - base < ENT_CAP ? n_events - base : ENT_CAP;
+                for (int i0 = 0; i0 < nb; i0 += 32) lines(i0, nb, base);
+                if (base == 0) e_first = lds64(ent_u32);  // the tile's first newline: K2 finishes the line it ends
+                if (base + ENT_CAP >= n_events) {
+                    e_last = lds64(ent_u32 + (uint32_t)(nb - 1) * 8u);  // the tile's last newline
+                    break;
+                }
+                carry = lds64(ent_u32 + (uint32_t)(ENT_CAP - 1) * 8u);
+                __syncwarp();  // everybody has read the table before the next pass overwrites it
+            }
         }
 
         // ---- C. tail word: what follows the tile's last newline (local information only)
         {
             const uint32_t b0 = lds8(nflut_u32 + lds8(sb + ((tile == 0 && pad0) ? swz((uint32_t)(a.begin - origin)) : 0u)));
             uint64_t tw;
-            if (has) {
-                const int src = 31 - __clz((int)has);  // lane holding the last record
-                const int lps = __shfl_sync(0xffffffffu, l_ps, src);
-                const uint32_t ly = __shfl_sync(0xffffffffu, l_y, src);
-                tw = tail_pack(2, (rec_next_flags(ly) << 2) | b0, (uint32_t)(rec_pos(ly) + 1), (uint32_t)(total_g - rec_pg(ly)),
-                               total_s - (lps + 10));
+            if (n_events > 0) {
+                tw = tail_pack(2, (rec_next_flags(e_last.y) << 2) | b0, (uint32_t)(rec_pos(e_last.y) + 1), (uint32_t)(total_g - rec_pg(e_last.y)),
+                               total_s - ((int)e_last.x + 10));
             } else {
                 tw = tail_pack(1, b0, 0, (uint32_t)total_g, total_s);
             }
@@ -559,28 +602,19 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         }
 
         if (kFused) {
-            // lane frame -> tile frame: tile hypothesis h (phase of the tile's line 0) is lane hypothesis (h + ex_cnt) & 3
-            const int r = ex_cnt & 3;
-            uint32_t cq[4];
-            int qs[4];
+            // lanes l, l + 4, ... share bucket (3 - l) & 3: three butterfly steps leave its totals in lanes 0..3
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t c1 = (r & 1) ? f_cq[(i + 1) & 3] : f_cq[i], c3 = (r & 1) ? f_cq[(i + 3) & 3] : f_cq[(i + 2) & 3];
-                const int q1 = (r & 1) ? f_qs[(i + 1) & 3] : f_qs[i], q3 = (r & 1) ? f_qs[(i + 3) & 3] : f_qs[(i + 2) & 3];
-                cq[i] = (r & 2) ? c3 : c1;
-                qs[i] = (r & 2) ? q3 : q1;
+            for (int d = 4; d < 32; d <<= 1) {
+                f_cq += __shfl_xor_sync(0xffffffffu, f_cq, d);
+                f_qs += __shfl_xor_sync(0xffffffffu, f_qs, d);
             }
-            const uint32_t bad_t = ((f_bad | (f_bad << 4)) >> r) & 15u;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                cq[i] = __reduce_add_sync(0xffffffffu, cq[i]);
-                qs[i] = __reduce_add_sync(0xffffffffu, qs[i]);
+            const uint32_t bad4 = __reduce_or_sync(0xffffffffu, f_bad);
+            FusedTile* ft = a.fused_tiles + tile;
+            if (lane < 4) {
+                ft->cq[(3 - lane) & 3] = f_cq;
+                ft->qs[(3 - lane) & 3] = f_qs;
             }
-            const uint32_t bad4 = __reduce_or_sync(0xffffffffu, bad_t);
-            uint4* ft = reinterpret_cast<uint4*>(a.fused_tiles + tile);
-            if (lane == 0) ft[0] = make_uint4(cq[0], cq[1], cq[2], cq[3]);
-            if (lane == 1) ft[1] = make_uint4((uint32_t)qs[0], (uint32_t)qs[1], (uint32_t)qs[2], (uint32_t)qs[3]);
-            if (lane == 2) ft[2] = make_uint4((uint32_t)first_ps, first_y, bad4, 0u);
+            if (lane == 4) *reinterpret_cast<uint4*>(&ft->ps0) = make_uint4(e_first.x, e_first.y, bad4, 0u);
         }
 
         __syncwarp();  // every lane is done with this buffer before lane 0 lets TMA refill it
