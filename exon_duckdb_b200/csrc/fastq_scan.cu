@@ -228,6 +228,13 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t x) {
 __device__ __forceinline__ void sts128(uint32_t addr, int x, int y, int z, int w) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+// inclusive warp scan; the shuffle's predicate output (source lane in range) guards the add: two instructions per step
+__device__ __forceinline__ uint32_t warp_incl_scan_u32p(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{\n .reg .pred p;\n .reg .u32 t;\n shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n @p add.u32 %0, %0, t;\n}\n" : "+r"(v) : "r"(d));
+    return v;
+}
 // tile-local byte index -> byte offset in the 128B-swizzled tile buffer (same map as sidx, two instructions)
 __device__ __forceinline__ uint32_t swz(uint32_t li) { return li ^ ((li >> 3) & 0x70u); }
 
@@ -242,7 +249,9 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint4* s_wlut = reinterpret_cast<uint4*>(smem_raw + AUX::off_wlut);  // s_wlut[k]: 0x01 in the first k bytes -- IDP.4A weights
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the warp index through a shuffle: the compiler then knows it (and every tile index / buffer address derived from it)
+    // is warp-uniform and keeps that arithmetic -- and the TMA descriptor operands -- in uniform registers
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     if (threadIdx.x < 17) {
         const int k = threadIdx.x;
         auto w = [k](int b) -> uint32_t {  // word holding bytes [b, b+4)
@@ -255,7 +264,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
     if (kFused && threadIdx.x < a.n_fused) s_preds[threadIdx.x] = a.fused[threadIdx.x];
     for (int i = threadIdx.x; i < 256; i += FQ_THREADS) (smem_raw + AUX::off_nflut)[i] = (uint8_t)at_plus_flags(i);
 
-    const uint32_t smem_u32 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    uint32_t smem_u32;  // volatile: computed once and kept in a register (the compiler otherwise re-derives it ~5 times per tile)
+    asm volatile("{\n .reg .u64 t;\n cvta.to.shared.u64 t, %1;\n cvt.u32.u64 %0, t;\n}\n" : "=r"(smem_u32) : "l"(smem_raw));
     if ((smem_u32 & 1023u) != 0) __trap();
     const uint32_t data0_u32 = smem_u32 + warp * (2 * WT_BYTES);
     const uint32_t aux_u32 = smem_u32 + FQ_WARPS * (2 * WT_BYTES) + warp * AUX::total;
@@ -322,6 +332,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             phase_bits ^= 1u << b;
         }
         // Rare edge tiles (uniform per warp): rows the tensor map does not cover, bytes before `begin`, the virtual '\n'
+        uint32_t b0_addr = sb;           // where the tile's first parsed byte sits (not byte 0 if the range starts inside tile 0's first 16 bytes)
         int virt = -1;                   // tile-local position of the virtual '\n' that terminates an unterminated last line
         int last_known = WT_BYTES - 1;   // first tile-local position whose NEXT byte lies outside the tile or the parse range
         if (tile >= first_edge || (tile == 0 && pad0)) {
@@ -349,6 +360,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic writes before this buffer's next TMA fill
             __syncwarp();
+            if (tile == 0 && pad0) b0_addr = sb + swz((uint32_t)(a.begin - origin));
             if (a.is_final && a.n >= tile_base && a.n < tile_base + WT_BYTES) virt = (int)(a.n - tile_base);
             if (partial && a.n - tile_base < WT_BYTES) last_known = (int)(a.n - tile_base) - 1;
         }
@@ -365,8 +377,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             for (int h = 0; h < 2; h++) {
                 const uint4 c0 = lds128(rowx ^ ((4 * h + 0) << 4)), c1 = lds128(rowx ^ ((4 * h + 1) << 4)), c2 = lds128(rowx ^ ((4 * h + 2) << 4)),
                             c3 = lds128(rowx ^ ((4 * h + 3) << 4));
-                w_nl[2 * h] = nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16);
-                w_nl[2 * h + 1] = nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16);
+                w_nl[2 * h] = nl_mask32r(c0, c1, c7f, pat_nl);
+                w_nl[2 * h + 1] = nl_mask32r(c2, c3, c7f, pat_nl);
                 if (kQual) {
                     pre[4 * h + 0] = acc;
                     acc = sbyte_sum16(c0, acc);
@@ -378,8 +390,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                     acc = sbyte_sum16(c3, acc);
                 }
                 if (kSeq)
-                    gm[h] = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
-                            (gc_mask16r(c0, c7b, c7f, pat_gc) | (gc_mask16r(c1, c7b, c7f, pat_gc) << 16));
+                    gm[h] = ((uint64_t)gc_mask32r(c2, c3, c7b, c7f, pat_gc) << 32) | gc_mask32r(c0, c1, c7b, c7f, pat_gc);
             }
             cnt = __popc(w_nl[0]) + __popc(w_nl[1]) + __popc(w_nl[2]) + __popc(w_nl[3]);
             g0 = kSeq ? __popcll(gm[0]) : 0;
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                 // ONE scan: newline count << 20 | byte sum, the sum biased by 2^14 per lane so that it is never negative
                 // (a row of 128 signed bytes sums to [-2^14, 2^14); 32 rows stay below 2^20)
                 const uint32_t packed = ((uint32_t)cnt << 20) + (uint32_t)(acc + 16384);
-                const uint32_t incl = warp_incl_scan_u32(packed);
+                const uint32_t incl = warp_incl_scan_u32p(packed);
                 const uint32_t ex = incl - packed;
                 const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
                 ex_cnt = (int)(ex >> 20);
@@ -398,7 +409,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             } else {
                 // newlines and G/C (each <= 4096 per tile: 13 bits) share one scan word; the byte sums get their own
                 const uint32_t packed = ((uint32_t)cnt << 16) + (uint32_t)(g0 + g1);
-                const uint32_t incl = warp_incl_scan_u32(packed);
+                const uint32_t incl = warp_incl_scan_u32p(packed);
                 const uint32_t ex = incl - packed;
                 const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
                 ex_cnt = (int)(ex >> 16);
@@ -406,7 +417,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                 ex_g = (int)(ex & 0xFFFFu);
                 total_g = (int)(tot & 0xFFFFu);
                 if (kQual) {
-                    const uint32_t si = warp_incl_scan_u32((uint32_t)acc);
+                    const uint32_t si = warp_incl_scan_u32p((uint32_t)acc);
                     ex_s = (int)(si - (uint32_t)acc);
                     total_s = (int)__shfl_sync(0xffffffffu, si, 31);
                 }
@@ -467,7 +478,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         const uint32_t a_prev = sb + o_prev, a_next = sb + o_next;
 
         // B1 for one newline: row position p (0..127), the lane's k-th, table slot ex_cnt + k - base
-        auto file_entry = [&](int k, int p, int base) {
+        auto file_entry = [&](int k, int p, int base, auto one_pass) {
             const int pos = lane_off + p;
             int ps = 0, pg = 0;
             if (kQual) {
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             const uint32_t nfk = lds8(nflut_u32 + after);
             const uint32_t nf = pos < last_known ? nfk : 3u;
             const uint32_t idx = (uint32_t)(ex_cnt + k - base);
-            if (k < cnt && idx < (uint32_t)ENT_CAP) sts64(ent_u32 + idx * 8u, (uint32_t)ps, rec_pack(pos, cr, nf, kSeq ? pg : 0));
+            if (k < cnt && (decltype(one_pass)::value || idx < (uint32_t)ENT_CAP)) sts64(ent_u32 + idx * 8u, (uint32_t)ps, rec_pack(pos, cr, nf, kSeq ? pg : 0));
         };
         // the byte before the tile's first byte lives in global memory: a newline at position 0 of the tile (entry 0,
         // filed by lane 0) learns its CR flag here (rare, so it is kept out of file_entry)
@@ -504,12 +515,12 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             }
         };
         // B2 for entries i0 + lane of a pass that starts at tile-local index `base` and holds nb entries
-        auto lines = [&](int i0, int nb, int base) {
+        auto lines = [&](int i0, int nb, int base, auto one_pass) {
             const int i = i0 + lane;
             const bool valid = i < nb;
             const uint2 e = lds64(ent_u32 + (uint32_t)i * 8u);  // i < ENT_CAP: in range even when not valid
             uint2 pe = lds64(ent_u32 + (uint32_t)(i > 0 ? i - 1 : 0) * 8u);
-            if (i == 0) pe = carry;  // the last newline of the previous pass (unused for the tile's line 0)
+            if (!decltype(one_pass)::value && i == 0) pe = carry;  // the last newline of the previous pass (unused for the tile's line 0)
             if (!kFused) {
                 const int t = base + i;
                 if (valid && (t < rec_n0 ? rec_ok0 : blk_ok)) a.records[t < rec_n0 ? rec_off0 + t : rec_off1 + (t - rec_n0)] = e;
@@ -550,17 +561,17 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                 // first newline of the row: ctz per word (0xFFFFFFFF for an empty word survives the OR), unsigned min
                 const uint32_t c0 = bfind_sh(__brev(w_nl[0])), c1 = bfind_sh(__brev(w_nl[1])) | 32u, c2 = bfind_sh(__brev(w_nl[2])) | 64u,
                                c3 = bfind_sh(__brev(w_nl[3])) | 96u;
-                file_entry(0, (int)(min(min(c0, c1), min(c2, c3)) & 127u), 0);
+                file_entry(0, (int)(min(min(c0, c1), min(c2, c3)) & 127u), 0, std::true_type());
             }
             if (rounds == 2) {
                 // last newline of the row: find-last per word (-1 for an empty word survives the OR), signed max
                 const int d0 = bfind_u32(w_nl[0]), d1 = bfind_u32(w_nl[1]) | 32, d2 = bfind_u32(w_nl[2]) | 64, d3 = bfind_u32(w_nl[3]) | 96;
-                file_entry(1, max(max(d0, d1), max(d2, d3)) & 127, 0);
+                file_entry(1, max(max(d0, d1), max(d2, d3)) & 127, 0, std::true_type());
             }
             patch_entry0();
             __syncwarp();
-            if (n_events > 0) lines(0, n_events, 0);
-            if (n_events > 32) lines(32, n_events, 0);
+            if (n_events > 0) lines(0, n_events, 0, std::true_type());
+            if (n_events > 32) lines(32, n_events, 0, std::true_type());
             e_first = lds64(ent_u32);
             e_last = lds64(ent_u32 + (uint32_t)(n_events > 0 ? n_events - 1 : 0) * 8u);
         } else {
@@ -572,12 +583,12 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                     const int p = __ffsll((long long)m) - 1 + (use_hi ? 64 : 0);  // position in the row
                     mlo &= mlo - 1;
                     mhi = use_hi ? (mhi & (mhi - 1)) : mhi;
-                    file_entry(k, p, base);
+                    file_entry(k, p, base, std::false_type());
                 }
                 if (base == 0) patch_entry0();
                 __syncwarp();
                 const int nb = n_events - base < ENT_CAP ? n_events - base : ENT_CAP;
-                for (int i0 = 0; i0 < nb; i0 += 32) lines(i0, nb, base);
+                for (int i0 = 0; i0 < nb; i0 += 32) lines(i0, nb, base, std::false_type());
                 if (base == 0) e_first = lds64(ent_u32);  // the tile's first newline: K2 finishes the line it ends
                 if (base + ENT_CAP >= n_events) {
                     e_last = lds64(ent_u32 + (uint32_t)(nb - 1) * 8u);  // the tile's last newline
@@ -590,7 +601,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
 
         // ---- C. tail word: what follows the tile's last newline (local information only)
         {
-            const uint32_t b0 = lds8(nflut_u32 + lds8(sb + ((tile == 0 && pad0) ? swz((uint32_t)(a.begin - origin)) : 0u)));
+            const uint32_t b0 = lds8(nflut_u32 + lds8(b0_addr));
             uint64_t tw;
             if (n_events > 0) {
                 tw = tail_pack(2, (rec_next_flags(e_last.y) << 2) | b0, (uint32_t)(rec_pos(e_last.y) + 1), (uint32_t)(total_g - rec_pg(e_last.y)),

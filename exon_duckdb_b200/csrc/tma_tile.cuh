@@ -36,6 +36,20 @@ __device__ __forceinline__ uint32_t eq_flags(uint32_t x, uint32_t c7f, uint32_t 
 __device__ __forceinline__ uint32_t nl_mask16r(const uint4& v, uint32_t c7f, uint32_t pat) {
     return flags_to_mask16(eq_flags(v.x, c7f, pat), eq_flags(v.y, c7f, pat), eq_flags(v.z, c7f, pat), eq_flags(v.w, c7f, pat));
 }
+// 32-bit equality mask of two consecutive 16-byte chunks.  Each IDP.4A chain leaves (8 flag bits) << 7; two multiply-adds
+// and one shift put the four pieces in place (the 16-bit form above would cost two more instructions per 32 bytes).
+__device__ __forceinline__ uint32_t flags_to_x16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {  // (16-bit mask) << 7
+    uint32_t lo = __dp4a(m0, 0x08040201u, 0u);
+    lo = __dp4a(m1, 0x80402010u, lo);
+    uint32_t hi = __dp4a(m2, 0x08040201u, 0u);
+    hi = __dp4a(m3, 0x80402010u, hi);
+    return hi * 256u + lo;
+}
+__device__ __forceinline__ uint32_t nl_mask32r(const uint4& a, const uint4& b, uint32_t c7f, uint32_t pat) {
+    const uint32_t x0 = flags_to_x16(eq_flags(a.x, c7f, pat), eq_flags(a.y, c7f, pat), eq_flags(a.z, c7f, pat), eq_flags(a.w, c7f, pat));
+    const uint32_t x1 = flags_to_x16(eq_flags(b.x, c7f, pat), eq_flags(b.y, c7f, pat), eq_flags(b.z, c7f, pat), eq_flags(b.w, c7f, pat));
+    return x1 * 512u + (x0 >> 7);
+}
 // 'G' (0x47) and 'C' (0x43) differ only in bit 2
 __device__ __forceinline__ uint32_t gc_flags(uint32_t x, uint32_t c7b, uint32_t c7f, uint32_t pat) {
     const uint32_t t = (x & c7b) ^ pat;
@@ -44,6 +58,12 @@ __device__ __forceinline__ uint32_t gc_flags(uint32_t x, uint32_t c7b, uint32_t 
 __device__ __forceinline__ uint32_t gc_mask16r(const uint4& v, uint32_t c7b, uint32_t c7f, uint32_t pat) {
     return flags_to_mask16(gc_flags(v.x, c7b, c7f, pat), gc_flags(v.y, c7b, c7f, pat), gc_flags(v.z, c7b, c7f, pat),
                            gc_flags(v.w, c7b, c7f, pat));
+}
+
+__device__ __forceinline__ uint32_t gc_mask32r(const uint4& a, const uint4& b, uint32_t c7b, uint32_t c7f, uint32_t pat) {
+    const uint32_t x0 = flags_to_x16(gc_flags(a.x, c7b, c7f, pat), gc_flags(a.y, c7b, c7f, pat), gc_flags(a.z, c7b, c7f, pat), gc_flags(a.w, c7b, c7f, pat));
+    const uint32_t x1 = flags_to_x16(gc_flags(b.x, c7b, c7f, pat), gc_flags(b.y, c7b, c7f, pat), gc_flags(b.z, c7b, c7f, pat), gc_flags(b.w, c7b, c7f, pat));
+    return x1 * 512u + (x0 >> 7);
 }
 
 // ---------------------------------------------------------------- TMA / mbarrier
