@@ -188,6 +188,21 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+// Read-only loads of data that does not change while a tile is being worked on (the tile buffer after its TMA fill, the
+// LUTs): NOT volatile, so the scheduler may overlap the load -> IDP chains of independent newlines instead of keeping
+// every shared-memory access in program order.  `tok` is a value produced by a volatile asm AFTER the buffer became
+// readable (see the tile loop): the data dependence keeps the loads below that point, and a new value per tile keeps
+// the compiler from reusing a result across tiles.
+__device__ __forceinline__ uint4 lds128_ro(uint32_t addr, uint32_t tok) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "r"(tok));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8_ro(uint32_t addr, uint32_t tok) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr), "r"(tok));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));
@@ -221,6 +236,9 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 }
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};\n" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts64_if(bool on, uint32_t addr, uint32_t x, uint32_t y) {  // predicated, not branched around
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %3, 0;\n @p st.shared.v2.u32 [%0], {%1,%2};\n}\n" ::"r"(addr), "r"(x), "r"(y), "r"((uint32_t)on) : "memory");
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t x) {
     asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(addr), "r"(x) : "memory");
@@ -365,6 +383,10 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             if (partial && a.n - tile_base < WT_BYTES) last_known = (int)(a.n - tile_base) - 1;
         }
 
+        // the buffer is readable from here on: the read-only loads below hang on this token (see lds128_ro)
+        uint32_t tok;
+        asm volatile("mov.u32 %0, %1;\n" : "=r"(tok) : "r"(tile) : "memory");
+
         // ---- A. analysis of the lane's row: two 64-byte halves
         uint32_t w_nl[4];  // newline mask of the row, 32 bytes per word
         uint64_t gm[2] = {0, 0};
@@ -375,8 +397,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             int pre[8];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const uint4 c0 = lds128(rowx ^ ((4 * h + 0) << 4)), c1 = lds128(rowx ^ ((4 * h + 1) << 4)), c2 = lds128(rowx ^ ((4 * h + 2) << 4)),
-                            c3 = lds128(rowx ^ ((4 * h + 3) << 4));
+                const uint4 c0 = lds128_ro(rowx ^ ((4 * h + 0) << 4), tok), c1 = lds128_ro(rowx ^ ((4 * h + 1) << 4), tok),
+                            c2 = lds128_ro(rowx ^ ((4 * h + 2) << 4), tok), c3 = lds128_ro(rowx ^ ((4 * h + 3) << 4), tok);
                 w_nl[2 * h] = nl_mask32r(c0, c1, c7f, pat_nl);
                 w_nl[2 * h + 1] = nl_mask32r(c2, c3, c7f, pat_nl);
                 if (kQual) {
@@ -482,29 +504,29 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             const int pos = lane_off + p;
             int ps = 0, pg = 0;
             if (kQual) {
-                const uint4 v = lds128(rowx ^ (uint32_t)(p & 0x70));
-                const uint4 w = lds128(wlut_u32 + (uint32_t)((p & 15) << 4));
-                int acc = lds_s16(cpre_u32 | (uint32_t)((p >> 3) & 0xE));
-                acc = __dp4a((int)v.x, (int)w.x, acc);
+                const uint4 v = lds128_ro(rowx ^ (uint32_t)(p & 0x70), tok);
+                const uint4 w = lds128_ro(wlut_u32 + (uint32_t)((p & 15) << 4), tok);
+                const int cp = lds_s16(cpre_u32 | (uint32_t)((p >> 3) & 0xE));  // written by this lane above: stays in program order
+                int acc = __dp4a((int)v.x, (int)w.x, ex_s);
                 acc = __dp4a((int)v.y, (int)w.y, acc);
                 acc = __dp4a((int)v.z, (int)w.z, acc);
                 acc = __dp4a((int)v.w, (int)w.w, acc);
-                ps = acc + ex_s;
+                ps = acc + cp;
             }
             if (kSeq) pg = p < 64 ? ex_g + __popcll(gm[0] & low_bits64(p)) : ex_g + g0 + __popcll(gm[1] & low_bits64(p - 64));
             // neighbours: byte q of the lane's own row sits at rowx ^ q (rowx is 16-byte aligned and the swizzle is an XOR
             // of bits 4..6); the byte before the row / after it at a per-lane offset of the buffer (lane 0 / 31: clamped
             // into the row; the byte before the tile's first byte is patched in below, the byte after its last one gets
             // no verdict: last_known)
-            const uint32_t before = lds8(p == 0 ? a_prev : (rowx ^ (uint32_t)(p - 1)));
-            const uint32_t after = lds8(p == 127 ? a_next : (rowx ^ (uint32_t)(p + 1)));
+            const uint32_t before = lds8_ro(p == 0 ? a_prev : (rowx ^ (uint32_t)(p - 1)), tok);
+            const uint32_t after = lds8_ro(p == 127 ? a_next : (rowx ^ (uint32_t)(p + 1)), tok);
             // a CR directly before a real LF is stripped; the virtual '\n' at EOF strips nothing
             const uint32_t cr = (before == '\r' && pos != virt) ? 1u : 0u;
             // '@' / '+' flags of the next line's first byte; 3 = that byte is not in this tile or range: no verdict here
-            const uint32_t nfk = lds8(nflut_u32 + after);
+            const uint32_t nfk = lds8_ro(nflut_u32 + after, tok);
             const uint32_t nf = pos < last_known ? nfk : 3u;
             const uint32_t idx = (uint32_t)(ex_cnt + k - base);
-            if (k < cnt && (decltype(one_pass)::value || idx < (uint32_t)ENT_CAP)) sts64(ent_u32 + idx * 8u, (uint32_t)ps, rec_pack(pos, cr, nf, kSeq ? pg : 0));
+            sts64_if(k < cnt && (decltype(one_pass)::value || idx < (uint32_t)ENT_CAP), ent_u32 + idx * 8u, (uint32_t)ps, rec_pack(pos, cr, nf, kSeq ? pg : 0));
         };
         // the byte before the tile's first byte lives in global memory: a newline at position 0 of the tile (entry 0,
         // filed by lane 0) learns its CR flag here (rare, so it is kept out of file_entry)
@@ -514,8 +536,9 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                 if (tile_base - 1 >= (a.prev ? 0 : a.begin) && buf[tile_base - 1] == '\r') sts32(ent_u32 + 4u, lds32(ent_u32 + 4u) | (1u << 12));
             }
         };
-        // B2 for entries i0 + lane of a pass that starts at tile-local index `base` and holds nb entries
-        auto lines = [&](int i0, int nb, int base, auto one_pass) {
+        // B2 for entries i0 + lane of a pass that starts at tile-local index `base` and holds nb entries.  Returns whether
+        // this lane's line sits exactly ON the threshold (rare: the two roundings of the reference decide, see `settle`).
+        auto lines = [&](int i0, int nb, int base, auto one_pass, int& qs, uint32_t& len) -> bool {
             const int i = i0 + lane;
             const bool valid = i < nb;
             const uint2 e = lds64(ent_u32 + (uint32_t)i * 8u);  // i < ENT_CAP: in range even when not valid
@@ -524,6 +547,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             if (!kFused) {
                 const int t = base + i;
                 if (valid && (t < rec_n0 ? rec_ok0 : blk_ok)) a.records[t < rec_n0 ? rec_off0 + t : rec_off1 + (t - rec_n0)] = e;
+                return false;
             } else {
                 // the line that STARTS after newline i is line i + 1 of the tile: a header under h = -(i + 1), a plus
                 // line under h = 2 - (i + 1).  nf: 0 -> both contradicted, 1 ('+') -> header, 2 ('@') -> plus, 3 -> none
@@ -532,8 +556,8 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                 // empty line's newline is the previous newline), so the length needs no clamp.
                 const bool line = valid && (i | base) != 0;
                 const uint32_t cr = rec_cr(e.y);
-                const uint32_t len = (uint32_t)(rec_pos(e.y) - rec_pos(pe.y) - 1) - cr;
-                const int qs = (int)e.x - (int)pe.x - 10 - 13 * (int)cr - 33 * (int)len;
+                len = (uint32_t)(rec_pos(e.y) - rec_pos(pe.y) - 1) - cr;
+                qs = (int)e.x - (int)pe.x - 10 - 13 * (int)cr - 33 * (int)len;
                 if (plan.i32) {
                     // ee = +-2^sh (sum - c n), exact in 32 bits; ee != 0 means |sum - c n| >= 2^-20 > 1e-7, which puts the
                     // exact quotient more than 40 ulp from c (see exb_mean_cmp): the sign of ee is the verdict.  n = 0: ee = 0.
@@ -542,36 +566,52 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                         f_cq += 1u + (len << 12);
                         f_qs += qs;
                     }
-                    const bool close = line && ee == 0;
-                    if (__any_sync(0xffffffffu, close)) {  // rare: the two roundings of the reference decide
-                        if (close && fused_pass_general(s_preds, a.n_fused, plan.simple, plan.c, plan.op, plan.want_pos, qs, len)) {
-                            f_cq += 1u + (len << 12);
-                            f_qs += qs;
-                        }
-                    }
-                } else if (line && fused_pass(s_preds, a.n_fused, plan, qs, len)) {
+                    return line && ee == 0;
+                }
+                if (line && fused_pass(s_preds, a.n_fused, plan, qs, len)) {
                     f_cq += 1u + (len << 12);
                     f_qs += qs;
                 }
+                return false;
+            }
+        };
+        auto settle = [&](bool close, int qs, uint32_t len) {
+            if (close && fused_pass_general(s_preds, a.n_fused, plan.simple, plan.c, plan.op, plan.want_pos, qs, len)) {
+                f_cq += 1u + (len << 12);
+                f_qs += qs;
             }
         };
 
         if (rounds <= 2) {  // warp-uniform; at most 64 newlines: one pass
-            if (rounds >= 1) {
-                // first newline of the row: ctz per word (0xFFFFFFFF for an empty word survives the OR), unsigned min
-                const uint32_t c0 = bfind_sh(__brev(w_nl[0])), c1 = bfind_sh(__brev(w_nl[1])) | 32u, c2 = bfind_sh(__brev(w_nl[2])) | 64u,
-                               c3 = bfind_sh(__brev(w_nl[3])) | 96u;
-                file_entry(0, (int)(min(min(c0, c1), min(c2, c3)) & 127u), 0, std::true_type());
-            }
+            // first newline of the row: ctz per word (0xFFFFFFFF for an empty word survives the OR), unsigned min;
+            // last newline of the row: find-last per word (-1 for an empty word survives the OR), signed max.
+            // Two rounds (the common case) run as ONE straight-line block so that their load -> IDP chains overlap.
+            const uint32_t c0 = bfind_sh(__brev(w_nl[0])), c1 = bfind_sh(__brev(w_nl[1])) | 32u, c2 = bfind_sh(__brev(w_nl[2])) | 64u,
+                           c3 = bfind_sh(__brev(w_nl[3])) | 96u;
+            const int p_first = (int)(min(min(c0, c1), min(c2, c3)) & 127u);
             if (rounds == 2) {
-                // last newline of the row: find-last per word (-1 for an empty word survives the OR), signed max
                 const int d0 = bfind_u32(w_nl[0]), d1 = bfind_u32(w_nl[1]) | 32, d2 = bfind_u32(w_nl[2]) | 64, d3 = bfind_u32(w_nl[3]) | 96;
-                file_entry(1, max(max(d0, d1), max(d2, d3)) & 127, 0, std::true_type());
+                const int p_last = max(max(d0, d1), max(d2, d3)) & 127;
+                file_entry(0, p_first, 0, std::true_type());
+                file_entry(1, p_last, 0, std::true_type());
+            } else if (rounds == 1) {
+                file_entry(0, p_first, 0, std::true_type());
             }
             patch_entry0();
             __syncwarp();
-            if (n_events > 0) lines(0, n_events, 0, std::true_type());
-            if (n_events > 32) lines(32, n_events, 0, std::true_type());
+            int qs0 = 0, qs1 = 0;
+            uint32_t len0 = 0, len1 = 0;
+            if (n_events > 32) {
+                const bool close0 = lines(0, n_events, 0, std::true_type(), qs0, len0);
+                const bool close1 = lines(32, n_events, 0, std::true_type(), qs1, len1);
+                if (kFused && __any_sync(0xffffffffu, close0 || close1)) {
+                    settle(close0, qs0, len0);
+                    settle(close1, qs1, len1);
+                }
+            } else if (n_events > 0) {
+                const bool close0 = lines(0, n_events, 0, std::true_type(), qs0, len0);
+                if (kFused && __any_sync(0xffffffffu, close0)) settle(close0, qs0, len0);
+            }
             e_first = lds64(ent_u32);
             e_last = lds64(ent_u32 + (uint32_t)(n_events > 0 ? n_events - 1 : 0) * 8u);
         } else {
@@ -588,7 +628,12 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                 if (base == 0) patch_entry0();
                 __syncwarp();
                 const int nb = n_events - base < ENT_CAP ? n_events - base : ENT_CAP;
-                for (int i0 = 0; i0 < nb; i0 += 32) lines(i0, nb, base, std::false_type());
+                for (int i0 = 0; i0 < nb; i0 += 32) {
+                    int qs0 = 0;
+                    uint32_t len0 = 0;
+                    const bool close0 = lines(i0, nb, base, std::false_type(), qs0, len0);
+                    if (kFused && __any_sync(0xffffffffu, close0)) settle(close0, qs0, len0);
+                }
                 if (base == 0) e_first = lds64(ent_u32);  // the tile's first newline: K2 finishes the line it ends
                 if (base + ENT_CAP >= n_events) {
                     e_last = lds64(ent_u32 + (uint32_t)(nb - 1) * 8u);  // the tile's last newline
@@ -601,7 +646,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
 
         // ---- C. tail word: what follows the tile's last newline (local information only)
         {
-            const uint32_t b0 = lds8(nflut_u32 + lds8(b0_addr));
+            const uint32_t b0 = lds8_ro(nflut_u32 + lds8_ro(b0_addr, tok), tok);
             uint64_t tw;
             if (n_events > 0) {
                 tw = tail_pack(2, (rec_next_flags(e_last.y) << 2) | b0, (uint32_t)(rec_pos(e_last.y) + 1), (uint32_t)(total_g - rec_pg(e_last.y)),
