@@ -39,6 +39,10 @@ class Predicate(C.Structure):
     _fields_ = [("field", C.c_int32), ("op", C.c_int32), ("value", C.c_double)]
 
 
+class FormatCols(C.Structure):
+    _fields_ = [("d_off", C.c_void_p * 4), ("d_data", C.c_void_p * 4), ("d_desc_valid", C.c_void_p)]
+
+
 class ReaderResult(C.Structure):
     _fields_ = [("error", C.c_void_p)]
 
@@ -181,6 +185,14 @@ SIGNATURES = {
     "exb_seq_map_host": (_i32, [_vp, _i64, _i32, _vp, C.POINTER(_i64)]),
     "exb_translate_host": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "exb_quality_decode_host": (_i32, [_vp, _i64, _vp]),
+    "exb_format_scratch_bytes": (_i64, [_i64]),
+    "exb_fastq_format": (_i32, [C.POINTER(FormatCols), _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "exb_fasta_format": (_i32, [C.POINTER(FormatCols), _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "exb_format_finish": (_i32, [_vp, _i64, _vp, _i64, C.POINTER(_i64), _vp]),
+    "exb_writer_open": (_i32, [C.c_char_p, C.c_char_p, C.c_char_p, _i32, _i32, C.POINTER(_vp)]),
+    "exb_writer_set_line_width": (_i32, [_vp, _i32]),
+    "exb_writer_append": (_i32, [_vp, _i64, C.POINTER(_vp), C.POINTER(_vp), _vp]),
+    "exb_writer_close": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "exb_fastq_count_host": (_i32, [_vp, _i64, C.POINTER(Predicate), _i32, _i64, _i32, C.POINTER(_i64), C.POINTER(ScanResult)]),
     "exb_engine_create": (_i32, [_i32, _i64, C.POINTER(_vp)]),
     "exb_engine_destroy": (None, [_vp]),

@@ -113,4 +113,22 @@ cudaError_t fasta_scan_launch(const FastaScanArgs& a, int flags, cudaStream_t st
 int64_t fasta_scan_tiles(int64_t begin, int64_t n, int is_final);
 int64_t fasta_workspace_payload(int64_t n_tiles);
 
+// ---- writers (writer_ops.cu): columns in HBM -> FASTQ / FASTA file image
+struct FormatArgs {
+    const int64_t* off[4];    // FASTQ: name, description, sequence, quality; FASTA: id, description, sequence
+    const uint8_t* data[4];
+    const uint8_t* desc_valid;  // one byte per row, may be null (all valid)
+    int64_t n_rows;
+    int line_width;           // FASTA
+    uint32_t* lens;           // [n_rows] bytes per record in the image
+    const int64_t* row_off;   // [n_rows + 1] exclusive scan of lens
+    uint8_t* out;
+    int64_t out_cap;          // bytes of `out`; a record that does not fit is skipped and counted
+    int64_t* long_rows;       // [n_rows] rows above LONG_ROW
+    unsigned long long* counters;  // [0] number of long rows, [1] ~(first row whose record exceeds 4 GiB), 0 = none,
+                                   // [2] records that did not fit out_cap
+};
+cudaError_t format_len_launch(const FormatArgs& a, bool fasta, cudaStream_t st);
+cudaError_t format_rows_launch(const FormatArgs& a, bool fasta, cudaStream_t st);
+
 }  // namespace exb

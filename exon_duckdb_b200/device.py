@@ -488,3 +488,73 @@ def quality_score_string_to_list(col):
     out = _empty(nb, torch.int32, col.offsets.device)
     check(lib().exb_quality_decode(_ptr(col.data), nb, _ptr(out), _stream()))
     return out
+
+
+# ------------------------------------------------------------------ writers (COPY ... TO (FORMAT 'fastq' | 'fasta'))
+def _format(fasta, cols, line_width=80, out_cap=None):
+    """Columns on the device -> (file image uint8 tensor, record offsets int64 tensor)."""
+    n_cols = 3 if fasta else 4
+    assert len(cols) == n_cols
+    n = len(cols[0])
+    dev = cols[0].offsets.device
+    fc = _lib.FormatCols()
+    for i, c in enumerate(cols):
+        fc.d_off[i] = _ptr(c.offsets).value
+        fc.d_data[i] = _ptr(c.data).value
+    valid = cols[1].valid
+    if valid is not None and valid.dtype != torch.uint8:
+        valid = valid.to(torch.uint8)
+    fc.d_desc_valid = _ptr(valid).value if valid is not None else None
+    if out_cap is None:
+        seq_bytes = int(cols[2].data.numel())
+        out_cap = sum(int(c.data.numel()) for c in cols) + 8 * n + (seq_bytes // max(line_width, 1) + n if fasta else 0)
+    out = alloc_input(out_cap, dev)
+    row_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(lib().exb_format_scratch_bytes(n), dtype=torch.uint8, device=dev)
+    if fasta:
+        check(lib().exb_fasta_format(C.byref(fc), n, line_width, _ptr(row_off), _ptr(out), out_cap, _ptr(scratch), scratch.numel(), _stream()))
+    else:
+        check(lib().exb_fastq_format(C.byref(fc), n, _ptr(row_off), _ptr(out), out_cap, _ptr(scratch), scratch.numel(), _stream()))
+    nb = C.c_int64(0)
+    check(lib().exb_format_finish(_ptr(row_off), n, _ptr(scratch), out_cap, C.byref(nb), _stream()))
+    return out[: nb.value], row_off
+
+
+def fastq_format(name, description, sequence, quality_scores, out_cap=None):
+    """The FASTQ file image of four device Columns (the inverse of fastq_table)."""
+    return _format(False, [name, description, sequence, quality_scores], out_cap=out_cap)
+
+
+def fasta_format(id, description, sequence, line_width=80, out_cap=None):
+    """The FASTA file image of three device Columns, sequences wrapped at `line_width` (the inverse of fasta_table)."""
+    return _format(True, [id, description, sequence], line_width, out_cap)
+
+
+class Writer:
+    """exb_writer_*: HOST columns -> file, formatted on the GPU (what the DuckDB copy function drives)."""
+
+    def __init__(self, path, file_format, compression=None, force=False, device=0, line_width=None):
+        self._w = C.c_void_p()
+        check(lib().exb_writer_open(path.encode(), file_format.encode(), compression.encode() if compression else None, int(force), device,
+                                    C.byref(self._w)))
+        self.n_cols = 3 if file_format.lower() == "fasta" else 4
+        if line_width is not None:
+            check(lib().exb_writer_set_line_width(self._w, line_width))
+
+    def append(self, columns, desc_valid=None):
+        """columns: list of (int64 numpy offsets[n + 1], uint8 numpy data); desc_valid: uint8 numpy [n] or None."""
+        import numpy as np
+
+        assert len(columns) == self.n_cols
+        n = len(columns[0][0]) - 1
+        keep = [(np.ascontiguousarray(o, np.int64), np.ascontiguousarray(d, np.uint8)) for o, d in columns]
+        offs = (C.c_void_p * 4)(*[o.ctypes.data for o, _ in keep] + [None] * (4 - self.n_cols))
+        dats = (C.c_void_p * 4)(*[d.ctypes.data for _, d in keep] + [None] * (4 - self.n_cols))
+        v = np.ascontiguousarray(desc_valid, np.uint8) if desc_valid is not None else None
+        check(lib().exb_writer_append(self._w, n, offs, dats, v.ctypes.data if v is not None else None))
+
+    def close(self):
+        rows, nbytes = C.c_int64(0), C.c_int64(0)
+        w, self._w = self._w, None
+        check(lib().exb_writer_close(w, C.byref(rows), C.byref(nbytes)))
+        return rows.value, nbytes.value

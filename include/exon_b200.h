@@ -558,6 +558,47 @@ EXB_API int exb_translate_host(const int64_t *offsets, const uint8_t *data, int6
                                int64_t *status);
 EXB_API int exb_quality_decode_host(const uint8_t *data, int64_t n_bytes, int32_t *out);
 
+/* ---- writers: the inverse of the scan --------------------------------------------------------
+ * Replace FastqFunctions::GetFastqCopyFunction (exon/include/exon/fastq_functions/module.hpp:30) and its FASTA twin:
+ * `COPY ... TO 'file' (FORMAT 'fastq' | 'fasta' [, COMPRESSION 'gzip' | 'zstd'] [, FORCE true])`
+ * (test/sql/exondb-release-with-deb-info/test_fastq_copy.test, test_fasta_copy.test; both commented out in the
+ * reference because it removed the writers).  Record layout (noodles-fastq / noodles-fasta writers):
+ *   FASTQ  '@' name [' ' description] '\n' sequence '\n' '+' '\n' quality_scores '\n'
+ *   FASTA  '>' id [' ' description] '\n' sequence in lines of `line_width` bases (noodles default: 80), each + '\n'
+ * A NULL or empty description writes no space.
+ *
+ * Device layer: Arrow-style columns already in HBM -> file image in HBM.  d_off[c] has n_rows + 1 entries (need not
+ * start at 0) and indexes d_data[c] (4-byte aligned base); columns are name / id, description, sequence and -- FASTQ
+ * only -- quality_scores; d_desc_valid (one byte per row) may be NULL.  d_row_off receives n_rows + 1 record offsets
+ * of the image.  d_scratch: exb_format_scratch_bytes(n_rows).  Asynchronous on `stream`; exb_format_finish
+ * synchronises, reports the image size and fails with EXB_ERR_CAPACITY if out_cap was too small (records that did
+ * not fit were skipped, nothing was written out of bounds). */
+typedef struct exb_format_cols {
+    const int64_t *d_off[4];
+    const uint8_t *d_data[4];
+    const uint8_t *d_desc_valid;
+} exb_format_cols;
+EXB_API int64_t exb_format_scratch_bytes(int64_t n_rows);
+EXB_API int exb_fastq_format(const exb_format_cols *cols, int64_t n_rows, int64_t *d_row_off, uint8_t *d_out,
+                             int64_t out_cap, void *d_scratch, int64_t scratch_bytes, void *stream);
+EXB_API int exb_fasta_format(const exb_format_cols *cols, int64_t n_rows, int line_width, int64_t *d_row_off,
+                             uint8_t *d_out, int64_t out_cap, void *d_scratch, int64_t scratch_bytes, void *stream);
+EXB_API int exb_format_finish(const int64_t *d_row_off, int64_t n_rows, const void *d_scratch, int64_t out_cap,
+                              int64_t *out_bytes, void *stream);
+
+/* Host layer: a file being written.  compression: NULL / "" / "auto" = by suffix (.gz, .zst), "gzip" | "gz",
+ * "zstd" | "zst", "none"; force = 0 refuses to replace an existing regular file (the reference's FORCE option).
+ * exb_writer_append takes HOST columns in the same offsets + bytes form (offsets need not start at 0), stages them in
+ * pinned memory and formats on `device` whenever ~64 MiB are staged; rows keep their order.  exb_writer_close flushes,
+ * closes the file and frees the writer (also after a failure). */
+typedef struct exb_writer exb_writer;
+EXB_API int exb_writer_open(const char *path, const char *file_format, const char *compression, int force, int device,
+                            exb_writer **out);
+EXB_API int exb_writer_set_line_width(exb_writer *writer, int line_width); /* FASTA; default 80 */
+EXB_API int exb_writer_append(exb_writer *writer, int64_t n_rows, const int64_t *const *offsets,
+                              const uint8_t *const *data, const uint8_t *desc_valid);
+EXB_API int exb_writer_close(exb_writer *writer, int64_t *rows_written, int64_t *bytes_written);
+
 /* ---- host-buffer engine (end-to-end path): parse a FASTQ held in host memory ----
  * Streams `n` host bytes through pinned staging buffers with double-buffered
  * cudaMemcpyAsync, runs scan + filter per chunk, returns the aggregates

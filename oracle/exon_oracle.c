@@ -422,3 +422,61 @@ int64_t orc_fastq_count_mean_quality(const uint8_t *b, int64_t n, int op, double
     orc_free_table(&t);
     return pass;
 }
+
+/* ------------------------------------------------------------------ writers
+ * The record writers the removed COPY TO path of the reference drove (declared at
+ * exon/include/exon/fastq_functions/module.hpp:30; tests commented out in
+ * test/sql/exondb-release-with-deb-info/test_fastq_copy.test and test_fasta_copy.test), restated from the published
+ * behaviour of the pinned crates: noodles-fastq 0.8.0 Writer::write_record ('@' name [' ' description] LF sequence LF
+ * '+' LF quality LF, the description only when it is not empty) and noodles-fasta 0.27.0 Writer (definition line
+ * '>' name [' ' description], then the sequence in lines of line_base_count bases, 80 by default).
+ * PARITY UNPINNED: the crates are not on disk and the reference has no live test of its writers; pinned only as the
+ * inverse of the parsers above (tests/test_oracle_golden.py round trips).
+ * One record at a time; returns the bytes written, or the bytes needed if `cap` is too small (nothing is cut). */
+static int64_t orc_put(uint8_t *out, int64_t cap, int64_t pos, const uint8_t *p, int64_t n) {
+    if (pos + n <= cap && n > 0) memcpy(out + pos, p, (size_t)n);
+    return pos + n;
+}
+static int64_t orc_putc(uint8_t *out, int64_t cap, int64_t pos, uint8_t c) {
+    if (pos + 1 <= cap) out[pos] = c;
+    return pos + 1;
+}
+static int64_t orc_definition(uint8_t *out, int64_t cap, int64_t pos, uint8_t lead, const int64_t *const *off,
+                              const uint8_t *const *data, const uint8_t *desc_valid, int64_t r) {
+    const int64_t dl = (desc_valid && !desc_valid[r]) ? 0 : off[1][r + 1] - off[1][r];
+    pos = orc_putc(out, cap, pos, lead);
+    pos = orc_put(out, cap, pos, data[0] + off[0][r], off[0][r + 1] - off[0][r]);
+    if (dl > 0) {
+        pos = orc_putc(out, cap, pos, ' ');
+        pos = orc_put(out, cap, pos, data[1] + off[1][r], dl);
+    }
+    return orc_putc(out, cap, pos, '\n');
+}
+int64_t orc_format_fastq(const int64_t *const *off, const uint8_t *const *data, const uint8_t *desc_valid, int64_t n_rows,
+                         uint8_t *out, int64_t cap) {
+    int64_t pos = 0;
+    for (int64_t r = 0; r < n_rows; r++) {
+        pos = orc_definition(out, cap, pos, '@', off, data, desc_valid, r);
+        pos = orc_put(out, cap, pos, data[2] + off[2][r], off[2][r + 1] - off[2][r]);
+        pos = orc_putc(out, cap, pos, '\n');
+        pos = orc_putc(out, cap, pos, '+');
+        pos = orc_putc(out, cap, pos, '\n');
+        pos = orc_put(out, cap, pos, data[3] + off[3][r], off[3][r + 1] - off[3][r]);
+        pos = orc_putc(out, cap, pos, '\n');
+    }
+    return pos;
+}
+int64_t orc_format_fasta(const int64_t *const *off, const uint8_t *const *data, const uint8_t *desc_valid, int64_t n_rows,
+                         int line_width, uint8_t *out, int64_t cap) {
+    int64_t pos = 0;
+    for (int64_t r = 0; r < n_rows; r++) {
+        pos = orc_definition(out, cap, pos, '>', off, data, desc_valid, r);
+        const uint8_t *s = data[2] + off[2][r];
+        const int64_t n = off[2][r + 1] - off[2][r];
+        for (int64_t b = 0; b < n; b += line_width) {
+            pos = orc_put(out, cap, pos, s + b, n - b < line_width ? n - b : line_width);
+            pos = orc_putc(out, cap, pos, '\n');
+        }
+    }
+    return pos;
+}

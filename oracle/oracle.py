@@ -64,6 +64,11 @@ def lib():
             C.c_void_p, C.c_int64, C.c_int, C.c_double,
             C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_fastq_count_mean_quality.restype = C.c_int64
+        pp = C.POINTER(C.c_void_p)
+        L.orc_format_fastq.argtypes = [pp, pp, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.orc_format_fastq.restype = C.c_int64
+        L.orc_format_fasta.argtypes = [pp, pp, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64]
+        L.orc_format_fasta.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -227,3 +232,42 @@ def fastq_count_mean_quality(buf, op, c):
     if p < 0:
         raise OracleError("parse error", -1)
     return int(p), nr.value, gc.value, tot.value
+
+
+def pack_strings(strings):
+    """list of bytes / None -> (int64 offsets[n + 1], uint8 data, bool valid[n]); None counts as empty and not valid."""
+    lens = np.fromiter((0 if x is None else len(x) for x in strings), np.int64, len(strings))
+    off = np.zeros(len(strings) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    data = np.frombuffer(b"".join(x for x in strings if x is not None), np.uint8).copy()
+    if data.size == 0:
+        data = np.zeros(4, np.uint8)
+    valid = np.fromiter((x is not None for x in strings), np.uint8, len(strings))
+    return off, data, valid
+
+
+def _format(fasta, columns, line_width=80):
+    """columns: lists of bytes (description entries may be None) -> the file image as bytes."""
+    n_cols = 3 if fasta else 4
+    assert len(columns) == n_cols
+    n = len(columns[0])
+    packed = [pack_strings(c) for c in columns]
+    offs = (C.c_void_p * 4)(*[p[0].ctypes.data for p in packed] + [None] * (4 - n_cols))
+    dats = (C.c_void_p * 4)(*[p[1].ctypes.data for p in packed] + [None] * (4 - n_cols))
+    valid = packed[1][2]
+    cap = sum(int(p[0][-1]) for p in packed) + 8 * n + (int(packed[2][0][-1]) // max(line_width, 1) + n if fasta else 0) + 16
+    out = np.zeros(cap, np.uint8)
+    if fasta:
+        m = lib().orc_format_fasta(offs, dats, valid.ctypes.data, n, line_width, out.ctypes.data, cap)
+    else:
+        m = lib().orc_format_fastq(offs, dats, valid.ctypes.data, n, out.ctypes.data, cap)
+    assert 0 <= m <= cap, (m, cap)
+    return out[:m].tobytes()
+
+
+def format_fastq(names, descriptions, sequences, qualities):
+    return _format(False, [names, descriptions, sequences, qualities])
+
+
+def format_fasta(ids, descriptions, sequences, line_width=80):
+    return _format(True, [ids, descriptions, sequences], line_width)

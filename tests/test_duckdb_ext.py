@@ -107,6 +107,26 @@ def test_no_gpu_is_a_loud_error():
     assert not r[1]["ok"] and "no CUDA device" in r[1]["error"]
 
 
+def test_copy_functions_bind_like_the_removed_reference_writers(tmp_path):
+    # test_fasta_copy.test:43-50 (commented out in the reference): an existing target is an error unless FORCE is given;
+    # unknown options, wrong column counts and non-VARCHAR columns are bind errors.  No GPU is touched at bind.
+    existing = tmp_path / "there.fasta"
+    existing.write_bytes(b">a\nACGT\n")
+    r = run_sql(PRODUCT, [
+        "COPY (SELECT * FROM read_fasta('%s/test.fasta')) TO '%s' (FORMAT 'fasta')" % (G, existing),
+        "COPY (SELECT 1 AS a, 'x' AS b, 'y' AS c) TO '%s/n.fasta' (FORMAT 'fasta')" % tmp_path,
+        "COPY (SELECT 'a' AS a, 'x' AS b) TO '%s/n.fastq' (FORMAT 'fastq')" % tmp_path,
+        "COPY (SELECT 'a' AS a, 'x' AS b, 'y' AS c) TO '%s/n.fasta' (FORMAT 'fasta', NOPE 1)" % tmp_path,
+        "COPY (SELECT 'a' AS a, 'x' AS b, 'y' AS c) TO '%s/n.fasta' (FORMAT 'fasta', COMPRESSION 'brotli')" % tmp_path,
+    ])
+    assert not r[0]["ok"] and "exists" in r[0]["error"] and "FORCE" in r[0]["error"]
+    assert not r[1]["ok"] and "VARCHAR" in r[1]["error"]
+    assert not r[2]["ok"] and "4 columns" in r[2]["error"]
+    assert not r[3]["ok"] and "Unknown option" in r[3]["error"]
+    assert not r[4]["ok"]
+    assert existing.read_bytes() == b">a\nACGT\n"
+
+
 # ------------------------------------------------------------------ GPU: the reference's sqllogictests replayed
 FASTQ_SCAN = [  # test_fastq_scan.test
     ("SELECT count(*) FROM read_fastq('{G}/test.fastq')", [["2"]]),
@@ -511,3 +531,79 @@ def test_one_pipeline_per_gpu_gives_the_same_answers(cuda_device, tmp_path):
         real = run_sql(PRODUCT, [s.replace("')", "', gpus=%d)" % n_dev) for s in stmts], threads=n_dev, env={"EXON_B200_CHUNK_BYTES": str(300_000)})
         for a, b in zip(one, real):
             assert rows(a) == rows(b)
+
+
+@pytest.mark.gpu
+def test_copy_to_fastq_replays_the_reference_copy_test(tmp_path):
+    # test/sql/exondb-release-with-deb-info/test_fastq_copy.test, statement by statement (the reference keeps it commented
+    # out since it removed its writers); COPY returns the number of records written
+    from oracle import oracle as O
+    T = str(tmp_path)
+    src = "%s/test.fastq" % G
+    r = run_sql(PRODUCT, [
+        "COPY (SELECT * FROM read_fastq('%s')) TO '%s/test.fastq' (FORMAT 'fastq')" % (src, T),
+        "COPY (FROM read_fastq('%s')) TO '%s/test.fastq.gz' (FORMAT 'fastq')" % (src, T),
+        "COPY (SELECT * FROM read_fastq('%s')) TO '%s/test.fastq.zst' (FORMAT 'fastq')" % (src, T),
+        "COPY (SELECT * FROM read_fastq('%s')) TO '%s/test.fastq.gzip' (FORMAT 'fastq', COMPRESSION 'gzip')" % (src, T),
+        "COPY (SELECT * FROM read_fastq('%s')) TO '%s/test.fastq.gzip' (FORMAT 'fastq', COMPRESSION 'gzip', FORCE true)" % (src, T),
+        "SELECT COUNT(*) FROM read_fastq('%s/test.fastq.gzip', compression='gzip')" % T,
+        "COPY (SELECT * FROM read_fastq('%s')) TO '%s/test.fastq.zstd' (FORMAT 'fastq', COMPRESSION 'zstd')" % (src, T),
+        "SELECT COUNT(*) FROM read_fastq('%s/test.fastq.zstd', compression='zstd')" % T,
+        "SELECT COUNT(*) FROM read_fastq('%s/test.fastq.gz')" % T,
+        "SELECT COUNT(*) FROM '%s/test.fastq.zst'" % T,
+        "SELECT * FROM read_fastq('%s/test.fastq') EXCEPT SELECT * FROM read_fastq('%s')" % (T, src),
+    ])
+    assert [int(scalar(x)) for x in r[:5]] == [2, 2, 2, 2, 2]
+    assert int(scalar(r[5])) == 2 and int(scalar(r[6])) == 2 and int(scalar(r[7])) == 2 and int(scalar(r[8])) == 2 and int(scalar(r[9])) == 2
+    assert rows(r[10]) == []
+    # the reference's fixture is in canonical form, so the plain copy reproduces it byte for byte -- and equals the oracle's writer
+    text = open(src, "rb").read()
+    t = O.parse_fastq(text)
+    want = O.format_fastq(t.strings("name"), t.strings("description"), t.strings("sequence"), t.strings("quality_scores"))
+    assert open(T + "/test.fastq", "rb").read() == want == text
+
+
+@pytest.mark.gpu
+def test_copy_to_fasta_replays_the_reference_copy_test(tmp_path):
+    # test_fasta_copy.test: plain, .gz, .zst, FORCE, explicit COMPRESSION, and the mixed NULL-description round trip (:74-86)
+    from oracle import oracle as O
+    T = str(tmp_path)
+    src = "%s/test.fasta" % G
+    r = run_sql(PRODUCT, [
+        "COPY (SELECT * FROM read_fasta('%s')) TO '%s/test.fasta' (FORMAT 'fasta')" % (src, T),
+        "SELECT COUNT(*) FROM read_fasta('%s/test.fasta')" % T,
+        "COPY (SELECT * FROM read_fasta('%s')) TO '%s/test.fasta.gz' (FORMAT 'fasta')" % (src, T),
+        "SELECT COUNT(*) FROM read_fasta('%s/test.fasta.gz')" % T,
+        "COPY (SELECT * FROM read_fasta('%s')) TO '%s/test.fasta.zst' (FORMAT 'fasta')" % (src, T),
+        "COPY (SELECT * FROM read_fasta('%s')) TO '%s/test.fasta.zst' (FORMAT 'fasta', FORCE true)" % (src, T),
+        "COPY (SELECT * FROM read_fasta('%s')) TO '%s/test.fasta.zst' (FORMAT 'fasta')" % (src, T),
+        "SELECT COUNT(*) FROM read_fasta('%s/test.fasta.zst')" % T,
+        "COPY (SELECT * FROM read_fasta('%s')) TO '%s/test.fasta.gzip' (FORMAT 'fasta', COMPRESSION 'gzip')" % (src, T),
+        "SELECT COUNT(*) FROM read_fasta('%s/test.fasta.gzip', compression='gzip')" % T,
+        "COPY (FROM read_fasta('%s/test.mixed-desc.fasta')) TO '%s/test.mixed-desc.fasta' (FORMAT 'fasta')" % (G, T),
+        "FROM read_fasta('%s/test.mixed-desc.fasta') WHERE description IS NULL" % T,
+    ])
+    assert int(scalar(r[0])) == 2 and int(scalar(r[1])) == 2 and int(scalar(r[2])) == 2 and int(scalar(r[3])) == 2 and int(scalar(r[4])) == 2 and int(scalar(r[5])) == 2
+    assert not r[6]["ok"] and "exists" in r[6]["error"]  # "Now don't force it, and expect an error"
+    assert int(scalar(r[7])) == 2 and int(scalar(r[8])) == 2 and int(scalar(r[9])) == 2 and int(scalar(r[10])) == 2
+    assert rows(r[11]) == [["b", None, "ATCG"]]
+    t = O.parse_fasta(open(src, "rb").read())
+    assert open(T + "/test.fasta", "rb").read() == O.format_fasta(t.strings("id"), t.strings("description"), t.strings("sequence"))
+
+
+@pytest.mark.gpu
+def test_copy_filters_and_rewrites_a_larger_file(tmp_path):
+    # the job the writers exist for: quality-filter a FASTQ into a new file.  The filter runs on the device inside the scan,
+    # the passing rows come back as DuckDB vectors and are formatted on the device again; order is the file's order.
+    from oracle import oracle as O
+    text, recs = util.random_fastq(77, 6000, min_len=1, max_len=250, tricky=False)
+    src = tmp_path / "in.fastq"
+    src.write_bytes(text)
+    for threads in (1, 4):
+        out = tmp_path / ("out%d.fastq" % threads)
+        r = run_sql(PRODUCT, ["COPY (SELECT * FROM read_fastq('%s') WHERE list_avg(quality_score_string_to_list(quality_scores)) > 45) "
+                              "TO '%s' (FORMAT 'fastq')" % (src, out)], threads=threads)
+        keep = [x for x in recs if O.mean_quality_pass(x[3], ">", 45.0)]
+        assert int(scalar(r[0])) == len(keep) and 0 < len(keep) < 6000
+        want = O.format_fastq([x[0] for x in keep], [x[1] for x in keep], [x[2] for x in keep], [x[3] for x in keep])
+        assert out.read_bytes() == want

@@ -158,3 +158,39 @@ def test_scalar_vectors_from_reference_build(golden_dir):
             assert O.quality_score_string_to_list(s).tolist() == case["qual"]
         if "mean_q" in case:
             assert O.mean_quality(s) == case["mean_q"]
+
+
+# ------------------------------------------------------------------ writers (parity unpinned, see exon_oracle.c)
+def test_oracle_writers_are_the_inverse_of_the_parsers(golden_dir):
+    import exb_testutil as util
+
+    # the reference's canonical fixtures come back byte for byte
+    text = open(os.path.join(golden_dir, "test.fastq"), "rb").read()
+    t = O.parse_fastq(text)
+    assert O.format_fastq(t.strings("name"), t.strings("description"), t.strings("sequence"), t.strings("quality_scores")) == text
+    for name in ("test.fasta", "test.mixed-desc.fasta"):
+        text = open(os.path.join(golden_dir, name), "rb").read()
+        t = O.parse_fasta(text)
+        img = O.format_fasta(t.strings("id"), t.strings("description"), t.strings("sequence"))
+        assert O.parse_fasta(img).rows() == t.rows()
+    # random records: parse(format(x)) == x (a NULL and an empty description are the same on disk: both parse as NULL)
+    _, recs = util.random_fastq(5, 500, tricky=False)
+    img = O.format_fastq([r[0] for r in recs], [r[1] for r in recs], [r[2] for r in recs], [r[3] for r in recs])
+    back = O.parse_fastq(img)
+    assert back.rows() == [(r[0], r[1] if r[1] else None, r[2], r[3]) for r in recs]
+    # FASTA wrapping: every sequence line but the last holds exactly line_width bases
+    seqs = [b"A" * n for n in (0, 1, 59, 60, 61, 120, 121)]
+    img = O.format_fasta([b"s%d" % i for i in range(len(seqs))], [None] * len(seqs), seqs, line_width=60)
+    assert img == b"".join(b">s%d\n" % i + b"".join(s[k:k + 60] + b"\n" for k in range(0, len(s), 60)) for i, s in enumerate(seqs))
+    assert O.parse_fasta(img).strings("sequence") == seqs
+
+
+def test_writer_without_a_gpu_is_a_loud_error(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    import ctypes as C
+    from exon_duckdb_b200 import _lib
+    w = C.c_void_p()
+    rc = _lib.lib().exb_writer_open(str(tmp_path / "x.fastq").encode(), b"fastq", None, 0, 0, C.byref(w))
+    assert rc == _lib.ERR_CUDA and b"no CUDA device" in _lib.lib().exb_last_error()
