@@ -792,21 +792,9 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const FastqScanArgs a) 
         const int n0 = (int)(w1 >> 48);
         int c_ps = 0;
         uint32_t c_y = 0;
-        for (int lo = 0; lo < n_events; lo += 32) {
-            const bool active = lo + lane < n_events;
-            uint2 r = make_uint2(0u, 0u);
+        // the per-line work of one record word: r = this line's newline, (pps, py) = the previous newline of the tile
+        auto emit_line = [&](bool active, int li, uint2 r, int pps, uint32_t py) {
             if (active) {
-                const int i = lo + lane;
-                r = a.records[i < n0 ? off0 + i : off1 + (i - n0)];
-            }
-            int pps = __shfl_up_sync(0xffffffffu, (int)r.x, 1);
-            uint32_t py = __shfl_up_sync(0xffffffffu, r.y, 1);
-            if (lane == 0) {
-                pps = c_ps;
-                py = c_y;
-            }
-            if (active) {
-                const int li = lo + lane;
                 const uint64_t g = excl + (uint64_t)li;  // global index of the line this newline ends
                 const int pos = rec_pos(r.y);
                 const int64_t e = tile_base + pos;
@@ -858,8 +846,29 @@ __global__ void __launch_bounds__(256) fastq_emit_kernel(const FastqScanArgs a) 
                     }
                 }
             }
-            c_ps = __shfl_sync(0xffffffffu, (int)r.x, 31);
-            c_y = __shfl_sync(0xffffffffu, r.y, 31);
+        };
+        // 64 records per round: both groups of 32 are loaded before either is worked on (a 4 KiB tile of 150 bp reads has ~45
+        // newlines, so this is ONE round of dependent global loads per tile instead of two -- the kernel is latency bound)
+        for (int lo = 0; lo < n_events; lo += 64) {
+            const int ia = lo + lane, ib = lo + 32 + lane;
+            const bool act_a = ia < n_events, act_b = ib < n_events;
+            uint2 ra = make_uint2(0u, 0u), rb = make_uint2(0u, 0u);
+            if (act_a) ra = a.records[ia < n0 ? off0 + ia : off1 + (ia - n0)];
+            if (act_b) rb = a.records[ib < n0 ? off0 + ib : off1 + (ib - n0)];
+            int pps_a = __shfl_up_sync(0xffffffffu, (int)ra.x, 1), pps_b = __shfl_up_sync(0xffffffffu, (int)rb.x, 1);
+            uint32_t py_a = __shfl_up_sync(0xffffffffu, ra.y, 1), py_b = __shfl_up_sync(0xffffffffu, rb.y, 1);
+            const int last_ps_a = __shfl_sync(0xffffffffu, (int)ra.x, 31);
+            const uint32_t last_y_a = __shfl_sync(0xffffffffu, ra.y, 31);
+            if (lane == 0) {
+                pps_a = c_ps;
+                py_a = c_y;
+                pps_b = last_ps_a;
+                py_b = last_y_a;
+            }
+            emit_line(act_a, ia, ra, pps_a, py_a);
+            emit_line(act_b, ib, rb, pps_b, py_b);
+            c_ps = __shfl_sync(0xffffffffu, (int)rb.x, 31);
+            c_y = __shfl_sync(0xffffffffu, rb.y, 31);
         }
       }
     }
