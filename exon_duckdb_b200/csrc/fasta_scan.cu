@@ -56,9 +56,11 @@ constexpr uint32_t ST_H = 0, ST_S = 1, ST_L = 2;  // inside a header line / insi
 //    newline is a header | [15] the last valid byte is a newline | [16] the first valid byte is '>' | [17] no valid byte
 // rest: kept | gc << 16   (lines that begin inside the tile)        head: kept | gc << 16   (the carried-in piece)
 struct alignas(16) FaTile {
-    uint32_t a, rest, head, pos0;  // pos0: position of the first newline (hdr_end of a carried-in header), 0xFFFF = none
+    uint32_t a, rest, head, pos0;  // pos0: [15:0] position of the first newline (hdr_end of a carried-in header), 0xFFFF = none;
+                                   //       [31:16] FT_REGULAR tiles with a newline: position of the last one
 };
 constexpr uint32_t FT_HAS_NL = 1u << 13, FT_HDR_LAST = 1u << 14, FT_ENDS_NL = 1u << 15, FT_B0_GT = 1u << 16, FT_EMPTY = 1u << 17;
+constexpr uint32_t FT_REGULAR = 1u << 18;  // a full interior tile whose only bytes below 0x40 are LFs (K1 tells K3: bit 3 of tile_state)
 
 __device__ __forceinline__ uint32_t ft_eff(uint32_t a, uint32_t s) { return s == ST_L ? ((a & FT_B0_GT) ? ST_H : ST_S) : s; }
 __device__ __forceinline__ uint32_t ft_out(uint32_t a, uint32_t s) {
@@ -213,8 +215,26 @@ __device__ __forceinline__ uint32_t fa_lds32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint4 fa_lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void fa_sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t fa_lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+// tile-local byte index -> byte offset in the 128B-swizzled tile buffer (sidx as two instructions)
+__device__ __forceinline__ uint32_t fa_swz(uint32_t li) { return li ^ ((li >> 3) & 0x70u); }
 __device__ __forceinline__ void fa_sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void fa_sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
+
+// 0xFF in the low k bytes of a word (k <= 0: none, k >= 4: all)
+__device__ __forceinline__ uint32_t bytes_below32c(int k) { return k >= 4 ? 0xFFFFFFFFu : (k <= 0 ? 0u : ((1u << (8 * k)) - 1u)); }
 
 // 128 x (number of bytes < 0x40 among the 16): bit 7 of x | x << 1 is set iff bit 7 or bit 6 of the byte is
 __device__ __forceinline__ uint32_t low_count128(const uint4& v, uint32_t acc) {
@@ -229,6 +249,7 @@ __device__ __forceinline__ uint32_t low_count128(const uint4& v, uint32_t acc) {
 // MODE 0: summary.  MODE 1: per-record outputs (state and bases known).  MODE 2: compaction (state and kept base known).
 struct FaTileIn {  // what K2 / K3 know about the tile from the scan
     uint32_t st;
+    uint32_t regular;  // K3: K1 found only LFs below 0x40 in this (full, interior) tile
     int64_t rec_base, kept_base, gc_base;
 };
 
@@ -243,6 +264,86 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
     const int64_t tile_base = origin + tile * WT_BYTES;
     const uint32_t pat_nl = c7f & 0x0A0A0A0Au, pat_gc = c7f & 0x43434343u;
 
+    // ---- K3, evenly wrapped tile: no dense pass at all.  K1 found only LFs below 0x40 in this tile (tile_state bit 3) and
+    // left their number and the positions of the first and the last one in its summary.  If the LFs sit on the lattice
+    // n0 + k P (lines of W = P - 1 bases: what every FASTA writer produces) -- checked by probing the lattice points, two
+    // or three bytes a lane: n_events LFs on n_events lattice points are all of them -- the position of the o-th kept
+    // byte has a closed form, o + (LFs before it), and the pass turns OUTPUT-centric: a lane builds whole 16-byte chunks
+    // of the compacted column (one unaligned 16-byte read of the tile: five swizzled words + funnel shifts; the bytes
+    // behind an LF inside the chunk moved up by one) and stores them straight to global memory, coalesced.  No masks, no
+    // per-row piece loops, no staging row (the staged path below executed ~1650 warp instructions a tile:
+    // profiles/r02e_fasta_compact_ncu.txt).
+    if (MODE == 2) {
+        if (in.regular != 0 && tile != 0 && g.s0 == 0 && g.data_end == WT_BYTES && !g.virt && in.st != ST_H) {
+            const FaTile ft = *summary;  // K1's summary of this tile
+            const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sbytes);
+            int n0 = WT_BYTES, P = 1 << 20, n_events = 0;
+            bool even = true;
+            if ((ft.pos0 & 0xFFFFu) != 0xFFFFu) {
+                n0 = (int)(ft.pos0 & 0xFFFFu);
+                const int c_last = (int)(ft.pos0 >> 16);
+                n_events = WT_BYTES - n0 - (int)(ft.rest & 0xFFFFu);
+                if (n_events >= 2) {
+                    P = (c_last - n0) / (n_events - 1);
+                    even = P * (n_events - 1) == c_last - n0 && P >= 17;
+                }
+                if (even) {
+                    bool ok = true;
+                    for (int k = lane; k < n_events; k += 32) ok = ok && fa_lds8(sb + fa_swz((uint32_t)(n0 + k * P))) == (uint32_t)'\n';
+                    even = __all_sync(0xffffffffu, ok);
+                }
+            }
+            if (even) {
+                const int total = WT_BYTES - n_events;
+                const int64_t G0 = in.kept_base;
+                if (G0 + total > a.seq_cap) {
+                    if (lane == 0) a.result->overflow = 1;
+                    return;
+                }
+                const int W = P - 1;
+                const uint32_t magic = 0xFFFFFFFFu / (uint32_t)W + 1u;  // floor(x / W) = umulhi(x, magic) for x W < 2^32
+                // byte masks "first k bytes of a 16-byte chunk" for the chunks an LF falls into: a table in the warp's G/C
+                // scratch (unused on this path; rewritten per tile because the general path overwrites it)
+                const uint32_t tab = (uint32_t)__cvta_generic_to_shared(s_gm);
+                if (lane < 16)
+                    fa_sts128(tab + 16u * (uint32_t)lane, bytes_below32c(lane), bytes_below32c(lane - 4), bytes_below32c(lane - 8), bytes_below32c(lane - 12));
+                __syncwarp();
+                uint8_t* __restrict__ gout = a.seq_out + G0;  // kept byte o of the tile -> gout[o]
+                auto lf_before = [&](int o) -> int { return o < n0 ? 0 : 1 + (int)__umulhi((uint32_t)(o - n0), magic); };
+                int h = (int)((16 - (G0 & 15)) & 15);  // kept bytes in front of the first whole 16-byte chunk
+                h = h < total ? h : total;
+                const int n_chunks = (total - h) >> 4;
+                if (lane < h) gout[lane] = (uint8_t)fa_lds8(sb + fa_swz((uint32_t)(lane + lf_before(lane))));
+                const int t0 = h + 16 * n_chunks + lane;  // ... and behind the last one (fewer than 16)
+                if (t0 < total) gout[t0] = (uint8_t)fa_lds8(sb + fa_swz((uint32_t)(t0 + lf_before(t0))));
+                for (int c = lane; c < n_chunks; c += 32) {
+                    const int o = h + 16 * c;
+                    const int m0 = lf_before(o), m1 = lf_before(o + 15);
+                    const int i0 = o + m0;
+                    const int bs = (i0 & 3) * 8;
+                    const uint32_t q = (uint32_t)(i0 & ~3);
+                    const uint32_t w0 = fa_lds32(sb + fa_swz(q)), w1 = fa_lds32(sb + fa_swz(q + 4)), w2 = fa_lds32(sb + fa_swz(q + 8)),
+                                   w3 = fa_lds32(sb + fa_swz(q + 12)), w4 = fa_lds32(sb + fa_swz(q + 16));
+                    uint4 v = make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs),
+                                         __funnelshift_r(w3, w4, bs));
+                    if (m1 != m0) {  // W >= 16: one LF at most; chunk bytes [0, k) stay, [k, 16) come from one byte further on
+                        const int k = n0 + (m1 - 1) * W - o;
+                        const uint32_t nx = w4 >> bs;  // source byte i0 + 16 in its low byte
+                        const uint4 u = make_uint4(__funnelshift_r(v.x, v.y, 8), __funnelshift_r(v.y, v.z, 8), __funnelshift_r(v.z, v.w, 8),
+                                                   __funnelshift_r(v.w, nx, 8));
+                        const uint4 km = fa_lds128(tab + 16u * (uint32_t)k);
+                        v.x = (v.x & km.x) | (u.x & ~km.x);
+                        v.y = (v.y & km.y) | (u.y & ~km.y);
+                        v.z = (v.z & km.z) | (u.z & ~km.z);
+                        v.w = (v.w & km.w) | (u.w & ~km.w);
+                    }
+                    *reinterpret_cast<uint4*>(gout + o) = v;
+                }
+                __syncwarp();  // every lane is done with the tile buffer (and the mask table) before the next TMA fill
+                return;
+            }
+        }
+    }
     // ---- A. dense masks of the lane's row
     uint64_t pm[2], gm[2];
     uint32_t low128 = 0;  // 128 x the number of bytes < 0x40 in the row (MODE 0 / 2: anything but LF among them = irregular tile)
@@ -252,7 +353,7 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint4 c0 = row[(4 * h + 0) ^ sw], c1 = row[(4 * h + 1) ^ sw], c2 = row[(4 * h + 2) ^ sw], c3 = row[(4 * h + 3) ^ sw];
-            if (MODE == 0 || MODE == 2) {
+            if (MODE == 0) {  // (the compaction pass reads K1's verdict from tile_state instead of counting again)
                 low128 = low_count128(c0, low128);
                 low128 = low_count128(c1, low128);
                 low128 = low_count128(c2, low128);
@@ -260,8 +361,11 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
             }
             pm[h] = ((uint64_t)(nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16)) << 32) |
                     (nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16));
-            gm[h] = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
-                    (gc_mask16r(c0, c7b, c7f, pat_gc) | (gc_mask16r(c1, c7b, c7f, pat_gc) << 16));
+            if (MODE != 2)  // the compaction pass moves bytes: no G/C bookkeeping
+                gm[h] = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
+                        (gc_mask16r(c0, c7b, c7f, pat_gc) | (gc_mask16r(c1, c7b, c7f, pat_gc) << 16));
+            else
+                gm[h] = 0;
         }
     }
     const int cnt = __popcll(pm[0]) + __popcll(pm[1]);
@@ -284,7 +388,7 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
             const uint32_t have = __ballot_sync(0xffffffffu, cnt > 0);
             FaTile t;
             if (have == 0) {  // one piece of a long line
-                t.a = 0;
+                t.a = FT_REGULAR;
                 t.rest = 0;
                 t.head = (uint32_t)WT_BYTES | ((uint32_t)total_g << 16);
                 t.pos0 = 0xFFFFu;
@@ -296,10 +400,10 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
                 const int pos0 = __shfl_sync(0xffffffffu, lane * ROW_BYTES + fr, first);
                 const int head_g = __shfl_sync(0xffffffffu, gb, first);
                 const int c_last = __shfl_sync(0xffffffffu, lane * ROW_BYTES + lr, last);
-                t.a = FT_HAS_NL | (c_last + 1 >= WT_BYTES ? FT_ENDS_NL : 0u);
+                t.a = FT_REGULAR | FT_HAS_NL | (c_last + 1 >= WT_BYTES ? FT_ENDS_NL : 0u);
                 t.rest = (uint32_t)(WT_BYTES - pos0 - n_events) | ((uint32_t)(total_g - head_g) << 16);
                 t.head = (uint32_t)pos0 | ((uint32_t)head_g << 16);
-                t.pos0 = (uint32_t)pos0;
+                t.pos0 = (uint32_t)pos0 | ((uint32_t)c_last << 16);  // + the last LF: K3 derives the line pitch from the two
             }
             if (lane == 0) *summary = t;
             return;
@@ -311,9 +415,7 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
     // scans, and source words come from one swizzled row (address math is 3 ops a word).
     bool fast2 = false;
     if (MODE == 2) {
-        const bool regular = tile != 0 && g.s0 == 0 && g.data_end == WT_BYTES && !g.virt && in.st != ST_H;
-        const bool odd = (int)(low128 >> 7) != cnt;
-        fast2 = regular && !__any_sync(0xffffffffu, odd);
+        fast2 = in.regular != 0 && tile != 0 && g.s0 == 0 && g.data_end == WT_BYTES && !g.virt && in.st != ST_H;
         if (fast2) {
             // 32-bit shared-window addresses + ld/st.shared: no generic-pointer arithmetic in the copy loop (with generic
             // pointers the word loop cost ~30 instructions a word: ncu r02b)
@@ -644,11 +746,13 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_tile_kernel(const __grid_con
         }
         const FaGeom g = fa_geom(a, origin, cur);
         fa_fix_edges(a, sbytes, origin, cur, full_rows, lane, g);
-        FaTileIn in{ST_S, 0, 0, 0};
+        FaTileIn in{ST_S, 0, 0, 0, 0};
         if (kCompact) {
-            in.st = a.tile_state[cur] & 3u;
+            const uint32_t ts = a.tile_state[cur];
+            in.st = ts & 3u;
+            in.regular = (ts >> 3) & 1u;
             in.kept_base = a.tile_base3[3 * cur + 1];
-            fa_tile<2>(a, sbytes, aux, origin, cur, g, c7f, c7b, in, nullptr, s_out);
+            fa_tile<2>(a, sbytes, aux, origin, cur, g, c7f, c7b, in, a.tiles + cur, s_out);
         } else {
             fa_tile<0>(a, sbytes, aux, origin, cur, g, c7f, c7b, in, a.tiles + cur, nullptr);
         }
@@ -802,7 +906,7 @@ __global__ void __launch_bounds__(FS_THREADS) fasta_scan_down_kernel(const FaTil
         const FaTile ft = tiles[tl];
         const uint32_t eff = ft_eff(ft.a, v.st);
         const bool emits = !(ft.a & FT_EMPTY) && (ft_nhs(ft.a, v.st) > 0 || (eff == ST_H && (ft.a & FT_HAS_NL)));
-        tile_state[tl] = (uint8_t)(v.st | (emits ? 4u : 0u));
+        tile_state[tl] = (uint8_t)(v.st | (emits ? 4u : 0u) | ((ft.a & FT_REGULAR) ? 8u : 0u));
         tile_base3[3 * tl + 0] = (int64_t)v.n;
         tile_base3[3 * tl + 1] = (int64_t)v.k;
         tile_base3[3 * tl + 2] = (int64_t)v.g;
