@@ -233,6 +233,13 @@ __device__ __forceinline__ uint32_t fa_swz(uint32_t li) { return li ^ ((li >> 3)
 __device__ __forceinline__ void fa_sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void fa_sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
 
+// inclusive warp scan; the shuffle's predicate output (source lane in range) guards the add: two instructions per step
+__device__ __forceinline__ uint32_t fa_incl_scan_u32p(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{\n .reg .pred p;\n .reg .u32 t;\n shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n @p add.u32 %0, %0, t;\n}\n" : "+r"(v) : "r"(d));
+    return v;
+}
 // 0xFF in the low k bytes of a word (k <= 0: none, k >= 4: all)
 __device__ __forceinline__ uint32_t bytes_below32c(int k) { return k >= 4 ? 0xFFFFFFFFu : (k <= 0 ? 0u : ((1u << (8 * k)) - 1u)); }
 
@@ -359,11 +366,9 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
                 low128 = low_count128(c2, low128);
                 low128 = low_count128(c3, low128);
             }
-            pm[h] = ((uint64_t)(nl_mask16r(c2, c7f, pat_nl) | (nl_mask16r(c3, c7f, pat_nl) << 16)) << 32) |
-                    (nl_mask16r(c0, c7f, pat_nl) | (nl_mask16r(c1, c7f, pat_nl) << 16));
+            pm[h] = ((uint64_t)nl_mask32r(c2, c3, c7f, pat_nl) << 32) | nl_mask32r(c0, c1, c7f, pat_nl);
             if (MODE != 2)  // the compaction pass moves bytes: no G/C bookkeeping
-                gm[h] = ((uint64_t)(gc_mask16r(c2, c7b, c7f, pat_gc) | (gc_mask16r(c3, c7b, c7f, pat_gc) << 16)) << 32) |
-                        (gc_mask16r(c0, c7b, c7f, pat_gc) | (gc_mask16r(c1, c7b, c7f, pat_gc) << 16));
+                gm[h] = ((uint64_t)gc_mask32r(c2, c3, c7b, c7f, pat_gc) << 32) | gc_mask32r(c0, c1, c7b, c7f, pat_gc);
             else
                 gm[h] = 0;
         }
@@ -371,7 +376,7 @@ __device__ __forceinline__ void fa_tile(const FastaScanArgs& a, const uint8_t* s
     const int cnt = __popcll(pm[0]) + __popcll(pm[1]);
     const int g0 = __popcll(gm[0]), g1 = __popcll(gm[1]);
     const uint32_t packed = ((uint32_t)cnt << 16) + (uint32_t)(g0 + g1);
-    const uint32_t incl = warp_incl_scan_u32(packed);
+    const uint32_t incl = fa_incl_scan_u32p(packed);
     const uint32_t ex = incl - packed;
     const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
     const int ex_cnt = (int)(ex >> 16), n_events = (int)(tot >> 16);
@@ -707,7 +712,8 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_tile_kernel(const __grid_con
                                                              const uint32_t c7b) {
     using SM = FaSmem<kCompact>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the warp index through a shuffle: the compiler then keeps tile arithmetic and the TMA operands in uniform registers
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     if (((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u) != 0) __trap();
     uint8_t* data0 = smem_raw + warp * SM::per_warp;
     uint8_t* aux = smem_raw + SM::aux0 + warp * FaAux::total;
@@ -738,6 +744,15 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_tile_kernel(const __grid_con
         const int64_t nxt = cur + stride;
         issue(nxt, b ^ 1);
         uint8_t* sbytes = data0 + b * WT_BYTES;
+        FaTileIn in{ST_S, 0, 0, 0, 0};
+        FaTile k1_summary;
+        if (kCompact) {  // what the scan left for this tile: fetched while the tile's bytes are still in flight
+            const uint32_t ts = a.tile_state[cur];
+            in.st = ts & 3u;
+            in.regular = (ts >> 3) & 1u;
+            in.kept_base = a.tile_base3[3 * cur + 1];
+            k1_summary = a.tiles[cur];
+        }
         if (cur * WT_ROWS < full_rows) {
             const uint32_t par = (phase_bits >> b) & 1u;
             while (!mbar_try_wait(bar0 + 8 * b, par)) {
@@ -746,13 +761,8 @@ __global__ void __launch_bounds__(FA_THREADS) fasta_tile_kernel(const __grid_con
         }
         const FaGeom g = fa_geom(a, origin, cur);
         fa_fix_edges(a, sbytes, origin, cur, full_rows, lane, g);
-        FaTileIn in{ST_S, 0, 0, 0, 0};
         if (kCompact) {
-            const uint32_t ts = a.tile_state[cur];
-            in.st = ts & 3u;
-            in.regular = (ts >> 3) & 1u;
-            in.kept_base = a.tile_base3[3 * cur + 1];
-            fa_tile<2>(a, sbytes, aux, origin, cur, g, c7f, c7b, in, a.tiles + cur, s_out);
+            fa_tile<2>(a, sbytes, aux, origin, cur, g, c7f, c7b, in, &k1_summary, s_out);
         } else {
             fa_tile<0>(a, sbytes, aux, origin, cur, g, c7f, c7b, in, a.tiles + cur, nullptr);
         }
