@@ -283,11 +283,14 @@ def main():
                 q = synth.gen_params("illumina", 1, seed=SEED, first_record=i, len_min=READ_LEN, len_max=READ_LEN)
                 return synth.gen_size(q)
 
-            def delta(k):  # offset of shard k's first byte inside record k*R; local offset of that byte is a multiple of 16
+            def delta(k):  # offset of shard k's first byte inside record k*R (96 .. 223 bytes into a ~350-byte record)
+                # the shard's device buffer (HALO bytes before that byte) starts on a 128-byte boundary of the generated
+                # image, as a per-GPU allocation of a host application would: 16 bytes is what the C ABI requires, but
+                # K1's TMA rows are 128 bytes and a buffer that straddles them costs ~5 % (profiles/round2_n2_launches.txt)
                 if k == 0:
                     return 0
                 s_prev = rec_size(k * R - 1)
-                return 96 + ((-(s_prev + 96)) % 16)
+                return 96 + ((XD.HALO - s_prev - 96) % 128)
 
             first = rank * R - (1 if rank else 0)
             count = R + (1 if rank else 0) + (1 if rank < world - 1 else 0)
@@ -302,7 +305,7 @@ def main():
             hi = off0 + own + (delta(rank + 1) if rank < world - 1 else 0)
             begin = XD.HALO if rank else 0
             local0 = s_prev + delta(rank) - begin  # view: file byte lo sits at local offset `begin`
-            assert local0 % 16 == 0
+            assert local0 % 128 == 0 and local0 >= 0
             buf = gbuf[local0:local0 + begin + (hi - lo)]
             return XD.Shard(buf, lo, hi, begin, rank == world - 1), gbuf, s_prev, own
 

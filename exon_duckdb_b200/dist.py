@@ -34,7 +34,9 @@ from . import _lib
 LO, HI, NEWLINES, OPEN_START, TAIL_S, TAIL_G, OPEN_FLAGS, LS0 = 0, 1, 2, 3, 4, 5, 6, 7
 N_LS = 5  # LS0..LS0+4: offsets of the first five line starts inside the shard (-1 = none)
 STATE_WORDS = LS0 + N_LS
-HALO = 16  # bytes of the file kept in front of a shard's first byte (the scan looks one byte back for CRLF)
+HALO = 128  # bytes of the file kept in front of a shard's first byte.  The scan only looks one byte back (CRLF); 128 keeps the
+            # shard's first byte on the same 128-byte grid as its buffer, so that K1's TMA rows are whole 128-byte lines
+            # (a shard whose tiles start 16 bytes off that grid scans ~5 % slower: profiles/round2_n2_launches.txt)
 RESULT_WORDS = 16  # the 128-byte result block of a scan as int64 words
 RECORD_WORDS = 32  # the 256-byte record of the single-exchange COUNT (exb_fastq_scan_filter_candidates)
 
