@@ -117,12 +117,14 @@ __device__ __forceinline__ RowFields row_fields(const FormatArgs& a, int64_t r) 
     return f;
 }
 
-// One warp per record (records up to LONG_ROW; longer ones only get their header here).
-template <bool kFasta>
+// LPR lanes per record (records up to LONG_ROW; longer ones only get their header here): 8 for short reads -- a 150-byte
+// field is nine 16-byte chunks, so a whole warp per record left three quarters of its lanes idle (3.3 ms per 1.4 GB of
+// Illumina reads against 0.9 ms with four records a warp) -- and 32 for long ones.
+template <bool kFasta, int LPR>
 __global__ void __launch_bounds__(FMT_THREADS) format_rows_kernel(const FormatArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.n_rows; r += warps) {
+    const int lane = (int)(threadIdx.x % LPR);
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) / LPR;  // record groups in flight
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR; r < a.n_rows; r += warps) {
         const uint32_t row_len = a.lens[r];
         if (row_len == 0) continue;  // record above 4 GiB: reported by the length pass
         if (a.row_off[r] + (int64_t)row_len > a.out_cap) {
@@ -133,24 +135,24 @@ __global__ void __launch_bounds__(FMT_THREADS) format_rows_kernel(const FormatAr
         uint8_t* d = a.out + a.row_off[r];
         // header line
         if (lane == 0) d[0] = kFasta ? '>' : '@';
-        group_copy(d + 1, f.p[0], f.n[0], lane, 32);
+        group_copy(d + 1, f.p[0], f.n[0], lane, LPR);
         int64_t q = 1 + f.n[0];
         if (f.n[1] > 0) {
             if (lane == 0) d[q] = ' ';
-            group_copy(d + q + 1, f.p[1], f.n[1], lane, 32);
+            group_copy(d + q + 1, f.p[1], f.n[1], lane, LPR);
             q += 1 + f.n[1];
         }
         if (lane == 0) d[q] = '\n';
         q += 1;
         if ((int64_t)row_len > LONG_ROW) continue;  // the rest is format_long_kernel's
         if (kFasta) {
-            wrapped_copy(d + q, f.p[2], f.n[2], a.line_width, 0, (f.n[2] + a.line_width - 1) / a.line_width, lane, 32);
+            wrapped_copy(d + q, f.p[2], f.n[2], a.line_width, 0, (f.n[2] + a.line_width - 1) / a.line_width, lane, LPR);
         } else {
-            group_copy(d + q, f.p[2], f.n[2], lane, 32);
+            group_copy(d + q, f.p[2], f.n[2], lane, LPR);
             q += f.n[2];
             if (lane < 3) d[q + lane] = lane == 1 ? '+' : '\n';
             q += 3;
-            group_copy(d + q, f.p[3], f.n[3], lane, 32);
+            group_copy(d + q, f.p[3], f.n[3], lane, LPR);
             q += f.n[3];
             if (lane == 0) d[q] = '\n';
         }
@@ -158,10 +160,15 @@ __global__ void __launch_bounds__(FMT_THREADS) format_rows_kernel(const FormatAr
 }
 
 // Long records: the sequence (and quality) of every row in long_rows, LONG_SLICE field bytes per block iteration.
+// The grid is spread over (row, part) pairs: with many long rows a block takes whole rows, with few (one chromosome)
+// every row is cut into gridDim / n_long parts, so the grid is busy either way.
 template <bool kFasta>
 __global__ void __launch_bounds__(FMT_THREADS) format_long_kernel(const FormatArgs a) {
     const int64_t n_long = (int64_t)a.counters[0];
-    for (int64_t li = 0; li < n_long; li++) {
+    if (n_long == 0) return;
+    const int64_t parts = (int64_t)gridDim.x / n_long > 1 ? (int64_t)gridDim.x / n_long : 1;
+    for (int64_t v = blockIdx.x; v < n_long * parts; v += gridDim.x) {
+        const int64_t li = v / parts, part = v - li * parts;
         const int64_t r = a.long_rows[li];
         if (a.row_off[r] + (int64_t)a.lens[r] > a.out_cap) continue;  // counted by format_rows_kernel
         const RowFields f = row_fields<kFasta>(a, r);
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(FMT_THREADS) format_long_kernel(const FormatAr
             const int w = a.line_width;
             const int64_t lines = (f.n[2] + w - 1) / w;
             const int64_t lines_per_slice = LONG_SLICE / w > 0 ? LONG_SLICE / w : 1;
-            for (int64_t l0 = (int64_t)blockIdx.x * lines_per_slice; l0 < lines; l0 += (int64_t)gridDim.x * lines_per_slice) {
+            for (int64_t l0 = part * lines_per_slice; l0 < lines; l0 += parts * lines_per_slice) {
                 const int64_t l1 = l0 + lines_per_slice < lines ? l0 + lines_per_slice : lines;
                 wrapped_copy(d, f.p[2], f.n[2], w, l0, l1, threadIdx.x, FMT_THREADS);
             }
@@ -178,14 +185,14 @@ __global__ void __launch_bounds__(FMT_THREADS) format_long_kernel(const FormatAr
             // sequence, "\n+\n", quality, '\n': both fields sliced the same way
             const int64_t s_sl = (f.n[2] + LONG_SLICE - 1) / LONG_SLICE, q_sl = (f.n[3] + LONG_SLICE - 1) / LONG_SLICE;
             uint8_t* dq = d + f.n[2] + 3;
-            for (int64_t s = blockIdx.x; s < s_sl + q_sl; s += gridDim.x) {
+            for (int64_t s = part; s < s_sl + q_sl; s += parts) {
                 const bool is_q = s >= s_sl;
                 const int64_t k = is_q ? s - s_sl : s;
                 const int64_t n = is_q ? f.n[3] : f.n[2];
                 const int64_t b = k * LONG_SLICE, m = n - b < LONG_SLICE ? n - b : LONG_SLICE;
                 group_copy((is_q ? dq : d) + b, (is_q ? f.p[3] : f.p[2]) + b, m, threadIdx.x, FMT_THREADS);
             }
-            if (blockIdx.x == 0 && threadIdx.x < 4) {
+            if (part == 0 && threadIdx.x < 4) {
                 if (threadIdx.x < 3) d[f.n[2] + threadIdx.x] = threadIdx.x == 1 ? '+' : '\n';
                 else dq[f.n[3]] = '\n';
             }
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(FMT_THREADS) format_long_kernel(const FormatAr
 static int fmt_grid(int64_t items_per_block_units) {
     int64_t g = items_per_block_units;
     if (g < 1) g = 1;
-    if (g > 148 * 8) g = 148 * 8;
+    if (g > 148 * 16) g = 148 * 16;
     return (int)g;
 }
 
@@ -209,9 +216,17 @@ cudaError_t format_len_launch(const FormatArgs& a, bool fasta, cudaStream_t st) 
     return cudaGetLastError();
 }
 cudaError_t format_rows_launch(const FormatArgs& a, bool fasta, cudaStream_t st) {
-    const int grid = fmt_grid((a.n_rows + FMT_THREADS / 32 - 1) / (FMT_THREADS / 32));
-    if (fasta) format_rows_kernel<true><<<grid, FMT_THREADS, 0, st>>>(a);
-    else format_rows_kernel<false><<<grid, FMT_THREADS, 0, st>>>(a);
+    // the image capacity bounds the mean record length (the sizes themselves are only known on the device)
+    const bool short_rows = a.n_rows > 0 && a.out_cap / a.n_rows < 1024;
+    const int lpr = short_rows ? 8 : 32;
+    const int grid = fmt_grid((a.n_rows + FMT_THREADS / lpr - 1) / (FMT_THREADS / lpr));
+    if (fasta) {
+        if (short_rows) format_rows_kernel<true, 8><<<grid, FMT_THREADS, 0, st>>>(a);
+        else format_rows_kernel<true, 32><<<grid, FMT_THREADS, 0, st>>>(a);
+    } else {
+        if (short_rows) format_rows_kernel<false, 8><<<grid, FMT_THREADS, 0, st>>>(a);
+        else format_rows_kernel<false, 32><<<grid, FMT_THREADS, 0, st>>>(a);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // the long-record pass reads its row count on the device: no host round trip; with no long record it is one empty loop

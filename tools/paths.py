@@ -141,6 +141,15 @@ def c2_paths(rep, buf, reads, iters=10, full=True):
         rep.add("reverse_complement(sequence) (exb_seq_map)", 2 * seq.data.numel(), med, best, seq.data.numel(), "includes 1 host sync for the error flag")
         med, best = timeit(lambda: D.quality_score_string_to_list(qual), iters)
         rep.add("quality_score_string_to_list (exb_quality_decode)", 5 * qual.data.numel(), med, best, qual.data.numel())
+    if not split_only:
+        # the writer (COPY ... TO (FORMAT 'fastq')): the four columns back into a file image -- which must be the input again
+        cols = [tab[k] for k in D.FASTQ_COLUMNS]
+        img, _ = D.fastq_format(*cols)
+        assert img.numel() == n and torch.equal(img, buf[:n])
+        col_b = sum(c.data.numel() for c in cols) + 32 * len(cols[0])
+        del img
+        med, best = timeit(lambda: D.fastq_format(*cols), iters=5)
+        rep.add("C2 writer: 4 columns -> FASTQ file image (exb_fastq_format)", col_b + n, med, best, n, "includes the scratch / image allocations and 1 host sync")
     del tab
 
 
@@ -179,5 +188,13 @@ def c3_paths(rep, dev, contigs, contig_len, iters=10):
     seq_bytes = int(fs2.result.seq_bytes)
     med, best = timeit(lambda: D.fasta_scan(buf, compact=True, out=fs2), iters)
     rep.add("C3 read_fasta with the sequence column compacted", n + seq_bytes, med, best, n)
-    del fs, fs2, buf
+    # the writer (COPY ... TO (FORMAT 'fasta')): id / description / sequence columns -> file image re-wrapped at 60
+    tab = D.fasta_table(buf)
+    cols = [tab[k] for k in D.FASTA_COLUMNS]
+    img, _ = D.fasta_format(*cols, line_width=60)
+    assert img.numel() == n and torch.equal(img, buf[:n])
+    del img
+    med, best = timeit(lambda: D.fasta_format(*cols, line_width=60), iters=5)
+    rep.add("C3 writer: 3 columns -> FASTA file image wrapped at 60 (exb_fasta_format)", seq_bytes + n, med, best, n, "includes the scratch / image allocations and 1 host sync")
+    del tab, cols, fs, fs2, buf
     torch.cuda.empty_cache()
