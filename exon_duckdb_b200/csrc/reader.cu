@@ -51,6 +51,7 @@ cudaError_t take_i64_launch(const int64_t*, const int64_t*, int64_t, int64_t*, c
 cudaError_t take_u8_launch(const uint8_t*, const int64_t*, int64_t, uint8_t*, cudaStream_t);
 // reader_ops.cu
 cudaError_t string_t_launch(const int64_t*, const uint8_t*, uint64_t, int64_t, void*, cudaStream_t);
+cudaError_t string_t_borrow_launch(const int64_t*, const uint32_t*, const uint8_t*, uint64_t, int64_t, void*, cudaStream_t);
 cudaError_t valid_bits_launch(const uint8_t*, int64_t, uint64_t*, uint64_t*, cudaStream_t);
 cudaError_t list_entries_launch(const int64_t*, int64_t, int64_t, void*, int64_t*, cudaStream_t);
 cudaError_t gc_sel_launch(const uint32_t*, const uint32_t*, const int64_t*, const int64_t*, const int64_t*, int64_t, float*, cudaStream_t);
@@ -883,6 +884,7 @@ struct ChunkResult {
     OutCol cols[MAX_OUT];
     int64_t rows = 0;
     std::vector<HBuf*> bufs;
+    std::shared_ptr<void> input;  // the pinned input block, when string_t entries of this chunk point into it
     std::shared_ptr<PinnedPool> pool;
     ~ChunkResult() {
         for (HBuf* b : bufs) pool->put(b);
@@ -891,14 +893,26 @@ struct ChunkResult {
 
 // One raw block of a file as the IO thread read it.  The part of the previous chunk that did not end on a record
 // boundary never comes back to the host: it stays in HBM and the device thread puts the next block behind it.
+// The raw bytes start BLOCK_SLACK bytes into the pinned buffer: the device thread copies the unconsumed tail of the
+// previous chunk (the record that straddles two blocks) in front of them ON THE HOST too, so that the host holds a
+// contiguous image of every chunk and string columns can point into it (string_t_borrow_kernel).
+constexpr int64_t BLOCK_SLACK = 1 << 20;
 struct Block {
     HBuf* h = nullptr;
+    int64_t data_off = 0;      // raw bytes live at h->p + data_off
+    uint8_t* data() const { return h->as<uint8_t>() + data_off; }
     int64_t raw_len = 0;
     int64_t raw_file_pos = 0;  // offset of the first raw byte in the (decompressed) file
     size_t file_idx = 0;
     bool eof = false;          // the file (or the shard of it) ends with this block
     std::string error;         // IO failure: the stream ends here
     bool end = false;          // no more files
+};
+struct HostBlock {  // an input block shared by the device thread and the chunk results whose strings point into it
+    HBuf* h;
+    std::shared_ptr<PinnedPool> pool;
+    HostBlock(HBuf* b, std::shared_ptr<PinnedPool> p) : h(b), pool(std::move(p)) {}
+    ~HostBlock() { pool->put(h); }
 };
 struct OutItem {
     std::shared_ptr<ChunkResult> res;
@@ -1245,7 +1259,8 @@ struct Reader {
                 const int64_t want = block_bytes.load() - (pos & 15);
                 Block b;
                 double t0 = now();
-                b.h = pool->get(want + 64);
+                b.h = pool->get(BLOCK_SLACK + want + 64);
+                b.data_off = BLOCK_SLACK;
                 t_io_alloc += now() - t0;
                 if (!b.h) {
                     err = "out of pinned host memory";
@@ -1255,7 +1270,7 @@ struct Reader {
                 NvtxRange nv("exb:io_block");
                 b.file_idx = fi;
                 b.raw_file_pos = pos;
-                uint8_t* dst = b.h->as<uint8_t>();
+                uint8_t* dst = b.data();
                 int64_t got = 0;
                 if (gz) {
                     while (got < want) {
@@ -1343,6 +1358,11 @@ struct Reader {
         inq.push(std::move(b));
     }
     int64_t shard_begin = 0, shard_end = 0;  // where the byte-range shard really starts / ends (after resync)
+    // host image of the chunk being processed: host_base[i] is the byte d_cur[i] (nullptr: no contiguous image, see
+    // dev_main); host_block keeps the pinned block that holds it alive
+    uint8_t* host_base = nullptr;
+    std::shared_ptr<HostBlock> host_block;
+    bool no_borrow = getenv("EXON_B200_NO_BORROW") != nullptr;  // debugging / A-B: always gather and copy the strings back
 
     // ------------------------------------------------------------------ device thread
     // evaluate node `k` into d_out (uint8 per row) using per-column starts/lens (cols x n) in column buffers
@@ -1478,13 +1498,40 @@ struct Reader {
         std::shared_ptr<ChunkResult> res = std::make_shared<ChunkResult>();
         res->pool = pool;
         res->rows = n;
-        const int64_t ws_bytes = exb_scan_workspace_bytes(4 * n * ncols + 16);
-        if (!d_ws2.need(ws_bytes) || !d_off.need((int64_t)ncols * (n + 1) * 8)) return fail("out of memory");
-        int64_t* d_offs = d_off.as<int64_t>();
-        if (!rc(exb_exclusive_scan_u32_multi(d_ln, n, ncols, n, d_offs, n + 1, d_ws2.p, d_ws2.cap, st))) return false;
-        if (!queue_small(32, d_offs + n, ncols, n + 1) || !wait_small()) return false;
+        // ---- borrowed columns: a VARCHAR column whose rows are byte ranges of the input chunk (every FASTQ column, FASTA id /
+        // description) is not gathered at all when the host reads string_t entries only and holds a contiguous image of the
+        // chunk: the entries point into the pinned INPUT block (string_t_borrow_kernel), which the result keeps alive.
+        bool borrow[MAX_OUT];
+        bool need_offsets = false;
+        for (int j = 0; j < nout; j++) {
+            borrow[j] = present[j] && type[j] == EXB_T_VARCHAR && mode[j] < 0 && want_string_t() && !want_offsets() && host_base != nullptr &&
+                        col_buf[src[j]] == d_cur && !no_borrow;
+        }
+        {
+            // ONE long column on its own (sequence or quality_scores, ~40 % of a record) is still gathered: a consumer that
+            // reads the bytes then walks a dense, freshly written buffer instead of 150 bytes of every 360 of the input
+            // image (DuckDB's SUM(length(sequence)): 35 GB/s gathered, 24 GB/s borrowed; all four columns: 11.5 -> 24 GB/s)
+            int n_borrow = 0, last = -1;
+            for (int j = 0; j < nout; j++)
+                if (borrow[j]) {
+                    n_borrow++;
+                    last = j;
+                }
+            if (n_borrow == 1 && src[last] >= 2 && !getenv("EXON_B200_BORROW_ALWAYS")) borrow[last] = false;
+        }
+        for (int j = 0; j < nout; j++) {
+            if (present[j] && ((type[j] == EXB_T_VARCHAR && !borrow[j]) || type[j] == EXB_T_INT32_LIST)) need_offsets = true;
+        }
+        int64_t* d_offs = nullptr;
         int64_t totals[4] = {0, 0, 0, 0};
-        for (int c = 0; c < ncols; c++) totals[c] = small(32)[c];
+        if (need_offsets) {  // (one multi-column scan + a stream sync for the totals: skipped when every string column is borrowed)
+            const int64_t ws_bytes = exb_scan_workspace_bytes(4 * n * ncols + 16);
+            if (!d_ws2.need(ws_bytes) || !d_off.need((int64_t)ncols * (n + 1) * 8)) return fail("out of memory");
+            d_offs = d_off.as<int64_t>();
+            if (!rc(exb_exclusive_scan_u32_multi(d_ln, n, ncols, n, d_offs, n + 1, d_ws2.p, d_ws2.cap, st))) return false;
+            if (!queue_small(32, d_offs + n, ncols, n + 1) || !wait_small()) return false;
+            for (int c = 0; c < ncols; c++) totals[c] = small(32)[c];
+        }
         // ---- layout of the two result buffers
         auto up = [](int64_t x, int64_t a) { return (x + a - 1) & ~(a - 1); };
         const int64_t n_batches = (n + batch_size - 1) / batch_size;
@@ -1499,7 +1546,7 @@ struct Reader {
             if (!present[j]) continue;
             if (type[j] == EXB_T_VARCHAR) {
                 data_base[j] = all;
-                all += up(totals[src[j]], 16);
+                if (!borrow[j]) all += up(totals[src[j]], 16);
                 if (want_string_t()) { m_str[j] = m; m += up(n * 16, 64); }
                 if (j < ncols && col_names[j] == "description") {
                     m_valid[j] = m; m += up(n, 64);
@@ -1547,7 +1594,21 @@ struct Reader {
             oc.type = type[j];
             oc.kind = kind[j];
             const int c = src[j];
-            if (type[j] == EXB_T_VARCHAR) {
+            if (type[j] == EXB_T_VARCHAR && borrow[j]) {
+                if (!cu(string_t_borrow_launch(d_st + (int64_t)c * n, d_ln + (int64_t)c * n, d_cur, (uint64_t)(uintptr_t)host_base, n, dm + m_str[j], st),
+                        "string_t_borrow"))
+                    return false;
+                oc.str = hm + m_str[j];
+                res->input = host_block;
+                if (m_valid[j] >= 0) {
+                    if (!cu(cudaMemcpyAsync(dm + m_valid[j], d_val, (size_t)n, cudaMemcpyDeviceToDevice, st), "D2D validity")) return false;
+                    if (!cu(valid_bits_launch(d_val, n, reinterpret_cast<uint64_t*>(dm + m_vbits[j]), reinterpret_cast<uint64_t*>(dm + m_nulls) + j, st),
+                            "valid_bits"))
+                        return false;
+                    oc.valid = hm + m_valid[j];
+                    oc.vbits = reinterpret_cast<const uint64_t*>(hm + m_vbits[j]);
+                }
+            } else if (type[j] == EXB_T_VARCHAR) {
                 const int64_t* offs = d_offs + (int64_t)c * (n + 1);
                 if (totals[c] > 0) {
                     if (mode[j] < 0) {
@@ -1807,7 +1868,8 @@ struct Reader {
     // k+1 -- if the IO thread already has it -- crosses PCIe on the copy stream into a staging buffer, so H2D of k+1
     // overlaps the kernels of k and the D2H of k-1 (two copy engines, opposite directions).
     void dev_main() {
-        HBuf* host_cur = nullptr;     // pinned block whose bytes may still be in flight to the device
+        std::shared_ptr<HostBlock> host_cur;  // pinned block whose bytes may still be in flight to the device (chunk results that
+                                              // borrow its bytes hold it too: see host_base)
         Block staged;                 // the prefetched block (its pinned buffer included); valid when have_staged
         bool have_staged = false, staged_on_device = false;
         int cur = 0;
@@ -1818,7 +1880,9 @@ struct Reader {
             cudaStreamSynchronize(sc);
             cudaStreamSynchronize(st);
             cudaStreamSynchronize(sd);
-            pool->put(host_cur);
+            host_cur.reset();
+            host_block.reset();
+            host_base = nullptr;
             if (have_staged) pool->put(staged.h);
             pend.clear();
             free_device();
@@ -1867,11 +1931,25 @@ struct Reader {
                          cu(cudaMemcpyAsync(dst + carry_len, d_stage.p, (size_t)b.raw_len, cudaMemcpyDeviceToDevice, st), "D2D block") &&
                          cu(cudaEventRecord(ev_stage_free, st), "record");
                 } else {
-                    ok = cu(cudaMemcpyAsync(dst + carry_len, b.h->p, (size_t)b.raw_len, cudaMemcpyHostToDevice, st), "H2D");
+                    ok = cu(cudaMemcpyAsync(dst + carry_len, b.data(), (size_t)b.raw_len, cudaMemcpyHostToDevice, st), "H2D");
                 }
             }
-            pool->put(host_cur);  // the previous chunk synchronised `st` after its copies: that block is idle
-            host_cur = b.h;
+            // ---- the same chunk on the host: the block's bytes are already there; the carried tail (at most the record that
+            // straddles the two blocks) is copied in front of them, into the block's slack.  Not possible when the tail is
+            // larger than the slack: that chunk's strings are gathered and copied back as before.
+            {
+                uint8_t* blk = b.data();
+                uint8_t* base = nullptr;
+                if (carry_len == 0) {
+                    base = blk;
+                } else if (carry_len <= b.data_off && host_base) {
+                    memcpy(blk - carry_len, host_base + carry_off, (size_t)carry_len);
+                    base = blk - carry_len;
+                }
+                host_base = base;
+            }
+            host_cur = std::make_shared<HostBlock>(b.h, pool);  // (the previous chunk synchronised `st` after its copies: that block
+            host_block = host_cur;                              //  goes back to the pool once no chunk result points into it)
             if (!ok) return finish(derr);
             mark(1);
             cur = nxt;
@@ -1887,7 +1965,7 @@ struct Reader {
                     if (!nb.end && nb.raw_len > 0 && d_stage.need(nb.raw_len + 64)) {
                         // the staging buffer is free once the previous staged block has been moved out of it
                         if (cu(cudaStreamWaitEvent(sc, ev_stage_free, 0), "wait") &&
-                            cu(cudaMemcpyAsync(d_stage.p, nb.h->p, (size_t)nb.raw_len, cudaMemcpyHostToDevice, sc), "H2D prefetch") &&
+                            cu(cudaMemcpyAsync(d_stage.p, nb.data(), (size_t)nb.raw_len, cudaMemcpyHostToDevice, sc), "H2D prefetch") &&
                             cu(cudaEventRecord(ev_staged, sc), "record"))
                             staged_on_device = true;
                         else
@@ -1932,7 +2010,9 @@ struct Reader {
         cudaStreamSynchronize(sc);
         cudaStreamSynchronize(st);
         cudaStreamSynchronize(sd);
-        pool->put(host_cur);
+        host_cur.reset();
+        host_block.reset();
+        host_base = nullptr;
         if (have_staged) pool->put(staged.h);
         pend.clear();
         free_device();
@@ -2042,7 +2122,7 @@ struct Reader {
                                         cudaMemcpyDeviceToDevice, st),
                         "D2D halo");
             }
-            if (ok && n) ok = cu(cudaMemcpyAsync(data, b.h->p, (size_t)n, cudaMemcpyHostToDevice, st), "H2D");
+            if (ok && n) ok = cu(cudaMemcpyAsync(data, b.data(), (size_t)n, cudaMemcpyHostToDevice, st), "H2D");
             cudaEvent_t ev = nullptr;
             if (!ev_pool.empty()) {
                 ev = ev_pool.back();

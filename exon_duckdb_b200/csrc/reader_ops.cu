@@ -3,6 +3,8 @@
 // of looping over rows.
 //   string_t_kernel      Arrow-style offsets + bytes -> DuckDB string_t entries (duckdb string_type.hpp:19-60); replaces
 //                        the SetVectorString loop of the reference's consumer (duckdb arrow_conversion.cpp:252-266)
+//   string_t_borrow_kernel  the same for columns that are byte ranges of the input chunk: the entries point into the pinned
+//                        INPUT block on the host, no bytes are gathered or copied back
 //   valid_bits_kernel    one validity byte per row -> DuckDB / Arrow validity bitmap (arrow_conversion.cpp:36-76)
 //   list_entries_kernel  list offsets -> list_entry_t {offset, length} relative to each 2048-row batch (types.hpp:56-68)
 //   computed columns     gc_content (sequence_functions/module.cpp:131-158), list_avg(quality_score_string_to_list(q))
@@ -48,6 +50,40 @@ __global__ void __launch_bounds__(256) string_t_kernel(const int64_t* __restrict
 cudaError_t string_t_launch(const int64_t* off, const uint8_t* data, uint64_t host_base, int64_t n, void* out, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     string_t_kernel<<<grid_for(n, 256), 256, 0, st>>>(off, data, host_base, n, reinterpret_cast<uint4*>(out));
+    return cudaGetLastError();
+}
+
+// The same entries for a column whose rows are byte ranges of the INPUT chunk (every FASTQ column, FASTA id / description):
+// start[i] / len[i] index the device copy of the chunk, host_base = host address of the chunk's byte 0 in the pinned
+// block the IO thread filled.  Strings above 12 bytes then point INTO THE INPUT BLOCK on the host: the column's bytes
+// are neither gathered on the device nor copied back -- only these 16 bytes per row cross PCIe.
+__global__ void __launch_bounds__(256) string_t_borrow_kernel(const int64_t* __restrict__ start, const uint32_t* __restrict__ len_of,
+                                                              const uint8_t* __restrict__ data, uint64_t host_base, int64_t n, uint4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = start[i];
+        const uint32_t len = len_of[i];
+        const uint8_t* p = data + b;
+        uint32_t w[3] = {0u, 0u, 0u};
+        const uint32_t take = len <= 12u ? len : 4u;  // inlined value, or the 4-byte prefix
+        for (uint32_t k = 0; k < take; k++) w[k >> 2] |= (uint32_t)p[k] << (8 * (k & 3));
+        uint4 v;
+        v.x = len;
+        v.y = w[0];
+        if (len <= 12u) {
+            v.z = w[1];
+            v.w = w[2];
+        } else {
+            const uint64_t ptr = host_base + (uint64_t)b;
+            v.z = (uint32_t)ptr;
+            v.w = (uint32_t)(ptr >> 32);
+        }
+        out[i] = v;
+    }
+}
+cudaError_t string_t_borrow_launch(const int64_t* start, const uint32_t* len, const uint8_t* data, uint64_t host_base, int64_t n, void* out,
+                                   cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    string_t_borrow_kernel<<<grid_for(n, 256), 256, 0, st>>>(start, len, data, host_base, n, reinterpret_cast<uint4*>(out));
     return cudaGetLastError();
 }
 

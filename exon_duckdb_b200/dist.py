@@ -65,6 +65,12 @@ def bind_to_gpu_numa_node(device_index):
         with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
             node = int(f.read().strip())
         if node < 0:
+            # the platform reports no affinity for the device (virtualised PCIe): with ONE node online every CPU and every
+            # pinned page is local to every GPU -- there is nothing to bind, and that node is the answer
+            with open("/sys/devices/system/node/online") as f:
+                online = f.read().strip()
+            if online.isdigit():
+                return int(online)
             return None
         with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
             cpus = set()
