@@ -164,7 +164,11 @@ typedef struct exb_computed {
                              {u32 length, 12 inlined bytes} or {u32 length, 4-byte prefix, pointer into the batch's
                              host buffer}, built on the device -- the host's SetVectorString loop
                              (arrow_conversion.cpp:252-266) becomes one pointer assignment per column           */
-#define EXB_RD_NO_OFFSETS 2 /* do not copy the Arrow-style int64 offsets back (hosts that only read string_t)    */
+#define EXB_RD_NO_OFFSETS 2 /* do not copy the Arrow-style int64 offsets back (hosts that only read string_t).  With both
+                               flags a column whose rows are byte ranges of the input (every FASTQ column, FASTA id /
+                               description) may come back with offsets == data == NULL: its string_t pointers then
+                               lead into the pinned input block the reader staged the file in -- nothing was gathered
+                               or copied back -- and stay valid until exb_batch_release like every other pointer     */
 
 typedef struct exb_reader_options {
     uint32_t size;       /* sizeof(exb_reader_options) of the caller (versioning)                                  */
