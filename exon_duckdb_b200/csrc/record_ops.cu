@@ -666,7 +666,9 @@ __global__ void __launch_bounds__(SP_THREADS, 5) fastq_split_kernel(FqLines<OffT
             for (int k = t; k < chunks; k += SP_THREADS) cp_async16(s_win + 16 * k, buf + w0a + 16 * (int64_t)k, 16);
             cp_async_commit();
         }
-        else if (a.prefetch) {  // the block's window will be read piecemeal below: start its trip from DRAM to L2 now
+        else if (a.prefetch && (a.mask & 0xFu) == 0xFu) {  // the block's window will be read piecemeal below: start its trip from
+            // DRAM to L2 now -- when every column is copied; with a projection the window holds bytes nobody reads (the quality
+            // lines of a `sequence`-only split were fetched for nothing: 3.2 GB read for a 1.2 GB input, half of it useful)
             for (int64_t o = w0a + 128 * (int64_t)t; o < w1; o += 128 * SP_THREADS) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(buf + o));
         }
         // (the input carries 64 bytes of slack behind n, so the look-ahead never leaves the allocation)
@@ -825,7 +827,20 @@ __global__ void __launch_bounds__(SP_THREADS, 5) fastq_split_kernel(FqLines<OffT
                 return m;
             };
             auto map4 = [&](uint32_t x, int64_t pos) -> uint32_t {
-                return map1(x & 0xFF, pos) | (map1((x >> 8) & 0xFF, pos + 1) << 8) | (map1((x >> 16) & 0xFF, pos + 2) << 16) | (map1(x >> 24, pos + 3) << 24);
+                // four table look-ups, ONE validity test per word: the table holds ASCII letters or 0 (= invalid), so the
+                // SWAR zero-byte test is exact; the per-byte search only runs for a word that holds an invalid character
+                // (a test and a branch per byte were 3/4 of this kernel's instructions on ONT reads: profiles/round2_split_map_ncu.txt)
+                const uint32_t m = (uint32_t)s_lut[x & 0xFF] | ((uint32_t)s_lut[(x >> 8) & 0xFF] << 8) | ((uint32_t)s_lut[(x >> 16) & 0xFF] << 16) |
+                                   ((uint32_t)s_lut[x >> 24] << 24);
+                if (((m - 0x01010101u) & ~m & 0x80808080u) != 0u) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (((m >> (8 * k)) & 0xFFu) == 0u) {
+                            const unsigned long long w = ((unsigned long long)(pos + k) << 8) | ((x >> (8 * k)) & 0xFFu);
+                            bad = w < bad ? w : bad;
+                        }
+                }
+                return m;
             };
             const int64_t col_bytes = B1 - B0;
             const int max_len = (int)(s_maxlen[c] > 0x7FFFFFFFull ? 0x7FFFFFFFull : s_maxlen[c]);
