@@ -581,6 +581,7 @@ def main():
         if all(c[1] for c in allchk):
             assert sum(c[0] for c in allchk) == got5[2], (allchk, got5)
         ms5 = t5.item()
+        job_fused = bool(job.fused)
         peak5, _ = measured_peak()
         c5 = {"workload": "C5: %.1f GB synthetic Illumina FASTQ, ONE file byte-range sharded over %d GPU(s), cuts inside records; "
                           "SELECT COUNT(*), SUM(#GC), SUM(length(sequence)), AVG(gc_content(sequence))" % (int(b5.item()) / 1e9, world),
@@ -588,8 +589,11 @@ def main():
               "scaling": "strong", "steps": c5_steps, "frac_of_hbm_peak": int(b5.item()) / (ms5 * 1e-3) / 1e9 / (peak5 * world),
               "count": got5[0], "sum_len": got5[1], "sum_gc": got5[2], "avg_gc_content": got5[5] / 4294967296.0 / n5,
               "sum_gc_cross_checked": bool(all(c[1] for c in allchk)),
-              "kernels": "exb_fastq_scan_begin (K1 + line offsets) -> block exchange -> exb_fastq_compose_prev -> exb_fastq_scan_resolve "
-                         "(EXB_F_SEQ | EXB_F_LOCAL_RECORDS) -> exb_fastq_seq_totals -> reduce"}
+              "kernels": ("exb_fastq_scan_totals_begin (K1 with the sequence-line aggregates of all four phase hypotheses + line offsets) -> "
+                          "block exchange -> exb_fastq_compose_prev -> exb_fastq_scan_totals_resolve (K2 picks the buckets) -> reduce")
+                         if job_fused else
+                         ("exb_fastq_scan_begin (K1 + line offsets) -> block exchange -> exb_fastq_compose_prev -> exb_fastq_scan_resolve "
+                          "(EXB_F_SEQ | EXB_F_LOCAL_RECORDS) -> exb_fastq_seq_totals -> reduce")}
         del job
 
     if rank == 0:

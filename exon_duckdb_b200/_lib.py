@@ -148,6 +148,9 @@ SIGNATURES = {
     "exb_fastq_workspace_bytes": (_i64, [_i64, _i64]),
     "exb_fastq_scan": (_i32, [_vp, _i64, _i64, _i32, _vp, _u64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "exb_fastq_scan_filter": (_i32, [_vp, _i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i32, _vp, _i64, _vp]),
+    "exb_fastq_scan_totals": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "exb_fastq_scan_totals_begin": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
+    "exb_fastq_scan_totals_resolve": (_i32, [_i64, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _vp]),
     "exb_fastq_scan_filter_begin": (_i32, [_vp, _i64, _i64, _i32, _vp, C.POINTER(Predicate), _i32, _vp, _i64, _vp]),
     "exb_fastq_scan_begin": (_i32, [_vp, _i64, _i64, _i32, _vp, _i32, _vp, _i64, _vp]),
     "exb_fastq_seq_totals": (_i32, [_vp, _vp, _i64, _vp, _vp]),

@@ -223,7 +223,9 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
     a.n_tiles = fastq_scan_tiles(begin, n, a.is_final);
     const FastqLayout L = fastq_layout(a.n_tiles);
     const int64_t payload = workspace_bytes - L.fixed;
-    const int64_t min_payload = (flags & EXB_F_FUSED) ? a.n_tiles * (int64_t)sizeof(FusedTile) : fastq_record_slack(a.n_tiles) * 8;
+    const bool fused_seq = (flags & EXB_F_FUSED) && (flags & EXB_F_SEQ) && !(flags & EXB_F_QUAL);  // totals flavour: + 32 B per tile
+    const int64_t min_payload =
+        (flags & EXB_F_FUSED) ? a.n_tiles * (int64_t)(sizeof(FusedTile) + (fused_seq ? 32 : 0)) : fastq_record_slack(a.n_tiles) * 8;
     if (payload < min_payload)
         return set_err(EXB_ERR_ARG, "%s: workspace too small: need at least %lld bytes, have %lld", who, (long long)(L.fixed + min_payload),
                        (long long)workspace_bytes);
@@ -246,6 +248,7 @@ static int fastq_scan_common(const char* who, const void* d_buf, int64_t begin, 
     a.records = reinterpret_cast<uint2*>(ws + L.off_payload);
     a.rec_space = payload / 8;
     a.fused_tiles = reinterpret_cast<FusedTile*>(ws + L.off_payload);
+    a.fused_fix = reinterpret_cast<unsigned long long*>(ws + L.off_payload + a.n_tiles * (int64_t)sizeof(FusedTile));
     a.n_fused = n_preds;
     for (int i = 0; i < n_preds; i++) a.fused[i] = preds[i];
     a.fused_agg = reinterpret_cast<long long*>(d_agg);
@@ -320,6 +323,35 @@ int exb_fastq_scan_filter(const void* d_buf, int64_t begin, int64_t n, int is_fi
     }
     return fastq_scan_common("exb_fastq_scan_filter", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_QUAL, nullptr, 0,
                              0, nullptr, nullptr, nullptr, nullptr, 0, preds, n_preds, d_agg, d_workspace, workspace_bytes, st);
+}
+
+// ---- fused TOTALS flavour (BASELINE C5): SUM(length(sequence)), SUM(#GC), AVG(gc_content(sequence)) in the byte pass
+int exb_fastq_scan_totals(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, int64_t* d_agg,
+                          int accumulate, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_agg) return set_err(EXB_ERR_ARG, "exb_fastq_scan_totals: d_agg is null");
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(d_agg, 0, 8 * sizeof(int64_t), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(agg)");
+    }
+    return fastq_scan_common("exb_fastq_scan_totals", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_SEQ, nullptr, 0, 0,
+                             nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, d_agg, d_workspace, workspace_bytes, st);
+}
+int exb_fastq_scan_totals_begin(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, void* d_workspace,
+                                int64_t workspace_bytes, void* stream) {
+    return fastq_scan_common("exb_fastq_scan_totals_begin", d_buf, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_SEQ, nullptr, 0, 0,
+                             nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, d_workspace, workspace_bytes, (cudaStream_t)stream, false, true);
+}
+int exb_fastq_scan_totals_resolve(int64_t begin, int64_t n, int is_final, const void* d_prev_workspace, int64_t* d_agg, int accumulate,
+                                  void* d_workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_agg) return set_err(EXB_ERR_ARG, "exb_fastq_scan_totals_resolve: d_agg is null");
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(d_agg, 0, 8 * sizeof(int64_t), st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(agg)");
+    }
+    return fastq_scan_common("exb_fastq_scan_totals_resolve", nullptr, begin, n, is_final, d_prev_workspace, ~0ull, EXB_F_FUSED | EXB_F_SEQ, nullptr, 0,
+                             0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, d_agg, d_workspace, workspace_bytes, st, true);
 }
 
 int exb_fastq_scan_filter_begin(const void* d_buf, int64_t begin, int64_t n, int is_final, const void* d_prev_workspace,

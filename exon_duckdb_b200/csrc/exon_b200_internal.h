@@ -64,6 +64,7 @@ struct FastqScanArgs {
     int n_fused;                // EXB_F_FUSED: predicates on the quality line (EXB_P_MEAN_QUALITY / EXB_P_QUAL_LEN)
     exb_predicate fused[EXB_MAX_PREDICATES];
     long long* fused_agg;       // int64[8] aggregates (same layout as exb_fastq_filter's d_agg)
+    unsigned long long* fused_fix;  // [n_tiles][4] EXB_F_FUSED | EXB_F_SEQ: sum of round(gc_content * 2^32) per hypothesis bucket
     // outputs
     void* line_end;             // OffT[line_cap]
     int64_t line_cap;

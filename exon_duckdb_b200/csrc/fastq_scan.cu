@@ -76,6 +76,12 @@ __device__ __forceinline__ uint32_t tail_open_flags(uint64_t w) { return (uint32
 __device__ __forceinline__ uint32_t tail_byte0_flags(uint64_t w) { return (uint32_t)(w >> 58) & 3u; }
 __device__ __forceinline__ uint32_t at_plus_flags(int byte) { return (byte == '@' ? 2u : 0u) | (byte == '+' ? 1u : 0u); }
 
+// round(gc_content * 2^32) of one sequence line, gc_content = (float)#GC / (float)len exactly as the scalar function
+// computes it (sequence_functions/module.cpp:131-158); 0 for an empty line.  Same expression as seq_totals_kernel.
+__device__ __forceinline__ unsigned long long gc_fix32(uint32_t g, uint32_t l) {
+    return l ? (unsigned long long)__double2ll_rn((double)__fdiv_rn(__uint2float_rn(g), __uint2float_rn(l)) * 4294967296.0) : 0ull;
+}
+
 // ---------------------------------------------------------------- line record (8 bytes per newline)
 // .x = byte-sum prefix at the newline (tile-relative, excludes the newline)
 // .y = [11:0] position in the tile | [12] CR before it | [14:13] next line starts with '@' / '+' | [27:15] G/C prefix
@@ -263,6 +269,9 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
     using AUX = FqWarpAux<FLAGS>;
     constexpr bool kSeq = AUX::kSeq, kQual = AUX::kQual;
     constexpr bool kFused = (FLAGS & EXB_F_FUSED) != 0;
+    // fused TOTALS flavour (C5: COUNT, SUM(len), SUM(#GC), AVG(gc_content) of the sequence lines): no predicate, the
+    // aggregates of every line that is a SEQUENCE line under one of the four hypotheses
+    constexpr bool kFusedSeq = kFused && kSeq && !kQual;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint4* s_wlut = reinterpret_cast<uint4*>(smem_raw + AUX::off_wlut);  // s_wlut[k]: 0x01 in the first k bytes -- IDP.4A weights
@@ -495,6 +504,7 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
         uint32_t f_cq = 0;   // lines of this lane's bucket that pass: count | length sum << 12
         int f_qs = 0;        // their Phred sums
         uint32_t f_bad = 0;  // bit h: a line start contradicts hypothesis h
+        unsigned long long f_fix = 0;  // totals flavour: sum of round(gc_content * 2^32) over the bucket's lines
         uint2 e_first = make_uint2(0u, 0u), e_last = make_uint2(0u, 0u), carry = make_uint2(0u, 0u);
         const int rounds = __reduce_max_sync(0xffffffffu, cnt);
         const uint32_t a_prev = sb + o_prev, a_next = sb + o_next;
@@ -557,6 +567,16 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
                 const bool line = valid && (i | base) != 0;
                 const uint32_t cr = rec_cr(e.y);
                 len = (uint32_t)(rec_pos(e.y) - rec_pos(pe.y) - 1) - cr;
+                if (kFusedSeq) {
+                    // line i is a sequence line under h = (1 - i) & 3 = (1 - lane) & 3: this lane's ONE bucket
+                    const int gsum = rec_pg(e.y) - rec_pg(pe.y);
+                    if (line) {
+                        f_cq += 1u + (len << 12);
+                        f_qs += gsum;
+                        f_fix += gc_fix32((uint32_t)gsum, len);
+                    }
+                    return false;
+                }
                 qs = (int)e.x - (int)pe.x - 10 - 13 * (int)cr - 33 * (int)len;
                 if (plan.i32) {
                     // ee = +-2^sh (sum - c n), exact in 32 bits; ee != 0 means |sum - c n| >= 2^-20 > 1e-7, which puts the
@@ -663,12 +683,15 @@ __global__ void __launch_bounds__(FQ_THREADS, 6) fastq_tile_kernel(const __grid_
             for (int d = 4; d < 32; d <<= 1) {
                 f_cq += __shfl_xor_sync(0xffffffffu, f_cq, d);
                 f_qs += __shfl_xor_sync(0xffffffffu, f_qs, d);
+                if (kFusedSeq) f_fix += __shfl_xor_sync(0xffffffffu, f_fix, d);
             }
             const uint32_t bad4 = __reduce_or_sync(0xffffffffu, f_bad);
             FusedTile* ft = a.fused_tiles + tile;
             if (lane < 4) {
-                ft->cq[(3 - lane) & 3] = f_cq;
-                ft->qs[(3 - lane) & 3] = f_qs;
+                const int bk = kFusedSeq ? ((1 - lane) & 3) : ((3 - lane) & 3);  // sequence lines: h = 1 - i; quality lines: h = 3 - i
+                ft->cq[bk] = f_cq;
+                ft->qs[bk] = f_qs;
+                if (kFusedSeq) a.fused_fix[(int64_t)tile * 4 + bk] = f_fix;
             }
             if (lane == 4) *reinterpret_cast<uint4*>(&ft->ps0) = make_uint4(e_first.x, e_first.y, bad4, 0u);
         }
@@ -944,6 +967,69 @@ __global__ void __launch_bounds__(256) fastq_fused_combine_kernel(const FastqSca
     }
 }
 
+// K2 of the fused TOTALS flavour (EXB_F_FUSED | EXB_F_SEQ): the bucket of the tile's true phase holds the aggregates of
+// its sequence lines 1..; the tile's first line is finished here from the predecessors' tail words (length and G/C
+// count of the part before the tile).  fused_agg: [1] sum of lengths, [2] sum of G/C, [3] sequence lines, [5] sum of
+// round(gc_content * 2^32)  -- the layout exb_fastq_seq_totals fills from the per-record arrays of the general scan.
+__global__ void __launch_bounds__(256) fastq_fused_seq_combine_kernel(const FastqScanArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = a.n_tiles;
+    const int64_t origin = a.begin & ~(int64_t)15;
+    const uint64_t init = a.prev ? a.prev->total_lines : 0ull;
+    const int64_t threads = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long cnt = 0, sl = 0, sg = 0, sf = 0;
+    bool bad = false;
+    for (int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tile < n_tiles; tile += threads) {
+        const int n_events = (int)a.tile_cnt[tile];
+        const bool is_last = tile == n_tiles - 1;
+        if (tile == 0 && a.prev && a.prev->err_pos != 0ull) atomicMax(&a.result->err_pos, a.prev->err_pos);
+        if (n_events == 0 && !is_last) continue;
+        const uint64_t excl = init + (uint64_t)a.line_base[tile];
+        const int64_t tile_base = origin + tile * WT_BYTES;
+        const OpenLine open = open_line_before(a.tails, tile, origin, a);
+        if (n_events > 0) {
+            const FusedTile* ft = a.fused_tiles + tile;
+            const int h = (int)(excl & 3);
+            const uint32_t cq = ft->cq[h];
+            cnt += cq & 0xFFFu;
+            sl += cq >> 12;
+            sg += (unsigned long long)(uint32_t)ft->qs[h];
+            sf += a.fused_fix[tile * 4 + h];
+            bad = bad || ((ft->bad4 >> h) & 1u) != 0;
+            const uint32_t y0 = ft->y0;
+            uint32_t len = (uint32_t)(tile_base - open.start) + (uint32_t)rec_pos(y0);
+            const uint32_t cr = len > 0 ? rec_cr(y0) : 0u;
+            len -= cr;
+            if ((h & 1) == 0) {
+                if (!(open.flags & (h == 0 ? 2u : 1u))) bad = true;
+            } else if (h == 1) {
+                const uint32_t g1 = (uint32_t)(rec_pg(y0) + open.g);
+                cnt += 1;
+                sl += len;
+                sg += g1;
+                sf += gc_fix32(g1, len);
+            }
+        }
+        if (is_last) write_final_state(a, excl + (uint64_t)n_events, n_events, tile_base, a.tails[tile], open);
+    }
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, dd);
+        sl += __shfl_xor_sync(0xffffffffu, sl, dd);
+        sg += __shfl_xor_sync(0xffffffffu, sg, dd);
+        sf += __shfl_xor_sync(0xffffffffu, sf, dd);
+    }
+    const bool any_bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        unsigned long long* agg = reinterpret_cast<unsigned long long*>(a.fused_agg);
+        if (sl) atomicAdd(agg + 1, sl);
+        if (sg) atomicAdd(agg + 2, sg);
+        if (cnt) atomicAdd(agg + 3, cnt);
+        if (sf) atomicAdd(agg + 5, sf);
+        if (any_bad) atomicMax(&a.result->err_pos, ~(unsigned long long)a.n);
+    }
+}
+
 // =================================================================== sharded COUNT with ONE exchange
 // A byte-range shard does not know the phase of its first line until it has heard from its predecessors.  Instead of
 // waiting for that (exchange -> compose -> K2 -> reduce: four dependent launches, two of them spinning on NVLink flags),
@@ -1139,7 +1225,8 @@ static cudaError_t launch_tile_kernel(FastqScanArgs a, cudaStream_t st) {
 }
 
 cudaError_t fastq_tile_launch(const FastqScanArgs& a, int flags, cudaStream_t st) {
-    if (flags & EXB_F_FUSED) return launch_tile_kernel<EXB_F_FUSED | EXB_F_QUAL>(a, st);
+    if (flags & EXB_F_FUSED)
+        return (flags & EXB_F_SEQ) && !(flags & EXB_F_QUAL) ? launch_tile_kernel<EXB_F_FUSED | EXB_F_SEQ>(a, st) : launch_tile_kernel<EXB_F_FUSED | EXB_F_QUAL>(a, st);
     switch (flags & (EXB_F_SEQ | EXB_F_QUAL)) {
     case 0: return launch_tile_kernel<0>(a, st);
     case EXB_F_SEQ: return launch_tile_kernel<EXB_F_SEQ>(a, st);
@@ -1191,7 +1278,8 @@ cudaError_t fastq_emit_launch(const FastqScanArgs& a, int flags, bool wide_offse
     if (flags & EXB_F_FUSED) {
         int64_t blocks = (a.n_tiles + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        fastq_fused_combine_kernel<<<dim3((unsigned)blocks), dim3(256), 0, st>>>(a);
+        if ((flags & EXB_F_SEQ) && !(flags & EXB_F_QUAL)) fastq_fused_seq_combine_kernel<<<dim3((unsigned)blocks), dim3(256), 0, st>>>(a);
+        else fastq_fused_combine_kernel<<<dim3((unsigned)blocks), dim3(256), 0, st>>>(a);
         return cudaGetLastError();
     }
     return wide_offsets ? launch_emit<uint64_t>(a, flags, st) : launch_emit<uint32_t>(a, flags, st);

@@ -429,8 +429,18 @@ __global__ void __launch_bounds__(GS_THREADS, 8) gather_span_kernel(const uint8_
         }
         return m;
     };
-    auto map4 = [&](uint32_t x, int64_t pos) -> uint32_t {
-        return map1(x & 0xFF, pos) | (map1((x >> 8) & 0xFF, pos + 1) << 8) | (map1((x >> 16) & 0xFF, pos + 2) << 16) | (map1(x >> 24, pos + 3) << 24);
+    auto map4 = [&](uint32_t x, int64_t pos) -> uint32_t {  // one validity test per word (see fastq_split_kernel)
+        const uint32_t m = (uint32_t)s_lut[x & 0xFF] | ((uint32_t)s_lut[(x >> 8) & 0xFF] << 8) | ((uint32_t)s_lut[(x >> 16) & 0xFF] << 16) |
+                           ((uint32_t)s_lut[x >> 24] << 24);
+        if (((m - 0x01010101u) & ~m & 0x80808080u) != 0u) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (((m >> (8 * k)) & 0xFFu) == 0u) {
+                    const unsigned long long w = ((unsigned long long)(pos + k) << 8) | ((x >> (8 * k)) & 0xFFu);
+                    bad = w < bad ? w : bad;
+                }
+        }
+        return m;
     };
     const int64_t total = off[n_rows];
     // spans are aligned to 16 bytes of the OUTPUT ADDRESS so that chunk stores are aligned whatever `out` is

@@ -196,6 +196,18 @@ def fastq_scan_filter(buf, preds, n=None, out=None):
     return c
 
 
+def fastq_scan_totals(buf, n=None, ws=None):
+    """Fused TOTALS flavour (C5): returns (int64[8] device tensor: [1] sum len, [2] sum #GC, [3] sequence lines,
+    [5] sum round(gc_content * 2^32)), the scan result block).  One pass, nothing per record is written."""
+    n = buf.numel() if n is None else int(n)
+    dev = buf.device
+    if ws is None:
+        ws = torch.empty(lib().exb_fastq_workspace_bytes(n + 16, n // 24 + 16384), dtype=torch.uint8, device=dev)
+    agg = torch.zeros(8, dtype=torch.int64, device=dev)
+    check(lib().exb_fastq_scan_totals(_ptr(buf), 0, n, 1, None, _ptr(agg), 0, _ptr(ws), ws.numel(), _stream()))
+    return agg, fetch_result(ws)
+
+
 def exclusive_scan_u32(x, n=None):
     n = x.numel() if n is None else n
     out = torch.empty(n + 1, dtype=torch.int64, device=x.device)

@@ -489,30 +489,39 @@ def fasta_first_header(shard, window=1 << 20):
 
 class ShardedFastqTotals:
     """SELECT COUNT(*), SUM(#GC), SUM(length(sequence)), AVG(gc_content(sequence)) FROM read_fastq(file) over this rank's
-    byte-range shard (BASELINE config C5).  Same protocol as ShardedFastqCount with the GENERAL scan flavour:
+    byte-range shard (BASELINE config C5).  Two-exchange protocol of ShardedFastqCount with the fused TOTALS flavour
+    (fused=True, the default):
 
-      byte pass + line offsets + result block (exb_fastq_scan_begin) -> exchange of the 128-byte result blocks ->
-      exb_fastq_compose_prev (device) -> K2 under the true predecessor with shard-local record indices
-      (exb_fastq_scan_resolve, EXB_F_SEQ | EXB_F_LOCAL_RECORDS) -> exb_fastq_seq_totals -> reduce.
+      byte pass with the sequence-line aggregates of all four phase hypotheses per tile + line offsets + result block
+      (exb_fastq_scan_totals_begin) -> exchange of the 128-byte result blocks -> exb_fastq_compose_prev (device) ->
+      K2 picks each tile's bucket under the true predecessor (exb_fastq_scan_totals_resolve) -> reduce.
 
-    Per-record sequence entries are written by the shard in which the sequence LINE ends, so the sums are additive over
-    shards whatever record the cut falls in.  `total` (int64[8], device) holds the GLOBAL values on every rank:
+    fused=False keeps the GENERAL scan flavour (exb_fastq_scan_begin -> ... -> exb_fastq_scan_resolve with
+    EXB_F_SEQ | EXB_F_LOCAL_RECORDS -> exb_fastq_seq_totals over the per-record arrays): the two are bit-identical
+    (tests/test_gpu_dist.py), the fused one writes nothing per record.
+
+    A sequence line counts in the shard in which the LINE ends, so the sums are additive over shards whatever record the
+    cut falls in.  `total` (int64[8], device) holds the GLOBAL values on every rank:
     [0] records (lines of the file / 4), [1] sum of sequence lengths, [2] sum of G/C, [5] sum of round(gc_content * 2^32),
     [6] lines of the file mod 4 (must be 0), [7] shards that met a malformed record (must be 0)."""
 
-    def __init__(self, shard, group, ranges=None, rec_cap=None, max_lines=None):
+    def __init__(self, shard, group, ranges=None, rec_cap=None, max_lines=None, fused=None):
+        import os
+
         import torch
 
         from . import device as D
 
         self.shard, self.group = shard, group
+        self.fused = (os.environ.get("EXB_TOTALS_FUSED", "1") != "0") if fused is None else bool(fused)
         dev = shard.buf.device
         # capacities: estimates that fit any file with records of >= 32 bytes; a caller that knows its records passes tight ones
         self.ws = torch.empty(_lib.lib().exb_fastq_workspace_bytes(shard.n + 16, max_lines if max_lines else shard.n // 24 + 16384),
                               dtype=torch.uint8, device=dev)
         self.rec_cap = rec_cap if rec_cap else shard.n // 32 + 4096
-        self.seq_len = torch.zeros(self.rec_cap, dtype=torch.int32, device=dev)
-        self.gc = torch.zeros(self.rec_cap, dtype=torch.int32, device=dev)
+        if not self.fused:
+            self.seq_len = torch.zeros(self.rec_cap, dtype=torch.int32, device=dev)
+            self.gc = torch.zeros(self.rec_cap, dtype=torch.int32, device=dev)
         self.agg = torch.zeros(8, dtype=torch.int64, device=dev)
         self.total = torch.zeros(8, dtype=torch.int64, device=dev)
         self.true_prev = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -533,8 +542,12 @@ class ShardedFastqTotals:
         from . import device as D
 
         s = self.shard
-        _lib.check(_lib.lib().exb_fastq_scan_begin(D._ptr(s.buf), s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.prov), self.flags,
-                                                   D._ptr(self.ws), self.ws.numel(), D._stream()))
+        if self.fused:
+            _lib.check(_lib.lib().exb_fastq_scan_totals_begin(D._ptr(s.buf), s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.prov),
+                                                              D._ptr(self.ws), self.ws.numel(), D._stream()))
+        else:
+            _lib.check(_lib.lib().exb_fastq_scan_begin(D._ptr(s.buf), s.begin, s.n, 1 if s.is_last else 0, D._ptr(self.prov), self.flags,
+                                                       D._ptr(self.ws), self.ws.numel(), D._stream()))
         return _result_block(self.ws)
 
     def resolve_local(self, blocks, rank):
@@ -546,6 +559,10 @@ class ShardedFastqTotals:
         if rank > 0:
             _lib.check(L.exb_fastq_compose_prev(D._ptr(blocks), D._ptr(self.d_ranges), self.world, rank, D._ptr(self.true_prev), D._stream()))
             prev = self.true_prev
+        if self.fused:
+            _lib.check(L.exb_fastq_scan_totals_resolve(s.begin, s.n, 1 if s.is_last else 0, D._ptr(prev), D._ptr(self.agg), 0,
+                                                       D._ptr(self.ws), self.ws.numel(), D._stream()))
+            return
         # a record that straddles the shard's first byte only gets the fields whose line ends here: start from zeros
         self.seq_len.zero_()
         self.gc.zero_()

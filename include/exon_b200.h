@@ -357,6 +357,24 @@ EXB_API int exb_fastq_scan_filter(const void *d_buf, int64_t begin, int64_t n, i
  *      input bytes are not read a second time.  d_agg / per-record outputs of step 1 are overwritten.
  * exon_duckdb_b200/dist.py is the host side of this protocol.
  */
+/* Fused TOTALS flavour (BASELINE config C5: SELECT COUNT(*), SUM(length(sequence)), SUM(#GC), AVG(gc_content(sequence))):
+ * the byte pass adds up, per 4 KiB tile and per phase hypothesis, the aggregates of every line that would be a
+ * SEQUENCE line; K2 picks the bucket of the tile's true phase.  Nothing per record or per line is written.
+ *   d_agg int64[8]: [1] sum of sequence lengths  [2] sum of G/C  [3] sequence lines  [5] sum of round(gc_content * 2^32)
+ *   with gc_content = (float)#GC / (float)len per record as the scalar function defines it (0 for an empty sequence);
+ *   the record count is total_lines / 4 of the result block.  Same layout as exb_fastq_seq_totals over the per-record
+ *   arrays of the general scan, and bit-identical to it.  accumulate != 0 adds to d_agg instead of zeroing it first.
+ * _begin / _resolve split the call for byte-range shards exactly like exb_fastq_scan_begin / _resolve: K1 + line
+ * offsets + result block first, K2 under the true predecessor (exb_fastq_compose_prev) after the block exchange. */
+EXB_API int exb_fastq_scan_totals(const void *d_buf, int64_t begin, int64_t n, int is_final, const void *d_prev_workspace,
+                                  int64_t *d_agg, int accumulate, void *d_workspace, int64_t workspace_bytes, void *stream);
+EXB_API int exb_fastq_scan_totals_begin(const void *d_buf, int64_t begin, int64_t n, int is_final,
+                                        const void *d_prev_workspace, void *d_workspace, int64_t workspace_bytes,
+                                        void *stream);
+EXB_API int exb_fastq_scan_totals_resolve(int64_t begin, int64_t n, int is_final, const void *d_prev_workspace,
+                                          int64_t *d_agg, int accumulate, void *d_workspace, int64_t workspace_bytes,
+                                          void *stream);
+
 /* Step 1 of the fused COUNT flavour without its K2: the byte pass, the line-offset scan and the result block only
  * (a shard does not know its phase yet, so a provisional K2 would be thrown away).  Follow with the exchange and
  * exb_fastq_scan_filter_resolve on EVERY shard (the first one with d_prev_workspace = NULL). */

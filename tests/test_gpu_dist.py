@@ -150,7 +150,7 @@ def test_fasta_first_header_and_bounds(cuda_device):
 
 
 # ------------------------------------------------------------------ C5: COUNT + SUM(#GC) + SUM(len) + AVG(gc_content) over byte-range shards
-def _sharded_totals(data, cuts, dev):
+def _sharded_totals(data, cuts, dev, fused=True):
     bounds = [0] + list(cuts) + [len(data)]
     G = len(bounds) - 1
     shards = []
@@ -160,7 +160,7 @@ def _sharded_totals(data, cuts, dev):
         halo = bytes(max(0, begin - lo)) + bytes(data[max(0, lo - begin):lo]) if begin else b""
         shards.append(dist.Shard(D.to_device(halo + bytes(data[lo:hi]), dev), lo, hi, begin, k == G - 1))
     ranges = [[s.lo, s.hi, s.begin] for s in shards]
-    jobs = [dist.ShardedFastqTotals(s, None, ranges=ranges) for s in shards]
+    jobs = [dist.ShardedFastqTotals(s, None, ranges=ranges, fused=fused) for s in shards]
     blocks = torch.cat([j.scan().clone() for j in jobs])  # the all-gather
     total = torch.zeros(8, dtype=torch.int64, device=dev)
     for k, j in enumerate(jobs):
@@ -185,5 +185,13 @@ def test_sharded_totals_equal_oracle(cuda_device, seed, kw):
     cut_sets = [[c] for c in range(0, len(data) + 1, max(1, len(data) // 61))]
     cut_sets += [sorted(rng.randint(0, len(data)) for _ in range(rng.randint(2, 7))) for _ in range(25)]
     for cuts in cut_sets:
-        t = dist.check_count(_sharded_totals(data, cuts, cuda_device))
-        assert (t[0], t[1], t[2], t[5]) == want, (cuts, t, want)
+        # the fused TOTALS flavour (aggregates of all four phase hypotheses in the byte pass) and the general scan +
+        # exb_fastq_seq_totals over per-record arrays: both exact
+        for fused in (True, False):
+            t = dist.check_count(_sharded_totals(data, cuts, cuda_device, fused))
+            assert (t[0], t[1], t[2], t[5]) == want, (fused, cuts, t, want)
+    # one shot over the whole file
+    agg, res = D.fastq_scan_totals(D.to_device(data, cuda_device))
+    a = agg.cpu().tolist()
+    assert res.err_pos == _lib.NO_POS and res.total_lines == 4 * want[0]
+    assert (a[1], a[2], a[3], a[5]) == (want[1], want[2], want[0], want[3])
