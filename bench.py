@@ -9,10 +9,12 @@ One step = one pass of the hot path over the whole file image:
     each tile's bucket)
 `value`  : input already resident in HBM, CUDA events on the launching stream, max over ranks.
 `e2e`    : the same query through the plugin's own C ABI (exb_reader_open2 + exb_reader_count + exb_reader_close, the
-           calls the DuckDB extension's init_global makes for this statement) on a FILE (tmpfs): page cache -> pinned
-           blocks -> H2D -> scan / filter kernels -> the count read back, every step; `h2d_peak_gbs` (pinned
-           cudaMemcpy, measured here, all ranks at once) is the bound it is compared with.  `e2e_pinned_image` keeps
-           round 1's number: the host-buffer engine (exb_engine_fastq_count) fed from an already pinned image.
+           calls the DuckDB extension's init_global makes for this statement) on a FILE (tmpfs), every step: the file's
+           page cache (registered with CUDA by the reader after the file's first scan: pinned in place) -> H2D -> scan /
+           filter kernels -> the count read back.  `e2e_first_scan` is the same call on the path a first scan takes
+           (page cache -> pinned blocks -> H2D, EXB_RD_COPY_IO); `h2d_peak_gbs` (pinned cudaMemcpy, measured here, all
+           ranks at once) is the bound both are compared with.  `e2e_pinned_image` keeps round 1's number: the
+           host-buffer engine (exb_engine_fastq_count) fed from an already pinned image.
 `paths`  : (N = 1) the other configurations of BASELINE.json, device-resident, each with its algorithmic GB/s, fraction
            of the HBM peak and committed DRAM traffic: C3 (wrapped FASTA, gc_content per contig), C4 (ONT reads,
            reverse_complement projection), C2 general scan and 4-column materialisation (tools/paths.py).
@@ -384,6 +386,7 @@ def main():
 
     # ---- end to end: file (tmpfs) -> the plugin's reader C ABI -> the count, every step
     e2e = None
+    e2e_first = None
     e2e_pinned = None
     host_ptr = None
     if not args.no_e2e:
@@ -417,37 +420,68 @@ def main():
         filt = ("mean_quality(quality_scores)>%r" % THRESH).encode()
         opt = _lib.reader_options(column_mask=0, device=local)
 
-        def reader_count():
+        def reader_count(flags=0):
+            opt.flags = flags
             h = C.c_void_p()
             _lib.check(L.exb_reader_open2(path.encode(), b"fastq", None, 2048, filt, C.byref(opt), C.byref(h)))
             n = C.c_int64()
             rc = L.exb_reader_count(h, C.byref(n))
+            direct = L.exb_reader_io_path(h)
             L.exb_reader_close(h)
             _lib.check(rc)
-            return n.value
+            return n.value, direct
 
-        for _ in range(2):
-            n_e2e = reader_count()
-        if world > 1:
-            dist.barrier()
+        def timed_reader(flags):
+            for _ in range(2):
+                reader_count(flags)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                n, direct = reader_count(flags)
+            dt = (time.perf_counter() - t0) / e2e_steps
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return n, direct, tt.item()
+
         e2e_steps = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            n_e2e = reader_count()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = tt.item()
         n_chunks = (e2e_bytes + (64 << 20) - 1) // (64 << 20)
-        e2e = {"value": total_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes,
-               "d2h_bytes_per_step": n_chunks * (C.sizeof(_lib.ScanResult) + 16 + 8) + 8,
-               "ms_per_step": dt * 1e3, "steps": e2e_steps, "pass": int(n_e2e),
-               "h2d_peak_gbs": h2d_peak_all, "frac_of_h2d_peak": (total_bytes / dt / 1e9) / h2d_peak_all if h2d_peak_all else None,
-               "api": "exb_reader_open2(file, filters='mean_quality(quality_scores)>30') + exb_reader_count + exb_reader_close",
-               "file": path,
-               "note": "host wall clock around open + count + close, max over ranks; the file lives on tmpfs (page cache), "
-                       "every byte is copied into pinned blocks, sent over PCIe and scanned inside the timed region"}
+        api = "exb_reader_open2(file, filters='mean_quality(quality_scores)>30') + exb_reader_count + exb_reader_close"
+
+        def e2e_entry(n, dt, note):
+            return {"value": total_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes,
+                    "d2h_bytes_per_step": n_chunks * (C.sizeof(_lib.ScanResult) + 16 + 8) + 8,
+                    "ms_per_step": dt * 1e3, "steps": e2e_steps, "pass": int(n),
+                    "h2d_peak_gbs": h2d_peak_all, "frac_of_h2d_peak": (total_bytes / dt / 1e9) / h2d_peak_all if h2d_peak_all else None,
+                    "api": api, "file": path, "note": note}
+
+        # (1) the path a FIRST scan of a file takes: page cache -> pinned blocks (16 host threads) -> PCIe -> scan
+        n_e2e, _, dt = timed_reader(_lib.RD_COPY_IO)
+        e2e_first = e2e_entry(n_e2e, dt, "host wall clock around open + count + close, max over ranks; the file lives on tmpfs (page cache), every "
+                                         "byte is copied into pinned blocks, sent over PCIe and scanned inside the timed region "
+                                         "(EXB_RD_COPY_IO: what the first scan of a file does)")
+        # (2) every later scan: the first complete scan had the file's page cache registered with CUDA (pinned in place), so
+        # the bytes go page cache -> PCIe -> scan with no host copy.  Nothing is cached on the device: all of the file
+        # crosses PCIe and is scanned inside the timed region of every step.
+        reader_count(0)
+        t_w = time.perf_counter()
+        while L.exb_file_cache_state(path.encode()) == 1 and time.perf_counter() - t_w < 120:
+            time.sleep(0.01)
+        t_reg = time.perf_counter() - t_w
+        n2, direct, dt2 = timed_reader(0)
+        assert n2 == n_e2e, (n2, n_e2e)
+        if direct:
+            e2e = e2e_entry(n2, dt2, "host wall clock around open + count + close, max over ranks; repeated scan of a tmpfs file whose page "
+                                     "cache the reader registered with CUDA after its first scan (cudaHostRegister, %.2f s in the background): "
+                                     "every byte goes page cache -> PCIe -> scan inside the timed region, no host copy; "
+                                     "`e2e_first_scan` is the same call on the copy path" % t_reg)
+            e2e["io_path"] = "registered page cache (DMA from the file's pages)"
+            e2e_first["io_path"] = "page cache -> pinned blocks -> DMA"
+        else:  # this kernel / file system refuses to pin page-cache pages: the copy path is the only one
+            e2e = e2e_first
+            e2e["io_path"] = "page cache -> pinned blocks -> DMA (registration not available here)"
+            e2e_first = None
         # round 1's number, kept for comparison: the host-buffer engine fed from an already pinned image
         eng = C.c_void_p()
         _lib.check(L.exb_engine_create(local, 64 << 20, C.byref(eng)))
@@ -626,6 +660,8 @@ def main():
         line["numa_node"] = numa_node
         if e2e:
             line["e2e"] = e2e
+        if e2e_first:
+            line["e2e_first_scan"] = e2e_first
         if e2e_pinned:
             line["e2e_pinned_image"] = e2e_pinned
         if path_rows:

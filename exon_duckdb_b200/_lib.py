@@ -69,7 +69,7 @@ class ColumnView(C.Structure):
 
 MAX_COMPUTED = 8
 C_GC_CONTENT, C_SEQ_MAP, C_QUALITY_LIST, C_MEAN_QUALITY, C_SEQ_LENGTH, C_QUAL_LENGTH = 1, 2, 3, 4, 5, 6
-RD_STRING_T, RD_NO_OFFSETS = 1, 2
+RD_STRING_T, RD_NO_OFFSETS, RD_COPY_IO = 1, 2, 4
 T_VARCHAR, T_FLOAT, T_DOUBLE, T_INT32_LIST, T_INT64 = 0, 1, 2, 3, 4
 
 
@@ -143,6 +143,8 @@ SIGNATURES = {
     "exb_reader_next": (_i32, [_vp, C.POINTER(Batch)]),
     "exb_batch_release": (None, [C.POINTER(Batch)]),
     "exb_reader_count": (_i32, [_vp, C.POINTER(_i64)]),
+    "exb_file_cache_state": (_i32, [C.c_char_p]),
+    "exb_reader_io_path": (_i32, [_vp]),
     "exb_reader_close": (None, [_vp]),
     "exb_scan_workspace_bytes": (_i64, [_i64]),
     "exb_fastq_workspace_bytes": (_i64, [_i64, _i64]),

@@ -755,14 +755,58 @@ struct IoPool {
 // and a repeated query finds the page tables already populated (the first pass over a 2.8 GB tmpfs file spends ~20 % of
 // its copy time in page faults, and unmapping it takes 25 ms).  At most four mappings are kept; evicted ones are unmapped
 // off the critical path.
+//
+// Registered page cache (round 2).  After its first complete scan, a mapping that could be made writable-shared (the
+// file opened O_RDWR; nothing is ever written) is registered with CUDA in the background (cudaHostRegister, portable):
+// the file's PAGE-CACHE pages become pinned memory, and every later scan of the file copies them to the device by DMA
+// straight from where they are -- no page cache -> pinned-block copy, which is what bounds a first scan (~46 GB/s on a
+// 16-core host, and it does not scale with the GPUs of a box: profiles/round2_iobench2.txt).  Measured: registration
+// 12 GB/s, H2D from the registered mapping 55.6 GB/s = the PCIe rate (profiles/round2_hostreg.txt).  Works for tmpfs and
+// other memory-backed files; where the kernel refuses long-term pins (most disk file systems) registration fails and
+// the copy path stays.  EXON_B200_REGISTER=0 turns it off, EXON_B200_REGISTER_MAX_GB caps the pinned page cache (32).
 struct FileMap {
     const uint8_t* p = nullptr;
     int64_t size = 0;
     dev_t dev = 0;
     ino_t ino = 0;
     int64_t mtime_ns = 0;
+    bool writable = false;            // mapped PROT_READ | PROT_WRITE, MAP_SHARED: the form cudaHostRegister accepts
+    std::atomic<int> reg{0};          // 0 not registered, 1 registration running, 2 registered, 3 failed / not possible
+    static std::atomic<int64_t>& registered_bytes() {
+        static std::atomic<int64_t> b{0};
+        return b;
+    }
     ~FileMap() {
+        if (p && reg.load() == 2) {
+            cudaHostUnregister(const_cast<uint8_t*>(p));
+            registered_bytes().fetch_sub(size);
+        }
         if (p) munmap(const_cast<uint8_t*>(p), (size_t)size);
+    }
+    // called when a scan has read the whole file once: register in the background (the scan that triggered it is done
+    // with the host side; nobody waits for this)
+    static void start_register(const std::shared_ptr<FileMap>& fm, int device) {
+        static const bool enabled = !(getenv("EXON_B200_REGISTER") && atoi(getenv("EXON_B200_REGISTER")) == 0);
+        static const int64_t cap = (getenv("EXON_B200_REGISTER_MAX_GB") ? atoll(getenv("EXON_B200_REGISTER_MAX_GB")) : 32) << 30;
+        if (!enabled || !fm || !fm->writable || fm->size < (16 << 20)) return;
+        int expect = 0;
+        if (!fm->reg.compare_exchange_strong(expect, 1)) return;
+        if (registered_bytes().fetch_add(fm->size) + fm->size > cap) {
+            registered_bytes().fetch_sub(fm->size);
+            fm->reg.store(3);
+            return;
+        }
+        std::thread([fm, device]() {
+            cudaSetDevice(device);
+            const cudaError_t e = cudaHostRegister(const_cast<uint8_t*>(fm->p), (size_t)fm->size, cudaHostRegisterPortable);
+            if (e == cudaSuccess) {
+                fm->reg.store(2);
+            } else {
+                cudaGetLastError();
+                registered_bytes().fetch_sub(fm->size);
+                fm->reg.store(3);
+            }
+        }).detach();
     }
 };
 struct MapCache {
@@ -772,7 +816,15 @@ struct MapCache {
         static MapCache* c = new MapCache();  // never destroyed (readers on detached threads may outlive static destructors)
         return *c;
     }
-    std::shared_ptr<FileMap> open(int fd) {
+    // the cached mapping of a file that is already mapped, or nullptr (exb_file_cache_state)
+    std::shared_ptr<FileMap> find(const struct stat& sb) {
+        const int64_t mt = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec;
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& f : keep)
+            if (f->dev == sb.st_dev && f->ino == sb.st_ino && f->size == (int64_t)sb.st_size && f->mtime_ns == mt) return f;
+        return nullptr;
+    }
+    std::shared_ptr<FileMap> open(int fd, const char* path = nullptr) {
         struct stat sb;
         if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size <= 0) return nullptr;
         const int64_t mt = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec;
@@ -786,10 +838,24 @@ struct MapCache {
                     return hit;
                 }
         }
-        void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
+        // writable-shared if the file may be opened for writing (the form CUDA can register; nothing is written), else read-only
+        void* m = MAP_FAILED;
+        bool writable = false;
+        if (path) {
+            const int wfd = ::open(path, O_RDWR);
+            if (wfd >= 0) {
+                struct stat wb;
+                if (fstat(wfd, &wb) == 0 && wb.st_dev == sb.st_dev && wb.st_ino == sb.st_ino)
+                    m = mmap(nullptr, (size_t)sb.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, wfd, 0);
+                ::close(wfd);
+                writable = m != MAP_FAILED;
+            }
+        }
+        if (m == MAP_FAILED) m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
         if (m == MAP_FAILED) return nullptr;
         madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
         std::shared_ptr<FileMap> fm = std::make_shared<FileMap>();
+        fm->writable = writable;
         fm->p = reinterpret_cast<const uint8_t*>(m);
         fm->size = sb.st_size;
         fm->dev = sb.st_dev;
@@ -900,7 +966,9 @@ constexpr int64_t BLOCK_SLACK = 1 << 20;
 struct Block {
     HBuf* h = nullptr;
     int64_t data_off = 0;      // raw bytes live at h->p + data_off
-    uint8_t* data() const { return h->as<uint8_t>() + data_off; }
+    const uint8_t* ext = nullptr;      // ... or at `ext`, inside a registered file mapping (h == nullptr): DMA straight from the page cache
+    std::shared_ptr<FileMap> ext_map;  // keeps that mapping alive
+    uint8_t* data() const { return ext ? const_cast<uint8_t*>(ext) : h->as<uint8_t>() + data_off; }
     int64_t raw_len = 0;
     int64_t raw_file_pos = 0;  // offset of the first raw byte in the (decompressed) file
     size_t file_idx = 0;
@@ -909,9 +977,10 @@ struct Block {
     bool end = false;          // no more files
 };
 struct HostBlock {  // an input block shared by the device thread and the chunk results whose strings point into it
-    HBuf* h;
+    HBuf* h;                          // pinned block (nullptr when the bytes live in a registered file mapping)
     std::shared_ptr<PinnedPool> pool;
-    HostBlock(HBuf* b, std::shared_ptr<PinnedPool> p) : h(b), pool(std::move(p)) {}
+    std::shared_ptr<FileMap> map;     // ... which this keeps alive instead
+    HostBlock(HBuf* b, std::shared_ptr<PinnedPool> p, std::shared_ptr<FileMap> m = nullptr) : h(b), pool(std::move(p)), map(std::move(m)) {}
     ~HostBlock() { pool->put(h); }
 };
 struct OutItem {
@@ -1216,7 +1285,7 @@ struct Reader {
                 if (fd < 0) err = "could not open " + path;
                 else {
                     const double tm = now();
-                    fmap = MapCache::get().open(fd);
+                    fmap = MapCache::get().open(fd, path.c_str());
                     if (fmap) {
                         map = fmap->p;
                         map_size = fmap->size;
@@ -1253,12 +1322,30 @@ struct Reader {
                 err = "compression of " + path + " is not supported by this build";
             }
             bool eof = false;
+            // DMA from the registered page cache (see FileMap) if an earlier scan of this file got it registered
+            const bool direct = map && fmap && fmap->reg.load() == 2 && !(flags & EXB_RD_COPY_IO);
+            io_direct.store(direct ? 1 : 0);
             while (err.empty() && !eof && !stopping) {
                 // block edges sit on multiples of 16 in file coordinates (the first block of a shard may be a little shorter):
                 // the chained COUNT scan of dev_main_fused needs that of every range but the first
                 const int64_t want = block_bytes.load() - (pos & 15);
                 Block b;
                 double t0 = now();
+                if (direct) {  // the mapping is pinned: the block IS the file's page cache, nothing to copy
+                    const int64_t got_d = std::min<int64_t>(want, end_pos - pos);
+                    b.ext = map + pos;
+                    b.ext_map = fmap;
+                    b.file_idx = fi;
+                    b.raw_file_pos = pos;
+                    b.raw_len = got_d;
+                    eof = pos + got_d >= end_pos;
+                    b.eof = eof;
+                    pos += got_d;
+                    if (n_blocks == 0) t_first_block = now() - t_open;
+                    n_blocks++;
+                    if (!inq.push(std::move(b))) break;
+                    continue;
+                }
                 b.h = pool->get(BLOCK_SLACK + want + 64);
                 b.data_off = BLOCK_SLACK;
                 t_io_alloc += now() - t0;
@@ -1340,6 +1427,8 @@ struct Reader {
                     break;
                 }
             }
+            // the whole file went by once through the copy path: have its page cache registered for the next scan
+            if (map && fmap && err.empty() && !stopping && !direct && !(flags & EXB_RD_COPY_IO)) FileMap::start_register(fmap, device);
             fmap.reset();
             if (fd >= 0) close(fd);
             if (gz) gzclose(gz);
@@ -1360,6 +1449,7 @@ struct Reader {
     int64_t shard_begin = 0, shard_end = 0;  // where the byte-range shard really starts / ends (after resync)
     // host image of the chunk being processed: host_base[i] is the byte d_cur[i] (nullptr: no contiguous image, see
     // dev_main); host_block keeps the pinned block that holds it alive
+    std::atomic<int> io_direct{0};  // the current file is read by DMA from its registered page cache (exb_reader_io_path)
     uint8_t* host_base = nullptr;
     std::shared_ptr<HostBlock> host_block;
     bool no_borrow = getenv("EXON_B200_NO_BORROW") != nullptr;  // debugging / A-B: always gather and copy the strings back
@@ -1942,13 +2032,15 @@ struct Reader {
                 uint8_t* base = nullptr;
                 if (carry_len == 0) {
                     base = blk;
+                } else if (b.ext) {  // the file is one contiguous piece of host memory: the carried tail sits right in front
+                    if (b.ext - b.ext_map->p >= carry_len) base = blk - carry_len;
                 } else if (carry_len <= b.data_off && host_base) {
                     memcpy(blk - carry_len, host_base + carry_off, (size_t)carry_len);
                     base = blk - carry_len;
                 }
                 host_base = base;
             }
-            host_cur = std::make_shared<HostBlock>(b.h, pool);  // (the previous chunk synchronised `st` after its copies: that block
+            host_cur = std::make_shared<HostBlock>(b.h, pool, b.ext_map);  // (the previous chunk synchronised `st` after its copies: that block
             host_block = host_cur;                              //  goes back to the pool once no chunk result points into it)
             if (!ok) return finish(derr);
             mark(1);
@@ -2049,7 +2141,8 @@ struct Reader {
     void dev_main_fused(std::vector<exb_predicate> preds) {
         DBuf d_chunk[2], d_wsx[2], d_agg;
         struct InFlight {
-            HBuf* h;
+            HBuf* h;                       // pinned block (nullptr: the bytes came straight from a registered file mapping,
+            std::shared_ptr<FileMap> map;  //  which this keeps alive until the copy is done)
             cudaEvent_t ev;
         };
         std::deque<InFlight> inflight;  // pinned blocks whose H2D copy may still be running
@@ -2135,7 +2228,7 @@ struct Reader {
                 pool->put(b.h);
                 return finish(derr, 0);
             }
-            inflight.push_back(InFlight{b.h, ev});
+            inflight.push_back(InFlight{b.h, b.ext_map, ev});
             const uint8_t* base = data - pos;  // base[file offset] = that byte
             if (!rc(exb_fastq_scan_filter(base, pos, pos + n, b.eof ? 1 : 0, prev_ws, preds.empty() ? nullptr : preds.data(), (int)preds.size(),
                                           d_agg.as<int64_t>(), 1, d_wsx[i].p, d_wsx[i].cap, st)))
@@ -2676,6 +2769,16 @@ int exb_reader_progress(const exb_reader* h, int64_t* bytes_done, int64_t* bytes
     if (bytes_total) *bytes_total = h->r->bytes_total.load();
     return 0;
 }
+
+int exb_file_cache_state(const char* path) {
+    struct stat sb;
+    if (!path || stat(path, &sb) != 0 || !S_ISREG(sb.st_mode)) return set_err(EXB_ERR_IO, "exb_file_cache_state: cannot stat the file");
+    std::shared_ptr<FileMap> fm = MapCache::get().find(sb);
+    if (!fm) return 0;
+    const int st = fm->reg.load();
+    return st == 3 ? 0 : st;
+}
+int exb_reader_io_path(const exb_reader* h) { return h && h->r ? h->r->io_direct.load() : 0; }
 
 void exb_reader_close(exb_reader* h) {
     if (!h) return;

@@ -170,6 +170,13 @@ typedef struct exb_computed {
                                lead into the pinned input block the reader staged the file in -- nothing was gathered
                                or copied back -- and stay valid until exb_batch_release like every other pointer     */
 
+#define EXB_RD_COPY_IO 4    /* always stage the file through pinned blocks (page cache -> pinned memory -> device) and do not
+                               have its page cache registered: the path a FIRST scan of a file takes anyway.  Without the
+                               flag, a plain file that was scanned once is registered with CUDA in the background (its
+                               page-cache pages become pinned memory; memory-backed file systems such as tmpfs, the file
+                               must be writable by the process although nothing is written) and every later scan copies
+                               it to the device by DMA straight from there.  exb_file_cache_state tells which applies.  */
+
 typedef struct exb_reader_options {
     uint32_t size;       /* sizeof(exb_reader_options) of the caller (versioning)                                  */
     int32_t device;      /* CUDA device ordinal that runs this reader's pipeline; -1 = the caller's current device */
@@ -236,6 +243,13 @@ EXB_API int exb_reader_progress(const exb_reader *reader, int64_t *bytes_done, i
 EXB_API int exb_reader_plan(const char *uri, const char *file_format, const char *compression, int64_t *total_bytes,
                             int32_t *n_files, int32_t *range_shardable);
 EXB_API void exb_reader_close(exb_reader *reader);
+/* Registered page cache of a plain input file: 0 = not registered (never scanned, not possible, or switched off),
+ * 1 = registration running in the background, 2 = registered: the next scan reads it by DMA from the page cache,
+ * negative = the file cannot be inspected. */
+EXB_API int exb_file_cache_state(const char *path);
+/* 1 if the file this reader is reading now comes by DMA from its registered page cache, 0 if it is staged through
+ * pinned blocks. */
+EXB_API int exb_reader_io_path(const exb_reader *reader);
 /* CUDA devices visible to the process (0 when there is none). */
 EXB_API int exb_device_count(void);
 

@@ -1,0 +1,7 @@
+python - <<'PY'
+import numpy as np
+np.random.default_rng(1).integers(0,255,size=3<<30,dtype=np.uint8).tofile('/dev/shm/hostreg.bin')
+PY
+tools/probe/hostreg /dev/shm/hostreg.bin
+rm -f /dev/shm/hostreg.bin
+uname -r

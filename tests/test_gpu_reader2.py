@@ -311,3 +311,61 @@ def test_gzip_input_that_is_not_gzip_or_is_truncated_fails(cuda_device, tmp_path
         msg = _lib.lib().exb_last_error()
         _lib.lib().exb_reader_close(h)
         assert rc != 0 and b"gzip" in msg, (path, rc, msg)
+
+
+def test_second_scan_reads_the_registered_page_cache(cuda_device, monkeypatch):
+    """A memory-backed file that was scanned once is registered with CUDA in the background (its page cache becomes pinned
+    memory); the next scans DMA from it instead of copying through pinned blocks.  Rows, borrowed string_t entries, the
+    fused COUNT and byte-range shards must be identical on both paths."""
+    import os
+    import time
+    from exon_duckdb_b200 import _lib
+    from oracle import oracle as O
+    from tools import synth
+    if not os.path.isdir("/dev/shm") or not os.access("/dev/shm", os.W_OK):
+        pytest.skip("no tmpfs to put a memory-backed file on")
+    L = _lib.lib()
+    monkeypatch.setenv("EXON_B200_CHUNK_BYTES", str(3 << 20))  # several blocks, records straddling every edge
+    text = synth.gen_host(synth.gen_params("illumina", 60000, seed=77)).tobytes()
+    assert len(text) > (16 << 20)
+    path = "/dev/shm/exb_test_registered_%d.fastq" % os.getpid()
+    with open(path, "wb") as f:
+        f.write(text)
+    try:
+        ref = O.parse_fastq(text)
+        want_pass = O.fastq_count_mean_quality(text, ">", 30.0)[0]
+        filt = b"mean_quality(quality_scores)>30.0"
+
+        def count(**kw):
+            h = _open(path, "fastq", filters=filt, column_mask=0, **kw)
+            c = C.c_int64()
+            _lib.check(L.exb_reader_count(h, C.byref(c)))
+            direct = L.exb_reader_io_path(h)
+            L.exb_reader_close(h)
+            return c.value, direct
+
+        assert L.exb_file_cache_state(path.encode()) == 0
+        assert count() == (want_pass, 0)                      # first scan: the copy path; triggers the registration
+        t0 = time.time()
+        while L.exb_file_cache_state(path.encode()) == 1 and time.time() - t0 < 20:
+            time.sleep(0.01)
+        if L.exb_file_cache_state(path.encode()) != 2:
+            pytest.skip("this kernel / file system does not let CUDA pin page-cache pages")
+        assert count() == (want_pass, 1)                      # fused COUNT by DMA from the page cache
+        assert count(flags=_lib.RD_COPY_IO) == (want_pass, 0)  # the flag keeps a reader on the copy path
+        for flags in (_lib.RD_STRING_T | _lib.RD_NO_OFFSETS, 0):  # borrowed strings point into the mapping / gathered columns
+            h = _open(path, "fastq", column_mask=0xF, flags=flags)
+            cols = _drain(h, 4)
+            assert L.exb_reader_io_path(h) == 1
+            L.exb_reader_close(h)
+            assert cols[0] == ref.strings("name") and cols[2] == ref.strings("sequence") and cols[3] == ref.strings("quality_scores")
+        # byte-range shards (cuts inside records) of the registered file
+        n = len(text)
+        got = []
+        for lo, hi in ((0, n // 3 + 5), (n // 3 + 5, 2 * n // 3 + 77), (2 * n // 3 + 77, n)):
+            h = _open(path, "fastq", column_mask=0x1, flags=_lib.RD_STRING_T, range_lo=lo, range_hi=hi)
+            got += _drain(h, 4)[0]
+            L.exb_reader_close(h)
+        assert got == ref.strings("name")
+    finally:
+        os.unlink(path)
