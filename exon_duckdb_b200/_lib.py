@@ -43,6 +43,11 @@ class FormatCols(C.Structure):
     _fields_ = [("d_off", C.c_void_p * 4), ("d_data", C.c_void_p * 4), ("d_desc_valid", C.c_void_p)]
 
 
+class BgzfBlock(C.Structure):
+    _fields_ = [("in_off", C.c_int64), ("out_off", C.c_int64), ("clen", C.c_uint32), ("isize", C.c_uint32), ("crc32", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
 class ReaderResult(C.Structure):
     _fields_ = [("error", C.c_void_p)]
 
@@ -204,6 +209,12 @@ SIGNATURES = {
     "exb_engine_fastq_count": (_i32, [_vp, _vp, _i64, C.POINTER(Predicate), _i32, C.POINTER(_i64), C.POINTER(ScanResult)]),
     "exb_host_alloc": (_vp, [_i64]),
     "exb_host_free": (None, [_vp]),
+    "exb_bgzf_probe_host": (_i32, [_vp, _i64]),
+    "exb_bgzf_index_host": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(BgzfBlock), _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "exb_bgzf_scratch_bytes": (_i64, []),
+    "exb_bgzf_inflate": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "exb_bgzf_finish": (_i32, [_vp, C.POINTER(_i64), _vp]),
+    "exb_bgzf_status": (_i32, [C.POINTER(C.c_uint32), C.POINTER(_i64)]),
 }
 
 _lib = None

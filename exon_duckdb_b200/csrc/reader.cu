@@ -41,6 +41,8 @@
 
 namespace exb {
 int set_err(int code, const char* fmt, ...);
+cudaError_t bgzf_inflate_launch(const uint8_t* d_in, const exb_bgzf_block* d_blocks, int64_t n_blocks, uint8_t* d_out, unsigned int* d_state, int check_crc,
+                                int64_t block_base, cudaStream_t st);
 cudaError_t str_pred_launch(const uint8_t*, const int64_t*, const uint32_t*, const uint8_t*, int64_t, int, const uint8_t*, int, uint8_t*,
                             cudaStream_t);
 cudaError_t pass_combine_launch(uint8_t*, const uint8_t*, int64_t, int, cudaStream_t);
@@ -969,6 +971,9 @@ struct Block {
     const uint8_t* ext = nullptr;      // ... or at `ext`, inside a registered file mapping (h == nullptr): DMA straight from the page cache
     std::shared_ptr<FileMap> ext_map;  // keeps that mapping alive
     uint8_t* data() const { return ext ? const_cast<uint8_t*>(ext) : h->as<uint8_t>() + data_off; }
+    // BGZF input inflated on the device (inflate.cu): data() holds zlen COMPRESSED bytes -- whole gzip members --, the
+    // member table (n_z x exb_bgzf_block) sits at h->p + ztab_off, and raw_len is the size of their text
+    int64_t zlen = 0, ztab_off = 0, n_z = 0, z_first = 0;
     int64_t raw_len = 0;
     int64_t raw_file_pos = 0;  // offset of the first raw byte in the (decompressed) file
     size_t file_idx = 0;
@@ -1063,6 +1068,39 @@ struct Reader {
     cudaStream_t st = nullptr, sc = nullptr, sd = nullptr;  // compute stream, H2D prefetch stream, D2H stream
     cudaEvent_t ev_staged = nullptr, ev_stage_free = nullptr;
     DBuf d_inb[2], d_stage;  // the chunk being scanned / the one being assembled; the prefetched raw block
+    // BGZF input: compressed members + their table on the device ([0] copied on the compute stream, [1] prefetched on
+    // the copy stream), the inflate kernel's ticket + first-error word, and whether an inflate has run since the last check
+    DBuf d_zin[2], d_zstate;
+    bool z_pending = false;
+    // compressed block -> device buffer `dz` (stream `s`): the members' bytes, then their table
+    static int64_t z_table_at(const Block& b) { return (b.zlen + 16 + 63) & ~(int64_t)63; }
+    bool z_copy_in(const Block& b, DBuf& dz, cudaStream_t s) {
+        const int64_t tab_bytes = b.n_z * (int64_t)sizeof(exb_bgzf_block);
+        if (!dz.need(z_table_at(b) + tab_bytes + 64)) return fail("out of device memory");
+        return cu(cudaMemcpyAsync(dz.p, b.data(), (size_t)b.zlen, cudaMemcpyHostToDevice, s), "H2D compressed") &&
+               cu(cudaMemcpyAsync(dz.as<uint8_t>() + z_table_at(b), b.h->as<uint8_t>() + b.ztab_off, (size_t)tab_bytes, cudaMemcpyHostToDevice, s), "H2D members");
+    }
+    // ... inflated into dst (stream `s`); the first-error word accumulates over the launches of a file
+    bool z_inflate(const Block& b, DBuf& dz, uint8_t* dst, cudaStream_t s) {
+        if (!d_zstate.p) {
+            if (!d_zstate.need(16) || !cu(cudaMemsetAsync(d_zstate.p, 0xFF, 16, s), "memset")) return fail(derr.empty() ? "out of device memory" : derr);
+        }
+        z_pending = true;
+        return cu(bgzf_inflate_launch(dz.as<uint8_t>(), reinterpret_cast<const exb_bgzf_block*>(dz.as<uint8_t>() + z_table_at(b)), b.n_z, dst,
+                                      d_zstate.as<unsigned int>(), 1, b.z_first, s),
+                  "bgzf_inflate");
+    }
+    // queue the read-back of the inflate kernel's error word with the chunk's other small results (slot 44) ...
+    bool z_queue_status() { return !z_pending || queue_small(44, d_zstate.p, 2); }
+    // ... and look at it once they are there
+    bool z_check(const std::string& fname) {
+        if (!z_pending) return true;
+        z_pending = false;
+        const unsigned int* w = reinterpret_cast<const unsigned int*>(small(44));
+        int64_t bad = -1;
+        if (exb_bgzf_status(w, &bad) == 0) return true;
+        return fail(std::string(exb_last_error()) + " of " + fname);
+    }
     uint8_t* d_cur = nullptr;  // = d_inb[cur].p while a chunk is processed
     DBuf d_ws, d_ws2, d_line, d_arr[4], d_lens, d_starts, d_valid, d_pass, d_selscratch, d_sel, d_lens2, d_starts2,
         d_valid2, d_off, d_cst, d_hdr_start, d_hdr_end, d_seq_off, d_gc_prefix, d_seq, d_err, d_info, d_qtmp, d_bad;
@@ -1194,7 +1232,7 @@ struct Reader {
     const int64_t* small(int slot) const { return reinterpret_cast<const int64_t*>(h_small) + slot; }
     void free_device() {  // device thread, at its end: buffers are freed on the device that owns them
         const double tf = now();
-        for (DBuf* b : {&d_inb[0], &d_inb[1], &d_stage, &d_ws, &d_ws2, &d_line, &d_arr[0], &d_arr[1], &d_arr[2], &d_arr[3], &d_lens, &d_starts,
+        for (DBuf* b : {&d_zin[0], &d_zin[1], &d_zstate, &d_inb[0], &d_inb[1], &d_stage, &d_ws, &d_ws2, &d_line, &d_arr[0], &d_arr[1], &d_arr[2], &d_arr[3], &d_lens, &d_starts,
                         &d_valid, &d_pass, &d_selscratch, &d_sel, &d_lens2, &d_starts2, &d_valid2, &d_off, &d_cst, &d_hdr_start, &d_hdr_end,
                         &d_seq_off, &d_gc_prefix, &d_seq, &d_err, &d_info, &d_qtmp, &d_bad, &outs[0].d_meta, &outs[0].d_data, &outs[1].d_meta,
                         &outs[1].d_data}) {
@@ -1269,7 +1307,30 @@ struct Reader {
             const uint8_t* map = nullptr;
             int64_t map_size = 0;
             int64_t pos = 0, end_pos = -1;  // plain files: [pos, end_pos) is what this reader parses
-            if (comp == 1) {
+            // BGZF (bgzip'ed) input: the compressed members go to the device as they are and are inflated there; the host
+            // only walks their headers.  Any other gzip file takes the streaming zlib decoder below.
+            bool bgzf = false;
+            int64_t upos = 0, z_seen = 0;  // text bytes / members handed on so far
+            std::vector<exb_bgzf_block> ztab;
+            if (comp == 1 && !(getenv("EXON_B200_BGZF") && atoi(getenv("EXON_B200_BGZF")) == 0)) {
+                fd = open(path.c_str(), O_RDONLY);
+                if (fd >= 0) {
+                    fmap = MapCache::get().open(fd, path.c_str());
+                    if (fmap && exb_bgzf_probe_host(fmap->p, fmap->size)) {
+                        bgzf = true;
+                        map = fmap->p;
+                        map_size = fmap->size;
+                        end_pos = map_size;
+                        ztab.resize(1 << 16);
+                    } else {
+                        fmap.reset();
+                        close(fd);
+                        fd = -1;
+                    }
+                }
+            }
+            if (bgzf) {
+            } else if (comp == 1) {
                 gz = gzopen(path.c_str(), "rb");
                 if (!gz) err = "could not open " + path;
                 else {
@@ -1331,6 +1392,49 @@ struct Reader {
                 const int64_t want = block_bytes.load() - (pos & 15);
                 Block b;
                 double t0 = now();
+                if (bgzf) {
+                    int64_t nb = 0, next = pos, outb = 0;
+                    if (exb_bgzf_index_host(map, map_size, pos, block_bytes.load(), ztab.data(), (int64_t)ztab.size(), &nb, &next, &outb) != 0) {
+                        err = std::string(exb_last_error()) + " in " + path;
+                        break;
+                    }
+                    const int64_t zlen = next - pos, tab_bytes = nb * (int64_t)sizeof(exb_bgzf_block);
+                    const int64_t zoff = direct ? 0 : 64, toff = direct ? 0 : ((zoff + zlen + 63) & ~(int64_t)63);
+                    b.h = pool->get(toff + tab_bytes + 64);
+                    if (!b.h) {
+                        err = "out of pinned host memory";
+                        break;
+                    }
+                    if (direct) {  // the compressed bytes are DMAed straight from the registered page cache
+                        b.ext = map + pos;
+                        b.ext_map = fmap;
+                    } else {
+                        b.data_off = zoff;
+                        IoPool::get().copy(b.h->as<uint8_t>() + zoff, map + pos, zlen);
+                    }
+                    memcpy(b.h->as<uint8_t>() + toff, ztab.data(), (size_t)tab_bytes);
+                    b.zlen = zlen;
+                    b.ztab_off = toff;
+                    b.n_z = nb;
+                    b.z_first = z_seen;
+                    z_seen += nb;
+                    b.file_idx = fi;
+                    b.raw_file_pos = upos;
+                    b.raw_len = outb;
+                    upos += outb;
+                    pos = next;
+                    eof = pos >= map_size;
+                    b.eof = eof;
+                    t_io_read += now() - t0;
+                    if (n_blocks == 0) t_first_block = now() - t_open;
+                    n_blocks++;
+                    HBuf* hb = b.h;
+                    if (!inq.push(std::move(b))) {
+                        pool->put(hb);
+                        break;
+                    }
+                    continue;
+                }
                 if (direct) {  // the mapping is pinned: the block IS the file's page cache, nothing to copy
                     const int64_t got_d = std::min<int64_t>(want, end_pos - pos);
                     b.ext = map + pos;
@@ -1844,7 +1948,9 @@ struct Reader {
                     return false;
                 // where the last complete record ends: fetched together with the result block (one sync)
                 if (!cu(fastq_chunk_info_launch(d_ws.p, d_line.as<uint32_t>(), d_info.as<int64_t>(), st), "chunk_info")) return false;
-                if (!queue_small(0, d_ws.p, (int)(sizeof(exb_scan_result) / 8)) || !queue_small(24, d_info.p, 2) || !wait_small()) return false;
+                if (!queue_small(0, d_ws.p, (int)(sizeof(exb_scan_result) / 8)) || !queue_small(24, d_info.p, 2) || !z_queue_status() || !wait_small())
+                    return false;
+                if (!z_check(fname)) return false;  // a corrupt gzip member: its text is garbage, report that and not what the parser made of it
                 memcpy(&res, small(0), sizeof(res));
                 res.err_pos = ~res.err_pos;  // the device keeps it inverted (see ScanResult)
                 info[0] = small(24)[0];
@@ -1904,7 +2010,8 @@ struct Reader {
                                    d_seq_off.as<int64_t>(), d_gc_prefix.as<int64_t>(), rec_cap, want_seq ? d_seq.as<uint8_t>() : nullptr,
                                    want_seq ? n + 64 : 0, d_ws.p, d_ws.cap, st)))
                 return false;
-            if (!queue_small(0, d_ws.p, (int)(sizeof(exb_scan_result) / 8)) || !wait_small()) return false;
+            if (!queue_small(0, d_ws.p, (int)(sizeof(exb_scan_result) / 8)) || !z_queue_status() || !wait_small()) return false;
+            if (!z_check(fname)) return false;
             memcpy(&res, small(0), sizeof(res));
             res.err_pos = ~res.err_pos;  // the device keeps it inverted (see ScanResult)
             if (!res.overflow) break;
@@ -1966,6 +2073,7 @@ struct Reader {
         int64_t carry_off = 0, carry_len = 0;  // the tail lives in d_inb[cur] at [carry_off, carry_off + carry_len)
         auto finish = [&](const std::string& err_in) {
             std::string err = err_in;
+            if (err.empty() && z_pending && !(z_queue_status() && wait_small() && z_check(files[std::min(cur_file, files.size() - 1)]))) err = derr;
             if (err.empty() && !flush_pending(0)) err = derr;
             cudaStreamSynchronize(sc);
             cudaStreamSynchronize(st);
@@ -2015,7 +2123,10 @@ struct Reader {
             uint8_t* dst = d_inb[nxt].as<uint8_t>();
             bool ok = true;
             if (carry_len) ok = cu(cudaMemcpyAsync(dst, d_inb[cur].as<uint8_t>() + carry_off, (size_t)carry_len, cudaMemcpyDeviceToDevice, st), "D2D tail");
-            if (ok && b.raw_len) {
+            if (ok && b.zlen) {  // BGZF: the members are inflated straight into the chunk
+                if (on_device) ok = cu(cudaStreamWaitEvent(st, ev_staged, 0), "wait") && z_inflate(b, d_zin[1], dst + carry_len, st) && cu(cudaEventRecord(ev_stage_free, st), "record");
+                else ok = z_copy_in(b, d_zin[0], st) && z_inflate(b, d_zin[0], dst + carry_len, st);
+            } else if (ok && b.raw_len) {
                 if (on_device) {
                     ok = cu(cudaStreamWaitEvent(st, ev_staged, 0), "wait") &&
                          cu(cudaMemcpyAsync(dst + carry_len, d_stage.p, (size_t)b.raw_len, cudaMemcpyDeviceToDevice, st), "D2D block") &&
@@ -2030,7 +2141,8 @@ struct Reader {
             {
                 uint8_t* blk = b.data();
                 uint8_t* base = nullptr;
-                if (carry_len == 0) {
+                if (b.zlen) {  // the host holds the compressed bytes only: strings are gathered on the device and copied back
+                } else if (carry_len == 0) {
                     base = blk;
                 } else if (b.ext) {  // the file is one contiguous piece of host memory: the carried tail sits right in front
                     if (b.ext - b.ext_map->p >= carry_len) base = blk - carry_len;
@@ -2054,7 +2166,12 @@ struct Reader {
                 Block nb;
                 if (inq.try_pop(nb)) {
                     staged_on_device = false;
-                    if (!nb.end && nb.raw_len > 0 && d_stage.need(nb.raw_len + 64)) {
+                    if (!nb.end && nb.zlen > 0) {
+                        if (cu(cudaStreamWaitEvent(sc, ev_stage_free, 0), "wait") && z_copy_in(nb, d_zin[1], sc) && cu(cudaEventRecord(ev_staged, sc), "record"))
+                            staged_on_device = true;
+                        else
+                            return finish(derr);
+                    } else if (!nb.end && nb.raw_len > 0 && d_stage.need(nb.raw_len + 64)) {
                         // the staging buffer is free once the previous staged block has been moved out of it
                         if (cu(cudaStreamWaitEvent(sc, ev_stage_free, 0), "wait") &&
                             cu(cudaMemcpyAsync(d_stage.p, nb.data(), (size_t)nb.raw_len, cudaMemcpyHostToDevice, sc), "H2D prefetch") &&
@@ -2178,10 +2295,12 @@ struct Reader {
             if (!ok) return finish(derr, 0);
         }
         if (!d_agg.need(64) || !cu(cudaMemsetAsync(d_agg.p, 0, 64, st), "memset")) return finish(derr.empty() ? "out of device memory" : derr, 0);
-        int k = 0;
-        const void* prev_ws = nullptr;
-        int64_t prev_tail = -1;  // which chunk buffer holds the previous range (its last 16 bytes are the next range's halo)
-        int64_t prev_end = 0;    // bytes of it
+        int kb = 0, kw = 0;              // chunk buffers alternate every block, scan workspaces every scan
+        const void* prev_ws = nullptr;   // workspace of the previous range of this file's chain
+        const uint8_t* prev_data = nullptr;  // previous chunk buffer: prev_data[0] is file offset prev_pos, prev_n bytes
+        int64_t prev_pos = 0, prev_n = 0;
+        int64_t tail = 0;  // bytes at the end of the previous buffer that were not scanned yet: a block of inflated BGZF members
+                           // ends anywhere, a chained range must end on a multiple of 16, so the last < 16 bytes wait for the next block
         while (!stopping) {
             Block b;
             double t0 = now();
@@ -2192,16 +2311,15 @@ struct Reader {
                 if (!b.error.empty()) return finish(b.error, 0);
                 break;
             }
-            if (b.raw_len == 0 && !prev_ws) {  // empty file
+            if (b.raw_len == 0 && !prev_ws && tail == 0 && !b.zlen) {  // empty file
                 pool->put(b.h);
                 continue;
             }
             t0 = now();
             NvtxRange nv("exb:count_chunk");
-            const int i = k & 1;
-            const int64_t n = b.raw_len, pos = b.raw_file_pos;
-            const int64_t ws_bytes = exb_scan_workspace_bytes(n + 64);
-            if (!d_chunk[i].need(n + 128) || !d_wsx[i].need(ws_bytes)) {
+            const int i = kb & 1;
+            const int64_t pos = b.raw_file_pos - tail, n = tail + b.raw_len;
+            if (!d_chunk[i].need(n + 128)) {
                 pool->put(b.h);
                 return finish("out of device memory", 0);
             }
@@ -2209,13 +2327,13 @@ struct Reader {
             // the 16 bytes in front of it are the end of the previous range (the scan looks one byte back for CR LF)
             uint8_t* data = d_chunk[i].as<uint8_t>() + 32 + (pos & 15);
             bool ok = true;
-            if (prev_ws && prev_tail >= 0) {
-                const int64_t h = std::min<int64_t>(16, prev_end);
-                ok = cu(cudaMemcpyAsync(data - h, d_chunk[prev_tail].as<uint8_t>() + 32 + ((pos - prev_end) & 15) + prev_end - h, (size_t)h,
-                                        cudaMemcpyDeviceToDevice, st),
-                        "D2D halo");
+            if (prev_data && (prev_ws || tail)) {  // halo + the unscanned tail, in one piece
+                const int64_t h = prev_ws ? 16 : 0;  // (a chain has scanned >= 16 bytes; they are in the previous buffer or in ITS halo)
+                if (h + tail > 0)
+                    ok = cu(cudaMemcpyAsync(data - h, prev_data + (pos - prev_pos) - h, (size_t)(h + tail), cudaMemcpyDeviceToDevice, st), "D2D halo");
             }
-            if (ok && n) ok = cu(cudaMemcpyAsync(data, b.data(), (size_t)n, cudaMemcpyHostToDevice, st), "H2D");
+            if (ok && b.zlen) ok = z_copy_in(b, d_zin[0], st) && z_inflate(b, d_zin[0], data + tail, st);
+            else if (ok && b.raw_len) ok = cu(cudaMemcpyAsync(data + tail, b.data(), (size_t)b.raw_len, cudaMemcpyHostToDevice, st), "H2D");
             cudaEvent_t ev = nullptr;
             if (!ev_pool.empty()) {
                 ev = ev_pool.back();
@@ -2229,29 +2347,40 @@ struct Reader {
                 return finish(derr, 0);
             }
             inflight.push_back(InFlight{b.h, b.ext_map, ev});
-            const uint8_t* base = data - pos;  // base[file offset] = that byte
-            if (!rc(exb_fastq_scan_filter(base, pos, pos + n, b.eof ? 1 : 0, prev_ws, preds.empty() ? nullptr : preds.data(), (int)preds.size(),
-                                          d_agg.as<int64_t>(), 1, d_wsx[i].p, d_wsx[i].cap, st)))
-                return finish(derr, 0);
-            prev_ws = d_wsx[i].p;
-            prev_tail = i;
-            prev_end = n;
-            bytes_done.fetch_add(n);
+            const int64_t scan_end = (b.eof || !b.zlen) ? pos + n : ((pos + n) & ~(int64_t)15);
+            if (scan_end > pos || b.eof) {
+                const int w = kw & 1;
+                if (!d_wsx[w].need(exb_scan_workspace_bytes(scan_end - pos + 64))) return finish("out of device memory", 0);
+                const uint8_t* base = data - pos;  // base[file offset] = that byte
+                if (!rc(exb_fastq_scan_filter(base, pos, scan_end, b.eof ? 1 : 0, prev_ws, preds.empty() ? nullptr : preds.data(), (int)preds.size(),
+                                              d_agg.as<int64_t>(), 1, d_wsx[w].p, d_wsx[w].cap, st)))
+                    return finish(derr, 0);
+                prev_ws = d_wsx[w].p;
+                kw++;
+            }
+            tail = pos + n - std::max(scan_end, pos);
+            prev_data = data;
+            prev_pos = pos;
+            prev_n = n;
+            bytes_done.fetch_add(b.raw_len);
             release_done(2);
-            k++;
+            kb++;
             if (b.eof) {  // the file (or shard) ends here: its line count and error marks, once per file
                 exb_scan_result res;
-                if (!queue_small(0, prev_ws, (int)(sizeof(exb_scan_result) / 8)) || !wait_small()) return finish(derr, 0);
+                if (!queue_small(0, prev_ws, (int)(sizeof(exb_scan_result) / 8)) || !z_queue_status() || !wait_small()) return finish(derr, 0);
+                const std::string& fname = files[b.file_idx];
+                if (!z_check(fname)) return finish(derr, 0);
                 memcpy(&res, small(0), sizeof(res));
                 res.err_pos = ~res.err_pos;
-                const std::string& fname = files[b.file_idx];
                 if (res.err_pos != ~0ull) return finish("invalid FASTQ record in " + fname + shard_note(), 0);
                 if (res.total_lines % 4 != 0) return finish("unexpected EOF in FASTQ record of " + fname + shard_note(), 0);
                 prev_ws = nullptr;  // the next file starts a new chain
-                prev_tail = -1;
+                prev_data = nullptr;
+                tail = 0;
             }
             t_dev_work += now() - t0;
         }
+        (void)prev_n;
         if (stopping) return finish("", 0);
         if (!queue_small(16, d_agg.p, 8) || !wait_small()) return finish(derr, 0);
         finish("", small(16)[0]);

@@ -570,3 +570,33 @@ class Writer:
         w, self._w = self._w, None
         check(lib().exb_writer_close(w, C.byref(rows), C.byref(nbytes)))
         return rows.value, nbytes.value
+
+
+def bgzf_index(image, pos=0, max_out_bytes=1 << 62, max_blocks=1 << 20):
+    """Member table of a BGZF file image (host bytes): exb_bgzf_index_host.  Returns (blocks, next_pos, out_bytes)."""
+    import numpy as np
+
+    arr = np.frombuffer(bytes(image), dtype=np.uint8)
+    cap = min(max_blocks, arr.size // 26 + 2)
+    tab = (_lib.BgzfBlock * cap)()
+    n, nxt, outb = C.c_int64(), C.c_int64(), C.c_int64()
+    check(lib().exb_bgzf_index_host(arr.ctypes.data, arr.size, pos, max_out_bytes, tab, cap, C.byref(n), C.byref(nxt), C.byref(outb)))
+    return tab, n.value, nxt.value, outb.value
+
+
+def bgzf_inflate(image, device="cuda", check_crc=True):
+    """Inflate a whole BGZF file image on the device (exb_bgzf_index_host + exb_bgzf_inflate + exb_bgzf_finish);
+    returns the text as a CUDA uint8 tensor.  Raises ExonError on a corrupt member."""
+    import numpy as np
+
+    tab, n, nxt, outb = bgzf_index(image)
+    if nxt != len(image):
+        raise _lib.ExonError(-3, "BGZF image has more members than the table holds")
+    d_in = to_device(image, device)
+    d_tab = torch.from_numpy(np.frombuffer(bytes(tab), dtype=np.uint8)[: max(n, 1) * 32].copy()).to(device)
+    d_out = alloc_input(outb, device)
+    d_state = torch.empty(16, dtype=torch.uint8, device=device)
+    check(lib().exb_bgzf_inflate(_ptr(d_in), _ptr(d_tab), n, _ptr(d_out), _ptr(d_state), 1 if check_crc else 0, _stream()))
+    bad = C.c_int64(-1)
+    check(lib().exb_bgzf_finish(_ptr(d_state), C.byref(bad), _stream()))
+    return d_out

@@ -635,6 +635,38 @@ EXB_API int exb_writer_append(exb_writer *writer, int64_t n_rows, const int64_t 
                               const uint8_t *const *data, const uint8_t *desc_valid);
 EXB_API int exb_writer_close(exb_writer *writer, int64_t *rows_written, int64_t *bytes_written);
 
+/* ---- BGZF (blocked gzip) input inflated on the device: SURVEY 8(f) rank 1 -------------------------------------
+ * Replaces, for bgzip'ed files, the streaming GzipDecoder the reference puts in front of its parser
+ * (rust/src/arrow_reader.rs:60-91, datafusion FileCompressionType::GZIP).  A BGZF file is a chain of independent gzip
+ * members of <= 64 KiB (SAM specification 4.1).  The host walks the member headers -- no decompression --, the
+ * compressed bytes go to the device as they are, one warp inflates one member (DEFLATE, RFC 1951) and checks its
+ * CRC-32.  The reader does this by itself for .gz inputs that are BGZF (exb_reader_open*); these are its pieces. */
+typedef struct exb_bgzf_block {
+    int64_t in_off;   /* offset of the member's DEFLATE payload, relative to the first byte handed to the device */
+    int64_t out_off;  /* offset of its text in the output                                                        */
+    uint32_t clen;    /* payload bytes                                                                           */
+    uint32_t isize;   /* text bytes (gzip ISIZE)                                                                 */
+    uint32_t crc32;   /* CRC-32 of the text (gzip trailer)                                                       */
+    uint32_t reserved;
+} exb_bgzf_block;
+/* 1 if `bytes` (HOST memory, the first n bytes of a file) start with a BGZF member header. */
+EXB_API int exb_bgzf_probe_host(const uint8_t *bytes, int64_t n);
+/* HOST: list the members that start at compressed offset `pos` of the n-byte compressed image `bytes` until their text
+ * would exceed max_out_bytes (at least one member is taken) or max_blocks are listed.  in_off is relative to `pos`.
+ * next_pos = compressed offset of the first member not listed; out_bytes = text bytes of the listed ones. */
+EXB_API int exb_bgzf_index_host(const uint8_t *bytes, int64_t n, int64_t pos, int64_t max_out_bytes,
+                                exb_bgzf_block *blocks, int64_t max_blocks, int64_t *n_blocks, int64_t *next_pos,
+                                int64_t *out_bytes);
+EXB_API int64_t exb_bgzf_scratch_bytes(void);
+/* DEVICE: inflate the listed members of d_in (16 readable bytes of slack behind the last payload) into d_out.
+ * Asynchronous on `stream`.  check_crc != 0 also verifies every member's CRC-32. */
+EXB_API int exb_bgzf_inflate(const uint8_t *d_in, const exb_bgzf_block *d_blocks, int64_t n_blocks, uint8_t *d_out,
+                             void *d_scratch, int check_crc, void *stream);
+/* Synchronises `stream`; EXB_ERR_FORMAT (+ the index of the first bad member) if a member was corrupt. */
+EXB_API int exb_bgzf_finish(const void *d_scratch, int64_t *bad_block, void *stream);
+/* The same test on a HOST copy of the 16 scratch bytes (callers that read them back with their other results). */
+EXB_API int exb_bgzf_status(const unsigned int *scratch_host, int64_t *bad_block);
+
 /* ---- host-buffer engine (end-to-end path): parse a FASTQ held in host memory ----
  * Streams `n` host bytes through pinned staging buffers with double-buffered
  * cudaMemcpyAsync, runs scan + filter per chunk, returns the aggregates

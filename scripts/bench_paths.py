@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--contigs", type=int, default=2400)
     ap.add_argument("--contig-len", type=int, default=500_000)
     ap.add_argument("--out", default="gpurun_out/paths.json")
-    ap.add_argument("--only", default="c2,c4,c3")
+    ap.add_argument("--only", default="c2,c4,c3,bgzf")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     rep = paths.Report()
@@ -36,6 +36,8 @@ def main():
         paths.c4_paths(rep, dev, args.ont_reads)
     if "c3" in only:
         paths.c3_paths(rep, dev, args.contigs, args.contig_len)
+    if "bgzf" in only:
+        paths.bgzf_paths(rep, dev)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
         json.dump({"peak_gbs": rep.peak, "rows": rep.rows}, f, indent=1)

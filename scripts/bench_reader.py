@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--dir", default="/dev/shm")
     ap.add_argument("--out", default="gpurun_out/reader.json")
     ap.add_argument("--repeat", type=int, default=5)
+    ap.add_argument("--cases", default="plain,bgzf")
     args = ap.parse_args()
 
     rows = []
@@ -71,7 +72,7 @@ def main():
         ("read_fasta id, gc_content(sequence) [computed]", fa, "fasta", 0x1, None, False, ((_lib.C_GC_CONTENT, 0),)),
         ("read_fasta all 3 columns", fa, "fasta", 0x7, None, False, ()),
     ]
-    for name, path, fmt, mask, filt, cnt, comp in cases:
+    for name, path, fmt, mask, filt, cnt, comp in (cases if "plain" in args.cases else []):
         size = os.path.getsize(path)
         # two I/O paths: "copy" = what the FIRST scan of a file does (page cache -> pinned blocks -> DMA); "registered" = every
         # later scan of a memory-backed file (its page cache was pinned in place by cudaHostRegister after the first scan)
@@ -92,6 +93,42 @@ def main():
             rows.append({"case": name, "io": io, "bytes": size, "rows": n, "best_ms": best * 1e3, "median_ms": med * 1e3, "best_gbs": size / 1e9 / best,
                          "median_gbs": size / 1e9 / med, "all_ms": [t * 1e3 for t in times]})
             print("%-68s %-10s best %7.1f ms %6.2f GB/s | median %7.1f ms %6.2f GB/s  rows %d" % (name, io, best * 1e3, size / 1e9 / best, med * 1e3, size / 1e9 / med, n), flush=True)
+    # ---- bgzip'ed FASTQ: the members cross PCIe compressed and are inflated on the device; the streaming
+    # zlib decoder (EXON_B200_BGZF=0: what every other gzip file takes, and what the reference does) beside it
+    from tools import paths as P
+    fqz = os.path.join(args.dir, "exb_bench_bgzf.fastq.gz")
+    text_bytes = os.path.getsize(fq)
+    if not os.path.exists(fqz):
+        with open(fq, "rb") as f:
+            img = P.bgzf_image(f.read())
+        with open(fqz, "wb") as f:
+            f.write(img)
+        del img
+    zbytes = os.path.getsize(fqz)
+    zcases = [
+        ("read_fastq(bgzf) COUNT(*) WHERE mean quality > 30", 0, "mean_quality(quality_scores)>30", True, ()),
+        ("read_fastq(bgzf) all 4 columns", 0xF, None, False, ()),
+        ("read_fastq(bgzf) gc_content(sequence) [computed]", 0, None, False, ((_lib.C_GC_CONTENT, 0),)),
+    ]
+    for name, mask, filt, cnt, comp in (zcases if "bgzf" in args.cases else []):
+        for mode, reps in (("device inflate", args.repeat), ("zlib stream", 1)):
+            if mode == "zlib stream":
+                if not cnt:
+                    continue
+                os.environ["EXON_B200_BGZF"] = "0"
+            else:
+                os.environ.pop("EXON_B200_BGZF", None)
+            times = []
+            for _ in range(reps + (1 if mode == "device inflate" else 0)):
+                dt, n = run(fqz, "fastq", mask, filt, cnt, comp)
+                times.append(dt)
+            times = times[1:] if len(times) > 1 else times
+            best = min(times)
+            rows.append({"case": name, "io": mode, "bytes": zbytes, "text_bytes": text_bytes, "rows": n, "best_ms": best * 1e3,
+                         "best_gbs": zbytes / 1e9 / best, "best_text_gbs": text_bytes / 1e9 / best, "all_ms": [t * 1e3 for t in times]})
+            print("%-68s %-14s best %8.1f ms %6.2f GB/s of file bytes = %6.2f GB/s of text  rows %d" %
+                  (name, mode, best * 1e3, zbytes / 1e9 / best, text_bytes / 1e9 / best, n), flush=True)
+    os.environ.pop("EXON_B200_BGZF", None)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(rows, f, indent=1)

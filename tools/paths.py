@@ -198,3 +198,52 @@ def c3_paths(rep, dev, contigs, contig_len, iters=10):
     rep.add("C3 writer: 3 columns -> FASTA file image wrapped at 60 (exb_fasta_format)", seq_bytes + n, med, best, n, "includes the scratch / image allocations and 1 host sync")
     del tab, cols, fs, fs2, buf
     torch.cuda.empty_cache()
+
+
+def bgzf_image(text, level=6, block=65280, threads=16):
+    """BGZF file image of `text` (what bgzip writes: members of 65280 text bytes, zlib level 6), compressed on `threads`
+    host threads (zlib releases the GIL).  Tooling: benchmark and test input."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    mv = memoryview(text)
+
+    def member(lo):
+        piece = mv[lo:lo + block]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        z = c.compress(piece) + c.flush()
+        hdr = b"\x1f\x8b\x08\x04\0\0\0\0\x00\xff\x06\x00BC\x02\x00" + (len(z) + 25).to_bytes(2, "little")
+        return hdr + z + zlib.crc32(piece).to_bytes(4, "little") + len(piece).to_bytes(4, "little")
+
+    with ThreadPoolExecutor(threads) as ex:
+        return b"".join(ex.map(member, range(0, len(text), block)))
+
+
+def bgzf_paths(rep, dev, reads=400_000, copies=8, iters=5):
+    """bgzip'ed FASTQ inflated on the device (exb_bgzf_inflate, CRC-32 checked), `copies` x `reads`
+    Illumina reads so that text + compressed bytes exceed L2."""
+    import ctypes as C
+    import numpy as np
+
+    text = synth.gen_host(synth.gen_params("illumina", reads, seed=20)).tobytes()
+    img = bgzf_image(text) * copies
+    tab, n, nxt, outb = D.bgzf_index(img)
+    assert nxt == len(img) and outb == len(text) * copies
+    d_in = D.to_device(img, dev)
+    d_tab = torch.from_numpy(np.frombuffer(bytes(tab), dtype=np.uint8)[: n * 32].copy()).to(dev)
+    d_out = D.alloc_input(outb, dev)
+    d_state = torch.empty(16, dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+
+    def run(crc):
+        _lib.check(L.exb_bgzf_inflate(D._ptr(d_in), D._ptr(d_tab), n, D._ptr(d_out), D._ptr(d_state), crc, D._stream()))
+
+    for crc, nm in ((1, "CRC-32 checked"), (0, "no CRC")):
+        med, best = timeit(lambda: run(crc), iters=iters)
+        _lib.check(L.exb_bgzf_finish(D._ptr(d_state), None, D._stream()))
+        rep.add("BGZF FASTQ inflated on the device (exb_bgzf_inflate, %s)" % nm, len(img) + outb, med, best, len(img),
+                "%d members, %.2f GB text from %.2f GB (ratio %.2f); text GB/s = %.1f" % (n, outb / 1e9, len(img) / 1e9, outb / len(img), outb / med / 1e6))
+    got = d_out[: len(text)].cpu().numpy().tobytes()
+    assert got == text
+    del d_in, d_out, d_tab
+    torch.cuda.empty_cache()
