@@ -15,6 +15,7 @@
 // 64 KiB window stays cached).  The kernel is bound by the serial symbol decode (instruction issue), not by DRAM.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/exon_b200.h"
@@ -27,15 +28,19 @@ int cuda_fail(cudaError_t e, const char* what);
 constexpr int IFL_WARPS = 8;  // warps per CTA: 8 x 6 KB of tables
 static_assert(sizeof(exb_bgzf_block) == 32, "exb_bgzf_block layout");
 
-__global__ void __launch_bounds__(IFL_WARPS * 32) bgzf_inflate_kernel(const uint8_t* __restrict__ in, const exb_bgzf_block* __restrict__ blocks, int n_blocks,
+__global__ void __launch_bounds__(IFL_WARPS * 32, 4) bgzf_inflate_kernel(const uint8_t* __restrict__ in, const exb_bgzf_block* __restrict__ blocks, int n_blocks,
                                                                        uint8_t* __restrict__ out, unsigned int* __restrict__ state, int check_crc, long long block_base) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ uint32_t s_crc[256];
-    ifl::Tables* tabs = reinterpret_cast<ifl::Tables*>(s_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // lane and the warp's table pointer are computed ONCE: left to itself the compiler rebuilds both from %tid inside the
+    // symbol loop (S2R + IMAD, 11 % of the instructions of the first version)
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    asm volatile("" : "+r"(lane));
+    ifl::Tables* tabs = reinterpret_cast<ifl::Tables*>(s_raw) + warp;
+    asm volatile("" : "+l"(tabs));
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = ifl::crc_table_entry((uint32_t)i);
     __syncthreads();
-    ifl::Tables& T = tabs[warp];
+    ifl::Tables& T = *tabs;
     for (;;) {
         unsigned int b = 0;
         if (lane == 0) b = atomicAdd(&state[0], 1u);
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(IFL_WARPS * 32) bgzf_inflate_kernel(const uint
         if (b >= (unsigned)n_blocks) break;
         const exb_bgzf_block blk = blocks[b];
         uint8_t* dst = out + blk.out_off;
-        int err = ifl::inflate_block(in + blk.in_off, (int)blk.clen, dst, (int)blk.isize, T, lane, 32);
+        int err = ifl::inflate_block<32>(in + blk.in_off, (int)blk.clen, dst, (int)blk.isize, T, lane);
         if (err == ifl::OK && check_crc) {
             __syncwarp();  // the block's bytes were stored by all lanes
             const int n = (int)blk.isize;

@@ -50,7 +50,8 @@ enum Err {
     E_CRC = 9,         // CRC-32 of the output differs from the trailer
 };
 
-// entry: bits 0-4 code length, 5-7 kind, 8-11 extra bits, 16-31 literal byte | base length | base distance | symbol (M_CL)
+// entry: bits 0-4 code length, 5-7 kind, 8-11 extra bits, 16-30 literal byte | base length | base distance | symbol (M_CL);
+// bit 31 = literal of the literal / length code (the decode loop's first test is the sign)
 struct Tables {
     uint32_t lit[1 << LB];
     uint32_t dist[1 << DB];     // (the code-length code's table lives in its first 1 << CLB entries while a header is read)
@@ -69,7 +70,7 @@ IFL_HD uint32_t make_entry(int mode, int sym, int len) {
         const uint32_t base = sym < 4 ? 1u + sym : 1u + ((2u + (sym & 1)) << xb);
         return (uint32_t)len | (K_BASE << 5) | ((uint32_t)xb << 8) | (base << 16);
     }
-    if (sym < 256) return (uint32_t)len | (K_LIT << 5) | ((uint32_t)sym << 16);
+    if (sym < 256) return 0x80000000u | (uint32_t)len | (K_LIT << 5) | ((uint32_t)sym << 16);
     if (sym == 256) return (uint32_t)len | (K_EOB << 5);
     if (sym >= 286) return 0u;
     const int idx = sym - 257;
@@ -189,7 +190,9 @@ struct BitReader {
 
 // Inflate one raw DEFLATE stream of `clen` bytes at `in` into exactly `isize` bytes at `out`.  The caller guarantees 16
 // readable bytes behind in + clen (the reader loads whole words ahead).  Returns an Err.
-IFL_HD int inflate_block(const uint8_t* in, int clen, uint8_t* out, int isize, Tables& T, int lane, int lanes) {
+template <int LANES>
+IFL_HD int inflate_block(const uint8_t* in, int clen, uint8_t* out, int isize, Tables& T, int lane) {
+    constexpr int lanes = LANES;
     BitReader br;
     br.init(in, in + clen + 16);
     int pos = 0;
@@ -282,24 +285,34 @@ IFL_HD int inflate_block(const uint8_t* in, int clen, uint8_t* out, int isize, T
                 if (err == OK) err = build_table<DB>(T.lens + hlit, hdist, T.dist, T.dist_sorted, T.dist_count, M_DIST, lane, lanes);
                 if (err != OK) return err;
             }
-            // ---- the symbols of this block
+            // ---- the symbols of this block.  The kernel is bound by instruction issue (profiles/round2_inflate_v1_ncu.txt:
+            // 72 % issue utilisation, 27 warp instructions per byte of text), so the loop is written for few instructions:
+            // a literal is recognised by the entry's sign, stored by EVERY lane (same byte, same address: one transaction
+            // and no divergent branch; each lane then reads its own store back without a barrier), and bounds are tested
+            // once per symbol.
+            const uint32_t* __restrict__ lit = T.lit;
+            const uint32_t* __restrict__ dtab = T.dist;
             for (;;) {
                 v = br.peek();
-                uint32_t e = T.lit[v & ((1u << LB) - 1u)];
-                if ((e & 0xE0u) == 0u) {
-                    e = decode_slow(v, T.lit_sorted, T.lit_count, M_LITLEN);
-                    if (e == 0u) return E_CODE;
-                }
-                const int nb = (int)(e & 31u);
-                const int kind = (int)((e >> 5) & 7u);
-                if (kind == K_LIT) {
+                uint32_t e = lit[v & ((1u << LB) - 1u)];
+                if ((int32_t)e < 0) {  // literal
                     if (pos >= isize) return E_OUTPUT;
-                    if (lane == 0) out[pos] = (uint8_t)(e >> 16);
-                    pos++;
-                    br.skip(nb);
+                    out[pos++] = (uint8_t)(e >> 16);
+                    br.skip((int)(e & 31u));
                     continue;
                 }
-                if (kind == K_EOB) {
+                if ((e & 0xE0u) == 0u) {  // a code word longer than the table's index
+                    e = decode_slow(v, T.lit_sorted, T.lit_count, M_LITLEN);
+                    if (e == 0u) return E_CODE;
+                    if ((int32_t)e < 0) {
+                        if (pos >= isize) return E_OUTPUT;
+                        out[pos++] = (uint8_t)(e >> 16);
+                        br.skip((int)(e & 31u));
+                        continue;
+                    }
+                }
+                const int nb = (int)(e & 31u);
+                if (((e >> 5) & 7u) == K_EOB) {
                     br.skip(nb);
                     break;
                 }
@@ -307,7 +320,7 @@ IFL_HD int inflate_block(const uint8_t* in, int clen, uint8_t* out, int isize, T
                 const int len = (int)(e >> 16) + (int)((v >> nb) & ((1u << xb) - 1u));
                 br.skip(nb + xb);
                 v = br.peek();
-                e = T.dist[v & ((1u << DB) - 1u)];
+                e = dtab[v & ((1u << DB) - 1u)];
                 if ((e & 0xE0u) == 0u) {
                     e = decode_slow(v, T.dist_sorted, T.dist_count, M_DIST);
                     if (e == 0u) return E_CODE;
@@ -320,13 +333,18 @@ IFL_HD int inflate_block(const uint8_t* in, int clen, uint8_t* out, int isize, T
                 if (pos + len > isize) return E_OUTPUT;
                 IFL_SYNC();  // the bytes the match refers to were stored by other lanes
                 const uint8_t* from = out + pos - dist;
+                uint8_t* to = out + pos;
                 if (dist >= len) {
-                    for (int i = lane; i < len; i += lanes) out[pos + i] = from[i];
+                    if (LANES == 32 && len <= 32) {
+                        if (lane < len) to[lane] = from[lane];
+                    } else {
+                        for (int i = lane; i < len; i += lanes) to[i] = from[i];
+                    }
                 } else if (dist == 1) {
                     const uint8_t b = from[0];
-                    for (int i = lane; i < len; i += lanes) out[pos + i] = b;
+                    for (int i = lane; i < len; i += lanes) to[i] = b;
                 } else {  // the match overlaps its own output: byte i repeats byte i mod dist of what was there before
-                    for (int i = lane; i < len; i += lanes) out[pos + i] = from[i % dist];
+                    for (int i = lane; i < len; i += lanes) to[i] = from[i % dist];
                 }
                 pos += len;
             }

@@ -1394,7 +1394,9 @@ struct Reader {
                 double t0 = now();
                 if (bgzf) {
                     int64_t nb = 0, next = pos, outb = 0;
-                    if (exb_bgzf_index_host(map, map_size, pos, block_bytes.load(), ztab.data(), (int64_t)ztab.size(), &nb, &next, &outb) != 0) {
+                    // (text per block: 4 x the plain block size -- one warp inflates one member, and a launch wants thousands of them)
+                    static const int64_t zmul = getenv("EXON_B200_BGZF_BLOCK_MUL") ? std::max(1, atoi(getenv("EXON_B200_BGZF_BLOCK_MUL"))) : 4;
+                    if (exb_bgzf_index_host(map, map_size, pos, block_bytes.load() * zmul, ztab.data(), (int64_t)ztab.size(), &nb, &next, &outb) != 0) {
                         err = std::string(exb_last_error()) + " in " + path;
                         break;
                     }

@@ -16,7 +16,7 @@ int ifl_host_inflate(const uint8_t* in, int clen, uint8_t* out, int isize, int m
     uint8_t* p = buf + 16 + (misalign & 3);
     memcpy(p, in, (size_t)clen);
     ifl::Tables* T = new ifl::Tables();
-    const int rc = ifl::inflate_block(p, clen, out, isize, *T, 0, 1);
+    const int rc = ifl::inflate_block<1>(p, clen, out, isize, *T, 0);
     delete T;
     free(buf);
     return rc;
