@@ -2264,6 +2264,7 @@ struct Reader {
             std::shared_ptr<FileMap> map;  //  which this keeps alive until the copy is done)
             cudaEvent_t ev;
         };
+        cudaEvent_t ev_zc = nullptr, ev_zf[2] = {nullptr, nullptr};  // BGZF: members copied / staging buffer free again
         std::deque<InFlight> inflight;  // pinned blocks whose H2D copy may still be running
         std::vector<cudaEvent_t> ev_pool;
         auto release_done = [&](size_t keep) {
@@ -2278,6 +2279,9 @@ struct Reader {
             cudaStreamSynchronize(st);
             release_done(0);
             for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+            cudaStreamSynchronize(sc);
+            for (cudaEvent_t e : {ev_zc, ev_zf[0], ev_zf[1]})
+                if (e) cudaEventDestroy(e);
             for (DBuf* b : {&d_chunk[0], &d_chunk[1], &d_wsx[0], &d_wsx[1], &d_agg}) b->release();
             free_device();
             if (err.empty() && count > 0) {
@@ -2334,7 +2338,17 @@ struct Reader {
                 if (h + tail > 0)
                     ok = cu(cudaMemcpyAsync(data - h, prev_data + (pos - prev_pos) - h, (size_t)(h + tail), cudaMemcpyDeviceToDevice, st), "D2D halo");
             }
-            if (ok && b.zlen) ok = z_copy_in(b, d_zin[0], st) && z_inflate(b, d_zin[0], data + tail, st);
+            if (ok && b.zlen) {
+                // the compressed members cross PCIe on the copy stream while the compute stream still inflates the block before:
+                // two staging buffers, an event per buffer says when its last reader (the inflate kernel) is done
+                const int z = kb & 1;
+                if (!ev_zc) {
+                    ok = cu(cudaEventCreateWithFlags(&ev_zc, cudaEventDisableTiming), "event") && cu(cudaEventCreateWithFlags(&ev_zf[0], cudaEventDisableTiming), "event") &&
+                         cu(cudaEventCreateWithFlags(&ev_zf[1], cudaEventDisableTiming), "event");
+                }
+                ok = ok && cu(cudaStreamWaitEvent(sc, ev_zf[z], 0), "wait") && z_copy_in(b, d_zin[z], sc) && cu(cudaEventRecord(ev_zc, sc), "record") &&
+                     cu(cudaStreamWaitEvent(st, ev_zc, 0), "wait") && z_inflate(b, d_zin[z], data + tail, st) && cu(cudaEventRecord(ev_zf[z], st), "record");
+            }
             else if (ok && b.raw_len) ok = cu(cudaMemcpyAsync(data + tail, b.data(), (size_t)b.raw_len, cudaMemcpyHostToDevice, st), "H2D");
             cudaEvent_t ev = nullptr;
             if (!ev_pool.empty()) {

@@ -92,6 +92,43 @@ def main():
             gbs = size / (ms * 1e-3) / 1e9
             rows.append({"extension": label, "query": name, "file_bytes": size, "ms": ms, "GB/s": gbs, "result": r["rows"][0][0]})
             print("%-8s %-60s %9.1f ms  %7.2f GB/s  (%.2f GB file)  -> %s" % (label, name, ms, gbs, size / 1e9, r["rows"][0][0]), flush=True)
+    # ---- bgzip'ed FASTQ: inflated on the device by PRODUCT and, through new_reader, for the reference's glue;
+    # EXON_B200_BGZF=0 = the streaming zlib decoder (the reference's own arrangement) on a smaller file
+    from tools import paths as P
+    bz = os.path.join(args.dir, "exb_duck_big.fastq.gz")
+    with open(big, "rb") as f:
+        text = f.read()
+    with open(bz, "wb") as f:
+        f.write(P.bgzf_image(text))
+    sz = os.path.join(args.dir, "exb_duck_small.fastq.gz")
+    with open(small, "rb") as f:
+        stext = f.read()
+    with open(sz, "wb") as f:
+        f.write(P.bgzf_image(stext))
+    for label, ext, path, tbytes, env in (("PRODUCT", PRODUCT, bz, len(text), None), ("PRODUCT, zlib stream (EXON_B200_BGZF=0)", PRODUCT, sz, len(stext), "0")):
+        for name, q in queries[:2] + queries[6:7]:
+            if env is not None:
+                os.environ["EXON_B200_BGZF"] = env
+            try:
+                res = run(ext, [q % path, q % path, q % path], threads=args.threads or None)
+            except Exception as e:
+                print("%-8s %-44s FAILED %s" % (label, name, str(e)[:200]), flush=True)
+                continue
+            finally:
+                os.environ.pop("EXON_B200_BGZF", None)
+            r = min((x for x in res[1:] if x.get("ok")), key=lambda x: x["ms"], default=res[-1])
+            if not r.get("ok"):
+                print("%-8s %-44s ERROR %s" % (label, name, r.get("error", "")[:200]), flush=True)
+                continue
+            ms = r["ms"]
+            size = os.path.getsize(path)
+            rows.append({"extension": label, "query": "bgzf: " + name, "file_bytes": size, "text_bytes": tbytes, "ms": ms, "GB/s": size / ms / 1e6,
+                         "text GB/s": tbytes / ms / 1e6, "result": r["rows"][0][0]})
+            print("%-8s bgzf: %-54s %9.1f ms  %7.2f GB/s of file bytes = %7.2f GB/s of text (%.2f GB file)  -> %s" %
+                  (label, name[:54], ms, size / ms / 1e6, tbytes / ms / 1e6, size / 1e9, r["rows"][0][0]), flush=True)
+    del text, stext
+    os.unlink(bz)
+    os.unlink(sz)
     os.unlink(big)
     os.unlink(small)
     os.unlink(fasta)

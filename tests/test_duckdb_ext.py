@@ -607,3 +607,28 @@ def test_copy_filters_and_rewrites_a_larger_file(tmp_path):
         assert int(scalar(r[0])) == len(keep) and 0 < len(keep) < 6000
         want = O.format_fastq([x[0] for x in keep], [x[1] for x in keep], [x[2] for x in keep], [x[3] for x in keep])
         assert out.read_bytes() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ext", [PRODUCT, REFGLUE], ids=["product", "refglue"])
+def test_bgzf_input_through_sql(cuda_device, tmp_path, ext):
+    """bgzip'ed FASTQ through DuckDB: the members are inflated on the device behind read_fastq, the
+    compression parameter and the replacement scan -- same rows as the plain file, also through the reference's own glue."""
+    from oracle import oracle as O
+    bgzf_bytes = util.bgzf_bytes
+    text, _ = util.random_fastq(17, 6000, min_len=10, max_len=150, tricky=False)
+    path = _write(tmp_path, "b.fastq.gz", bgzf_bytes(text, sizes=[65280, 3, 40000]))
+    other = _write(tmp_path, "b.dat", bgzf_bytes(text, block=30000))
+    ref = O.parse_fastq(text)
+    want = [tuple(None if v is None else v.decode() for v in row) for row in ref.rows()]
+    mq = sum(O.mean_quality_pass(q, ">", 50.0) for q in ref.strings("quality_scores"))
+    res = run_sql(ext, [
+        "SELECT count(*) FROM read_fastq('%s')" % path,
+        "SELECT * FROM read_fastq('%s')" % path,
+        "SELECT count(*) FROM read_fastq('%s', compression='gzip')" % other,
+        "SELECT count(*) FROM '%s' WHERE list_avg(quality_score_string_to_list(quality_scores)) > 50" % path,
+    ], env={"EXON_B200_CHUNK_BYTES": str(150_000)})
+    assert rows(res[0]) == [[str(ref.n)]]
+    assert [tuple(r) for r in rows(res[1])] == want
+    assert rows(res[2]) == [[str(ref.n)]]
+    assert rows(res[3]) == [[str(mq)]]

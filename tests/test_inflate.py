@@ -29,30 +29,7 @@ def _host(small=False):
     return lib
 
 
-def raw_deflate(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8):
-    c = zlib.compressobj(level, zlib.DEFLATED, -15, mem, strategy)
-    return c.compress(data) + c.flush()
-
-
-def bgzf_bytes(data, block=65280, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, eof_marker=True, sizes=None):
-    """A BGZF file image of `data` (SAM specification 4.1): what bgzip writes."""
-    out = []
-    pos = 0
-    k = 0
-    while pos < len(data) or (pos == 0 and not out):
-        n = sizes[k % len(sizes)] if sizes else block
-        k += 1
-        piece = data[pos:pos + n]
-        pos += len(piece)
-        z = raw_deflate(piece, level, strategy)
-        assert len(z) + 26 <= 65536
-        hdr = b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + (6).to_bytes(2, "little") + b"BC" + (2).to_bytes(2, "little") + (len(z) + 25).to_bytes(2, "little")
-        out.append(hdr + z + zlib.crc32(piece).to_bytes(4, "little") + len(piece).to_bytes(4, "little"))
-        if not data:
-            break
-    if eof_marker:
-        out.append(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
-    return b"".join(out)
+raw_deflate, bgzf_bytes = util.raw_deflate, util.bgzf_bytes
 
 
 def _payloads():
