@@ -547,6 +547,7 @@ def main():
         torch.cuda.empty_cache()
         P.c3_paths(rep, dev, int(os.environ.get("EXB_BENCH_CONTIGS", "6000")), 500_000, iters=5)   # C3: 3 Gbp wrapped at 60
         P.c4_paths(rep, dev, int(os.environ.get("EXB_BENCH_ONT_READS", "200000")), iters=3)       # C4: 200 k ONT reads, ~12 GB
+        P.bgzf_paths(rep, dev, iters=3)                                                           # bgzip'ed FASTQ inflated on the device
         path_rows = rep.rows
 
     # ---- C5 (BASELINE configs[4]): ~100 GB of the same FASTQ as ONE file cut into byte ranges over the N GPUs (cuts inside

@@ -9,7 +9,7 @@
 // into the buffer the scan kernels read, then checks the block's CRC-32:
 //
 //   bgzf_inflate_kernel   grid = resident warps of the machine, blocks handed out by ticket (their cost varies);
-//                         per warp 6 KB of shared memory (two Huffman index tables + canonical arrays)
+//                         per warp 4 KB of shared memory (two Huffman index tables + canonical arrays)
 //
 // HBM traffic: compressed bytes once in, text once out (+ the match copies and the CRC pass, which hit L1 / L2: a block's
 // 64 KiB window stays cached).  The kernel is bound by the serial symbol decode (instruction issue), not by DRAM.
@@ -25,10 +25,13 @@ namespace exb {
 int set_err(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 
-constexpr int IFL_WARPS = 8;  // warps per CTA: 8 x 6 KB of tables
+constexpr int IFL_WARPS = 8;  // warps per CTA: 8 x 4 KB of tables
+#ifndef IFL_MINB
+#define IFL_MINB 6            // resident CTAs per SM the kernel is compiled for (registers) and launched as (grid)
+#endif
 static_assert(sizeof(exb_bgzf_block) == 32, "exb_bgzf_block layout");
 
-__global__ void __launch_bounds__(IFL_WARPS * 32, 4) bgzf_inflate_kernel(const uint8_t* __restrict__ in, const exb_bgzf_block* __restrict__ blocks, int n_blocks,
+__global__ void __launch_bounds__(IFL_WARPS * 32, IFL_MINB) bgzf_inflate_kernel(const uint8_t* __restrict__ in, const exb_bgzf_block* __restrict__ blocks, int n_blocks,
                                                                        uint8_t* __restrict__ out, unsigned int* __restrict__ state, int check_crc, long long block_base) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     __shared__ uint32_t s_crc[256];
@@ -36,8 +39,8 @@ __global__ void __launch_bounds__(IFL_WARPS * 32, 4) bgzf_inflate_kernel(const u
     // symbol loop (S2R + IMAD, 11 % of the instructions of the first version)
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     asm volatile("" : "+r"(lane));
+    asm volatile("" : "+r"(warp));  // (the pointer itself stays a shared-memory pointer: LDS, not generic LD)
     ifl::Tables* tabs = reinterpret_cast<ifl::Tables*>(s_raw) + warp;
-    asm volatile("" : "+l"(tabs));
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = ifl::crc_table_entry((uint32_t)i);
     __syncthreads();
     ifl::Tables& T = *tabs;
@@ -91,7 +94,7 @@ cudaError_t bgzf_inflate_launch(const uint8_t* d_in, const exb_bgzf_block* d_blo
         attr_set[dev] = true;
     }
     int64_t ctas = (n_blocks + IFL_WARPS - 1) / IFL_WARPS;
-    const int64_t machine = 148 * 4;  // 4 CTAs of 8 warps per SM (49 KB of shared memory each)
+    const int64_t machine = 148 * IFL_MINB;  // resident CTAs of 8 warps (33 KB of shared memory each)
     if (ctas > machine) ctas = machine;
     bgzf_inflate_kernel<<<(unsigned)ctas, IFL_WARPS * 32, dyn, st>>>(d_in, d_blocks, (int)n_blocks, d_out, d_state, check_crc, (long long)block_base);
     return cudaGetLastError();

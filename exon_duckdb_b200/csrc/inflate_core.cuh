@@ -29,8 +29,8 @@
 namespace ifl {
 
 #ifndef IFL_LB  // (the host test build also compiles a variant with tiny tables: every code word takes the bit-by-bit path)
-#define IFL_LB 10
-#define IFL_DB 8
+#define IFL_LB 9   // 9 + 8 bits: 4 KB of tables per warp, 6 CTAs of 8 warps per SM.  Measured against 10 + 8 bits at 4 CTAs
+#define IFL_DB 8   // (31.5 ms per 1.12 GB of text) and 9 + 7 bits at 8 CTAs (28.7 ms): 28.2 ms (profiles/round2_inflate_ab.txt)
 #endif
 constexpr int LB = IFL_LB;  // index bits of the literal / length table
 constexpr int DB = IFL_DB;  // index bits of the distance table
