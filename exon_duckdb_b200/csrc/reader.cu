@@ -778,9 +778,27 @@ struct FileMap {
         static std::atomic<int64_t> b{0};
         return b;
     }
+    // WHEN the mapping is registered matters: cudaHostRegister holds the driver's locks and the mapping's page locks for
+    // as long as it pins pages (~0.1 s per GB), and a scan that runs meanwhile waits for it.  Measured on a 2.8 GB file
+    // (profiles/round2_register_sequence.txt): registered right after the first scan's IO stage, that scan took 397
+    // instead of 77 ms; registered in 64 MiB pieces regardless of activity, the next three scans took 433 / 257 / 126
+    // instead of 65 ms; in pieces between scans, single scans stalled for up to 2 s.  So the registration is ONE call, made
+    // once no reader of this process has been active for 50 ms -- the time between two statements of a session.  Under
+    // back-to-back scans it does not get its turn and the copy path stays; a scan that starts while it runs waits for
+    // it once.  (EXON_B200_REGISTER_PIECE_MB registers in pieces instead -- tests; a DMA never spans two pieces.)
+    static std::atomic<int>& io_active() {
+        static std::atomic<int> n{0};
+        return n;
+    }
+    int64_t piece = 1ll << 62;  // set when the registration starts, fixed from then on (default: the whole mapping is one piece)
+    int64_t pieces_done = 0;   // (registration thread only, then the destructor)
+    void unregister_pieces() {
+        for (int64_t k = 0; k < pieces_done; k++) cudaHostUnregister(const_cast<uint8_t*>(p) + k * piece);
+        pieces_done = 0;
+    }
     ~FileMap() {
         if (p && reg.load() == 2) {
-            cudaHostUnregister(const_cast<uint8_t*>(p));
+            unregister_pieces();
             registered_bytes().fetch_sub(size);
         }
         if (p) munmap(const_cast<uint8_t*>(p), (size_t)size);
@@ -798,17 +816,56 @@ struct FileMap {
             fm->reg.store(3);
             return;
         }
+        if (const char* e = getenv("EXON_B200_REGISTER_PIECE_MB")) fm->piece = (int64_t)std::max(1, atoi(e)) << 20;
+        else fm->piece = std::max<int64_t>(fm->size, 1);
         std::thread([fm, device]() {
             cudaSetDevice(device);
-            const cudaError_t e = cudaHostRegister(const_cast<uint8_t*>(fm->p), (size_t)fm->size, cudaHostRegisterPortable);
-            if (e == cudaSuccess) {
+            const int64_t pb = fm->piece;
+            bool ok = true;
+            // wait for 50 ms without an active reader (five minutes at most: then give up, a later scan may ask again)
+            int idle = 0;
+            for (int waited = 0; idle < 50 && waited < 300000; waited += 5) {
+                std::this_thread::sleep_for(std::chrono::milliseconds(5));
+                idle = io_active().load() > 0 ? 0 : idle + 5;
+            }
+            if (idle < 50) {
+                registered_bytes().fetch_sub(fm->size);
+                fm->reg.store(0);
+                return;
+            }
+            for (int64_t off = 0; ok && off < fm->size; off += pb) {
+                const int64_t len = std::min(pb, fm->size - off);
+                if (cudaHostRegister(const_cast<uint8_t*>(fm->p) + off, (size_t)len, cudaHostRegisterPortable) == cudaSuccess) {
+                    fm->pieces_done++;
+                } else {
+                    cudaGetLastError();
+                    ok = false;
+                }
+            }
+            if (ok) {
                 fm->reg.store(2);
             } else {
-                cudaGetLastError();
+                fm->unregister_pieces();
                 registered_bytes().fetch_sub(fm->size);
                 fm->reg.store(3);
             }
         }).detach();
+    }
+    // H2D copy out of a registered mapping: one DMA per piece the range touches
+    static cudaError_t host_to_device(void* dst, const uint8_t* src, int64_t len, const FileMap* fm, cudaStream_t s) {
+        if (!fm) return cudaMemcpyAsync(dst, src, (size_t)len, cudaMemcpyHostToDevice, s);
+        const int64_t pb = fm->piece;
+        int64_t off = src - fm->p;
+        uint8_t* d = reinterpret_cast<uint8_t*>(dst);
+        while (len > 0) {
+            const int64_t n = std::min(len, (off / pb + 1) * pb - off);
+            const cudaError_t e = cudaMemcpyAsync(d, fm->p + off, (size_t)n, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return e;
+            d += n;
+            off += n;
+            len -= n;
+        }
+        return cudaSuccess;
     }
 };
 struct MapCache {
@@ -1077,7 +1134,7 @@ struct Reader {
     bool z_copy_in(const Block& b, DBuf& dz, cudaStream_t s) {
         const int64_t tab_bytes = b.n_z * (int64_t)sizeof(exb_bgzf_block);
         if (!dz.need(z_table_at(b) + tab_bytes + 64)) return fail("out of device memory");
-        return cu(cudaMemcpyAsync(dz.p, b.data(), (size_t)b.zlen, cudaMemcpyHostToDevice, s), "H2D compressed") &&
+        return cu(FileMap::host_to_device(dz.p, b.data(), b.zlen, b.ext ? b.ext_map.get() : nullptr, s), "H2D compressed") &&
                cu(cudaMemcpyAsync(dz.as<uint8_t>() + z_table_at(b), b.h->as<uint8_t>() + b.ztab_off, (size_t)tab_bytes, cudaMemcpyHostToDevice, s), "H2D members");
     }
     // ... inflated into dst (stream `s`); the first-error word accumulates over the launches of a file
@@ -1291,6 +1348,7 @@ struct Reader {
         *got_out = total;
     }
     void io_main() {
+        Active active;
         cudaSetDevice(device);  // pinned allocations below belong to a context of this reader's device
         const bool sharded = range_lo > 0 || range_hi > 0;
         for (size_t fi = 0; fi < files.size() && !stopping; fi++) {
@@ -2066,7 +2124,12 @@ struct Reader {
     // the other input buffer) followed by the next raw block.  While chunk k is scanned, split and copied back, block
     // k+1 -- if the IO thread already has it -- crosses PCIe on the copy stream into a staging buffer, so H2D of k+1
     // overlaps the kernels of k and the D2H of k-1 (two copy engines, opposite directions).
+    struct Active {  // (page-cache registration waits while any reader thread runs: FileMap::start_register)
+        Active() { FileMap::io_active().fetch_add(1); }
+        ~Active() { FileMap::io_active().fetch_sub(1); }
+    };
     void dev_main() {
+        Active active;
         std::shared_ptr<HostBlock> host_cur;  // pinned block whose bytes may still be in flight to the device (chunk results that
                                               // borrow its bytes hold it too: see host_base)
         Block staged;                 // the prefetched block (its pinned buffer included); valid when have_staged
@@ -2134,7 +2197,7 @@ struct Reader {
                          cu(cudaMemcpyAsync(dst + carry_len, d_stage.p, (size_t)b.raw_len, cudaMemcpyDeviceToDevice, st), "D2D block") &&
                          cu(cudaEventRecord(ev_stage_free, st), "record");
                 } else {
-                    ok = cu(cudaMemcpyAsync(dst + carry_len, b.data(), (size_t)b.raw_len, cudaMemcpyHostToDevice, st), "H2D");
+                    ok = cu(FileMap::host_to_device(dst + carry_len, b.data(), b.raw_len, b.ext ? b.ext_map.get() : nullptr, st), "H2D");
                 }
             }
             // ---- the same chunk on the host: the block's bytes are already there; the carried tail (at most the record that
@@ -2176,7 +2239,7 @@ struct Reader {
                     } else if (!nb.end && nb.raw_len > 0 && d_stage.need(nb.raw_len + 64)) {
                         // the staging buffer is free once the previous staged block has been moved out of it
                         if (cu(cudaStreamWaitEvent(sc, ev_stage_free, 0), "wait") &&
-                            cu(cudaMemcpyAsync(d_stage.p, nb.data(), (size_t)nb.raw_len, cudaMemcpyHostToDevice, sc), "H2D prefetch") &&
+                            cu(FileMap::host_to_device(d_stage.p, nb.data(), nb.raw_len, nb.ext ? nb.ext_map.get() : nullptr, sc), "H2D prefetch") &&
                             cu(cudaEventRecord(ev_staged, sc), "record"))
                             staged_on_device = true;
                         else
@@ -2258,6 +2321,7 @@ struct Reader {
         return out->size() <= EXB_MAX_PREDICATES;
     }
     void dev_main_fused(std::vector<exb_predicate> preds) {
+        Active active;
         DBuf d_chunk[2], d_wsx[2], d_agg;
         struct InFlight {
             HBuf* h;                       // pinned block (nullptr: the bytes came straight from a registered file mapping,
@@ -2349,7 +2413,7 @@ struct Reader {
                 ok = ok && cu(cudaStreamWaitEvent(sc, ev_zf[z], 0), "wait") && z_copy_in(b, d_zin[z], sc) && cu(cudaEventRecord(ev_zc, sc), "record") &&
                      cu(cudaStreamWaitEvent(st, ev_zc, 0), "wait") && z_inflate(b, d_zin[z], data + tail, st) && cu(cudaEventRecord(ev_zf[z], st), "record");
             }
-            else if (ok && b.raw_len) ok = cu(cudaMemcpyAsync(data + tail, b.data(), (size_t)b.raw_len, cudaMemcpyHostToDevice, st), "H2D");
+            else if (ok && b.raw_len) ok = cu(FileMap::host_to_device(data + tail, b.data(), b.raw_len, b.ext ? b.ext_map.get() : nullptr, st), "H2D");
             cudaEvent_t ev = nullptr;
             if (!ev_pool.empty()) {
                 ev = ev_pool.back();

@@ -79,19 +79,25 @@ def main():
             if label == "REFGLUE" and ("len(quality" in q or "list_avg" in name and "AVG(" in name):
                 continue
             size = os.path.getsize(path)
+            # PRODUCT: three statements back to back (the file's page cache is copied through pinned blocks), then a pause -- an
+            # interactive user's think time, in which the reader registers the page cache -- and the statement twice more
+            stmts = [q % path, q % path, q % path] + ([".sleep 1500", q % path, q % path] if label == "PRODUCT" else [])
             try:
-                res = run(ext, [q % path, q % path, q % path], threads=args.threads or None)
+                res = run(ext, stmts, threads=args.threads or None)
             except Exception as e:
                 print("%-8s %-44s FAILED %s" % (label, name, str(e)[:200]), flush=True)
                 continue
-            r = min((x for x in res[1:] if x.get("ok")), key=lambda x: x["ms"], default=res[-1])
-            if not r.get("ok"):
-                print("%-8s %-44s ERROR %s" % (label, name, r.get("error", "")[:200]), flush=True)
-                continue
-            ms = r["ms"]
-            gbs = size / (ms * 1e-3) / 1e9
-            rows.append({"extension": label, "query": name, "file_bytes": size, "ms": ms, "GB/s": gbs, "result": r["rows"][0][0]})
-            print("%-8s %-60s %9.1f ms  %7.2f GB/s  (%.2f GB file)  -> %s" % (label, name, ms, gbs, size / 1e9, r["rows"][0][0]), flush=True)
+            for tag, part in ((label, res[1:3]), (label + " after a pause", res[3:])):
+                if not part:
+                    continue
+                r = min((x for x in part if x.get("ok")), key=lambda x: x["ms"], default=part[-1])
+                if not r.get("ok"):
+                    print("%-8s %-44s ERROR %s" % (tag, name, r.get("error", "")[:200]), flush=True)
+                    continue
+                ms = r["ms"]
+                gbs = size / (ms * 1e-3) / 1e9
+                rows.append({"extension": tag, "query": name, "file_bytes": size, "ms": ms, "GB/s": gbs, "result": r["rows"][0][0]})
+                print("%-22s %-60s %9.1f ms  %7.2f GB/s  (%.2f GB file)  -> %s" % (tag, name, ms, gbs, size / 1e9, r["rows"][0][0]), flush=True)
     # ---- bgzip'ed FASTQ: inflated on the device by PRODUCT and, through new_reader, for the reference's glue;
     # EXON_B200_BGZF=0 = the streaming zlib decoder (the reference's own arrangement) on a smaller file
     from tools import paths as P

@@ -7,8 +7,8 @@
 # usage: bash scripts/gpu_sanitize.sh [outdir]      (logs + a summary; copy the summary to profiles/)
 OUT=${1:-gpurun_out/sanitize}
 mkdir -p "$OUT"
-SEL='test_reference_fixtures or test_edge_cases or test_tile_edge_sweep or test_fused_scan_filter_rejects_malformed or test_combined_predicates_and_projection or test_map_fused_into_the_gather or test_gc_content_column or test_quality_score_string_to_list or test_reader_reference_queries or test_computed_columns_fasta or test_string_t_entries or test_fastq_format_matches_the_oracle or test_fasta_format_matches_the_oracle or test_format_is_the_inverse_of_the_scan or test_a_short_output_buffer or test_random_records'
-FILES="tests/test_gpu_fastq.py tests/test_gpu_fasta.py tests/test_gpu_scalar_reader.py tests/test_gpu_reader2.py tests/test_gpu_writer.py"
+SEL=${SEL:-'test_reference_fixtures or test_edge_cases or test_tile_edge_sweep or test_fused_scan_filter_rejects_malformed or test_combined_predicates_and_projection or test_map_fused_into_the_gather or test_gc_content_column or test_quality_score_string_to_list or test_reader_reference_queries or test_computed_columns_fasta or test_string_t_entries or test_fastq_format_matches_the_oracle or test_fasta_format_matches_the_oracle or test_format_is_the_inverse_of_the_scan or test_a_short_output_buffer or test_random_records or test_kernel_inflates_every_block_type or test_kernel_reports_the_first_corrupt_member or test_reader_on_bgzf_fastq_and_fasta or test_rows_of_a_corrupt_bgzf_file or test_second_scan_reads_the_registered_page_cache'}
+FILES=${FILES:-"tests/test_gpu_fastq.py tests/test_gpu_fasta.py tests/test_gpu_scalar_reader.py tests/test_gpu_reader2.py tests/test_gpu_writer.py tests/test_inflate.py"}
 for tool in memcheck racecheck; do
   timeout 1500 compute-sanitizer --tool $tool --target-processes all --log-file "$OUT/$tool.%p.log" \
       python -m pytest $FILES -m gpu -x -q -k "$SEL" -p no:cacheprovider > "$OUT/$tool.pytest.txt" 2>&1

@@ -326,6 +326,7 @@ def test_second_scan_reads_the_registered_page_cache(cuda_device, monkeypatch):
         pytest.skip("no tmpfs to put a memory-backed file on")
     L = _lib.lib()
     monkeypatch.setenv("EXON_B200_CHUNK_BYTES", str(3 << 20))  # several blocks, records straddling every edge
+    monkeypatch.setenv("EXON_B200_REGISTER_PIECE_MB", "4")     # the mapping is pinned in pieces; 3 MiB blocks cross their edges
     text = synth.gen_host(synth.gen_params("illumina", 60000, seed=77)).tobytes()
     assert len(text) > (16 << 20)
     path = "/dev/shm/exb_test_registered_%d.fastq" % os.getpid()

@@ -14,6 +14,7 @@
 #include <iostream>
 #include <chrono>
 #include <sstream>
+#include <thread>
 #include <string>
 
 #include "duckdb.hpp"
@@ -67,6 +68,14 @@ int main(int argc, char **argv) {
 		for (char c : sql)
 			if (!isspace((unsigned char)c)) blank = false;
 		if (blank) return;
+		{  // ".sleep <ms>": a pause between two statements (an interactive user's think time); prints nothing
+			size_t a = 0;
+			while (a < sql.size() && isspace((unsigned char)sql[a])) a++;
+			if (sql.compare(a, 6, ".sleep") == 0) {
+				std::this_thread::sleep_for(std::chrono::milliseconds(atoi(sql.c_str() + a + 6)));
+				return;
+			}
+		}
 		const auto t0 = std::chrono::steady_clock::now();
 		auto res = con.Query(sql);
 		if (res->HasError()) {
