@@ -172,7 +172,7 @@ typedef struct exb_computed {
 
 #define EXB_RD_COPY_IO 4    /* always stage the file through pinned blocks (page cache -> pinned memory -> device) and do not
                                have its page cache registered: the path a FIRST scan of a file takes anyway.  Without the
-                               flag, a plain file that was scanned once is registered with CUDA in the background (its
+                               flag, a plain file that was scanned once is registered with CUDA as soon as the process's readers pause (its
                                page-cache pages become pinned memory; memory-backed file systems such as tmpfs, the file
                                must be writable by the process although nothing is written) and every later scan copies
                                it to the device by DMA straight from there.  exb_file_cache_state tells which applies.  */
