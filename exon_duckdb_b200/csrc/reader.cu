@@ -783,7 +783,7 @@ struct FileMap {
     // (profiles/round2_register_sequence.txt): registered right after the first scan's IO stage, that scan took 397
     // instead of 77 ms; registered in 64 MiB pieces regardless of activity, the next three scans took 433 / 257 / 126
     // instead of 65 ms; in pieces between scans, single scans stalled for up to 2 s.  So the registration is ONE call, made
-    // once no reader of this process has been active for 50 ms -- the time between two statements of a session.  Under
+    // once no reader of this process has been active for 200 ms -- the time between two statements of a session.  Under
     // back-to-back scans it does not get its turn and the copy path stays; a scan that starts while it runs waits for
     // it once.  (EXON_B200_REGISTER_PIECE_MB registers in pieces instead -- tests; a DMA never spans two pieces.)
     static std::atomic<int>& io_active() {
@@ -822,13 +822,13 @@ struct FileMap {
             cudaSetDevice(device);
             const int64_t pb = fm->piece;
             bool ok = true;
-            // wait for 50 ms without an active reader (five minutes at most: then give up, a later scan may ask again)
+            // wait for 200 ms without an active reader (five minutes at most: then give up, a later scan may ask again)
             int idle = 0;
-            for (int waited = 0; idle < 50 && waited < 300000; waited += 5) {
+            for (int waited = 0; idle < 200 && waited < 300000; waited += 5) {
                 std::this_thread::sleep_for(std::chrono::milliseconds(5));
                 idle = io_active().load() > 0 ? 0 : idle + 5;
             }
-            if (idle < 50) {
+            if (idle < 200) {
                 registered_bytes().fetch_sub(fm->size);
                 fm->reg.store(0);
                 return;
