@@ -211,6 +211,8 @@ SIGNATURES = {
     "exb_host_free": (None, [_vp]),
     "exb_bgzf_probe_host": (_i32, [_vp, _i64]),
     "exb_bgzf_index_host": (_i32, [_vp, _i64, _i64, _i64, C.POINTER(BgzfBlock), _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "exb_bgzf_compress_bound": (_i64, [_i64]),
+    "exb_bgzf_compress_host": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, C.POINTER(_i64)]),
     "exb_bgzf_scratch_bytes": (_i64, []),
     "exb_bgzf_inflate": (_i32, [_vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "exb_bgzf_finish": (_i32, [_vp, C.POINTER(_i64), _vp]),

@@ -17,6 +17,11 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <thread>
+#include <vector>
 
 #include "../../include/exon_b200.h"
 #include "inflate_core.cuh"
@@ -160,6 +165,75 @@ int exb_bgzf_index_host(const uint8_t* bytes, int64_t n, int64_t pos, int64_t ma
     *n_blocks = k;
     *next_pos = pos;
     *out_bytes = out;
+    return EXB_OK;
+}
+
+// ---- host: BGZF output (the writers' gzip sink).  Members of 65280 text bytes like htslib's, deflated by zlib on
+// `threads` host threads; a member that does not fit 64 KiB (incompressible text) is stored.
+static const uint8_t BGZF_EOF[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+constexpr int64_t BGZF_TEXT = 65280, BGZF_SLOT = 65536;
+
+static int bgzf_member(const uint8_t* text, int n, int level, uint8_t* out) {  // returns the member's size, 0 on a zlib failure
+    for (int attempt = 0; attempt < 2; attempt++) {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, attempt ? 0 : level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return 0;
+        zs.next_in = const_cast<Bytef*>(text);
+        zs.avail_in = (uInt)n;
+        zs.next_out = out + 18;
+        zs.avail_out = (uInt)(BGZF_SLOT - 18 - 8);
+        const int rc = deflate(&zs, Z_FINISH);
+        const int clen = (int)zs.total_out;
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END) continue;  // did not fit: store it
+        const int bsize = 18 + clen + 8;
+        const uint8_t hdr[18] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, (uint8_t)((bsize - 1) & 0xFF), (uint8_t)((bsize - 1) >> 8)};
+        memcpy(out, hdr, 18);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), text, (uInt)n);
+        uint8_t* t = out + 18 + clen;
+        for (int k = 0; k < 4; k++) t[k] = (uint8_t)(crc >> (8 * k)), t[4 + k] = (uint8_t)((uint32_t)n >> (8 * k));
+        return bsize;
+    }
+    return 0;
+}
+
+int64_t exb_bgzf_compress_bound(int64_t n) { return ((n + BGZF_TEXT - 1) / BGZF_TEXT + 1) * BGZF_SLOT + 28; }
+
+int exb_bgzf_compress_host(const uint8_t* text, int64_t n, int level, int threads, int eof_marker, uint8_t* out, int64_t out_cap, int64_t* out_bytes) {
+    if (n < 0 || (n && !text) || !out || !out_bytes || out_cap < exb_bgzf_compress_bound(n)) return set_err(EXB_ERR_ARG, "exb_bgzf_compress_host: bad arguments");
+    const int64_t pieces = (n + BGZF_TEXT - 1) / BGZF_TEXT;
+    if (level < 0 || level > 9) level = 6;
+    int T = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+    if (T > pieces) T = (int)(pieces > 0 ? pieces : 1);
+    // every member is deflated into its own 64 KiB slot of `out` (the slots are then closed up in place)
+    std::vector<int> size((size_t)pieces, 0);
+    std::atomic<int64_t> next{0};
+    std::atomic<int> failed{0};
+    auto work = [&]() {
+        for (;;) {
+            const int64_t k = next.fetch_add(1);
+            if (k >= pieces) return;
+            const int64_t lo = k * BGZF_TEXT;
+            const int m = (int)(n - lo < BGZF_TEXT ? n - lo : BGZF_TEXT);
+            size[(size_t)k] = bgzf_member(text + lo, m, level, out + k * BGZF_SLOT);
+            if (size[(size_t)k] == 0) failed.store(1);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
+    if (failed.load()) return set_err(EXB_ERR_IO, "exb_bgzf_compress_host: deflate failed");
+    int64_t w = 0;
+    for (int64_t k = 0; k < pieces; k++) {
+        if (w != k * BGZF_SLOT) memmove(out + w, out + k * BGZF_SLOT, (size_t)size[(size_t)k]);
+        w += size[(size_t)k];
+    }
+    if (eof_marker) {
+        memcpy(out + w, BGZF_EOF, sizeof(BGZF_EOF));
+        w += sizeof(BGZF_EOF);
+    }
+    *out_bytes = w;
     return EXB_OK;
 }
 

@@ -19,7 +19,9 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "exon_b200_internal.h"
@@ -150,6 +152,52 @@ struct GzipSink : Sink {
         const int rc = gzclose(gz);
         gz = nullptr;
         return rc == Z_OK ? 0 : set_err(EXB_ERR_IO, "gzclose failed (%d)", rc);
+    }
+};
+// gzip output as BGZF: the image the device formatted is cut into members of 65280 text bytes and deflated on several host
+// threads (exb_bgzf_compress_host, inflate.cu) -- a valid multi-member gzip file for every other reader, and one this
+// library's own reader inflates on the device.  (EXON_B200_GZIP_WRITER=zlib keeps the single-stream sink above.)
+struct BgzfSink : Sink {
+    int fd;
+    std::vector<uint8_t> carry, out;  // text that does not fill a member yet; compressed members of one write
+    int threads;
+    explicit BgzfSink(int f) : fd(f) {
+        const unsigned hc = std::thread::hardware_concurrency();
+        threads = (int)(hc ? (hc > 16 ? 16 : hc) : 4);
+        if (const char* e = getenv("EXON_B200_WRITER_THREADS")) threads = atoi(e) > 0 ? atoi(e) : threads;
+    }
+    ~BgzfSink() override {
+        if (fd >= 0) ::close(fd);
+    }
+    int emit(const uint8_t* p, int64_t n, bool eof) {
+        out.resize((size_t)exb_bgzf_compress_bound(n));
+        int64_t w = 0;
+        if (exb_bgzf_compress_host(p, n, 6, threads, eof ? 1 : 0, out.data(), (int64_t)out.size(), &w) != 0) return EXB_ERR_IO;
+        return write_all(fd, out.data(), w);
+    }
+    int write(const uint8_t* p, int64_t n) override {
+        constexpr int64_t M = 65280;
+        if (!carry.empty()) {  // complete the open member first
+            const int64_t take = std::min<int64_t>(n, M - (int64_t)carry.size());
+            carry.insert(carry.end(), p, p + take);
+            p += take;
+            n -= take;
+            if ((int64_t)carry.size() < M) return 0;
+            if (int rc = emit(carry.data(), M, false)) return rc;
+            carry.clear();
+        }
+        const int64_t whole = n / M * M;
+        if (whole)
+            if (int rc = emit(p, whole, false)) return rc;
+        carry.assign(p + whole, p + n);
+        return 0;
+    }
+    int finish() override {
+        int rc = emit(carry.data(), (int64_t)carry.size(), true);
+        carry.clear();
+        if (::close(fd) != 0 && rc == 0) rc = set_err(EXB_ERR_IO, "close failed: %s", strerror(errno));
+        fd = -1;
+        return rc;
     }
 };
 // zstd: the public streaming compression API of the system's libzstd.so.1 (same library the reader binds for input)
@@ -412,7 +460,8 @@ int exb_writer_open(const char* path, const char* file_format, const char* compr
     w->fasta = fasta;
     w->n_cols = fasta ? 3 : 4;
     w->device = device;
-    w->sink = comp == 1 ? static_cast<Sink*>(new GzipSink(fd)) : comp == 2 ? static_cast<Sink*>(new ZstdSink(fd)) : static_cast<Sink*>(new PlainSink(fd));
+    const bool zlib_sink = getenv("EXON_B200_GZIP_WRITER") && !strcmp(getenv("EXON_B200_GZIP_WRITER"), "zlib");
+    w->sink = comp == 1 ? (zlib_sink ? static_cast<Sink*>(new GzipSink(fd)) : static_cast<Sink*>(new BgzfSink(fd))) : comp == 2 ? static_cast<Sink*>(new ZstdSink(fd)) : static_cast<Sink*>(new PlainSink(fd));
     if (const char* e = getenv("EXON_B200_WRITER_FLUSH_BYTES")) w->flush_bytes = atoll(e) > 0 ? atoll(e) : w->flush_bytes;
     cudaError_t ce = cudaSetDevice(device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking);

@@ -657,6 +657,13 @@ EXB_API int exb_bgzf_probe_host(const uint8_t *bytes, int64_t n);
 EXB_API int exb_bgzf_index_host(const uint8_t *bytes, int64_t n, int64_t pos, int64_t max_out_bytes,
                                 exb_bgzf_block *blocks, int64_t max_blocks, int64_t *n_blocks, int64_t *next_pos,
                                 int64_t *out_bytes);
+/* HOST: the inverse, for output -- `text` as BGZF members of 65280 text bytes (like htslib's bgzip), deflated by zlib at
+ * `level` (0-9, else 6) on `threads` host threads; eof_marker != 0 appends the 28-byte empty member that ends a BGZF
+ * file.  out_cap >= exb_bgzf_compress_bound(n).  What the writers' gzip sink produces (COPY ... TO, COMPRESSION 'gzip'):
+ * any gzip reader reads it, and this library's reader inflates it on the device. */
+EXB_API int64_t exb_bgzf_compress_bound(int64_t n);
+EXB_API int exb_bgzf_compress_host(const uint8_t *text, int64_t n, int level, int threads, int eof_marker, uint8_t *out,
+                                   int64_t out_cap, int64_t *out_bytes);
 EXB_API int64_t exb_bgzf_scratch_bytes(void);
 /* DEVICE: inflate the listed members of d_in (16 readable bytes of slack behind the last payload) into d_out.
  * Asynchronous on `stream`.  check_crc != 0 also verifies every member's CRC-32. */

@@ -259,3 +259,35 @@ def test_rows_of_a_corrupt_bgzf_file_are_an_error(cuda_device, tmp_path):
     with pytest.raises(_lib.ExonError) as e:
         _rows(p, "fasta", 3)
     assert "corrupt gzip stream" in str(e.value) and "block 2" in str(e.value)
+
+
+def test_bgzf_compress_host_round_trips():
+    """The writers' gzip sink (exb_bgzf_compress_host): BGZF members any gzip reader reads, whose member table the index walk
+    finds, and whose payloads the inflate core decodes.  Host code of the product library: no GPU needed."""
+    import gzip
+    from exon_duckdb_b200 import _lib
+    L = _lib.lib()
+    host = _host()
+    rng = np.random.default_rng(9)
+    fq, _ = util.random_fastq(43, 3000, min_len=50, max_len=150, tricky=False)
+    for data in (b"", b"x", fq, rng.integers(0, 256, 200000, dtype=np.uint8).tobytes(), bytes(65280 * 2)):
+        for threads in (1, 5):
+            cap = L.exb_bgzf_compress_bound(len(data))
+            out = C.create_string_buffer(cap)
+            n = C.c_int64()
+            _lib.check(L.exb_bgzf_compress_host(data, len(data), 6, threads, 1, out, cap, C.byref(n)))
+            img = out.raw[:n.value]
+            assert gzip.decompress(img) == data
+            assert L.exb_bgzf_probe_host(img, len(img)) == 1
+            tab = (_lib.BgzfBlock * (len(data) // 65280 + 3))()
+            nb, nxt, outb = C.c_int64(), C.c_int64(), C.c_int64()
+            _lib.check(L.exb_bgzf_index_host(img, len(img), 0, 1 << 40, tab, len(tab), C.byref(nb), C.byref(nxt), C.byref(outb)))
+            assert nxt.value == len(img) and outb.value == len(data) and nb.value == (len(data) + 65279) // 65280 + 1
+            got = b""
+            for k in range(nb.value):
+                b = tab[k]
+                piece = C.create_string_buffer(b.isize + 8)
+                assert host.ifl_host_inflate(img[b.in_off:b.in_off + b.clen], b.clen, piece, b.isize, k & 3) == 0
+                assert zlib.crc32(piece.raw[:b.isize]) == b.crc32
+                got += piece.raw[:b.isize]
+            assert got == data
