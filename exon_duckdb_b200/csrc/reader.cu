@@ -786,6 +786,21 @@ struct FileMap {
     // once no reader of this process has been active for 200 ms -- the time between two statements of a session.  Under
     // back-to-back scans it does not get its turn and the copy path stays; a scan that starts while it runs waits for
     // it once.  (EXON_B200_REGISTER_PIECE_MB registers in pieces instead -- tests; a DMA never spans two pieces.)
+    static constexpr int64_t REGISTER_MIN = 16 << 20;  // smaller files are not worth a registration (and are mapped read-only)
+    static bool register_enabled() {
+        static const bool on = !(getenv("EXON_B200_REGISTER") && atoi(getenv("EXON_B200_REGISTER")) == 0);
+        return on;
+    }
+    // pinned page cache cannot be reclaimed: at most EXON_B200_REGISTER_MAX_GB (32) and a quarter of the host's memory
+    static int64_t register_cap() {
+        int64_t cap = (getenv("EXON_B200_REGISTER_MAX_GB") ? atoll(getenv("EXON_B200_REGISTER_MAX_GB")) : 32) << 30;
+        if (FILE* f = fopen("/proc/meminfo", "r")) {
+            long long kb = 0;
+            if (fscanf(f, "MemTotal: %lld kB", &kb) == 1 && kb > 0) cap = std::min<int64_t>(cap, kb * 1024 / 4);
+            fclose(f);
+        }
+        return cap;
+    }
     static std::atomic<int>& io_active() {
         static std::atomic<int> n{0};
         return n;
@@ -806,9 +821,8 @@ struct FileMap {
     // called when a scan has read the whole file once: register in the background (the scan that triggered it is done
     // with the host side; nobody waits for this)
     static void start_register(const std::shared_ptr<FileMap>& fm, int device) {
-        static const bool enabled = !(getenv("EXON_B200_REGISTER") && atoi(getenv("EXON_B200_REGISTER")) == 0);
-        static const int64_t cap = (getenv("EXON_B200_REGISTER_MAX_GB") ? atoll(getenv("EXON_B200_REGISTER_MAX_GB")) : 32) << 30;
-        if (!enabled || !fm || !fm->writable || fm->size < (16 << 20)) return;
+        static const int64_t cap = register_cap();
+        if (!register_enabled() || !fm || !fm->writable || fm->size < REGISTER_MIN) return;
         int expect = 0;
         if (!fm->reg.compare_exchange_strong(expect, 1)) return;
         if (registered_bytes().fetch_add(fm->size) + fm->size > cap) {
@@ -900,7 +914,7 @@ struct MapCache {
         // writable-shared if the file may be opened for writing (the form CUDA can register; nothing is written), else read-only
         void* m = MAP_FAILED;
         bool writable = false;
-        if (path) {
+        if (path && FileMap::register_enabled() && (int64_t)sb.st_size >= FileMap::REGISTER_MIN) {
             const int wfd = ::open(path, O_RDWR);
             if (wfd >= 0) {
                 struct stat wb;
