@@ -9,7 +9,10 @@
 // the product path is the kernel in inflate.cu.
 //
 // Replaces, for BGZF input: the streaming GzipDecoder the reference wraps around the file (rust/src/arrow_reader.rs:60-91,
-// datafusion FileCompressionType::GZIP) -- SURVEY 8(f) rank 1 "BGZF ... GPU inflate later".
+// datafusion FileCompressionType::GZIP) -- SURVEY 8(f) rank 1 "BGZF ... GPU inflate later".  The reference's decoder is a
+// third-party dependency that is not in its tree (rust/Cargo.lock: async-compression 0.4.0 -> flate2 1.0.26 ->
+// miniz_oxide 0.7.1); the algorithm is the published one, RFC 1951 (DEFLATE) inside RFC 1952 (gzip) members, and parity
+// is anchored on zlib -- the implementation every gzip file is defined against -- and on the reference's own .gz fixtures.
 #pragma once
 #include <stdint.h>
 
