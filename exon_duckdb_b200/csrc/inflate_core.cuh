@@ -300,8 +300,19 @@ IFL_HD int inflate_block(const uint8_t* in, int clen, uint8_t* out, int isize, T
                 uint32_t e = lit[v & ((1u << LB) - 1u)];
                 if ((int32_t)e < 0) {  // literal
                     if (pos >= isize) return E_OUTPUT;
-                    out[pos++] = (uint8_t)(e >> 16);
-                    br.skip((int)(e & 31u));
+                    // ... and, more often than not, another one: the peeked word still holds its code (two table-resolved
+                    // code words are <= 2 x LB bits), so it costs one more look-up instead of one more trip round the loop
+                    const int nb1 = (int)(e & 31u);
+                    const uint32_t e2 = lit[(v >> nb1) & ((1u << LB) - 1u)];
+                    out[pos] = (uint8_t)(e >> 16);
+                    if ((int32_t)e2 < 0 && pos + 1 < isize) {
+                        out[pos + 1] = (uint8_t)(e2 >> 16);
+                        pos += 2;
+                        br.skip(nb1 + (int)(e2 & 31u));
+                        continue;
+                    }
+                    pos++;
+                    br.skip(nb1);
                     continue;
                 }
                 if ((e & 0xE0u) == 0u) {  // a code word longer than the table's index
