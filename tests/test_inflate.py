@@ -203,13 +203,15 @@ def _count(path, fmt, filters=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("chunk", [0, 150000])
+@pytest.mark.parametrize("chunk", [0, 150000, 4096])
 def test_reader_on_bgzf_fastq_and_fasta(cuda_device, tmp_path, monkeypatch, chunk):
     """bgzip'ed input through the reader: rows, COUNT(*) (fused chained scan: members end anywhere, ranges on multiples of
     16) and the mean-quality filter, identical to the oracle on the text and to the streaming zlib path."""
     from oracle import oracle as O
     if chunk:
-        monkeypatch.setenv("EXON_B200_CHUNK_BYTES", str(chunk))  # many blocks: tails, carried records
+        # many blocks: tails, carried records; at 4096 (16 KiB of text per block) every member is a block of its own, and the
+        # 5-byte and 1-byte members are blocks below the 16 bytes a chained range of the fused COUNT scan needs
+        monkeypatch.setenv("EXON_B200_CHUNK_BYTES", str(chunk))
     fq, _ = util.random_fastq(31, 9000, min_len=20, max_len=150, tricky=False)
     fa, _ = util.random_fasta(33, 300, min_len=10, max_len=4000, tricky=False)
     pq = tmp_path / "r.fastq.gz"
