@@ -2274,7 +2274,7 @@ struct Reader {
             }
             carry_off = consumed;
             carry_len = n - consumed;
-            bytes_done.fetch_add(consumed);
+            bytes_done.fetch_add(b.zlen ? b.zlen : consumed);  // (progress is in FILE bytes: a block of BGZF members counts as its compressed size)
             t_dev_work += now() - t0;
             if (trace >= 2) {
                 mark(5);
@@ -2456,7 +2456,7 @@ struct Reader {
             prev_data = data;
             prev_pos = pos;
             prev_n = n;
-            bytes_done.fetch_add(b.raw_len);
+            bytes_done.fetch_add(b.zlen ? b.zlen : b.raw_len);
             release_done(2);
             kb++;
             if (b.eof) {  // the file (or shard) ends here: its line count and error marks, once per file
@@ -2988,8 +2988,10 @@ int exb_reader_count(exb_reader* h, int64_t* n_rows) {
 
 int exb_reader_progress(const exb_reader* h, int64_t* bytes_done, int64_t* bytes_total) {
     if (!h) return set_err(EXB_ERR_ARG, "exb_reader_progress: null reader");
-    if (bytes_done) *bytes_done = h->r->bytes_done.load();
-    if (bytes_total) *bytes_total = h->r->bytes_total.load();
+    // (streamed gzip / zstd / bzip2 / xz input is counted in text bytes against the compressed size: capped at the total)
+    const int64_t total = h->r->bytes_total.load(), done = h->r->bytes_done.load();
+    if (bytes_done) *bytes_done = total > 0 && done > total ? total : done;
+    if (bytes_total) *bytes_total = total;
     return 0;
 }
 
