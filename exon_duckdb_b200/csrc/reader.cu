@@ -2381,8 +2381,8 @@ struct Reader {
         if (!d_agg.need(64) || !cu(cudaMemsetAsync(d_agg.p, 0, 64, st), "memset")) return finish(derr.empty() ? "out of device memory" : derr, 0);
         int kb = 0, kw = 0;              // chunk buffers alternate every block, scan workspaces every scan
         const void* prev_ws = nullptr;   // workspace of the previous range of this file's chain
-        const uint8_t* prev_data = nullptr;  // previous chunk buffer: prev_data[0] is file offset prev_pos, prev_n bytes
-        int64_t prev_pos = 0, prev_n = 0;
+        const uint8_t* prev_data = nullptr;  // previous chunk buffer: prev_data[0] is file offset prev_pos
+        int64_t prev_pos = 0;
         int64_t tail = 0;  // bytes at the end of the previous buffer that were not scanned yet: a block of inflated BGZF members
                            // ends anywhere, a chained range must end on a multiple of 16, so the last < 16 bytes wait for the next block
         while (!stopping) {
@@ -2455,7 +2455,6 @@ struct Reader {
             tail = pos + n - std::max(scan_end, pos);
             prev_data = data;
             prev_pos = pos;
-            prev_n = n;
             bytes_done.fetch_add(b.zlen ? b.zlen : b.raw_len);
             release_done(2);
             kb++;
@@ -2474,7 +2473,6 @@ struct Reader {
             }
             t_dev_work += now() - t0;
         }
-        (void)prev_n;
         if (stopping) return finish("", 0);
         if (!queue_small(16, d_agg.p, 8) || !wait_small()) return finish(derr, 0);
         finish("", small(16)[0]);
