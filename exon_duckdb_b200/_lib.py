@@ -48,6 +48,13 @@ class BgzfBlock(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
+class ScanStats(C.Structure):
+    _fields_ = [("path", C.c_char * 256), ("n_files", C.c_int32), ("format", C.c_int32), ("device", C.c_int32), ("compression", C.c_int32),
+                ("io_path", C.c_int32), ("failed", C.c_int32), ("file_bytes", C.c_int64), ("bytes_done", C.c_int64), ("rows", C.c_int64),
+                ("blocks", C.c_int64), ("seconds_total", C.c_double), ("seconds_io", C.c_double), ("seconds_device", C.c_double),
+                ("seconds_scan", C.c_double), ("seconds_select", C.c_double), ("seconds_materialise", C.c_double), ("seconds_first_block", C.c_double)]
+
+
 class ReaderResult(C.Structure):
     _fields_ = [("error", C.c_void_p)]
 
@@ -148,6 +155,8 @@ SIGNATURES = {
     "exb_reader_next": (_i32, [_vp, C.POINTER(Batch)]),
     "exb_batch_release": (None, [C.POINTER(Batch)]),
     "exb_reader_count": (_i32, [_vp, C.POINTER(_i64)]),
+    "exb_stats_snapshot": (_i32, [C.POINTER(ScanStats), _i32, C.POINTER(_i32)]),
+    "exb_stats_reset": (None, []),
     "exb_file_cache_state": (_i32, [C.c_char_p]),
     "exb_reader_io_path": (_i32, [_vp]),
     "exb_reader_close": (None, [_vp]),

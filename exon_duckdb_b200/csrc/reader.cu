@@ -1116,6 +1116,23 @@ struct NvtxRange {  // one range per pipeline stage (visible in nsys / ncu --nvt
 //   device thread block -> H2D -> scan / filter / field split / gather / string_t kernels -> D2H into pinned result buffers
 //   caller(s)     exb_reader_next / the Arrow stream: hand out <= batch_size-row views of a chunk's result
 // so reading block k+1, the device work of block k, the D2H of block k-1 and the host's consumption overlap.
+// ------------------------------------------------------------------ per-scan counters ("exon_gpu_stats()")
+// Every reader leaves one record when it is closed; the last 64 are kept (exb_stats_snapshot, the extension's
+// exon_gpu_stats() table function).
+struct StatsRing {
+    std::mutex mu;
+    std::deque<exb_scan_stats> q;
+    static StatsRing& get() {
+        static StatsRing* r = new StatsRing();
+        return *r;
+    }
+    void push(const exb_scan_stats& st) {
+        std::lock_guard<std::mutex> lk(mu);
+        q.push_front(st);
+        if (q.size() > 64) q.pop_back();
+    }
+};
+
 struct Reader {
     int format = 0;  // 1 FASTA, 2 FASTQ
     int ncols = 0;
@@ -1201,6 +1218,8 @@ struct Reader {
     uint32_t column_mask = 0xF;          // bit c: column c is materialised (projection push-down)
     std::atomic<bool> count_only{false}; // COUNT(*): rows are counted, nothing is gathered or copied back
     int64_t counted = 0;
+    int64_t rows_out = 0;                // rows that reached the caller (batches + counts): exon_gpu_stats
+    std::atomic<int> any_bgzf{0}, any_direct{0};
     std::string error;  // caller's thread: the failure reported to the host
     std::string derr;   // device thread: failure of the chunk being processed
     // pipeline
@@ -1231,6 +1250,29 @@ struct Reader {
         for (Block& b : inq.q) pool->put(b.h);
         cur.reset();
         outq.q.clear();
+        if (started) {
+            exb_scan_stats st;
+            memset(&st, 0, sizeof(st));
+            snprintf(st.path, sizeof(st.path), "%s", files.empty() ? "" : files[0].c_str());
+            st.n_files = (int32_t)files.size();
+            st.format = format;
+            st.device = device;
+            st.compression = any_bgzf.load() ? 5 : (file_comp.empty() ? 0 : file_comp[0]);
+            st.io_path = any_direct.load();
+            st.file_bytes = bytes_total.load();
+            st.bytes_done = bytes_done.load();
+            st.rows = rows_out;
+            st.blocks = n_blocks;
+            st.seconds_total = now() - t_open;
+            st.seconds_io = t_io_read;
+            st.seconds_device = t_dev_work;
+            st.seconds_scan = t_scan;
+            st.seconds_select = t_select;
+            st.seconds_materialise = t_mat;
+            st.seconds_first_block = t_first_block;
+            st.failed = error.empty() ? 0 : 1;
+            StatsRing::get().push(st);
+        }
         if (getenv("EXON_B200_TRACE"))
             fprintf(stderr, "exon_b200 reader: %lld blocks | io: alloc %.3f read %.3f push-wait %.3f | device: pop-wait %.3f work %.3f "
                             "(scan %.3f select %.3f materialise %.3f d2h-wait %.3f) push-wait %.3f | caller: pop-wait %.3f s | "
@@ -1458,6 +1500,8 @@ struct Reader {
             // DMA from the registered page cache (see FileMap) if an earlier scan of this file got it registered
             const bool direct = map && fmap && fmap->reg.load() == 2 && !(flags & EXB_RD_COPY_IO);
             io_direct.store(direct ? 1 : 0);
+            if (direct) any_direct.store(1);
+            if (bgzf) any_bgzf.store(1);
             while (err.empty() && !eof && !stopping) {
                 // block edges sit on multiples of 16 in file coordinates (the first block of a shard may be a little shorter):
                 // the chained COUNT scan of dev_main_fused needs that of every range but the first
@@ -2511,9 +2555,11 @@ struct Reader {
                 return false;
             }
             counted += it.counted;
+            rows_out += it.counted;
             if (it.res) {
                 cur = it.res;
                 rows = cur->rows;
+                rows_out += rows;
             }
         }
         return true;
@@ -2991,6 +3037,24 @@ int exb_reader_progress(const exb_reader* h, int64_t* bytes_done, int64_t* bytes
     if (bytes_done) *bytes_done = total > 0 && done > total ? total : done;
     if (bytes_total) *bytes_total = total;
     return 0;
+}
+
+int exb_stats_snapshot(exb_scan_stats* out, int max, int* n) {
+    if (!n || max < 0 || (max && !out)) return set_err(EXB_ERR_ARG, "exb_stats_snapshot: bad arguments");
+    StatsRing& r = StatsRing::get();
+    std::lock_guard<std::mutex> lk(r.mu);
+    int k = 0;
+    for (const exb_scan_stats& st : r.q) {
+        if (k >= max) break;
+        out[k++] = st;
+    }
+    *n = k;
+    return 0;
+}
+void exb_stats_reset(void) {
+    StatsRing& r = StatsRing::get();
+    std::lock_guard<std::mutex> lk(r.mu);
+    r.q.clear();
 }
 
 int exb_file_cache_state(const char* path) {

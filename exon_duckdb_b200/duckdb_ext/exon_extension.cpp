@@ -831,6 +831,73 @@ static void RegisterScan(ClientContext &context, const string &name, const strin
 	catalog.CreateTableFunction(context, &info);
 }
 
+// ---- exon_gpu_stats(): per-scan counters of the readers that ran in this process (SURVEY 5 "Metrics / logging": the reference has
+// only the lines_read atomic of module.cpp:40,276).  One row per closed reader, newest first: what was read, from where and how
+// (I/O path, compression), rows, and seconds per pipeline stage.
+struct StatsState : public GlobalTableFunctionState {
+	bool done = false;
+};
+static unique_ptr<FunctionData> StatsBind(ClientContext &, TableFunctionBindInput &, vector<LogicalType> &types, vector<string> &names) {
+	const vector<std::pair<string, LogicalType>> cols = {
+	    {"path", LogicalType::VARCHAR},          {"files", LogicalType::INTEGER},        {"format", LogicalType::VARCHAR},
+	    {"device", LogicalType::INTEGER},        {"compression", LogicalType::VARCHAR},  {"io_path", LogicalType::VARCHAR},
+	    {"failed", LogicalType::BOOLEAN},        {"file_bytes", LogicalType::BIGINT},    {"bytes_done", LogicalType::BIGINT},
+	    {"rows", LogicalType::BIGINT},           {"blocks", LogicalType::BIGINT},        {"seconds_total", LogicalType::DOUBLE},
+	    {"seconds_io", LogicalType::DOUBLE},     {"seconds_device", LogicalType::DOUBLE}, {"seconds_scan", LogicalType::DOUBLE},
+	    {"seconds_select", LogicalType::DOUBLE}, {"seconds_materialise", LogicalType::DOUBLE}, {"seconds_first_block", LogicalType::DOUBLE},
+	    {"gb_per_s", LogicalType::DOUBLE}};
+	for (auto &c : cols) {
+		names.push_back(c.first);
+		types.push_back(c.second);
+	}
+	return nullptr;
+}
+static unique_ptr<GlobalTableFunctionState> StatsInit(ClientContext &, TableFunctionInitInput &) {
+	return make_uniq<StatsState>();
+}
+static void StatsFunction(ClientContext &, TableFunctionInput &input, DataChunk &output) {
+	auto &state = input.global_state->Cast<StatsState>();
+	if (state.done) {
+		output.SetCardinality(0);
+		return;
+	}
+	state.done = true;
+	exb_scan_stats st[64];
+	int n = 0;
+	exb_stats_snapshot(st, 64, &n);
+	static const char *comp[] = {"none", "gzip (zlib stream)", "zstd", "bzip2", "xz", "bgzf (inflated on the device)"};
+	for (int i = 0; i < n; i++) {
+		const exb_scan_stats &r = st[i];
+		idx_t c = 0;
+		output.SetValue(c++, i, Value(string(r.path)));
+		output.SetValue(c++, i, Value::INTEGER(r.n_files));
+		output.SetValue(c++, i, Value(r.format == 1 ? "fasta" : "fastq"));
+		output.SetValue(c++, i, Value::INTEGER(r.device));
+		output.SetValue(c++, i, Value(comp[r.compression >= 0 && r.compression <= 5 ? r.compression : 0]));
+		output.SetValue(c++, i, Value(r.io_path ? "registered page cache" : "pinned blocks"));
+		output.SetValue(c++, i, Value::BOOLEAN(r.failed != 0));
+		output.SetValue(c++, i, Value::BIGINT(r.file_bytes));
+		output.SetValue(c++, i, Value::BIGINT(r.bytes_done));
+		output.SetValue(c++, i, Value::BIGINT(r.rows));
+		output.SetValue(c++, i, Value::BIGINT(r.blocks));
+		output.SetValue(c++, i, Value::DOUBLE(r.seconds_total));
+		output.SetValue(c++, i, Value::DOUBLE(r.seconds_io));
+		output.SetValue(c++, i, Value::DOUBLE(r.seconds_device));
+		output.SetValue(c++, i, Value::DOUBLE(r.seconds_scan));
+		output.SetValue(c++, i, Value::DOUBLE(r.seconds_select));
+		output.SetValue(c++, i, Value::DOUBLE(r.seconds_materialise));
+		output.SetValue(c++, i, Value::DOUBLE(r.seconds_first_block));
+		output.SetValue(c++, i, Value::DOUBLE(r.seconds_total > 0 ? (double)r.bytes_done / r.seconds_total / 1e9 : 0.0));
+	}
+	output.SetCardinality(n);
+}
+static void RegisterStats(ClientContext &context) {
+	TableFunction fn("exon_gpu_stats", {}, StatsFunction, StatsBind, StatsInit);
+	auto &catalog = Catalog::GetSystemCatalog(context);
+	CreateTableFunctionInfo info(fn);
+	catalog.CreateTableFunction(context, &info);
+}
+
 static unique_ptr<TableRef> ExonReplacementScan(ClientContext &context, const string &table_name, ReplacementScanData *data) {
 	auto lower_name = StringUtil::Lower(table_name);
 	auto res = replacement_scan(lower_name.c_str());
@@ -1213,6 +1280,7 @@ static void LoadInternal(DatabaseInstance &instance) {
 	RegisterScan(context, "read_fastq", "fastq");
 	RegisterCopy<false>(context);
 	RegisterCopy<true>(context);
+	RegisterStats(context);
 	config.replacement_scans.emplace_back(ExonReplacementScan);
 	OptimizerExtension fuse;
 	fuse.optimize_function = ExonOptimize;

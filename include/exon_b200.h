@@ -250,6 +250,22 @@ EXB_API int exb_file_cache_state(const char *path);
 /* 1 if the file this reader is reading now comes by DMA from its registered page cache, 0 if it is staged through
  * pinned blocks. */
 EXB_API int exb_reader_io_path(const exb_reader *reader);
+/* Per-scan counters (SURVEY 5 "exon_gpu_stats()"): every reader that ran leaves one record when it is closed; the most
+ * recent 64 are kept, newest first.  The extension serves them as the table function exon_gpu_stats(). */
+typedef struct exb_scan_stats {
+    char path[256];        /* first input file                                                            */
+    int32_t n_files;
+    int32_t format;        /* 1 = FASTA, 2 = FASTQ                                                        */
+    int32_t device;
+    int32_t compression;   /* 0 none, 1 gzip (zlib stream), 2 zstd, 3 bzip2, 4 xz, 5 BGZF inflated on the device */
+    int32_t io_path;       /* 1 = DMA from the registered page cache, 0 = copied through pinned blocks    */
+    int32_t failed;
+    int64_t file_bytes, bytes_done, rows, blocks;
+    double seconds_total, seconds_io, seconds_device, seconds_scan, seconds_select, seconds_materialise,
+        seconds_first_block;
+} exb_scan_stats;
+EXB_API int exb_stats_snapshot(exb_scan_stats *out, int max, int *n);
+EXB_API void exb_stats_reset(void);
 /* CUDA devices visible to the process (0 when there is none). */
 EXB_API int exb_device_count(void);
 

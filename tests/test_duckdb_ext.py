@@ -70,6 +70,15 @@ def test_load_registers_the_path_functions():
                           ["read_fastq", "table", None], ["reverse_complement", "scalar", "VARCHAR"]]
 
 
+def test_gpu_stats_table_function_is_registered():
+    """SURVEY 5 'Metrics / logging': exon_gpu_stats() -- per-scan counters; empty before any scan ran."""
+    r = run_sql(PRODUCT, ["DESCRIBE SELECT * FROM exon_gpu_stats()", "SELECT count(*) FROM exon_gpu_stats()"])
+    cols = [(x[0], x[1]) for x in rows(r[0])]
+    assert cols[:3] == [("path", "VARCHAR"), ("files", "INTEGER"), ("format", "VARCHAR")]
+    assert ("rows", "BIGINT") in cols and ("io_path", "VARCHAR") in cols and ("seconds_scan", "DOUBLE") in cols and ("gb_per_s", "DOUBLE") in cols
+    assert rows(r[1]) == [["0"]]
+
+
 @pytest.mark.parametrize("ext", [PRODUCT, REFGLUE], ids=["product", "refglue"])
 def test_schema_matches_the_reference(ext):
     # FileTypeBind: FASTQ (name, description, sequence, quality_scores), FASTA (id, description, sequence), all VARCHAR
@@ -632,3 +641,22 @@ def test_bgzf_input_through_sql(cuda_device, tmp_path, ext):
     assert [tuple(r) for r in rows(res[1])] == want
     assert rows(res[2]) == [[str(ref.n)]]
     assert rows(res[3]) == [[str(mq)]]
+
+
+@pytest.mark.gpu
+def test_gpu_stats_rows_describe_the_scans(cuda_device, tmp_path):
+    """exon_gpu_stats(): one row per reader that ran, newest first -- file, format, compression, rows, bytes."""
+    bgzf_bytes = util.bgzf_bytes
+    text, _ = util.random_fastq(19, 3000, min_len=10, max_len=150, tricky=False)
+    fa, _ = util.random_fasta(21, 50, min_len=10, max_len=2000, tricky=False)
+    pq = _write(tmp_path, "s.fastq.gz", bgzf_bytes(text))
+    pa = _write(tmp_path, "s.fasta", fa)
+    res = run_sql(PRODUCT, [
+        "SELECT count(*) FROM read_fastq('%s')" % pq,
+        "SELECT count(*), sum(length(sequence)) FROM read_fasta('%s')" % pa,
+        "SELECT path, format, compression, io_path, failed, rows, file_bytes, bytes_done, blocks > 0, seconds_total > 0 FROM exon_gpu_stats()",
+    ])
+    got = rows(res[2])
+    assert got[0] == [pa, "fasta", "none", "pinned blocks", "false", "50", str(len(fa)), str(len(fa)), "true", "true"]
+    assert got[1][:6] == [pq, "fastq", "bgzf (inflated on the device)", "pinned blocks", "false", "3000"]
+    assert got[1][6] == got[1][7] == str(os.path.getsize(pq))
