@@ -293,3 +293,51 @@ def test_bgzf_compress_host_round_trips():
                 assert zlib.crc32(piece.raw[:b.isize]) == b.crc32
                 got += piece.raw[:b.isize]
             assert got == data
+
+
+def test_bgzf_member_walk_edge_cases():
+    """exb_bgzf_probe_host / exb_bgzf_index_host (host code): other extra subfields next to BC, members that are not BGZF
+    (plain gzip, FNAME set), truncated files, size limits, max_out_bytes / max_blocks cuts."""
+    from exon_duckdb_b200 import _lib
+    L = _lib.lib()
+
+    def member(piece, extra_before=b"", extra_after=b"", flags=4):
+        z = raw_deflate(piece)
+        xlen = len(extra_before) + 6 + len(extra_after)
+        bsize = 12 + xlen + len(z) + 8
+        hdr = b"\x1f\x8b\x08" + bytes([flags]) + b"\0\0\0\0\x00\xff" + xlen.to_bytes(2, "little") + extra_before + b"BC\x02\x00" + (bsize - 1).to_bytes(2, "little") + extra_after
+        return hdr + z + zlib.crc32(piece).to_bytes(4, "little") + len(piece).to_bytes(4, "little")
+
+    def index(img, pos=0, max_out=1 << 40, cap=64):
+        tab = (_lib.BgzfBlock * cap)()
+        nb, nxt, outb = C.c_int64(), C.c_int64(), C.c_int64()
+        rc = L.exb_bgzf_index_host(img, len(img), pos, max_out, tab, cap, C.byref(nb), C.byref(nxt), C.byref(outb))
+        return rc, [(tab[k].in_off, tab[k].out_off, tab[k].clen, tab[k].isize) for k in range(nb.value)], nxt.value, outb.value
+
+    a, b, c = b"A" * 1000, b"CG" * 700, b"T" * 10
+    other = b"XY\x03\x00abc"  # a foreign subfield: SI1 SI2 SLEN data
+    img = member(a, extra_before=other) + member(b, extra_after=other) + member(c)
+    assert L.exb_bgzf_probe_host(img, len(img)) == 1
+    rc, tab, nxt, outb = index(img)
+    assert rc == 0 and nxt == len(img) and outb == 2410 and [t[3] for t in tab] == [1000, 1400, 10] and [t[1] for t in tab] == [0, 1000, 2400]
+    host = _host()
+    for (in_off, _, clen, isize), want in zip(tab, (a, b, c)):
+        out = C.create_string_buffer(isize + 8)
+        assert host.ifl_host_inflate(img[in_off:in_off + clen], clen, out, isize, 0) == 0 and out.raw[:isize] == want
+    # cuts: by text size (at least one member is always taken) and by table capacity; in_off is relative to `pos`
+    rc, tab, nxt, outb = index(img, max_out=1500)
+    assert rc == 0 and len(tab) == 1 and outb == 1000
+    rc, tab2, nxt2, outb2 = index(img, pos=nxt, max_out=10)
+    assert rc == 0 and len(tab2) == 1 and outb2 == 1400 and tab2[0][0] == 12 + 6 + len(other) and tab2[0][1] == 0
+    rc, tab3, _, _ = index(img, cap=2)
+    assert rc == 0 and len(tab3) == 2
+    # not BGZF: plain gzip, a member with FNAME, no BC subfield; truncated; a header that lies about the text size
+    import gzip
+    assert L.exb_bgzf_probe_host(gzip.compress(a), 40) == 0
+    assert L.exb_bgzf_probe_host(member(a, flags=4 | 8), 40) == 0
+    assert L.exb_bgzf_probe_host(img[:10], 10) == 0
+    assert index(img + gzip.compress(a))[0] != 0 and b"not a BGZF block header" in L.exb_last_error()
+    assert index(img[:-5])[0] != 0 and b"truncated BGZF block" in L.exb_last_error()
+    big = bytearray(member(a))
+    big[-4:] = (70000).to_bytes(4, "little")
+    assert index(bytes(big))[0] != 0 and b"claims 70000 bytes" in L.exb_last_error()
