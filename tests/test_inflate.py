@@ -341,3 +341,26 @@ def test_bgzf_member_walk_edge_cases():
     big = bytearray(member(a))
     big[-4:] = (70000).to_bytes(4, "little")
     assert index(bytes(big))[0] != 0 and b"claims 70000 bytes" in L.exb_last_error()
+
+
+def test_bgzip_tool_rewrites_gzip_as_bgzf(tmp_path):
+    """tools/bgzip.py: a single-stream .gz (which keeps the streaming host decoder) rewritten as BGZF (which the reader inflates
+    on the device); host-side only."""
+    import gzip
+    from exon_duckdb_b200 import _lib
+    from tools import bgzip
+    fq, _ = util.random_fastq(47, 4000, min_len=50, max_len=150, tricky=False)
+    src = tmp_path / "plain.fastq.gz"
+    src.write_bytes(gzip.compress(fq))
+    dst = tmp_path / "blocked.fastq.gz"
+    assert _lib.lib().exb_bgzf_probe_host(src.read_bytes(), 64) == 0
+    t, f = bgzip.recompress(str(src), str(dst), threads=3)
+    img = dst.read_bytes()
+    assert t == len(fq) and f == len(img)
+    assert _lib.lib().exb_bgzf_probe_host(img, len(img)) == 1
+    assert gzip.decompress(img) == fq
+    assert img.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    raw = tmp_path / "raw.fasta"
+    raw.write_bytes(b">a\nACGT\n")
+    bgzip.recompress(str(raw), str(dst))
+    assert gzip.decompress(dst.read_bytes()) == b">a\nACGT\n"
