@@ -138,3 +138,60 @@ int main(void){ unsigned long long s=88172645463325252ULL; long bad=0,dr=0;
     bad, dr = subprocess.check_output([str(exe)]).split()
     assert int(bad) == 0
     assert int(dr) > 0  # the sample does contain double-rounding cases, so the emulation is exercised
+
+
+# ---------------------------------------------------------------- host logic of the native reader (no GPU: nothing is scanned)
+def _open2(path, fmt, filters=None, **kw):
+    import ctypes as C
+    from exon_duckdb_b200 import _lib
+    h = C.c_void_p()
+    o = _lib.reader_options(**kw)
+    rc = _lib.lib().exb_reader_open2(str(path).encode(), fmt.encode(), None, 2048, filters, C.byref(o), C.byref(h))
+    return rc, h, _lib.lib().exb_last_error()
+
+
+def test_filter_text_is_parsed_at_open(golden_dir):
+    """a4: the predicate text FilterToString emits is parsed when the reader is opened -- a malformed or unsupported predicate is
+    the reference's 'could not execute sql' error, before any device work."""
+    from exon_duckdb_b200 import _lib
+    fq = os.path.join(golden_dir, "test.fastq")
+    for good in (b"name = 'SEQ_ID'", b"(name = 'a' AND sequence != 'ACGT') OR description IS NULL", b"mean_quality(quality_scores)>30",
+                 b"gc_content(sequence) <= 0.5 AND length(sequence) > 10"):
+        rc, h, msg = _open2(fq, "fastq", good)
+        assert rc == 0, (good, msg)
+        _lib.lib().exb_reader_close(h)
+    for bad, what in ((b"name = 'x' AND", b"expected a column or function name"), (b"nosuch(quality_scores) > 3", b"unsupported function"),
+                      (b"(sequence = 'A'", b"expected ')'"), (b"quality_scores = 'II' extra", b"cannot parse filter")):
+        rc, h, msg = _open2(fq, "fastq", bad)
+        assert rc != 0 and b"could not execute sql" in msg and what in msg, (bad, msg)
+    rc, h, msg = _open2(fq, "fastq", None, range_lo=10, range_hi=5)
+    assert rc != 0 and b"bad byte range" in msg
+    rc, h, msg = _open2(os.path.join(golden_dir, "test.fastq.gz"), "fastq", None, range_lo=0, range_hi=100)
+    assert rc != 0 and b"one uncompressed file" in msg
+
+
+def test_reader_plan_and_cache_state(golden_dir, tmp_path):
+    """What a host needs to plan one reader per GPU (exb_reader_plan), and the cache-state / stats calls on a process that has not
+    scanned anything."""
+    import ctypes as C
+    from exon_duckdb_b200 import _lib
+    L = _lib.lib()
+
+    def plan(uri, fmt, comp=None):
+        total, n, sh = C.c_int64(), C.c_int32(), C.c_int32()
+        rc = L.exb_reader_plan(str(uri).encode(), fmt.encode(), comp, C.byref(total), C.byref(n), C.byref(sh))
+        return rc, total.value, n.value, sh.value
+
+    fq = os.path.join(golden_dir, "test.fastq")
+    assert plan(fq, "fastq") == (0, os.path.getsize(fq), 1, 1)
+    rc, total, n, sh = plan(os.path.join(golden_dir, "test.fastq.gz"), "fastq")
+    assert rc == 0 and n == 1 and sh == 0                     # compressed input is not cut into byte ranges
+    rc, total, n, sh = plan(os.path.join(golden_dir, "fastq"), "fastq")
+    assert rc == 0 and n == 2 and sh == 0                     # a directory shards by file
+    assert plan(tmp_path / "missing.fastq", "fastq")[0] != 0
+    assert L.exb_file_cache_state(fq.encode()) == 0           # never scanned
+    assert L.exb_file_cache_state(str(tmp_path / "missing.fastq").encode()) < 0
+    L.exb_stats_reset()
+    st = (_lib.ScanStats * 4)()
+    n = C.c_int32(-1)
+    assert L.exb_stats_snapshot(st, 4, C.byref(n)) == 0 and n.value == 0
