@@ -195,3 +195,18 @@ def test_reader_plan_and_cache_state(golden_dir, tmp_path):
     st = (_lib.ScanStats * 4)()
     n = C.c_int32(-1)
     assert L.exb_stats_snapshot(st, 4, C.byref(n)) == 0 and n.value == 0
+
+
+def test_ctypes_mirrors_of_the_round2_structs_match_the_header(tmp_path):
+    """exb_scan_stats / exb_bgzf_block / exb_reader_options as a C compiler lays them out vs the ctypes mirrors in _lib.py."""
+    import ctypes as C
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\n'
+                   'int main(void) { printf("%%zu %%zu %%zu %%zu %%zu\\n", sizeof(exb_scan_stats), offsetof(exb_scan_stats, file_bytes), '
+                   'offsetof(exb_scan_stats, seconds_total), sizeof(exb_bgzf_block), sizeof(exb_reader_options)); return 0; }\n'
+                   % os.path.join(ROOT, "include", "exon_b200.h"))
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(_lib.ScanStats), _lib.ScanStats.file_bytes.offset, _lib.ScanStats.seconds_total.offset, C.sizeof(_lib.BgzfBlock),
+                   C.sizeof(_lib.ReaderOptions)]
